@@ -1,0 +1,188 @@
+/*
+ * venusaur_b200.h -- C ABI of libvenusaur_b200.so, the B200-native replacement for Venusaur's one
+ * data-parallel hot path (the per-pixel Monte-Carlo loop of Core/RayTracer.cu and the three Renderer
+ * methods that feed it).
+ *
+ * The reference has no FFI layer: Core/Core.cpp calls Renderer::{Init,Draw,Cleanup} (Renderer.h:25,35,80)
+ * and Renderer talks to OptiX.  This header is the boundary a maintainer binds instead of OptiX; the C++17
+ * drop-in classes in include/venusaur/ (Renderer, Scene, Camera, CUDAOutputBuffer, Exception) are a thin
+ * header-only shim over it.  Every entry point names the reference interface it replaces.
+ *
+ * Conventions: plain pointers and sizes only; no function throws; each returns VN_OK (0) or a negative
+ * vn_status, and vn_last_error() returns the message (the C++ shim turns it into `throw Exception(msg)`,
+ * mirroring CUDA_CHECK / OPTIX_CHECK in Exception.h:16-102).  A handle is bound to one CUDA device and is
+ * not thread-safe (the reference is single-threaded, Core.cpp:358-430).  There is no CPU fallback: without
+ * a CUDA device vn_create fails.
+ */
+#ifndef VENUSAUR_B200_H
+#define VENUSAUR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define VN_API __declspec(dllexport)
+#else
+#define VN_API __attribute__((visibility("default")))
+#endif
+
+typedef struct vn_context* vn_handle;
+
+typedef enum vn_status {
+    VN_OK = 0,
+    VN_ERR_INVALID = -1,     /* bad argument / call order */
+    VN_ERR_CUDA = -2,        /* a CUDA call or kernel failed; message has the call and the CUDA error string */
+    VN_ERR_NO_DEVICE = -3,   /* no usable CUDA device (there is no CPU path) */
+    VN_ERR_OOM = -4
+} vn_status;
+
+/* Material::Type, material.h:9-14 */
+enum { VN_LAMBERTIAN = 0, VN_METAL = 1, VN_DIELECTRIC = 2 };
+
+/* One sphere = SphereHitGroupData (RayTracer.h:40-45; center, radius, MaterialData{albedo,fuzz}|{ir}) plus the
+ * material type that the reference encodes in the SBT program header (Renderer.h:487-503).  36 bytes. */
+typedef struct vn_sphere {
+    float cx, cy, cz, r;
+    float ax, ay, az;       /* albedo: Lambertian, metal */
+    float fuzz_or_ir;       /* metal: fuzz; dielectric: index of refraction */
+    uint32_t type;          /* VN_LAMBERTIAN / VN_METAL / VN_DIELECTRIC */
+} vn_sphere;
+
+/* vn_params.flags */
+enum {
+    VN_EXACT          = 1u << 0, /* IEEE build of the kernels (no FMA contraction, IEEE div/sqrt, FP64 where the
+                                    reference uses it): bit-identical to the host oracle.  Default is the FAST build. */
+    VN_IMAGE_HOST     = 1u << 1, /* params.image is HOST memory: the uchar4 frame is copied D2H before returning
+                                    (what CUDAOutputBuffer::getHostPointer does, CUDAOutputBuffer.h:348-372) */
+    VN_ACCUM_SUM      = 1u << 2, /* accum += frame mean (multi-GPU partial sums) instead of the running mean */
+    VN_NO_TONEMAP     = 1u << 3, /* do not write params.image */
+    VN_WAVEFRONT      = 1u << 4, /* use the queue-based wavefront kernels instead of the persistent path kernel */
+    VN_COUNTERS       = 1u << 5, /* instrumented launch: also count BVH node visits and sphere tests */
+    VN_ASYNC          = 1u << 6  /* do not synchronise the stream before returning (stats are then stale) */
+};
+
+/* Launch parameters = Params (RayTracer.h:3-17) minus the OptiX handle, plus what the reference hard-codes:
+ * max_depth (RayTracer.cu:172, constant 4 there) and the blend weight it derives from subframe_index
+ * (RayTracer.cu:208-213). */
+typedef struct vn_params {
+    void* image;                  /* uchar4[width*height], device pointer (or host with VN_IMAGE_HOST), may be NULL */
+    uint32_t width, height;
+    uint32_t samples_per_pixel;   /* Renderer.h:53 uses 16 */
+    uint32_t subframe_index;      /* RNG stream id: seed = tea<4>(pixel, subframe_index), RayTracer.cu:169 */
+    uint32_t max_depth;           /* max ray segments per path; reference = 4 */
+    uint32_t accum_count;         /* frames already in accum: new = prev + (mean-prev)/(accum_count+1); 0 overwrites.
+                                     The reference passes subframe_index here (RayTracer.cu:210). */
+    float origin[3], u[3], v[3], w[3];
+    float lens_radius;
+    uint32_t row_begin, row_end;  /* render rows [row_begin,row_end) only; 0,0 = whole frame (tile sharding) */
+    uint32_t flags;
+} vn_params;
+
+typedef struct vn_stats {
+    uint64_t segments;        /* ray segments (closest-hit queries) traced by the last vn_render */
+    uint64_t paths;
+    uint64_t node_visits;     /* VN_COUNTERS only */
+    uint64_t sphere_tests;    /* VN_COUNTERS only */
+    uint64_t segments_total;  /* since vn_create / vn_reset_stats */
+    uint32_t kernel_launches; /* kernels launched by the last vn_render */
+    uint32_t kernel_launches_total;
+    float ms_render;          /* CUDA-event time of the last vn_render's kernels (0 with VN_ASYNC) */
+    float ms_trace;           /* the dominant trace kernel(s) alone */
+    float ms_build;           /* last vn_build_bvh */
+    float ms_upload;          /* last vn_set_spheres H2D */
+} vn_stats;
+
+typedef struct vn_bvh_info {
+    uint64_t num_spheres;
+    uint64_t num_nodes;       /* packed 32-byte nodes */
+    uint32_t max_leaf_size;
+    uint32_t scene_in_smem;   /* 1 when nodes+spheres are staged in shared memory by the trace kernels */
+    float bounds_lo[3], bounds_hi[3];
+} vn_bvh_info;
+
+/* 32-byte BVH node as laid out in HBM (read by the kernels with two 128-bit loads).  Children of an internal
+ * node are adjacent: child pair at [link, link+1]. */
+typedef struct vn_node32 {
+    float lo[3];
+    uint32_t link;            /* internal: index of the left child (right = link+1); leaf: 0x80000000 | first<<3 | (count-1) */
+    float hi[3];
+    uint32_t aux;             /* number of spheres under this node */
+} vn_node32;
+
+/* ---- lifetime: Renderer::CreateContext / Cleanup (Renderer.h:144-158, 80-97) ---- */
+VN_API int vn_create(int device, vn_handle* out);
+VN_API void vn_destroy(vn_handle h);
+VN_API const char* vn_last_error(vn_handle h);            /* h may be NULL: error of the last failed vn_create */
+VN_API int vn_device_count(void);
+VN_API const char* vn_version(void);
+
+/* ---- scene: Renderer::CreateSBT (Renderer.h:452-520) + BuildAccelerationStructures (Renderer.h:160-255) ---- */
+VN_API int vn_set_spheres(vn_handle h, const vn_sphere* host_spheres, uint64_t n);
+VN_API int vn_set_option(vn_handle h, const char* name, double value); /* "leaf_size", "aabb_pad", "threads", "blocks_per_sm" */
+VN_API int vn_build_bvh(vn_handle h);
+VN_API int vn_get_bvh_info(vn_handle h, vn_bvh_info* out);
+VN_API int vn_read_bvh(vn_handle h, vn_node32* host_nodes, uint64_t cap_nodes, uint32_t* host_prim_order, uint64_t cap_prims);
+
+/* ---- frame: Renderer::Draw (Renderer.h:35-78) ---- */
+VN_API int vn_resize(vn_handle h, uint32_t width, uint32_t height);   /* (re)allocates + zeroes accum (fixes Q3/Q4) */
+VN_API int vn_reset_accum(vn_handle h);                               /* camera.Changed() path, Renderer.h:37-45 */
+VN_API int vn_render(vn_handle h, const vn_params* p);                /* optixLaunch, Renderer.h:75 */
+VN_API int vn_tonemap(vn_handle h, float scale, void* image, uint32_t flags); /* image = make_color(accum*scale), RayTracer.cu:16-47,216 */
+VN_API int vn_synchronize(vn_handle h);                               /* CUDA_SYNC_CHECK, Renderer.h:77 */
+VN_API int vn_get_stats(vn_handle h, vn_stats* out);
+VN_API int vn_reset_stats(vn_handle h);
+
+/* ---- accumulation buffer: Params::accum (RayTracer.h:6), float4 per pixel ---- */
+VN_API int vn_read_accum(vn_handle h, float* host_rgba);              /* D2H, width*height*4 floats */
+VN_API int vn_write_accum(vn_handle h, const float* host_rgba);       /* H2D (resume a progressive render) */
+VN_API int vn_accum_device_ptr(vn_handle h, void** dev_ptr);          /* for the cross-GPU reduce (NCCL / peer kernel) */
+VN_API int vn_set_accum_external(vn_handle h, void* dev_ptr);         /* render into caller-owned float4[width*height]; NULL restores */
+/* fused reduce + tonemap over peer-mapped accumulation buffers: image rows [row_begin,row_end) =
+ * make_color(scale * sum_i peers[i]) ; also writes the sum into this handle's accum. */
+VN_API int vn_reduce_tonemap_peers(vn_handle h, const void* const* peer_accum, uint32_t n_peers, float scale,
+                                   uint32_t row_begin, uint32_t row_end, void* image, uint32_t flags);
+
+/* ---- plain device/host buffer helpers, so that the header-only C++ shim (CUDAOutputBuffer.h:173-281,348-372) needs no
+ * CUDA toolkit of its own ---- */
+VN_API int vn_buffer_alloc(int device, uint64_t bytes, int zero_copy_host, void** dev_ptr, void** host_ptr);
+VN_API int vn_buffer_free(int device, void* dev_ptr, void* host_ptr, int zero_copy_host);
+VN_API int vn_buffer_copy_to_host(int device, void* host_dst, const void* dev_src, uint64_t bytes);
+VN_API int vn_stream_synchronize(int device, void* cuda_stream);
+VN_API void* vn_stream(vn_handle h);                                  /* the handle's cudaStream_t */
+/* CUDA IPC, to map another process's accumulation buffer for vn_reduce_tonemap_peers (one process per GPU) */
+VN_API int vn_ipc_export(vn_handle h, void* dev_ptr, unsigned char handle_out[64]);
+VN_API int vn_ipc_open(vn_handle h, const unsigned char handle_in[64], void** dev_ptr);
+VN_API int vn_ipc_close(vn_handle h, void* dev_ptr);
+
+/* ---- host-side scene/camera helpers (Scene.h:13-80, Camera.cpp:24-37); no GPU needed ---- */
+VN_API uint32_t vn_scene_rtiow_final(vn_sphere* out, uint32_t cap);
+VN_API void vn_scene_random(vn_sphere* out, uint64_t n, uint32_t seed, float S, uint32_t mix);
+VN_API void vn_camera_frame(const float lookfrom[3], const float forward[3], float vfov_deg, float aspect, float aperture,
+                            float focal_length, float origin[3], float u[3], float v[3], float w[3], float* lens_radius);
+
+/* ---- unit-level entry points used by the parity tests (each runs a CUDA kernel) ---- */
+/* random.cuh:31-67 on the device: out[i] = tea<4>(v0[i], v1[i]); then n_draws LCG draws from that state. */
+VN_API int vn_test_rng(vn_handle h, const uint32_t* v0, const uint32_t* v1, uint64_t n, uint32_t n_draws,
+                       uint32_t* seeds_out, uint32_t* lcg_out, float* rnd_out);
+/* closest hit (tmin 1e-3, tmax 1e16) through the BVH for arbitrary host rays: t (or -1) and ORIGINAL sphere index */
+VN_API int vn_trace_rays(vn_handle h, const float* origins, const float* dirs, uint64_t n, float* t_out,
+                         int32_t* prim_out, uint32_t flags);
+/* the hand-written onesweep radix sort: sorts host (key,value) pairs on the device, keys ascending, stable */
+VN_API int vn_sort_pairs(vn_handle h, uint32_t* keys, uint32_t* values, uint64_t n, uint32_t key_bits);
+/* 30-bit Morton codes of the uploaded spheres' centroids (LBVH builder stage 2) */
+VN_API int vn_morton_codes(vn_handle h, uint32_t* codes_out, uint64_t cap);
+/* make_color on the device (RayTracer.cu:16-47) */
+VN_API int vn_test_make_color(vn_handle h, const float* rgb, uint64_t n, uint8_t* rgba_out, uint32_t flags);
+/* one scatter event on the device: RayTracer.cu:272-440.  in: per-event ray dir(3), hit normal(3), front(1), seed;
+ * out: new dir(3), scattered flag, seed after. */
+VN_API int vn_test_scatter(vn_handle h, uint32_t material_type, const float albedo_fuzz_ir[4], const float* dirs,
+                           const float* normals, const uint8_t* front, const uint32_t* seeds, uint64_t n,
+                           float* dirs_out, uint8_t* scattered_out, uint32_t* seeds_out, uint32_t flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VENUSAUR_B200_H */

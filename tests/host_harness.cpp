@@ -1,0 +1,209 @@
+// host_harness.cpp -- TEST ONLY.  Compiles the product's device math (venusaur_b200/csrc/vn_math.cuh, exact build)
+// and the per-element LBVH builder bodies (lbvh_core.cuh) with g++ and drives them in plain CPU loops, so the
+// logic that the CUDA kernels wrap can be checked against the oracle in the GPU-less container.  The product never
+// uses this: libvenusaur_b200.so has no CPU path.
+//
+// g++ -O2 -std=c++17 -ffp-contract=off -fPIC -shared -Ivenusaur_b200/csrc tests/host_harness.cpp
+#define VN_EXACT 1
+#include "lbvh_core.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+using namespace vn;
+
+struct hh_sphere { float cx, cy, cz, r, ax, ay, az, fuzz_or_ir; uint32_t type; };
+
+struct hh_params {
+    uint32_t width, height, spp, subframe_index, max_depth;
+    float origin[3], u[3], v[3], w[3], lens_radius;
+};
+
+struct HostBvh {
+    std::vector<node_f4> nodes, geom, mat;
+    std::vector<uint8_t> type;
+    std::vector<uint32_t> orig, codes;
+    std::vector<KarrasNode> kn;
+    uint32_t root_link = kEmptyScene;
+};
+
+static void build(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pad_rel, HostBvh& B) {
+    B = HostBvh();
+    if (n == 0) { B.nodes.resize(4); return; }
+    std::vector<f4> llo(n), lhi(n);
+    float clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (uint32_t i = 0; i < n; i++) {
+        const float c[3] = {s[i].cx, s[i].cy, s[i].cz};
+        for (int a = 0; a < 3; a++) { clo[a] = std::min(clo[a], c[a]); chi[a] = std::max(chi[a], c[a]); }
+    }
+    float cinv[3];
+    for (int a = 0; a < 3; a++) cinv[a] = chi[a] > clo[a] ? 1.0f / (chi[a] - clo[a]) : 0.0f;
+    std::vector<uint32_t> codes(n), idx(n);
+    for (uint32_t i = 0; i < n; i++) codes[i] = morton30(s[i].cx, s[i].cy, s[i].cz, clo, cinv);
+    std::iota(idx.begin(), idx.end(), 0u);
+    std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return codes[a] < codes[b]; });
+    B.codes.resize(n); B.orig = idx; B.geom.resize(n); B.mat.resize(n); B.type.resize(n);
+    for (uint32_t i = 0; i < n; i++) {
+        const hh_sphere& p = s[idx[i]];
+        B.codes[i] = codes[idx[i]];
+        B.geom[i] = node_f4{p.cx, p.cy, p.cz, p.r};
+        B.mat[i] = p.type == 2 ? node_f4{p.fuzz_or_ir, 0, 0, 0} : node_f4{p.ax, p.ay, p.az, p.fuzz_or_ir};
+        B.type[i] = (uint8_t)p.type;
+        const float pad = fabsf(p.r) * (1.0f + pad_rel) + 1e-6f;
+        llo[i] = f4{p.cx - pad, p.cy - pad, p.cz - pad, 0};
+        lhi[i] = f4{p.cx + pad, p.cy + pad, p.cz + pad, 0};
+    }
+    const uint32_t ni = n - 1;
+    B.kn.resize(ni);
+    for (uint32_t i = 0; i < ni; i++) B.kn[i] = karras_node(B.codes.data(), (int)n, (int)i);
+    std::vector<f4> ilo(ni), ihi(ni);
+    // refit: children before parents == process internal nodes in post-order (iterative)
+    if (ni) {
+        std::vector<uint32_t> order; order.reserve(ni);
+        std::vector<uint32_t> st{0};
+        while (!st.empty()) {
+            uint32_t i = st.back(); st.pop_back(); order.push_back(i);
+            if (!(B.kn[i].left & kChildLeaf)) st.push_back(B.kn[i].left);
+            if (!(B.kn[i].right & kChildLeaf)) st.push_back(B.kn[i].right);
+        }
+        for (auto it = order.rbegin(); it != order.rend(); ++it) {
+            const KarrasNode& k = B.kn[*it];
+            auto lo = [&](uint32_t c) { return (c & kChildLeaf) ? llo[c & ~kChildLeaf] : ilo[c]; };
+            auto hi = [&](uint32_t c) { return (c & kChildLeaf) ? lhi[c & ~kChildLeaf] : ihi[c]; };
+            f4 a = lo(k.left), b = lo(k.right), c = hi(k.left), d = hi(k.right);
+            ilo[*it] = f4{std::min(a.x, b.x), std::min(a.y, b.y), std::min(a.z, b.z), 0};
+            ihi[*it] = f4{std::max(c.x, d.x), std::max(c.y, d.y), std::max(c.z, d.z), 0};
+        }
+    }
+    std::vector<uint32_t> rank(ni ? ni : 1, 0);
+    uint32_t kept = 0;
+    for (uint32_t i = 0; i < ni; i++) { rank[i] = kept; kept += (B.kn[i].last - B.kn[i].first + 1u) > leaf_size; }
+    B.nodes.assign(2 * (2 + 2 * (size_t)kept), node_f4{0, 0, 0, 0});
+    // root = node 1
+    if (ni == 0) {
+        B.nodes[2] = node_f4{llo[0].x, llo[0].y, llo[0].z, u2f(leaf_link(0, 1))};
+        B.nodes[3] = node_f4{lhi[0].x, lhi[0].y, lhi[0].z, u2f(1u)};
+    } else {
+        const bool root_kept = n > leaf_size;
+        B.nodes[2] = node_f4{ilo[0].x, ilo[0].y, ilo[0].z, u2f(root_kept ? 2u : leaf_link(0, n))};
+        B.nodes[3] = node_f4{ihi[0].x, ihi[0].y, ihi[0].z, u2f(n)};
+        for (uint32_t i = 0; i < ni; i++) {
+            if ((B.kn[i].last - B.kn[i].first + 1u) <= leaf_size) continue;
+            const uint32_t base = 2u + 2u * rank[i];
+            PackedNode L = pack_child(B.kn[i].left, B.kn.data(), rank.data(), ilo.data(), ihi.data(), llo.data(), lhi.data(), leaf_size);
+            PackedNode R = pack_child(B.kn[i].right, B.kn.data(), rank.data(), ilo.data(), ihi.data(), llo.data(), lhi.data(), leaf_size);
+            B.nodes[2 * base + 0] = node_f4{L.a.x, L.a.y, L.a.z, L.a.w};
+            B.nodes[2 * base + 1] = node_f4{L.b.x, L.b.y, L.b.z, L.b.w};
+            B.nodes[2 * base + 2] = node_f4{R.a.x, R.a.y, R.a.z, R.a.w};
+            B.nodes[2 * base + 3] = node_f4{R.b.x, R.b.y, R.b.z, R.b.w};
+        }
+    }
+    B.root_link = f2u(B.nodes[2].w);
+}
+
+extern "C" {
+
+uint32_t hh_tea4(uint32_t a, uint32_t b) { return tea4(a, b); }
+uint32_t hh_lcg(uint32_t* s) { return lcg(*s); }
+float hh_rnd(uint32_t* s) { return rnd(*s); }
+uint32_t hh_morton30(float x, float y, float z, const float* clo, const float* cinv) { return morton30(x, y, z, clo, cinv); }
+void hh_make_color(const float* rgb, uint8_t* out) { uint32_t c = make_color_u32(mk3(rgb[0], rgb[1], rgb[2])); memcpy(out, &c, 4); }
+
+// Builds the packed LBVH on the CPU with the product's per-element functions.  Returns the node count; copies out
+// up to cap nodes (32 B each) and the sorted->original permutation.
+uint64_t hh_build_bvh(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pad_rel, void* nodes_out, uint64_t cap,
+                      uint32_t* orig_out, uint32_t* codes_out) {
+    HostBvh B;
+    build(s, n, leaf_size, pad_rel, B);
+    uint64_t nn = B.nodes.size() / 2;
+    if (nodes_out) memcpy(nodes_out, B.nodes.data(), std::min<uint64_t>(nn, cap) * 32);
+    if (orig_out) memcpy(orig_out, B.orig.data(), 4ull * n);
+    if (codes_out) memcpy(codes_out, B.codes.data(), 4ull * n);
+    return nn;
+}
+
+void hh_closest_hit(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pad_rel, const float* o, const float* d,
+                    uint64_t nrays, float* t_out, int32_t* prim_out, uint64_t* node_visits, uint64_t* sphere_tests) {
+    HostBvh B;
+    build(s, n, leaf_size, pad_rel, B);
+    TraceCounters cnt{0, 0};
+    uint64_t nv = 0, st = 0;
+    for (uint64_t i = 0; i < nrays; i++) {
+        float t; int prim;
+        cnt.nodes = cnt.spheres = 0;
+        closest_hit<true>(B.nodes.data(), B.geom.data(), B.root_link, mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]),
+                          mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), t, prim, cnt);
+        nv += cnt.nodes; st += cnt.spheres;
+        t_out[i] = prim >= 0 ? t : -1.0f;
+        prim_out[i] = prim >= 0 ? (int32_t)B.orig[prim] : -1;
+    }
+    if (node_visits) *node_visits = nv;
+    if (sphere_tests) *sphere_tests = st;
+}
+
+// pixel_color / spp for every pixel, forward throughput order (what the kernels compute).
+void hh_render_mean(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pad_rel, const hh_params* P,
+                    float* mean_rgba, uint64_t* segments, uint64_t* node_visits, uint64_t* sphere_tests) {
+    HostBvh B;
+    build(s, n, leaf_size, pad_rel, B);
+    SceneView sc{B.nodes.data(), B.geom.data(), B.mat.data(), B.type.data(), B.root_link};
+    Camera cam;
+    cam.origin = mk3(P->origin[0], P->origin[1], P->origin[2]);
+    cam.u = mk3(P->u[0], P->u[1], P->u[2]);
+    cam.v = mk3(P->v[0], P->v[1], P->v[2]);
+    cam.w = mk3(P->w[0], P->w[1], P->w[2]);
+    cam.u_unit = normalize(cam.u);
+    cam.v_unit = normalize(cam.v);
+    cam.lens_radius = P->lens_radius;
+    cam.wm1 = (float)(P->width - 1); cam.hm1 = (float)(P->height - 1);
+    cam.inv_wm1 = 1.0f / cam.wm1; cam.inv_hm1 = 1.0f / cam.hm1;
+    uint64_t segs = 0, nv = 0, stt = 0;
+    const float inv_spp = 1.0f / (float)P->spp;
+    for (uint32_t px = 0; px < P->width * P->height; px++) {
+        uint32_t seed = tea4(px, P->subframe_index);
+        f3 sum = mk3(0.0f);
+        for (uint32_t k = 0; k < P->spp; k++) {
+            PathState st;
+            camera_ray(cam, px % P->width, px / P->width, seed, st.o, st.d);
+            st.thr = mk3(1.0f);
+            st.seed = seed;
+            st.depth = (int)P->max_depth - 1;
+            f3 result;
+            while (true) {
+                float t; int prim;
+                TraceCounters cnt{0, 0};
+                closest_hit<true>(sc.nodes, sc.geom, sc.root_link, st.o, st.d, t, prim, cnt);
+                segs++; nv += cnt.nodes; stt += cnt.spheres;
+                if (!shade_segment(sc, st, t, prim, result)) break;
+            }
+            sum = sum + result;
+        }
+        f3 m = sum * inv_spp;
+        mean_rgba[4 * px] = m.x; mean_rgba[4 * px + 1] = m.y; mean_rgba[4 * px + 2] = m.z; mean_rgba[4 * px + 3] = 1.0f;
+    }
+    if (segments) *segments = segs;
+    if (node_visits) *node_visits = nv;
+    if (sphere_tests) *sphere_tests = stt;
+}
+
+}  // extern "C"
+
+// One scatter event with the product's exact math on the CPU (same packing as k_scatter in path_kernels.cu).
+extern "C" void hh_scatter(uint32_t type, const float* mat4, const float* dirs, const float* normals, const uint8_t* front,
+                           const uint32_t* seeds, uint64_t n, float* dirs_out, uint8_t* scattered, uint32_t* seeds_out) {
+    for (uint64_t i = 0; i < n; i++) {
+        const f3 d = mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
+        const f3 nrm = mk3(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]);
+        uint32_t seed = seeds[i];
+        f3 out = mk3(0.0f);
+        bool ok = true;
+        if (type == 0u) out = scatter_lambertian(nrm, seed);
+        else if (type == 1u) ok = scatter_metal(d, nrm, mat4[3], seed, out);
+        else out = scatter_dielectric(d, nrm, front[i] != 0, mat4[3], seed);
+        dirs_out[3 * i] = out.x; dirs_out[3 * i + 1] = out.y; dirs_out[3 * i + 2] = out.z;
+        scattered[i] = ok ? 1 : 0;
+        seeds_out[i] = seed;
+    }
+}

@@ -1,0 +1,200 @@
+"""CPU tests of the product's host side: the C ABI library loads and exports what the header declares, the drop-in
+scene/camera match the oracle, and the product's device math + LBVH logic (compiled for the host by tests/host_harness.cpp)
+is bit-identical to the oracle.  No kernel is launched here."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import venusaur_b200 as vb
+from venusaur_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "venusaur_b200.h")).read()
+    declared = set(re.findall(r"VN_API\s+[\w\s\*]+?\b(vn_\w+)\s*\(", header))
+    assert len(declared) >= 35
+    lib = vb.load()
+    for name in declared:
+        assert hasattr(lib, name), "libvenusaur_b200.so does not export %s" % name
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    out = subprocess.run(["nm", "-D", "--defined-only", vb.lib_path()], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (vn_\w+)", out))
+    assert declared <= exported
+    assert lib.vn_version().decode().startswith("venusaur_b200")
+
+
+def test_abi_struct_sizes():
+    assert C.sizeof(_lib.vn_sphere) == 36 and C.sizeof(_lib.vn_node32) == 32
+    # the C side static_asserts the same numbers (vn_api.cu)
+    assert C.sizeof(_lib.vn_params) == 96 and C.sizeof(_lib.vn_stats) == 64 and C.sizeof(_lib.vn_bvh_info) == 48
+    assert _lib.vn_params.origin.offset == 32 and _lib.vn_params.flags.offset == 92
+
+
+def test_no_gpu_fails_loudly():
+    lib = vb.load()
+    if lib.vn_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(vb.Exception, match="no CPU path"):
+        vb.Context(0)
+    with pytest.raises(vb.Exception):
+        r = vb.Renderer()
+        r.Init(vb.Scene())
+
+
+def test_scene_and_camera_match_oracle(oracle_mod, rtiow):
+    assert np.array_equal(vb.rtiow_final_scene().view(np.uint8), rtiow.view(np.uint8))
+    sc = vb.Scene()
+    assert len(sc.m_spheres) == 486 and sc.m_aabbs.shape == (486, 6) and list(sc.m_indices[:3]) == [0, 1, 2]
+    for (w, h) in [(400, 225), (1920, 1080), (1200, 800)]:
+        a = oracle_mod.rtiow_camera(w, h)
+        b = vb.rtiow_camera(w, h).frame()
+        for x, y in zip(a, b):
+            assert np.array_equal(np.asarray(x), np.asarray(y))
+    for n, seed, S, mix in [(1000, 0x5EED0001, 100.0, 0), (1000, 0x5EED0002, 250.0, 1)]:
+        a = oracle_mod.random_scene(n, seed, S, mix)
+        b = vb.random_scene(n, seed, S, mix)
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+    mixes = np.bincount(vb.random_scene(20000, 0x5EED0002, 250.0, 1)["type"], minlength=3) / 20000.0
+    assert abs(mixes[2] - 0.5) < 0.02 and abs(mixes[0] - 0.4) < 0.02
+
+
+def test_camera_dirty_flag():
+    cam = vb.rtiow_camera(400, 225)
+    assert cam.Changed() is True and cam.Changed() is False
+    cam.SetFocalLength(10.0)
+    assert cam.Changed() is False
+    cam.SetFocalLength(9.0)
+    assert cam.Changed() is True
+    assert cam.GetLensRadius() == pytest.approx(0.05)
+
+
+def _hh_params(cam, W, H, spp, sub, depth):
+    class HP(C.Structure):
+        _fields_ = [(n, C.c_uint32) for n in "width height spp subframe max_depth".split()] + \
+                   [("origin", C.c_float * 3), ("u", C.c_float * 3), ("v", C.c_float * 3), ("w", C.c_float * 3), ("lens", C.c_float)]
+    p = HP()
+    p.width, p.height, p.spp, p.subframe, p.max_depth = W, H, spp, sub, depth
+    p.origin, p.u, p.v, p.w, p.lens = (C.c_float * 3)(*cam[0]), (C.c_float * 3)(*cam[1]), (C.c_float * 3)(*cam[2]), (C.c_float * 3)(*cam[3]), float(cam[4])
+    return p
+
+
+@pytest.mark.parametrize("leaf,depth,sub", [(1, 50, 1), (2, 4, 0), (2, 50, 7), (4, 50, 2), (8, 12, 3)])
+def test_product_math_equals_oracle_on_cpu(host_harness, oracle_mod, rtiow, leaf, depth, sub):
+    """vn_math.cuh (exact build) + the LBVH bodies of lbvh_core.cuh, run on the CPU, vs the oracle with brute-force
+    closest hit: every pixel bit-identical, same number of ray segments."""
+    W, H, spp = 48, 27, 3
+    cam = oracle_mod.rtiow_camera(W, H)
+    hp = _hh_params(cam, W, H, spp, sub, depth)
+    mean = np.zeros((H, W, 4), np.float32)
+    segs, nv, st = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    host_harness.hh_render_mean(rtiow.ctypes.data_as(C.c_void_p), len(rtiow), leaf, C.c_float(0.01), C.byref(hp),
+                                mean.ctypes.data_as(C.c_void_p), C.byref(segs), C.byref(nv), C.byref(st))
+    orc = oracle_mod.Oracle(rtiow)
+    want, stats = orc.render_mean(orc.params(cam, W, H, spp, sub, depth, atten=oracle_mod.ATTEN_FORWARD, closest=oracle_mod.CLOSEST_BRUTE))
+    assert segs.value == stats.segments
+    assert np.array_equal(mean, want)
+    assert nv.value / segs.value < 20      # the LBVH actually prunes
+
+
+def _check_bvh(nodes, order, spheres, leaf_size, pad_rel=0.01):
+    """Structural invariants of the packed 32-byte-node LBVH."""
+    n = len(spheres)
+    assert sorted(order.tolist()) == list(range(n))
+    seen = np.zeros(n, np.int32)
+    LEAF = 0x80000000
+
+    def walk(idx, depth):
+        nd = nodes[idx]
+        link = int(nd["link"])
+        if link & LEAF:
+            first, cnt = (link & 0x7FFFFFFF) >> 3, (link & 7) + 1
+            assert cnt <= max(leaf_size, 1) and int(nd["aux"]) == cnt
+            for k in range(first, first + cnt):
+                seen[k] += 1
+                s = spheres[order[k]]
+                r = abs(float(s["r"]))
+                c = np.array([s["cx"], s["cy"], s["cz"]], np.float64)
+                assert (nd["lo"] <= c - r).all() and (nd["hi"] >= c + r).all()
+            return cnt, depth
+        assert link % 2 == 0 and link >= 2
+        tot, dmax = 0, depth
+        for ch in (link, link + 1):
+            c = nodes[ch]
+            assert (c["lo"] >= nd["lo"]).all() and (c["hi"] <= nd["hi"]).all(), "child box outside parent"
+            k, d = walk(ch, depth + 1)
+            tot += k
+            dmax = max(dmax, d)
+        assert int(nd["aux"]) == tot
+        return tot, dmax
+
+    total, depth = walk(1, 0)
+    assert total == n and (seen == 1).all()
+    assert depth <= 62
+    return depth
+
+
+@pytest.mark.parametrize("leaf", [1, 2, 4])
+def test_lbvh_logic_invariants_on_cpu(host_harness, oracle_mod, rtiow, leaf):
+    import sys
+    sys.setrecursionlimit(10000)
+    for spheres in (rtiow, oracle_mod.random_scene(3000, 0x5EED0001, 30.0, 0), rtiow[:1], rtiow[:2], rtiow[:3],
+                    np.repeat(rtiow[5:6], 40)):      # 40 identical spheres: equal Morton codes
+        n = len(spheres)
+        spheres = np.ascontiguousarray(spheres)
+        nodes = np.zeros(2 * n + 4, vb.api.NODE_DTYPE)
+        order = np.zeros(n, np.uint32)
+        codes = np.zeros(n, np.uint32)
+        nn = host_harness.hh_build_bvh(spheres.ctypes.data_as(C.c_void_p), n, leaf, C.c_float(0.01), nodes.ctypes.data_as(C.c_void_p), len(nodes),
+                                       order.ctypes.data_as(C.c_void_p), codes.ctypes.data_as(C.c_void_p))
+        assert nn <= 2 * n + 2
+        assert (np.diff(codes.astype(np.int64)) >= 0).all() and codes.max() < (1 << 30)
+        _check_bvh(nodes[:nn], order, spheres, leaf)
+
+
+def test_traversal_equals_brute_force_on_cpu(host_harness, oracle_mod):
+    spheres = oracle_mod.random_scene(2000, 0x5EED0001, 20.0, 0)
+    rng = np.random.RandomState(11)
+    o = (rng.rand(20000, 3).astype(np.float32) - 0.5) * np.float32(50.0)
+    d = rng.randn(20000, 3).astype(np.float32)
+    orc = oracle_mod.Oracle(spheres)
+    t0, p0 = orc.closest_hit(o, d, use_bvh=False)
+    t1 = np.zeros(len(o), np.float32)
+    p1 = np.zeros(len(o), np.int32)
+    host_harness.hh_closest_hit(spheres.ctypes.data_as(C.c_void_p), len(spheres), 2, C.c_float(0.01), o.ctypes.data_as(C.c_void_p),
+                                d.ctypes.data_as(C.c_void_p), len(o), t1.ctypes.data_as(C.c_void_p), p1.ctypes.data_as(C.c_void_p), None, None)
+    assert (p0 >= 0).sum() > 1000
+    assert np.array_equal(t0, t1) and np.array_equal(p0, p1)
+
+
+def test_cpp_dropin_headers_compile():
+    """The header-only C++17 shim compiles without CUDA or glm and uses the reference's class and method names."""
+    src = r'''
+    #include "venusaur/Renderer.h"
+    int main() {
+        Scene scene;                                   // Core.cpp:30
+        Camera camera(venusaur::vec3(13, 2, 3), 20.0f, 3.0f / 2.0f, 0.1f, 10.0f);   // Core.cpp:29
+        camera.SetForward(venusaur::vec3(0 - 13, 0 - 2, 0 - 3));                    // Core.cpp:355
+        Renderer renderer;
+        if (scene.m_spheres.size() != 486 || scene.m_aabbs.size() != 486 || scene.m_indices.size() != 486) return 1;
+        try { renderer.Init(scene, "ptx is ignored"); } catch (const Exception& e) { return 0; }   // no GPU here -> throws
+        CUDAOutputBuffer<uchar4> buf(CUDAOutputBufferType::CUDA_DEVICE, 64, 36);
+        renderer.Draw(camera, buf);
+        uchar4* px = buf.getHostPointer();
+        renderer.Cleanup();
+        return px ? 0 : 2;
+    }'''
+    out = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out, exist_ok=True)
+    cpp = os.path.join(out, "dropin.cpp")
+    open(cpp, "w").write(src)
+    exe = os.path.join(out, "dropin")
+    libdir = os.path.dirname(vb.lib_path())
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"), cpp, "-o", exe,
+                    "-L" + libdir, "-lvenusaur_b200", "-Wl,-rpath," + libdir], check=True)
+    assert subprocess.run([exe]).returncode == 0

@@ -1,0 +1,95 @@
+// kernels.h -- internal launch interface between the C ABI (vn_api.cu) and the trace / tonemap kernels.
+// path_kernels.cu and wavefront.cu are each compiled twice: namespace vn::exact (-DVN_EXACT=1 -fmad=false) and
+// namespace vn::fast (-DVN_EXACT=0, FMA + approximate reciprocal/rsqrt).  See vn_math.cuh.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "vn_math.cuh"
+
+namespace vn {
+
+constexpr int kMaxPeers = 8;
+
+enum BlendMode : uint32_t { kBlendOverwrite = 0, kBlendLerp = 1, kBlendSum = 2 };
+
+// Everything one render launch needs; passed by value (__grid_constant__), i.e. in the constant bank like the
+// reference's `__constant__ Params params` (RayTracer.cu:49-52).
+struct RenderLaunch {
+    Camera cam;
+    uint32_t width, height, spp, subframe_index, max_depth;
+    uint32_t row_begin, row_end;
+    uint32_t blend_mode;
+    float blend_a, inv_spp;
+    float4* accum;
+    uint32_t* image;                 // uchar4 pixels, may be null
+    const float4* nodes;
+    const float4* geom;
+    const float4* mat;
+    const uint8_t* type;
+    uint32_t root_link, num_nodes, num_spheres;
+    unsigned long long* counters;    // [0] segments, [1] paths, [2] node visits, [3] sphere tests
+    uint32_t* work_counter;          // persistent-thread work ticket
+    uint32_t total_work, tiles_x;    // work items = 8x4 pixel tiles * 32
+};
+
+struct KernelConfig {
+    int threads;
+    int blocks;
+    size_t smem_bytes;               // dynamic shared memory (scene staging), 0 when the scene stays in HBM/L2
+    bool scene_in_smem;
+    bool count;                      // instrumented variant
+};
+
+size_t scene_smem_bytes(uint32_t num_nodes, uint32_t num_spheres);
+
+// Wavefront state: SoA queues in HBM (L2-resident at the default capacity), owned by the context.
+// One path slot = 48 bytes of ray state (o 12, d 12, throughput 12, seed 4, sample slot 4, depth 4).
+struct WfState {
+    float *ox, *oy, *oz, *dx, *dy, *dz, *tr, *tg, *tb;
+    uint32_t* seed;
+    uint32_t* ps;        // index into sample_rgb: sample * region_pixels + region_pixel
+    int32_t* depth;
+};
+constexpr int kWfStateArrays = 12;
+enum WfCount : uint32_t {      // words of WavefrontBuffers::counts
+    kWfCountNext = 0,          // entries appended to the next ray queue so far
+    kWfCountMat = 1,           // [1..4] material queue sizes: miss, Lambertian, metal, dielectric
+    kWfTicketExtend = 5,
+    kWfTicketShade = 6,        // [6..9]
+    kWfCountWords = 16
+};
+struct WavefrontBuffers {
+    uint32_t capacity = 0;     // path slots per queue
+    void* slab = nullptr;      // one allocation, carved into the arrays below
+    WfState st[2];             // ray queues, ping-pong: shade compacts survivors of st[cur] into st[cur^1]
+    float* hit_t = nullptr;    // hit queue, indexed like the current ray queue
+    int32_t* hit_prim = nullptr;
+    uint32_t* mat_queue[4] = {nullptr, nullptr, nullptr, nullptr};
+    uint32_t* counts = nullptr;
+    float* sample_rgb = nullptr;   // per (sample, pixel) radiance, summed in sample order by k_wf_accumulate
+};
+constexpr int kWfArraysTotal = 2 * kWfStateArrays + 2 + 4;   // 4-byte arrays of `capacity` entries in the slab
+
+#define VN_DECLARE_KERNEL_API                                                                                          \
+    int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool count);                             \
+    cudaError_t launch_render_persistent(const RenderLaunch& p, const KernelConfig& cfg, cudaStream_t stream);         \
+    cudaError_t launch_tonemap(const float4* accum, float scale, uint32_t* image, uint64_t n, cudaStream_t stream);    \
+    cudaError_t launch_reduce_tonemap_peers(const float4* const* peers, uint32_t n_peers, float scale, uint64_t begin, \
+                                            uint64_t end, float4* accum_out, uint32_t* image, cudaStream_t stream);    \
+    cudaError_t launch_test_rng(const uint32_t* v0, const uint32_t* v1, uint64_t n, uint32_t n_draws, uint32_t* seeds, \
+                                uint32_t* lcg_out, float* rnd_out, cudaStream_t stream);                               \
+    cudaError_t launch_trace_rays(const RenderLaunch& scene, const float* o, const float* d, uint64_t n, float* t_out, \
+                                  int32_t* prim_out, const uint32_t* orig, cudaStream_t stream);                       \
+    cudaError_t launch_make_color(const float* rgb, uint64_t n, uint32_t* out, cudaStream_t stream);                   \
+    cudaError_t launch_scatter(uint32_t type, float4 mat, const float* dirs, const float* normals,                     \
+                               const uint8_t* front, const uint32_t* seeds, uint64_t n, float* dirs_out,               \
+                               uint8_t* scattered, uint32_t* seeds_out, cudaStream_t stream);                          \
+    cudaError_t launch_wavefront(const RenderLaunch& p, const WavefrontBuffers& wf, int num_sms, cudaStream_t stream,   \
+                                 uint32_t* launches);
+
+namespace exact { VN_DECLARE_KERNEL_API }
+namespace fast { VN_DECLARE_KERNEL_API }
+
+}  // namespace vn

@@ -1,0 +1,359 @@
+// lbvh.cu -- LBVH builder kernels for sm_100a.  Replaces Renderer::BuildAccelerationStructures
+// (Renderer.h:160-255: optixAccelComputeMemoryUsage / optixAccelBuild / optixAccelCompact over per-sphere AABBs)
+// and the per-sphere SBT records of Renderer::CreateSBT (Renderer.h:452-520).
+//
+// Pipeline (all on one stream, no host round trip except the final node count):
+//   k_centroid_bounds   centroid AABB of the scene            (warp shuffle reduce + ordered-int atomics)
+//   k_morton            30-bit Morton code per sphere + index
+//   rs::sort_pairs      hand-written onesweep radix sort (radix_sort.cuh)
+//   k_gather            sphere records permuted into Morton order (SoA: geom, material, type) + padded leaf AABBs
+//   k_karras            Karras 2012 hierarchy, one thread per internal node
+//   k_refit             bottom-up AABB refit, one thread per leaf, atomic arrival counters
+//   k_mark_kept + scan  which Karras nodes survive leaf collapsing, and their rank
+//   k_pack              32-byte nodes, sibling pairs adjacent and 64-byte aligned
+// Compiled with -fmad=false so that Morton quantisation matches the CPU emulation in tests bit for bit.
+#include "lbvh.h"
+
+#include "lbvh_core.cuh"
+#include "radix_sort.cuh"
+
+namespace vn {
+
+namespace {
+
+constexpr int kBlock = 256;
+
+__device__ __forceinline__ uint32_t enc_ordered(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float dec_ordered(uint32_t e) {
+    const uint32_t u = (e & 0x80000000u) ? (e & 0x7FFFFFFFu) : ~e;
+    return __uint_as_float(u);
+}
+
+// bounds[0..2] = min centroid (ordered encoding), bounds[3..5] = max centroid.  Pre-set to 0xFFFFFFFF / 0.
+__global__ void __launch_bounds__(kBlock) k_centroid_bounds(const vn_sphere* __restrict__ s, uint32_t n, uint32_t* __restrict__ bounds) {
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+        const float c[3] = {s[i].cx, s[i].cy, s[i].cz};
+#pragma unroll
+        for (int a = 0; a < 3; a++) { lo[a] = fminf(lo[a], c[a]); hi[a] = fmaxf(hi[a], c[a]); }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            atomicMin(&bounds[a], enc_ordered(lo[a]));
+            atomicMax(&bounds[3 + a], enc_ordered(hi[a]));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_morton(const vn_sphere* __restrict__ s, uint32_t n, const uint32_t* __restrict__ bounds,
+                                                  uint32_t* __restrict__ codes, uint32_t* __restrict__ idx) {
+    const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    float clo[3], cinv[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const float l = dec_ordered(bounds[a]), h = dec_ordered(bounds[3 + a]);
+        clo[a] = l;
+        cinv[a] = h > l ? 1.0f / (h - l) : 0.0f;
+    }
+    codes[i] = morton30(s[i].cx, s[i].cy, s[i].cz, clo, cinv);
+    idx[i] = i;
+}
+
+__global__ void __launch_bounds__(kBlock) k_gather(const vn_sphere* __restrict__ s, const uint32_t* __restrict__ sorted_idx, uint32_t n,
+                                                  float pad_rel, float4* __restrict__ geom, float4* __restrict__ mat,
+                                                  uint8_t* __restrict__ type, uint32_t* __restrict__ orig,
+                                                  f4* __restrict__ leaf_lo, f4* __restrict__ leaf_hi) {
+    const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t src = sorted_idx[i];
+    const vn_sphere p = s[src];
+    geom[i] = make_float4(p.cx, p.cy, p.cz, p.r);
+    // MaterialData (RayTracer.h:27-38): {albedo, fuzz} or {ir} aliasing albedo.x
+    mat[i] = p.type == VN_DIELECTRIC ? make_float4(p.fuzz_or_ir, 0.0f, 0.0f, 0.0f) : make_float4(p.ax, p.ay, p.az, p.fuzz_or_ir);
+    type[i] = (uint8_t)p.type;
+    orig[i] = src;
+    // |r| (sphere.h:17-28 computes fabsf(radius) and then forgets to use it) plus a pad that keeps the slab
+    // test conservative against float rounding in the sphere quadratic.
+    const float pad = fabsf(p.r) * (1.0f + pad_rel) + 1e-6f;
+    leaf_lo[i] = f4{p.cx - pad, p.cy - pad, p.cz - pad, 0.0f};
+    leaf_hi[i] = f4{p.cx + pad, p.cy + pad, p.cz + pad, 0.0f};
+}
+
+__global__ void __launch_bounds__(kBlock) k_karras(const uint32_t* __restrict__ codes, uint32_t n, KarrasNode* __restrict__ kn,
+                                                  uint32_t* __restrict__ parent_internal, uint32_t* __restrict__ parent_leaf) {
+    const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    if (i + 1 >= n) return;
+    const KarrasNode k = karras_node(codes, (int)n, (int)i);
+    kn[i] = k;
+    if (k.left & kChildLeaf) parent_leaf[k.left & ~kChildLeaf] = i; else parent_internal[k.left] = i;
+    if (k.right & kChildLeaf) parent_leaf[k.right & ~kChildLeaf] = i; else parent_internal[k.right] = i;
+}
+
+__device__ __forceinline__ f4 ldcg4(const f4* p) {
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(p));
+    return f4{v.x, v.y, v.z, v.w};
+}
+
+// One thread per leaf walks towards the root.  The first thread to reach a node leaves; the second one finds both
+// children complete (the first made its box visible with a fence before bumping the counter) and merges them.
+// Child boxes are read with ld.cg: L1 is not coherent across SMs.
+__global__ void __launch_bounds__(kBlock) k_refit(uint32_t n, const KarrasNode* __restrict__ kn, const uint32_t* __restrict__ parent_internal,
+                                                 const uint32_t* __restrict__ parent_leaf, const f4* __restrict__ leaf_lo,
+                                                 const f4* __restrict__ leaf_hi, f4* ilo, f4* ihi, uint32_t* __restrict__ arrivals) {
+    const uint32_t leaf = blockIdx.x * kBlock + threadIdx.x;
+    if (leaf >= n || n < 2) return;
+    uint32_t node = parent_leaf[leaf];
+    while (true) {
+        __threadfence();
+        if (atomicAdd(&arrivals[node], 1u) == 0u) return;
+        const KarrasNode k = kn[node];
+        const f4 la = (k.left & kChildLeaf) ? leaf_lo[k.left & ~kChildLeaf] : ldcg4(&ilo[k.left]);
+        const f4 ha = (k.left & kChildLeaf) ? leaf_hi[k.left & ~kChildLeaf] : ldcg4(&ihi[k.left]);
+        const f4 lb = (k.right & kChildLeaf) ? leaf_lo[k.right & ~kChildLeaf] : ldcg4(&ilo[k.right]);
+        const f4 hb = (k.right & kChildLeaf) ? leaf_hi[k.right & ~kChildLeaf] : ldcg4(&ihi[k.right]);
+        const float4 lo = make_float4(fminf(la.x, lb.x), fminf(la.y, lb.y), fminf(la.z, lb.z), 0.0f);
+        const float4 hi = make_float4(fmaxf(ha.x, hb.x), fmaxf(ha.y, hb.y), fmaxf(ha.z, hb.z), 0.0f);
+        __stcg(reinterpret_cast<float4*>(&ilo[node]), lo);
+        __stcg(reinterpret_cast<float4*>(&ihi[node]), hi);
+        if (node == 0u) return;
+        node = parent_internal[node];
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_mark_kept(const KarrasNode* __restrict__ kn, uint32_t n_internal, uint32_t leaf_size,
+                                                     uint32_t* __restrict__ kept) {
+    const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n_internal) return;
+    kept[i] = (kn[i].last - kn[i].first + 1u) > leaf_size ? 1u : 0u;
+}
+
+// ---- exclusive scan of uint32 (three small kernels; 1024 elements per block)
+constexpr int kScanItems = 4;
+constexpr int kScanTile = kBlock * kScanItems;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t* total) {
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc += t;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0, tot = 0;
+    for (int w = 0; w < kBlock / 32; w++) {
+        const uint32_t t = s_warp[w];
+        if (w < (int)warp) base += t;
+        tot += t;
+    }
+    __syncthreads();
+    *total = tot;
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(kBlock) k_scan_block_sums(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ sums) {
+    __shared__ uint32_t s_warp[kBlock / 32];
+    uint32_t v = 0;
+    const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) if (base + k < n) v += in[base + k];
+    uint32_t total;
+    block_exclusive_scan(v, s_warp, &total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of sums[0..nb) in place; sums[nb] = grand total
+__global__ void __launch_bounds__(kBlock) k_scan_sums(uint32_t* __restrict__ sums, uint32_t nb) {
+    __shared__ uint32_t s_warp[kBlock / 32];
+    uint32_t carry = 0;
+    for (uint32_t b0 = 0; b0 < nb; b0 += kBlock) {
+        const uint32_t i = b0 + threadIdx.x;
+        const uint32_t v = i < nb ? sums[i] : 0u;
+        uint32_t total;
+        const uint32_t e = block_exclusive_scan(v, s_warp, &total);
+        if (i < nb) sums[i] = carry + e;
+        carry += total;
+    }
+    if (threadIdx.x == 0) sums[nb] = carry;
+}
+
+__global__ void __launch_bounds__(kBlock) k_scan_final(const uint32_t* __restrict__ in, uint32_t n, const uint32_t* __restrict__ sums,
+                                                      uint32_t* __restrict__ out) {
+    __shared__ uint32_t s_warp[kBlock / 32];
+    uint32_t x[kScanItems];
+    uint32_t v = 0;
+    const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) { x[k] = base + k < n ? in[base + k] : 0u; v += x[k]; }
+    uint32_t total;
+    uint32_t e = sums[blockIdx.x] + block_exclusive_scan(v, s_warp, &total);
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) { if (base + k < n) out[base + k] = e; e += x[k]; }
+}
+
+__device__ __forceinline__ void store_node(float4* nodes, uint32_t index, const PackedNode& p) {
+    nodes[2 * index] = make_float4(p.a.x, p.a.y, p.a.z, p.a.w);
+    nodes[2 * index + 1] = make_float4(p.b.x, p.b.y, p.b.z, p.b.w);
+}
+
+__global__ void __launch_bounds__(kBlock) k_pack(uint32_t n, const KarrasNode* __restrict__ kn, const uint32_t* __restrict__ rank,
+                                                const f4* __restrict__ ilo, const f4* __restrict__ ihi, const f4* __restrict__ leaf_lo,
+                                                const f4* __restrict__ leaf_hi, uint32_t leaf_size, float4* __restrict__ nodes) {
+    const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    if (i == 0) {
+        // node 0: padding; node 1: root
+        nodes[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        nodes[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        PackedNode root;
+        if (n == 1) {
+            root.a = leaf_lo[0]; root.b = leaf_hi[0];
+            root.a.w = u2f(leaf_link(0u, 1u)); root.b.w = u2f(1u);
+        } else {
+            root.a = ilo[0]; root.b = ihi[0];
+            root.a.w = u2f(n > leaf_size ? 2u : leaf_link(0u, n)); root.b.w = u2f(n);
+        }
+        store_node(nodes, 1u, root);
+    }
+    if (i + 1 >= n) return;
+    if ((kn[i].last - kn[i].first + 1u) <= leaf_size) return;
+    const uint32_t base = 2u + 2u * rank[i];
+    store_node(nodes, base, pack_child(kn[i].left, kn, rank, ilo, ihi, leaf_lo, leaf_hi, leaf_size));
+    store_node(nodes, base + 1u, pack_child(kn[i].right, kn, rank, ilo, ihi, leaf_lo, leaf_hi, leaf_size));
+}
+
+#define LB_CHECK(call)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e_); goto fail; } \
+    } while (0)
+
+inline uint32_t blocks_for(uint64_t n) { return (uint32_t)((n + kBlock - 1) / kBlock); }
+
+}  // namespace
+
+void lbvh_free(LbvhScene& sc) {
+    cudaFree(sc.geom); cudaFree(sc.mat); cudaFree(sc.type); cudaFree(sc.orig); cudaFree(sc.nodes); cudaFree(sc.codes);
+    sc.geom = sc.mat = sc.nodes = nullptr; sc.type = nullptr; sc.orig = sc.codes = nullptr;
+    sc.num_nodes = 0; sc.n = 0; sc.root_link = kEmptyScene;
+}
+
+int lbvh_build(const vn_sphere* d_spheres, uint64_t n64, uint32_t leaf_size, float pad_rel, int num_sms, cudaStream_t stream,
+               LbvhScene& out, uint32_t* launches, std::string& err) {
+    lbvh_free(out);
+    if (n64 > (1ull << 28)) { err = "too many spheres (limit 2^28)"; return -1; }
+    const uint32_t n = (uint32_t)n64;
+    if (leaf_size < 1) leaf_size = 1;
+    if (leaf_size > 8) leaf_size = 8;
+    out.n = n;
+    out.leaf_size = leaf_size;
+    uint32_t *bounds = nullptr, *codes0 = nullptr, *codes1 = nullptr, *idx0 = nullptr, *idx1 = nullptr, *parent_i = nullptr,
+             *parent_l = nullptr, *arrivals = nullptr, *kept = nullptr, *rank = nullptr, *sums = nullptr;
+    void* ws = nullptr;
+    KarrasNode* kn = nullptr;
+    f4 *leaf_lo = nullptr, *leaf_hi = nullptr, *ilo = nullptr, *ihi = nullptr;
+    uint32_t launched = 0;
+
+    if (n == 0) {
+        LB_CHECK(cudaMalloc(&out.nodes, 4 * sizeof(float4)));
+        LB_CHECK(cudaMemsetAsync(out.nodes, 0, 4 * sizeof(float4), stream));
+        out.num_nodes = 2;
+        out.root_link = kEmptyScene;
+        return 0;
+    }
+    {
+        const uint32_t ni = n - 1;
+        const uint32_t nb = (uint32_t)((ni + kScanTile - 1) / kScanTile);
+        LB_CHECK(cudaMalloc(&bounds, 6 * sizeof(uint32_t)));
+        LB_CHECK(cudaMalloc(&codes0, 4ull * n)); LB_CHECK(cudaMalloc(&codes1, 4ull * n));
+        LB_CHECK(cudaMalloc(&idx0, 4ull * n));   LB_CHECK(cudaMalloc(&idx1, 4ull * n));
+        LB_CHECK(cudaMalloc(&ws, rs::workspace_bytes(n)));
+        LB_CHECK(cudaMalloc(&out.geom, 16ull * n)); LB_CHECK(cudaMalloc(&out.mat, 16ull * n));
+        LB_CHECK(cudaMalloc(&out.type, n)); LB_CHECK(cudaMalloc(&out.orig, 4ull * n));
+        LB_CHECK(cudaMalloc(&leaf_lo, 16ull * n)); LB_CHECK(cudaMalloc(&leaf_hi, 16ull * n));
+        LB_CHECK(cudaMalloc(&kn, sizeof(KarrasNode) * (size_t)(ni + 1)));
+        LB_CHECK(cudaMalloc(&ilo, 16ull * (ni + 1))); LB_CHECK(cudaMalloc(&ihi, 16ull * (ni + 1)));
+        LB_CHECK(cudaMalloc(&parent_i, 4ull * (ni + 1))); LB_CHECK(cudaMalloc(&parent_l, 4ull * n));
+        LB_CHECK(cudaMalloc(&arrivals, 4ull * (ni + 1)));
+        LB_CHECK(cudaMalloc(&kept, 4ull * (ni + 1))); LB_CHECK(cudaMalloc(&rank, 4ull * (ni + 1)));
+        LB_CHECK(cudaMalloc(&sums, 4ull * (nb + 2)));
+
+        const uint32_t init[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
+        LB_CHECK(cudaMemcpyAsync(bounds, init, sizeof(init), cudaMemcpyHostToDevice, stream));
+        LB_CHECK(cudaMemsetAsync(arrivals, 0, 4ull * (ni + 1), stream));
+        LB_CHECK(cudaMemsetAsync(rank, 0, 4ull * (ni + 1), stream));
+
+        const uint32_t red_blocks = (uint32_t)std::min<uint64_t>((uint64_t)num_sms * 8ull, blocks_for(n));
+        k_centroid_bounds<<<red_blocks, kBlock, 0, stream>>>(d_spheres, n, bounds);
+        k_morton<<<blocks_for(n), kBlock, 0, stream>>>(d_spheres, n, bounds, codes0, idx0);
+        launched += 2;
+        const int which = rs::sort_pairs(codes0, idx0, codes1, idx1, n, 30, ws, stream, num_sms, &launched);
+        uint32_t* codes = which ? codes1 : codes0;
+        uint32_t* idx = which ? idx1 : idx0;
+        k_gather<<<blocks_for(n), kBlock, 0, stream>>>(d_spheres, idx, n, pad_rel, out.geom, out.mat, out.type, out.orig, leaf_lo, leaf_hi);
+        launched += 1;
+        if (ni > 0) {
+            k_karras<<<blocks_for(ni), kBlock, 0, stream>>>(codes, n, kn, parent_i, parent_l);
+            k_refit<<<blocks_for(n), kBlock, 0, stream>>>(n, kn, parent_i, parent_l, leaf_lo, leaf_hi, ilo, ihi, arrivals);
+            k_mark_kept<<<blocks_for(ni), kBlock, 0, stream>>>(kn, ni, leaf_size, kept);
+            k_scan_block_sums<<<nb, kBlock, 0, stream>>>(kept, ni, sums);
+            k_scan_sums<<<1, kBlock, 0, stream>>>(sums, nb);
+            k_scan_final<<<nb, kBlock, 0, stream>>>(kept, ni, sums, rank);
+            launched += 6;
+        }
+        uint32_t total_kept = 0;
+        if (ni > 0) LB_CHECK(cudaMemcpyAsync(&total_kept, sums + nb, 4, cudaMemcpyDeviceToHost, stream));
+        LB_CHECK(cudaStreamSynchronize(stream));
+        out.num_nodes = 2ull + 2ull * total_kept;
+        LB_CHECK(cudaMalloc(&out.nodes, out.num_nodes * 2 * sizeof(float4)));
+        k_pack<<<blocks_for(n), kBlock, 0, stream>>>(n, kn, rank, ilo, ihi, leaf_lo, leaf_hi, leaf_size, out.nodes);
+        launched += 1;
+        uint32_t root_link = 0;
+        // root link = nodes[2].w (node 1, first float4)
+        LB_CHECK(cudaMemcpyAsync(&root_link, reinterpret_cast<const char*>(out.nodes) + 2 * sizeof(float4) + 12, 4, cudaMemcpyDeviceToHost, stream));
+        LB_CHECK(cudaMemcpyAsync(out.bounds_lo, reinterpret_cast<const char*>(out.nodes) + 2 * sizeof(float4), 12, cudaMemcpyDeviceToHost, stream));
+        LB_CHECK(cudaMemcpyAsync(out.bounds_hi, reinterpret_cast<const char*>(out.nodes) + 3 * sizeof(float4), 12, cudaMemcpyDeviceToHost, stream));
+        LB_CHECK(cudaStreamSynchronize(stream));
+        LB_CHECK(cudaGetLastError());
+        out.root_link = root_link;
+        // keep the sorted Morton codes for vn_morton_codes()
+        out.codes = codes == codes0 ? codes0 : codes1;
+        if (codes == codes0) codes0 = nullptr; else codes1 = nullptr;
+    }
+    if (launches) *launches += launched;
+    cudaFree(bounds); cudaFree(codes0); cudaFree(codes1); cudaFree(idx0); cudaFree(idx1); cudaFree(ws); cudaFree(leaf_lo); cudaFree(leaf_hi);
+    cudaFree(kn); cudaFree(ilo); cudaFree(ihi); cudaFree(parent_i); cudaFree(parent_l); cudaFree(arrivals); cudaFree(kept); cudaFree(rank); cudaFree(sums);
+    return 0;
+fail:
+    cudaFree(bounds); cudaFree(codes0); cudaFree(codes1); cudaFree(idx0); cudaFree(idx1); cudaFree(ws); cudaFree(leaf_lo); cudaFree(leaf_hi);
+    cudaFree(kn); cudaFree(ilo); cudaFree(ihi); cudaFree(parent_i); cudaFree(parent_l); cudaFree(arrivals); cudaFree(kept); cudaFree(rank); cudaFree(sums);
+    lbvh_free(out);
+    return -2;
+}
+
+int radix_sort_pairs_device(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, uint32_t n, int key_bits, int num_sms,
+                            cudaStream_t stream, uint32_t* launches, std::string& err) {
+    void* ws = nullptr;
+    cudaError_t e = cudaMalloc(&ws, rs::workspace_bytes(n ? n : 1));
+    if (e != cudaSuccess) { err = std::string("cudaMalloc(sort workspace): ") + cudaGetErrorString(e); return -1; }
+    const int which = rs::sort_pairs(k0, v0, k1, v1, n, key_bits, ws, stream, num_sms, launches);
+    e = cudaStreamSynchronize(stream);
+    cudaFree(ws);
+    if (e != cudaSuccess) { err = std::string("radix sort: ") + cudaGetErrorString(e); return -1; }
+    return which;
+}
+
+}  // namespace vn

@@ -1,0 +1,39 @@
+// lbvh.h -- internal interface between the C ABI (vn_api.cu) and the LBVH builder (lbvh.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <string>
+
+#include "../../include/venusaur_b200.h"
+
+namespace vn {
+
+// Device-resident scene in traversal order (Morton-sorted), as the trace kernels read it.
+struct LbvhScene {
+    uint64_t n = 0;
+    float4* geom = nullptr;      // {cx, cy, cz, r}
+    float4* mat = nullptr;       // {albedo.xyz, fuzz} or {ir, 0, 0, 0}
+    uint8_t* type = nullptr;     // material.h:9-14
+    uint32_t* orig = nullptr;    // sorted position -> index in the caller's sphere array
+    uint32_t* codes = nullptr;   // sorted Morton codes
+    float4* nodes = nullptr;     // num_nodes x 32 B (vn_node32)
+    uint64_t num_nodes = 0;
+    uint32_t root_link = 0xFFFFFFFFu;
+    uint32_t leaf_size = 0;
+    float bounds_lo[3] = {0, 0, 0}, bounds_hi[3] = {0, 0, 0};
+};
+
+void lbvh_free(LbvhScene& sc);
+
+// Builds the packed LBVH for n spheres already resident on the device.  Returns 0 or a negative status with `err` set.
+int lbvh_build(const vn_sphere* d_spheres, uint64_t n, uint32_t leaf_size, float pad_rel, int num_sms, cudaStream_t stream,
+               LbvhScene& out, uint32_t* launches, std::string& err);
+
+// Onesweep sort of device (key, value) pairs; returns 0/1 = which buffer pair holds the result, or -1.
+int radix_sort_pairs_device(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, uint32_t n, int key_bits, int num_sms,
+                            cudaStream_t stream, uint32_t* launches, std::string& err);
+
+}  // namespace vn

@@ -1,0 +1,310 @@
+// path_kernels.cu -- the persistent-thread path kernel, the accumulate/tonemap kernels and the unit-test kernels.
+// Compiled twice (see kernels.h): -DVN_EXACT=1 -fmad=false -> namespace vn::exact, -DVN_EXACT=0 -> vn::fast.
+//
+// k_render_persistent replaces the whole OptiX launch of Renderer::Draw (Renderer.h:75): __raygen__rg,
+// optixTrace + __intersection__hit_sphere, the three closest-hit programs and __miss__ms (RayTracer.cu:163-450).
+//
+// Design (B200: 148 SMs, 227 KB smem, no RT cores):
+//   * one resident CTA wave (grid = SMs x occupancy); every lane owns one pixel at a time and walks its spp samples
+//     in order (so the per-pixel RNG chain of RayTracer.cu:169-183 and the float summation order are the
+//     reference's); when its pixel is done the lane takes the next pixel from a global ticket (warp-aggregated
+//     atomic), so lanes never idle on finished paths (path regeneration).
+//   * the whole scene (32-byte BVH nodes, sphere geometry, materials) is staged once per CTA into shared memory when
+//     it fits (RTIOW: ~35 KB), so traversal never leaves the SM: LDS.128 node fetches, no L2/HBM traffic at all;
+//     larger scenes are traversed straight from L2/HBM through the same code (128-bit __ldg loads).
+//   * accumulate + sRGB quantise are fused at the end of each pixel (RayTracer.cu:206-216).
+#include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
+
+#include <algorithm>
+
+#include "kernels.h"
+
+namespace cg = cooperative_groups;
+
+#if VN_EXACT
+#define VN_NS exact
+#else
+#define VN_NS fast
+#endif
+
+namespace vn {
+
+#if VN_EXACT
+size_t scene_smem_bytes(uint32_t num_nodes, uint32_t num_spheres) {
+    return (size_t)num_nodes * 32 + (size_t)num_spheres * 32 + (((size_t)num_spheres + 15) & ~(size_t)15);
+}
+#endif
+
+namespace VN_NS {
+
+namespace {
+
+__device__ __forceinline__ uint32_t fetch_work(uint32_t* counter) {
+    cg::coalesced_group g = cg::coalesced_threads();
+    uint32_t base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(counter, g.size());
+    base = g.shfl(base, 0);
+    return base + g.thread_rank();
+}
+
+__device__ __forceinline__ void finish_pixel(const RenderLaunch& p, uint32_t pix, f3 sum) {
+    f3 mean = sum * p.inv_spp;                                   // RayTracer.cu:206 (vec_math.h:483-487)
+    if (p.blend_mode == kBlendLerp) {                            // RayTracer.cu:208-213
+        const float4 prev = p.accum[pix];
+        mean = lerp3(mk3(prev.x, prev.y, prev.z), mean, p.blend_a);
+    } else if (p.blend_mode == kBlendSum) {
+        const float4 prev = p.accum[pix];
+        mean = mk3(prev.x, prev.y, prev.z) + mean;
+    }
+    p.accum[pix] = make_float4(mean.x, mean.y, mean.z, 1.0f);    // RayTracer.cu:215
+    if (p.image) p.image[pix] = make_color_u32(mean);            // RayTracer.cu:216
+}
+
+template <bool kSmem, bool kCount>
+__global__ void __launch_bounds__(256) k_render_persistent(const __grid_constant__ RenderLaunch p) {
+    extern __shared__ float4 s_scene[];
+    SceneView sc;
+    if (kSmem) {
+        // stage nodes | geom | mat | type into shared memory with 128-bit copies
+        float4* s_nodes = s_scene;
+        float4* s_geom = s_nodes + 2 * (size_t)p.num_nodes;
+        float4* s_mat = s_geom + p.num_spheres;
+        uint8_t* s_type = reinterpret_cast<uint8_t*>(s_mat + p.num_spheres);
+        for (uint32_t i = threadIdx.x; i < 2 * p.num_nodes; i += blockDim.x) s_nodes[i] = p.nodes[i];
+        for (uint32_t i = threadIdx.x; i < p.num_spheres; i += blockDim.x) { s_geom[i] = p.geom[i]; s_mat[i] = p.mat[i]; }
+        for (uint32_t i = threadIdx.x; i < p.num_spheres; i += blockDim.x) s_type[i] = p.type[i];
+        __syncthreads();
+        sc.nodes = s_nodes; sc.geom = s_geom; sc.mat = s_mat; sc.type = s_type;
+    } else {
+        sc.nodes = p.nodes; sc.geom = p.geom; sc.mat = p.mat; sc.type = p.type;
+    }
+    sc.root_link = p.root_link;
+
+    uint32_t pix = 0, px = 0, py = 0, cam_seed = 0, s_left = 0;
+    bool has_pixel = false, active = false;
+    f3 sum = mk3(0.0f);
+    PathState st;
+    st.o = st.d = st.thr = mk3(0.0f); st.seed = 0; st.depth = 0;
+    uint32_t n_seg = 0, n_path = 0;
+    TraceCounters cnt{0u, 0u};
+    unsigned long long n_nodes = 0, n_sph = 0;
+
+    for (;;) {
+        if (!active) {
+            if (has_pixel && s_left == 0u) { finish_pixel(p, pix, sum); has_pixel = false; }
+            if (!has_pixel) {
+                bool got = false;
+                for (;;) {
+                    const uint32_t w = fetch_work(p.work_counter);
+                    if (w >= p.total_work) break;
+                    const uint32_t tile = w >> 5, in = w & 31u;
+                    const uint32_t ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+                    px = tx * 8u + (in & 7u);
+                    py = p.row_begin + ty * 4u + (in >> 3);
+                    if (px < p.width && py < p.row_end) { got = true; break; }
+                }
+                if (!got) break;                                  // no pixels left: this lane retires
+                pix = py * p.width + px;
+                cam_seed = tea4(pix, p.subframe_index);           // RayTracer.cu:169
+                sum = mk3(0.0f);
+                s_left = p.spp;
+                has_pixel = true;
+            }
+            camera_ray(p.cam, px, py, cam_seed, st.o, st.d);      // RayTracer.cu:173-177
+            st.thr = mk3(1.0f);
+            st.seed = cam_seed;                                   // prd.seed = seed: a copy (RayTracer.cu:183)
+            st.depth = (int)p.max_depth - 1;                      // RayTracer.cu:184
+            s_left -= 1u;
+            active = true;
+            n_path += 1u;
+        }
+        float t;
+        int prim;
+        closest_hit<kCount>(sc.nodes, sc.geom, sc.root_link, st.o, st.d, t, prim, cnt);
+        n_seg += 1u;
+        if (kCount) { n_nodes += cnt.nodes; n_sph += cnt.spheres; cnt.nodes = 0; cnt.spheres = 0; }
+        f3 result;
+        if (!shade_segment(sc, st, t, prim, result)) {
+            sum = sum + result;                                   // pixel_color += prd.attenuation (RayTracer.cu:203)
+            active = false;
+        }
+    }
+    // per-lane totals -> global counters
+    {
+        unsigned long long seg = n_seg, path = n_path;
+        cg::coalesced_group g = cg::coalesced_threads();
+        seg = cg::reduce(g, seg, cg::plus<unsigned long long>());
+        path = cg::reduce(g, path, cg::plus<unsigned long long>());
+        if (kCount) {
+            n_nodes = cg::reduce(g, n_nodes, cg::plus<unsigned long long>());
+            n_sph = cg::reduce(g, n_sph, cg::plus<unsigned long long>());
+        }
+        if (g.thread_rank() == 0) {
+            atomicAdd(&p.counters[0], seg);
+            atomicAdd(&p.counters[1], path);
+            if (kCount) { atomicAdd(&p.counters[2], n_nodes); atomicAdd(&p.counters[3], n_sph); }
+        }
+    }
+}
+
+// Kernel (3) of the north star when used stand-alone: image = make_color(accum * scale).  One pixel per thread:
+// a warp reads 512 contiguous bytes of float4 and writes 128 contiguous bytes of uchar4.
+__global__ void __launch_bounds__(256) k_tonemap(const float4* __restrict__ accum, float scale, uint32_t* __restrict__ image, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float4 a = accum[i];
+        f3 c = mk3(a.x, a.y, a.z);
+        if (scale != 1.0f) c = c * scale;
+        image[i] = make_color_u32(c);
+    }
+}
+
+struct PeerList { const float4* p[kMaxPeers]; };
+
+// Fused cross-GPU reduce + tonemap: each GPU owns a slice of pixels, loads that slice from every peer's partial-sum
+// buffer over NVLink (peer-mapped pointers), adds them in rank order (deterministic), writes the reduced float4
+// into its own accum and the uchar4 pixels into the image.  Replaces ncclReduce + a separate tonemap launch.
+__global__ void __launch_bounds__(256) k_reduce_tonemap_peers(const PeerList peers, uint32_t n_peers, float scale, uint64_t begin, uint64_t end,
+                                                             float4* __restrict__ accum_out, uint32_t* __restrict__ image) {
+    for (uint64_t i = begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (uint64_t)gridDim.x * blockDim.x) {
+        f3 s = mk3(0.0f);
+        for (uint32_t r = 0; r < n_peers; r++) {
+            const float4 a = __ldcg(&peers.p[r][i]);
+            s = s + mk3(a.x, a.y, a.z);
+        }
+        accum_out[i] = make_float4(s.x, s.y, s.z, 1.0f);
+        if (image) image[i] = make_color_u32(scale != 1.0f ? s * scale : s);
+    }
+}
+
+// ---- unit-test kernels
+__global__ void k_test_rng(const uint32_t* __restrict__ v0, const uint32_t* __restrict__ v1, uint64_t n, uint32_t n_draws,
+                           uint32_t* __restrict__ seeds, uint32_t* __restrict__ lcg_out, float* __restrict__ rnd_out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s = tea4(v0[i], v1[i]);
+    seeds[i] = s;
+    uint32_t s2 = s;
+    for (uint32_t k = 0; k < n_draws; k++) {
+        lcg_out[i * n_draws + k] = lcg(s);
+        rnd_out[i * n_draws + k] = rnd(s2);
+    }
+}
+
+__global__ void k_trace_rays(const float4* __restrict__ nodes, const float4* __restrict__ geom, uint32_t root_link, const float* __restrict__ o,
+                             const float* __restrict__ d, uint64_t n, float* __restrict__ t_out, int32_t* __restrict__ prim_out,
+                             const uint32_t* __restrict__ orig) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float t;
+    int prim;
+    TraceCounters cnt{0u, 0u};
+    closest_hit<false>(nodes, geom, root_link, mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), t, prim, cnt);
+    t_out[i] = prim >= 0 ? t : -1.0f;
+    prim_out[i] = prim >= 0 ? (int32_t)orig[prim] : -1;
+}
+
+__global__ void k_make_color(const float* __restrict__ rgb, uint64_t n, uint32_t* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = make_color_u32(mk3(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]));
+}
+
+__global__ void k_scatter(uint32_t type, float4 mat, const float* __restrict__ dirs, const float* __restrict__ normals,
+                          const uint8_t* __restrict__ front, const uint32_t* __restrict__ seeds, uint64_t n, float* __restrict__ dirs_out,
+                          uint8_t* __restrict__ scattered, uint32_t* __restrict__ seeds_out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const f3 d = mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
+    const f3 nrm = mk3(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]);
+    uint32_t seed = seeds[i];
+    f3 out = mk3(0.0f);
+    bool ok = true;
+    if (type == 0u) out = scatter_lambertian(nrm, seed);
+    else if (type == 1u) ok = scatter_metal(d, nrm, mat.w, seed, out);
+    else out = scatter_dielectric(d, nrm, front[i] != 0, mat.x, seed);
+    dirs_out[3 * i] = out.x; dirs_out[3 * i + 1] = out.y; dirs_out[3 * i + 2] = out.z;
+    scattered[i] = ok ? 1 : 0;
+    seeds_out[i] = seed;
+}
+
+template <typename K>
+cudaError_t set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return cudaSuccess;
+}
+
+inline uint32_t grid_for(uint64_t n, int threads) { return (uint32_t)((n + threads - 1) / threads); }
+
+}  // namespace
+
+int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool count) {
+    int nb = 0;
+    cudaError_t e;
+    if (scene_in_smem) {
+        if (count) { set_smem(k_render_persistent<true, true>, smem_bytes); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_render_persistent<true, true>, threads, smem_bytes); }
+        else       { set_smem(k_render_persistent<true, false>, smem_bytes); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_render_persistent<true, false>, threads, smem_bytes); }
+    } else {
+        if (count) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_render_persistent<false, true>, threads, 0);
+        else       e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_render_persistent<false, false>, threads, 0);
+    }
+    return e == cudaSuccess ? nb : -1;
+}
+
+cudaError_t launch_render_persistent(const RenderLaunch& p, const KernelConfig& cfg, cudaStream_t stream) {
+    cudaError_t e = cudaSuccess;
+    if (cfg.scene_in_smem) {
+        if (cfg.count) { e = set_smem(k_render_persistent<true, true>, cfg.smem_bytes); if (e) return e; k_render_persistent<true, true><<<cfg.blocks, cfg.threads, cfg.smem_bytes, stream>>>(p); }
+        else           { e = set_smem(k_render_persistent<true, false>, cfg.smem_bytes); if (e) return e; k_render_persistent<true, false><<<cfg.blocks, cfg.threads, cfg.smem_bytes, stream>>>(p); }
+    } else {
+        if (cfg.count) k_render_persistent<false, true><<<cfg.blocks, cfg.threads, 0, stream>>>(p);
+        else           k_render_persistent<false, false><<<cfg.blocks, cfg.threads, 0, stream>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tonemap(const float4* accum, float scale, uint32_t* image, uint64_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    k_tonemap<<<(uint32_t)std::min<uint64_t>(grid_for(n, 256), 148u * 16u), 256, 0, stream>>>(accum, scale, image, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_tonemap_peers(const float4* const* peers, uint32_t n_peers, float scale, uint64_t begin, uint64_t end,
+                                        float4* accum_out, uint32_t* image, cudaStream_t stream) {
+    if (end <= begin) return cudaSuccess;
+    if (n_peers > (uint32_t)kMaxPeers) return cudaErrorInvalidValue;
+    PeerList pl;
+    for (int i = 0; i < kMaxPeers; i++) pl.p[i] = i < (int)n_peers ? peers[i] : nullptr;
+    k_reduce_tonemap_peers<<<(uint32_t)std::min<uint64_t>(grid_for(end - begin, 256), 148u * 16u), 256, 0, stream>>>(pl, n_peers, scale, begin, end, accum_out, image);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_test_rng(const uint32_t* v0, const uint32_t* v1, uint64_t n, uint32_t n_draws, uint32_t* seeds, uint32_t* lcg_out,
+                            float* rnd_out, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    k_test_rng<<<grid_for(n, 128), 128, 0, stream>>>(v0, v1, n, n_draws, seeds, lcg_out, rnd_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_trace_rays(const RenderLaunch& scene, const float* o, const float* d, uint64_t n, float* t_out, int32_t* prim_out,
+                              const uint32_t* orig, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    k_trace_rays<<<grid_for(n, 128), 128, 0, stream>>>(scene.nodes, scene.geom, scene.root_link, o, d, n, t_out, prim_out, orig);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_make_color(const float* rgb, uint64_t n, uint32_t* out, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    k_make_color<<<grid_for(n, 128), 128, 0, stream>>>(rgb, n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scatter(uint32_t type, float4 mat, const float* dirs, const float* normals, const uint8_t* front, const uint32_t* seeds,
+                           uint64_t n, float* dirs_out, uint8_t* scattered, uint32_t* seeds_out, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    k_scatter<<<grid_for(n, 128), 128, 0, stream>>>(type, mat, dirs, normals, front, seeds, n, dirs_out, scattered, seeds_out);
+    return cudaGetLastError();
+}
+
+}  // namespace VN_NS
+}  // namespace vn

@@ -1,0 +1,745 @@
+// vn_api.cu -- implementation of the C ABI declared in include/venusaur_b200.h.
+// Host-side plumbing only: device memory, one stream per handle, CUDA-event timing, launch configuration.
+// All compute happens in the kernels of lbvh.cu / path_kernels.cu / wavefront.cu; there is no CPU path.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/venusaur/Camera.h"
+#include "../../include/venusaur/Scene.h"
+#include "kernels.h"
+#include "lbvh.h"
+
+using namespace vn;
+
+#include <cstddef>
+static_assert(sizeof(vn_sphere) == 36 && sizeof(vn_node32) == 32, "ABI");
+static_assert(sizeof(vn_params) == 96 && offsetof(vn_params, origin) == 32 && offsetof(vn_params, flags) == 92, "ABI");
+static_assert(sizeof(vn_stats) == 64 && sizeof(vn_bvh_info) == 48, "ABI");
+
+struct vn_context {
+    int device = 0;
+    int num_sms = 0;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::string last_error;
+
+    vn_sphere* d_spheres = nullptr;
+    uint64_t n_spheres = 0;
+    bool have_spheres = false, bvh_valid = false;
+    LbvhScene scene;
+
+    uint32_t width = 0, height = 0;
+    float4* accum_own = nullptr;
+    float4* accum = nullptr;          // own or external
+    uint32_t* image_tmp = nullptr;    // device staging for VN_IMAGE_HOST
+    uint64_t image_tmp_pixels = 0;
+
+    unsigned long long* d_counters = nullptr;   // 4 x u64 + work ticket (u32) at +32 bytes
+    unsigned long long* h_counters = nullptr;   // pinned
+
+    WavefrontBuffers wf;
+    uint64_t wf_sample_floats_ = 0;
+
+    // options
+    uint32_t leaf_size = 2;
+    float aabb_pad = 0.01f;
+    int threads = 256;
+    int blocks_per_sm = 0;            // 0 = occupancy
+    size_t smem_scene_limit = 100 * 1024;
+    uint32_t wavefront_slots = 1u << 21;
+
+    vn_stats stats{};
+    bool stats_pending = false;      // an async vn_render whose counters have not been folded into stats yet
+};
+
+namespace {
+
+std::mutex g_err_mutex;
+std::string g_create_error;
+
+void set_global_error(const std::string& s) {
+    std::lock_guard<std::mutex> lk(g_err_mutex);
+    g_create_error = s;
+}
+
+int fail(vn_context* c, int status, const std::string& msg) {
+    if (c) c->last_error = msg;
+    set_global_error(msg);
+    return status;
+}
+
+#define VN_CUDA(c, call)                                                                                      \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess)                                                                                \
+            return fail((c), e_ == cudaErrorMemoryAllocation ? VN_ERR_OOM : VN_ERR_CUDA,                      \
+                        std::string("CUDA call (") + #call + ") failed with error: '" + cudaGetErrorString(e_) + \
+                            "' (" + __FILE__ + ":" + std::to_string(__LINE__) + ")");                         \
+    } while (0)
+
+#define VN_REQUIRE(c, cond, msg) \
+    do { if (!(cond)) return fail((c), VN_ERR_INVALID, std::string(msg)); } while (0)
+
+inline f3 to_f3(const float* p) { return mk3(p[0], p[1], p[2]); }
+
+void free_wavefront(WavefrontBuffers& w) {
+    cudaFree(w.slab);
+    cudaFree(w.counts);
+    cudaFree(w.sample_rgb);
+    w = WavefrontBuffers();
+}
+
+int fill_launch(vn_context* c, const vn_params* p, RenderLaunch& L) {
+    memset(&L, 0, sizeof(L));
+    L.cam.origin = to_f3(p->origin);
+    L.cam.u = to_f3(p->u);
+    L.cam.v = to_f3(p->v);
+    L.cam.w = to_f3(p->w);
+    // loop invariants of get_ray (RayTracer.cu:155-156); host IEEE float == the device's exact build
+    L.cam.u_unit = normalize(L.cam.u);
+    L.cam.v_unit = normalize(L.cam.v);
+    L.cam.lens_radius = p->lens_radius;
+    L.cam.wm1 = (float)(p->width - 1u);
+    L.cam.hm1 = (float)(p->height - 1u);
+    L.cam.inv_wm1 = 1.0f / L.cam.wm1;
+    L.cam.inv_hm1 = 1.0f / L.cam.hm1;
+    L.width = p->width; L.height = p->height;
+    L.spp = p->samples_per_pixel;
+    L.subframe_index = p->subframe_index;
+    L.max_depth = p->max_depth;
+    L.row_begin = p->row_begin; L.row_end = p->row_end;
+    if (L.row_begin == 0 && L.row_end == 0) L.row_end = p->height;
+    if (p->flags & VN_ACCUM_SUM) { L.blend_mode = kBlendSum; L.blend_a = 0.0f; }
+    else if (p->accum_count > 0) { L.blend_mode = kBlendLerp; L.blend_a = 1.0f / (float)(p->accum_count + 1u); }   // RayTracer.cu:210
+    else { L.blend_mode = kBlendOverwrite; L.blend_a = 1.0f; }
+    L.inv_spp = 1.0f / (float)p->samples_per_pixel;                                                                // vec_math.h:483-487
+    L.accum = c->accum;
+    L.nodes = c->scene.nodes; L.geom = c->scene.geom; L.mat = c->scene.mat; L.type = c->scene.type;
+    L.root_link = c->scene.root_link;
+    L.num_nodes = (uint32_t)c->scene.num_nodes;
+    L.num_spheres = (uint32_t)c->scene.n;
+    L.counters = c->d_counters;
+    L.work_counter = reinterpret_cast<uint32_t*>(c->d_counters + 4);
+    const uint32_t rows = L.row_end - L.row_begin;
+    L.tiles_x = (p->width + 7u) / 8u;
+    L.total_work = L.tiles_x * ((rows + 3u) / 4u) * 32u;
+    return VN_OK;
+}
+
+bool scene_fits_smem(const vn_context* c) {
+    const size_t need = scene_smem_bytes((uint32_t)c->scene.num_nodes, (uint32_t)c->scene.n);
+    return c->scene.n > 0 && need <= c->smem_scene_limit && need + 1024 <= c->smem_optin;
+}
+
+}  // namespace
+
+// scratch device buffer for the unit-level test entry points
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 4); }
+    template <typename T> T* as() { return static_cast<T*>(p); }
+};
+}  // namespace
+
+extern "C" {
+
+const char* vn_version(void) { return "venusaur_b200 0.1 (sm_100a)"; }
+
+int vn_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* vn_last_error(vn_handle h) {
+    if (h) return h->last_error.c_str();
+    static thread_local std::string copy;
+    std::lock_guard<std::mutex> lk(g_err_mutex);
+    copy = g_create_error;
+    return copy.c_str();
+}
+
+int vn_create(int device, vn_handle* out) {
+    if (!out) return fail(nullptr, VN_ERR_INVALID, "vn_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(nullptr, VN_ERR_NO_DEVICE, std::string("vn_create: no CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                                                   "); venusaur_b200 has no CPU path");
+    }
+    if (device < 0 || device >= n) return fail(nullptr, VN_ERR_INVALID, "vn_create: device index out of range");
+    vn_context* c = new vn_context();
+    c->device = device;
+    VN_CUDA(c, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    VN_CUDA(c, cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        std::string msg = std::string("vn_create: device '") + prop.name + "' is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                          "; this library contains sm_100a code only";
+        delete c;
+        return fail(nullptr, VN_ERR_NO_DEVICE, msg);
+    }
+    c->num_sms = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    VN_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto& ev : c->ev) VN_CUDA(c, cudaEventCreate(&ev));
+    VN_CUDA(c, cudaMalloc(&c->d_counters, 64));
+    VN_CUDA(c, cudaMemset(c->d_counters, 0, 64));
+    VN_CUDA(c, cudaHostAlloc(&c->h_counters, 64, cudaHostAllocDefault));
+    *out = c;
+    return VN_OK;
+}
+
+void vn_destroy(vn_handle c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    lbvh_free(c->scene);
+    free_wavefront(c->wf); c->wf_sample_floats_ = 0;
+    cudaFree(c->d_spheres); cudaFree(c->accum_own); cudaFree(c->image_tmp); cudaFree(c->d_counters);
+    cudaFreeHost(c->h_counters);
+    for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+void* vn_stream(vn_handle c) { return c ? (void*)c->stream : nullptr; }
+
+int vn_set_option(vn_handle c, const char* name, double value) {
+    VN_REQUIRE(c, c && name, "vn_set_option: NULL argument");
+    const std::string k(name);
+    if (k == "leaf_size") { VN_REQUIRE(c, value >= 1 && value <= 8, "leaf_size must be in [1,8]"); c->leaf_size = (uint32_t)value; c->bvh_valid = false; }
+    else if (k == "aabb_pad") { VN_REQUIRE(c, value >= 0 && value < 1, "aabb_pad must be in [0,1)"); c->aabb_pad = (float)value; c->bvh_valid = false; }
+    else if (k == "threads") { VN_REQUIRE(c, value == 64 || value == 128 || value == 256, "threads must be 64, 128 or 256"); c->threads = (int)value; }
+    else if (k == "blocks_per_sm") { VN_REQUIRE(c, value >= 0 && value <= 32, "blocks_per_sm must be in [0,32]"); c->blocks_per_sm = (int)value; }
+    else if (k == "smem_scene_limit") { VN_REQUIRE(c, value >= 0, "smem_scene_limit must be >= 0"); c->smem_scene_limit = (size_t)value; }
+    else if (k == "wavefront_slots") { VN_REQUIRE(c, value >= 1024 && value <= (double)(1u << 26), "wavefront_slots out of range"); c->wavefront_slots = (uint32_t)value; free_wavefront(c->wf); c->wf_sample_floats_ = 0; }
+    else return fail(c, VN_ERR_INVALID, "vn_set_option: unknown option '" + k + "'");
+    return VN_OK;
+}
+
+int vn_set_spheres(vn_handle c, const vn_sphere* host_spheres, uint64_t n) {
+    VN_REQUIRE(c, c, "vn_set_spheres: NULL handle");
+    VN_REQUIRE(c, n == 0 || host_spheres, "vn_set_spheres: NULL spheres");
+    for (uint64_t i = 0; i < n; i++) VN_REQUIRE(c, host_spheres[i].type <= 2u, "vn_set_spheres: material type must be 0, 1 or 2");
+    VN_CUDA(c, cudaSetDevice(c->device));
+    cudaFree(c->d_spheres);
+    c->d_spheres = nullptr;
+    c->bvh_valid = false;
+    c->have_spheres = false;
+    if (n) {
+        VN_CUDA(c, cudaMalloc(&c->d_spheres, n * sizeof(vn_sphere)));
+        VN_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+        VN_CUDA(c, cudaMemcpyAsync(c->d_spheres, host_spheres, n * sizeof(vn_sphere), cudaMemcpyHostToDevice, c->stream));
+        VN_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+        VN_CUDA(c, cudaStreamSynchronize(c->stream));
+        VN_CUDA(c, cudaEventElapsedTime(&c->stats.ms_upload, c->ev[0], c->ev[1]));
+    }
+    c->n_spheres = n;
+    c->have_spheres = true;
+    return VN_OK;
+}
+
+int vn_build_bvh(vn_handle c) {
+    VN_REQUIRE(c, c, "vn_build_bvh: NULL handle");
+    VN_REQUIRE(c, c->have_spheres, "vn_build_bvh: call vn_set_spheres first");
+    VN_CUDA(c, cudaSetDevice(c->device));
+    std::string err;
+    uint32_t launches = 0;
+    VN_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    const int rc = lbvh_build(c->d_spheres, c->n_spheres, c->leaf_size, c->aabb_pad, c->num_sms, c->stream, c->scene, &launches, err);
+    if (rc != 0) return fail(c, rc == -1 ? VN_ERR_INVALID : VN_ERR_CUDA, "vn_build_bvh: " + err);
+    VN_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    VN_CUDA(c, cudaStreamSynchronize(c->stream));
+    VN_CUDA(c, cudaEventElapsedTime(&c->stats.ms_build, c->ev[0], c->ev[1]));
+    c->stats.kernel_launches_total += launches;
+    c->bvh_valid = true;
+    return VN_OK;
+}
+
+int vn_get_bvh_info(vn_handle c, vn_bvh_info* out) {
+    VN_REQUIRE(c, c && out, "vn_get_bvh_info: NULL argument");
+    VN_REQUIRE(c, c->bvh_valid, "vn_get_bvh_info: no BVH (call vn_build_bvh)");
+    memset(out, 0, sizeof(*out));
+    out->num_spheres = c->scene.n;
+    out->num_nodes = c->scene.num_nodes;
+    out->max_leaf_size = c->scene.leaf_size;
+    out->scene_in_smem = scene_fits_smem(c) ? 1u : 0u;
+    for (int a = 0; a < 3; a++) { out->bounds_lo[a] = c->scene.bounds_lo[a]; out->bounds_hi[a] = c->scene.bounds_hi[a]; }
+    return VN_OK;
+}
+
+int vn_read_bvh(vn_handle c, vn_node32* host_nodes, uint64_t cap_nodes, uint32_t* host_prim_order, uint64_t cap_prims) {
+    VN_REQUIRE(c, c, "vn_read_bvh: NULL handle");
+    VN_REQUIRE(c, c->bvh_valid, "vn_read_bvh: no BVH (call vn_build_bvh)");
+    VN_CUDA(c, cudaSetDevice(c->device));
+    if (host_nodes && c->scene.nodes)
+        VN_CUDA(c, cudaMemcpy(host_nodes, c->scene.nodes, std::min<uint64_t>(cap_nodes, c->scene.num_nodes) * 32, cudaMemcpyDeviceToHost));
+    if (host_prim_order && c->scene.orig)
+        VN_CUDA(c, cudaMemcpy(host_prim_order, c->scene.orig, std::min<uint64_t>(cap_prims, c->scene.n) * 4, cudaMemcpyDeviceToHost));
+    return VN_OK;
+}
+
+int vn_morton_codes(vn_handle c, uint32_t* codes_out, uint64_t cap) {
+    VN_REQUIRE(c, c && codes_out, "vn_morton_codes: NULL argument");
+    VN_REQUIRE(c, c->bvh_valid, "vn_morton_codes: no BVH (call vn_build_bvh)");
+    VN_CUDA(c, cudaSetDevice(c->device));
+    if (c->scene.codes) VN_CUDA(c, cudaMemcpy(codes_out, c->scene.codes, std::min<uint64_t>(cap, c->scene.n) * 4, cudaMemcpyDeviceToHost));
+    return VN_OK;
+}
+
+int vn_resize(vn_handle c, uint32_t width, uint32_t height) {
+    VN_REQUIRE(c, c, "vn_resize: NULL handle");
+    VN_REQUIRE(c, width >= 2 && height >= 2, "vn_resize: width and height must be >= 2 (the camera divides by width-1, RayTracer.cu:173)");
+    VN_REQUIRE(c, (uint64_t)width * height < (1ull << 31), "vn_resize: too many pixels");
+    VN_CUDA(c, cudaSetDevice(c->device));
+    if (width != c->width || height != c->height || !c->accum_own) {
+        VN_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->accum_own);
+        c->accum_own = nullptr;
+        VN_CUDA(c, cudaMalloc(&c->accum_own, (size_t)width * height * sizeof(float4)));
+        c->accum = c->accum_own;   // an external buffer does not survive a resize
+        c->width = width; c->height = height;
+    }
+    VN_CUDA(c, cudaMemsetAsync(c->accum, 0, (size_t)width * height * sizeof(float4), c->stream));
+    return VN_OK;
+}
+
+int vn_reset_accum(vn_handle c) {
+    VN_REQUIRE(c, c, "vn_reset_accum: NULL handle");
+    VN_REQUIRE(c, c->accum, "vn_reset_accum: no accumulation buffer (call vn_resize)");
+    VN_CUDA(c, cudaSetDevice(c->device));
+    VN_CUDA(c, cudaMemsetAsync(c->accum, 0, (size_t)c->width * c->height * sizeof(float4), c->stream));
+    return VN_OK;
+}
+
+int vn_set_accum_external(vn_handle c, void* dev_ptr) {
+    VN_REQUIRE(c, c, "vn_set_accum_external: NULL handle");
+    VN_REQUIRE(c, c->width && c->height, "vn_set_accum_external: call vn_resize first");
+    c->accum = dev_ptr ? static_cast<float4*>(dev_ptr) : c->accum_own;
+    return VN_OK;
+}
+
+int vn_accum_device_ptr(vn_handle c, void** dev_ptr) {
+    VN_REQUIRE(c, c && dev_ptr, "vn_accum_device_ptr: NULL argument");
+    VN_REQUIRE(c, c->accum, "vn_accum_device_ptr: no accumulation buffer (call vn_resize)");
+    *dev_ptr = c->accum;
+    return VN_OK;
+}
+
+int vn_read_accum(vn_handle c, float* host_rgba) {
+    VN_REQUIRE(c, c && host_rgba, "vn_read_accum: NULL argument");
+    VN_REQUIRE(c, c->accum, "vn_read_accum: no accumulation buffer");
+    VN_CUDA(c, cudaSetDevice(c->device));
+    VN_CUDA(c, cudaMemcpyAsync(host_rgba, c->accum, (size_t)c->width * c->height * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    VN_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VN_OK;
+}
+
+int vn_write_accum(vn_handle c, const float* host_rgba) {
+    VN_REQUIRE(c, c && host_rgba, "vn_write_accum: NULL argument");
+    VN_REQUIRE(c, c->accum, "vn_write_accum: no accumulation buffer");
+    VN_CUDA(c, cudaSetDevice(c->device));
+    VN_CUDA(c, cudaMemcpyAsync(c->accum, host_rgba, (size_t)c->width * c->height * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+    VN_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VN_OK;
+}
+
+static int collect_render_stats(vn_context* c) {
+    float ms = 0.0f;
+    VN_CUDA(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
+    c->stats.ms_render = ms;
+    c->stats.ms_trace = ms;
+    c->stats.segments = c->h_counters[0];
+    c->stats.paths = c->h_counters[1];
+    c->stats.node_visits = c->h_counters[2];
+    c->stats.sphere_tests = c->h_counters[3];
+    c->stats.segments_total += c->h_counters[0];
+    c->stats_pending = false;
+    return VN_OK;
+}
+
+int vn_synchronize(vn_handle c) {
+    VN_REQUIRE(c, c, "vn_synchronize: NULL handle");
+    VN_CUDA(c, cudaSetDevice(c->device));
+    VN_CUDA(c, cudaStreamSynchronize(c->stream));
+    VN_CUDA(c, cudaGetLastError());
+    if (c->stats_pending) return collect_render_stats(c);
+    return VN_OK;
+}
+
+static int ensure_image_tmp(vn_context* c, uint64_t pixels) {
+    if (c->image_tmp_pixels >= pixels && c->image_tmp) return VN_OK;
+    cudaFree(c->image_tmp);
+    c->image_tmp = nullptr;
+    c->image_tmp_pixels = 0;
+    VN_CUDA(c, cudaMalloc(&c->image_tmp, pixels * 4));
+    c->image_tmp_pixels = pixels;
+    return VN_OK;
+}
+
+static int ensure_wavefront(vn_context* c, uint64_t pixels, uint32_t spp) {
+    WavefrontBuffers& w = c->wf;
+    const uint32_t cap = c->wavefront_slots;
+    if (w.capacity != cap) {
+        free_wavefront(w);
+        c->wf_sample_floats_ = 0;
+        VN_CUDA(c, cudaMalloc(&w.slab, 4ull * cap * kWfArraysTotal));
+        uint32_t* base = static_cast<uint32_t*>(w.slab);
+        auto take = [&]() { uint32_t* p = base; base += cap; return p; };
+        for (int q = 0; q < 2; q++) {
+            WfState& s = w.st[q];
+            float** fl[] = {&s.ox, &s.oy, &s.oz, &s.dx, &s.dy, &s.dz, &s.tr, &s.tg, &s.tb};
+            for (float** p : fl) *p = reinterpret_cast<float*>(take());
+            s.seed = take();
+            s.ps = take();
+            s.depth = reinterpret_cast<int32_t*>(take());
+        }
+        w.hit_t = reinterpret_cast<float*>(take());
+        w.hit_prim = reinterpret_cast<int32_t*>(take());
+        for (int i = 0; i < 4; i++) w.mat_queue[i] = take();
+        VN_CUDA(c, cudaMalloc(&w.counts, 4 * kWfCountWords));
+        w.capacity = cap;
+    }
+    // per-(pixel, sample) radiance of one launch, summed in sample order by the accumulate kernel
+    const uint64_t need = pixels * spp * 3ull;
+    if (need > c->wf_sample_floats_) {
+        cudaFree(w.sample_rgb);
+        w.sample_rgb = nullptr;
+        c->wf_sample_floats_ = 0;
+        VN_CUDA(c, cudaMalloc(&w.sample_rgb, need * 4ull));
+        c->wf_sample_floats_ = need;
+    }
+    return VN_OK;
+}
+
+int vn_render(vn_handle c, const vn_params* p) {
+    VN_REQUIRE(c, c && p, "vn_render: NULL argument");
+    VN_REQUIRE(c, c->bvh_valid, "vn_render: no BVH (call vn_set_spheres + vn_build_bvh; Renderer::Init does both)");
+    VN_REQUIRE(c, p->width >= 2 && p->height >= 2, "vn_render: width and height must be >= 2");
+    VN_REQUIRE(c, p->samples_per_pixel >= 1, "vn_render: samples_per_pixel must be >= 1");
+    VN_REQUIRE(c, p->max_depth >= 1, "vn_render: max_depth must be >= 1");
+    VN_REQUIRE(c, p->row_begin <= p->row_end && p->row_end <= p->height, "vn_render: bad row range");
+    VN_CUDA(c, cudaSetDevice(c->device));
+    if (p->width != c->width || p->height != c->height || !c->accum) {
+        const int rc = vn_resize(c, p->width, p->height);
+        if (rc != VN_OK) return rc;
+    }
+    const uint64_t pixels = (uint64_t)p->width * p->height;
+    const bool want_image = p->image && !(p->flags & VN_NO_TONEMAP) && !(p->flags & VN_ACCUM_SUM);
+    const bool host_image = want_image && (p->flags & VN_IMAGE_HOST);
+    RenderLaunch L;
+    fill_launch(c, p, L);
+    if (want_image) {
+        if (host_image) { const int rc = ensure_image_tmp(c, pixels); if (rc != VN_OK) return rc; L.image = c->image_tmp; }
+        else L.image = static_cast<uint32_t*>(p->image);
+    }
+    const bool exact_build = (p->flags & VN_EXACT) != 0;
+    const bool count = (p->flags & VN_COUNTERS) != 0;
+    uint32_t launches = 0;
+
+    if (c->stats_pending) { const int rc = vn_synchronize(c); if (rc != VN_OK) return rc; }
+    VN_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 64, c->stream));
+    VN_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    if (p->flags & VN_WAVEFRONT) {
+        const uint32_t rows = L.row_end - L.row_begin;
+        const int rc = ensure_wavefront(c, (uint64_t)p->width * rows, p->samples_per_pixel);
+        if (rc != VN_OK) return rc;
+        VN_CUDA(c, exact_build ? exact::launch_wavefront(L, c->wf, c->num_sms, c->stream, &launches)
+                               : fast::launch_wavefront(L, c->wf, c->num_sms, c->stream, &launches));
+    } else {
+        KernelConfig cfg;
+        cfg.threads = c->threads;
+        cfg.count = count;
+        cfg.scene_in_smem = scene_fits_smem(c);
+        cfg.smem_bytes = cfg.scene_in_smem ? scene_smem_bytes(L.num_nodes, L.num_spheres) : 0;
+        int per_sm = c->blocks_per_sm;
+        if (per_sm <= 0) {
+            per_sm = exact_build ? exact::max_blocks_per_sm(cfg.threads, cfg.smem_bytes, cfg.scene_in_smem, count)
+                                 : fast::max_blocks_per_sm(cfg.threads, cfg.smem_bytes, cfg.scene_in_smem, count);
+            if (per_sm <= 0) return fail(c, VN_ERR_CUDA, "vn_render: occupancy query failed for the path kernel");
+        }
+        cfg.blocks = c->num_sms * per_sm;
+        // never launch more lanes than there is work
+        const uint64_t max_blocks = ((uint64_t)L.total_work + cfg.threads - 1) / cfg.threads;
+        if ((uint64_t)cfg.blocks > max_blocks) cfg.blocks = (int)std::max<uint64_t>(1, max_blocks);
+        VN_CUDA(c, exact_build ? exact::launch_render_persistent(L, cfg, c->stream) : fast::launch_render_persistent(L, cfg, c->stream));
+        launches += 1;
+    }
+    VN_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    if (host_image) VN_CUDA(c, cudaMemcpyAsync(p->image, c->image_tmp, pixels * 4, cudaMemcpyDeviceToHost, c->stream));
+    VN_CUDA(c, cudaMemcpyAsync(c->h_counters, c->d_counters, 32, cudaMemcpyDeviceToHost, c->stream));
+    c->stats.kernel_launches = launches;
+    c->stats.kernel_launches_total += launches;
+    c->stats_pending = true;
+    if (!(p->flags & VN_ASYNC) || host_image) {
+        VN_CUDA(c, cudaStreamSynchronize(c->stream));
+        VN_CUDA(c, cudaGetLastError());
+        return collect_render_stats(c);
+    }
+    return VN_OK;
+}
+
+int vn_tonemap(vn_handle c, float scale, void* image, uint32_t flags) {
+    VN_REQUIRE(c, c && image, "vn_tonemap: NULL argument");
+    VN_REQUIRE(c, c->accum, "vn_tonemap: no accumulation buffer");
+    VN_CUDA(c, cudaSetDevice(c->device));
+    const uint64_t pixels = (uint64_t)c->width * c->height;
+    uint32_t* dst = static_cast<uint32_t*>(image);
+    if (flags & VN_IMAGE_HOST) { const int rc = ensure_image_tmp(c, pixels); if (rc != VN_OK) return rc; dst = c->image_tmp; }
+    VN_CUDA(c, (flags & VN_EXACT) ? exact::launch_tonemap(c->accum, scale, dst, pixels, c->stream) : fast::launch_tonemap(c->accum, scale, dst, pixels, c->stream));
+    c->stats.kernel_launches_total += 1;
+    if (flags & VN_IMAGE_HOST) VN_CUDA(c, cudaMemcpyAsync(image, c->image_tmp, pixels * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (!(flags & VN_ASYNC) || (flags & VN_IMAGE_HOST)) VN_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VN_OK;
+}
+
+int vn_reduce_tonemap_peers(vn_handle c, const void* const* peer_accum, uint32_t n_peers, float scale, uint32_t row_begin,
+                            uint32_t row_end, void* image, uint32_t flags) {
+    VN_REQUIRE(c, c && peer_accum, "vn_reduce_tonemap_peers: NULL argument");
+    VN_REQUIRE(c, n_peers >= 1 && n_peers <= (uint32_t)kMaxPeers, "vn_reduce_tonemap_peers: 1..8 peers");
+    VN_REQUIRE(c, c->accum, "vn_reduce_tonemap_peers: no accumulation buffer");
+    VN_REQUIRE(c, row_begin <= row_end && row_end <= c->height, "vn_reduce_tonemap_peers: bad row range");
+    VN_CUDA(c, cudaSetDevice(c->device));
+    const float4* peers[kMaxPeers];
+    for (uint32_t i = 0; i < n_peers; i++) peers[i] = static_cast<const float4*>(peer_accum[i]);
+    const uint64_t begin = (uint64_t)row_begin * c->width, end = (uint64_t)row_end * c->width;
+    uint32_t* img = static_cast<uint32_t*>(image);
+    VN_CUDA(c, (flags & VN_EXACT) ? exact::launch_reduce_tonemap_peers(peers, n_peers, scale, begin, end, c->accum, img, c->stream)
+                                  : fast::launch_reduce_tonemap_peers(peers, n_peers, scale, begin, end, c->accum, img, c->stream));
+    c->stats.kernel_launches_total += 1;
+    if (!(flags & VN_ASYNC)) VN_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VN_OK;
+}
+
+int vn_get_stats(vn_handle c, vn_stats* out) {
+    VN_REQUIRE(c, c && out, "vn_get_stats: NULL argument");
+    *out = c->stats;
+    return VN_OK;
+}
+
+int vn_reset_stats(vn_handle c) {
+    VN_REQUIRE(c, c, "vn_reset_stats: NULL handle");
+    const float b = c->stats.ms_build, u = c->stats.ms_upload;
+    c->stats = vn_stats{};
+    c->stats.ms_build = b; c->stats.ms_upload = u;
+    return VN_OK;
+}
+
+// ---- buffers / IPC
+int vn_buffer_alloc(int device, uint64_t bytes, int zero_copy_host, void** dev_ptr, void** host_ptr) {
+    if (!dev_ptr || !host_ptr) return fail(nullptr, VN_ERR_INVALID, "vn_buffer_alloc: NULL argument");
+    *dev_ptr = *host_ptr = nullptr;
+    VN_CUDA(nullptr, cudaSetDevice(device));
+    if (zero_copy_host) {
+        VN_CUDA(nullptr, cudaHostAlloc(host_ptr, bytes, cudaHostAllocPortable | cudaHostAllocMapped));
+        VN_CUDA(nullptr, cudaHostGetDevicePointer(dev_ptr, *host_ptr, 0));
+    } else {
+        VN_CUDA(nullptr, cudaMalloc(dev_ptr, bytes));
+    }
+    return VN_OK;
+}
+
+int vn_buffer_free(int device, void* dev_ptr, void* host_ptr, int zero_copy_host) {
+    VN_CUDA(nullptr, cudaSetDevice(device));
+    if (zero_copy_host) { if (host_ptr) VN_CUDA(nullptr, cudaFreeHost(host_ptr)); }
+    else if (dev_ptr) VN_CUDA(nullptr, cudaFree(dev_ptr));
+    return VN_OK;
+}
+
+int vn_buffer_copy_to_host(int device, void* host_dst, const void* dev_src, uint64_t bytes) {
+    VN_CUDA(nullptr, cudaSetDevice(device));
+    VN_CUDA(nullptr, cudaMemcpy(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost));
+    return VN_OK;
+}
+
+int vn_stream_synchronize(int device, void* cuda_stream) {
+    VN_CUDA(nullptr, cudaSetDevice(device));
+    VN_CUDA(nullptr, cudaStreamSynchronize(static_cast<cudaStream_t>(cuda_stream)));
+    return VN_OK;
+}
+
+int vn_ipc_export(vn_handle c, void* dev_ptr, unsigned char handle_out[64]) {
+    VN_REQUIRE(c, c && dev_ptr && handle_out, "vn_ipc_export: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    VN_CUDA(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t hd;
+    VN_CUDA(c, cudaIpcGetMemHandle(&hd, dev_ptr));
+    memcpy(handle_out, &hd, 64);
+    return VN_OK;
+}
+
+int vn_ipc_open(vn_handle c, const unsigned char handle_in[64], void** dev_ptr) {
+    VN_REQUIRE(c, c && handle_in && dev_ptr, "vn_ipc_open: NULL argument");
+    VN_CUDA(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle_in, 64);
+    VN_CUDA(c, cudaIpcOpenMemHandle(dev_ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    return VN_OK;
+}
+
+int vn_ipc_close(vn_handle c, void* dev_ptr) {
+    VN_REQUIRE(c, c && dev_ptr, "vn_ipc_close: NULL argument");
+    VN_CUDA(c, cudaSetDevice(c->device));
+    VN_CUDA(c, cudaIpcCloseMemHandle(dev_ptr));
+    return VN_OK;
+}
+
+// ---- host-side scene / camera helpers: thin C wrappers over the drop-in classes of include/venusaur/
+uint32_t vn_scene_rtiow_final(vn_sphere* out, uint32_t cap) {
+    venusaur::Scene scene;                                   // Scene.h:13-80
+    const std::vector<vn_sphere> flat = scene.Flatten();
+    if (out) for (uint32_t i = 0; i < flat.size() && i < cap; i++) out[i] = flat[i];
+    return (uint32_t)flat.size();
+}
+
+void vn_scene_random(vn_sphere* out, uint64_t n, uint32_t seed, float S, uint32_t mix) {
+    // sphere i is a pure function of (i, seed) through the reference's own tea<4>/lcg stream.
+    for (uint64_t i = 0; i < n; i++) {
+        uint32_t s = tea4((uint32_t)i, seed);
+        vn_sphere o;
+        const float rx = rnd(s); o.cx = S * (2.0f * rx - 1.0f);
+        const float ry = rnd(s); o.cy = S * (2.0f * ry - 1.0f);
+        const float rz = rnd(s); o.cz = S * (2.0f * rz - 1.0f);
+        const float rr = rnd(s); o.r = 0.1f + 0.2f * rr;
+        const float m = rnd(s);
+        if (mix == 0) o.type = m < 0.80f ? VN_LAMBERTIAN : (m < 0.95f ? VN_METAL : VN_DIELECTRIC);
+        else          o.type = m < 0.50f ? VN_DIELECTRIC : (m < 0.90f ? VN_LAMBERTIAN : VN_METAL);
+        if (o.type == VN_LAMBERTIAN) {
+            const float a0 = rnd(s), a1 = rnd(s), b0 = rnd(s), b1 = rnd(s), c0 = rnd(s), c1 = rnd(s);
+            o.ax = a0 * a1; o.ay = b0 * b1; o.az = c0 * c1; o.fuzz_or_ir = 0.0f;
+        } else if (o.type == VN_METAL) {
+            const float a0 = rnd(s), a1 = rnd(s), a2 = rnd(s), f = rnd(s);
+            o.ax = 0.5f + 0.5f * a0; o.ay = 0.5f + 0.5f * a1; o.az = 0.5f + 0.5f * a2; o.fuzz_or_ir = 0.5f * f;
+        } else {
+            o.ax = o.ay = o.az = 0.0f; o.fuzz_or_ir = 1.5f;
+        }
+        out[i] = o;
+    }
+}
+
+void vn_camera_frame(const float lookfrom[3], const float forward[3], float vfov_deg, float aspect, float aperture, float focal_length,
+                     float origin[3], float u[3], float v[3], float w[3], float* lens_radius) {
+    venusaur::Camera cam(venusaur::vec3(lookfrom[0], lookfrom[1], lookfrom[2]), vfov_deg, aspect, aperture, focal_length);   // Core.cpp:29
+    cam.SetForward(venusaur::vec3(forward[0], forward[1], forward[2]));                                                     // Core.cpp:355
+    venusaur::vec3 U, V, W;
+    cam.UVWFrame(U, V, W);
+    origin[0] = cam.GetPosition().x; origin[1] = cam.GetPosition().y; origin[2] = cam.GetPosition().z;
+    u[0] = U.x; u[1] = U.y; u[2] = U.z;
+    v[0] = V.x; v[1] = V.y; v[2] = V.z;
+    w[0] = W.x; w[1] = W.y; w[2] = W.z;
+    *lens_radius = cam.GetLensRadius();
+}
+
+// ---- unit-level test entry points
+
+int vn_test_rng(vn_handle c, const uint32_t* v0, const uint32_t* v1, uint64_t n, uint32_t n_draws, uint32_t* seeds_out,
+                uint32_t* lcg_out, float* rnd_out) {
+    VN_REQUIRE(c, c && v0 && v1 && seeds_out && lcg_out && rnd_out, "vn_test_rng: NULL argument");
+    VN_CUDA(c, cudaSetDevice(c->device));
+    DevBuf a, b, s, l, r;
+    VN_CUDA(c, a.alloc(4 * n)); VN_CUDA(c, b.alloc(4 * n)); VN_CUDA(c, s.alloc(4 * n));
+    VN_CUDA(c, l.alloc(4 * n * n_draws)); VN_CUDA(c, r.alloc(4 * n * n_draws));
+    VN_CUDA(c, cudaMemcpyAsync(a.p, v0, 4 * n, cudaMemcpyHostToDevice, c->stream));
+    VN_CUDA(c, cudaMemcpyAsync(b.p, v1, 4 * n, cudaMemcpyHostToDevice, c->stream));
+    VN_CUDA(c, fast::launch_test_rng(a.as<uint32_t>(), b.as<uint32_t>(), n, n_draws, s.as<uint32_t>(), l.as<uint32_t>(), r.as<float>(), c->stream));
+    VN_CUDA(c, cudaMemcpyAsync(seeds_out, s.p, 4 * n, cudaMemcpyDeviceToHost, c->stream));
+    VN_CUDA(c, cudaMemcpyAsync(lcg_out, l.p, 4 * n * n_draws, cudaMemcpyDeviceToHost, c->stream));
+    VN_CUDA(c, cudaMemcpyAsync(rnd_out, r.p, 4 * n * n_draws, cudaMemcpyDeviceToHost, c->stream));
+    VN_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VN_OK;
+}
+
+int vn_trace_rays(vn_handle c, const float* origins, const float* dirs, uint64_t n, float* t_out, int32_t* prim_out, uint32_t flags) {
+    VN_REQUIRE(c, c && origins && dirs && t_out && prim_out, "vn_trace_rays: NULL argument");
+    VN_REQUIRE(c, c->bvh_valid, "vn_trace_rays: no BVH");
+    VN_CUDA(c, cudaSetDevice(c->device));
+    DevBuf o, d, t, pr;
+    VN_CUDA(c, o.alloc(12 * n)); VN_CUDA(c, d.alloc(12 * n)); VN_CUDA(c, t.alloc(4 * n)); VN_CUDA(c, pr.alloc(4 * n));
+    VN_CUDA(c, cudaMemcpyAsync(o.p, origins, 12 * n, cudaMemcpyHostToDevice, c->stream));
+    VN_CUDA(c, cudaMemcpyAsync(d.p, dirs, 12 * n, cudaMemcpyHostToDevice, c->stream));
+    RenderLaunch L;
+    memset(&L, 0, sizeof(L));
+    L.nodes = c->scene.nodes; L.geom = c->scene.geom; L.root_link = c->scene.root_link;
+    VN_CUDA(c, (flags & VN_EXACT) ? exact::launch_trace_rays(L, o.as<float>(), d.as<float>(), n, t.as<float>(), pr.as<int32_t>(), c->scene.orig, c->stream)
+                                  : fast::launch_trace_rays(L, o.as<float>(), d.as<float>(), n, t.as<float>(), pr.as<int32_t>(), c->scene.orig, c->stream));
+    VN_CUDA(c, cudaMemcpyAsync(t_out, t.p, 4 * n, cudaMemcpyDeviceToHost, c->stream));
+    VN_CUDA(c, cudaMemcpyAsync(prim_out, pr.p, 4 * n, cudaMemcpyDeviceToHost, c->stream));
+    VN_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VN_OK;
+}
+
+int vn_sort_pairs(vn_handle c, uint32_t* keys, uint32_t* values, uint64_t n, uint32_t key_bits) {
+    VN_REQUIRE(c, c && (n == 0 || (keys && values)), "vn_sort_pairs: NULL argument");
+    VN_REQUIRE(c, key_bits >= 1 && key_bits <= 32, "vn_sort_pairs: key_bits must be in [1,32]");
+    VN_REQUIRE(c, n < (1ull << 30), "vn_sort_pairs: n must be < 2^30");
+    if (n == 0) return VN_OK;
+    VN_CUDA(c, cudaSetDevice(c->device));
+    DevBuf k0, v0, k1, v1;
+    VN_CUDA(c, k0.alloc(4 * n)); VN_CUDA(c, v0.alloc(4 * n)); VN_CUDA(c, k1.alloc(4 * n)); VN_CUDA(c, v1.alloc(4 * n));
+    VN_CUDA(c, cudaMemcpyAsync(k0.p, keys, 4 * n, cudaMemcpyHostToDevice, c->stream));
+    VN_CUDA(c, cudaMemcpyAsync(v0.p, values, 4 * n, cudaMemcpyHostToDevice, c->stream));
+    std::string err;
+    uint32_t launches = 0;
+    const int which = radix_sort_pairs_device(k0.as<uint32_t>(), v0.as<uint32_t>(), k1.as<uint32_t>(), v1.as<uint32_t>(), (uint32_t)n, (int)key_bits,
+                                              c->num_sms, c->stream, &launches, err);
+    if (which < 0) return fail(c, VN_ERR_CUDA, "vn_sort_pairs: " + err);
+    c->stats.kernel_launches_total += launches;
+    VN_CUDA(c, cudaMemcpyAsync(keys, which ? k1.p : k0.p, 4 * n, cudaMemcpyDeviceToHost, c->stream));
+    VN_CUDA(c, cudaMemcpyAsync(values, which ? v1.p : v0.p, 4 * n, cudaMemcpyDeviceToHost, c->stream));
+    VN_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VN_OK;
+}
+
+int vn_test_make_color(vn_handle c, const float* rgb, uint64_t n, uint8_t* rgba_out, uint32_t flags) {
+    VN_REQUIRE(c, c && rgb && rgba_out, "vn_test_make_color: NULL argument");
+    VN_CUDA(c, cudaSetDevice(c->device));
+    DevBuf in, out;
+    VN_CUDA(c, in.alloc(12 * n)); VN_CUDA(c, out.alloc(4 * n));
+    VN_CUDA(c, cudaMemcpyAsync(in.p, rgb, 12 * n, cudaMemcpyHostToDevice, c->stream));
+    VN_CUDA(c, (flags & VN_EXACT) ? exact::launch_make_color(in.as<float>(), n, out.as<uint32_t>(), c->stream)
+                                  : fast::launch_make_color(in.as<float>(), n, out.as<uint32_t>(), c->stream));
+    VN_CUDA(c, cudaMemcpyAsync(rgba_out, out.p, 4 * n, cudaMemcpyDeviceToHost, c->stream));
+    VN_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VN_OK;
+}
+
+int vn_test_scatter(vn_handle c, uint32_t material_type, const float albedo_fuzz_ir[4], const float* dirs, const float* normals,
+                    const uint8_t* front, const uint32_t* seeds, uint64_t n, float* dirs_out, uint8_t* scattered_out,
+                    uint32_t* seeds_out, uint32_t flags) {
+    VN_REQUIRE(c, c && albedo_fuzz_ir && dirs && normals && front && seeds && dirs_out && scattered_out && seeds_out, "vn_test_scatter: NULL argument");
+    VN_REQUIRE(c, material_type <= 2u, "vn_test_scatter: bad material type");
+    VN_CUDA(c, cudaSetDevice(c->device));
+    DevBuf d, nr, fr, sd, dout, sc, sout;
+    VN_CUDA(c, d.alloc(12 * n)); VN_CUDA(c, nr.alloc(12 * n)); VN_CUDA(c, fr.alloc(n)); VN_CUDA(c, sd.alloc(4 * n));
+    VN_CUDA(c, dout.alloc(12 * n)); VN_CUDA(c, sc.alloc(n)); VN_CUDA(c, sout.alloc(4 * n));
+    VN_CUDA(c, cudaMemcpyAsync(d.p, dirs, 12 * n, cudaMemcpyHostToDevice, c->stream));
+    VN_CUDA(c, cudaMemcpyAsync(nr.p, normals, 12 * n, cudaMemcpyHostToDevice, c->stream));
+    VN_CUDA(c, cudaMemcpyAsync(fr.p, front, n, cudaMemcpyHostToDevice, c->stream));
+    VN_CUDA(c, cudaMemcpyAsync(sd.p, seeds, 4 * n, cudaMemcpyHostToDevice, c->stream));
+    // same packing as k_gather: {albedo.xyz, fuzz} or {ir, 0, 0, 0}
+    const float4 mat = material_type == VN_DIELECTRIC ? make_float4(albedo_fuzz_ir[3], 0.f, 0.f, 0.f)
+                                                      : make_float4(albedo_fuzz_ir[0], albedo_fuzz_ir[1], albedo_fuzz_ir[2], albedo_fuzz_ir[3]);
+    VN_CUDA(c, (flags & VN_EXACT) ? exact::launch_scatter(material_type, mat, d.as<float>(), nr.as<float>(), fr.as<uint8_t>(), sd.as<uint32_t>(), n,
+                                                          dout.as<float>(), sc.as<uint8_t>(), sout.as<uint32_t>(), c->stream)
+                                  : fast::launch_scatter(material_type, mat, d.as<float>(), nr.as<float>(), fr.as<uint8_t>(), sd.as<uint32_t>(), n,
+                                                         dout.as<float>(), sc.as<uint8_t>(), sout.as<uint32_t>(), c->stream));
+    VN_CUDA(c, cudaMemcpyAsync(dirs_out, dout.p, 12 * n, cudaMemcpyDeviceToHost, c->stream));
+    VN_CUDA(c, cudaMemcpyAsync(scattered_out, sc.p, n, cudaMemcpyDeviceToHost, c->stream));
+    VN_CUDA(c, cudaMemcpyAsync(seeds_out, sout.p, 4 * n, cudaMemcpyDeviceToHost, c->stream));
+    VN_CUDA(c, cudaStreamSynchronize(c->stream));
+    return VN_OK;
+}
+
+}  // extern "C"

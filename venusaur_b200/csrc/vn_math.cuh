@@ -1,0 +1,411 @@
+// vn_math.cuh -- per-path device math of the B200 path tracer: RNG, samplers, camera ray, ray/sphere
+// intersection, the three scatter functions, sky, sRGB quantisation.
+//
+// Two builds of every kernel are made from this one header:
+//   VN_EXACT=1  compiled with -fmad=false: each float operation is one IEEE-754 binary32 op in the order the
+//               reference writes it (RayTracer.cu / vec_math.h), FP64 where the reference uses FP64.  Bit-identical
+//               to the host oracle; used by the parity tests.
+//   VN_EXACT=0  the FAST build that is benchmarked: FMA contraction, approximate reciprocal / rsqrt, FP32
+//               replacements for the FP64 fragments.  Checked statistically against the same oracle.
+// The header also compiles as plain C++ (g++) so that tests can run the exact math on the CPU; that host build
+// is test-only -- the library itself has no CPU path.
+//
+// Citations: file:line in /root/reference/Core/.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define VN_HD __host__ __device__ __forceinline__
+#else
+#define VN_HD inline
+#endif
+
+#ifndef VN_EXACT
+#define VN_EXACT 1
+#endif
+
+#if VN_EXACT || !defined(__CUDA_ARCH__)
+#define VN_FAST_DEVICE 0
+#else
+#define VN_FAST_DEVICE 1
+#endif
+
+namespace vn {
+
+struct f3 { float x, y, z; };
+
+VN_HD f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+VN_HD f3 mk3(float s) { return mk3(s, s, s); }
+VN_HD f3 operator+(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+VN_HD f3 operator-(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+VN_HD f3 operator-(f3 a) { return mk3(-a.x, -a.y, -a.z); }
+VN_HD f3 operator*(f3 a, f3 b) { return mk3(a.x * b.x, a.y * b.y, a.z * b.z); }
+VN_HD f3 operator*(f3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+VN_HD f3 operator*(float s, f3 a) { return mk3(a.x * s, a.y * s, a.z * s); }
+VN_HD float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }            // vec_math.h:527-530
+
+// ---- mode-dependent scalar primitives
+VN_HD float rcp(float a) {
+#if VN_FAST_DEVICE
+    return __fdividef(1.0f, a);       // MUFU.RCP + FMUL
+#else
+    return 1.0f / a;
+#endif
+}
+VN_HD float fdiv(float a, float b) {
+#if VN_FAST_DEVICE
+    return __fdividef(a, b);
+#else
+    return a / b;
+#endif
+}
+VN_HD float fsqrt(float a) {
+#if VN_FAST_DEVICE
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));   // MUFU.SQRT
+    return r;
+#else
+    return sqrtf(a);
+#endif
+}
+// 1/sqrt(a): the reference computes 1.0f / sqrtf(a) (vec_math.h:545-549)
+VN_HD float inv_sqrt(float a) {
+#if VN_FAST_DEVICE
+    return rsqrtf(a);
+#else
+    return 1.0f / sqrtf(a);
+#endif
+}
+
+VN_HD f3 normalize(f3 v) { float invLen = inv_sqrt(dot(v, v)); return v * invLen; }   // vec_math.h:545-549
+VN_HD f3 reflect(f3 i, f3 n) { return i - 2.0f * n * dot(n, i); }                     // vec_math.h:558-561
+VN_HD f3 refract(f3 uv, f3 n, float etai_over_etat) {                                 // vec_math.h:564-570
+    float cos_theta = fminf(dot(-uv, n), 1.0f);
+    f3 r_out_perp = etai_over_etat * (uv + cos_theta * n);
+    f3 r_out_parallel = -fsqrt(fabsf(1.0f - dot(r_out_perp, r_out_perp))) * n;
+    return r_out_perp + r_out_parallel;
+}
+VN_HD f3 lerp3(f3 a, f3 b, float t) { return a + t * (b - a); }                        // vec_math.h:500-503
+VN_HD float clamp01(float f) { return fmaxf(0.0f, fminf(f, 1.0f)); }                  // vec_math.h:119-122
+
+// ---- RNG: random.cuh:31-67, uint32, bit-exact in both builds
+VN_HD uint32_t tea4(uint32_t val0, uint32_t val1) {
+    uint32_t v0 = val0, v1 = val1, s0 = 0;
+#pragma unroll
+    for (int n = 0; n < 4; n++) {
+        s0 += 0x9e3779b9u;
+        v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + s0) ^ ((v1 >> 5) + 0xc8013ea4u);
+        v1 += ((v0 << 4) + 0xad90777du) ^ (v0 + s0) ^ ((v0 >> 5) + 0x7e95761eu);
+    }
+    return v0;
+}
+VN_HD uint32_t lcg(uint32_t& prev) {
+    prev = 1664525u * prev + 1013904223u;
+    return prev & 0x00FFFFFFu;
+}
+// (float)lcg / (float)0x01000000: dividing by 2^24 is exact, so multiplying by 2^-24 gives the same bits.
+VN_HD float rnd(uint32_t& prev) { return (float)lcg(prev) * 5.9604644775390625e-8f; }
+// random_float(seed,-1,1) = -1 + (1 - -1) * rnd (RayTracer.cu:93-97): 2*rnd and the sum are both exact.
+VN_HD float rnd_pm1(uint32_t& prev) { return -1.0f + 2.0f * rnd(prev); }
+
+// RayTracer.cu:117-125; draws sequenced x, y, z (the contract of SURVEY 3.4)
+VN_HD f3 random_in_unit_sphere(uint32_t& seed) {
+    while (true) {
+        f3 p;
+        p.x = rnd_pm1(seed);
+        p.y = rnd_pm1(seed);
+        p.z = rnd_pm1(seed);
+        if (dot(p, p) >= 1.0f) continue;
+        return p;
+    }
+}
+// RayTracer.cu:141-149
+VN_HD void random_in_unit_disk(uint32_t& seed, float& px, float& py) {
+    while (true) {
+        float x = rnd_pm1(seed);
+        float y = rnd_pm1(seed);
+        if (x * x + y * y + 0.0f * 0.0f >= 1.0f) continue;
+        px = x; py = y;
+        return;
+    }
+}
+
+// ---- launch constants (Params, RayTracer.h:3-17, plus hoisted loop invariants)
+struct Camera {
+    f3 origin, u, v, w;
+    f3 u_unit, v_unit;       // normalize(params.u), normalize(params.v): loop invariants of get_ray (RayTracer.cu:155-156)
+    float lens_radius;
+    float wm1, hm1;          // float(width-1), float(height-1)
+    float inv_wm1, inv_hm1;  // FAST build only
+};
+
+// get_ray + the jitter of __raygen__rg: RayTracer.cu:151-161,173-174
+VN_HD void camera_ray(const Camera& c, uint32_t px, uint32_t py, uint32_t& seed, f3& origin, f3& direction) {
+    float ju = rnd(seed);
+    float jv = rnd(seed);
+#if VN_FAST_DEVICE
+    float s = 2.0f * ((float)px + ju) * c.inv_wm1 - 1.0f;
+    float t = 2.0f * ((float)py + jv) * c.inv_hm1 - 1.0f;
+#else
+    float s = 2.0f * ((float)px + ju) / c.wm1 - 1.0f;
+    float t = 2.0f * ((float)py + jv) / c.hm1 - 1.0f;
+#endif
+    float dx, dy;
+    random_in_unit_disk(seed, dx, dy);
+    float rdx = c.lens_radius * dx, rdy = c.lens_radius * dy;
+    f3 offset = c.u_unit * rdx + c.v_unit * rdy;
+    origin = c.origin + offset;
+    direction = c.w + s * c.u * 0.5f + t * c.v * 0.5f - offset;
+}
+
+// ---- ray / sphere: RayTracer.cu:229-270.  Returns the accepted root or -1.  `a` = dot(d,d).
+VN_HD float sphere_root(f3 o, f3 d, float a, float inv_a, float cx, float cy, float cz, float r, float t_min, float t_max) {
+    f3 oc = o - mk3(cx, cy, cz);
+    float half_b = dot(oc, d);
+    float c = dot(oc, oc) - r * r;
+    float discriminant = half_b * half_b - a * c;
+    if (discriminant < 0.0f) return -1.0f;
+    float sqrtd = fsqrt(discriminant);
+#if VN_FAST_DEVICE
+    float root = (-half_b - sqrtd) * inv_a;
+    if (root < t_min || t_max < root) {
+        root = (-half_b + sqrtd) * inv_a;
+        if (root < t_min || t_max < root) return -1.0f;
+    }
+#else
+    (void)inv_a;
+    float root = (-half_b - sqrtd) / a;
+    if (root < t_min || t_max < root) {
+        root = (-half_b + sqrtd) / a;
+        if (root < t_min || t_max < root) return -1.0f;
+    }
+#endif
+    return root;
+}
+
+// hit point + face-forwarded normal: RayTracer.cu:256-258, 219-224
+VN_HD void hit_frame(f3 o, f3 d, float t, float cx, float cy, float cz, float r, f3& p, f3& n, bool& front) {
+    p = o + d * t;
+    float inv = rcp(r);                                   // vec_math.h:483-487: (p - c) / r = (p - c) * (1/r)
+    f3 normal = (p - mk3(cx, cy, cz)) * inv;
+    front = dot(d, normal) < 0.0f;
+    n = front ? normal : -normal;
+}
+
+// ---- materials
+// __closesthit__lambertian, RayTracer.cu:288-291 (+ near_zero :8-13, which compares in double)
+VN_HD f3 scatter_lambertian(f3 n, uint32_t& seed) {
+    f3 dir = n + normalize(random_in_unit_sphere(seed));
+#if VN_FAST_DEVICE
+    // |x| < 1e-8 in double <=> |x| <= the largest float below 1e-8
+    const float s = 9.99999993922529e-09f;
+    bool nz = (fabsf(dir.x) <= s) && (fabsf(dir.y) <= s) && (fabsf(dir.z) <= s);
+#else
+    const double s = 1e-8;
+    bool nz = ((double)fabsf(dir.x) < s) && ((double)fabsf(dir.y) < s) && ((double)fabsf(dir.z) < s);
+#endif
+    return nz ? n : dir;
+}
+
+// __closesthit__metal, RayTracer.cu:338-341.  Returns false when the ray is absorbed.
+VN_HD bool scatter_metal(f3 dir_in, f3 n, float fuzz, uint32_t& seed, f3& dir_out) {
+    f3 reflected = reflect(normalize(dir_in), n);
+    dir_out = reflected + fuzz * random_in_unit_sphere(seed);
+    return dot(dir_out, n) > 0.0f;
+}
+
+// reflectance, RayTracer.cu:373-379 (__powf there)
+VN_HD float reflectance(float cosine, float ref_idx) {
+    float r0 = fdiv(1.0f - ref_idx, 1.0f + ref_idx);
+    r0 = r0 * r0;
+#if VN_FAST_DEVICE
+    float x = 1.0f - cosine;
+    float x2 = x * x;
+    return r0 + (1.0f - r0) * (x2 * x2 * x);
+#else
+    return r0 + (1.0f - r0) * powf(1.0f - cosine, 5.0f);
+#endif
+}
+
+// __closesthit__dielectric, RayTracer.cu:398-414
+VN_HD f3 scatter_dielectric(f3 dir_in, f3 n, bool front, float ir, uint32_t& seed) {
+    float refraction_ratio = front ? rcp(ir) : ir;
+    f3 unit_direction = normalize(dir_in);
+#if VN_FAST_DEVICE
+    float cos_theta = fminf(dot(-unit_direction, n), 1.0f);
+    float sin2 = 1.0f - cos_theta * cos_theta;
+    bool cannot_refract = refraction_ratio * refraction_ratio * sin2 > 1.0f;
+    float cos_f = cos_theta;
+#else
+    double cos_theta = (double)fminf(dot(-unit_direction, n), 1.0f);
+    double sin_theta = sqrt(1.0 - cos_theta * cos_theta);
+    bool cannot_refract = (double)refraction_ratio * sin_theta > 1.0;
+    float cos_f = (float)cos_theta;
+#endif
+    // `cannot_refract || reflectance > random_float` short-circuits: no draw when cannot_refract
+    bool do_reflect = cannot_refract;
+    if (!do_reflect) do_reflect = reflectance(cos_f, refraction_ratio) > rnd(seed);
+    return do_reflect ? reflect(unit_direction, n) : refract(unit_direction, n, refraction_ratio);
+}
+
+// __miss__ms, RayTracer.cu:442-450.  0.5*(y+1.0) in double then narrowed == the float expression below
+// (y+1 is exact in double; halving is exact; one rounding either way).
+VN_HD f3 sky(f3 d) {
+    f3 unit_direction = normalize(d);
+    float t = 0.5f * (unit_direction.y + 1.0f);
+    return lerp3(mk3(1.0f), mk3(0.5f, 0.7f, 1.0f), t);
+}
+
+// ---- toSRGB / quantizeUnsigned8Bits / make_color, RayTracer.cu:16-47
+VN_HD float to_srgb(float c) {
+    const float invGamma = 1.0f / 2.4f;
+    float powed = powf(c, invGamma);
+    return c < 0.0031308f ? 12.92f * c : 1.055f * powed - 0.055f;
+}
+VN_HD uint32_t quantize8(float x) {
+    x = clamp01(x);
+    uint32_t v = (uint32_t)(x * 256.0f);
+    return v < 255u ? v : 255u;
+}
+VN_HD uint32_t make_color_u32(f3 c) {   // uchar4 {r,g,b,255} packed little-endian
+    uint32_t r = quantize8(to_srgb(clamp01(c.x)));
+    uint32_t g = quantize8(to_srgb(clamp01(c.y)));
+    uint32_t b = quantize8(to_srgb(clamp01(c.z)));
+    return r | (g << 8) | (b << 16) | (255u << 24);
+}
+
+// ---- BVH traversal over packed 32-byte nodes (see lbvh.cu for the layout)
+//   node i = nodes[2i] = {lo.xyz, link}, nodes[2i+1] = {hi.xyz, aux}; children of an internal node are the
+//   64-byte aligned pair (link, link+1); leaf link = 0x80000000 | first<<3 | (count-1).
+struct alignas(16) f4 { float x, y, z, w; };
+#if defined(__CUDACC__)
+typedef float4 node_f4;
+#else
+typedef f4 node_f4;
+#endif
+
+constexpr uint32_t kLeafFlag = 0x80000000u;
+constexpr uint32_t kEmptyScene = 0xFFFFFFFFu;
+constexpr int kStackSize = 64;
+constexpr float kTMin = 0.001f;   // RayTracer.cu:194
+constexpr float kTMax = 1e16f;    // RayTracer.cu:195
+
+VN_HD uint32_t f2u(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    union { float f; uint32_t u; } c; c.f = f; return c.u;
+#endif
+}
+
+struct TraceCounters { uint32_t nodes, spheres; };
+
+// Slab test against one child box.  Not parity-relevant (it only has to be conservative; boxes are padded at build
+// time), so it uses explicit FMAs in both builds.  NaNs from 0*inf are dropped by fminf/fmaxf => "overlaps".
+VN_HD bool box_hit(const node_f4& lo, const node_f4& hi, f3 idir, f3 ood, float tbest, float& tnear) {
+    float t0x = fmaf(lo.x, idir.x, -ood.x), t1x = fmaf(hi.x, idir.x, -ood.x);
+    float t0y = fmaf(lo.y, idir.y, -ood.y), t1y = fmaf(hi.y, idir.y, -ood.y);
+    float t0z = fmaf(lo.z, idir.z, -ood.z), t1z = fmaf(hi.z, idir.z, -ood.z);
+    float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), 0.0f));
+    float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tbest));
+    tnear = tn;
+    return tn <= tf;
+}
+
+// Closest hit in [kTMin, kTMax] = optixTrace(...) of RayTracer.cu:190-202.  prim = index into the SORTED sphere
+// arrays, -1 on miss.
+template <bool kCount>
+VN_HD void closest_hit(const node_f4* __restrict__ nodes, const node_f4* __restrict__ geom, uint32_t root_link,
+                       f3 o, f3 d, float& t_out, int& prim_out, TraceCounters& cnt) {
+    float tbest = kTMax;
+    int prim = -1;
+    if (root_link != kEmptyScene) {
+        const f3 idir = mk3(rcp(d.x), rcp(d.y), rcp(d.z));
+        const f3 ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
+        const float a = dot(d, d);
+        const float inv_a = rcp(a);
+        uint32_t stack[kStackSize];
+        int sp = 0;
+        uint32_t cur = root_link;
+        while (true) {
+            if (!(cur & kLeafFlag)) {
+                const node_f4 l0 = nodes[2 * cur], l1 = nodes[2 * cur + 1];
+                const node_f4 r0 = nodes[2 * cur + 2], r1 = nodes[2 * cur + 3];
+                if (kCount) cnt.nodes += 1;
+                float tl, tr;
+                const bool hl = box_hit(l0, l1, idir, ood, tbest, tl);
+                const bool hr = box_hit(r0, r1, idir, ood, tbest, tr);
+                const uint32_t ll = f2u(l0.w), lr = f2u(r0.w);
+                if (hl && hr) {
+                    const bool left_first = tl <= tr;
+                    cur = left_first ? ll : lr;
+                    stack[sp++] = left_first ? lr : ll;
+                    continue;
+                }
+                if (hl) { cur = ll; continue; }
+                if (hr) { cur = lr; continue; }
+            } else {
+                const uint32_t first = (cur & 0x7FFFFFFFu) >> 3;
+                const uint32_t count = (cur & 7u) + 1u;
+                for (uint32_t k = 0; k < count; k++) {
+                    const node_f4 g = geom[first + k];
+                    if (kCount) cnt.spheres += 1;
+                    const float t = sphere_root(o, d, a, inv_a, g.x, g.y, g.z, g.w, kTMin, tbest);
+                    if (t >= 0.0f) { tbest = t; prim = (int)(first + k); }
+                }
+            }
+            if (sp == 0) break;
+            cur = stack[--sp];
+        }
+    }
+    t_out = tbest;
+    prim_out = prim;
+}
+
+// ---- one full path, iterative: the recursion of RayTracer.cu:190-202 -> closest-hit -> optixTrace -> ... -> miss.
+// The albedo product is accumulated forward (throughput), the reference multiplies on recursion unwind
+// (RayTracer.cu:313,360): same factors, different association (<= depth * 2^-24 relative).
+struct SceneView {
+    const node_f4* nodes;
+    const node_f4* geom;     // {cx, cy, cz, r}, sorted order
+    const node_f4* mat;      // {albedo.xyz | ir, fuzz}
+    const uint8_t* type;
+    uint32_t root_link;
+};
+
+struct PathState {
+    f3 o, d, thr;
+    uint32_t seed;
+    int depth;
+};
+
+// Shades the closest hit (or miss) of one segment.  Returns true when the path continues (st updated), false when
+// it ended with radiance `result`.
+VN_HD bool shade_segment(const SceneView& sc, PathState& st, float t, int prim, f3& result) {
+    if (prim < 0) { result = st.thr * sky(st.d); return false; }
+    if (!(st.depth > 0)) { result = mk3(0.0f); return false; }      // RayTracer.cu:275,324,384: depth budget exhausted
+    const node_f4 g = sc.geom[prim];
+    const node_f4 m = sc.mat[prim];
+    const uint32_t type = sc.type[prim];
+    f3 p, n;
+    bool front;
+    hit_frame(st.o, st.d, t, g.x, g.y, g.z, g.w, p, n, front);
+    if (type == 0u) {
+        st.d = scatter_lambertian(n, st.seed);
+        st.thr = st.thr * mk3(m.x, m.y, m.z);
+    } else if (type == 1u) {
+        f3 dir;
+        if (!scatter_metal(st.d, n, m.w, st.seed, dir)) { result = mk3(0.0f); return false; }
+        st.d = dir;
+        st.thr = st.thr * mk3(m.x, m.y, m.z);
+    } else {
+        st.d = scatter_dielectric(st.d, n, front, m.x, st.seed);
+    }
+    st.o = p;
+    st.depth -= 1;
+    return true;
+}
+
+}  // namespace vn
