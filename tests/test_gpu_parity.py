@@ -1,0 +1,534 @@
+"""GPU parity tests: every call goes through the C ABI of libvenusaur_b200.so and runs CUDA kernels on cuda:0; the CPU
+oracle (oracle/) is only the checker.  Bars: bit-exact for integer / index work and for the IEEE (VN_EXACT) build of the
+float path; the tolerance BASELINE.json states (per-channel relative error <= 1e-3 on >= 99.9 % of pixels, PSNR >= 45 dB
+at 1024 spp) for the FAST build that is benchmarked."""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import venusaur_b200 as vb
+from venusaur_b200 import VN_ACCUM_SUM, VN_COUNTERS, VN_EXACT, VN_IMAGE_HOST, VN_NO_TONEMAP, VN_WAVEFRONT
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+C1 = dict(width=400, height=225, spp=10, max_depth=50)     # BASELINE.json configs[0]
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def render(ctx, cam, width, height, spp, sub, max_depth, flags=0, accum_count=0, rows=(0, 0), image=True):
+    img = np.zeros((height, width, 4), np.uint8) if image else None
+    p = ctx.make_params(cam, width, height, spp, sub, max_depth, accum_count=accum_count, image=ptr(img) if image else None,
+                        flags=flags | (VN_IMAGE_HOST if image else VN_NO_TONEMAP), rows=rows)
+    ctx.render(p)
+    return ctx.read_accum(), img, ctx.stats()
+
+
+@pytest.fixture()
+def rtiow_ctx(ctx, rtiow):
+    ctx.set_option("leaf_size", 2)
+    ctx.set_spheres(rtiow)
+    ctx.build_bvh()
+    return ctx
+
+
+# ------------------------------------------------------------------ integer work: bit-exact
+def test_rng_device_bit_exact(ctx, oracle_mod):
+    kat = json.load(open(os.path.join(GOLD, "ref_kat.json")))
+    v0 = np.array([a for a, _, _ in kat["tea4"]], np.uint32)
+    v1 = np.array([b for _, b, _ in kat["tea4"]], np.uint32)
+    seeds, lcg, rnd = ctx.test_rng(v0, v1, 8)
+    assert seeds.tolist() == [w for _, _, w in kat["tea4"]]
+    i = [k for k, (a, b, _) in enumerate(kat["tea4"]) if (a, b) == (0, 1)][0]
+    assert [float(x) for x in rnd[i]] == kat["rnd_from_tea4_0_1"][:8]
+    # random (pixel, subframe) pairs incl. the last pixels of 1080p / 4K, 32 draws each, vs the oracle
+    rng = np.random.RandomState(5)
+    v0 = np.concatenate([rng.randint(0, 8294400, 4000), [0, 2073599, 8294399]]).astype(np.uint32)
+    v1 = np.concatenate([rng.randint(0, 4097, 4000), [0, 64, 256]]).astype(np.uint32)
+    seeds, lcg, rnd = ctx.test_rng(v0, v1, 32)
+    o = oracle_mod.load()
+    for k in range(0, len(v0), 97):
+        s = C.c_uint32(o.orc_tea(4, int(v0[k]), int(v1[k])))
+        assert s.value == seeds[k]
+        s2 = C.c_uint32(s.value)
+        for j in range(32):
+            assert o.orc_lcg(C.byref(s)) == lcg[k, j]
+            assert np.float32(o.orc_rnd(C.byref(s2))) == rnd[k, j]
+    assert rnd.max() < 1.0 and rnd.min() >= 0.0
+
+
+@pytest.mark.parametrize("n,bits", [(1, 32), (2, 32), (255, 8), (4096, 30), (4097, 30), (100003, 32), (1 << 20, 30), (3_000_017, 32)])
+def test_onesweep_radix_sort(ctx, n, bits):
+    rng = np.random.RandomState(n % 1000)
+    keys = rng.randint(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32) & np.uint32((1 << bits) - 1 if bits < 32 else 0xFFFFFFFF)
+    if n > 1000:
+        keys[rng.randint(0, n, n // 3)] = keys[rng.randint(0, n, n // 3)]      # plenty of duplicates: stability matters
+    vals = np.arange(n, dtype=np.uint32)
+    k, v = ctx.sort_pairs(keys, vals, bits)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(k, keys[order])
+    assert np.array_equal(v, order.astype(np.uint32))
+
+
+def test_onesweep_degenerate_inputs(ctx):
+    for keys in (np.zeros(50000, np.uint32), np.full(50000, 0xFFFFFFFF, np.uint32), np.arange(50000, dtype=np.uint32)[::-1].copy(),
+                 (np.arange(70000, dtype=np.uint32) % 3)):
+        k, v = ctx.sort_pairs(keys, np.arange(len(keys), dtype=np.uint32), 32)
+        order = np.argsort(keys, kind="stable")
+        assert np.array_equal(k, keys[order]) and np.array_equal(v, order.astype(np.uint32))
+    k, v = ctx.sort_pairs(np.zeros(0, np.uint32), np.zeros(0, np.uint32), 32)
+    assert len(k) == 0
+
+
+# ------------------------------------------------------------------ LBVH builder
+def _host_bvh(host_harness, spheres, leaf):
+    n = len(spheres)
+    nodes = np.zeros(2 * n + 4, vb.api.NODE_DTYPE)
+    order = np.zeros(max(n, 1), np.uint32)
+    codes = np.zeros(max(n, 1), np.uint32)
+    nn = host_harness.hh_build_bvh(ptr(spheres), n, leaf, C.c_float(0.01), ptr(nodes), len(nodes), ptr(order), ptr(codes))
+    return nodes[:nn], order[:n], codes[:n]
+
+
+@pytest.mark.parametrize("leaf", [1, 2, 4, 8])
+def test_lbvh_matches_cpu_emulation(ctx, host_harness, oracle_mod, rtiow, leaf):
+    """Morton codes, sort order, Karras hierarchy, refit and packing on the GPU == the same per-element functions run
+    sequentially on the CPU, node for node (and therefore satisfy the invariants test_host_logic checks)."""
+    from test_host_logic import _check_bvh
+    import sys
+    sys.setrecursionlimit(100000)
+    scenes = [rtiow, oracle_mod.random_scene(50000, 0x5EED0001, 100.0, 0), rtiow[:1], rtiow[:2], rtiow[:5], np.repeat(rtiow[7:8], 300)]
+    for spheres in scenes:
+        spheres = np.ascontiguousarray(spheres)
+        ctx.set_option("leaf_size", leaf)
+        ctx.set_spheres(spheres)
+        ctx.build_bvh()
+        nodes, order = ctx.read_bvh()
+        codes = ctx.morton_codes()
+        hn, ho, hc = _host_bvh(host_harness, spheres, leaf)
+        assert np.array_equal(codes, hc)
+        assert np.array_equal(order, ho)
+        assert len(nodes) == len(hn) and nodes.tobytes() == hn.tobytes()
+        info = ctx.bvh_info()
+        assert info.num_spheres == len(spheres) and info.num_nodes == len(nodes)
+        if len(spheres) <= 5000:
+            _check_bvh(nodes, order, spheres, leaf)
+    ctx.set_option("leaf_size", 2)
+
+
+def test_lbvh_large_build_invariants(ctx, oracle_mod):
+    """1 M spheres (BASELINE config 4 scale): sorted codes, permutation, root bounds; build time is reported."""
+    n = 1_000_000
+    spheres = vb.random_scene(n, 0x5EED0001, 100.0, 0)
+    ctx.set_spheres(spheres)
+    ctx.build_bvh()
+    codes = ctx.morton_codes()
+    assert (np.diff(codes.astype(np.int64)) >= 0).all()
+    nodes, order = ctx.read_bvh()
+    assert np.array_equal(np.sort(order), np.arange(n, dtype=np.uint32))
+    r = np.abs(spheres["r"])
+    lo = np.array([(spheres[a] - r).min() for a in ("cx", "cy", "cz")])
+    hi = np.array([(spheres[a] + r).max() for a in ("cx", "cy", "cz")])
+    assert (nodes[1]["lo"] <= lo).all() and (nodes[1]["hi"] >= hi).all() and int(nodes[1]["aux"]) == n
+    leaves = nodes[2:][(nodes[2:]["link"] & 0x80000000) != 0]
+    assert int(leaves["aux"].sum()) == n                       # every sphere in exactly one leaf
+    st = ctx.stats()
+    print("LBVH build 1M spheres: %.3f ms (%.1f Mprims/s)" % (st.ms_build, n / st.ms_build / 1e3))
+    assert ctx.bvh_info().scene_in_smem == 0
+
+
+# ------------------------------------------------------------------ traversal = brute force
+@pytest.mark.parametrize("scene_name", ["rtiow", "random20k"])
+def test_traversal_equals_brute_force(ctx, oracle_mod, rtiow, scene_name):
+    spheres = rtiow if scene_name == "rtiow" else oracle_mod.random_scene(20000, 0x5EED0001, 30.0, 0)
+    ctx.set_spheres(spheres)
+    ctx.build_bvh()
+    rng = np.random.RandomState(17)
+    n = 200000 if scene_name == "rtiow" else 20000
+    o = (rng.rand(n, 3).astype(np.float32) - np.float32(0.5)) * np.float32(40.0)
+    if scene_name == "rtiow":
+        o[:, 1] = np.abs(o[:, 1]) * np.float32(0.1) + np.float32(0.05)
+    d = rng.randn(n, 3).astype(np.float32)
+    orc = oracle_mod.Oracle(spheres)
+    t0, p0 = orc.closest_hit(o, d, use_bvh=(scene_name != "rtiow"))
+    if scene_name != "rtiow":                                   # spot-check the oracle's BVH against its brute force
+        tb, pb = orc.closest_hit(o[:500], d[:500], use_bvh=False)
+        assert np.array_equal(tb, t0[:500]) and np.array_equal(pb, p0[:500])
+    t1, p1 = ctx.trace_rays(o, d, VN_EXACT)
+    assert (p0 >= 0).sum() > n // 20
+    assert np.array_equal(p0, p1) and np.array_equal(t0, t1)    # IEEE build: bit-exact
+    t2, p2 = ctx.trace_rays(o, d, 0)                            # FAST build: same hits up to float noise
+    same = p0 == p2
+    assert same.mean() > 0.9995
+    hit = same & (p0 >= 0)
+    rel = np.abs(t0[hit] - t2[hit]) / np.abs(t0[hit])          # approximate rcp/sqrt: a few ulp, more at grazing hits
+    assert np.median(rel) < 1e-6 and np.quantile(rel, 0.999) < 1e-3
+
+
+# ------------------------------------------------------------------ unit-level float parity (IEEE build)
+def test_make_color_device(ctx, oracle_mod):
+    rng = np.random.RandomState(2)
+    cols = np.concatenate([rng.rand(20000, 3).astype(np.float32) * np.float32(1.3) - np.float32(0.15),
+                           np.array([[0, 0, 0], [1, 1, 1], [0.0031308, 0.0031307, 0.0031309], [2, -1, 0.999999]], np.float32)])
+    want = oracle_mod.make_color(cols)
+    for flags in (VN_EXACT, 0):
+        got = ctx.make_color(cols, flags)
+        diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
+        assert diff.max() <= 1                                  # powf on the device vs glibc: at most one code value
+        assert (diff > 0).mean() < 2e-3
+        assert (got[:, 3] == 255).all()
+
+
+@pytest.mark.parametrize("mtype,mat", [(0, (0.5, 0.4, 0.3, 0.0)), (1, (0.8, 0.7, 0.6, 0.3)), (1, (0.7, 0.6, 0.5, 0.0)), (2, (0, 0, 0, 1.5))])
+def test_scatter_device_bit_exact(ctx, host_harness, mtype, mat):
+    """Lambertian / metal / dielectric scatter (RayTracer.cu:272-440) in the IEEE build == the same code on the CPU:
+    direction bits, absorbed flag and RNG state after (i.e. the number of draws consumed)."""
+    rng = np.random.RandomState(100 + mtype)
+    n = 50000
+    d = rng.randn(n, 3).astype(np.float32)
+    nr = rng.randn(n, 3).astype(np.float32)
+    nr /= np.linalg.norm(nr, axis=1, keepdims=True).astype(np.float32)
+    flip = (d * nr).sum(axis=1) > 0
+    nr[flip] *= -1                                              # face-forwarded normals, like set_face_normal
+    front = rng.randint(0, 2, n).astype(np.uint8)
+    seeds = rng.randint(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    d_gpu, ok_gpu, s_gpu = ctx.scatter(mtype, mat, d, nr, front, seeds, VN_EXACT)
+    d_cpu = np.zeros((n, 3), np.float32)
+    ok_cpu = np.zeros(n, np.uint8)
+    s_cpu = np.zeros(n, np.uint32)
+    m4 = (C.c_float * 4)(*mat)
+    host_harness.hh_scatter(mtype, m4, ptr(d), ptr(nr), ptr(front), ptr(seeds), n, ptr(d_cpu), ptr(ok_cpu), ptr(s_cpu))
+    assert np.array_equal(s_gpu, s_cpu)
+    assert np.array_equal(ok_gpu, ok_cpu)
+    if mtype == 2:
+        # Schlick uses powf (device) vs glibc powf: a reflect/refract flip needs the draw within 1 ulp of R
+        same = (d_gpu.view(np.uint32) == d_cpu.view(np.uint32)).all(axis=1)
+        assert same.mean() > 0.9999
+    else:
+        assert np.array_equal(d_gpu.view(np.uint32), d_cpu.view(np.uint32))
+    d_fast, ok_fast, s_fast = ctx.scatter(mtype, mat, d, nr, front, seeds, 0)
+    assert (s_fast == s_cpu).mean() > 0.999
+    good = (s_fast == s_cpu) & (ok_fast == ok_cpu)
+    assert np.allclose(d_fast[good], d_cpu[good], rtol=1e-3, atol=1e-4)
+
+
+# ------------------------------------------------------------------ the path: config 1 (BASELINE.json configs[0])
+def test_c1_exact_build_is_bit_identical_to_oracle(rtiow_ctx, oracle_mod, rtiow):
+    """RTIOW final scene 400x225, 10 spp, max depth 50: GPU (IEEE build) vs the CPU oracle -- identical ray counts, every
+    pixel of the float accumulation buffer bit-identical, uchar4 image within one code value (powf)."""
+    W, H, spp, depth = C1["width"], C1["height"], C1["spp"], C1["max_depth"]
+    cam = vb.rtiow_camera(W, H)
+    acc, img, st = render(rtiow_ctx, cam, W, H, spp, 1, depth, flags=VN_EXACT)
+    orc = oracle_mod.Oracle(rtiow)
+    want, ost = orc.render_mean(orc.params(cam.frame(), W, H, spp, 1, depth, atten=oracle_mod.ATTEN_FORWARD, closest=oracle_mod.CLOSEST_BVH))
+    assert st.paths == W * H * spp == ost.paths
+    assert st.segments == ost.segments
+    assert np.array_equal(acc.view(np.uint32), want.view(np.uint32))
+    _, want_img = oracle_mod.accumulate_tonemap(None, want, False, 1.0)
+    d = np.abs(img.astype(np.int32) - want_img.astype(np.int32))
+    assert d.max() <= 1 and (d > 0).mean() < 2e-3
+    # and against the reference's multiplication order (unwind): float re-association only
+    ref_order, _ = orc.render_mean(orc.params(cam.frame(), W, H, spp, 1, depth, atten=oracle_mod.ATTEN_UNWIND, closest=oracle_mod.CLOSEST_BVH))
+    rel = np.abs(acc - ref_order) / np.maximum(np.abs(ref_order), 1e-6)
+    assert rel.max() < 1e-5
+
+
+@pytest.mark.parametrize("sub,depth,spp", [(0, 4, 16), (7, 4, 16), (64, 50, 3), (3, 1, 2), (5, 2, 5)])
+def test_exact_build_other_launch_shapes(rtiow_ctx, oracle_mod, rtiow, sub, depth, spp):
+    W, H = 160, 90
+    cam = vb.rtiow_camera(W, H)
+    acc, img, st = render(rtiow_ctx, cam, W, H, spp, sub, depth, flags=VN_EXACT)
+    orc = oracle_mod.Oracle(rtiow)
+    want, ost = orc.render_mean(orc.params(cam.frame(), W, H, spp, sub, depth, atten=oracle_mod.ATTEN_FORWARD))
+    assert st.segments == ost.segments
+    assert np.array_equal(acc.view(np.uint32), want.view(np.uint32))
+
+
+def test_wavefront_equals_persistent_kernel(rtiow_ctx, oracle_mod, rtiow):
+    """The queue-based wavefront kernels and the persistent path kernel are two schedules of the same math: in the IEEE
+    build their accumulation buffers are bit-identical (per-sample radiances are summed in sample order)."""
+    W, H, spp, depth = 200, 120, 6, 50
+    cam = vb.rtiow_camera(W, H)
+    a, ia, sa = render(rtiow_ctx, cam, W, H, spp, 2, depth, flags=VN_EXACT)
+    rtiow_ctx.set_option("wavefront_slots", 65536)              # small queues: many regenerate/compact iterations
+    b, ib, sb = render(rtiow_ctx, cam, W, H, spp, 2, depth, flags=VN_EXACT | VN_WAVEFRONT)
+    assert sa.segments == sb.segments and sa.paths == sb.paths
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(ia, ib)
+    rtiow_ctx.set_option("wavefront_slots", 1 << 21)
+    c, ic, sc = render(rtiow_ctx, cam, W, H, spp, 2, depth, flags=VN_EXACT | VN_WAVEFRONT)
+    assert np.array_equal(a.view(np.uint32), c.view(np.uint32))
+    f1, _, s1 = render(rtiow_ctx, cam, W, H, spp, 2, depth, flags=0)
+    f2, _, s2 = render(rtiow_ctx, cam, W, H, spp, 2, depth, flags=VN_WAVEFRONT)
+    assert np.array_equal(f1.view(np.uint32), f2.view(np.uint32)) and s1.segments == s2.segments
+
+
+def test_fast_build_meets_baseline_tolerance_at_1024spp(rtiow_ctx, oracle_mod, rtiow):
+    """BASELINE.json: per-channel relative error <= 1e-3 on >= 99.9 % of pixels and PSNR >= 45 dB at 1024 spp, FAST build
+    (the one bench.py times) vs the oracle in the reference's own multiplication order.  400x225, 64 subframes x 16 spp
+    accumulated as a running mean (Renderer::Draw cadence)."""
+    W, H, depth, frames = C1["width"], C1["height"], C1["max_depth"], 64
+    cam = vb.rtiow_camera(W, H)
+    rtiow_ctx.resize(W, H)
+    total_seg = 0
+    for k in range(frames):
+        p = rtiow_ctx.make_params(cam, W, H, 16, k + 1, depth, accum_count=k, flags=VN_NO_TONEMAP)
+        rtiow_ctx.render(p)
+        total_seg += rtiow_ctx.stats().segments
+    got = rtiow_ctx.read_accum()[..., :3].astype(np.float64)
+    orc = oracle_mod.Oracle(rtiow)
+    want = np.zeros((H, W, 4), np.float32)
+    oseg = 0
+    for k in range(frames):
+        mean, ost = orc.render_mean(orc.params(cam.frame(), W, H, 16, k + 1, depth, atten=oracle_mod.ATTEN_UNWIND))
+        want, _ = oracle_mod.accumulate_tonemap(want, mean, k > 0, np.float32(1.0) / np.float32(k + 1))
+        oseg += ost.segments
+    want = want[..., :3].astype(np.float64)
+    rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-12)
+    frac_ok = float((rel.max(axis=-1) <= 1e-3).mean())
+    mse = float(((got - want) ** 2).mean())
+    psnr = 10.0 * np.log10(1.0 / max(mse, 1e-30))
+    print("FAST vs oracle @1024spp: frac(px rel<=1e-3)=%.5f  PSNR=%.1f dB  segments gpu/oracle=%d/%d" % (frac_ok, psnr, total_seg, oseg))
+    assert abs(total_seg - oseg) / oseg < 1e-4
+    assert frac_ok >= 0.999
+    assert psnr >= 45.0
+
+
+# ------------------------------------------------------------------ accumulation, tiles, drop-in API
+def test_renderer_draw_progressive_accumulation(oracle_mod, rtiow):
+    """Renderer::Draw cadence (Renderer.h:35-78): subframe_index 1,2,3..., 16 spp, running-mean blend; camera change resets."""
+    W, H = 96, 54
+    r = vb.Renderer()
+    r.m_flags = VN_EXACT
+    r.m_maxDepth = 6
+    r.Init(vb.Scene())
+    cam = vb.rtiow_camera(W, H)
+    buf = vb.CUDAOutputBuffer(vb.CUDAOutputBuffer.CUDA_DEVICE, W, H)
+    orc = oracle_mod.Oracle(rtiow)
+    want = np.zeros((H, W, 4), np.float32)
+    for k in range(3):
+        r.Draw(cam, buf)
+        mean, _ = orc.render_mean(orc.params(cam.frame(), W, H, 16, k + 1, 6, atten=oracle_mod.ATTEN_FORWARD))
+        want, want_img = oracle_mod.accumulate_tonemap(want, mean, k > 0, np.float32(1.0) / np.float32(k + 1))
+        assert np.array_equal(r.ctx.read_accum().view(np.uint32), want.view(np.uint32)), "frame %d" % k
+        assert np.abs(buf.getHostPointer().astype(np.int32) - want_img.astype(np.int32)).max() <= 1
+    assert r.m_subframe_index == 3
+    cam.SetFocalLength(9.5)                                     # dirty -> accumulation restarts, stream id restarts at 1
+    r.Draw(cam, buf)
+    mean, _ = orc.render_mean(orc.params(cam.frame(), W, H, 16, 1, 6, atten=oracle_mod.ATTEN_FORWARD))
+    assert r.m_subframe_index == 1
+    assert np.array_equal(r.ctx.read_accum().view(np.uint32), mean.view(np.uint32))
+    buf.resize(64, 36)                                          # Q4: accum follows the buffer size
+    cam.SetAspect(64 / 36)
+    r.Draw(cam, buf)
+    assert r.ctx.read_accum().shape == (36, 64, 4)
+    # strict mode: the literal blend weights 1/(subframe_index+1) of RayTracer.cu:208-213, on a zeroed buffer
+    r2 = vb.Renderer()
+    r2.m_flags = VN_EXACT
+    r2.strict_accum = True
+    r2.Init(vb.Scene())
+    cam2 = vb.rtiow_camera(W, H)
+    buf2 = vb.CUDAOutputBuffer(vb.CUDAOutputBuffer.CUDA_DEVICE, W, H)
+    r2.Draw(cam2, buf2)
+    mean, _ = orc.render_mean(orc.params(cam2.frame(), W, H, 16, 1, 4, atten=oracle_mod.ATTEN_FORWARD))
+    want, _ = oracle_mod.accumulate_tonemap(np.zeros_like(mean), mean, True, np.float32(0.5))
+    assert np.array_equal(r2.ctx.read_accum().view(np.uint32), want.view(np.uint32))
+    r.Cleanup()
+    r2.Cleanup()
+
+
+def test_row_tiles_and_partial_sums(rtiow_ctx):
+    """Tile sharding (rows) and sample-range sharding (VN_ACCUM_SUM partial sums): the multi-GPU building blocks."""
+    W, H, spp, depth = 128, 72, 4, 50
+    cam = vb.rtiow_camera(W, H)
+    full, _, sf = render(rtiow_ctx, cam, W, H, spp, 3, depth, flags=VN_EXACT, image=False)
+    rtiow_ctx.reset_accum()
+    segs = 0
+    for rows in ((0, 20), (20, 21), (21, 72)):
+        p = rtiow_ctx.make_params(cam, W, H, spp, 3, depth, flags=VN_EXACT | VN_NO_TONEMAP, rows=rows)
+        rtiow_ctx.render(p)
+        segs += rtiow_ctx.stats().segments
+    tiled = rtiow_ctx.read_accum()
+    assert np.array_equal(full.view(np.uint32), tiled.view(np.uint32)) and segs == sf.segments
+    # two subframes as partial sums, then one tonemap with scale 1/2 == mean of the two frames
+    rtiow_ctx.reset_accum()
+    means = []
+    for sub in (1, 2):
+        m, _, _ = render(rtiow_ctx, cam, W, H, spp, sub, depth, flags=VN_EXACT, image=False)
+        means.append(m)
+    rtiow_ctx.reset_accum()
+    for sub in (1, 2):
+        rtiow_ctx.render(rtiow_ctx.make_params(cam, W, H, spp, sub, depth, flags=VN_EXACT | VN_ACCUM_SUM | VN_NO_TONEMAP))
+    s = rtiow_ctx.read_accum()
+    assert np.array_equal(s[..., :3], (means[0][..., :3] + means[1][..., :3]))
+    img = np.zeros((H, W, 4), np.uint8)
+    rtiow_ctx.tonemap(0.5, ptr(img), VN_IMAGE_HOST | VN_EXACT)
+    import oracle_lib
+    want = oracle_lib.make_color((s[..., :3] * np.float32(0.5)).reshape(-1, 3)).reshape(H, W, 4)
+    assert np.abs(img.astype(np.int32) - want.astype(np.int32)).max() <= 1
+
+
+def test_fused_peer_reduce_tonemap_single_gpu(rtiow_ctx):
+    """vn_reduce_tonemap_peers with 'peers' that live on the same GPU: sum in rank order + tonemap of a row slice."""
+    W, H = 64, 40
+    cam = vb.rtiow_camera(W, H)
+    parts = []
+    ctxs = [vb.Context(0) for _ in range(3)]
+    for k, c in enumerate(ctxs):
+        c.set_spheres(vb.rtiow_final_scene())
+        c.build_bvh()
+        c.resize(W, H)
+        c.render(c.make_params(cam, W, H, 4, k + 1, 50, flags=VN_EXACT | VN_ACCUM_SUM | VN_NO_TONEMAP))
+        parts.append(c.read_accum())
+    ptrs = [c.accum_device_ptr() for c in ctxs]
+    rtiow_ctx.resize(W, H)
+    vb.load().vn_buffer_alloc.restype = C.c_int
+    dev, host = C.c_void_p(), C.c_void_p()
+    assert vb.load().vn_buffer_alloc(0, W * H * 4, 0, C.byref(dev), C.byref(host)) == 0
+    rtiow_ctx.reduce_tonemap_peers(ptrs, 1.0 / 3.0, (10, 30), dev, VN_EXACT)
+    got = rtiow_ctx.read_accum()
+    want = (parts[0][..., :3] + parts[1][..., :3]) + parts[2][..., :3]
+    assert np.array_equal(got[10:30, :, :3], want[10:30])
+    assert (got[:10] == 0).all() and (got[30:] == 0).all()
+    img = np.zeros((H, W, 4), np.uint8)
+    assert vb.load().vn_buffer_copy_to_host(0, ptr(img), dev, img.nbytes) == 0
+    import oracle_lib
+    wimg = oracle_lib.make_color((want * np.float32(1.0 / 3.0)).reshape(-1, 3)).reshape(H, W, 4)
+    assert np.abs(img[10:30].astype(np.int32) - wimg[10:30].astype(np.int32)).max() <= 1
+    vb.load().vn_buffer_free(0, dev, host, 0)
+    for c in ctxs:
+        c.close()
+
+
+def test_empty_single_and_ragged_scenes(ctx, oracle_mod, rtiow):
+    W, H = 33, 17                                               # ragged: not a multiple of the 8x4 work tile
+    cam = vb.rtiow_camera(W, H)
+    for spheres in (rtiow[:0], rtiow[:1], rtiow[1:2], rtiow[:3]):
+        spheres = np.ascontiguousarray(spheres)
+        ctx.set_spheres(spheres)
+        ctx.build_bvh()
+        for flags in (VN_EXACT, VN_EXACT | VN_WAVEFRONT):
+            acc, img, st = render(ctx, cam, W, H, 5, 9, 8, flags=flags)
+            orc = oracle_mod.Oracle(spheres)
+            want, ost = orc.render_mean(orc.params(cam.frame(), W, H, 5, 9, 8, atten=oracle_mod.ATTEN_FORWARD, closest=oracle_mod.CLOSEST_BRUTE))
+            assert st.segments == ost.segments and st.paths == W * H * 5
+            assert np.array_equal(acc.view(np.uint32), want.view(np.uint32))
+    with pytest.raises(vb.Exception):
+        ctx.render(ctx.make_params(cam, W, H, 0, 1, 8))        # spp 0
+    with pytest.raises(vb.Exception):
+        ctx.render(ctx.make_params(cam, 1, H, 1, 1, 8))        # width 1 divides by zero in the reference (RayTracer.cu:173)
+    bad = vb.rtiow_final_scene()[:2].copy()
+    bad["type"][1] = 7
+    with pytest.raises(vb.Exception):
+        ctx.set_spheres(bad)
+
+
+def test_large_scene_from_hbm_matches_oracle(ctx, oracle_mod):
+    """Scene too large for shared memory (nodes + spheres traversed from L2/HBM): dielectric-heavy config-5 mix."""
+    spheres = vb.random_scene(200_000, 0x5EED0002, 60.0, 1)
+    ctx.set_spheres(spheres)
+    ctx.build_bvh()
+    assert ctx.bvh_info().scene_in_smem == 0
+    W, H = 160, 90
+    cam = vb.Camera((0.0, 0.0, 120.0), 40.0, W / H, 0.0, 120.0)
+    cam.SetForward((0.0, 0.0, -1.0))
+    orc = oracle_mod.Oracle(spheres)
+    want, ost = orc.render_mean(orc.params(cam.frame(), W, H, 4, 1, 64, atten=oracle_mod.ATTEN_FORWARD))
+    for flags in (VN_EXACT, VN_EXACT | VN_WAVEFRONT):
+        acc, _, st = render(ctx, cam, W, H, 4, 1, 64, flags=flags, image=False)
+        # distant small spheres: grazing rays inside the float noise of the quadratic may be culled by one BVH and not
+        # the other (tie/grazing order is unspecified in OptiX too) -- allow a handful of pixels
+        bad = (acc.view(np.uint32) != want.view(np.uint32)).any(axis=-1)
+        assert bad.mean() < 1e-3, "mismatching pixels: %d" % bad.sum()
+        assert abs(int(st.segments) - int(ost.segments)) <= 64 * max(1, int(bad.sum()))
+    accf, _, stf = render(ctx, cam, W, H, 4, 1, 64, flags=0, image=False)
+    assert abs(int(stf.segments) - int(ost.segments)) / ost.segments < 0.01
+
+
+def test_counters_and_determinism_at_full_size(rtiow_ctx):
+    """1920x1080 (BASELINE configs[1] frame size), one 16-spp subframe: size-independent properties."""
+    W, H = 1920, 1080
+    cam = vb.rtiow_camera(W, H)
+    a, _, sa = render(rtiow_ctx, cam, W, H, 16, 1, 50, flags=VN_COUNTERS, image=False)
+    b, _, sb = render(rtiow_ctx, cam, W, H, 16, 1, 50, flags=0, image=False)
+    assert sa.paths == sb.paths == W * H * 16
+    assert sa.segments == sb.segments and np.array_equal(a.view(np.uint32), b.view(np.uint32))     # deterministic
+    assert W * H * 16 <= sa.segments <= W * H * 16 * 50
+    assert 2.0 < sa.node_visits / sa.segments < 40.0 and 0.5 < sa.sphere_tests / sa.segments < 20.0
+    assert np.isfinite(a).all() and a[..., :3].min() >= 0.0 and a[..., :3].max() <= 1.0 + 1e-5
+    # sky rows are brighter than ground rows (row 0 is the bottom of the picture)
+    assert a[-1, :, :3].mean() > a[0, :, :3].mean() * 0.5
+    # top half rendered alone == top half of the full frame
+    rtiow_ctx.reset_accum()
+    rtiow_ctx.render(rtiow_ctx.make_params(cam, W, H, 16, 1, 50, flags=VN_NO_TONEMAP, rows=(540, 1080)))
+    t = rtiow_ctx.read_accum()
+    assert np.array_equal(t[540:].view(np.uint32), b[540:].view(np.uint32)) and (t[:540] == 0).all()
+    print("1080p 16spp: %.2f ms, %.1f Mrays/s, nodes/seg %.2f, spheres/seg %.2f" %
+          (sb.ms_render, sb.segments / sb.ms_render / 1e3, sa.node_visits / sa.segments, sa.sphere_tests / sa.segments))
+
+
+def test_accum_checkpoint_resume(rtiow_ctx):
+    W, H = 80, 45
+    cam = vb.rtiow_camera(W, H)
+    for k in range(4):
+        rtiow_ctx.render(rtiow_ctx.make_params(cam, W, H, 4, k + 1, 50, accum_count=k, flags=VN_EXACT | VN_NO_TONEMAP))
+    straight = rtiow_ctx.read_accum()
+    for k in range(2):
+        rtiow_ctx.render(rtiow_ctx.make_params(cam, W, H, 4, k + 1, 50, accum_count=k, flags=VN_EXACT | VN_NO_TONEMAP))
+    saved = rtiow_ctx.read_accum()
+    rtiow_ctx.reset_accum()
+    rtiow_ctx.write_accum(saved)
+    for k in range(2, 4):
+        rtiow_ctx.render(rtiow_ctx.make_params(cam, W, H, 4, k + 1, 50, accum_count=k, flags=VN_EXACT | VN_NO_TONEMAP))
+    assert np.array_equal(rtiow_ctx.read_accum().view(np.uint32), straight.view(np.uint32))
+
+
+def test_cpp_dropin_renders_same_image(oracle_mod, rtiow):
+    """The header-only C++17 Renderer/Scene/Camera/CUDAOutputBuffer shim, used exactly like Core.cpp uses the reference's."""
+    src = r'''
+    #include <cstdio>
+    #include "venusaur/Renderer.h"
+    int main(int argc, char** argv) {
+        Scene scene;
+        Camera camera(venusaur::vec3(13, 2, 3), 20.0f, 96.0f / 54.0f, 0.1f, 10.0f);
+        camera.SetForward(venusaur::vec3(0 - 13, 0 - 2, 0 - 3));
+        Renderer renderer;
+        renderer.SetFlags(VN_EXACT);
+        renderer.Init(scene, "");
+        CUDAOutputBuffer<uchar4> buf(CUDAOutputBufferType::CUDA_DEVICE, 96, 54);
+        for (int i = 0; i < 2; ++i) renderer.Draw(camera, buf);
+        uchar4* px = buf.getHostPointer();
+        FILE* f = fopen(argv[1], "wb");
+        fwrite(px, 4, 96 * 54, f);
+        fclose(f);
+        vn_stats st = renderer.Stats();
+        printf("%llu\n", (unsigned long long)st.segments);
+        renderer.Cleanup();
+        try { renderer.Draw(camera, buf); return 3; } catch (const Exception&) {}
+        return 0;
+    }'''
+    out = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out, exist_ok=True)
+    cpp, exe, raw = os.path.join(out, "dropin_gpu.cpp"), os.path.join(out, "dropin_gpu"), os.path.join(out, "dropin_gpu.raw")
+    open(cpp, "w").write(src)
+    libdir = os.path.dirname(vb.lib_path())
+    subprocess.run(["g++", "-std=c++17", "-I" + os.path.join(ROOT, "include"), cpp, "-o", exe, "-L" + libdir, "-lvenusaur_b200",
+                    "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([exe, raw], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    img = np.fromfile(raw, np.uint8).reshape(54, 96, 4)
+    cam = oracle_mod.rtiow_camera(96, 54)
+    orc = oracle_mod.Oracle(rtiow)
+    want = np.zeros((54, 96, 4), np.float32)
+    for k in range(2):
+        mean, ost = orc.render_mean(orc.params(cam, 96, 54, 16, k + 1, 4, atten=oracle_mod.ATTEN_FORWARD))
+        want, wimg = oracle_mod.accumulate_tonemap(want, mean, k > 0, np.float32(1.0) / np.float32(k + 1))
+    assert np.abs(img.astype(np.int32) - wimg.astype(np.int32)).max() <= 1
+    assert int(r.stdout.strip()) == ost.segments

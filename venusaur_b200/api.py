@@ -130,6 +130,7 @@ class Context:
             raise Exception("vn_create failed (%d): %s" % (rc, self.lib.vn_last_error(None).decode()))
         self.h = h
         self.device = device
+        self.width = self.height = 0
 
     def close(self):
         if getattr(self, "h", None):
@@ -195,6 +196,7 @@ class Context:
 
     def render(self, params: vn_params):
         self._check(self.lib.vn_render(self.h, C.byref(params)), "vn_render")
+        self.width, self.height = params.width, params.height      # vn_render (re)sizes accum to the frame
 
     def tonemap(self, scale: float, image, flags: int = 0):
         self._check(self.lib.vn_tonemap(self.h, scale, image, flags), "vn_tonemap")
