@@ -155,7 +155,7 @@ def run_ours(args):
     import torch
     import venusaur_b200 as vb
     from venusaur_b200 import sharding
-    from venusaur_b200 import VN_ACCUM_SUM, VN_ASYNC, VN_COUNTERS, VN_IMAGE_HOST, VN_NO_TONEMAP, VN_WAVEFRONT
+    from venusaur_b200 import VN_ACCUM_SUM, VN_ASYNC, VN_COUNTERS, VN_FAST, VN_IMAGE_HOST, VN_NO_TONEMAP, VN_POOL, VN_WAVEFRONT
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -190,7 +190,10 @@ def run_ours(args):
         cam = vb.Camera((0.0, 0.0, 200.0), 40.0, width / height, 0.0, 200.0)
         cam.SetForward((0.0, 0.0, -1.0))
     ctx.resize(width, height)
-    kflag = VN_WAVEFRONT if args.kernel == "wavefront" else 0
+    kflag = {"wavefront": VN_WAVEFRONT, "pool": VN_POOL, "persistent": 0}[args.kernel] | (VN_FAST if args.fast else 0)
+    for opt in ("pool_slots", "pool_threads", "pool_service", "pool_leaf_batch"):
+        if getattr(args, opt):
+            ctx.set_option(opt, getattr(args, opt))
 
     stream = torch.cuda.ExternalStream(ctx.lib.vn_stream(ctx.h), device=dev)      # the stream the kernels are launched on
     image = torch.zeros((height, width, 4), dtype=torch.uint8, device=dev)
@@ -247,7 +250,7 @@ def run_ours(args):
                 ctx.tonemap(scale, image.data_ptr(), 0)
 
     # ---- instrumented pass (untimed): V_node / V_sphere per segment for the roofline model
-    ctx.render(ctx.make_params(cam, width, height, spp, 1, depth, flags=VN_COUNTERS | VN_NO_TONEMAP))
+    ctx.render(ctx.make_params(cam, width, height, spp, 1, depth, flags=VN_COUNTERS | VN_NO_TONEMAP | (VN_FAST if args.fast else 0)))
     cst = ctx.stats()
     v_node = cst.node_visits / max(1, cst.segments)
     v_sphere = cst.sphere_tests / max(1, cst.segments)
@@ -359,7 +362,7 @@ def run_ours(args):
             "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": describe(args.workload, K), "parallelism": "subframe(sample-range) sharding x%d, scene+BVH replicated" % world,
-                       "kernel": args.kernel, "build": "FAST (fma, approx rcp/rsqrt)", "l2_flush": "256 MiB fill between timed steps",
+                       "kernel": args.kernel, "build": ("VN_FAST (relaxed numerics; not within the image tolerance)" if args.fast else "default IEEE build, bit-identical to the oracle"), "l2_flush": "256 MiB fill between timed steps",
                        "scene_in_smem": bool(info.scene_in_smem), "bvh_nodes": int(info.num_nodes), "leaf_size": int(info.max_leaf_size),
                        "bvh_build_ms": build_ms, "reduce": (args.reduce if world > 1 else "none"), "reduce_ms": fin_ms},
             "clocks": clk,
@@ -397,12 +400,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--kernel", default="persistent", choices=["persistent", "wavefront"])
+    ap.add_argument("--kernel", default="persistent", choices=["persistent", "wavefront", "pool"])
+    for opt in ("pool-slots", "pool-threads", "pool-service", "pool-leaf-batch"):
+        ap.add_argument("--" + opt, type=int, default=0)
     ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--leaf-size", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fast", action="store_true", help="opt-in relaxed-numerics kernels (VN_FAST)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else max(1, args.warmup)
     if args.impl == "reference":

@@ -53,15 +53,19 @@ typedef struct vn_sphere {
 
 /* vn_params.flags */
 enum {
-    VN_EXACT          = 1u << 0, /* IEEE build of the kernels (no FMA contraction, IEEE div/sqrt, FP64 where the
-                                    reference uses it): bit-identical to the host oracle.  Default is the FAST build. */
+    VN_EXACT          = 1u << 0, /* the default build, named for explicitness: IEEE kernels (no FMA contraction, IEEE div/sqrt),
+                                    bit-identical to the host oracle -- the build that meets BASELINE.json's image tolerance */
     VN_IMAGE_HOST     = 1u << 1, /* params.image is HOST memory: the uchar4 frame is copied D2H before returning
                                     (what CUDAOutputBuffer::getHostPointer does, CUDAOutputBuffer.h:348-372) */
     VN_ACCUM_SUM      = 1u << 2, /* accum += frame mean (multi-GPU partial sums) instead of the running mean */
     VN_NO_TONEMAP     = 1u << 3, /* do not write params.image */
     VN_WAVEFRONT      = 1u << 4, /* use the queue-based wavefront kernels instead of the persistent path kernel */
     VN_COUNTERS       = 1u << 5, /* instrumented launch: also count BVH node visits and sphere tests */
-    VN_ASYNC          = 1u << 6  /* do not synchronise the stream before returning (stats are then stale) */
+    VN_ASYNC          = 1u << 6, /* do not synchronise the stream before returning (stats are then stale) */
+    VN_POOL           = 1u << 8, /* use the shared-memory warp-pool wavefront kernel (pool_kernels.cu) */
+    VN_FAST           = 1u << 7  /* relaxed-numerics build (FMA contraction, approximate rcp/rsqrt/sqrt, FP32 for the FP64
+                                    fragments): a few % faster, PSNR > 60 dB vs the oracle but NOT within the 1e-3 per-pixel
+                                    tolerance at 1024 spp (individual paths diverge); never the default */
 };
 
 /* Launch parameters = Params (RayTracer.h:3-17) minus the OptiX handle, plus what the reference hard-codes:
@@ -121,7 +125,7 @@ VN_API const char* vn_version(void);
 
 /* ---- scene: Renderer::CreateSBT (Renderer.h:452-520) + BuildAccelerationStructures (Renderer.h:160-255) ---- */
 VN_API int vn_set_spheres(vn_handle h, const vn_sphere* host_spheres, uint64_t n);
-VN_API int vn_set_option(vn_handle h, const char* name, double value); /* "leaf_size", "aabb_pad", "threads", "blocks_per_sm" */
+VN_API int vn_set_option(vn_handle h, const char* name, double value); /* "leaf_size", "aabb_pad", "threads", "blocks_per_sm", "pool_slots", "pool_threads", "pool_service", "pool_leaf_batch", ... */
 VN_API int vn_build_bvh(vn_handle h);
 VN_API int vn_get_bvh_info(vn_handle h, vn_bvh_info* out);
 VN_API int vn_read_bvh(vn_handle h, vn_node32* host_nodes, uint64_t cap_nodes, uint32_t* host_prim_order, uint64_t cap_prims);

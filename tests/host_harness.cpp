@@ -199,11 +199,110 @@ extern "C" void hh_scatter(uint32_t type, const float* mat4, const float* dirs, 
         uint32_t seed = seeds[i];
         f3 out = mk3(0.0f);
         bool ok = true;
-        if (type == 0u) out = scatter_lambertian(nrm, seed);
-        else if (type == 1u) ok = scatter_metal(d, nrm, mat4[3], seed, out);
-        else out = scatter_dielectric(d, nrm, front[i] != 0, mat4[3], seed);
+        if (type == 0u) out = scatter_lambertian(nrm, random_in_unit_sphere(seed));
+        else if (type == 1u) ok = scatter_metal(normalize(d), nrm, mat4[3], random_in_unit_sphere(seed), out);
+        else out = scatter_dielectric(normalize(d), nrm, front[i] != 0, mat4[3], seed);
         dirs_out[3 * i] = out.x; dirs_out[3 * i + 1] = out.y; dirs_out[3 * i + 2] = out.z;
         scattered[i] = ok ? 1 : 0;
         seeds_out[i] = seed;
     }
+}
+
+// Histogram of BVH node-pair visits and sphere tests per ray segment (for scheduling studies; tools/simt_model.py).
+extern "C" void hh_visit_histogram(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pad_rel, const hh_params* P,
+                                   uint64_t* node_hist, uint64_t* sphere_hist, uint32_t bins) {
+    HostBvh B;
+    build(s, n, leaf_size, pad_rel, B);
+    SceneView sc{B.nodes.data(), B.geom.data(), B.mat.data(), B.type.data(), B.root_link};
+    Camera cam;
+    cam.origin = mk3(P->origin[0], P->origin[1], P->origin[2]);
+    cam.u = mk3(P->u[0], P->u[1], P->u[2]); cam.v = mk3(P->v[0], P->v[1], P->v[2]); cam.w = mk3(P->w[0], P->w[1], P->w[2]);
+    cam.u_unit = normalize(cam.u); cam.v_unit = normalize(cam.v);
+    cam.lens_radius = P->lens_radius;
+    cam.wm1 = (float)(P->width - 1); cam.hm1 = (float)(P->height - 1);
+    cam.inv_wm1 = 1.0f / cam.wm1; cam.inv_hm1 = 1.0f / cam.hm1;
+    for (uint32_t px = 0; px < P->width * P->height; px++) {
+        uint32_t seed = tea4(px, P->subframe_index);
+        for (uint32_t k = 0; k < P->spp; k++) {
+            PathState st;
+            camera_ray(cam, px % P->width, px / P->width, seed, st.o, st.d);
+            st.thr = mk3(1.0f); st.seed = seed; st.depth = (int)P->max_depth - 1;
+            f3 result;
+            while (true) {
+                float t; int prim;
+                TraceCounters cnt{0, 0};
+                closest_hit<true>(sc.nodes, sc.geom, sc.root_link, st.o, st.d, t, prim, cnt);
+                node_hist[std::min(cnt.nodes, bins - 1)]++;
+                sphere_hist[std::min(cnt.spheres, bins - 1)]++;
+                if (!shade_segment(sc, st, t, prim, result)) break;
+            }
+        }
+    }
+}
+
+// Per-ray step sequences (0 = node-pair step, k>0 = leaf step testing k spheres, 255 = end of ray), for the SIMT
+// scheduling model in tools/simt_model.py.  Same visiting order as closest_hit().
+static void trace_sequence(const SceneView& sc, f3 o, f3 d, std::vector<uint8_t>& out) {
+    float tbest = kTMax;
+    const f3 idir = mk3(rcp(d.x), rcp(d.y), rcp(d.z));
+    const f3 ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
+    const float a = dot(d, d), inv_a = rcp(a);
+    uint32_t stack[kStackSize]; int sp = 0; uint32_t cur = sc.root_link;
+    while (cur != kEmptyScene) {
+        if (!(cur & kLeafFlag)) {
+            out.push_back(0);
+            const node_f4 l0 = sc.nodes[2 * cur], l1 = sc.nodes[2 * cur + 1], r0 = sc.nodes[2 * cur + 2], r1 = sc.nodes[2 * cur + 3];
+            float tl, tr;
+            const bool hl = box_hit(l0, l1, idir, ood, tbest, tl), hr = box_hit(r0, r1, idir, ood, tbest, tr);
+            const uint32_t ll = f2u(l0.w), lr = f2u(r0.w);
+            if (hl && hr) { const bool lf = tl <= tr; cur = lf ? ll : lr; stack[sp++] = lf ? lr : ll; }
+            else if (hl) cur = ll; else if (hr) cur = lr; else cur = sp ? stack[--sp] : kEmptyScene;
+        } else {
+            const uint32_t first = (cur & 0x7FFFFFFFu) >> 3, count = (cur & 7u) + 1u;
+            out.push_back((uint8_t)count);
+            for (uint32_t k = 0; k < count; k++) {
+                const node_f4 g = sc.geom[first + k];
+                const float t = sphere_root(o, d, a, inv_a, g.x, g.y, g.z, g.w, kTMin, tbest);
+                if (t >= 0.0f) tbest = t;
+            }
+            cur = sp ? stack[--sp] : kEmptyScene;
+        }
+    }
+    out.push_back(255);
+}
+
+extern "C" uint64_t hh_step_sequences(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pad_rel, const hh_params* P,
+                                      uint8_t* out, uint64_t cap) {
+    HostBvh B;
+    build(s, n, leaf_size, pad_rel, B);
+    SceneView sc{B.nodes.data(), B.geom.data(), B.mat.data(), B.type.data(), B.root_link};
+    Camera cam;
+    cam.origin = mk3(P->origin[0], P->origin[1], P->origin[2]);
+    cam.u = mk3(P->u[0], P->u[1], P->u[2]); cam.v = mk3(P->v[0], P->v[1], P->v[2]); cam.w = mk3(P->w[0], P->w[1], P->w[2]);
+    cam.u_unit = normalize(cam.u); cam.v_unit = normalize(cam.v);
+    cam.lens_radius = P->lens_radius;
+    cam.wm1 = (float)(P->width - 1); cam.hm1 = (float)(P->height - 1);
+    cam.inv_wm1 = 1.0f / cam.wm1; cam.inv_hm1 = 1.0f / cam.hm1;
+    std::vector<uint8_t> seq;
+    // pixel-major like the persistent kernel: each pixel's samples/segments are consecutive; 254 separates pixels
+    for (uint32_t px = 0; px < P->width * P->height; px++) {
+        uint32_t seed = tea4(px, P->subframe_index);
+        for (uint32_t k = 0; k < P->spp; k++) {
+            PathState st;
+            seq.push_back(253);   // a new path starts (camera ray)
+            camera_ray(cam, px % P->width, px / P->width, seed, st.o, st.d);
+            st.thr = mk3(1.0f); st.seed = seed; st.depth = (int)P->max_depth - 1;
+            f3 result;
+            while (true) {
+                trace_sequence(sc, st.o, st.d, seq);
+                float t; int prim; TraceCounters cnt{0, 0};
+                closest_hit<false>(sc.nodes, sc.geom, sc.root_link, st.o, st.d, t, prim, cnt);
+                if (!shade_segment(sc, st, t, prim, result)) break;
+            }
+        }
+        seq.push_back(254);
+    }
+    const uint64_t m = std::min<uint64_t>(cap, seq.size());
+    if (out) memcpy(out, seq.data(), m);
+    return seq.size();
 }

@@ -198,3 +198,13 @@ def test_cpp_dropin_headers_compile():
     subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"), cpp, "-o", exe,
                     "-L" + libdir, "-lvenusaur_b200", "-Wl,-rpath," + libdir], check=True)
     assert subprocess.run([exe]).returncode == 0
+
+
+def test_near_zero_float_threshold_equals_double_compare():
+    """vn_math.cuh replaces near_zero's double compare (RayTracer.cu:8-13) by a float compare; they agree for every float
+    around the threshold."""
+    c = np.float32(9.99999993922529e-09)
+    assert float(c) < 1e-8 <= float(np.nextafter(c, np.float32(1)))
+    xs = np.float32(1e-8) + np.arange(-2000, 2000, dtype=np.float32) * np.float32(1e-15)
+    xs = np.concatenate([xs, np.array([0, 1e-9, 1e-7, c, np.nextafter(c, np.float32(1)), np.nextafter(c, np.float32(0))], np.float32)])
+    assert np.array_equal(xs.astype(np.float64) < 1e-8, xs <= c)

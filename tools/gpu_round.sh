@@ -10,6 +10,8 @@ echo "=== smoke"
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/smoke.log
 echo "=== bench"
 timeout 600 python bench.py --steps ${BENCH_STEPS:-64} --warmup 3 2>&1 | tail -3 | tee gpurun_out/bench.log
+echo "=== bench --fast"
+timeout 600 python bench.py --steps 16 --warmup 3 --fast --no-cpu-baseline 2>&1 | tail -3 | tee gpurun_out/bench_fast.log
 if [ "${WITH_WAVEFRONT:-1}" = "1" ]; then
   echo "=== bench wavefront"
   timeout 600 python bench.py --steps 8 --warmup 3 --kernel wavefront --no-cpu-baseline 2>&1 | tail -3 | tee gpurun_out/bench_wavefront.log

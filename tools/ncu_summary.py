@@ -1,0 +1,57 @@
+#!/usr/bin/env python
+"""Summarises an exported ncu report: key raw metrics + the hottest source lines (needs -lineinfo).
+usage: ncu_summary.py raw.csv source.csv [n_lines]"""
+import csv
+import sys
+
+
+def fl(x):
+    try:
+        return float(x.replace(",", ""))
+    except (ValueError, AttributeError):
+        return 0.0
+
+
+def main():
+    raw, src = sys.argv[1], sys.argv[2]
+    nlines = int(sys.argv[3]) if len(sys.argv) > 3 else 30
+    rows = list(csv.reader(open(raw)))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    d = {h: (vals[i], units[i]) for i, h in enumerate(hdr)}
+    keys = ["Kernel Name", "gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+            "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers",
+            "launch__occupancy_limit_shared_mem", "dram__bytes_read.sum", "dram__bytes_write.sum", "sm__cycles_elapsed.avg",
+            "smsp__sass_average_branch_targets_threads_uniform.pct", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+            "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum",
+            "smsp__inst_executed_op_shared_ld.sum"]
+    for k in keys:
+        if k in d:
+            print("%-70s %s %s" % (k, d[k][0], d[k][1]))
+    print("--- warp stall reasons (warps per issue-active cycle)")
+    for h in hdr:
+        if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio") and "not_issued" not in h:
+            print("  %-24s %s" % (h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")], d[h][0]))
+    total_w = fl(d["smsp__inst_executed.sum"][0])
+    rows = list(csv.reader(open(src)))
+    hidx = [i for i, r in enumerate(rows) if r and r[0] == "Line No"]
+    allrows = []
+    for h in hidx:
+        fname = rows[h - 2][1] if h >= 2 else ""
+        if not fname.endswith((".cu", ".cuh")):
+            continue
+        H = rows[h]
+        ci, ti = H.index("Instructions Executed"), H.index("Thread Instructions Executed")
+        for r in rows[h + 1:]:
+            if not r or r[0] in ("File Path", "Function Name", "Line No"):
+                break
+            allrows.append((fl(r[ci]), fl(r[ti]), fname.split("/")[-1], r[0], r[1].strip()))
+    s_w = sum(a for a, *_ in allrows)
+    print("--- hottest source lines (share of warp instructions in .cu/.cuh sources, avg active threads)")
+    for w, t, f, ln, text in sorted(allrows, key=lambda x: -x[0])[:nlines]:
+        print("%6.2f%% act=%4.1f %s:%s  %s" % (100 * w / s_w, t / max(w, 1), f, ln, text[:100]))
+    print("sum of source-attributed warp inst %.3e, kernel total %.3e" % (s_w, total_w))
+
+
+if __name__ == "__main__":
+    main()

@@ -49,7 +49,7 @@ class vn_node32(C.Structure):
 VN_OK = 0
 VN_LAMBERTIAN, VN_METAL, VN_DIELECTRIC = 0, 1, 2
 VN_EXACT, VN_IMAGE_HOST, VN_ACCUM_SUM, VN_NO_TONEMAP = 1 << 0, 1 << 1, 1 << 2, 1 << 3
-VN_WAVEFRONT, VN_COUNTERS, VN_ASYNC = 1 << 4, 1 << 5, 1 << 6
+VN_WAVEFRONT, VN_COUNTERS, VN_ASYNC, VN_FAST, VN_POOL = 1 << 4, 1 << 5, 1 << 6, 1 << 7, 1 << 8
 
 # name -> (restype, argtypes); must list every VN_API symbol of include/venusaur_b200.h (checked by tests)
 _P = C.POINTER

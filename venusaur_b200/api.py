@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib as L
-from ._lib import (VN_ACCUM_SUM, VN_ASYNC, VN_COUNTERS, VN_DIELECTRIC, VN_EXACT, VN_IMAGE_HOST, VN_LAMBERTIAN,  # noqa: F401
+from ._lib import (VN_ACCUM_SUM, VN_ASYNC, VN_COUNTERS, VN_DIELECTRIC, VN_EXACT, VN_FAST, VN_IMAGE_HOST, VN_POOL, VN_LAMBERTIAN,  # noqa: F401
                    VN_METAL, VN_NO_TONEMAP, VN_WAVEFRONT, vn_bvh_info, vn_node32, vn_params, vn_sphere, vn_stats)
 
 SPHERE_DTYPE = np.dtype([("cx", "f4"), ("cy", "f4"), ("cz", "f4"), ("r", "f4"), ("ax", "f4"), ("ay", "f4"),

@@ -31,6 +31,8 @@ UNITS = [
     ("path_kernels.cu", "path_fast.o", ["-DVN_EXACT=0", "-fmad=true", "-ftz=true"]),
     ("wavefront.cu", "wavefront_exact.o", ["-DVN_EXACT=1", "-fmad=false"]),
     ("wavefront.cu", "wavefront_fast.o", ["-DVN_EXACT=0", "-fmad=true", "-ftz=true"]),
+    ("pool_kernels.cu", "pool_exact.o", ["-DVN_EXACT=1", "-fmad=false"]),
+    ("pool_kernels.cu", "pool_fast.o", ["-DVN_EXACT=0", "-fmad=true", "-ftz=true"]),
 ]
 
 

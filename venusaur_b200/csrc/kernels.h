@@ -87,7 +87,11 @@ constexpr int kWfArraysTotal = 2 * kWfStateArrays + 2 + 4;   // 4-byte arrays of
                                const uint8_t* front, const uint32_t* seeds, uint64_t n, float* dirs_out,               \
                                uint8_t* scattered, uint32_t* seeds_out, cudaStream_t stream);                          \
     cudaError_t launch_wavefront(const RenderLaunch& p, const WavefrontBuffers& wf, int num_sms, cudaStream_t stream,   \
-                                 uint32_t* launches);
+                                 uint32_t* launches);                                                                  \
+    size_t pool_smem_bytes(uint32_t num_nodes, uint32_t num_spheres, bool scene_in_smem, int warps, uint32_t slots);    \
+    int pool_max_blocks_per_sm(bool scene_in_smem, int threads, size_t smem);                                          \
+    cudaError_t launch_render_pool(const RenderLaunch& p, bool scene_in_smem, int threads, int blocks, uint32_t slots,  \
+                                   uint32_t service_threshold, uint32_t leaf_batch, cudaStream_t stream);
 
 namespace exact { VN_DECLARE_KERNEL_API }
 namespace fast { VN_DECLARE_KERNEL_API }

@@ -12,7 +12,8 @@
 //   * the whole scene (32-byte BVH nodes, sphere geometry, materials) is staged once per CTA into shared memory when
 //     it fits (RTIOW: ~35 KB), so traversal never leaves the SM: LDS.128 node fetches, no L2/HBM traffic at all;
 //     larger scenes are traversed straight from L2/HBM through the same code (128-bit __ldg loads).
-//   * accumulate + sRGB quantise are fused at the end of each pixel (RayTracer.cu:206-216).
+//   * the accumulate step (RayTracer.cu:206-215) is fused at the end of each pixel; sRGB + quantise (:216) is the
+//     coalesced k_tonemap launched right behind (one pixel per thread, 128-byte uchar4 stores per warp).
 #include <cooperative_groups.h>
 #include <cooperative_groups/reduce.h>
 
@@ -58,7 +59,8 @@ __device__ __forceinline__ void finish_pixel(const RenderLaunch& p, uint32_t pix
         mean = mk3(prev.x, prev.y, prev.z) + mean;
     }
     p.accum[pix] = make_float4(mean.x, mean.y, mean.z, 1.0f);    // RayTracer.cu:215
-    if (p.image) p.image[pix] = make_color_u32(mean);            // RayTracer.cu:216
+    // RayTracer.cu:216 (make_color) runs afterwards in k_tonemap: three powf per pixel executed by the one or two lanes
+    // that happen to finish a pixel in this iteration would cost every other lane of the warp the same issue slots.
 }
 
 template <bool kSmem, bool kCount>
@@ -220,9 +222,9 @@ __global__ void k_scatter(uint32_t type, float4 mat, const float* __restrict__ d
     uint32_t seed = seeds[i];
     f3 out = mk3(0.0f);
     bool ok = true;
-    if (type == 0u) out = scatter_lambertian(nrm, seed);
-    else if (type == 1u) ok = scatter_metal(d, nrm, mat.w, seed, out);
-    else out = scatter_dielectric(d, nrm, front[i] != 0, mat.x, seed);
+    if (type == 0u) out = scatter_lambertian(nrm, random_in_unit_sphere(seed));
+    else if (type == 1u) ok = scatter_metal(normalize(d), nrm, mat.w, random_in_unit_sphere(seed), out);
+    else out = scatter_dielectric(normalize(d), nrm, front[i] != 0, mat.x, seed);
     dirs_out[3 * i] = out.x; dirs_out[3 * i + 1] = out.y; dirs_out[3 * i + 2] = out.z;
     scattered[i] = ok ? 1 : 0;
     seeds_out[i] = seed;

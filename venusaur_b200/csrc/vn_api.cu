@@ -54,6 +54,7 @@ struct vn_context {
     int blocks_per_sm = 0;            // 0 = occupancy
     size_t smem_scene_limit = 100 * 1024;
     uint32_t wavefront_slots = 1u << 21;
+    uint32_t pool_slots = 96, pool_threads = 768, pool_service = 8, pool_leaf_batch = 8;
 
     vn_stats stats{};
     bool stats_pending = false;      // an async vn_render whose counters have not been folded into stats yet
@@ -225,6 +226,10 @@ int vn_set_option(vn_handle c, const char* name, double value) {
     else if (k == "blocks_per_sm") { VN_REQUIRE(c, value >= 0 && value <= 32, "blocks_per_sm must be in [0,32]"); c->blocks_per_sm = (int)value; }
     else if (k == "smem_scene_limit") { VN_REQUIRE(c, value >= 0, "smem_scene_limit must be >= 0"); c->smem_scene_limit = (size_t)value; }
     else if (k == "wavefront_slots") { VN_REQUIRE(c, value >= 1024 && value <= (double)(1u << 26), "wavefront_slots out of range"); c->wavefront_slots = (uint32_t)value; free_wavefront(c->wf); c->wf_sample_floats_ = 0; }
+    else if (k == "pool_slots") { VN_REQUIRE(c, value >= 32 && value <= 1024, "pool_slots must be in [32,1024]"); c->pool_slots = (uint32_t)value; }
+    else if (k == "pool_threads") { VN_REQUIRE(c, value >= 32 && value <= 768 && ((int)value % 32) == 0, "pool_threads must be a multiple of 32 in [32,768]"); c->pool_threads = (uint32_t)value; }
+    else if (k == "pool_service") { VN_REQUIRE(c, value >= 1 && value <= 32, "pool_service must be in [1,32]"); c->pool_service = (uint32_t)value; }
+    else if (k == "pool_leaf_batch") { VN_REQUIRE(c, value >= 1 && value <= 33, "pool_leaf_batch must be in [1,33]"); c->pool_leaf_batch = (uint32_t)value; }
     else return fail(c, VN_ERR_INVALID, "vn_set_option: unknown option '" + k + "'");
     return VN_OK;
 }
@@ -445,7 +450,7 @@ int vn_render(vn_handle c, const vn_params* p) {
         if (host_image) { const int rc = ensure_image_tmp(c, pixels); if (rc != VN_OK) return rc; L.image = c->image_tmp; }
         else L.image = static_cast<uint32_t*>(p->image);
     }
-    const bool exact_build = (p->flags & VN_EXACT) != 0;
+    const bool exact_build = !(p->flags & VN_FAST);
     const bool count = (p->flags & VN_COUNTERS) != 0;
     uint32_t launches = 0;
 
@@ -458,6 +463,32 @@ int vn_render(vn_handle c, const vn_params* p) {
         if (rc != VN_OK) return rc;
         VN_CUDA(c, exact_build ? exact::launch_wavefront(L, c->wf, c->num_sms, c->stream, &launches)
                                : fast::launch_wavefront(L, c->wf, c->num_sms, c->stream, &launches));
+    } else if ((p->flags & VN_POOL) && !count && p->samples_per_pixel < 32768u && p->max_depth < 32768u) {
+        // shared-memory warp-pool wavefront kernel; the scene is staged next to the pools when both fit
+        const int threads = (int)c->pool_threads;
+        bool in_smem = scene_fits_smem(c);
+        size_t smem = exact_build ? exact::pool_smem_bytes(L.num_nodes, L.num_spheres, in_smem, threads / 32, c->pool_slots)
+                                  : fast::pool_smem_bytes(L.num_nodes, L.num_spheres, in_smem, threads / 32, c->pool_slots);
+        if (in_smem && smem > c->smem_optin) {
+            in_smem = false;
+            smem = exact::pool_smem_bytes(L.num_nodes, L.num_spheres, false, threads / 32, c->pool_slots);
+        }
+        if (smem > c->smem_optin) return fail(c, VN_ERR_INVALID, "vn_render: pool_slots x pool_threads does not fit in shared memory");
+        int per_sm = exact_build ? exact::pool_max_blocks_per_sm(in_smem, threads, smem) : fast::pool_max_blocks_per_sm(in_smem, threads, smem);
+        if (per_sm <= 0) return fail(c, VN_ERR_CUDA, "vn_render: occupancy query failed for the pool kernel");
+        int blocks = c->num_sms * per_sm;
+        const uint64_t slots_per_block = (uint64_t)(threads / 32) * c->pool_slots;
+        const uint64_t max_blocks = ((uint64_t)L.total_work + slots_per_block - 1) / slots_per_block;
+        if ((uint64_t)blocks > max_blocks) blocks = (int)std::max<uint64_t>(1, max_blocks);
+        VN_CUDA(c, exact_build ? exact::launch_render_pool(L, in_smem, threads, blocks, c->pool_slots, c->pool_service, c->pool_leaf_batch, c->stream)
+                               : fast::launch_render_pool(L, in_smem, threads, blocks, c->pool_slots, c->pool_service, c->pool_leaf_batch, c->stream));
+        launches += 1;
+        if (L.image) {
+            const uint64_t begin = (uint64_t)L.row_begin * L.width, npx = (uint64_t)(L.row_end - L.row_begin) * L.width;
+            VN_CUDA(c, exact_build ? exact::launch_tonemap(L.accum + begin, 1.0f, L.image + begin, npx, c->stream)
+                                   : fast::launch_tonemap(L.accum + begin, 1.0f, L.image + begin, npx, c->stream));
+            launches += 1;
+        }
     } else {
         KernelConfig cfg;
         cfg.threads = c->threads;
@@ -476,6 +507,13 @@ int vn_render(vn_handle c, const vn_params* p) {
         if ((uint64_t)cfg.blocks > max_blocks) cfg.blocks = (int)std::max<uint64_t>(1, max_blocks);
         VN_CUDA(c, exact_build ? exact::launch_render_persistent(L, cfg, c->stream) : fast::launch_render_persistent(L, cfg, c->stream));
         launches += 1;
+        if (L.image) {
+            // sRGB + quantise of the rows just rendered (RayTracer.cu:216), as a coalesced kernel behind the path kernel
+            const uint64_t begin = (uint64_t)L.row_begin * L.width, count = (uint64_t)(L.row_end - L.row_begin) * L.width;
+            VN_CUDA(c, exact_build ? exact::launch_tonemap(L.accum + begin, 1.0f, L.image + begin, count, c->stream)
+                                   : fast::launch_tonemap(L.accum + begin, 1.0f, L.image + begin, count, c->stream));
+            launches += 1;
+        }
     }
     VN_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     if (host_image) VN_CUDA(c, cudaMemcpyAsync(p->image, c->image_tmp, pixels * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -498,7 +536,7 @@ int vn_tonemap(vn_handle c, float scale, void* image, uint32_t flags) {
     const uint64_t pixels = (uint64_t)c->width * c->height;
     uint32_t* dst = static_cast<uint32_t*>(image);
     if (flags & VN_IMAGE_HOST) { const int rc = ensure_image_tmp(c, pixels); if (rc != VN_OK) return rc; dst = c->image_tmp; }
-    VN_CUDA(c, (flags & VN_EXACT) ? exact::launch_tonemap(c->accum, scale, dst, pixels, c->stream) : fast::launch_tonemap(c->accum, scale, dst, pixels, c->stream));
+    VN_CUDA(c, !(flags & VN_FAST) ? exact::launch_tonemap(c->accum, scale, dst, pixels, c->stream) : fast::launch_tonemap(c->accum, scale, dst, pixels, c->stream));
     c->stats.kernel_launches_total += 1;
     if (flags & VN_IMAGE_HOST) VN_CUDA(c, cudaMemcpyAsync(image, c->image_tmp, pixels * 4, cudaMemcpyDeviceToHost, c->stream));
     if (!(flags & VN_ASYNC) || (flags & VN_IMAGE_HOST)) VN_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -516,7 +554,7 @@ int vn_reduce_tonemap_peers(vn_handle c, const void* const* peer_accum, uint32_t
     for (uint32_t i = 0; i < n_peers; i++) peers[i] = static_cast<const float4*>(peer_accum[i]);
     const uint64_t begin = (uint64_t)row_begin * c->width, end = (uint64_t)row_end * c->width;
     uint32_t* img = static_cast<uint32_t*>(image);
-    VN_CUDA(c, (flags & VN_EXACT) ? exact::launch_reduce_tonemap_peers(peers, n_peers, scale, begin, end, c->accum, img, c->stream)
+    VN_CUDA(c, !(flags & VN_FAST) ? exact::launch_reduce_tonemap_peers(peers, n_peers, scale, begin, end, c->accum, img, c->stream)
                                   : fast::launch_reduce_tonemap_peers(peers, n_peers, scale, begin, end, c->accum, img, c->stream));
     c->stats.kernel_launches_total += 1;
     if (!(flags & VN_ASYNC)) VN_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -672,7 +710,7 @@ int vn_trace_rays(vn_handle c, const float* origins, const float* dirs, uint64_t
     RenderLaunch L;
     memset(&L, 0, sizeof(L));
     L.nodes = c->scene.nodes; L.geom = c->scene.geom; L.root_link = c->scene.root_link;
-    VN_CUDA(c, (flags & VN_EXACT) ? exact::launch_trace_rays(L, o.as<float>(), d.as<float>(), n, t.as<float>(), pr.as<int32_t>(), c->scene.orig, c->stream)
+    VN_CUDA(c, !(flags & VN_FAST) ? exact::launch_trace_rays(L, o.as<float>(), d.as<float>(), n, t.as<float>(), pr.as<int32_t>(), c->scene.orig, c->stream)
                                   : fast::launch_trace_rays(L, o.as<float>(), d.as<float>(), n, t.as<float>(), pr.as<int32_t>(), c->scene.orig, c->stream));
     VN_CUDA(c, cudaMemcpyAsync(t_out, t.p, 4 * n, cudaMemcpyDeviceToHost, c->stream));
     VN_CUDA(c, cudaMemcpyAsync(prim_out, pr.p, 4 * n, cudaMemcpyDeviceToHost, c->stream));
@@ -708,7 +746,7 @@ int vn_test_make_color(vn_handle c, const float* rgb, uint64_t n, uint8_t* rgba_
     DevBuf in, out;
     VN_CUDA(c, in.alloc(12 * n)); VN_CUDA(c, out.alloc(4 * n));
     VN_CUDA(c, cudaMemcpyAsync(in.p, rgb, 12 * n, cudaMemcpyHostToDevice, c->stream));
-    VN_CUDA(c, (flags & VN_EXACT) ? exact::launch_make_color(in.as<float>(), n, out.as<uint32_t>(), c->stream)
+    VN_CUDA(c, !(flags & VN_FAST) ? exact::launch_make_color(in.as<float>(), n, out.as<uint32_t>(), c->stream)
                                   : fast::launch_make_color(in.as<float>(), n, out.as<uint32_t>(), c->stream));
     VN_CUDA(c, cudaMemcpyAsync(rgba_out, out.p, 4 * n, cudaMemcpyDeviceToHost, c->stream));
     VN_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -731,7 +769,7 @@ int vn_test_scatter(vn_handle c, uint32_t material_type, const float albedo_fuzz
     // same packing as k_gather: {albedo.xyz, fuzz} or {ir, 0, 0, 0}
     const float4 mat = material_type == VN_DIELECTRIC ? make_float4(albedo_fuzz_ir[3], 0.f, 0.f, 0.f)
                                                       : make_float4(albedo_fuzz_ir[0], albedo_fuzz_ir[1], albedo_fuzz_ir[2], albedo_fuzz_ir[3]);
-    VN_CUDA(c, (flags & VN_EXACT) ? exact::launch_scatter(material_type, mat, d.as<float>(), nr.as<float>(), fr.as<uint8_t>(), sd.as<uint32_t>(), n,
+    VN_CUDA(c, !(flags & VN_FAST) ? exact::launch_scatter(material_type, mat, d.as<float>(), nr.as<float>(), fr.as<uint8_t>(), sd.as<uint32_t>(), n,
                                                           dout.as<float>(), sc.as<uint8_t>(), sout.as<uint32_t>(), c->stream)
                                   : fast::launch_scatter(material_type, mat, d.as<float>(), nr.as<float>(), fr.as<uint8_t>(), sd.as<uint32_t>(), n,
                                                          dout.as<float>(), sc.as<uint8_t>(), sout.as<uint32_t>(), c->stream));

@@ -195,24 +195,23 @@ VN_HD void hit_frame(f3 o, f3 d, float t, float cx, float cy, float cz, float r,
 }
 
 // ---- materials
-// __closesthit__lambertian, RayTracer.cu:288-291 (+ near_zero :8-13, which compares in double)
-VN_HD f3 scatter_lambertian(f3 n, uint32_t& seed) {
-    f3 dir = n + normalize(random_in_unit_sphere(seed));
-#if VN_FAST_DEVICE
-    // |x| < 1e-8 in double <=> |x| <= the largest float below 1e-8
+// near_zero (RayTracer.cu:8-13) compares fabs(float) < 1e-8 in double.  For a float x that is exactly
+// x <= 9.99999993922529e-09f, the largest float below 1e-8 (checked in tests), so no FP64 is needed.
+VN_HD bool near_zero(f3 e) {
     const float s = 9.99999993922529e-09f;
-    bool nz = (fabsf(dir.x) <= s) && (fabsf(dir.y) <= s) && (fabsf(dir.z) <= s);
-#else
-    const double s = 1e-8;
-    bool nz = ((double)fabsf(dir.x) < s) && ((double)fabsf(dir.y) < s) && ((double)fabsf(dir.z) < s);
-#endif
-    return nz ? n : dir;
+    return (fabsf(e.x) <= s) && (fabsf(e.y) <= s) && (fabsf(e.z) <= s);
+}
+// __closesthit__lambertian, RayTracer.cu:288-291, given the rejection-sampled point in the unit sphere
+VN_HD f3 scatter_lambertian(f3 n, f3 in_unit_sphere) {
+    f3 dir = n + normalize(in_unit_sphere);
+    return near_zero(dir) ? n : dir;
 }
 
-// __closesthit__metal, RayTracer.cu:338-341.  Returns false when the ray is absorbed.
-VN_HD bool scatter_metal(f3 dir_in, f3 n, float fuzz, uint32_t& seed, f3& dir_out) {
-    f3 reflected = reflect(normalize(dir_in), n);
-    dir_out = reflected + fuzz * random_in_unit_sphere(seed);
+// __closesthit__metal, RayTracer.cu:338-341, given normalize(direction) and the rejection-sampled point.
+// Returns false when the ray is absorbed.
+VN_HD bool scatter_metal(f3 unit_direction, f3 n, float fuzz, f3 in_unit_sphere, f3& dir_out) {
+    f3 reflected = reflect(unit_direction, n);
+    dir_out = reflected + fuzz * in_unit_sphere;
     return dot(dir_out, n) > 0.0f;
 }
 
@@ -225,14 +224,17 @@ VN_HD float reflectance(float cosine, float ref_idx) {
     float x2 = x * x;
     return r0 + (1.0f - r0) * (x2 * x2 * x);
 #else
-    return r0 + (1.0f - r0) * powf(1.0f - cosine, 5.0f);
+    // powf(1 - cosine, 5): x^5 formed in double and rounded once, i.e. the correctly rounded power (glibc's powf in the
+    // oracle is within 1 ulp of it; the reference itself uses the approximate __powf)
+    const double x = (double)(1.0f - cosine);
+    const double x2 = x * x;
+    return r0 + (1.0f - r0) * (float)(x2 * x2 * x);
 #endif
 }
 
 // __closesthit__dielectric, RayTracer.cu:398-414
-VN_HD f3 scatter_dielectric(f3 dir_in, f3 n, bool front, float ir, uint32_t& seed) {
+VN_HD f3 scatter_dielectric(f3 unit_direction, f3 n, bool front, float ir, uint32_t& seed) {
     float refraction_ratio = front ? rcp(ir) : ir;
-    f3 unit_direction = normalize(dir_in);
 #if VN_FAST_DEVICE
     float cos_theta = fminf(dot(-unit_direction, n), 1.0f);
     float sin2 = 1.0f - cos_theta * cos_theta;
@@ -252,8 +254,7 @@ VN_HD f3 scatter_dielectric(f3 dir_in, f3 n, bool front, float ir, uint32_t& see
 
 // __miss__ms, RayTracer.cu:442-450.  0.5*(y+1.0) in double then narrowed == the float expression below
 // (y+1 is exact in double; halving is exact; one rounding either way).
-VN_HD f3 sky(f3 d) {
-    f3 unit_direction = normalize(d);
+VN_HD f3 sky(f3 unit_direction) {
     float t = 0.5f * (unit_direction.y + 1.0f);
     return lerp3(mk3(1.0f), mk3(0.5f, 0.7f, 1.0f), t);
 }
@@ -321,7 +322,7 @@ VN_HD void closest_hit(const node_f4* __restrict__ nodes, const node_f4* __restr
                        f3 o, f3 d, float& t_out, int& prim_out, TraceCounters& cnt) {
     float tbest = kTMax;
     int prim = -1;
-    if (root_link != kEmptyScene) {
+    {
         const f3 idir = mk3(rcp(d.x), rcp(d.y), rcp(d.z));
         const f3 ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
         const float a = dot(d, d);
@@ -329,8 +330,11 @@ VN_HD void closest_hit(const node_f4* __restrict__ nodes, const node_f4* __restr
         uint32_t stack[kStackSize];
         int sp = 0;
         uint32_t cur = root_link;
-        while (true) {
-            if (!(cur & kLeafFlag)) {
+        // while-while: every lane first descends through internal nodes until it holds a leaf (or is done); the warp
+        // reconverges at the end of the inner loop, so the sphere tests below run with many lanes active instead of
+        // being interleaved, a few lanes at a time, with other lanes' box tests.  kEmptyScene doubles as "done".
+        for (;;) {
+            while (!(cur & kLeafFlag)) {
                 const node_f4 l0 = nodes[2 * cur], l1 = nodes[2 * cur + 1];
                 const node_f4 r0 = nodes[2 * cur + 2], r1 = nodes[2 * cur + 3];
                 if (kCount) cnt.nodes += 1;
@@ -342,22 +346,24 @@ VN_HD void closest_hit(const node_f4* __restrict__ nodes, const node_f4* __restr
                     const bool left_first = tl <= tr;
                     cur = left_first ? ll : lr;
                     stack[sp++] = left_first ? lr : ll;
-                    continue;
-                }
-                if (hl) { cur = ll; continue; }
-                if (hr) { cur = lr; continue; }
-            } else {
-                const uint32_t first = (cur & 0x7FFFFFFFu) >> 3;
-                const uint32_t count = (cur & 7u) + 1u;
-                for (uint32_t k = 0; k < count; k++) {
-                    const node_f4 g = geom[first + k];
-                    if (kCount) cnt.spheres += 1;
-                    const float t = sphere_root(o, d, a, inv_a, g.x, g.y, g.z, g.w, kTMin, tbest);
-                    if (t >= 0.0f) { tbest = t; prim = (int)(first + k); }
+                } else if (hl) {
+                    cur = ll;
+                } else if (hr) {
+                    cur = lr;
+                } else {
+                    cur = sp ? stack[--sp] : kEmptyScene;
                 }
             }
-            if (sp == 0) break;
-            cur = stack[--sp];
+            if (cur == kEmptyScene) break;
+            const uint32_t first = (cur & 0x7FFFFFFFu) >> 3;
+            const uint32_t count = (cur & 7u) + 1u;
+            for (uint32_t k = 0; k < count; k++) {
+                const node_f4 g = geom[first + k];
+                if (kCount) cnt.spheres += 1;
+                const float t = sphere_root(o, d, a, inv_a, g.x, g.y, g.z, g.w, kTMin, tbest);
+                if (t >= 0.0f) { tbest = t; prim = (int)(first + k); }
+            }
+            cur = sp ? stack[--sp] : kEmptyScene;
         }
     }
     t_out = tbest;
@@ -384,7 +390,10 @@ struct PathState {
 // Shades the closest hit (or miss) of one segment.  Returns true when the path continues (st updated), false when
 // it ended with radiance `result`.
 VN_HD bool shade_segment(const SceneView& sc, PathState& st, float t, int prim, f3& result) {
-    if (prim < 0) { result = st.thr * sky(st.d); return false; }
+    // normalize(direction) is needed by miss (RayTracer.cu:444), metal (:338) and dielectric (:404); computing it for
+    // every lane keeps the warp converged (a Lambertian lane simply does not use it).
+    const f3 unit_direction = normalize(st.d);
+    if (prim < 0) { result = st.thr * sky(unit_direction); return false; }
     if (!(st.depth > 0)) { result = mk3(0.0f); return false; }      // RayTracer.cu:275,324,384: depth budget exhausted
     const node_f4 g = sc.geom[prim];
     const node_f4 m = sc.mat[prim];
@@ -392,16 +401,18 @@ VN_HD bool shade_segment(const SceneView& sc, PathState& st, float t, int prim, 
     f3 p, n;
     bool front;
     hit_frame(st.o, st.d, t, g.x, g.y, g.z, g.w, p, n, front);
-    if (type == 0u) {
-        st.d = scatter_lambertian(n, st.seed);
-        st.thr = st.thr * mk3(m.x, m.y, m.z);
-    } else if (type == 1u) {
+    if (type != 2u) {
+        // Lambertian (:288) and metal (:340) both start with the same rejection loop: run it once for both
+        const f3 s = random_in_unit_sphere(st.seed);
         f3 dir;
-        if (!scatter_metal(st.d, n, m.w, st.seed, dir)) { result = mk3(0.0f); return false; }
+        bool ok = true;
+        if (type == 0u) dir = scatter_lambertian(n, s);
+        else ok = scatter_metal(unit_direction, n, m.w, s, dir);
+        if (!ok) { result = mk3(0.0f); return false; }
         st.d = dir;
         st.thr = st.thr * mk3(m.x, m.y, m.z);
     } else {
-        st.d = scatter_dielectric(st.d, n, front, m.x, st.seed);
+        st.d = scatter_dielectric(unit_direction, n, front, m.x, st.seed);
     }
     st.o = p;
     st.depth -= 1;
