@@ -173,6 +173,9 @@ def run_ours(args):
     width, height, spp, depth, scene_name = WORKLOADS[args.workload]
     K, W = args.steps, args.warmup
     ctx = vb.Context(local_rank)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ctx.set_option(k, float(v))
     if args.leaf_size:
         ctx.set_option("leaf_size", args.leaf_size)
     if args.threads:
@@ -409,6 +412,7 @@ def main():
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fast", action="store_true", help="opt-in relaxed-numerics kernels (VN_FAST)")
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value (vn_set_option), repeatable")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "ours" else max(1, args.warmup)
     if args.impl == "reference":

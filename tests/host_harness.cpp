@@ -21,7 +21,11 @@ struct hh_params {
     float origin[3], u[3], v[3], w[3], lens_radius;
 };
 
+static int g_use_oct = 0;
+static int g_seq_postpone = 0;   // hh_set_oct(1): traverse octant-mirrored node copies like k_render_persistent<.., kOct=true>
+
 struct HostBvh {
+    std::vector<node_f4> nodes_oct;
     std::vector<node_f4> nodes, geom, mat;
     std::vector<uint8_t> type;
     std::vector<uint32_t> orig, codes;
@@ -101,10 +105,30 @@ static void build(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pad_
         }
     }
     B.root_link = f2u(B.nodes[2].w);
+    // 8 copies in near/far-plane form, one per direction octant (same construction as the kernel prologue)
+    const size_t nn = B.nodes.size() / 2;
+    B.nodes_oct.resize(8 * B.nodes.size());
+    for (uint32_t k = 0; k < 8; k++)
+        for (size_t j = 0; j < nn; j++) {
+            const node_f4 lo = B.nodes[2 * j], hi = B.nodes[2 * j + 1];
+            node_f4 nr = lo, fr = hi;
+            if (k & 1) { nr.x = hi.x; fr.x = lo.x; }
+            if (k & 2) { nr.y = hi.y; fr.y = lo.y; }
+            if (k & 4) { nr.z = hi.z; fr.z = lo.z; }
+            B.nodes_oct[k * B.nodes.size() + 2 * j] = nr;
+            B.nodes_oct[k * B.nodes.size() + 2 * j + 1] = fr;
+        }
+}
+
+template <bool kCount>
+static inline void hh_closest(const HostBvh& B, f3 o, f3 d, float& t, int& prim, TraceCounters& cnt) {
+    if (g_use_oct) closest_hit<kCount, true>(B.nodes_oct.data(), B.geom.data(), B.root_link, o, d, t, prim, cnt, (uint32_t)B.nodes.size());
+    else closest_hit<kCount, false>(B.nodes.data(), B.geom.data(), B.root_link, o, d, t, prim, cnt);
 }
 
 extern "C" {
 
+void hh_set_oct(int on) { g_use_oct = on; }
 uint32_t hh_tea4(uint32_t a, uint32_t b) { return tea4(a, b); }
 uint32_t hh_lcg(uint32_t* s) { return lcg(*s); }
 float hh_rnd(uint32_t* s) { return rnd(*s); }
@@ -133,8 +157,7 @@ void hh_closest_hit(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pa
     for (uint64_t i = 0; i < nrays; i++) {
         float t; int prim;
         cnt.nodes = cnt.spheres = 0;
-        closest_hit<true>(B.nodes.data(), B.geom.data(), B.root_link, mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]),
-                          mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), t, prim, cnt);
+        hh_closest<true>(B, mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), t, prim, cnt);
         nv += cnt.nodes; st += cnt.spheres;
         t_out[i] = prim >= 0 ? t : -1.0f;
         prim_out[i] = prim >= 0 ? (int32_t)B.orig[prim] : -1;
@@ -174,7 +197,7 @@ void hh_render_mean(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pa
             while (true) {
                 float t; int prim;
                 TraceCounters cnt{0, 0};
-                closest_hit<true>(sc.nodes, sc.geom, sc.root_link, st.o, st.d, t, prim, cnt);
+                hh_closest<true>(B, st.o, st.d, t, prim, cnt);
                 segs++; nv += cnt.nodes; stt += cnt.spheres;
                 if (!shade_segment(sc, st, t, prim, result)) break;
             }
@@ -244,7 +267,7 @@ extern "C" void hh_visit_histogram(const hh_sphere* s, uint32_t n, uint32_t leaf
 // scheduling model in tools/simt_model.py.  Same visiting order as closest_hit().
 static void trace_sequence(const SceneView& sc, f3 o, f3 d, std::vector<uint8_t>& out) {
     float tbest = kTMax;
-    const f3 idir = mk3(rcp(d.x), rcp(d.y), rcp(d.z));
+    const f3 idir = slab_idir(d);
     const f3 ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
     const float a = dot(d, d), inv_a = rcp(a);
     uint32_t stack[kStackSize]; int sp = 0; uint32_t cur = sc.root_link;
@@ -271,6 +294,7 @@ static void trace_sequence(const SceneView& sc, f3 o, f3 d, std::vector<uint8_t>
     out.push_back(255);
 }
 
+static void trace_sequence_pp(const SceneView& sc, f3 o, f3 d, std::vector<uint8_t>& out);
 extern "C" uint64_t hh_step_sequences(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pad_rel, const hh_params* P,
                                       uint8_t* out, uint64_t cap) {
     HostBvh B;
@@ -294,7 +318,7 @@ extern "C" uint64_t hh_step_sequences(const hh_sphere* s, uint32_t n, uint32_t l
             st.thr = mk3(1.0f); st.seed = seed; st.depth = (int)P->max_depth - 1;
             f3 result;
             while (true) {
-                trace_sequence(sc, st.o, st.d, seq);
+                if (g_seq_postpone) trace_sequence_pp(sc, st.o, st.d, seq); else trace_sequence(sc, st.o, st.d, seq);
                 float t; int prim; TraceCounters cnt{0, 0};
                 closest_hit<false>(sc.nodes, sc.geom, sc.root_link, st.o, st.d, t, prim, cnt);
                 if (!shade_segment(sc, st, t, prim, result)) break;
@@ -305,4 +329,78 @@ extern "C" uint64_t hh_step_sequences(const hh_sphere* s, uint32_t n, uint32_t l
     const uint64_t m = std::min<uint64_t>(cap, seq.size());
     if (out) memcpy(out, seq.data(), m);
     return seq.size();
+}
+
+// Step sequence under the "postponed leaf" schedule: the first leaf a lane meets is parked and the lane keeps
+// descending; leaves are tested when a second one turns up or the stack runs dry (model input only).
+static void trace_sequence_pp(const SceneView& sc, f3 o, f3 d, std::vector<uint8_t>& out) {
+    float tbest = kTMax;
+    const f3 idir = slab_idir(d);
+    const f3 ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
+    const float a = dot(d, d), inv_a = rcp(a);
+    uint32_t stack[kStackSize]; int sp = 0; uint32_t cur = sc.root_link, pend = kEmptyScene;
+    auto leaf = [&](uint32_t l) {
+        const uint32_t first = (l & 0x7FFFFFFFu) >> 3, count = (l & 7u) + 1u;
+        out.push_back((uint8_t)count);
+        for (uint32_t k = 0; k < count; k++) {
+            const node_f4 g = sc.geom[first + k];
+            const float t = sphere_root(o, d, a, inv_a, g.x, g.y, g.z, g.w, kTMin, tbest);
+            if (t >= 0.0f) tbest = t;
+        }
+    };
+    for (;;) {
+        while (!(cur & kLeafFlag)) {
+            out.push_back(0);
+            const node_f4 l0 = sc.nodes[2 * cur], l1 = sc.nodes[2 * cur + 1], r0 = sc.nodes[2 * cur + 2], r1 = sc.nodes[2 * cur + 3];
+            float tl, tr;
+            const bool hl = box_hit(l0, l1, idir, ood, tbest, tl), hr = box_hit(r0, r1, idir, ood, tbest, tr);
+            const uint32_t ll = f2u(l0.w), lr = f2u(r0.w);
+            if (hl && hr) { const bool lf = tl <= tr; cur = lf ? ll : lr; stack[sp++] = lf ? lr : ll; }
+            else if (hl) cur = ll; else if (hr) cur = lr; else cur = sp ? stack[--sp] : kEmptyScene;
+            if ((cur & kLeafFlag) && cur != kEmptyScene && pend == kEmptyScene) { pend = cur; cur = sp ? stack[--sp] : kEmptyScene; }
+        }
+        if (pend != kEmptyScene) { leaf(pend); pend = kEmptyScene; }
+        if (cur != kEmptyScene) { leaf(cur); cur = sp ? stack[--sp] : kEmptyScene; }
+        else break;
+    }
+    out.push_back(255);
+}
+extern "C" void hh_set_seq_postpone(int on) { g_seq_postpone = on; }
+
+// Node / sphere visit counts for an externally built tree in the packed layout (BVH-quality studies).
+extern "C" void hh_visits_custom(const node_f4* nodes, uint32_t n_nodes, const hh_sphere* sorted, uint32_t n, const hh_params* P,
+                                 uint64_t* segs_out, uint64_t* nodes_out, uint64_t* spheres_out) {
+    std::vector<node_f4> geom(n), mat(n);
+    std::vector<uint8_t> type(n);
+    for (uint32_t i = 0; i < n; i++) {
+        geom[i] = node_f4{sorted[i].cx, sorted[i].cy, sorted[i].cz, sorted[i].r};
+        mat[i] = sorted[i].type == 2 ? node_f4{sorted[i].fuzz_or_ir, 0, 0, 0} : node_f4{sorted[i].ax, sorted[i].ay, sorted[i].az, sorted[i].fuzz_or_ir};
+        type[i] = (uint8_t)sorted[i].type;
+    }
+    (void)n_nodes;
+    SceneView sc{nodes, geom.data(), mat.data(), type.data(), f2u(nodes[2].w)};
+    Camera cam;
+    cam.origin = mk3(P->origin[0], P->origin[1], P->origin[2]);
+    cam.u = mk3(P->u[0], P->u[1], P->u[2]); cam.v = mk3(P->v[0], P->v[1], P->v[2]); cam.w = mk3(P->w[0], P->w[1], P->w[2]);
+    cam.u_unit = normalize(cam.u); cam.v_unit = normalize(cam.v);
+    cam.lens_radius = P->lens_radius;
+    cam.wm1 = (float)(P->width - 1); cam.hm1 = (float)(P->height - 1);
+    cam.inv_wm1 = 1.0f / cam.wm1; cam.inv_hm1 = 1.0f / cam.hm1;
+    uint64_t segs = 0, nv = 0, sv = 0;
+    for (uint32_t px = 0; px < P->width * P->height; px++) {
+        uint32_t seed = tea4(px, P->subframe_index);
+        for (uint32_t k = 0; k < P->spp; k++) {
+            PathState st;
+            camera_ray(cam, px % P->width, px / P->width, seed, st.o, st.d);
+            st.thr = mk3(1.0f); st.seed = seed; st.depth = (int)P->max_depth - 1;
+            f3 result;
+            while (true) {
+                float t; int prim; TraceCounters cnt{0, 0};
+                closest_hit<true>(sc.nodes, sc.geom, sc.root_link, st.o, st.d, t, prim, cnt);
+                segs++; nv += cnt.nodes; sv += cnt.spheres;
+                if (!shade_segment(sc, st, t, prim, result)) break;
+            }
+        }
+    }
+    *segs_out = segs; *nodes_out = nv; *spheres_out = sv;
 }

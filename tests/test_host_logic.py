@@ -208,3 +208,34 @@ def test_near_zero_float_threshold_equals_double_compare():
     xs = np.float32(1e-8) + np.arange(-2000, 2000, dtype=np.float32) * np.float32(1e-15)
     xs = np.concatenate([xs, np.array([0, 1e-9, 1e-7, c, np.nextafter(c, np.float32(1)), np.nextafter(c, np.float32(0))], np.float32)])
     assert np.array_equal(xs.astype(np.float64) < 1e-8, xs <= c)
+
+
+def test_octant_mirrored_traversal_equals_plain_on_cpu(host_harness, oracle_mod, rtiow):
+    """k_render_persistent's octant-specialised node copies (near/far-plane form, no per-axis min/max) find exactly
+    the same closest hits, and visit exactly as many nodes, as the plain lo/hi slab test."""
+    rng = np.random.RandomState(23)
+    n = 30000
+    o = (rng.rand(n, 3).astype(np.float32) - np.float32(0.5)) * np.float32(30.0)
+    o[:, 1] = np.abs(o[:, 1]) * np.float32(0.2) + np.float32(0.01)
+    d = rng.randn(n, 3).astype(np.float32)
+    d[:50, 0] = 0.0                                   # axis-parallel rays: 1/0 = inf planes
+    d[50:100, 1] = -0.0
+    d[100:150, 2] = 0.0
+    out = {}
+    try:
+        for oct_ in (0, 1):
+            host_harness.hh_set_oct(oct_)
+            t = np.zeros(n, np.float32)
+            p = np.zeros(n, np.int32)
+            nv, st = C.c_uint64(), C.c_uint64()
+            host_harness.hh_closest_hit(rtiow.ctypes.data_as(C.c_void_p), len(rtiow), 2, C.c_float(0.01), o.ctypes.data_as(C.c_void_p),
+                                        d.ctypes.data_as(C.c_void_p), n, t.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p),
+                                        C.byref(nv), C.byref(st))
+            out[oct_] = (t, p, nv.value, st.value)
+    finally:
+        host_harness.hh_set_oct(0)
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    assert abs(out[0][2] - out[1][2]) <= 0.001 * out[0][2]      # NaN planes of axis-parallel rays may add a visit or two
+    orc = oracle_mod.Oracle(rtiow)
+    t0, p0 = orc.closest_hit(o, d, use_bvh=False)
+    assert np.array_equal(t0, out[1][0]) and np.array_equal(p0, out[1][1])

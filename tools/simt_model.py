@@ -74,9 +74,11 @@ def run(seq, policy, K=0, vote_T=8, n_warps=64, seed=0):
                     while node.any():
                         cost += N_NODE + 2; P[node] += 1
                         cur = np.where(A, seq[P], 250); node = cur == 0
+                    # leaf phase: every lane tests all the leaves it holds (consecutive leaf tokens)
                     leaf = (cur >= 1) & (cur <= 8)
-                    if leaf.any():
+                    while leaf.any():
                         cost += LOOP + LEAF_BASE + LEAF_PER * int(cur[leaf].max()); P[leaf] += 1
+                        cur = np.where(A, seq[P], 250); leaf = (cur >= 1) & (cur <= 8)
                 cur = np.where(A, seq[P], 250)
             m = cur == 255
             if m.any():

@@ -40,9 +40,10 @@ struct KernelConfig {
     size_t smem_bytes;               // dynamic shared memory (scene staging), 0 when the scene stays in HBM/L2
     bool scene_in_smem;
     bool count;                      // instrumented variant
+    bool octant;                     // nodes staged 8x in shared memory, once per ray-direction octant (near/far-plane form)
 };
 
-size_t scene_smem_bytes(uint32_t num_nodes, uint32_t num_spheres);
+size_t scene_smem_bytes(uint32_t num_nodes, uint32_t num_spheres, uint32_t node_copies = 1);
 
 // Wavefront state: SoA queues in HBM (L2-resident at the default capacity), owned by the context.
 // One path slot = 48 bytes of ray state (o 12, d 12, throughput 12, seed 4, sample slot 4, depth 4).
@@ -73,7 +74,7 @@ struct WavefrontBuffers {
 constexpr int kWfArraysTotal = 2 * kWfStateArrays + 2 + 4;   // 4-byte arrays of `capacity` entries in the slab
 
 #define VN_DECLARE_KERNEL_API                                                                                          \
-    int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool count);                             \
+    int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool count, bool octant);                \
     cudaError_t launch_render_persistent(const RenderLaunch& p, const KernelConfig& cfg, cudaStream_t stream);         \
     cudaError_t launch_tonemap(const float4* accum, float scale, uint32_t* image, uint64_t n, cudaStream_t stream);    \
     cudaError_t launch_reduce_tonemap_peers(const float4* const* peers, uint32_t n_peers, float scale, uint64_t begin, \

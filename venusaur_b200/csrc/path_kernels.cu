@@ -32,8 +32,8 @@ namespace cg = cooperative_groups;
 namespace vn {
 
 #if VN_EXACT
-size_t scene_smem_bytes(uint32_t num_nodes, uint32_t num_spheres) {
-    return (size_t)num_nodes * 32 + (size_t)num_spheres * 32 + (((size_t)num_spheres + 15) & ~(size_t)15);
+size_t scene_smem_bytes(uint32_t num_nodes, uint32_t num_spheres, uint32_t node_copies) {
+    return (size_t)num_nodes * 32 * node_copies + (size_t)num_spheres * 32 + (((size_t)num_spheres + 15) & ~(size_t)15);
 }
 #endif
 
@@ -63,17 +63,35 @@ __device__ __forceinline__ void finish_pixel(const RenderLaunch& p, uint32_t pix
     // that happen to finish a pixel in this iteration would cost every other lane of the warp the same issue slots.
 }
 
-template <bool kSmem, bool kCount>
-__global__ void __launch_bounds__(256) k_render_persistent(const __grid_constant__ RenderLaunch p) {
+template <bool kSmem, bool kCount, bool kOct, int kMaxThreads>
+__global__ void __launch_bounds__(kMaxThreads) k_render_persistent(const __grid_constant__ RenderLaunch p) {
     extern __shared__ float4 s_scene[];
     SceneView sc;
+    const uint32_t node_f4s = 2 * p.num_nodes;
     if (kSmem) {
         // stage nodes | geom | mat | type into shared memory with 128-bit copies
         float4* s_nodes = s_scene;
-        float4* s_geom = s_nodes + 2 * (size_t)p.num_nodes;
+        float4* s_geom = s_nodes + (size_t)node_f4s * (kOct ? 8 : 1);
         float4* s_mat = s_geom + p.num_spheres;
         uint8_t* s_type = reinterpret_cast<uint8_t*>(s_mat + p.num_spheres);
-        for (uint32_t i = threadIdx.x; i < 2 * p.num_nodes; i += blockDim.x) s_nodes[i] = p.nodes[i];
+        if (kOct) {
+            // 8 copies of the node array, one per ray-direction octant, in near/far-plane form: for octant k the first
+            // float4 of a node holds the planes a ray of that octant enters through (hi where the direction component
+            // is negative), the second the planes it leaves through.  227 KB of shared memory buys the removal of the
+            // six per-axis min/max from every box test (box_hit_oct).
+            for (uint32_t i = threadIdx.x; i < 8u * p.num_nodes; i += blockDim.x) {
+                const uint32_t k = i / p.num_nodes, j = i - k * p.num_nodes;
+                const float4 lo = p.nodes[2 * j], hi = p.nodes[2 * j + 1];
+                float4 nr = lo, fr = hi;
+                if (k & 1u) { nr.x = hi.x; fr.x = lo.x; }
+                if (k & 2u) { nr.y = hi.y; fr.y = lo.y; }
+                if (k & 4u) { nr.z = hi.z; fr.z = lo.z; }
+                s_nodes[(size_t)k * node_f4s + 2 * j] = nr;
+                s_nodes[(size_t)k * node_f4s + 2 * j + 1] = fr;
+            }
+        } else {
+            for (uint32_t i = threadIdx.x; i < node_f4s; i += blockDim.x) s_nodes[i] = p.nodes[i];
+        }
         for (uint32_t i = threadIdx.x; i < p.num_spheres; i += blockDim.x) { s_geom[i] = p.geom[i]; s_mat[i] = p.mat[i]; }
         for (uint32_t i = threadIdx.x; i < p.num_spheres; i += blockDim.x) s_type[i] = p.type[i];
         __syncthreads();
@@ -123,7 +141,7 @@ __global__ void __launch_bounds__(256) k_render_persistent(const __grid_constant
         }
         float t;
         int prim;
-        closest_hit<kCount>(sc.nodes, sc.geom, sc.root_link, st.o, st.d, t, prim, cnt);
+        closest_hit<kCount, kOct>(sc.nodes, sc.geom, sc.root_link, st.o, st.d, t, prim, cnt, node_f4s);
         n_seg += 1u;
         if (kCount) { n_nodes += cnt.nodes; n_sph += cnt.spheres; cnt.nodes = 0; cnt.spheres = 0; }
         f3 result;
@@ -240,28 +258,30 @@ inline uint32_t grid_for(uint64_t n, int threads) { return (uint32_t)((n + threa
 
 }  // namespace
 
-int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool count) {
+namespace {
+typedef void (*PathKernel)(const RenderLaunch);
+PathKernel pick_kernel(bool scene_in_smem, bool count, bool octant) {
+    if (scene_in_smem && octant) return count ? k_render_persistent<true, true, true, 1024> : k_render_persistent<true, false, true, 1024>;
+    if (scene_in_smem) return count ? k_render_persistent<true, true, false, 256> : k_render_persistent<true, false, false, 256>;
+    return count ? k_render_persistent<false, true, false, 256> : k_render_persistent<false, false, false, 256>;
+}
+}  // namespace
+
+int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool count, bool octant) {
     int nb = 0;
-    cudaError_t e;
-    if (scene_in_smem) {
-        if (count) { set_smem(k_render_persistent<true, true>, smem_bytes); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_render_persistent<true, true>, threads, smem_bytes); }
-        else       { set_smem(k_render_persistent<true, false>, smem_bytes); e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_render_persistent<true, false>, threads, smem_bytes); }
-    } else {
-        if (count) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_render_persistent<false, true>, threads, 0);
-        else       e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_render_persistent<false, false>, threads, 0);
-    }
+    PathKernel k = pick_kernel(scene_in_smem, count, octant);
+    if (smem_bytes > 48 * 1024 && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) return -1;
+    const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, threads, smem_bytes);
     return e == cudaSuccess ? nb : -1;
 }
 
 cudaError_t launch_render_persistent(const RenderLaunch& p, const KernelConfig& cfg, cudaStream_t stream) {
-    cudaError_t e = cudaSuccess;
-    if (cfg.scene_in_smem) {
-        if (cfg.count) { e = set_smem(k_render_persistent<true, true>, cfg.smem_bytes); if (e) return e; k_render_persistent<true, true><<<cfg.blocks, cfg.threads, cfg.smem_bytes, stream>>>(p); }
-        else           { e = set_smem(k_render_persistent<true, false>, cfg.smem_bytes); if (e) return e; k_render_persistent<true, false><<<cfg.blocks, cfg.threads, cfg.smem_bytes, stream>>>(p); }
-    } else {
-        if (cfg.count) k_render_persistent<false, true><<<cfg.blocks, cfg.threads, 0, stream>>>(p);
-        else           k_render_persistent<false, false><<<cfg.blocks, cfg.threads, 0, stream>>>(p);
+    PathKernel k = pick_kernel(cfg.scene_in_smem, cfg.count, cfg.octant);
+    if (cfg.smem_bytes > 48 * 1024) {
+        const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes);
+        if (e != cudaSuccess) return e;
     }
+    k<<<cfg.blocks, cfg.threads, cfg.smem_bytes, stream>>>(p);
     return cudaGetLastError();
 }
 

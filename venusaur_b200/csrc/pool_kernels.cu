@@ -224,8 +224,7 @@ __global__ void __launch_bounds__(768) k_render_pool(const __grid_constant__ Ren
                         slot = P.q_ray[idx];
                         o = mk3(P.ox[slot], P.oy[slot], P.oz[slot]);
                         d = mk3(P.dx[slot], P.dy[slot], P.dz[slot]);
-                        // box tests only have to be conservative: approximate reciprocals in both builds
-                        idir = mk3(__fdividef(1.0f, d.x), __fdividef(1.0f, d.y), __fdividef(1.0f, d.z));
+                        idir = slab_idir(d);
                         ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
                         a = dot(d, d);
                         inv_a = rcp(a);

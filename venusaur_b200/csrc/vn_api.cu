@@ -54,6 +54,7 @@ struct vn_context {
     int blocks_per_sm = 0;            // 0 = occupancy
     size_t smem_scene_limit = 100 * 1024;
     uint32_t wavefront_slots = 1u << 21;
+    bool octant_nodes = true;         // stage the BVH nodes once per ray octant when 8 copies fit in shared memory
     uint32_t pool_slots = 96, pool_threads = 768, pool_service = 8, pool_leaf_batch = 8;
 
     vn_stats stats{};
@@ -222,10 +223,11 @@ int vn_set_option(vn_handle c, const char* name, double value) {
     const std::string k(name);
     if (k == "leaf_size") { VN_REQUIRE(c, value >= 1 && value <= 8, "leaf_size must be in [1,8]"); c->leaf_size = (uint32_t)value; c->bvh_valid = false; }
     else if (k == "aabb_pad") { VN_REQUIRE(c, value >= 0 && value < 1, "aabb_pad must be in [0,1)"); c->aabb_pad = (float)value; c->bvh_valid = false; }
-    else if (k == "threads") { VN_REQUIRE(c, value == 64 || value == 128 || value == 256, "threads must be 64, 128 or 256"); c->threads = (int)value; }
+    else if (k == "threads") { VN_REQUIRE(c, value == 64 || value == 128 || value == 256 || value == 512 || value == 1024, "threads must be 64, 128, 256, 512 or 1024"); c->threads = (int)value; }
     else if (k == "blocks_per_sm") { VN_REQUIRE(c, value >= 0 && value <= 32, "blocks_per_sm must be in [0,32]"); c->blocks_per_sm = (int)value; }
     else if (k == "smem_scene_limit") { VN_REQUIRE(c, value >= 0, "smem_scene_limit must be >= 0"); c->smem_scene_limit = (size_t)value; }
     else if (k == "wavefront_slots") { VN_REQUIRE(c, value >= 1024 && value <= (double)(1u << 26), "wavefront_slots out of range"); c->wavefront_slots = (uint32_t)value; free_wavefront(c->wf); c->wf_sample_floats_ = 0; }
+    else if (k == "octant_nodes") { c->octant_nodes = value != 0; }
     else if (k == "pool_slots") { VN_REQUIRE(c, value >= 32 && value <= 1024, "pool_slots must be in [32,1024]"); c->pool_slots = (uint32_t)value; }
     else if (k == "pool_threads") { VN_REQUIRE(c, value >= 32 && value <= 768 && ((int)value % 32) == 0, "pool_threads must be a multiple of 32 in [32,768]"); c->pool_threads = (uint32_t)value; }
     else if (k == "pool_service") { VN_REQUIRE(c, value >= 1 && value <= 32, "pool_service must be in [1,32]"); c->pool_service = (uint32_t)value; }
@@ -495,10 +497,15 @@ int vn_render(vn_handle c, const vn_params* p) {
         cfg.count = count;
         cfg.scene_in_smem = scene_fits_smem(c);
         cfg.smem_bytes = cfg.scene_in_smem ? scene_smem_bytes(L.num_nodes, L.num_spheres) : 0;
-        int per_sm = c->blocks_per_sm;
+        // 8 octant-specialised copies of the nodes when they fit beside the spheres: one 1024-thread CTA per SM shares them
+        const size_t oct_bytes = scene_smem_bytes(L.num_nodes, L.num_spheres, 8);
+        cfg.octant = cfg.scene_in_smem && c->octant_nodes && oct_bytes + 2048 <= c->smem_optin;
+        if (cfg.octant) { cfg.smem_bytes = oct_bytes; cfg.threads = 1024; }
+        else if (cfg.threads > 256) cfg.threads = 256;
+        int per_sm = cfg.octant ? 1 : c->blocks_per_sm;
         if (per_sm <= 0) {
-            per_sm = exact_build ? exact::max_blocks_per_sm(cfg.threads, cfg.smem_bytes, cfg.scene_in_smem, count)
-                                 : fast::max_blocks_per_sm(cfg.threads, cfg.smem_bytes, cfg.scene_in_smem, count);
+            per_sm = exact_build ? exact::max_blocks_per_sm(cfg.threads, cfg.smem_bytes, cfg.scene_in_smem, count, cfg.octant)
+                                 : fast::max_blocks_per_sm(cfg.threads, cfg.smem_bytes, cfg.scene_in_smem, count, cfg.octant);
             if (per_sm <= 0) return fail(c, VN_ERR_CUDA, "vn_render: occupancy query failed for the path kernel");
         }
         cfg.blocks = c->num_sms * per_sm;

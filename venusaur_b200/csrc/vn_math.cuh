@@ -304,7 +304,7 @@ VN_HD uint32_t f2u(float f) {
 struct TraceCounters { uint32_t nodes, spheres; };
 
 // Slab test against one child box.  Not parity-relevant (it only has to be conservative; boxes are padded at build
-// time), so it uses explicit FMAs in both builds.  NaNs from 0*inf are dropped by fminf/fmaxf => "overlaps".
+// time), so it uses explicit FMAs in both builds; idir comes from slab_idir(), so all products are finite.
 VN_HD bool box_hit(const node_f4& lo, const node_f4& hi, f3 idir, f3 ood, float tbest, float& tnear) {
     float t0x = fmaf(lo.x, idir.x, -ood.x), t1x = fmaf(hi.x, idir.x, -ood.x);
     float t0y = fmaf(lo.y, idir.y, -ood.y), t1y = fmaf(hi.y, idir.y, -ood.y);
@@ -315,15 +315,44 @@ VN_HD bool box_hit(const node_f4& lo, const node_f4& hi, f3 idir, f3 ood, float 
     return tn <= tf;
 }
 
+// Reciprocal direction for the slab tests.  A component that is exactly (or nearly) zero would give idir = inf and
+// o*idir - plane*idir = inf - inf = NaN, which the NaN-dropping min/max could turn into a wrongly culled box; keeping
+// |d| >= 1e-30 keeps every product finite and the test conservative.  The slab test only has to be conservative (the
+// boxes are padded), so the reciprocal itself is the approximate MUFU.RCP in both builds.
+VN_HD f3 slab_idir(f3 d) {
+    const float tiny = 1e-30f;
+    const float dx = fabsf(d.x) < tiny ? copysignf(tiny, d.x) : d.x;
+    const float dy = fabsf(d.y) < tiny ? copysignf(tiny, d.y) : d.y;
+    const float dz = fabsf(d.z) < tiny ? copysignf(tiny, d.z) : d.z;
+#if defined(__CUDA_ARCH__)
+    return mk3(__fdividef(1.0f, dx), __fdividef(1.0f, dy), __fdividef(1.0f, dz));
+#else
+    return mk3(1.0f / dx, 1.0f / dy, 1.0f / dz);
+#endif
+}
+
+// Same test against a node stored in NEAR/FAR-plane form for the ray's direction octant (see k_render_persistent:
+// when shared memory allows, the nodes are staged 8 times, once per octant, with lo/hi already swapped per axis).
+// The six per-axis min/max of box_hit disappear: 6 FFMA + 2 FMNMX3 + 2 FMNMX per box instead of 6 FFMA + 10 min/max.
+VN_HD bool box_hit_oct(const node_f4& nr, const node_f4& fr, f3 idir, f3 ood, float tbest, float& tnear) {
+    const float tn = fmaxf(fmaxf(fmaf(nr.x, idir.x, -ood.x), fmaf(nr.y, idir.y, -ood.y)), fmaxf(fmaf(nr.z, idir.z, -ood.z), 0.0f));
+    const float tf = fminf(fminf(fmaf(fr.x, idir.x, -ood.x), fmaf(fr.y, idir.y, -ood.y)), fminf(fmaf(fr.z, idir.z, -ood.z), tbest));
+    tnear = tn;
+    return tn <= tf;
+}
+// direction octant: bit a set when component a has its sign bit set (so -0 pairs with idir = -inf)
+VN_HD uint32_t ray_octant(f3 d) { return (f2u(d.x) >> 31) | ((f2u(d.y) >> 31) << 1) | ((f2u(d.z) >> 31) << 2); }
+
 // Closest hit in [kTMin, kTMax] = optixTrace(...) of RayTracer.cu:190-202.  prim = index into the SORTED sphere
 // arrays, -1 on miss.
-template <bool kCount>
+template <bool kCount, bool kOct = false>
 VN_HD void closest_hit(const node_f4* __restrict__ nodes, const node_f4* __restrict__ geom, uint32_t root_link,
-                       f3 o, f3 d, float& t_out, int& prim_out, TraceCounters& cnt) {
+                       f3 o, f3 d, float& t_out, int& prim_out, TraceCounters& cnt, uint32_t oct_stride = 0) {
     float tbest = kTMax;
     int prim = -1;
     {
-        const f3 idir = mk3(rcp(d.x), rcp(d.y), rcp(d.z));
+        const f3 idir = slab_idir(d);
+        if (kOct) nodes += ray_octant(d) * oct_stride;
         const f3 ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
         const float a = dot(d, d);
         const float inv_a = rcp(a);
@@ -339,8 +368,8 @@ VN_HD void closest_hit(const node_f4* __restrict__ nodes, const node_f4* __restr
                 const node_f4 r0 = nodes[2 * cur + 2], r1 = nodes[2 * cur + 3];
                 if (kCount) cnt.nodes += 1;
                 float tl, tr;
-                const bool hl = box_hit(l0, l1, idir, ood, tbest, tl);
-                const bool hr = box_hit(r0, r1, idir, ood, tbest, tr);
+                const bool hl = kOct ? box_hit_oct(l0, l1, idir, ood, tbest, tl) : box_hit(l0, l1, idir, ood, tbest, tl);
+                const bool hr = kOct ? box_hit_oct(r0, r1, idir, ood, tbest, tr) : box_hit(r0, r1, idir, ood, tbest, tr);
                 const uint32_t ll = f2u(l0.w), lr = f2u(r0.w);
                 if (hl && hr) {
                     const bool left_first = tl <= tr;
