@@ -14,6 +14,8 @@
 // Compiled with -fmad=false so that Morton quantisation matches the CPU emulation in tests bit for bit.
 #include "lbvh.h"
 
+#include <cstring>
+
 #include "lbvh_core.cuh"
 #include "radix_sort.cuh"
 
@@ -246,13 +248,31 @@ inline uint32_t blocks_for(uint64_t n) { return (uint32_t)((n + kBlock - 1) / kB
 }  // namespace
 
 void lbvh_free(LbvhScene& sc) {
-    cudaFree(sc.geom); cudaFree(sc.mat); cudaFree(sc.type); cudaFree(sc.orig); cudaFree(sc.nodes); cudaFree(sc.codes);
-    sc.geom = sc.mat = sc.nodes = nullptr; sc.type = nullptr; sc.orig = sc.codes = nullptr;
-    sc.num_nodes = 0; sc.n = 0; sc.root_link = kEmptyScene;
+    cudaFree(sc.arena);
+    sc = LbvhScene();
 }
 
+void lbvh_workspace_free(LbvhWorkspace& ws) {
+    cudaFree(ws.ptr);
+    ws = LbvhWorkspace();
+}
+
+namespace {
+// Bump allocator over one cudaMalloc: a build used to spend 96 % of its time in ~25 cudaMalloc/cudaFree calls.
+struct Arena {
+    char* base = nullptr;
+    size_t off = 0;
+    template <typename T> T* take(size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        T* p = reinterpret_cast<T*>(base + off);
+        off += count * sizeof(T);
+        return p;
+    }
+};
+}  // namespace
+
 int lbvh_build(const vn_sphere* d_spheres, uint64_t n64, uint32_t leaf_size, float pad_rel, int num_sms, cudaStream_t stream,
-               LbvhScene& out, uint32_t* launches, std::string& err) {
+               LbvhScene& out, LbvhWorkspace& ws, uint32_t* launches, std::string& err) {
     lbvh_free(out);
     if (n64 > (1ull << 28)) { err = "too many spheres (limit 2^28)"; return -1; }
     const uint32_t n = (uint32_t)n64;
@@ -260,15 +280,11 @@ int lbvh_build(const vn_sphere* d_spheres, uint64_t n64, uint32_t leaf_size, flo
     if (leaf_size > 8) leaf_size = 8;
     out.n = n;
     out.leaf_size = leaf_size;
-    uint32_t *bounds = nullptr, *codes0 = nullptr, *codes1 = nullptr, *idx0 = nullptr, *idx1 = nullptr, *parent_i = nullptr,
-             *parent_l = nullptr, *arrivals = nullptr, *kept = nullptr, *rank = nullptr, *sums = nullptr;
-    void* ws = nullptr;
-    KarrasNode* kn = nullptr;
-    f4 *leaf_lo = nullptr, *leaf_hi = nullptr, *ilo = nullptr, *ihi = nullptr;
     uint32_t launched = 0;
 
     if (n == 0) {
-        LB_CHECK(cudaMalloc(&out.nodes, 4 * sizeof(float4)));
+        LB_CHECK(cudaMalloc(&out.arena, 4 * sizeof(float4)));
+        out.nodes = static_cast<float4*>(out.arena);
         LB_CHECK(cudaMemsetAsync(out.nodes, 0, 4 * sizeof(float4), stream));
         out.num_nodes = 2;
         out.root_link = kEmptyScene;
@@ -277,34 +293,65 @@ int lbvh_build(const vn_sphere* d_spheres, uint64_t n64, uint32_t leaf_size, flo
     {
         const uint32_t ni = n - 1;
         const uint32_t nb = (uint32_t)((ni + kScanTile - 1) / kScanTile);
-        LB_CHECK(cudaMalloc(&bounds, 6 * sizeof(uint32_t)));
-        LB_CHECK(cudaMalloc(&codes0, 4ull * n)); LB_CHECK(cudaMalloc(&codes1, 4ull * n));
-        LB_CHECK(cudaMalloc(&idx0, 4ull * n));   LB_CHECK(cudaMalloc(&idx1, 4ull * n));
-        LB_CHECK(cudaMalloc(&ws, rs::workspace_bytes(n)));
-        LB_CHECK(cudaMalloc(&out.geom, 16ull * n)); LB_CHECK(cudaMalloc(&out.mat, 16ull * n));
-        LB_CHECK(cudaMalloc(&out.type, n)); LB_CHECK(cudaMalloc(&out.orig, 4ull * n));
-        LB_CHECK(cudaMalloc(&leaf_lo, 16ull * n)); LB_CHECK(cudaMalloc(&leaf_hi, 16ull * n));
-        LB_CHECK(cudaMalloc(&kn, sizeof(KarrasNode) * (size_t)(ni + 1)));
-        LB_CHECK(cudaMalloc(&ilo, 16ull * (ni + 1))); LB_CHECK(cudaMalloc(&ihi, 16ull * (ni + 1)));
-        LB_CHECK(cudaMalloc(&parent_i, 4ull * (ni + 1))); LB_CHECK(cudaMalloc(&parent_l, 4ull * n));
-        LB_CHECK(cudaMalloc(&arrivals, 4ull * (ni + 1)));
-        LB_CHECK(cudaMalloc(&kept, 4ull * (ni + 1))); LB_CHECK(cudaMalloc(&rank, 4ull * (ni + 1)));
-        LB_CHECK(cudaMalloc(&sums, 4ull * (nb + 2)));
+        // ---- outputs: one allocation (nodes at their upper bound 2n+2, so the node count needs no mid-build sync)
+        Arena oa;
+        oa.take<float4>(2 * (2ull * n + 2)); oa.take<float4>(n); oa.take<float4>(n); oa.take<uint32_t>(n); oa.take<uint32_t>(n); oa.take<uint8_t>(n);
+        const size_t out_bytes = oa.off + 256;
+        LB_CHECK(cudaMalloc(&out.arena, out_bytes));
+        oa = Arena{static_cast<char*>(out.arena), 0};
+        out.nodes = oa.take<float4>(2 * (2ull * n + 2));
+        out.geom = oa.take<float4>(n);
+        out.mat = oa.take<float4>(n);
+        out.orig = oa.take<uint32_t>(n);
+        out.codes = oa.take<uint32_t>(n);
+        out.type = oa.take<uint8_t>(n);
+        // ---- temporaries: one cached workspace that only grows
+        Arena ta;
+        auto carve = [&](Arena& t, uint32_t*& bounds, uint32_t*& codes0, uint32_t*& codes1, uint32_t*& idx0, uint32_t*& idx1, void*& sortws,
+                         f4*& leaf_lo, f4*& leaf_hi, KarrasNode*& kn, f4*& ilo, f4*& ihi, uint32_t*& parent_i, uint32_t*& parent_l,
+                         uint32_t*& arrivals, uint32_t*& kept, uint32_t*& rank, uint32_t*& sums, uint32_t*& result) {
+            bounds = t.take<uint32_t>(8);
+            result = t.take<uint32_t>(8);
+            codes0 = t.take<uint32_t>(n); codes1 = t.take<uint32_t>(n); idx0 = t.take<uint32_t>(n); idx1 = t.take<uint32_t>(n);
+            sortws = t.take<char>(rs::workspace_bytes(n));
+            leaf_lo = t.take<f4>(n); leaf_hi = t.take<f4>(n);
+            kn = t.take<KarrasNode>(ni + 1);
+            ilo = t.take<f4>(ni + 1); ihi = t.take<f4>(ni + 1);
+            parent_i = t.take<uint32_t>(ni + 1); parent_l = t.take<uint32_t>(n);
+            arrivals = t.take<uint32_t>(ni + 1); kept = t.take<uint32_t>(ni + 1); rank = t.take<uint32_t>(ni + 1);
+            sums = t.take<uint32_t>(nb + 2);
+        };
+        uint32_t *bounds, *codes0, *codes1, *idx0, *idx1, *parent_i, *parent_l, *arrivals, *kept, *rank, *sums, *result;
+        void* sortws;
+        KarrasNode* kn;
+        f4 *leaf_lo, *leaf_hi, *ilo, *ihi;
+        carve(ta, bounds, codes0, codes1, idx0, idx1, sortws, leaf_lo, leaf_hi, kn, ilo, ihi, parent_i, parent_l, arrivals, kept, rank, sums, result);
+        const size_t need = ta.off + 256;
+        if (ws.bytes < need) {
+            cudaFree(ws.ptr);
+            ws = LbvhWorkspace();
+            LB_CHECK(cudaMalloc(&ws.ptr, need));
+            ws.bytes = need;
+        }
+        ta = Arena{static_cast<char*>(ws.ptr), 0};
+        carve(ta, bounds, codes0, codes1, idx0, idx1, sortws, leaf_lo, leaf_hi, kn, ilo, ihi, parent_i, parent_l, arrivals, kept, rank, sums, result);
 
         const uint32_t init[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
         LB_CHECK(cudaMemcpyAsync(bounds, init, sizeof(init), cudaMemcpyHostToDevice, stream));
         LB_CHECK(cudaMemsetAsync(arrivals, 0, 4ull * (ni + 1), stream));
         LB_CHECK(cudaMemsetAsync(rank, 0, 4ull * (ni + 1), stream));
+        LB_CHECK(cudaMemsetAsync(sums, 0, 4ull * (nb + 2), stream));
 
         const uint32_t red_blocks = (uint32_t)std::min<uint64_t>((uint64_t)num_sms * 8ull, blocks_for(n));
         k_centroid_bounds<<<red_blocks, kBlock, 0, stream>>>(d_spheres, n, bounds);
         k_morton<<<blocks_for(n), kBlock, 0, stream>>>(d_spheres, n, bounds, codes0, idx0);
         launched += 2;
-        const int which = rs::sort_pairs(codes0, idx0, codes1, idx1, n, 30, ws, stream, num_sms, &launched);
+        const int which = rs::sort_pairs(codes0, idx0, codes1, idx1, n, 30, sortws, stream, num_sms, &launched);
         uint32_t* codes = which ? codes1 : codes0;
         uint32_t* idx = which ? idx1 : idx0;
         k_gather<<<blocks_for(n), kBlock, 0, stream>>>(d_spheres, idx, n, pad_rel, out.geom, out.mat, out.type, out.orig, leaf_lo, leaf_hi);
         launched += 1;
+        LB_CHECK(cudaMemcpyAsync(out.codes, codes, 4ull * n, cudaMemcpyDeviceToDevice, stream));   // kept for vn_morton_codes()
         if (ni > 0) {
             k_karras<<<blocks_for(ni), kBlock, 0, stream>>>(codes, n, kn, parent_i, parent_l);
             k_refit<<<blocks_for(n), kBlock, 0, stream>>>(n, kn, parent_i, parent_l, leaf_lo, leaf_hi, ilo, ihi, arrivals);
@@ -314,32 +361,23 @@ int lbvh_build(const vn_sphere* d_spheres, uint64_t n64, uint32_t leaf_size, flo
             k_scan_final<<<nb, kBlock, 0, stream>>>(kept, ni, sums, rank);
             launched += 6;
         }
-        uint32_t total_kept = 0;
-        if (ni > 0) LB_CHECK(cudaMemcpyAsync(&total_kept, sums + nb, 4, cudaMemcpyDeviceToHost, stream));
-        LB_CHECK(cudaStreamSynchronize(stream));
-        out.num_nodes = 2ull + 2ull * total_kept;
-        LB_CHECK(cudaMalloc(&out.nodes, out.num_nodes * 2 * sizeof(float4)));
         k_pack<<<blocks_for(n), kBlock, 0, stream>>>(n, kn, rank, ilo, ihi, leaf_lo, leaf_hi, leaf_size, out.nodes);
         launched += 1;
-        uint32_t root_link = 0;
-        // root link = nodes[2].w (node 1, first float4)
-        LB_CHECK(cudaMemcpyAsync(&root_link, reinterpret_cast<const char*>(out.nodes) + 2 * sizeof(float4) + 12, 4, cudaMemcpyDeviceToHost, stream));
-        LB_CHECK(cudaMemcpyAsync(out.bounds_lo, reinterpret_cast<const char*>(out.nodes) + 2 * sizeof(float4), 12, cudaMemcpyDeviceToHost, stream));
-        LB_CHECK(cudaMemcpyAsync(out.bounds_hi, reinterpret_cast<const char*>(out.nodes) + 3 * sizeof(float4), 12, cudaMemcpyDeviceToHost, stream));
+        // one host round trip at the end: kept-node count, root link, root bounds
+        uint32_t host[12] = {0};
+        LB_CHECK(cudaMemcpyAsync(&host[0], sums + nb, 4, cudaMemcpyDeviceToHost, stream));
+        LB_CHECK(cudaMemcpyAsync(&host[4], reinterpret_cast<const char*>(out.nodes) + 2 * sizeof(float4), 2 * sizeof(float4), cudaMemcpyDeviceToHost, stream));
         LB_CHECK(cudaStreamSynchronize(stream));
         LB_CHECK(cudaGetLastError());
-        out.root_link = root_link;
-        // keep the sorted Morton codes for vn_morton_codes()
-        out.codes = codes == codes0 ? codes0 : codes1;
-        if (codes == codes0) codes0 = nullptr; else codes1 = nullptr;
+        const uint32_t total_kept = ni > 0 ? host[0] : 0u;
+        out.num_nodes = 2ull + 2ull * total_kept;
+        out.root_link = host[7];
+        memcpy(out.bounds_lo, &host[4], 12);
+        memcpy(out.bounds_hi, &host[8], 12);
     }
     if (launches) *launches += launched;
-    cudaFree(bounds); cudaFree(codes0); cudaFree(codes1); cudaFree(idx0); cudaFree(idx1); cudaFree(ws); cudaFree(leaf_lo); cudaFree(leaf_hi);
-    cudaFree(kn); cudaFree(ilo); cudaFree(ihi); cudaFree(parent_i); cudaFree(parent_l); cudaFree(arrivals); cudaFree(kept); cudaFree(rank); cudaFree(sums);
     return 0;
 fail:
-    cudaFree(bounds); cudaFree(codes0); cudaFree(codes1); cudaFree(idx0); cudaFree(idx1); cudaFree(ws); cudaFree(leaf_lo); cudaFree(leaf_hi);
-    cudaFree(kn); cudaFree(ilo); cudaFree(ihi); cudaFree(parent_i); cudaFree(parent_l); cudaFree(arrivals); cudaFree(kept); cudaFree(rank); cudaFree(sums);
     lbvh_free(out);
     return -2;
 }

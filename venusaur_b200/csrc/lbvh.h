@@ -13,6 +13,7 @@ namespace vn {
 
 // Device-resident scene in traversal order (Morton-sorted), as the trace kernels read it.
 struct LbvhScene {
+    void* arena = nullptr;       // one allocation holding every array below
     uint64_t n = 0;
     float4* geom = nullptr;      // {cx, cy, cz, r}
     float4* mat = nullptr;       // {albedo.xyz, fuzz} or {ir, 0, 0, 0}
@@ -28,9 +29,16 @@ struct LbvhScene {
 
 void lbvh_free(LbvhScene& sc);
 
+// Scratch memory of the builder, cached across builds (grows on demand).
+struct LbvhWorkspace {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+void lbvh_workspace_free(LbvhWorkspace& ws);
+
 // Builds the packed LBVH for n spheres already resident on the device.  Returns 0 or a negative status with `err` set.
 int lbvh_build(const vn_sphere* d_spheres, uint64_t n, uint32_t leaf_size, float pad_rel, int num_sms, cudaStream_t stream,
-               LbvhScene& out, uint32_t* launches, std::string& err);
+               LbvhScene& out, LbvhWorkspace& ws, uint32_t* launches, std::string& err);
 
 // Onesweep sort of device (key, value) pairs; returns 0/1 = which buffer pair holds the result, or -1.
 int radix_sort_pairs_device(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, uint32_t n, int key_bits, int num_sms,

@@ -34,6 +34,7 @@ struct vn_context {
     uint64_t n_spheres = 0;
     bool have_spheres = false, bvh_valid = false;
     LbvhScene scene;
+    LbvhWorkspace bvh_ws;
 
     uint32_t width = 0, height = 0;
     float4* accum_own = nullptr;
@@ -208,6 +209,7 @@ void vn_destroy(vn_handle c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     lbvh_free(c->scene);
+    lbvh_workspace_free(c->bvh_ws);
     free_wavefront(c->wf); c->wf_sample_floats_ = 0;
     cudaFree(c->d_spheres); cudaFree(c->accum_own); cudaFree(c->image_tmp); cudaFree(c->d_counters);
     cudaFreeHost(c->h_counters);
@@ -265,7 +267,7 @@ int vn_build_bvh(vn_handle c) {
     std::string err;
     uint32_t launches = 0;
     VN_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
-    const int rc = lbvh_build(c->d_spheres, c->n_spheres, c->leaf_size, c->aabb_pad, c->num_sms, c->stream, c->scene, &launches, err);
+    const int rc = lbvh_build(c->d_spheres, c->n_spheres, c->leaf_size, c->aabb_pad, c->num_sms, c->stream, c->scene, c->bvh_ws, &launches, err);
     if (rc != 0) return fail(c, rc == -1 ? VN_ERR_INVALID : VN_ERR_CUDA, "vn_build_bvh: " + err);
     VN_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     VN_CUDA(c, cudaStreamSynchronize(c->stream));
