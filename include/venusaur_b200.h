@@ -129,6 +129,10 @@ VN_API int vn_set_option(vn_handle h, const char* name, double value); /* "leaf_
 VN_API int vn_build_bvh(vn_handle h);
 VN_API int vn_get_bvh_info(vn_handle h, vn_bvh_info* out);
 VN_API int vn_read_bvh(vn_handle h, vn_node32* host_nodes, uint64_t cap_nodes, uint32_t* host_prim_order, uint64_t cap_prims);
+/* 4-wide nodes derived from the pairs for scenes traversed out of shared memory (<= "wide_max_prims" spheres): 128 B per
+ * node = 4 x { {lo.xyz, link}, {hi.xyz, count} }; link = wide-node index, a leaf link as above, or 0xFFFFFFFF (empty slot).
+ * num_nodes_out = 0 when the scene has none. */
+VN_API int vn_read_wide_bvh(vn_handle h, float* host_nodes, uint64_t cap_nodes, uint32_t* num_nodes_out, uint32_t* levels_out);
 
 /* ---- frame: Renderer::Draw (Renderer.h:35-78) ---- */
 VN_API int vn_resize(vn_handle h, uint32_t width, uint32_t height);   /* (re)allocates + zeroes accum (fixes Q3/Q4) */

@@ -46,6 +46,10 @@ def host_harness():
                                  C.c_void_p, C.c_void_p]
     h.hh_render_mean.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     h.hh_set_oct.argtypes = [C.c_int]
+    h.hh_set_wide.argtypes = [C.c_int]
+    h.hh_set_sah_max.argtypes = [C.c_uint32]
+    h.hh_build_wide.restype = C.c_uint64
+    h.hh_build_wide.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_void_p, C.c_uint64, C.c_void_p]
     h.hh_scatter.argtypes = [C.c_uint32, C.c_float * 4, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
     h.hh_morton30.restype = C.c_uint32
     h.hh_morton30.argtypes = [C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]

@@ -21,7 +21,9 @@ struct hh_params {
     float origin[3], u[3], v[3], w[3], lens_radius;
 };
 
+static uint32_t g_sah_max = 4096;   // same default as the library's "sah_max_prims" option
 static int g_use_oct = 0;
+static int g_use_wide = 0;         // hh_set_wide(1): traverse the 4-wide octant-sorted nodes like k_render_persistent<.., kWide>
 static int g_seq_postpone = 0;   // hh_set_oct(1): traverse octant-mirrored node copies like k_render_persistent<.., kOct=true>
 
 struct HostBvh {
@@ -31,7 +33,112 @@ struct HostBvh {
     std::vector<uint32_t> orig, codes;
     std::vector<KarrasNode> kn;
     uint32_t root_link = kEmptyScene;
+    std::vector<node_f4> wide;        // canonical 4-wide nodes (8 float4 each), BFS order
+    std::vector<node_f4> wide_oct;    // 8 octant-specialised copies (7 float4 per node)
+    uint32_t wide_root = kEmptyScene, wide_levels = 0;
 };
+
+// Sequential emulation of k_sah_small (lbvh.cu): same per-element functions, same level-by-level order.
+static void sah_small_host(uint32_t n, const f4* cen, const f4* blo, const f4* bhi, std::vector<KarrasNode>& kn, std::vector<uint32_t>& perm_final) {
+    const uint32_t INACT = 0xFFFFFFFFu;
+    std::vector<uint32_t> permA(n), permB(n), ownA(n), ownB(n), nfirst(n), nlast(n);
+    std::vector<unsigned long long> best(n);
+    for (uint32_t p = 0; p < n; p++) { permA[p] = p; ownA[p] = n >= 2 ? 0u : INACT; }
+    nfirst[0] = 0; nlast[0] = n - 1;
+    uint32_t *perm = permA.data(), *pnext = permB.data(), *own = ownA.data(), *onext = ownB.data();
+    for (uint32_t level = 0; level < n; level++) {
+        for (uint32_t p = 0; p < n; p++) { const uint32_t id = own[p]; if (id != INACT && p == nfirst[id]) best[id] = ~0ull; }
+        for (uint32_t idx = 0; idx < 3 * n; idx++) {
+            const uint32_t a = idx / n, p = idx - a * n, id = own[p];
+            if (id == INACT) continue;
+            uint32_t nl;
+            const float cost = sah_candidate_cost(perm, nfirst[id], nlast[id], p, (int)a, cen, blo, bhi, &nl);
+            if (cost < 3e38f) best[id] = std::min(best[id], sah_pack(cost, (int)a, p - nfirst[id]));
+        }
+        bool any = false;
+        // children write nfirst/nlast for ids that are not active in this level (see the kernel), so in-place is safe
+        for (uint32_t p = 0; p < n; p++) {
+            const uint32_t id = own[p], e = perm[p];
+            if (id == INACT) { pnext[p] = e; onext[p] = INACT; continue; }
+            any = true;
+            const uint32_t first = nfirst[id], last = nlast[id];
+            const unsigned long long b = best[id];
+            const int a = (int)((b >> 28) & 3ull);
+            const uint32_t es = perm[first + (uint32_t)(b & 0xFFFFFFFull)];
+            const SahKey key{axis_of(cen[es], a), es};
+            uint32_t nL = 0, before_l = 0, before_r = 0;
+            for (uint32_t q = first; q <= last; q++) {
+                const uint32_t eq = perm[q];
+                const bool l = sah_key_le(axis_of(cen[eq], a), eq, key);
+                nL += l ? 1u : 0u;
+                if (q < p) { if (l) before_l++; else before_r++; }
+            }
+            const bool me_left = sah_key_le(axis_of(cen[e], a), e, key);
+            const uint32_t gamma = first + nL - 1u, nR = last - gamma;
+            const uint32_t newpos = me_left ? first + before_l : first + nL + before_r;
+            pnext[newpos] = e;
+            onext[newpos] = me_left ? (nL >= 2u ? gamma : INACT) : (nR >= 2u ? gamma + 1u : INACT);
+        }
+        // node emission after the partition pass (the kernel does it inside; nfirst/nlast of current nodes are not touched)
+        for (uint32_t p = 0; p < n; p++) {
+            const uint32_t id = own[p];
+            if (id == INACT || p != nfirst[id]) continue;
+            const uint32_t first = nfirst[id], last = nlast[id];
+            const unsigned long long b = best[id];
+            const int a = (int)((b >> 28) & 3ull);
+            const uint32_t es = perm[first + (uint32_t)(b & 0xFFFFFFFull)];
+            const SahKey key{axis_of(cen[es], a), es};
+            uint32_t nL = 0;
+            for (uint32_t q = first; q <= last; q++) nL += sah_key_le(axis_of(cen[perm[q]], a), perm[q], key) ? 1u : 0u;
+            const uint32_t gamma = first + nL - 1u, nR = last - gamma;
+            KarrasNode k;
+            k.left = nL == 1u ? (kChildLeaf | first) : gamma;
+            k.right = nR == 1u ? (kChildLeaf | last) : gamma + 1u;
+            k.first = first; k.last = last;
+            kn[id] = k;
+            if (nL != 1u) { nfirst[gamma] = first; nlast[gamma] = gamma; }
+            if (nR != 1u) { nfirst[gamma + 1u] = gamma + 1u; nlast[gamma + 1u] = last; }
+        }
+        std::swap(perm, pnext);
+        std::swap(own, onext);
+        if (!any) break;
+    }
+    perm_final.assign(perm, perm + n);
+}
+
+// Sequential emulation of k_wide_build (lbvh.cu): breadth-first, level by level; the internal children of a level's
+// entries receive consecutive indices in entry order, then canonical child order.
+static void build_wide(HostBvh& B) {
+    B.wide.clear(); B.wide_oct.clear(); B.wide_levels = 0;
+    B.wide_root = B.root_link;
+    if (B.root_link & kLeafFlag) return;                 // a single leaf (or the empty scene): no wide nodes
+    B.wide_root = 0;
+    std::vector<uint32_t> src{B.root_link};              // packed pair link of every wide node
+    size_t lo = 0;
+    while (lo < src.size()) {
+        const size_t hi = src.size();
+        B.wide_levels++;
+        for (size_t e = lo; e < hi; e++) {
+            uint32_t ch[4];
+            const uint32_t n = wide_collapse(B.nodes.data(), src[e], ch);
+            B.wide.resize(8 * (e + 1), node_f4{0, 0, 0, 0});
+            for (uint32_t c = 0; c < 4; c++) {
+                node_f4 a{3e38f, 3e38f, 3e38f, u2f(kWideEmpty)}, b{-3e38f, -3e38f, -3e38f, u2f(0u)};
+                if (c < n) {
+                    a = B.nodes[2 * ch[c]]; b = B.nodes[2 * ch[c] + 1];
+                    const uint32_t link = f2u(a.w);
+                    if (!(link & kLeafFlag)) { a.w = u2f((uint32_t)src.size()); src.push_back(link); }
+                }
+                B.wide[8 * e + 2 * c] = a; B.wide[8 * e + 2 * c + 1] = b;
+            }
+        }
+        lo = hi;
+    }
+    const size_t W = src.size();
+    B.wide_oct.resize(8 * 7 * W);
+    for (uint32_t k = 0; k < 8; k++)
+        for (size_t j = 0; j < W; j++) wide_octant_node(&B.wide[8 * j], k, &B.wide_oct[(k * W + j) * 7]);
+}
 
 static void build(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pad_rel, HostBvh& B) {
     B = HostBvh();
@@ -61,7 +168,38 @@ static void build(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pad_
     }
     const uint32_t ni = n - 1;
     B.kn.resize(ni);
-    for (uint32_t i = 0; i < ni; i++) B.kn[i] = karras_node(B.codes.data(), (int)n, (int)i);
+    bool use_sah = ni > 0 && n <= g_sah_max;
+    std::vector<uint32_t> perm_final;
+    if (use_sah) {
+        // same guard as lbvh_build: a SAH tree taller than 48 levels falls back to Karras
+        std::vector<f4> cen0(n);
+        for (uint32_t i = 0; i < n; i++) cen0[i] = f4{B.geom[i].x, B.geom[i].y, B.geom[i].z, B.geom[i].w};
+        sah_small_host(n, cen0.data(), llo.data(), lhi.data(), B.kn, perm_final);
+        std::vector<uint32_t> h(ni, 0);
+        std::vector<std::pair<uint32_t, int>> st{{0u, 0}};
+        // post-order height
+        std::vector<uint32_t> order2; std::vector<uint32_t> stk{0};
+        while (!stk.empty()) { uint32_t i = stk.back(); stk.pop_back(); order2.push_back(i); if (!(B.kn[i].left & kChildLeaf)) stk.push_back(B.kn[i].left); if (!(B.kn[i].right & kChildLeaf)) stk.push_back(B.kn[i].right); }
+        for (auto it = order2.rbegin(); it != order2.rend(); ++it) { const KarrasNode& k = B.kn[*it]; uint32_t hl = (k.left & kChildLeaf) ? 0 : h[k.left], hr = (k.right & kChildLeaf) ? 0 : h[k.right]; h[*it] = 1 + std::max(hl, hr); }
+        if (h[0] > 48) use_sah = false;
+    }
+    if (use_sah) {
+        // small scene: SAH splits, then everything re-gathered in the final primitive order (codes stay Morton-sorted)
+        std::vector<uint32_t> final_idx(n);
+        for (uint32_t i = 0; i < n; i++) final_idx[i] = idx[perm_final[i]];
+        B.orig = final_idx;
+        for (uint32_t i = 0; i < n; i++) {
+            const hh_sphere& p = s[final_idx[i]];
+            B.geom[i] = node_f4{p.cx, p.cy, p.cz, p.r};
+            B.mat[i] = p.type == 2 ? node_f4{p.fuzz_or_ir, 0, 0, 0} : node_f4{p.ax, p.ay, p.az, p.fuzz_or_ir};
+            B.type[i] = (uint8_t)p.type;
+            const float pad = fabsf(p.r) * (1.0f + pad_rel) + 1e-6f;
+            llo[i] = f4{p.cx - pad, p.cy - pad, p.cz - pad, 0};
+            lhi[i] = f4{p.cx + pad, p.cy + pad, p.cz + pad, 0};
+        }
+    } else {
+        for (uint32_t i = 0; i < ni; i++) B.kn[i] = karras_node(B.codes.data(), (int)n, (int)i);
+    }
     std::vector<f4> ilo(ni), ihi(ni);
     // refit: children before parents == process internal nodes in post-order (iterative)
     if (ni) {
@@ -118,17 +256,30 @@ static void build(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pad_
             B.nodes_oct[k * B.nodes.size() + 2 * j] = nr;
             B.nodes_oct[k * B.nodes.size() + 2 * j + 1] = fr;
         }
+    build_wide(B);
 }
 
 template <bool kCount>
 static inline void hh_closest(const HostBvh& B, f3 o, f3 d, float& t, int& prim, TraceCounters& cnt) {
-    if (g_use_oct) closest_hit<kCount, true>(B.nodes_oct.data(), B.geom.data(), B.root_link, o, d, t, prim, cnt, (uint32_t)B.nodes.size());
+    if (g_use_wide && B.wide_levels <= kWideMaxLevels) closest_hit_wide<kCount>(B.wide_oct.data(), (uint32_t)(B.wide_oct.size() / 8), B.geom.data(), B.wide_root, o, d, t, prim, cnt);
+    else if (g_use_oct) closest_hit<kCount, true>(B.nodes_oct.data(), B.geom.data(), B.root_link, o, d, t, prim, cnt, (uint32_t)B.nodes.size());
     else closest_hit<kCount, false>(B.nodes.data(), B.geom.data(), B.root_link, o, d, t, prim, cnt);
 }
 
 extern "C" {
 
 void hh_set_oct(int on) { g_use_oct = on; }
+void hh_set_wide(int on) { g_use_wide = on; }
+// canonical 4-wide nodes of the host build (8 float4 each); returns their number, *levels = breadth-first levels
+uint64_t hh_build_wide(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pad_rel, float* wide_out, uint64_t cap_nodes, uint32_t* levels) {
+    HostBvh B;
+    build(s, n, leaf_size, pad_rel, B);
+    const uint64_t W = B.wide.size() / 8;
+    if (wide_out) memcpy(wide_out, B.wide.data(), std::min<uint64_t>(W, cap_nodes) * 128);
+    if (levels) *levels = B.wide_levels;
+    return W;
+}
+void hh_set_sah_max(uint32_t n) { g_sah_max = n; }
 uint32_t hh_tea4(uint32_t a, uint32_t b) { return tea4(a, b); }
 uint32_t hh_lcg(uint32_t* s) { return lcg(*s); }
 float hh_rnd(uint32_t* s) { return rnd(*s); }
@@ -295,6 +446,37 @@ static void trace_sequence(const SceneView& sc, f3 o, f3 d, std::vector<uint8_t>
 }
 
 static void trace_sequence_pp(const SceneView& sc, f3 o, f3 d, std::vector<uint8_t>& out);
+// Same for the 4-wide octant-sorted nodes (closest_hit_wide): token 0 = one wide-node step.
+static void trace_sequence_wide(const HostBvh& B, f3 o, f3 d, std::vector<uint8_t>& out) {
+    float tbest = kTMax;
+    const f3 idir = slab_idir(d);
+    const node_f4* wn = B.wide_oct.data() + ray_octant(d) * (B.wide_oct.size() / 8);
+    const f3 ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
+    const float a = dot(d, d), inv_a = rcp(a);
+    uint32_t stack[kStackSize]; int sp = 0; uint32_t cur = B.wide_root;
+    while (cur != kEmptyScene) {
+        if (!(cur & kLeafFlag)) {
+            out.push_back(0);
+            const node_f4* p = wn + kWideNodeF4 * cur;
+            const node_f4 nx = p[0], ny = p[1], nz = p[2], fx = p[3], fy = p[4], fz = p[5], lk = p[6];
+            if (slab_hit(nx.w, ny.w, nz.w, fx.w, fy.w, fz.w, idir, ood, tbest)) stack[sp++] = f2u(lk.w);
+            if (slab_hit(nx.z, ny.z, nz.z, fx.z, fy.z, fz.z, idir, ood, tbest)) stack[sp++] = f2u(lk.z);
+            if (slab_hit(nx.y, ny.y, nz.y, fx.y, fy.y, fz.y, idir, ood, tbest)) stack[sp++] = f2u(lk.y);
+            if (slab_hit(nx.x, ny.x, nz.x, fx.x, fy.x, fz.x, idir, ood, tbest)) stack[sp++] = f2u(lk.x);
+            cur = sp ? stack[--sp] : kEmptyScene;
+        } else {
+            const uint32_t first = (cur & 0x7FFFFFFFu) >> 3, count = (cur & 7u) + 1u;
+            out.push_back((uint8_t)count);
+            for (uint32_t k = 0; k < count; k++) {
+                const node_f4 g = B.geom[first + k];
+                const float t = sphere_root(o, d, a, inv_a, g.x, g.y, g.z, g.w, kTMin, tbest);
+                if (t >= 0.0f) tbest = t;
+            }
+            cur = sp ? stack[--sp] : kEmptyScene;
+        }
+    }
+    out.push_back(255);
+}
 extern "C" uint64_t hh_step_sequences(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pad_rel, const hh_params* P,
                                       uint8_t* out, uint64_t cap) {
     HostBvh B;
@@ -318,7 +500,8 @@ extern "C" uint64_t hh_step_sequences(const hh_sphere* s, uint32_t n, uint32_t l
             st.thr = mk3(1.0f); st.seed = seed; st.depth = (int)P->max_depth - 1;
             f3 result;
             while (true) {
-                if (g_seq_postpone) trace_sequence_pp(sc, st.o, st.d, seq); else trace_sequence(sc, st.o, st.d, seq);
+                if (g_use_wide && B.wide_levels <= kWideMaxLevels) trace_sequence_wide(B, st.o, st.d, seq);
+                else if (g_seq_postpone) trace_sequence_pp(sc, st.o, st.d, seq); else trace_sequence(sc, st.o, st.d, seq);
                 float t; int prim; TraceCounters cnt{0, 0};
                 closest_hit<false>(sc.nodes, sc.geom, sc.root_link, st.o, st.d, t, prim, cnt);
                 if (!shade_segment(sc, st, t, prim, result)) break;

@@ -125,6 +125,36 @@ def test_lbvh_matches_cpu_emulation(ctx, host_harness, oracle_mod, rtiow, leaf):
     ctx.set_option("leaf_size", 2)
 
 
+@pytest.mark.parametrize("leaf", [1, 2, 3])
+def test_wide_nodes_match_cpu_emulation(ctx, host_harness, oracle_mod, rtiow, leaf):
+    """k_wide_build (one CTA, breadth-first with prefix sums) == the sequential host emulation, byte for byte, for
+    Karras- and SAH-split trees; scenes above "wide_max_prims" get none."""
+    from test_host_logic import _host_wide
+    scenes = [rtiow, np.ascontiguousarray(oracle_mod.random_scene(3000, 0x5EED0001, 30.0, 0)), np.ascontiguousarray(rtiow[:5]),
+              np.ascontiguousarray(rtiow[:1]), np.ascontiguousarray(oracle_mod.random_scene(9000, 0x5EED0003, 60.0, 1))]
+    try:
+        for sah in (4096, 0):
+            ctx.set_option("sah_max_prims", sah)
+            host_harness.hh_set_sah_max(sah)
+            for spheres in scenes:
+                ctx.set_option("leaf_size", leaf)
+                ctx.set_spheres(spheres)
+                ctx.build_bvh()
+                wide, levels = ctx.read_wide_bvh()
+                hw, hl = _host_wide(host_harness, spheres, leaf)
+                assert len(wide) == len(hw) and levels == hl
+                assert wide.tobytes() == hw.tobytes()
+        ctx.set_option("wide_max_prims", 1000)
+        ctx.set_spheres(scenes[1])
+        ctx.build_bvh()
+        assert len(ctx.read_wide_bvh()[0]) == 0
+    finally:
+        ctx.set_option("wide_max_prims", 16384)
+        ctx.set_option("sah_max_prims", 4096)
+        ctx.set_option("leaf_size", 2)
+        host_harness.hh_set_sah_max(4096)
+
+
 def test_lbvh_large_build_invariants(ctx, oracle_mod):
     """1 M spheres (BASELINE config 4 scale): sorted codes, permutation, root bounds; build time is reported."""
     n = 1_000_000
@@ -268,14 +298,24 @@ def test_octant_and_plain_persistent_kernels_agree(rtiow_ctx):
     W, H, spp, depth = 200, 120, 6, 50
     cam = vb.rtiow_camera(W, H)
     try:
+        rtiow_ctx.set_option("wide_nodes", 0)
         rtiow_ctx.set_option("octant_nodes", 1)
         a, ia, sa = render(rtiow_ctx, cam, W, H, spp, 2, depth)
         rtiow_ctx.set_option("octant_nodes", 0)
         b, ib, sb = render(rtiow_ctx, cam, W, H, spp, 2, depth)
         c, ic, sc = render(rtiow_ctx, cam, W, H, spp, 2, depth, flags=VN_COUNTERS)
+        rtiow_ctx.set_option("octant_nodes", 1)
+        d, idd, sd = render(rtiow_ctx, cam, W, H, spp, 2, depth, flags=VN_COUNTERS)
+        # the default: 4-wide octant-sorted nodes (half the node steps, same hits)
+        rtiow_ctx.set_option("wide_nodes", 1)
+        e, ie, se = render(rtiow_ctx, cam, W, H, spp, 2, depth)
+        f, iff, sf = render(rtiow_ctx, cam, W, H, spp, 2, depth, flags=VN_COUNTERS)
     finally:
         rtiow_ctx.set_option("octant_nodes", 1)
-    d, idd, sd = render(rtiow_ctx, cam, W, H, spp, 2, depth, flags=VN_COUNTERS)
+        rtiow_ctx.set_option("wide_nodes", 1)
+    assert se.segments == sf.segments == sa.segments
+    assert np.array_equal(a.view(np.uint32), e.view(np.uint32)) and np.array_equal(ia, ie) and np.array_equal(a.view(np.uint32), f.view(np.uint32))
+    assert sf.sphere_tests <= 1.02 * sc.sphere_tests and sf.node_visits < 0.55 * sc.node_visits
     assert sa.segments == sb.segments == sc.segments == sd.segments
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(ia, ib)
     assert np.array_equal(a.view(np.uint32), c.view(np.uint32)) and np.array_equal(a.view(np.uint32), d.view(np.uint32))

@@ -239,3 +239,91 @@ def test_octant_mirrored_traversal_equals_plain_on_cpu(host_harness, oracle_mod,
     orc = oracle_mod.Oracle(rtiow)
     t0, p0 = orc.closest_hit(o, d, use_bvh=False)
     assert np.array_equal(t0, out[1][0]) and np.array_equal(p0, out[1][1])
+
+
+def _host_wide(host_harness, spheres, leaf):
+    n = len(spheres)
+    wide = np.zeros((max(n, 1), 4, 2, 4), np.float32)
+    lev = C.c_uint32()
+    W = host_harness.hh_build_wide(spheres.ctypes.data_as(C.c_void_p), n, leaf, C.c_float(0.01), wide.ctypes.data_as(C.c_void_p), len(wide), C.byref(lev))
+    return wide[:W], lev.value
+
+
+@pytest.mark.parametrize("leaf", [1, 2, 3, 8])
+def test_wide_nodes_invariants_on_cpu(host_harness, oracle_mod, rtiow, leaf):
+    """The 4-wide nodes derived from the packed pairs (lbvh_core.cuh::wide_collapse, breadth-first): every sphere is in
+    exactly one leaf, every wide node is referenced exactly once, child boxes are the pairs' boxes, empty slots are
+    inverted boxes, and the level count is what the traversal stack was sized for."""
+    for spheres in (rtiow, np.ascontiguousarray(oracle_mod.random_scene(3000, 0x5EED0001, 30.0, 0)), np.ascontiguousarray(rtiow[:5])):
+        wide, levels = _host_wide(host_harness, spheres, leaf)
+        n = len(spheres)
+        if n <= leaf:
+            assert len(wide) == 0
+            continue
+        links = wide[:, :, 0, 3].copy().view(np.uint32)
+        seen = np.zeros(n, np.int32)
+        refs = np.zeros(len(wide), np.int32)
+        refs[0] = 1
+        for w in range(len(wide)):
+            kids = 0
+            for c in range(4):
+                l = int(links[w, c])
+                lo, hi = wide[w, c, 0, :3], wide[w, c, 1, :3]
+                if l == 0xFFFFFFFF:
+                    assert (lo > 1e38).all() and (hi < -1e38).all()
+                    continue
+                kids += 1
+                assert (lo <= hi).all()
+                if l & 0x80000000:
+                    first, cnt = (l & 0x7FFFFFFF) >> 3, (l & 7) + 1
+                    assert cnt <= leaf
+                    seen[first:first + cnt] += 1
+                else:
+                    assert w < l < len(wide)          # breadth-first: children come later
+                    refs[l] += 1
+            assert kids >= 2
+        assert (seen == 1).all() and (refs == 1).all()
+        assert 1 <= levels <= 20
+        assert len(wide) <= (n + 1) // 2 + 1
+
+
+def test_wide_traversal_equals_plain_on_cpu(host_harness, oracle_mod, rtiow):
+    """closest_hit_wide over the octant-sorted 4-wide nodes finds exactly the closest hits of the pair traversal and of
+    brute force, with fewer than half the node steps; a whole render through it is bit-identical to the oracle."""
+    rng = np.random.RandomState(29)
+    n = 30000
+    o = (rng.rand(n, 3).astype(np.float32) - np.float32(0.5)) * np.float32(30.0)
+    o[:, 1] = np.abs(o[:, 1]) * np.float32(0.2) + np.float32(0.01)
+    d = rng.randn(n, 3).astype(np.float32)
+    d[:50, 0] = 0.0
+    d[50:100, 1] = -0.0
+    d[100:150, 2] = 0.0
+    out = {}
+    try:
+        for wide in (0, 1):
+            host_harness.hh_set_wide(wide)
+            t = np.zeros(n, np.float32)
+            p = np.zeros(n, np.int32)
+            nv, st = C.c_uint64(), C.c_uint64()
+            host_harness.hh_closest_hit(rtiow.ctypes.data_as(C.c_void_p), len(rtiow), 2, C.c_float(0.01), o.ctypes.data_as(C.c_void_p),
+                                        d.ctypes.data_as(C.c_void_p), n, t.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p),
+                                        C.byref(nv), C.byref(st))
+            out[wide] = (t, p, nv.value, st.value)
+        assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+        assert out[1][2] < 0.6 * out[0][2]
+        orc = oracle_mod.Oracle(rtiow)
+        t0, p0 = orc.closest_hit(o, d, use_bvh=False)
+        assert np.array_equal(t0, out[1][0]) and np.array_equal(p0, out[1][1])
+        W, H, spp, sub, depth = 48, 27, 3, 5, 50
+        cam = oracle_mod.rtiow_camera(W, H)
+        hp = _hh_params(cam, W, H, spp, sub, depth)
+        want, stats = orc.render_mean(orc.params(cam, W, H, spp, sub, depth, atten=oracle_mod.ATTEN_FORWARD, closest=oracle_mod.CLOSEST_BRUTE))
+        for leaf in (1, 3):
+            mean = np.zeros((H, W, 4), np.float32)
+            segs, nv, st = C.c_uint64(), C.c_uint64(), C.c_uint64()
+            host_harness.hh_render_mean(rtiow.ctypes.data_as(C.c_void_p), len(rtiow), leaf, C.c_float(0.01), C.byref(hp),
+                                        mean.ctypes.data_as(C.c_void_p), C.byref(segs), C.byref(nv), C.byref(st))
+            assert segs.value == stats.segments and np.array_equal(mean, want)
+            assert nv.value / segs.value < 8
+    finally:
+        host_harness.hh_set_wide(0)

@@ -64,6 +64,7 @@ SIGNATURES = {
     "vn_build_bvh": (C.c_int, [C.c_void_p]),
     "vn_get_bvh_info": (C.c_int, [C.c_void_p, _P(vn_bvh_info)]),
     "vn_read_bvh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
+    "vn_read_wide_bvh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, _P(C.c_uint32), _P(C.c_uint32)]),
     "vn_resize": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "vn_reset_accum": (C.c_int, [C.c_void_p]),
     "vn_render": (C.c_int, [C.c_void_p, _P(vn_params)]),

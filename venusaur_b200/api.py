@@ -169,6 +169,15 @@ class Context:
         self._check(self.lib.vn_read_bvh(self.h, _ptr(nodes), len(nodes), _ptr(order), len(order)), "vn_read_bvh")
         return nodes, order
 
+    def read_wide_bvh(self):
+        """(nodes[num_wide, 4, 2, 4] float32 -- child c = {lo.xyz, link}, {hi.xyz, count} --, levels); empty when the scene has no 4-wide nodes."""
+        n, lev = C.c_uint32(), C.c_uint32()
+        self._check(self.lib.vn_read_wide_bvh(self.h, None, 0, C.byref(n), C.byref(lev)), "vn_read_wide_bvh")
+        nodes = np.zeros((n.value, 4, 2, 4), np.float32)
+        if n.value:
+            self._check(self.lib.vn_read_wide_bvh(self.h, _ptr(nodes), n.value, C.byref(n), C.byref(lev)), "vn_read_wide_bvh")
+        return nodes, lev.value
+
     def morton_codes(self) -> np.ndarray:
         codes = np.zeros(self.bvh_info().num_spheres, np.uint32)
         self._check(self.lib.vn_morton_codes(self.h, _ptr(codes), len(codes)), "vn_morton_codes")

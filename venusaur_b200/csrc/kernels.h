@@ -29,6 +29,8 @@ struct RenderLaunch {
     const float4* mat;
     const uint8_t* type;
     uint32_t root_link, num_nodes, num_spheres;
+    const float4* wide;              // canonical 4-wide nodes (8 float4 each) or null; staged per octant by the path kernel
+    uint32_t num_wide, wide_root;
     unsigned long long* counters;    // [0] segments, [1] paths, [2] node visits, [3] sphere tests
     uint32_t* work_counter;          // persistent-thread work ticket
     uint32_t total_work, tiles_x;    // work items = 8x4 pixel tiles * 32
@@ -41,9 +43,11 @@ struct KernelConfig {
     bool scene_in_smem;
     bool count;                      // instrumented variant
     bool octant;                     // nodes staged 8x in shared memory, once per ray-direction octant (near/far-plane form)
+    bool wide;                       // 4-wide octant-sorted nodes in shared memory (implies scene_in_smem; excludes octant)
 };
 
 size_t scene_smem_bytes(uint32_t num_nodes, uint32_t num_spheres, uint32_t node_copies = 1);
+size_t wide_smem_bytes(uint32_t num_wide, uint32_t num_spheres);
 
 // Wavefront state: SoA queues in HBM (L2-resident at the default capacity), owned by the context.
 // One path slot = 48 bytes of ray state (o 12, d 12, throughput 12, seed 4, sample slot 4, depth 4).
@@ -74,7 +78,7 @@ struct WavefrontBuffers {
 constexpr int kWfArraysTotal = 2 * kWfStateArrays + 2 + 4;   // 4-byte arrays of `capacity` entries in the slab
 
 #define VN_DECLARE_KERNEL_API                                                                                          \
-    int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool count, bool octant);                \
+    int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool count, bool octant, bool wide);              \
     cudaError_t launch_render_persistent(const RenderLaunch& p, const KernelConfig& cfg, cudaStream_t stream);         \
     cudaError_t launch_tonemap(const float4* accum, float scale, uint32_t* image, uint64_t n, cudaStream_t stream);    \
     cudaError_t launch_reduce_tonemap_peers(const float4* const* peers, uint32_t n_peers, float scale, uint64_t begin, \

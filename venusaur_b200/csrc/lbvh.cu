@@ -104,6 +104,90 @@ __global__ void __launch_bounds__(kBlock) k_karras(const uint32_t* __restrict__ 
     if (k.right & kChildLeaf) parent_leaf[k.right & ~kChildLeaf] = i; else parent_internal[k.right] = i;
 }
 
+// ---- stage 4': SAH splits for small scenes, one CTA, level by level (see lbvh_core.cuh for the per-element bodies).
+// Every level: (1) each (axis, position) candidate of every active node evaluates its SAH cost by brute force over the
+// node's range and does a 64-bit atomicMin on the node's slot; (2) every position is moved by a stable partition around
+// its node's winning candidate, the node is emitted with Karras' id convention and its children become active.
+constexpr int kSahThreads = 1024;
+constexpr uint32_t kMaxSahHeight = 48;   // < kStackSize (64) with margin
+constexpr uint32_t kSahInactive = 0xFFFFFFFFu;
+
+__global__ void __launch_bounds__(kSahThreads) k_sah_small(uint32_t n, const f4* __restrict__ cen, const f4* __restrict__ blo, const f4* __restrict__ bhi,
+                                                          uint32_t* permA, uint32_t* permB, uint32_t* ownerA, uint32_t* ownerB,
+                                                          unsigned long long* best, uint32_t* nfirst, uint32_t* nlast, KarrasNode* kn,
+                                                          uint32_t* parent_internal, uint32_t* parent_leaf, uint32_t* perm_final, uint32_t* height_out) {
+    const uint32_t tid = threadIdx.x;
+    uint32_t levels = 0;
+    for (uint32_t p = tid; p < n; p += kSahThreads) { permA[p] = p; ownerA[p] = n >= 2u ? 0u : kSahInactive; }
+    if (tid == 0) { nfirst[0] = 0u; nlast[0] = n - 1u; }
+    __syncthreads();
+    uint32_t *perm = permA, *pnext = permB, *own = ownerA, *onext = ownerB;
+    for (uint32_t level = 0; level < n; level++) {
+        for (uint32_t p = tid; p < n; p += kSahThreads) {
+            const uint32_t id = own[p];
+            if (id != kSahInactive && p == nfirst[id]) best[id] = ~0ull;
+        }
+        __syncthreads();
+        for (uint32_t idx = tid; idx < 3u * n; idx += kSahThreads) {
+            const uint32_t a = idx / n, p = idx - a * n;
+            const uint32_t id = own[p];
+            if (id == kSahInactive) continue;
+            const uint32_t first = nfirst[id], last = nlast[id];
+            uint32_t nl;
+            const float cost = sah_candidate_cost(perm, first, last, p, (int)a, cen, blo, bhi, &nl);
+            if (cost < 3e38f) atomicMin(&best[id], sah_pack(cost, (int)a, p - first));
+        }
+        __syncthreads();
+        bool any = false;
+        for (uint32_t p = tid; p < n; p += kSahThreads) {
+            const uint32_t id = own[p];
+            const uint32_t e = perm[p];
+            if (id == kSahInactive) { pnext[p] = e; onext[p] = kSahInactive; continue; }
+            any = true;
+            const uint32_t first = nfirst[id], last = nlast[id];
+            // best[] was updated with atomics, which are performed in L2 and do not refresh this SM's L1 copy of the
+            // line (it holds the ~0 written above): read it with ld.cg
+            const unsigned long long b = __ldcg(&best[id]);
+            const int a = (int)((b >> 28) & 3ull);
+            const uint32_t es = perm[first + (uint32_t)(b & 0xFFFFFFFull)];
+            const SahKey key{axis_of(cen[es], a), es};
+            uint32_t nL = 0, before_l = 0, before_r = 0;
+            for (uint32_t q = first; q <= last; q++) {
+                const uint32_t eq = perm[q];
+                const bool l = sah_key_le(axis_of(cen[eq], a), eq, key);
+                nL += l ? 1u : 0u;
+                if (q < p) { if (l) before_l++; else before_r++; }
+            }
+            const bool me_left = sah_key_le(axis_of(cen[e], a), e, key);
+            const uint32_t gamma = first + nL - 1u, nR = last - gamma;
+            const uint32_t newpos = me_left ? first + before_l : first + nL + before_r;
+            pnext[newpos] = e;
+            onext[newpos] = me_left ? (nL >= 2u ? gamma : kSahInactive) : (nR >= 2u ? gamma + 1u : kSahInactive);
+            if (p == first) {
+                KarrasNode k;
+                k.left = nL == 1u ? (kChildLeaf | first) : gamma;
+                k.right = nR == 1u ? (kChildLeaf | last) : gamma + 1u;
+                k.first = first; k.last = last;
+                kn[id] = k;
+                if (nL == 1u) parent_leaf[first] = id; else { parent_internal[gamma] = id; nfirst[gamma] = first; nlast[gamma] = gamma; }
+                if (nR == 1u) parent_leaf[last] = id; else { parent_internal[gamma + 1u] = id; nfirst[gamma + 1u] = gamma + 1u; nlast[gamma + 1u] = last; }
+            }
+        }
+        any = __syncthreads_or(any ? 1 : 0) != 0;
+        uint32_t* t = perm; perm = pnext; pnext = t;
+        t = own; own = onext; onext = t;
+        if (!any) break;
+        levels += 1u;
+    }
+    for (uint32_t p = tid; p < n; p += kSahThreads) perm_final[p] = perm[p];
+    if (tid == 0) *height_out = levels;   // levels of internal nodes = entries the traversal stack may need
+}
+
+__global__ void __launch_bounds__(kBlock) k_compose(const uint32_t* __restrict__ perm, const uint32_t* __restrict__ idx, uint32_t n, uint32_t* __restrict__ out) {
+    const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    if (i < n) out[i] = idx[perm[i]];
+}
+
 __device__ __forceinline__ f4 ldcg4(const f4* p) {
     const float4 v = __ldcg(reinterpret_cast<const float4*>(p));
     return f4{v.x, v.y, v.z, v.w};
@@ -237,6 +321,51 @@ __global__ void __launch_bounds__(kBlock) k_pack(uint32_t n, const KarrasNode* _
     store_node(nodes, base + 1u, pack_child(kn[i].right, kn, rank, ilo, ihi, leaf_lo, leaf_hi, leaf_size));
 }
 
+// ---- stage 7 (small scenes): 4-wide nodes from the packed pairs, breadth-first in ONE CTA so that the node order is
+// deterministic (prefix sums, no atomics): each level's wide nodes open their pair (lbvh_core.cuh::wide_collapse) and
+// their internal children receive consecutive indices in entry order.  result[1] = wide nodes, result[2] = levels.
+__global__ void __launch_bounds__(kBlock) k_wide_build(const float4* __restrict__ nodes, uint32_t* src, uint32_t cap, float4* __restrict__ wide,
+                                                      uint32_t* __restrict__ result) {
+    __shared__ uint32_t s_warp[kBlock / 32];
+    const uint32_t root_link = __float_as_uint(nodes[2].w);
+    if (root_link & kLeafFlag) {            // a single leaf or the empty scene: nothing to widen
+        if (threadIdx.x == 0) { result[1] = 0u; result[2] = 0u; }
+        return;
+    }
+    if (threadIdx.x == 0) src[0] = root_link;
+    __syncthreads();
+    uint32_t lo = 0, hi = 1, levels = 0;
+    while (lo < hi) {
+        levels += 1u;
+        uint32_t next = hi;
+        for (uint32_t base = lo; base < hi; base += kBlock) {
+            const uint32_t e = base + threadIdx.x;
+            uint32_t ch[4], n = 0, n_internal = 0;
+            if (e < hi) {
+                n = wide_collapse(nodes, src[e], ch);
+                for (uint32_t c = 0; c < n; c++) n_internal += (__float_as_uint(nodes[2 * ch[c]].w) & kLeafFlag) ? 0u : 1u;
+            }
+            uint32_t total;
+            uint32_t at = next + block_exclusive_scan(n_internal, s_warp, &total);
+            if (e < hi) {
+                for (uint32_t c = 0; c < 4u; c++) {
+                    float4 a = make_float4(3e38f, 3e38f, 3e38f, __uint_as_float(kWideEmpty)), b = make_float4(-3e38f, -3e38f, -3e38f, 0.0f);
+                    if (c < n) {
+                        a = nodes[2 * ch[c]]; b = nodes[2 * ch[c] + 1];
+                        const uint32_t link = __float_as_uint(a.w);
+                        if (!(link & kLeafFlag)) { if (at < cap) src[at] = link; a.w = __uint_as_float(at); at += 1u; }
+                    }
+                    wide[8ull * e + 2 * c] = a; wide[8ull * e + 2 * c + 1] = b;
+                }
+            }
+            next += total;
+        }
+        __syncthreads();
+        lo = hi; hi = next;
+    }
+    if (threadIdx.x == 0) { result[1] = hi; result[2] = levels; }
+}
+
 #define LB_CHECK(call)                                                                                   \
     do {                                                                                                 \
         cudaError_t e_ = (call);                                                                         \
@@ -271,7 +400,8 @@ struct Arena {
 };
 }  // namespace
 
-int lbvh_build(const vn_sphere* d_spheres, uint64_t n64, uint32_t leaf_size, float pad_rel, int num_sms, cudaStream_t stream,
+int lbvh_build(const vn_sphere* d_spheres, uint64_t n64, uint32_t leaf_size, float pad_rel, uint32_t sah_max_prims, uint32_t wide_max_prims, int num_sms,
+               cudaStream_t stream,
                LbvhScene& out, LbvhWorkspace& ws, uint32_t* launches, std::string& err) {
     lbvh_free(out);
     if (n64 > (1ull << 28)) { err = "too many spheres (limit 2^28)"; return -1; }
@@ -295,7 +425,9 @@ int lbvh_build(const vn_sphere* d_spheres, uint64_t n64, uint32_t leaf_size, flo
         const uint32_t nb = (uint32_t)((ni + kScanTile - 1) / kScanTile);
         // ---- outputs: one allocation (nodes at their upper bound 2n+2, so the node count needs no mid-build sync)
         Arena oa;
+        const bool want_wide = n <= wide_max_prims;
         oa.take<float4>(2 * (2ull * n + 2)); oa.take<float4>(n); oa.take<float4>(n); oa.take<uint32_t>(n); oa.take<uint32_t>(n); oa.take<uint8_t>(n);
+        if (want_wide) oa.take<float4>(8ull * n);
         const size_t out_bytes = oa.off + 256;
         LB_CHECK(cudaMalloc(&out.arena, out_bytes));
         oa = Arena{static_cast<char*>(out.arena), 0};
@@ -305,11 +437,13 @@ int lbvh_build(const vn_sphere* d_spheres, uint64_t n64, uint32_t leaf_size, flo
         out.orig = oa.take<uint32_t>(n);
         out.codes = oa.take<uint32_t>(n);
         out.type = oa.take<uint8_t>(n);
+        out.wide = want_wide ? oa.take<float4>(8ull * n) : nullptr;
         // ---- temporaries: one cached workspace that only grows
         Arena ta;
         auto carve = [&](Arena& t, uint32_t*& bounds, uint32_t*& codes0, uint32_t*& codes1, uint32_t*& idx0, uint32_t*& idx1, void*& sortws,
                          f4*& leaf_lo, f4*& leaf_hi, KarrasNode*& kn, f4*& ilo, f4*& ihi, uint32_t*& parent_i, uint32_t*& parent_l,
-                         uint32_t*& arrivals, uint32_t*& kept, uint32_t*& rank, uint32_t*& sums, uint32_t*& result) {
+                         uint32_t*& arrivals, uint32_t*& kept, uint32_t*& rank, uint32_t*& sums, uint32_t*& result, uint32_t*& sah_u32,
+                         unsigned long long*& sah_best) {
             bounds = t.take<uint32_t>(8);
             result = t.take<uint32_t>(8);
             codes0 = t.take<uint32_t>(n); codes1 = t.take<uint32_t>(n); idx0 = t.take<uint32_t>(n); idx1 = t.take<uint32_t>(n);
@@ -320,12 +454,15 @@ int lbvh_build(const vn_sphere* d_spheres, uint64_t n64, uint32_t leaf_size, flo
             parent_i = t.take<uint32_t>(ni + 1); parent_l = t.take<uint32_t>(n);
             arrivals = t.take<uint32_t>(ni + 1); kept = t.take<uint32_t>(ni + 1); rank = t.take<uint32_t>(ni + 1);
             sums = t.take<uint32_t>(nb + 2);
+            sah_u32 = t.take<uint32_t>(8ull * n);
+            sah_best = t.take<unsigned long long>(n);
         };
-        uint32_t *bounds, *codes0, *codes1, *idx0, *idx1, *parent_i, *parent_l, *arrivals, *kept, *rank, *sums, *result;
+        uint32_t *bounds, *codes0, *codes1, *idx0, *idx1, *parent_i, *parent_l, *arrivals, *kept, *rank, *sums, *result, *sah_u32;
+        unsigned long long* sah_best;
         void* sortws;
         KarrasNode* kn;
         f4 *leaf_lo, *leaf_hi, *ilo, *ihi;
-        carve(ta, bounds, codes0, codes1, idx0, idx1, sortws, leaf_lo, leaf_hi, kn, ilo, ihi, parent_i, parent_l, arrivals, kept, rank, sums, result);
+        carve(ta, bounds, codes0, codes1, idx0, idx1, sortws, leaf_lo, leaf_hi, kn, ilo, ihi, parent_i, parent_l, arrivals, kept, rank, sums, result, sah_u32, sah_best);
         const size_t need = ta.off + 256;
         if (ws.bytes < need) {
             cudaFree(ws.ptr);
@@ -334,7 +471,7 @@ int lbvh_build(const vn_sphere* d_spheres, uint64_t n64, uint32_t leaf_size, flo
             ws.bytes = need;
         }
         ta = Arena{static_cast<char*>(ws.ptr), 0};
-        carve(ta, bounds, codes0, codes1, idx0, idx1, sortws, leaf_lo, leaf_hi, kn, ilo, ihi, parent_i, parent_l, arrivals, kept, rank, sums, result);
+        carve(ta, bounds, codes0, codes1, idx0, idx1, sortws, leaf_lo, leaf_hi, kn, ilo, ihi, parent_i, parent_l, arrivals, kept, rank, sums, result, sah_u32, sah_best);
 
         const uint32_t init[6] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u};
         LB_CHECK(cudaMemcpyAsync(bounds, init, sizeof(init), cudaMemcpyHostToDevice, stream));
@@ -352,8 +489,22 @@ int lbvh_build(const vn_sphere* d_spheres, uint64_t n64, uint32_t leaf_size, flo
         k_gather<<<blocks_for(n), kBlock, 0, stream>>>(d_spheres, idx, n, pad_rel, out.geom, out.mat, out.type, out.orig, leaf_lo, leaf_hi);
         launched += 1;
         LB_CHECK(cudaMemcpyAsync(out.codes, codes, 4ull * n, cudaMemcpyDeviceToDevice, stream));   // kept for vn_morton_codes()
+        uint32_t* height = result;               // written by k_sah_small only
+        const bool use_sah = ni > 0 && n <= sah_max_prims;
+        out.sah = use_sah;
+        if (use_sah) {
+            // small scene: SAH splits instead of Karras' spatial medians, then re-gather in the final primitive order
+            uint32_t *permA = sah_u32, *permB = sah_u32 + n, *ownA = sah_u32 + 2ull * n, *ownB = sah_u32 + 3ull * n, *nfirst = sah_u32 + 4ull * n,
+                     *nlast = sah_u32 + 5ull * n, *perm_final = sah_u32 + 6ull * n, *final_idx = sah_u32 + 7ull * n;
+            k_sah_small<<<1, kSahThreads, 0, stream>>>(n, reinterpret_cast<const f4*>(out.geom), leaf_lo, leaf_hi, permA, permB, ownA, ownB, sah_best,
+                                                      nfirst, nlast, kn, parent_i, parent_l, perm_final, height);
+            k_compose<<<blocks_for(n), kBlock, 0, stream>>>(perm_final, idx, n, final_idx);
+            // the SAH kernel read geom/leaf boxes in Morton order; they are rewritten in the final order on the stream after it
+            k_gather<<<blocks_for(n), kBlock, 0, stream>>>(d_spheres, final_idx, n, pad_rel, out.geom, out.mat, out.type, out.orig, leaf_lo, leaf_hi);
+            launched += 3;
+        }
         if (ni > 0) {
-            k_karras<<<blocks_for(ni), kBlock, 0, stream>>>(codes, n, kn, parent_i, parent_l);
+            if (!use_sah) k_karras<<<blocks_for(ni), kBlock, 0, stream>>>(codes, n, kn, parent_i, parent_l);
             k_refit<<<blocks_for(n), kBlock, 0, stream>>>(n, kn, parent_i, parent_l, leaf_lo, leaf_hi, ilo, ihi, arrivals);
             k_mark_kept<<<blocks_for(ni), kBlock, 0, stream>>>(kn, ni, leaf_size, kept);
             k_scan_block_sums<<<nb, kBlock, 0, stream>>>(kept, ni, sums);
@@ -363,10 +514,17 @@ int lbvh_build(const vn_sphere* d_spheres, uint64_t n64, uint32_t leaf_size, flo
         }
         k_pack<<<blocks_for(n), kBlock, 0, stream>>>(n, kn, rank, ilo, ihi, leaf_lo, leaf_hi, leaf_size, out.nodes);
         launched += 1;
+        if (want_wide) {
+            // sah_u32 is free again here (the SAH pass, if any, has been consumed by the second gather): queue of pair links
+            k_wide_build<<<1, kBlock, 0, stream>>>(out.nodes, sah_u32, n, out.wide, result);
+            launched += 1;
+        }
         // one host round trip at the end: kept-node count, root link, root bounds
         uint32_t host[12] = {0};
         LB_CHECK(cudaMemcpyAsync(&host[0], sums + nb, 4, cudaMemcpyDeviceToHost, stream));
         LB_CHECK(cudaMemcpyAsync(&host[4], reinterpret_cast<const char*>(out.nodes) + 2 * sizeof(float4), 2 * sizeof(float4), cudaMemcpyDeviceToHost, stream));
+        if (use_sah) LB_CHECK(cudaMemcpyAsync(&host[1], height, 4, cudaMemcpyDeviceToHost, stream));
+        if (want_wide) LB_CHECK(cudaMemcpyAsync(&host[2], result + 1, 8, cudaMemcpyDeviceToHost, stream));
         LB_CHECK(cudaStreamSynchronize(stream));
         LB_CHECK(cudaGetLastError());
         const uint32_t total_kept = ni > 0 ? host[0] : 0u;
@@ -374,6 +532,15 @@ int lbvh_build(const vn_sphere* d_spheres, uint64_t n64, uint32_t leaf_size, flo
         out.root_link = host[7];
         memcpy(out.bounds_lo, &host[4], 12);
         memcpy(out.bounds_hi, &host[8], 12);
+        out.num_wide = want_wide ? host[2] : 0u;
+        out.wide_levels = want_wide ? host[3] : 0u;
+        out.height = use_sah ? host[1] : 0u;     // 0 = not measured (Karras: bounded by the 30-bit key + index tie-break)
+        if (use_sah && out.height > kMaxSahHeight) {
+            // a degenerate scene (e.g. hundreds of coincident spheres) makes SAH peel one primitive per level; the
+            // traversal stack holds kStackSize entries, so fall back to Karras, whose height is bounded by the key width
+            if (launches) *launches += launched;
+            return lbvh_build(d_spheres, n64, leaf_size, pad_rel, 0u, wide_max_prims, num_sms, stream, out, ws, launches, err);
+        }
     }
     if (launches) *launches += launched;
     return 0;

@@ -24,6 +24,10 @@ struct LbvhScene {
     uint64_t num_nodes = 0;
     uint32_t root_link = 0xFFFFFFFFu;
     uint32_t leaf_size = 0;
+    float4* wide = nullptr;      // num_wide x 128 B: 4-wide nodes derived from the pairs (small scenes only), see lbvh_core.cuh
+    uint32_t num_wide = 0, wide_levels = 0;
+    uint32_t height = 0;         // levels of internal nodes (the traversal stack must hold that many entries)
+    bool sah = false;            // splits chosen by the surface-area heuristic (small scenes) instead of Karras' spatial medians
     float bounds_lo[3] = {0, 0, 0}, bounds_hi[3] = {0, 0, 0};
 };
 
@@ -37,7 +41,8 @@ struct LbvhWorkspace {
 void lbvh_workspace_free(LbvhWorkspace& ws);
 
 // Builds the packed LBVH for n spheres already resident on the device.  Returns 0 or a negative status with `err` set.
-int lbvh_build(const vn_sphere* d_spheres, uint64_t n, uint32_t leaf_size, float pad_rel, int num_sms, cudaStream_t stream,
+int lbvh_build(const vn_sphere* d_spheres, uint64_t n, uint32_t leaf_size, float pad_rel, uint32_t sah_max_prims, uint32_t wide_max_prims, int num_sms,
+               cudaStream_t stream,
                LbvhScene& out, LbvhWorkspace& ws, uint32_t* launches, std::string& err);
 
 // Onesweep sort of device (key, value) pairs; returns 0/1 = which buffer pair holds the result, or -1.

@@ -115,3 +115,114 @@ VN_HD PackedNode pack_child(uint32_t child, const KarrasNode* __restrict__ kn, c
 }
 
 }  // namespace vn
+
+// ---- optional stage 4': surface-area-heuristic splits for SMALL scenes (n <= sah_max_prims), replacing Karras' spatial-
+// median splits.  The tree keeps Karras' conventions (contiguous primitive ranges, left child id = last index of its
+// range, right child id = first index of its range, root id 0), so refit and packing are unchanged.  Candidate split
+// = (axis, primitive): everything whose centroid key is <= that primitive's goes left.  Per-element bodies:
+namespace vn {
+
+struct SahKey { float c; uint32_t id; };
+VN_HD bool sah_key_le(float c, uint32_t id, SahKey k) { return c < k.c || (c == k.c && id <= k.id); }
+VN_HD float box_area(float lx, float ly, float lz, float hx, float hy, float hz) {
+    const float dx = fmaxf(hx - lx, 0.0f), dy = fmaxf(hy - ly, 0.0f), dz = fmaxf(hz - lz, 0.0f);
+    return 2.0f * (dx * dy + dy * dz + dz * dx);
+}
+VN_HD float axis_of(const f4& v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
+
+// SAH cost of splitting range [first,last] of perm[] at candidate (axis a, position p); returns +inf-like (3e38) when the
+// split would leave one side empty.  cen = primitive centres, blo/bhi = padded primitive boxes (all indexed by primitive).
+VN_HD float sah_candidate_cost(const uint32_t* __restrict__ perm, uint32_t first, uint32_t last, uint32_t p, int a,
+                               const f4* __restrict__ cen, const f4* __restrict__ blo, const f4* __restrict__ bhi, uint32_t* n_left_out) {
+    const uint32_t ep = perm[p];
+    const SahKey key{axis_of(cen[ep], a), ep};
+    float llx = 3e38f, lly = 3e38f, llz = 3e38f, lhx = -3e38f, lhy = -3e38f, lhz = -3e38f;
+    float rlx = 3e38f, rly = 3e38f, rlz = 3e38f, rhx = -3e38f, rhy = -3e38f, rhz = -3e38f;
+    uint32_t nl = 0, nr = 0;
+    for (uint32_t q = first; q <= last; q++) {
+        const uint32_t e = perm[q];
+        const f4 lo = blo[e], hi = bhi[e];
+        if (sah_key_le(axis_of(cen[e], a), e, key)) {
+            llx = fminf(llx, lo.x); lly = fminf(lly, lo.y); llz = fminf(llz, lo.z);
+            lhx = fmaxf(lhx, hi.x); lhy = fmaxf(lhy, hi.y); lhz = fmaxf(lhz, hi.z);
+            nl++;
+        } else {
+            rlx = fminf(rlx, lo.x); rly = fminf(rly, lo.y); rlz = fminf(rlz, lo.z);
+            rhx = fmaxf(rhx, hi.x); rhy = fmaxf(rhy, hi.y); rhz = fmaxf(rhz, hi.z);
+            nr++;
+        }
+    }
+    *n_left_out = nl;
+    if (nr == 0u) return 3e38f;
+    return box_area(llx, lly, llz, lhx, lhy, lhz) * (float)nl + box_area(rlx, rly, rlz, rhx, rhy, rhz) * (float)nr;
+}
+
+// (cost, axis, position-in-range) packed so that an unsigned 64-bit min picks the cheapest candidate, ties broken by
+// axis then position: deterministic on CPU and GPU.
+VN_HD unsigned long long sah_pack(float cost, int a, uint32_t rel_pos) {
+    return ((unsigned long long)f2u(cost) << 32) | ((unsigned long long)a << 28) | (unsigned long long)rel_pos;
+}
+
+}  // namespace vn
+
+// ---- optional stage 7: 4-wide nodes derived from the packed pairs, for scenes that are traversed out of shared memory.
+// A wide node is a packed internal node whose pair has been opened greedily (largest surface area first) until it has
+// four children or only leaves are left.  Canonical form (global memory, what vn_read_wide_bvh returns): 8 float4 per
+// wide node, child c = { {lo.xyz, link}, {hi.xyz, count} }; link = wide-node index, a leaf link (as in the packed
+// nodes) or kWideEmpty with an inverted box.  Half as many traversal steps as the pairs, four slab tests per step.
+namespace vn {
+
+constexpr uint32_t kWideEmpty = 0xFFFFFFFFu;
+constexpr uint32_t kWideMaxLevels = 20;    // 3 pushes per level + 1 <= kStackSize
+
+VN_HD float packed_area(const node_f4& a, const node_f4& b) { return box_area(a.x, a.y, a.z, b.x, b.y, b.z); }
+
+// Opens the pair at `pair_link`; out[] = packed-node indices of the (2..4) children in stable left-to-right order.
+VN_HD uint32_t wide_collapse(const node_f4* __restrict__ nodes, uint32_t pair_link, uint32_t* out) {
+    uint32_t n = 2;
+    out[0] = pair_link; out[1] = pair_link + 1u;
+    while (n < 4u) {
+        int best = -1;
+        float best_area = -1.0f;
+        for (uint32_t i = 0; i < n; i++) {
+            const node_f4 a = nodes[2 * out[i]], b = nodes[2 * out[i] + 1];
+            if (f2u(a.w) & kLeafFlag) continue;
+            const float area = packed_area(a, b);
+            if (area > best_area) { best_area = area; best = (int)i; }
+        }
+        if (best < 0) break;
+        const uint32_t link = f2u(nodes[2 * out[best]].w);
+        for (uint32_t i = n; i > (uint32_t)best + 1u; i--) out[i] = out[i - 1];
+        out[best] = link; out[best + 1] = link + 1u;
+        n++;
+    }
+    return n;
+}
+
+// Octant-specialised shared-memory form of one wide node: 7 float4 = near.x[4] near.y[4] near.z[4] far.x[4] far.y[4]
+// far.z[4] link[4], children sorted front to back for rays of that octant (by box centre along the octant diagonal,
+// ties by canonical position; empty slots last), near/far planes already selected per axis.  With the order fixed per
+// octant the traversal needs no distance compare and no per-axis min/max.
+VN_HD void wide_octant_node(const node_f4* __restrict__ canon /* 8 float4 */, uint32_t octant, node_f4* out /* 7 float4 */) {
+    float key[4];
+    int ord[4];
+    for (int c = 0; c < 4; c++) {
+        const node_f4 lo = canon[2 * c], hi = canon[2 * c + 1];
+        const float kx = lo.x + hi.x, ky = lo.y + hi.y, kz = lo.z + hi.z;
+        key[c] = f2u(lo.w) == kWideEmpty ? 3e38f : ((octant & 1u) ? -kx : kx) + ((octant & 2u) ? -ky : ky) + ((octant & 4u) ? -kz : kz);
+        ord[c] = c;
+    }
+    for (int i = 1; i < 4; i++)                                       // stable insertion sort
+        for (int j = i; j > 0 && key[ord[j]] < key[ord[j - 1]]; j--) { const int t = ord[j]; ord[j] = ord[j - 1]; ord[j - 1] = t; }
+    float v[7][4];
+    for (int s = 0; s < 4; s++) {
+        const node_f4 lo = canon[2 * ord[s]], hi = canon[2 * ord[s] + 1];
+        v[0][s] = (octant & 1u) ? hi.x : lo.x; v[3][s] = (octant & 1u) ? lo.x : hi.x;
+        v[1][s] = (octant & 2u) ? hi.y : lo.y; v[4][s] = (octant & 2u) ? lo.y : hi.y;
+        v[2][s] = (octant & 4u) ? hi.z : lo.z; v[5][s] = (octant & 4u) ? lo.z : hi.z;
+        v[6][s] = lo.w;
+    }
+    for (int r = 0; r < 7; r++) { out[r].x = v[r][0]; out[r].y = v[r][1]; out[r].z = v[r][2]; out[r].w = v[r][3]; }
+}
+
+}  // namespace vn

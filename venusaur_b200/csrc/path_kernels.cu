@@ -20,6 +20,7 @@
 #include <algorithm>
 
 #include "kernels.h"
+#include "lbvh_core.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -34,6 +35,9 @@ namespace vn {
 #if VN_EXACT
 size_t scene_smem_bytes(uint32_t num_nodes, uint32_t num_spheres, uint32_t node_copies) {
     return (size_t)num_nodes * 32 * node_copies + (size_t)num_spheres * 32 + (((size_t)num_spheres + 15) & ~(size_t)15);
+}
+size_t wide_smem_bytes(uint32_t num_wide, uint32_t num_spheres) {
+    return (size_t)num_wide * 16 * kWideNodeF4 * 8 + (size_t)num_spheres * 32 + (((size_t)num_spheres + 15) & ~(size_t)15);
 }
 #endif
 
@@ -63,18 +67,30 @@ __device__ __forceinline__ void finish_pixel(const RenderLaunch& p, uint32_t pix
     // that happen to finish a pixel in this iteration would cost every other lane of the warp the same issue slots.
 }
 
-template <bool kSmem, bool kCount, bool kOct, int kMaxThreads>
+template <bool kSmem, bool kCount, bool kOct, int kMaxThreads, bool kWide = false>
 __global__ void __launch_bounds__(kMaxThreads) k_render_persistent(const __grid_constant__ RenderLaunch p) {
     extern __shared__ float4 s_scene[];
     SceneView sc;
-    const uint32_t node_f4s = 2 * p.num_nodes;
+    const uint32_t node_f4s = kWide ? kWideNodeF4 * p.num_wide : 2 * p.num_nodes;
     if (kSmem) {
         // stage nodes | geom | mat | type into shared memory with 128-bit copies
         float4* s_nodes = s_scene;
-        float4* s_geom = s_nodes + (size_t)node_f4s * (kOct ? 8 : 1);
+        float4* s_geom = s_nodes + (size_t)node_f4s * ((kOct || kWide) ? 8 : 1);
         float4* s_mat = s_geom + p.num_spheres;
         uint8_t* s_type = reinterpret_cast<uint8_t*>(s_mat + p.num_spheres);
-        if (kOct) {
+        if (kWide) {
+            // 8 octant-specialised copies of the 4-wide nodes: children sorted front to back for that octant, planes in
+            // near/far form (lbvh_core.cuh::wide_octant_node); one thread per (octant, node)
+            for (uint32_t i = threadIdx.x; i < 8u * p.num_wide; i += blockDim.x) {
+                const uint32_t k = i / p.num_wide, j = i - k * p.num_wide;
+                float4 canon[8], out[kWideNodeF4];
+#pragma unroll
+                for (int q = 0; q < 8; q++) canon[q] = p.wide[8ull * j + q];
+                wide_octant_node(canon, k, out);
+#pragma unroll
+                for (int q = 0; q < (int)kWideNodeF4; q++) s_nodes[(size_t)k * node_f4s + kWideNodeF4 * j + q] = out[q];
+            }
+        } else if (kOct) {
             // 8 copies of the node array, one per ray-direction octant, in near/far-plane form: for octant k the first
             // float4 of a node holds the planes a ray of that octant enters through (hi where the direction component
             // is negative), the second the planes it leaves through.  227 KB of shared memory buys the removal of the
@@ -141,7 +157,8 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_persistent(const __grid_
         }
         float t;
         int prim;
-        closest_hit<kCount, kOct>(sc.nodes, sc.geom, sc.root_link, st.o, st.d, t, prim, cnt, node_f4s);
+        if (kWide) closest_hit_wide<kCount>(sc.nodes, node_f4s, sc.geom, p.wide_root, st.o, st.d, t, prim, cnt);
+        else closest_hit<kCount, kOct>(sc.nodes, sc.geom, sc.root_link, st.o, st.d, t, prim, cnt, node_f4s);
         n_seg += 1u;
         if (kCount) { n_nodes += cnt.nodes; n_sph += cnt.spheres; cnt.nodes = 0; cnt.spheres = 0; }
         f3 result;
@@ -260,23 +277,24 @@ inline uint32_t grid_for(uint64_t n, int threads) { return (uint32_t)((n + threa
 
 namespace {
 typedef void (*PathKernel)(const RenderLaunch);
-PathKernel pick_kernel(bool scene_in_smem, bool count, bool octant) {
+PathKernel pick_kernel(bool scene_in_smem, bool count, bool octant, bool wide = false) {
+    if (wide) return count ? k_render_persistent<true, true, false, 1024, true> : k_render_persistent<true, false, false, 1024, true>;
     if (scene_in_smem && octant) return count ? k_render_persistent<true, true, true, 1024> : k_render_persistent<true, false, true, 1024>;
     if (scene_in_smem) return count ? k_render_persistent<true, true, false, 256> : k_render_persistent<true, false, false, 256>;
     return count ? k_render_persistent<false, true, false, 256> : k_render_persistent<false, false, false, 256>;
 }
 }  // namespace
 
-int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool count, bool octant) {
+int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool count, bool octant, bool wide) {
     int nb = 0;
-    PathKernel k = pick_kernel(scene_in_smem, count, octant);
+    PathKernel k = pick_kernel(scene_in_smem, count, octant, wide);
     if (smem_bytes > 48 * 1024 && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) return -1;
     const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, threads, smem_bytes);
     return e == cudaSuccess ? nb : -1;
 }
 
 cudaError_t launch_render_persistent(const RenderLaunch& p, const KernelConfig& cfg, cudaStream_t stream) {
-    PathKernel k = pick_kernel(cfg.scene_in_smem, cfg.count, cfg.octant);
+    PathKernel k = pick_kernel(cfg.scene_in_smem, cfg.count, cfg.octant, cfg.wide);
     if (cfg.smem_bytes > 48 * 1024) {
         const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes);
         if (e != cudaSuccess) return e;

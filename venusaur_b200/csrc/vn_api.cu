@@ -14,6 +14,7 @@
 #include "../../include/venusaur/Scene.h"
 #include "kernels.h"
 #include "lbvh.h"
+#include "lbvh_core.cuh"
 
 using namespace vn;
 
@@ -49,8 +50,11 @@ struct vn_context {
     uint64_t wf_sample_floats_ = 0;
 
     // options
-    uint32_t leaf_size = 2;
+    uint32_t leaf_size = 0;           // 0 = auto: 3 with SAH splits (small scenes), 2 with Karras splits
     float aabb_pad = 0.01f;
+    uint32_t wide_max_prims = 16384;  // scenes up to this size also get 4-wide nodes (k_wide_build) for the shared-memory path kernel; 0 = never
+    bool wide_nodes = true;           // use them when they fit in shared memory
+    uint32_t sah_max_prims = 4096;    // scenes up to this size get SAH splits (k_sah_small); 0 = always Karras
     int threads = 256;
     int blocks_per_sm = 0;            // 0 = occupancy
     size_t smem_scene_limit = 100 * 1024;
@@ -128,6 +132,7 @@ int fill_launch(vn_context* c, const vn_params* p, RenderLaunch& L) {
     L.root_link = c->scene.root_link;
     L.num_nodes = (uint32_t)c->scene.num_nodes;
     L.num_spheres = (uint32_t)c->scene.n;
+    L.wide = c->scene.wide; L.num_wide = c->scene.num_wide; L.wide_root = 0u;
     L.counters = c->d_counters;
     L.work_counter = reinterpret_cast<uint32_t*>(c->d_counters + 4);
     const uint32_t rows = L.row_end - L.row_begin;
@@ -223,12 +228,15 @@ void* vn_stream(vn_handle c) { return c ? (void*)c->stream : nullptr; }
 int vn_set_option(vn_handle c, const char* name, double value) {
     VN_REQUIRE(c, c && name, "vn_set_option: NULL argument");
     const std::string k(name);
-    if (k == "leaf_size") { VN_REQUIRE(c, value >= 1 && value <= 8, "leaf_size must be in [1,8]"); c->leaf_size = (uint32_t)value; c->bvh_valid = false; }
+    if (k == "leaf_size") { VN_REQUIRE(c, value >= 0 && value <= 8, "leaf_size must be in [0,8] (0 = auto)"); c->leaf_size = (uint32_t)value; c->bvh_valid = false; }
     else if (k == "aabb_pad") { VN_REQUIRE(c, value >= 0 && value < 1, "aabb_pad must be in [0,1)"); c->aabb_pad = (float)value; c->bvh_valid = false; }
     else if (k == "threads") { VN_REQUIRE(c, value == 64 || value == 128 || value == 256 || value == 512 || value == 1024, "threads must be 64, 128, 256, 512 or 1024"); c->threads = (int)value; }
     else if (k == "blocks_per_sm") { VN_REQUIRE(c, value >= 0 && value <= 32, "blocks_per_sm must be in [0,32]"); c->blocks_per_sm = (int)value; }
     else if (k == "smem_scene_limit") { VN_REQUIRE(c, value >= 0, "smem_scene_limit must be >= 0"); c->smem_scene_limit = (size_t)value; }
     else if (k == "wavefront_slots") { VN_REQUIRE(c, value >= 1024 && value <= (double)(1u << 26), "wavefront_slots out of range"); c->wavefront_slots = (uint32_t)value; free_wavefront(c->wf); c->wf_sample_floats_ = 0; }
+    else if (k == "sah_max_prims") { VN_REQUIRE(c, value >= 0 && value <= 8192, "sah_max_prims must be in [0,8192]"); c->sah_max_prims = (uint32_t)value; c->bvh_valid = false; }
+    else if (k == "wide_max_prims") { VN_REQUIRE(c, value >= 0 && value <= 65536, "wide_max_prims must be in [0,65536]"); c->wide_max_prims = (uint32_t)value; c->bvh_valid = false; }
+    else if (k == "wide_nodes") { c->wide_nodes = value != 0; }
     else if (k == "octant_nodes") { c->octant_nodes = value != 0; }
     else if (k == "pool_slots") { VN_REQUIRE(c, value >= 32 && value <= 1024, "pool_slots must be in [32,1024]"); c->pool_slots = (uint32_t)value; }
     else if (k == "pool_threads") { VN_REQUIRE(c, value >= 32 && value <= 768 && ((int)value % 32) == 0, "pool_threads must be a multiple of 32 in [32,768]"); c->pool_threads = (uint32_t)value; }
@@ -267,7 +275,8 @@ int vn_build_bvh(vn_handle c) {
     std::string err;
     uint32_t launches = 0;
     VN_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
-    const int rc = lbvh_build(c->d_spheres, c->n_spheres, c->leaf_size, c->aabb_pad, c->num_sms, c->stream, c->scene, c->bvh_ws, &launches, err);
+    const uint32_t leaf_size = c->leaf_size ? c->leaf_size : (c->n_spheres >= 2 && c->n_spheres <= c->sah_max_prims ? 3u : 2u);
+    const int rc = lbvh_build(c->d_spheres, c->n_spheres, leaf_size, c->aabb_pad, c->sah_max_prims, c->wide_max_prims, c->num_sms, c->stream, c->scene, c->bvh_ws, &launches, err);
     if (rc != 0) return fail(c, rc == -1 ? VN_ERR_INVALID : VN_ERR_CUDA, "vn_build_bvh: " + err);
     VN_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     VN_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -297,6 +306,17 @@ int vn_read_bvh(vn_handle c, vn_node32* host_nodes, uint64_t cap_nodes, uint32_t
         VN_CUDA(c, cudaMemcpy(host_nodes, c->scene.nodes, std::min<uint64_t>(cap_nodes, c->scene.num_nodes) * 32, cudaMemcpyDeviceToHost));
     if (host_prim_order && c->scene.orig)
         VN_CUDA(c, cudaMemcpy(host_prim_order, c->scene.orig, std::min<uint64_t>(cap_prims, c->scene.n) * 4, cudaMemcpyDeviceToHost));
+    return VN_OK;
+}
+
+int vn_read_wide_bvh(vn_handle c, float* host_nodes, uint64_t cap_nodes, uint32_t* num_nodes_out, uint32_t* levels_out) {
+    VN_REQUIRE(c, c, "vn_read_wide_bvh: NULL handle");
+    VN_REQUIRE(c, c->bvh_valid, "vn_read_wide_bvh: no BVH (call vn_build_bvh)");
+    VN_CUDA(c, cudaSetDevice(c->device));
+    if (num_nodes_out) *num_nodes_out = c->scene.num_wide;
+    if (levels_out) *levels_out = c->scene.wide_levels;
+    if (host_nodes && c->scene.wide && c->scene.num_wide)
+        VN_CUDA(c, cudaMemcpy(host_nodes, c->scene.wide, std::min<uint64_t>(cap_nodes, c->scene.num_wide) * 128, cudaMemcpyDeviceToHost));
     return VN_OK;
 }
 
@@ -502,12 +522,16 @@ int vn_render(vn_handle c, const vn_params* p) {
         // 8 octant-specialised copies of the nodes when they fit beside the spheres: one 1024-thread CTA per SM shares them
         const size_t oct_bytes = scene_smem_bytes(L.num_nodes, L.num_spheres, 8);
         cfg.octant = cfg.scene_in_smem && c->octant_nodes && oct_bytes + 2048 <= c->smem_optin;
-        if (cfg.octant) { cfg.smem_bytes = oct_bytes; cfg.threads = 1024; }
+        // preferred: 4-wide nodes, octant-sorted, 8 copies in shared memory (half the traversal steps, no distance compare)
+        const size_t wide_bytes = wide_smem_bytes(L.num_wide, L.num_spheres);
+        cfg.wide = c->wide_nodes && L.wide && L.num_wide > 0 && c->scene.wide_levels <= kWideMaxLevels && wide_bytes + 2048 <= c->smem_optin;
+        if (cfg.wide) { cfg.scene_in_smem = true; cfg.octant = false; cfg.smem_bytes = wide_bytes; cfg.threads = 1024; }
+        else if (cfg.octant) { cfg.smem_bytes = oct_bytes; cfg.threads = 1024; }
         else if (cfg.threads > 256) cfg.threads = 256;
-        int per_sm = cfg.octant ? 1 : c->blocks_per_sm;
+        int per_sm = (cfg.octant || cfg.wide) ? 1 : c->blocks_per_sm;
         if (per_sm <= 0) {
-            per_sm = exact_build ? exact::max_blocks_per_sm(cfg.threads, cfg.smem_bytes, cfg.scene_in_smem, count, cfg.octant)
-                                 : fast::max_blocks_per_sm(cfg.threads, cfg.smem_bytes, cfg.scene_in_smem, count, cfg.octant);
+            per_sm = exact_build ? exact::max_blocks_per_sm(cfg.threads, cfg.smem_bytes, cfg.scene_in_smem, count, cfg.octant, cfg.wide)
+                                 : fast::max_blocks_per_sm(cfg.threads, cfg.smem_bytes, cfg.scene_in_smem, count, cfg.octant, cfg.wide);
             if (per_sm <= 0) return fail(c, VN_ERR_CUDA, "vn_render: occupancy query failed for the path kernel");
         }
         cfg.blocks = c->num_sms * per_sm;

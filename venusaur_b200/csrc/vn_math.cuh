@@ -399,6 +399,62 @@ VN_HD void closest_hit(const node_f4* __restrict__ nodes, const node_f4* __restr
     prim_out = prim;
 }
 
+// Closest hit over the 4-wide, octant-specialised shared-memory nodes (lbvh_core.cuh::wide_octant_node): one step
+// = 7 x 128-bit loads + four slab tests; hit children are pushed far to near in the octant's static order, so the
+// step has no distance compare.  Same leaves, same sphere_root() as closest_hit(): the result is identical.
+constexpr uint32_t kWideNodeF4 = 7;
+VN_HD bool slab_hit(float nx, float ny, float nz, float fx, float fy, float fz, f3 idir, f3 ood, float tbest) {
+    const float tn = fmaxf(fmaxf(fmaf(nx, idir.x, -ood.x), fmaf(ny, idir.y, -ood.y)), fmaxf(fmaf(nz, idir.z, -ood.z), 0.0f));
+    const float tf = fminf(fminf(fmaf(fx, idir.x, -ood.x), fmaf(fy, idir.y, -ood.y)), fminf(fmaf(fz, idir.z, -ood.z), tbest));
+    return tn <= tf;
+}
+template <bool kCount>
+VN_HD void closest_hit_wide(const node_f4* __restrict__ wnodes, uint32_t oct_stride, const node_f4* __restrict__ geom, uint32_t root_link,
+                            f3 o, f3 d, float& t_out, int& prim_out, TraceCounters& cnt) {
+    float tbest = kTMax;
+    int prim = -1;
+    {
+        const f3 idir = slab_idir(d);
+        const node_f4* __restrict__ wn = wnodes + ray_octant(d) * oct_stride;
+        const f3 ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
+        const float a = dot(d, d);
+        const float inv_a = rcp(a);
+        uint32_t stack[kStackSize];
+        int sp = 0;
+        uint32_t cur = root_link;
+        for (;;) {
+            while (!(cur & kLeafFlag)) {
+                const node_f4* __restrict__ p = wn + kWideNodeF4 * cur;
+                const node_f4 nx = p[0], ny = p[1], nz = p[2], fx = p[3], fy = p[4], fz = p[5], lk = p[6];
+                if (kCount) cnt.nodes += 1;
+                const bool h0 = slab_hit(nx.x, ny.x, nz.x, fx.x, fy.x, fz.x, idir, ood, tbest);
+                const bool h1 = slab_hit(nx.y, ny.y, nz.y, fx.y, fy.y, fz.y, idir, ood, tbest);
+                const bool h2 = slab_hit(nx.z, ny.z, nz.z, fx.z, fy.z, fz.z, idir, ood, tbest);
+                const bool h3 = slab_hit(nx.w, ny.w, nz.w, fx.w, fy.w, fz.w, idir, ood, tbest);
+                // the nearest hit child (static octant order) becomes the current node straight from registers; the
+                // others are pushed far to near.  Only a step without any hit pays the stack load.
+                if (h3 && (h0 || h1 || h2)) stack[sp++] = f2u(lk.w);
+                if (h2 && (h0 || h1)) stack[sp++] = f2u(lk.z);
+                if (h1 && h0) stack[sp++] = f2u(lk.y);
+                cur = h0 ? f2u(lk.x) : (h1 ? f2u(lk.y) : (h2 ? f2u(lk.z) : f2u(lk.w)));
+                if (!(h0 || h1 || h2 || h3)) cur = sp ? stack[--sp] : kEmptyScene;
+            }
+            if (cur == kEmptyScene) break;
+            const uint32_t first = (cur & 0x7FFFFFFFu) >> 3;
+            const uint32_t count = (cur & 7u) + 1u;
+            for (uint32_t k = 0; k < count; k++) {
+                const node_f4 g = geom[first + k];
+                if (kCount) cnt.spheres += 1;
+                const float t = sphere_root(o, d, a, inv_a, g.x, g.y, g.z, g.w, kTMin, tbest);
+                if (t >= 0.0f) { tbest = t; prim = (int)(first + k); }
+            }
+            cur = sp ? stack[--sp] : kEmptyScene;
+        }
+    }
+    t_out = tbest;
+    prim_out = prim;
+}
+
 // ---- one full path, iterative: the recursion of RayTracer.cu:190-202 -> closest-hit -> optixTrace -> ... -> miss.
 // The albedo product is accumulated forward (throughput), the reference multiplies on recursion unwind
 // (RayTracer.cu:313,360): same factors, different association (<= depth * 2^-24 relative).
