@@ -155,7 +155,7 @@ def run_ours(args):
     import torch
     import venusaur_b200 as vb
     from venusaur_b200 import sharding
-    from venusaur_b200 import VN_ACCUM_SUM, VN_ASYNC, VN_COUNTERS, VN_FAST, VN_IMAGE_HOST, VN_NO_TONEMAP, VN_POOL, VN_WAVEFRONT
+    from venusaur_b200 import VN_ACCUM_SUM, VN_ASYNC, VN_COUNTERS, VN_FAST, VN_IMAGE_HOST, VN_NO_TONEMAP, VN_POOL, VN_SLOTS, VN_WAVEFRONT
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -193,7 +193,7 @@ def run_ours(args):
         cam = vb.Camera((0.0, 0.0, 200.0), 40.0, width / height, 0.0, 200.0)
         cam.SetForward((0.0, 0.0, -1.0))
     ctx.resize(width, height)
-    kflag = {"wavefront": VN_WAVEFRONT, "pool": VN_POOL, "persistent": 0}[args.kernel] | (VN_FAST if args.fast else 0)
+    kflag = {"wavefront": VN_WAVEFRONT, "pool": VN_POOL, "persistent": 0, "slots": VN_SLOTS}[args.kernel] | (VN_FAST if args.fast else 0)
     for opt in ("pool_slots", "pool_threads", "pool_service", "pool_leaf_batch"):
         if getattr(args, opt):
             ctx.set_option(opt, getattr(args, opt))
@@ -253,8 +253,9 @@ def run_ours(args):
                 ctx.tonemap(scale, image.data_ptr(), 0)
 
     # ---- instrumented pass (untimed): V_node / V_sphere per segment for the roofline model
-    ctx.render(ctx.make_params(cam, width, height, spp, 1, depth, flags=VN_COUNTERS | VN_NO_TONEMAP | (VN_FAST if args.fast else 0)))
+    ctx.render(ctx.make_params(cam, width, height, spp, 1, depth, flags=VN_COUNTERS | VN_NO_TONEMAP | (VN_FAST if args.fast else 0) | (VN_SLOTS if args.kernel == "slots" else 0)))
     cst = ctx.stats()
+    sched = ctx.sched_counters() if args.kernel == "slots" else None
     v_node = cst.node_visits / max(1, cst.segments)
     v_sphere = cst.sphere_tests / max(1, cst.segments)
 
@@ -367,7 +368,8 @@ def run_ours(args):
             "config": {"workload": describe(args.workload, K), "parallelism": "subframe(sample-range) sharding x%d, scene+BVH replicated" % world,
                        "kernel": args.kernel, "build": ("VN_FAST (relaxed numerics; not within the image tolerance)" if args.fast else "default IEEE build, bit-identical to the oracle"), "l2_flush": "256 MiB fill between timed steps",
                        "scene_in_smem": bool(info.scene_in_smem), "bvh_nodes": int(info.num_nodes), "leaf_size": int(info.max_leaf_size),
-                       "bvh_build_ms": build_ms, "reduce": (args.reduce if world > 1 else "none"), "reduce_ms": fin_ms},
+                       "bvh_build_ms": build_ms, "reduce": (args.reduce if world > 1 else "none"), "reduce_ms": fin_ms,
+                       "sched": ({k: [v[0], round(v[1], 2)] for k, v in sched.items()} if sched else None)},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": C.sizeof(vb._lib.vn_params),
                     "d2h_bytes_per_step": (width * height * 4 if world == 1 else width * height * 4 // max(1, K)),
@@ -403,7 +405,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--kernel", default="persistent", choices=["persistent", "wavefront", "pool"])
+    ap.add_argument("--kernel", default="persistent", choices=["persistent", "wavefront", "pool", "slots"])
     for opt in ("pool-slots", "pool-threads", "pool-service", "pool-leaf-batch"):
         ap.add_argument("--" + opt, type=int, default=0)
     ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"])

@@ -63,6 +63,9 @@ enum {
     VN_COUNTERS       = 1u << 5, /* instrumented launch: also count BVH node visits and sphere tests */
     VN_ASYNC          = 1u << 6, /* do not synchronise the stream before returning (stats are then stale) */
     VN_POOL           = 1u << 8, /* use the shared-memory warp-pool wavefront kernel (pool_kernels.cu) */
+    VN_SLOTS          = 1u << 9, /* use the slot-scheduled path kernel (slot_kernels.cu) when the scene qualifies (4-wide nodes in
+                                    shared memory); otherwise the persistent kernel runs */
+    VN_PERSISTENT     = 1u << 10, /* force k_render_persistent even when the "slot_kernel" option makes the slot kernel the default */
     VN_FAST           = 1u << 7  /* relaxed-numerics build (FMA contraction, approximate rcp/rsqrt/sqrt, FP32 for the FP64
                                     fragments): a few % faster, PSNR > 60 dB vs the oracle but NOT within the 1e-3 per-pixel
                                     tolerance at 1024 spp (individual paths diverge); never the default */
@@ -142,6 +145,9 @@ VN_API int vn_tonemap(vn_handle h, float scale, void* image, uint32_t flags); /*
 VN_API int vn_synchronize(vn_handle h);                               /* CUDA_SYNC_CHECK, Renderer.h:77 */
 VN_API int vn_get_stats(vn_handle h, vn_stats* out);
 VN_API int vn_reset_stats(vn_handle h);
+/* Scheduler statistics of the last VN_SLOTS | VN_COUNTERS launch: for each warp-wide operation (node step, leaf, retire+fetch,
+ * shade opaque, shade dielectric, shade miss, camera ray) the number of times it ran and the lanes that took part. */
+VN_API int vn_read_sched_counters(vn_handle h, uint64_t* out14);
 
 /* ---- accumulation buffer: Params::accum (RayTracer.h:6), float4 per pixel ---- */
 VN_API int vn_read_accum(vn_handle h, float* host_rgba);              /* D2H, width*height*4 floats */

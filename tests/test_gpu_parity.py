@@ -12,7 +12,8 @@ import numpy as np
 import pytest
 
 import venusaur_b200 as vb
-from venusaur_b200 import VN_ACCUM_SUM, VN_COUNTERS, VN_EXACT, VN_FAST, VN_IMAGE_HOST, VN_NO_TONEMAP, VN_POOL, VN_WAVEFRONT
+from venusaur_b200 import (VN_ACCUM_SUM, VN_COUNTERS, VN_EXACT, VN_FAST, VN_IMAGE_HOST, VN_NO_TONEMAP, VN_PERSISTENT, VN_POOL, VN_SLOTS,
+                           VN_WAVEFRONT)
 
 pytestmark = pytest.mark.gpu
 
@@ -320,6 +321,43 @@ def test_octant_and_plain_persistent_kernels_agree(rtiow_ctx):
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(ia, ib)
     assert np.array_equal(a.view(np.uint32), c.view(np.uint32)) and np.array_equal(a.view(np.uint32), d.view(np.uint32))
     assert sc.node_visits == sd.node_visits and sc.sphere_tests == sd.sphere_tests
+
+
+@pytest.mark.parametrize("slots,threads", [(3, 768), (2, 1024), (4, 512), (2, 768), (3, 512), (4, 384)])
+def test_slot_kernel_equals_persistent_kernel(rtiow_ctx, slots, threads):
+    """The slot-scheduled kernel (K path slots per lane, warp-voted node / leaf / retire / shade-by-material / camera
+    operations) is another schedule of the same math: bit-identical accumulation buffer and image, same segment and
+    path counts, for every slot geometry, for extreme vote thresholds, with a running-mean blend and on a row range."""
+    W, H, spp, depth = 200, 120, 6, 50
+    cam = vb.rtiow_camera(W, H)
+    a, ia, sa = render(rtiow_ctx, cam, W, H, spp, 2, depth, flags=VN_PERSISTENT)
+    c, ic, sc = render(rtiow_ctx, cam, W, H, spp, 3, depth, flags=VN_PERSISTENT, accum_count=1)
+    try:
+        rtiow_ctx.set_option("slot_slots", slots)
+        rtiow_ctx.set_option("slot_threads", threads)
+        b, ib, sb = render(rtiow_ctx, cam, W, H, spp, 2, depth, flags=VN_SLOTS)
+        assert rtiow_ctx.stats().kernel_launches == 2
+        assert sa.segments == sb.segments and sa.paths == sb.paths
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(ia, ib)
+        d, idd, sd = render(rtiow_ctx, cam, W, H, spp, 3, depth, flags=VN_SLOTS | VN_COUNTERS, accum_count=1)   # lerp onto frame 2
+        assert np.array_equal(c.view(np.uint32), d.view(np.uint32)) and np.array_equal(ic, idd) and sc.segments == sd.segments
+        sched = rtiow_ctx.sched_counters()
+        assert sched["node"][0] > 0 and sched["node"][1] > 12.0 and sched["shade_opaque"][1] > 12.0
+        assert sd.node_visits == sched["node"][0] * sched["node"][1] or abs(sd.node_visits - sched["node"][0] * sched["node"][1]) < 1e-6 * sd.node_visits
+        for tn, tl, tw, ts, tr in [(1, 1, 1, 1, 1), (33, 33, 33, 33, 33), (32, 2, 30, 5, 9)]:
+            for k, v in zip(("slot_tn", "slot_tl", "slot_tw", "slot_ts", "slot_tr"), (tn, tl, tw, ts, tr)):
+                rtiow_ctx.set_option(k, v)
+            e, ie, se = render(rtiow_ctx, cam, W, H, spp, 2, depth, flags=VN_SLOTS)
+            assert se.segments == sa.segments and np.array_equal(a.view(np.uint32), e.view(np.uint32)) and np.array_equal(ia, ie)
+        # a row range of a ragged frame (tiles hang over the right and bottom edges)
+        W2, H2 = 203, 117
+        cam2 = vb.rtiow_camera(W2, H2)
+        f, iff, sf = render(rtiow_ctx, cam2, W2, H2, 5, 4, 12, flags=VN_PERSISTENT, rows=(30, 77))
+        g, ig, sg = render(rtiow_ctx, cam2, W2, H2, 5, 4, 12, flags=VN_SLOTS, rows=(30, 77))
+        assert sf.segments == sg.segments and np.array_equal(f.view(np.uint32)[30:77], g.view(np.uint32)[30:77]) and np.array_equal(iff[30:77], ig[30:77])
+    finally:
+        for k, v in (("slot_slots", 3), ("slot_threads", 768), ("slot_tn", 20), ("slot_tl", 12), ("slot_tw", 8), ("slot_ts", 20), ("slot_tr", 20)):
+            rtiow_ctx.set_option(k, v)
 
 
 def test_wavefront_equals_persistent_kernel(rtiow_ctx, oracle_mod, rtiow):

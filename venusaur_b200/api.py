@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib as L
-from ._lib import (VN_ACCUM_SUM, VN_ASYNC, VN_COUNTERS, VN_DIELECTRIC, VN_EXACT, VN_FAST, VN_IMAGE_HOST, VN_POOL, VN_LAMBERTIAN,  # noqa: F401
+from ._lib import (VN_ACCUM_SUM, VN_ASYNC, VN_COUNTERS, VN_DIELECTRIC, VN_EXACT, VN_FAST, VN_IMAGE_HOST, VN_POOL, VN_SLOTS, VN_PERSISTENT, VN_LAMBERTIAN,  # noqa: F401
                    VN_METAL, VN_NO_TONEMAP, VN_WAVEFRONT, vn_bvh_info, vn_node32, vn_params, vn_sphere, vn_stats)
 
 SPHERE_DTYPE = np.dtype([("cx", "f4"), ("cy", "f4"), ("cz", "f4"), ("r", "f4"), ("ax", "f4"), ("ay", "f4"),
@@ -212,6 +212,13 @@ class Context:
 
     def synchronize(self):
         self._check(self.lib.vn_synchronize(self.h), "vn_synchronize")
+
+    def sched_counters(self) -> dict:
+        """Per warp-wide operation of the slot kernel: (times it ran, mean lanes taking part); needs VN_SLOTS | VN_COUNTERS."""
+        raw = (C.c_uint64 * 14)()
+        self._check(self.lib.vn_read_sched_counters(self.h, raw), "vn_read_sched_counters")
+        names = ["node", "leaf", "retire_fetch", "shade_opaque", "shade_dielectric", "shade_miss", "camera"]
+        return {n: (int(raw[2 * i]), (raw[2 * i + 1] / raw[2 * i]) if raw[2 * i] else 0.0) for i, n in enumerate(names)}
 
     def stats(self) -> vn_stats:
         s = vn_stats()

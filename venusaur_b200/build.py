@@ -33,6 +33,8 @@ UNITS = [
     ("wavefront.cu", "wavefront_fast.o", ["-DVN_EXACT=0", "-fmad=true", "-ftz=true"]),
     ("pool_kernels.cu", "pool_exact.o", ["-DVN_EXACT=1", "-fmad=false"]),
     ("pool_kernels.cu", "pool_fast.o", ["-DVN_EXACT=0", "-fmad=true", "-ftz=true"]),
+    ("slot_kernels.cu", "slot_exact.o", ["-DVN_EXACT=1", "-fmad=false"]),
+    ("slot_kernels.cu", "slot_fast.o", ["-DVN_EXACT=0", "-fmad=true", "-ftz=true"]),
 ]
 
 

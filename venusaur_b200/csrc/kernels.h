@@ -46,6 +46,9 @@ struct KernelConfig {
     bool wide;                       // 4-wide octant-sorted nodes in shared memory (implies scene_in_smem; excludes octant)
 };
 
+// Vote thresholds of the slot-scheduled kernel (slot_kernels.cu): an operation runs when that many lanes wait for it.
+struct SlotTune { uint32_t node_threshold, leaf_threshold, switch_threshold, shade_threshold, regen_threshold; };
+
 size_t scene_smem_bytes(uint32_t num_nodes, uint32_t num_spheres, uint32_t node_copies = 1);
 size_t wide_smem_bytes(uint32_t num_wide, uint32_t num_spheres);
 
@@ -93,6 +96,11 @@ constexpr int kWfArraysTotal = 2 * kWfStateArrays + 2 + 4;   // 4-byte arrays of
                                uint8_t* scattered, uint32_t* seeds_out, cudaStream_t stream);                          \
     cudaError_t launch_wavefront(const RenderLaunch& p, const WavefrontBuffers& wf, int num_sms, cudaStream_t stream,   \
                                  uint32_t* launches);                                                                  \
+    cudaError_t launch_accumulate_samples(const RenderLaunch& p, const float* sample_rgb, cudaStream_t stream);                \
+    size_t slot_smem_bytes(uint32_t num_wide, uint32_t num_spheres, int slots, int threads);                               \
+    bool slot_config_supported(int slots, int threads);                                                                    \
+    cudaError_t launch_render_slots(const RenderLaunch& p, float* sample_rgb, int slots, int threads, int blocks,           \
+                                    const SlotTune& tune, bool count, cudaStream_t stream);                                \
     size_t pool_smem_bytes(uint32_t num_nodes, uint32_t num_spheres, bool scene_in_smem, int warps, uint32_t slots);    \
     int pool_max_blocks_per_sm(bool scene_in_smem, int threads, size_t smem);                                          \
     cudaError_t launch_render_pool(const RenderLaunch& p, bool scene_in_smem, int threads, int blocks, uint32_t slots,  \

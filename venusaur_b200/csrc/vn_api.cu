@@ -43,7 +43,7 @@ struct vn_context {
     uint32_t* image_tmp = nullptr;    // device staging for VN_IMAGE_HOST
     uint64_t image_tmp_pixels = 0;
 
-    unsigned long long* d_counters = nullptr;   // 4 x u64 + work ticket (u32) at +32 bytes
+    unsigned long long* d_counters = nullptr;   // 4 x u64 + work ticket (u32) at +32 bytes; [8..22) scheduler statistics of the slot kernel
     unsigned long long* h_counters = nullptr;   // pinned
 
     WavefrontBuffers wf;
@@ -53,6 +53,9 @@ struct vn_context {
     uint32_t leaf_size = 0;           // 0 = auto: 3 with SAH splits (small scenes), 2 with Karras splits
     float aabb_pad = 0.01f;
     uint32_t wide_max_prims = 16384;  // scenes up to this size also get 4-wide nodes (k_wide_build) for the shared-memory path kernel; 0 = never
+    bool slot_kernel = false;         // default path kernel for wide-node scenes: slot-scheduled (slot_kernels.cu) instead of k_render_persistent
+    int slot_slots = 3, slot_threads = 768;
+    SlotTune slot_tune{20u, 12u, 8u, 20u, 20u};
     bool wide_nodes = true;           // use them when they fit in shared memory
     uint32_t sah_max_prims = 4096;    // scenes up to this size get SAH splits (k_sah_small); 0 = always Karras
     int threads = 256;
@@ -202,9 +205,9 @@ int vn_create(int device, vn_handle* out) {
     c->smem_optin = prop.sharedMemPerBlockOptin;
     VN_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto& ev : c->ev) VN_CUDA(c, cudaEventCreate(&ev));
-    VN_CUDA(c, cudaMalloc(&c->d_counters, 64));
-    VN_CUDA(c, cudaMemset(c->d_counters, 0, 64));
-    VN_CUDA(c, cudaHostAlloc(&c->h_counters, 64, cudaHostAllocDefault));
+    VN_CUDA(c, cudaMalloc(&c->d_counters, 256));
+    VN_CUDA(c, cudaMemset(c->d_counters, 0, 256));
+    VN_CUDA(c, cudaHostAlloc(&c->h_counters, 256, cudaHostAllocDefault));
     *out = c;
     return VN_OK;
 }
@@ -237,6 +240,18 @@ int vn_set_option(vn_handle c, const char* name, double value) {
     else if (k == "sah_max_prims") { VN_REQUIRE(c, value >= 0 && value <= 8192, "sah_max_prims must be in [0,8192]"); c->sah_max_prims = (uint32_t)value; c->bvh_valid = false; }
     else if (k == "wide_max_prims") { VN_REQUIRE(c, value >= 0 && value <= 65536, "wide_max_prims must be in [0,65536]"); c->wide_max_prims = (uint32_t)value; c->bvh_valid = false; }
     else if (k == "wide_nodes") { c->wide_nodes = value != 0; }
+    else if (k == "slot_kernel") { c->slot_kernel = value != 0; }
+    else if (k == "slot_slots" || k == "slot_threads") {
+        const int slots = k == "slot_slots" ? (int)value : c->slot_slots, threads = k == "slot_threads" ? (int)value : c->slot_threads;
+        (k == "slot_slots" ? c->slot_slots : c->slot_threads) = (int)value;   // validated as a pair at launch
+        (void)slots; (void)threads;
+    }
+    else if (k == "slot_tn" || k == "slot_tl" || k == "slot_tw" || k == "slot_ts" || k == "slot_tr") {
+        VN_REQUIRE(c, value >= 1 && value <= 33, "slot thresholds must be in [1,33]");
+        uint32_t& t = k == "slot_tn" ? c->slot_tune.node_threshold : k == "slot_tl" ? c->slot_tune.leaf_threshold : k == "slot_tw" ? c->slot_tune.switch_threshold
+                      : k == "slot_ts" ? c->slot_tune.shade_threshold : c->slot_tune.regen_threshold;
+        t = (uint32_t)value;
+    }
     else if (k == "octant_nodes") { c->octant_nodes = value != 0; }
     else if (k == "pool_slots") { VN_REQUIRE(c, value >= 32 && value <= 1024, "pool_slots must be in [32,1024]"); c->pool_slots = (uint32_t)value; }
     else if (k == "pool_threads") { VN_REQUIRE(c, value >= 32 && value <= 768 && ((int)value % 32) == 0, "pool_threads must be a multiple of 32 in [32,768]"); c->pool_threads = (uint32_t)value; }
@@ -306,6 +321,13 @@ int vn_read_bvh(vn_handle c, vn_node32* host_nodes, uint64_t cap_nodes, uint32_t
         VN_CUDA(c, cudaMemcpy(host_nodes, c->scene.nodes, std::min<uint64_t>(cap_nodes, c->scene.num_nodes) * 32, cudaMemcpyDeviceToHost));
     if (host_prim_order && c->scene.orig)
         VN_CUDA(c, cudaMemcpy(host_prim_order, c->scene.orig, std::min<uint64_t>(cap_prims, c->scene.n) * 4, cudaMemcpyDeviceToHost));
+    return VN_OK;
+}
+
+int vn_read_sched_counters(vn_handle c, uint64_t* out14) {
+    VN_REQUIRE(c, c && out14, "vn_read_sched_counters: NULL argument");
+    if (c->stats_pending) { const int rc = vn_synchronize(c); if (rc != VN_OK) return rc; }
+    for (int i = 0; i < 14; i++) out14[i] = c->h_counters[8 + i];
     return VN_OK;
 }
 
@@ -418,6 +440,20 @@ static int ensure_image_tmp(vn_context* c, uint64_t pixels) {
     return VN_OK;
 }
 
+// per-(pixel, sample) radiance of one launch, summed in sample order by the accumulate kernel
+static int ensure_sample_buffer(vn_context* c, uint64_t pixels, uint32_t spp) {
+    WavefrontBuffers& w = c->wf;
+    const uint64_t need = pixels * spp * 3ull;
+    if (need > c->wf_sample_floats_) {
+        cudaFree(w.sample_rgb);
+        w.sample_rgb = nullptr;
+        c->wf_sample_floats_ = 0;
+        VN_CUDA(c, cudaMalloc(&w.sample_rgb, need * 4ull));
+        c->wf_sample_floats_ = need;
+    }
+    return VN_OK;
+}
+
 static int ensure_wavefront(vn_context* c, uint64_t pixels, uint32_t spp) {
     WavefrontBuffers& w = c->wf;
     const uint32_t cap = c->wavefront_slots;
@@ -441,16 +477,16 @@ static int ensure_wavefront(vn_context* c, uint64_t pixels, uint32_t spp) {
         VN_CUDA(c, cudaMalloc(&w.counts, 4 * kWfCountWords));
         w.capacity = cap;
     }
-    // per-(pixel, sample) radiance of one launch, summed in sample order by the accumulate kernel
-    const uint64_t need = pixels * spp * 3ull;
-    if (need > c->wf_sample_floats_) {
-        cudaFree(w.sample_rgb);
-        w.sample_rgb = nullptr;
-        c->wf_sample_floats_ = 0;
-        VN_CUDA(c, cudaMalloc(&w.sample_rgb, need * 4ull));
-        c->wf_sample_floats_ = need;
-    }
-    return VN_OK;
+    return ensure_sample_buffer(c, pixels, spp);
+}
+
+// The slot kernel needs the 4-wide nodes in shared memory next to its slots, and sample / depth counters that fit 16 bits.
+static bool use_slot_kernel(const vn_context* c, const vn_params* p, const RenderLaunch& L) {
+    if (!((p->flags & VN_SLOTS) || c->slot_kernel) || (p->flags & VN_PERSISTENT)) return false;
+    if (!c->wide_nodes || !L.wide || L.num_wide == 0 || c->scene.wide_levels > kWideMaxLevels) return false;
+    if (p->samples_per_pixel > 65535u || p->max_depth > 65535u) return false;
+    if (!exact::slot_config_supported(c->slot_slots, c->slot_threads)) return false;
+    return exact::slot_smem_bytes(L.num_wide, L.num_spheres, c->slot_slots, c->slot_threads) + 1024 <= c->smem_optin;
 }
 
 int vn_render(vn_handle c, const vn_params* p) {
@@ -479,7 +515,7 @@ int vn_render(vn_handle c, const vn_params* p) {
     uint32_t launches = 0;
 
     if (c->stats_pending) { const int rc = vn_synchronize(c); if (rc != VN_OK) return rc; }
-    VN_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 64, c->stream));
+    VN_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 256, c->stream));
     VN_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
     if (p->flags & VN_WAVEFRONT) {
         const uint32_t rows = L.row_end - L.row_begin;
@@ -513,6 +549,18 @@ int vn_render(vn_handle c, const vn_params* p) {
                                    : fast::launch_tonemap(L.accum + begin, 1.0f, L.image + begin, npx, c->stream));
             launches += 1;
         }
+    } else if (use_slot_kernel(c, p, L)) {
+        // slot-scheduled path kernel over the 4-wide nodes (K path slots per lane, warp-voted operations)
+        const uint32_t rows = L.row_end - L.row_begin;
+        const int rc = ensure_sample_buffer(c, (uint64_t)p->width * rows, p->samples_per_pixel);
+        if (rc != VN_OK) return rc;
+        int blocks = c->num_sms;
+        const uint64_t max_blocks = ((uint64_t)L.total_work + c->slot_threads - 1) / c->slot_threads;
+        if ((uint64_t)blocks > max_blocks) blocks = (int)std::max<uint64_t>(1, max_blocks);
+        VN_CUDA(c, exact_build ? exact::launch_render_slots(L, c->wf.sample_rgb, c->slot_slots, c->slot_threads, blocks, c->slot_tune, count, c->stream)
+                               : fast::launch_render_slots(L, c->wf.sample_rgb, c->slot_slots, c->slot_threads, blocks, c->slot_tune, count, c->stream));
+        VN_CUDA(c, exact_build ? exact::launch_accumulate_samples(L, c->wf.sample_rgb, c->stream) : fast::launch_accumulate_samples(L, c->wf.sample_rgb, c->stream));
+        launches += 2;
     } else {
         KernelConfig cfg;
         cfg.threads = c->threads;
@@ -550,7 +598,7 @@ int vn_render(vn_handle c, const vn_params* p) {
     }
     VN_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     if (host_image) VN_CUDA(c, cudaMemcpyAsync(p->image, c->image_tmp, pixels * 4, cudaMemcpyDeviceToHost, c->stream));
-    VN_CUDA(c, cudaMemcpyAsync(c->h_counters, c->d_counters, 32, cudaMemcpyDeviceToHost, c->stream));
+    VN_CUDA(c, cudaMemcpyAsync(c->h_counters, c->d_counters, 256, cudaMemcpyDeviceToHost, c->stream));
     c->stats.kernel_launches = launches;
     c->stats.kernel_launches_total += launches;
     c->stats_pending = true;

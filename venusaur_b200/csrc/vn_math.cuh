@@ -408,6 +408,37 @@ VN_HD bool slab_hit(float nx, float ny, float nz, float fx, float fy, float fz, 
     const float tf = fminf(fminf(fmaf(fx, idir.x, -ood.x), fmaf(fy, idir.y, -ood.y)), fminf(fmaf(fz, idir.z, -ood.z), tbest));
     return tn <= tf;
 }
+// One step over a 4-wide node: returns the next node / leaf link (kEmptyScene when the ray is finished).
+VN_HD uint32_t wide_node_step(const node_f4* __restrict__ wn, uint32_t cur, f3 idir, f3 ood, float tbest, uint32_t* stack, int& sp) {
+    const node_f4* __restrict__ p = wn + kWideNodeF4 * cur;
+    const node_f4 nx = p[0], ny = p[1], nz = p[2], fx = p[3], fy = p[4], fz = p[5], lk = p[6];
+    const bool h0 = slab_hit(nx.x, ny.x, nz.x, fx.x, fy.x, fz.x, idir, ood, tbest);
+    const bool h1 = slab_hit(nx.y, ny.y, nz.y, fx.y, fy.y, fz.y, idir, ood, tbest);
+    const bool h2 = slab_hit(nx.z, ny.z, nz.z, fx.z, fy.z, fz.z, idir, ood, tbest);
+    const bool h3 = slab_hit(nx.w, ny.w, nz.w, fx.w, fy.w, fz.w, idir, ood, tbest);
+    // the nearest hit child (static octant order) becomes the current node straight from registers; the others are
+    // pushed far to near.  Only a step without any hit pays the stack load.
+    if (h3 && (h0 || h1 || h2)) stack[sp++] = f2u(lk.w);
+    if (h2 && (h0 || h1)) stack[sp++] = f2u(lk.z);
+    if (h1 && h0) stack[sp++] = f2u(lk.y);
+    uint32_t next = h0 ? f2u(lk.x) : (h1 ? f2u(lk.y) : (h2 ? f2u(lk.z) : f2u(lk.w)));
+    if (!(h0 || h1 || h2 || h3)) next = sp ? stack[--sp] : kEmptyScene;
+    return next;
+}
+// One leaf: the reference's ray/sphere test on its (<= 8) spheres; returns the next link.
+template <bool kCount>
+VN_HD uint32_t leaf_step(const node_f4* __restrict__ geom, uint32_t cur, f3 o, f3 d, float a, float inv_a, float& tbest, int& prim,
+                         uint32_t* stack, int& sp, TraceCounters& cnt) {
+    const uint32_t first = (cur & 0x7FFFFFFFu) >> 3;
+    const uint32_t count = (cur & 7u) + 1u;
+    for (uint32_t k = 0; k < count; k++) {
+        const node_f4 g = geom[first + k];
+        if (kCount) cnt.spheres += 1;
+        const float t = sphere_root(o, d, a, inv_a, g.x, g.y, g.z, g.w, kTMin, tbest);
+        if (t >= 0.0f) { tbest = t; prim = (int)(first + k); }
+    }
+    return sp ? stack[--sp] : kEmptyScene;
+}
 template <bool kCount>
 VN_HD void closest_hit_wide(const node_f4* __restrict__ wnodes, uint32_t oct_stride, const node_f4* __restrict__ geom, uint32_t root_link,
                             f3 o, f3 d, float& t_out, int& prim_out, TraceCounters& cnt) {
@@ -424,31 +455,11 @@ VN_HD void closest_hit_wide(const node_f4* __restrict__ wnodes, uint32_t oct_str
         uint32_t cur = root_link;
         for (;;) {
             while (!(cur & kLeafFlag)) {
-                const node_f4* __restrict__ p = wn + kWideNodeF4 * cur;
-                const node_f4 nx = p[0], ny = p[1], nz = p[2], fx = p[3], fy = p[4], fz = p[5], lk = p[6];
                 if (kCount) cnt.nodes += 1;
-                const bool h0 = slab_hit(nx.x, ny.x, nz.x, fx.x, fy.x, fz.x, idir, ood, tbest);
-                const bool h1 = slab_hit(nx.y, ny.y, nz.y, fx.y, fy.y, fz.y, idir, ood, tbest);
-                const bool h2 = slab_hit(nx.z, ny.z, nz.z, fx.z, fy.z, fz.z, idir, ood, tbest);
-                const bool h3 = slab_hit(nx.w, ny.w, nz.w, fx.w, fy.w, fz.w, idir, ood, tbest);
-                // the nearest hit child (static octant order) becomes the current node straight from registers; the
-                // others are pushed far to near.  Only a step without any hit pays the stack load.
-                if (h3 && (h0 || h1 || h2)) stack[sp++] = f2u(lk.w);
-                if (h2 && (h0 || h1)) stack[sp++] = f2u(lk.z);
-                if (h1 && h0) stack[sp++] = f2u(lk.y);
-                cur = h0 ? f2u(lk.x) : (h1 ? f2u(lk.y) : (h2 ? f2u(lk.z) : f2u(lk.w)));
-                if (!(h0 || h1 || h2 || h3)) cur = sp ? stack[--sp] : kEmptyScene;
+                cur = wide_node_step(wn, cur, idir, ood, tbest, stack, sp);
             }
             if (cur == kEmptyScene) break;
-            const uint32_t first = (cur & 0x7FFFFFFFu) >> 3;
-            const uint32_t count = (cur & 7u) + 1u;
-            for (uint32_t k = 0; k < count; k++) {
-                const node_f4 g = geom[first + k];
-                if (kCount) cnt.spheres += 1;
-                const float t = sphere_root(o, d, a, inv_a, g.x, g.y, g.z, g.w, kTMin, tbest);
-                if (t >= 0.0f) { tbest = t; prim = (int)(first + k); }
-            }
-            cur = sp ? stack[--sp] : kEmptyScene;
+            cur = leaf_step<kCount>(geom, cur, o, d, a, inv_a, tbest, prim, stack, sp, cnt);
         }
     }
     t_out = tbest;
@@ -472,30 +483,49 @@ struct PathState {
     int depth;
 };
 
+// ---- shading programs, one per class of hit, on the hit POINT p (= o + d*t, RayTracer.cu:256).  shade_segment() below
+// composes them; the slot-scheduled kernel (slot_kernels.cu) calls them one class at a time.
+VN_HD f3 hit_point(f3 o, f3 d, float t) { return o + d * t; }
+// normal + face-forwarding of hit_frame() for a known hit point (RayTracer.cu:257-258, 219-224)
+VN_HD void hit_normal(f3 p, f3 d, const node_f4& g, f3& n, bool& front) {
+    float inv = rcp(g.w);
+    f3 normal = (p - mk3(g.x, g.y, g.z)) * inv;
+    front = dot(d, normal) < 0.0f;
+    n = front ? normal : -normal;
+}
+// __miss__ms (RayTracer.cu:442-450): radiance of a path that left the scene
+VN_HD f3 shade_miss(f3 thr, f3 unit_direction) { return thr * sky(unit_direction); }
+// __closesthit__lambertian / __closesthit__metal (RayTracer.cu:272-366) after the depth check.  `unit_direction` is only
+// read for metal.  Returns false when the ray is absorbed.
+VN_HD bool shade_opaque(uint32_t type, const node_f4& m, f3 unit_direction, f3 n, PathState& st) {
+    const f3 s = random_in_unit_sphere(st.seed);          // both programs start with the same rejection loop
+    f3 dir;
+    bool ok = true;
+    if (type == 0u) dir = scatter_lambertian(n, s);
+    else ok = scatter_metal(unit_direction, n, m.w, s, dir);
+    if (!ok) return false;
+    st.d = dir;
+    st.thr = st.thr * mk3(m.x, m.y, m.z);
+    return true;
+}
+
 // Shades the closest hit (or miss) of one segment.  Returns true when the path continues (st updated), false when
 // it ended with radiance `result`.
 VN_HD bool shade_segment(const SceneView& sc, PathState& st, float t, int prim, f3& result) {
     // normalize(direction) is needed by miss (RayTracer.cu:444), metal (:338) and dielectric (:404); computing it for
     // every lane keeps the warp converged (a Lambertian lane simply does not use it).
     const f3 unit_direction = normalize(st.d);
-    if (prim < 0) { result = st.thr * sky(unit_direction); return false; }
+    if (prim < 0) { result = shade_miss(st.thr, unit_direction); return false; }
     if (!(st.depth > 0)) { result = mk3(0.0f); return false; }      // RayTracer.cu:275,324,384: depth budget exhausted
     const node_f4 g = sc.geom[prim];
     const node_f4 m = sc.mat[prim];
     const uint32_t type = sc.type[prim];
-    f3 p, n;
+    const f3 p = hit_point(st.o, st.d, t);
+    f3 n;
     bool front;
-    hit_frame(st.o, st.d, t, g.x, g.y, g.z, g.w, p, n, front);
+    hit_normal(p, st.d, g, n, front);
     if (type != 2u) {
-        // Lambertian (:288) and metal (:340) both start with the same rejection loop: run it once for both
-        const f3 s = random_in_unit_sphere(st.seed);
-        f3 dir;
-        bool ok = true;
-        if (type == 0u) dir = scatter_lambertian(n, s);
-        else ok = scatter_metal(unit_direction, n, m.w, s, dir);
-        if (!ok) { result = mk3(0.0f); return false; }
-        st.d = dir;
-        st.thr = st.thr * mk3(m.x, m.y, m.z);
+        if (!shade_opaque(type, m, unit_direction, n, st)) { result = mk3(0.0f); return false; }
     } else {
         st.d = scatter_dielectric(unit_direction, n, front, m.x, st.seed);
     }

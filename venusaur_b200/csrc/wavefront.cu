@@ -279,5 +279,14 @@ cudaError_t launch_wavefront(const RenderLaunch& p, const WavefrontBuffers& wf, 
     return cudaGetLastError();
 }
 
+// North-star kernel (3) on its own: used behind the slot-scheduled path kernel, which also writes per-sample radiance.
+cudaError_t launch_accumulate_samples(const RenderLaunch& p, const float* sample_rgb, cudaStream_t stream) {
+    const uint32_t region_pixels = p.width * (p.row_end - p.row_begin);
+    if (region_pixels == 0u) return cudaSuccess;
+    const uint32_t blocks = (uint32_t)std::min<uint64_t>(((uint64_t)region_pixels + 255) / 256, 148ull * 16);
+    k_wf_accumulate<<<blocks, 256, 0, stream>>>(p, sample_rgb);
+    return cudaGetLastError();
+}
+
 }  // namespace VN_NS
 }  // namespace vn
