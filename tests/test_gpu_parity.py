@@ -330,6 +330,8 @@ def test_slot_kernel_equals_persistent_kernel(rtiow_ctx, slots, threads):
     path counts, for every slot geometry, for extreme vote thresholds, with a running-mean blend and on a row range."""
     W, H, spp, depth = 200, 120, 6, 50
     cam = vb.rtiow_camera(W, H)
+    rtiow_ctx.set_option("leaf_size", 4)        # 74 wide nodes x 8 octant copies = 66 KB: leaves room for every slot geometry
+    rtiow_ctx.build_bvh()
     a, ia, sa = render(rtiow_ctx, cam, W, H, spp, 2, depth, flags=VN_PERSISTENT)
     c, ic, sc = render(rtiow_ctx, cam, W, H, spp, 3, depth, flags=VN_PERSISTENT, accum_count=1)
     try:
@@ -358,6 +360,7 @@ def test_slot_kernel_equals_persistent_kernel(rtiow_ctx, slots, threads):
     finally:
         for k, v in (("slot_slots", 3), ("slot_threads", 768), ("slot_tn", 20), ("slot_tl", 12), ("slot_tw", 8), ("slot_ts", 20), ("slot_tr", 20)):
             rtiow_ctx.set_option(k, v)
+        rtiow_ctx.set_option("leaf_size", 2)
 
 
 def test_wavefront_equals_persistent_kernel(rtiow_ctx, oracle_mod, rtiow):

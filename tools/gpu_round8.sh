@@ -11,8 +11,9 @@ try:
     d=json.loads(l); print('$1: value %.0f Mrays/s  e2e %.0f  ms/step %.3f' % (d['value'], d['e2e']['value'], d['ms_per_step']), d['config'].get('sched'))
 except Exception as e: print('$1 FAILED', l[-400:])
 "; }
-B="timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --leaf-size 1"
-$B 2>&1 | show "persistent wide leaf1"
+B="timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --leaf-size ${LEAF:-3}"
+$B 2>&1 | show "persistent wide leaf${LEAF:-3}"
+$B --opt wide_nodes=0 2>&1 | show "persistent pairs-oct leaf${LEAF:-3}"
 for cfg in "3 768" "2 1024" "4 512" "2 768" "3 512"; do set -- $cfg
   $B --kernel slots --opt slot_slots=$1 --opt slot_threads=$2 2>&1 | show "slots K=$1 T=$2"
 done

@@ -101,12 +101,26 @@ __global__ void __launch_bounds__(THREADS, 1) k_render_slots(const __grid_consta
     const uint32_t TN = tune.node_threshold, TL = tune.leaf_threshold, TW = tune.switch_threshold, TS = tune.shade_threshold,
                    TR = tune.regen_threshold;
 
+    bool force_n = false;                               // the service pass found nothing above threshold but node work
     for (;;) {
+        // ---- N burst: node steps while at least TN lanes stand on an internal node (one vote per step)
+        uint32_t nN;
+        for (;;) {
+            const bool atN = cur_slot >= 0 && !(cur & kLeafFlag);
+            nN = __popc(__ballot_sync(kFull, atN));
+            if (nN < TN && !force_n) break;
+            force_n = false;
+            if (kCount) { op_count[0] += 1u; op_lanes[0] += nN; }
+            if (atN) {
+                if (kCount) cnt.nodes += 1;
+                cur = wide_node_step(wn, cur, idir, ood, tbest, stack, sp);
+            }
+        }
+        // ---- service pass: ONE packed reduction counts the lanes waiting for every other operation; every operation
+        // above its threshold runs once, in pipeline order (leaf -> retire/fetch -> shade by material -> camera)
         const bool holds = cur_slot >= 0;
-        const bool atN = holds && !(cur & kLeafFlag);
-        const uint32_t nN = __popc(__ballot_sync(kFull, atN));
-        int op = 0;                                     // 0 N, 1 L, 2 W, 3 O, 4 D, 5 M, 6 R
-        if (nN < TN) {
+        uint32_t todo;
+        {
             const bool atL = holds && (cur & kLeafFlag) && cur != kEmptyScene;
             const bool wantW = (holds && cur == kEmptyScene) || (!holds && ((m >> kShReady) & 0xFu));
             const bool wantO = (m >> kShOpaque) & 0xFu, wantD = (m >> kShDiel) & 0xFu, wantM = (m >> kShMiss) & 0xFu;
@@ -116,14 +130,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_render_slots(const __grid_consta
             const uint32_t c = __reduce_add_sync(kFull, packed);
             const uint32_t nR = __popc(__ballot_sync(kFull, wantR));
             const uint32_t nL = c & 63u, nW = (c >> 6) & 63u, nO = (c >> 12) & 63u, nD = (c >> 18) & 63u, nM = (c >> 24) & 63u;
-            if (nL >= TL) op = 1;
-            else if (nW >= TW) op = 2;
-            else if (nO >= TS) op = 3;
-            else if (nM >= TS) op = 5;
-            else if (nR >= TR) op = 6;
-            else if (nD >= TS) op = 4;
-            else {
+            todo = (nL >= TL ? 2u : 0u) | (nW >= TW ? 4u : 0u) | (nO >= TS ? 8u : 0u) | (nD >= TS ? 16u : 0u) | (nM >= TS ? 32u : 0u) |
+                   (nR >= TR ? 64u : 0u);
+            if (todo == 0u) {
                 uint32_t best = nN;
+                int op = 0;
                 if (nL > best) { best = nL; op = 1; }
                 if (nW > best) { best = nW; op = 2; }
                 if (nO > best) { best = nO; op = 3; }
@@ -131,23 +142,29 @@ __global__ void __launch_bounds__(THREADS, 1) k_render_slots(const __grid_consta
                 if (nR > best) { best = nR; op = 6; }
                 if (nD > best) { best = nD; op = 4; }
                 if (best == 0u) break;                  // nothing left anywhere in this warp
+                todo = 1u << op;
             }
             if (kCount) {
                 const uint32_t lanes[7] = {nN, nL, nW, nO, nD, nM, nR};
-                op_count[op] += 1u; op_lanes[op] += lanes[op];
+#pragma unroll
+                for (int i = 1; i < 7; i++) if (todo & (1u << i)) { op_count[i] += 1u; op_lanes[i] += lanes[i]; }
             }
-        } else if (kCount) { op_count[0] += 1u; op_lanes[0] += nN; }
-
-        if (op == 0) {
-            if (atN) {
-                if (kCount) cnt.nodes += 1;
-                cur = wide_node_step(wn, cur, idir, ood, tbest, stack, sp);
+        }
+        if (todo & 1u) force_n = true;
+        if (todo & 2u) {
+            // ---- L: ONE sphere of the leaf the lane stands on (no inner loop: every lane does the same work)
+            if (holds && (cur & kLeafFlag) && cur != kEmptyScene) {
+                const uint32_t idx = (cur & 0x7FFFFFFFu) >> 3;
+                const float4 g = s_geom[idx];
+                if (kCount) cnt.spheres += 1;
+                const float t = sphere_root(o, d, a, inv_a, g.x, g.y, g.z, g.w, kTMin, tbest);
+                if (t >= 0.0f) { tbest = t; prim = (int)idx; }
+                cur = (cur & 7u) ? cur + 7u : (sp ? stack[--sp] : kEmptyScene);     // first + 1, count - 1 -- or pop
             }
-        } else if (op == 1) {
-            if (holds && (cur & kLeafFlag) && cur != kEmptyScene) cur = leaf_step<kCount>(s_geom, cur, o, d, a, inv_a, tbest, prim, stack, sp, cnt);
-        } else if (op == 2) {
+        }
+        if (todo & 4u) {
             // ---- W: retire the finished ray into its slot, then take the next ready slot
-            if (holds && cur == kEmptyScene) {
+            if (cur_slot >= 0 && cur == kEmptyScene) {
                 int cls = kShMiss;
                 if (prim >= 0) {
                     const f3 hp = hit_point(o, d, tbest);               // RayTracer.cu:256
@@ -175,41 +192,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_render_slots(const __grid_consta
                 cur = p.wide_root;
                 cur_slot = j;
             }
-        } else if (op == 6) {
-            // ---- R: next sample of the lane's pixel (or the next pixel) into a free slot
-            if (((m >> kShEmpty) & 0xFu) && !(exhausted && s_left == 0u)) {
-                if (s_left == 0u) {
-                    for (;;) {
-                        const uint32_t w = fetch_ticket(p.work_counter);
-                        if (w >= p.total_work) { exhausted = true; break; }
-                        const uint32_t tile = w >> 5, in = w & 31u;
-                        const uint32_t ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
-                        const uint32_t px = tx * 8u + (in & 7u), py = p.row_begin + ty * 4u + (in >> 3);
-                        if (px < p.width && py < p.row_end) {
-                            pix = py * p.width + px;
-                            pxy = px | (py << 16);
-                            cam_seed = tea4(pix, p.subframe_index);     // RayTracer.cu:169
-                            s_left = p.spp;
-                            break;
-                        }
-                    }
-                }
-                if (s_left != 0u) {
-                    const int j = __ffs((m >> kShEmpty) & 0xFu) - 1;
-                    f3 co, cd;
-                    camera_ray(p.cam, pxy & 0xFFFFu, pxy >> 16, cam_seed, co, cd);   // RayTracer.cu:173-177
-                    SLOT_F(kOx, j) = co.x; SLOT_F(kOy, j) = co.y; SLOT_F(kOz, j) = co.z;
-                    SLOT_F(kDx, j) = cd.x; SLOT_F(kDy, j) = cd.y; SLOT_F(kDz, j) = cd.z;
-                    SLOT_F(kTr, j) = 1.0f; SLOT_F(kTg, j) = 1.0f; SLOT_F(kTb, j) = 1.0f;
-                    SLOT_U(kSeed, j) = cam_seed;                                     // prd.seed = seed: a copy (:183)
-                    SLOT_U(kMeta, j) = ((p.spp - s_left) << 16) | (p.max_depth - 1u); // depth = max_depth - 1 (:184)
-                    SLOT_U(kPix, j) = pix - region_first;
-                    s_left -= 1u;
-                    n_path += 1u;
-                    m = (m & ~(1u << (kShEmpty + j))) | (1u << (kShReady + j));
-                }
-            }
-        } else {
+        }
+#pragma unroll 1
+        for (int op = 3; op <= 5; op++) {
+            if (!(todo & (1u << op))) continue;
             // ---- O / D / M: shade one waiting slot with ONE program
             const int sh = op == 3 ? kShOpaque : (op == 4 ? kShDiel : kShMiss);
             if ((m >> sh) & 0xFu) {
@@ -254,6 +240,41 @@ __global__ void __launch_bounds__(THREADS, 1) k_render_slots(const __grid_consta
                     float* out = sample_rgb + 3ull * ((uint64_t)(meta >> 16) * region_pixels + SLOT_U(kPix, j));
                     out[0] = result.x; out[1] = result.y; out[2] = result.z;         // pixel_color += ... happens in k_wf_accumulate
                     m |= 1u << (kShEmpty + j);
+                }
+            }
+        }
+        if (todo & 64u) {
+            // ---- R: next sample of the lane's pixel (or the next pixel) into a free slot
+            if (((m >> kShEmpty) & 0xFu) && !(exhausted && s_left == 0u)) {
+                if (s_left == 0u) {
+                    for (;;) {
+                        const uint32_t w = fetch_ticket(p.work_counter);
+                        if (w >= p.total_work) { exhausted = true; break; }
+                        const uint32_t tile = w >> 5, in = w & 31u;
+                        const uint32_t ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+                        const uint32_t px = tx * 8u + (in & 7u), py = p.row_begin + ty * 4u + (in >> 3);
+                        if (px < p.width && py < p.row_end) {
+                            pix = py * p.width + px;
+                            pxy = px | (py << 16);
+                            cam_seed = tea4(pix, p.subframe_index);     // RayTracer.cu:169
+                            s_left = p.spp;
+                            break;
+                        }
+                    }
+                }
+                if (s_left != 0u) {
+                    const int j = __ffs((m >> kShEmpty) & 0xFu) - 1;
+                    f3 co, cd;
+                    camera_ray(p.cam, pxy & 0xFFFFu, pxy >> 16, cam_seed, co, cd);   // RayTracer.cu:173-177
+                    SLOT_F(kOx, j) = co.x; SLOT_F(kOy, j) = co.y; SLOT_F(kOz, j) = co.z;
+                    SLOT_F(kDx, j) = cd.x; SLOT_F(kDy, j) = cd.y; SLOT_F(kDz, j) = cd.z;
+                    SLOT_F(kTr, j) = 1.0f; SLOT_F(kTg, j) = 1.0f; SLOT_F(kTb, j) = 1.0f;
+                    SLOT_U(kSeed, j) = cam_seed;                                     // prd.seed = seed: a copy (:183)
+                    SLOT_U(kMeta, j) = ((p.spp - s_left) << 16) | (p.max_depth - 1u); // depth = max_depth - 1 (:184)
+                    SLOT_U(kPix, j) = pix - region_first;
+                    s_left -= 1u;
+                    n_path += 1u;
+                    m = (m & ~(1u << (kShEmpty + j))) | (1u << (kShReady + j));
                 }
             }
         }

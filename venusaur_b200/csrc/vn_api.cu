@@ -290,8 +290,16 @@ int vn_build_bvh(vn_handle c) {
     std::string err;
     uint32_t launches = 0;
     VN_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
-    const uint32_t leaf_size = c->leaf_size ? c->leaf_size : (c->n_spheres >= 2 && c->n_spheres <= c->sah_max_prims ? 3u : 2u);
-    const int rc = lbvh_build(c->d_spheres, c->n_spheres, leaf_size, c->aabb_pad, c->sah_max_prims, c->wide_max_prims, c->num_sms, c->stream, c->scene, c->bvh_ws, &launches, err);
+    // leaf_size 0 = auto.  Small (SAH-split) scenes: the smallest leaf whose 4-wide nodes still fit in shared memory next to the
+    // spheres (one-sphere leaves need no sphere loop and test the fewest spheres; RTIOW: 238 wide nodes = 213 KB of the 227 KB);
+    // larger scenes: 2.
+    const bool small = c->n_spheres >= 2 && c->n_spheres <= c->sah_max_prims && c->n_spheres <= c->wide_max_prims;
+    int rc = 0;
+    for (uint32_t leaf_size = c->leaf_size ? c->leaf_size : (small ? 1u : 2u);; leaf_size++) {
+        rc = lbvh_build(c->d_spheres, c->n_spheres, leaf_size, c->aabb_pad, c->sah_max_prims, c->wide_max_prims, c->num_sms, c->stream, c->scene, c->bvh_ws, &launches, err);
+        if (rc != 0 || c->leaf_size || !small || leaf_size >= 4u) break;
+        if (c->scene.num_wide > 0 && c->scene.wide_levels <= kWideMaxLevels && wide_smem_bytes(c->scene.num_wide, (uint32_t)c->scene.n) + 2048 <= c->smem_optin) break;
+    }
     if (rc != 0) return fail(c, rc == -1 ? VN_ERR_INVALID : VN_ERR_CUDA, "vn_build_bvh: " + err);
     VN_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     VN_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -408,6 +408,12 @@ VN_HD bool slab_hit(float nx, float ny, float nz, float fx, float fy, float fz, 
     const float tf = fminf(fminf(fmaf(fx, idir.x, -ood.x), fmaf(fy, idir.y, -ood.y)), fminf(fmaf(fz, idir.z, -ood.z), tbest));
     return tn <= tf;
 }
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void push_if(uint32_t* stack, int& sp, uint32_t v, bool pred) {
+    asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q st.local.u32 [%0], %1; }" ::"r"((uint32_t)__cvta_generic_to_local(stack + sp)), "r"(v), "r"((uint32_t)pred) : "memory");
+    sp += pred ? 1 : 0;
+}
+#endif
 // One step over a 4-wide node: returns the next node / leaf link (kEmptyScene when the ray is finished).
 VN_HD uint32_t wide_node_step(const node_f4* __restrict__ wn, uint32_t cur, f3 idir, f3 ood, float tbest, uint32_t* stack, int& sp) {
     const node_f4* __restrict__ p = wn + kWideNodeF4 * cur;
@@ -418,9 +424,17 @@ VN_HD uint32_t wide_node_step(const node_f4* __restrict__ wn, uint32_t cur, f3 i
     const bool h3 = slab_hit(nx.w, ny.w, nz.w, fx.w, fy.w, fz.w, idir, ood, tbest);
     // the nearest hit child (static octant order) becomes the current node straight from registers; the others are
     // pushed far to near.  Only a step without any hit pays the stack load.
-    if (h3 && (h0 || h1 || h2)) stack[sp++] = f2u(lk.w);
-    if (h2 && (h0 || h1)) stack[sp++] = f2u(lk.z);
-    if (h1 && h0) stack[sp++] = f2u(lk.y);
+    const bool c3 = h3 && (h0 || h1 || h2), c2 = h2 && (h0 || h1), c1 = h1 && h0;
+#if defined(__CUDA_ARCH__)
+    // predicated stores written in PTX: left to itself the compiler turns the three pushes into six divergent branches
+    push_if(stack, sp, f2u(lk.w), c3);
+    push_if(stack, sp, f2u(lk.z), c2);
+    push_if(stack, sp, f2u(lk.y), c1);
+#else
+    if (c3) stack[sp++] = f2u(lk.w);
+    if (c2) stack[sp++] = f2u(lk.z);
+    if (c1) stack[sp++] = f2u(lk.y);
+#endif
     uint32_t next = h0 ? f2u(lk.x) : (h1 ? f2u(lk.y) : (h2 ? f2u(lk.z) : f2u(lk.w)));
     if (!(h0 || h1 || h2 || h3)) next = sp ? stack[--sp] : kEmptyScene;
     return next;
@@ -431,6 +445,9 @@ VN_HD uint32_t leaf_step(const node_f4* __restrict__ geom, uint32_t cur, f3 o, f
                          uint32_t* stack, int& sp, TraceCounters& cnt) {
     const uint32_t first = (cur & 0x7FFFFFFFu) >> 3;
     const uint32_t count = (cur & 7u) + 1u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1          // leaves of SAH-built small scenes hold one sphere: keep the loop small instead of unrolled
+#endif
     for (uint32_t k = 0; k < count; k++) {
         const node_f4 g = geom[first + k];
         if (kCount) cnt.spheres += 1;
