@@ -36,13 +36,18 @@ WORKLOADS = {
     "c1": (400, 225, 10, 50, "rtiow"),
     "c3": (3840, 2160, 16, 50, "rtiow"),
     "c4": (1920, 1080, 16, 50, "random1m"),
+    "c5": (1920, 1080, 16, 64, "random16m"),
+}
+SCENES = {   # name: (count, seed, half-extent S, material mix) -- SURVEY 8(d) C4 / C5
+    "random1m": (1_000_000, 0x5EED0001, 100.0, 0),
+    "random16m": (16_000_000, 0x5EED0002, 250.0, 1),
 }
 METRIC = "Mrays/sec (primary+secondary) at 1080p RTIOW final scene, 1/2/4/8 B200"
 
 
 def describe(name, steps):
     w, h, spp, depth, scene = WORKLOADS[name]
-    scene_txt = "RTIOW final scene (486 spheres)" if scene == "rtiow" else "synthetic 1M random spheres"
+    scene_txt = "RTIOW final scene (486 spheres)" if scene == "rtiow" else "synthetic %dM random spheres%s" % (SCENES[scene][0] // 1_000_000, " (50%% dielectric)" if SCENES[scene][3] else "")
     return "%s %dx%d, %d spp/subframe x %d subframes, max depth %d" % (scene_txt, w, h, spp, steps, depth)
 
 
@@ -113,9 +118,10 @@ def cpu_reference_rate(workload, subframes, threads=0, first_subframe=1):
     64 seeded 32x32 tiles x spp x `subframes`.  Returns (Mrays/s, cores, sample description, seconds)."""
     import oracle_lib as ol
     width, height, spp, depth, scene = WORKLOADS[workload]
-    spheres = ol.rtiow_final_scene() if scene == "rtiow" else ol.random_scene(1_000_000, 0x5EED0001, 100.0, 0)
+    spheres = ol.rtiow_final_scene() if scene == "rtiow" else ol.random_scene(*SCENES[scene])
     orc = ol.Oracle(spheres)
-    cam = ol.rtiow_camera(width, height) if scene == "rtiow" else ol.camera((0, 0, 200.0), (0, 0, -1.0), 40.0, width / height, 0.0, 200.0)
+    S2 = 2.0 * SCENES[scene][2] if scene != "rtiow" else 0.0
+    cam = ol.rtiow_camera(width, height) if scene == "rtiow" else ol.camera((0, 0, S2), (0, 0, -1.0), 40.0, width / height, 0.0, S2)
     px = sample_pixels(width, height)
     cores = threads or (os.cpu_count() or 1)
     segs, t0 = 0, time.perf_counter()
@@ -182,7 +188,7 @@ def run_ours(args):
         ctx.set_option("threads", args.threads)
     if args.blocks_per_sm:
         ctx.set_option("blocks_per_sm", args.blocks_per_sm)
-    spheres = vb.rtiow_final_scene() if scene_name == "rtiow" else vb.random_scene(1_000_000, 0x5EED0001, 100.0, 0)
+    spheres = vb.rtiow_final_scene() if scene_name == "rtiow" else vb.random_scene(*SCENES[scene_name])
     ctx.set_spheres(spheres)
     ctx.build_bvh()
     info = ctx.bvh_info()
@@ -190,7 +196,8 @@ def run_ours(args):
     if scene_name == "rtiow":
         cam = vb.rtiow_camera(width, height)
     else:
-        cam = vb.Camera((0.0, 0.0, 200.0), 40.0, width / height, 0.0, 200.0)
+        S2 = 2.0 * SCENES[scene_name][2]
+        cam = vb.Camera((0.0, 0.0, S2), 40.0, width / height, 0.0, S2)
         cam.SetForward((0.0, 0.0, -1.0))
     ctx.resize(width, height)
     kflag = {"wavefront": VN_WAVEFRONT, "pool": VN_POOL, "persistent": 0, "slots": VN_SLOTS}[args.kernel] | (VN_FAST if args.fast else 0)

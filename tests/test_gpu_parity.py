@@ -311,9 +311,16 @@ def test_octant_and_plain_persistent_kernels_agree(rtiow_ctx):
         rtiow_ctx.set_option("wide_nodes", 1)
         e, ie, se = render(rtiow_ctx, cam, W, H, spp, 2, depth)
         f, iff, sf = render(rtiow_ctx, cam, W, H, spp, 2, depth, flags=VN_COUNTERS)
+        # the warp vote between node steps and leaf tests only changes WHEN a lane does its steps, not which
+        for vote in (0, 1, 5, 32):
+            rtiow_ctx.set_option("leaf_vote", vote)
+            g, ig, sg = render(rtiow_ctx, cam, W, H, spp, 2, depth, flags=VN_COUNTERS)
+            assert np.array_equal(g.view(np.uint32), e.view(np.uint32)) and np.array_equal(ig, ie)
+            assert (sg.segments, sg.node_visits, sg.sphere_tests) == (sf.segments, sf.node_visits, sf.sphere_tests)
     finally:
         rtiow_ctx.set_option("octant_nodes", 1)
         rtiow_ctx.set_option("wide_nodes", 1)
+        rtiow_ctx.set_option("leaf_vote", 12)
     assert se.segments == sf.segments == sa.segments
     assert np.array_equal(a.view(np.uint32), e.view(np.uint32)) and np.array_equal(ia, ie) and np.array_equal(a.view(np.uint32), f.view(np.uint32))
     assert sf.sphere_tests <= 1.02 * sc.sphere_tests and sf.node_visits < 0.55 * sc.node_visits
@@ -344,7 +351,7 @@ def test_slot_kernel_equals_persistent_kernel(rtiow_ctx, slots, threads):
         d, idd, sd = render(rtiow_ctx, cam, W, H, spp, 3, depth, flags=VN_SLOTS | VN_COUNTERS, accum_count=1)   # lerp onto frame 2
         assert np.array_equal(c.view(np.uint32), d.view(np.uint32)) and np.array_equal(ic, idd) and sc.segments == sd.segments
         sched = rtiow_ctx.sched_counters()
-        assert sched["node"][0] > 0 and sched["node"][1] > 12.0 and sched["shade_opaque"][1] > 12.0
+        assert sched["node"][0] > 0 and sched["node"][1] > 6.0 and sched["shade_opaque"][1] > 6.0
         assert sd.node_visits == sched["node"][0] * sched["node"][1] or abs(sd.node_visits - sched["node"][0] * sched["node"][1]) < 1e-6 * sd.node_visits
         for tn, tl, tw, ts, tr in [(1, 1, 1, 1, 1), (33, 33, 33, 33, 33), (32, 2, 30, 5, 9)]:
             for k, v in zip(("slot_tn", "slot_tl", "slot_tw", "slot_ts", "slot_tr"), (tn, tl, tw, ts, tr)):

@@ -31,6 +31,7 @@ struct RenderLaunch {
     uint32_t root_link, num_nodes, num_spheres;
     const float4* wide;              // canonical 4-wide nodes (8 float4 each) or null; staged per octant by the path kernel
     uint32_t num_wide, wide_root;
+    uint32_t leaf_vote;              // wide traversal: lanes waiting at a leaf that trigger the leaf turn (0 = while-while phases)
     unsigned long long* counters;    // [0] segments, [1] paths, [2] node visits, [3] sphere tests
     uint32_t* work_counter;          // persistent-thread work ticket
     uint32_t total_work, tiles_x;    // work items = 8x4 pixel tiles * 32

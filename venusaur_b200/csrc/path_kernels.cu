@@ -67,6 +67,41 @@ __device__ __forceinline__ void finish_pixel(const RenderLaunch& p, uint32_t pix
     // that happen to finish a pixel in this iteration would cost every other lane of the warp the same issue slots.
 }
 
+// closest_hit_wide() with a warp vote instead of the while-while phases: every iteration the converged lanes of the warp
+// either all take a node step or all test a leaf sphere set -- the leaf turn comes when `leaf_vote` lanes wait at a leaf (or
+// nobody stands on a node).  With 4-wide nodes a ray only takes ~5 node steps between ~2 leaves, so in the while-while
+// form a lane that reached its leaf idled until the slowest lane of the warp had found one too (9.5 of 32 lanes active in
+// the node step, ncu); tools/simt_model + the SIMT simulator predicted 16 of 32 for a threshold of 8.  Same steps per
+// ray, same order, same result.
+template <bool kCount>
+__device__ __forceinline__ void closest_hit_wide_vote(const float4* __restrict__ wnodes, uint32_t oct_stride, const float4* __restrict__ geom,
+                                                      uint32_t root_link, uint32_t leaf_vote, f3 o, f3 d, float& t_out, int& prim_out,
+                                                      TraceCounters& cnt) {
+    float tbest = kTMax;
+    int prim = -1;
+    const f3 idir = slab_idir(d);
+    const float4* __restrict__ wn = wnodes + ray_octant(d) * oct_stride;
+    const f3 ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
+    const float a = dot(d, d);
+    const float inv_a = rcp(a);
+    uint32_t stack[kStackSize];
+    int sp = 0;
+    uint32_t cur = root_link;
+    while (cur != kEmptyScene) {
+        const bool at_leaf = (cur & kLeafFlag) != 0u;
+        const unsigned act = __activemask();
+        const unsigned lm = __ballot_sync(act, at_leaf);
+        if (lm == act || (uint32_t)__popc(lm) >= leaf_vote) {
+            if (at_leaf) cur = leaf_step<kCount>(geom, cur, o, d, a, inv_a, tbest, prim, stack, sp, cnt);
+        } else if (!at_leaf) {
+            if (kCount) cnt.nodes += 1;
+            cur = wide_node_step(wn, cur, idir, ood, tbest, stack, sp);
+        }
+    }
+    t_out = tbest;
+    prim_out = prim;
+}
+
 template <bool kSmem, bool kCount, bool kOct, int kMaxThreads, bool kWide = false>
 __global__ void __launch_bounds__(kMaxThreads) k_render_persistent(const __grid_constant__ RenderLaunch p) {
     extern __shared__ float4 s_scene[];
@@ -157,7 +192,8 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_persistent(const __grid_
         }
         float t;
         int prim;
-        if (kWide) closest_hit_wide<kCount>(sc.nodes, node_f4s, sc.geom, p.wide_root, st.o, st.d, t, prim, cnt);
+        if (kWide && p.leaf_vote) closest_hit_wide_vote<kCount>(sc.nodes, node_f4s, sc.geom, p.wide_root, p.leaf_vote, st.o, st.d, t, prim, cnt);
+        else if (kWide) closest_hit_wide<kCount>(sc.nodes, node_f4s, sc.geom, p.wide_root, st.o, st.d, t, prim, cnt);
         else closest_hit<kCount, kOct>(sc.nodes, sc.geom, sc.root_link, st.o, st.d, t, prim, cnt, node_f4s);
         n_seg += 1u;
         if (kCount) { n_nodes += cnt.nodes; n_sph += cnt.spheres; cnt.nodes = 0; cnt.spheres = 0; }

@@ -56,6 +56,7 @@ struct vn_context {
     bool slot_kernel = false;         // default path kernel for wide-node scenes: slot-scheduled (slot_kernels.cu) instead of k_render_persistent
     int slot_slots = 3, slot_threads = 768;
     SlotTune slot_tune{20u, 12u, 8u, 20u, 20u};
+    uint32_t leaf_vote = 12;          // see closest_hit_wide_vote (path_kernels.cu); 0 = while-while
     bool wide_nodes = true;           // use them when they fit in shared memory
     uint32_t sah_max_prims = 4096;    // scenes up to this size get SAH splits (k_sah_small); 0 = always Karras
     int threads = 256;
@@ -136,6 +137,7 @@ int fill_launch(vn_context* c, const vn_params* p, RenderLaunch& L) {
     L.num_nodes = (uint32_t)c->scene.num_nodes;
     L.num_spheres = (uint32_t)c->scene.n;
     L.wide = c->scene.wide; L.num_wide = c->scene.num_wide; L.wide_root = 0u;
+    L.leaf_vote = c->leaf_vote;
     L.counters = c->d_counters;
     L.work_counter = reinterpret_cast<uint32_t*>(c->d_counters + 4);
     const uint32_t rows = L.row_end - L.row_begin;
@@ -240,6 +242,7 @@ int vn_set_option(vn_handle c, const char* name, double value) {
     else if (k == "sah_max_prims") { VN_REQUIRE(c, value >= 0 && value <= 8192, "sah_max_prims must be in [0,8192]"); c->sah_max_prims = (uint32_t)value; c->bvh_valid = false; }
     else if (k == "wide_max_prims") { VN_REQUIRE(c, value >= 0 && value <= 65536, "wide_max_prims must be in [0,65536]"); c->wide_max_prims = (uint32_t)value; c->bvh_valid = false; }
     else if (k == "wide_nodes") { c->wide_nodes = value != 0; }
+    else if (k == "leaf_vote") { VN_REQUIRE(c, value >= 0 && value <= 32, "leaf_vote must be in [0,32]"); c->leaf_vote = (uint32_t)value; }
     else if (k == "slot_kernel") { c->slot_kernel = value != 0; }
     else if (k == "slot_slots" || k == "slot_threads") {
         const int slots = k == "slot_slots" ? (int)value : c->slot_slots, threads = k == "slot_threads" ? (int)value : c->slot_threads;
