@@ -23,7 +23,7 @@ struct hh_params {
 
 static uint32_t g_sah_max = 4096;   // same default as the library's "sah_max_prims" option
 static int g_use_oct = 0;
-static int g_use_wide = 0;         // hh_set_wide(1): traverse the 4-wide octant-sorted nodes like k_render_persistent<.., kWide>
+static int g_use_wide = 0;         // hh_set_wide(2): canonical wide nodes with distance sort (closest_hit_wide_global); hh_set_wide(1): traverse the 4-wide octant-sorted nodes like k_render_persistent<.., kWide>
 static int g_seq_postpone = 0;   // hh_set_oct(1): traverse octant-mirrored node copies like k_render_persistent<.., kOct=true>
 
 struct HostBvh {
@@ -135,6 +135,7 @@ static void build_wide(HostBvh& B) {
         lo = hi;
     }
     const size_t W = src.size();
+    if (W > 65536) return;                                 // large scenes are traversed in canonical form (closest_hit_wide_global)
     B.wide_oct.resize(8 * 7 * W);
     for (uint32_t k = 0; k < 8; k++)
         for (size_t j = 0; j < W; j++) wide_octant_node(&B.wide[8 * j], k, &B.wide_oct[(k * W + j) * 7]);
@@ -261,7 +262,8 @@ static void build(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pad_
 
 template <bool kCount>
 static inline void hh_closest(const HostBvh& B, f3 o, f3 d, float& t, int& prim, TraceCounters& cnt) {
-    if (g_use_wide && B.wide_levels <= kWideMaxLevels) closest_hit_wide<kCount>(B.wide_oct.data(), (uint32_t)(B.wide_oct.size() / 8), B.geom.data(), B.wide_root, o, d, t, prim, cnt);
+    if (g_use_wide == 2 && B.wide_levels <= kWideGlobalMaxLevels) closest_hit_wide_global<kCount>(B.wide.data(), B.geom.data(), B.wide_root, o, d, t, prim, cnt);
+    else if (g_use_wide && B.wide_levels <= kWideMaxLevels && !B.wide_oct.empty()) closest_hit_wide<kCount>(B.wide_oct.data(), (uint32_t)(B.wide_oct.size() / 8), B.geom.data(), B.wide_root, o, d, t, prim, cnt);
     else if (g_use_oct) closest_hit<kCount, true>(B.nodes_oct.data(), B.geom.data(), B.root_link, o, d, t, prim, cnt, (uint32_t)B.nodes.size());
     else closest_hit<kCount, false>(B.nodes.data(), B.geom.data(), B.root_link, o, d, t, prim, cnt);
 }
@@ -500,7 +502,7 @@ extern "C" uint64_t hh_step_sequences(const hh_sphere* s, uint32_t n, uint32_t l
             st.thr = mk3(1.0f); st.seed = seed; st.depth = (int)P->max_depth - 1;
             f3 result;
             while (true) {
-                if (g_use_wide && B.wide_levels <= kWideMaxLevels) trace_sequence_wide(B, st.o, st.d, seq);
+                if (g_use_wide == 1 && B.wide_levels <= kWideMaxLevels && !B.wide_oct.empty()) trace_sequence_wide(B, st.o, st.d, seq);
                 else if (g_seq_postpone) trace_sequence_pp(sc, st.o, st.d, seq); else trace_sequence(sc, st.o, st.d, seq);
                 float t; int prim; TraceCounters cnt{0, 0};
                 closest_hit<false>(sc.nodes, sc.geom, sc.root_link, st.o, st.d, t, prim, cnt);

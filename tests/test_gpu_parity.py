@@ -132,8 +132,10 @@ def test_wide_nodes_match_cpu_emulation(ctx, host_harness, oracle_mod, rtiow, le
     Karras- and SAH-split trees; scenes above "wide_max_prims" get none."""
     from test_host_logic import _host_wide
     scenes = [rtiow, np.ascontiguousarray(oracle_mod.random_scene(3000, 0x5EED0001, 30.0, 0)), np.ascontiguousarray(rtiow[:5]),
-              np.ascontiguousarray(rtiow[:1]), np.ascontiguousarray(oracle_mod.random_scene(9000, 0x5EED0003, 60.0, 1))]
+              np.ascontiguousarray(rtiow[:1]), np.ascontiguousarray(oracle_mod.random_scene(9000, 0x5EED0003, 60.0, 1)),
+              np.ascontiguousarray(oracle_mod.random_scene(60000, 0x5EED0001, 100.0, 0))]     # > 16384: one launch pair per level
     try:
+        ctx.set_option("wide_max_prims", 1 << 20)
         for sah in (4096, 0):
             ctx.set_option("sah_max_prims", sah)
             host_harness.hh_set_sah_max(sah)
@@ -583,16 +585,28 @@ def test_empty_single_and_ragged_scenes(ctx, oracle_mod, rtiow):
 def test_large_scene_from_hbm_matches_oracle(ctx, oracle_mod):
     """Scene too large for shared memory (nodes + spheres traversed from L2/HBM): dielectric-heavy config-5 mix."""
     spheres = vb.random_scene(200_000, 0x5EED0002, 60.0, 1)
+    ctx.set_option("wide_max_prims", 1 << 20)
     ctx.set_spheres(spheres)
     ctx.build_bvh()
-    assert ctx.bvh_info().scene_in_smem == 0
+    ctx.set_option("wide_max_prims", 16384)
+    assert ctx.bvh_info().scene_in_smem == 0 and len(ctx.read_wide_bvh()[0]) > 10000
     W, H = 160, 90
     cam = vb.Camera((0.0, 0.0, 120.0), 40.0, W / H, 0.0, 120.0)
     cam.SetForward((0.0, 0.0, -1.0))
     orc = oracle_mod.Oracle(spheres)
     want, ost = orc.render_mean(orc.params(cam.frame(), W, H, 4, 1, 64, atten=oracle_mod.ATTEN_FORWARD))
-    for flags in (VN_EXACT, VN_EXACT | VN_WAVEFRONT, VN_POOL):
-        acc, _, st = render(ctx, cam, W, H, 4, 1, 64, flags=flags, image=False)
+    # default: pair nodes from L2/HBM; opt-in: canonical wide nodes from L2/HBM (distance-sorted children, warp-voted leaf turns)
+    for flags, opts in ((VN_EXACT, {}), (VN_EXACT, {"wide_global": 1}), (VN_EXACT, {"wide_global": 1, "leaf_vote": 0}),
+                        (VN_EXACT | VN_COUNTERS, {"wide_global": 1}), (VN_EXACT | VN_WAVEFRONT, {}), (VN_POOL, {})):
+        for k, v in opts.items():
+            ctx.set_option(k, v)
+        try:
+            acc, _, st = render(ctx, cam, W, H, 4, 1, 64, flags=flags, image=False)
+            if flags & VN_COUNTERS:
+                assert st.node_visits / st.segments < 30          # the wide nodes really were traversed (pairs: ~50)
+        finally:
+            ctx.set_option("leaf_vote", 12)
+            ctx.set_option("wide_global", 0)
         # distant small spheres: grazing rays inside the float noise of the quadratic may be culled by one BVH and not
         # the other (SURVEY 3.4: tie/grazing order is unspecified in OptiX too) -- allow a handful of pixels
         bad = (acc.view(np.uint32) != want.view(np.uint32)).any(axis=-1)

@@ -327,3 +327,30 @@ def test_wide_traversal_equals_plain_on_cpu(host_harness, oracle_mod, rtiow):
             assert nv.value / segs.value < 8
     finally:
         host_harness.hh_set_wide(0)
+
+
+def test_wide_global_traversal_equals_pairs_on_cpu(host_harness, oracle_mod):
+    """closest_hit_wide_global (canonical 128-byte wide nodes, hit children sorted by entry distance -- the form large
+    scenes are traversed in from L2/HBM) finds the closest hits of the pair traversal with about half the node steps."""
+    spheres = np.ascontiguousarray(oracle_mod.random_scene(20000, 0x5EED0001, 30.0, 0))
+    rng = np.random.RandomState(31)
+    n = 20000
+    o = (rng.rand(n, 3).astype(np.float32) - np.float32(0.5)) * np.float32(60.0)
+    d = rng.randn(n, 3).astype(np.float32)
+    d[:30, 1] = 0.0
+    out = {}
+    try:
+        for wide in (0, 2):
+            host_harness.hh_set_wide(wide)
+            t = np.zeros(n, np.float32)
+            p = np.zeros(n, np.int32)
+            nv, st = C.c_uint64(), C.c_uint64()
+            host_harness.hh_closest_hit(spheres.ctypes.data_as(C.c_void_p), len(spheres), 2, C.c_float(0.01), o.ctypes.data_as(C.c_void_p),
+                                        d.ctypes.data_as(C.c_void_p), n, t.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p),
+                                        C.byref(nv), C.byref(st))
+            out[wide] = (t, p, nv.value, st.value)
+    finally:
+        host_harness.hh_set_wide(0)
+    assert np.array_equal(out[0][0], out[2][0]) and np.array_equal(out[0][1], out[2][1])
+    assert (out[0][1] >= 0).sum() > 500
+    assert out[2][2] < 0.6 * out[0][2] and out[2][3] < 1.05 * out[0][3]

@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(kBlock) k_karras(const uint32_t* __restrict__ 
 constexpr int kSahThreads = 1024;
 constexpr uint32_t kMaxSahHeight = 48;   // < kStackSize (64) with margin
 constexpr uint32_t kSahInactive = 0xFFFFFFFFu;
+constexpr uint32_t kWideSingleCtaMax = 16384;
 
 __global__ void __launch_bounds__(kSahThreads) k_sah_small(uint32_t n, const f4* __restrict__ cen, const f4* __restrict__ blo, const f4* __restrict__ bhi,
                                                           uint32_t* permA, uint32_t* permB, uint32_t* ownerA, uint32_t* ownerB,
@@ -366,6 +367,36 @@ __global__ void __launch_bounds__(kBlock) k_wide_build(const float4* __restrict_
     if (threadIdx.x == 0) { result[1] = hi; result[2] = levels; }
 }
 
+// The same for scenes of any size, one level per launch pair: count the internal children of every wide node of the level,
+// exclusive scan, emit.  Node order = the single-CTA kernel's (and the host emulation's) breadth-first order.
+__global__ void __launch_bounds__(kBlock) k_wide_count(const float4* __restrict__ nodes, const uint32_t* __restrict__ src, uint32_t m, uint32_t* __restrict__ cnt) {
+    const uint32_t e = blockIdx.x * kBlock + threadIdx.x;
+    if (e >= m) return;
+    uint32_t ch[4];
+    const uint32_t n = wide_collapse(nodes, src[e], ch);
+    uint32_t n_internal = 0;
+    for (uint32_t c = 0; c < n; c++) n_internal += (__float_as_uint(nodes[2 * ch[c]].w) & kLeafFlag) ? 0u : 1u;
+    cnt[e] = n_internal;
+}
+__global__ void __launch_bounds__(kBlock) k_wide_emit(const float4* __restrict__ nodes, uint32_t* src, uint32_t lo, uint32_t m, const uint32_t* __restrict__ off,
+                                                     uint32_t next, uint32_t cap, float4* __restrict__ wide) {
+    const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+    if (i >= m) return;
+    const uint32_t e = lo + i;
+    uint32_t ch[4];
+    const uint32_t n = wide_collapse(nodes, src[e], ch);
+    uint32_t at = next + off[i];
+    for (uint32_t c = 0; c < 4u; c++) {
+        float4 a = make_float4(3e38f, 3e38f, 3e38f, __uint_as_float(kWideEmpty)), b = make_float4(-3e38f, -3e38f, -3e38f, 0.0f);
+        if (c < n) {
+            a = nodes[2 * ch[c]]; b = nodes[2 * ch[c] + 1];
+            const uint32_t link = __float_as_uint(a.w);
+            if (!(link & kLeafFlag)) { if (at < cap) src[at] = link; a.w = __uint_as_float(at); at += 1u; }
+        }
+        wide[8ull * e + 2 * c] = a; wide[8ull * e + 2 * c + 1] = b;
+    }
+}
+
 #define LB_CHECK(call)                                                                                   \
     do {                                                                                                 \
         cudaError_t e_ = (call);                                                                         \
@@ -378,6 +409,7 @@ inline uint32_t blocks_for(uint64_t n) { return (uint32_t)((n + kBlock - 1) / kB
 
 void lbvh_free(LbvhScene& sc) {
     cudaFree(sc.arena);
+    cudaFree(sc.wide_alloc);
     sc = LbvhScene();
 }
 
@@ -425,7 +457,8 @@ int lbvh_build(const vn_sphere* d_spheres, uint64_t n64, uint32_t leaf_size, flo
         const uint32_t nb = (uint32_t)((ni + kScanTile - 1) / kScanTile);
         // ---- outputs: one allocation (nodes at their upper bound 2n+2, so the node count needs no mid-build sync)
         Arena oa;
-        const bool want_wide = n <= wide_max_prims;
+        const bool want_wide = n <= wide_max_prims && n <= kWideSingleCtaMax;        // one-CTA breadth-first kernel, nodes in the arena
+        const bool want_wide_large = n <= wide_max_prims && n > kWideSingleCtaMax;   // one launch pair per level, own allocation
         oa.take<float4>(2 * (2ull * n + 2)); oa.take<float4>(n); oa.take<float4>(n); oa.take<uint32_t>(n); oa.take<uint32_t>(n); oa.take<uint8_t>(n);
         if (want_wide) oa.take<float4>(8ull * n);
         const size_t out_bytes = oa.off + 256;
@@ -534,6 +567,34 @@ int lbvh_build(const vn_sphere* d_spheres, uint64_t n64, uint32_t leaf_size, flo
         memcpy(out.bounds_hi, &host[8], 12);
         out.num_wide = want_wide ? host[2] : 0u;
         out.wide_levels = want_wide ? host[3] : 0u;
+        if (want_wide_large && total_kept > 0u && !(out.root_link & kLeafFlag)) {
+            const uint32_t cap = total_kept;                        // every wide node is a kept internal pair node
+            const uint32_t nbw = (cap + kScanTile - 1) / kScanTile;
+            uint32_t *src = nullptr, *cnt = nullptr, *off = nullptr, *wsums = nullptr;
+            LB_CHECK(cudaMalloc(&out.wide_alloc, 128ull * cap));
+            out.wide = static_cast<float4*>(out.wide_alloc);
+            LB_CHECK(cudaMalloc(&src, 4ull * (3ull * cap + nbw + 8)));
+            cnt = src + cap; off = cnt + cap; wsums = off + cap;
+            cudaError_t werr = cudaMemcpyAsync(src, &out.root_link, 4, cudaMemcpyHostToDevice, stream);
+            uint32_t lo = 0, hi = 1, levels = 0;
+            while (werr == cudaSuccess && lo < hi) {
+                const uint32_t m = hi - lo, nbm = (m + kScanTile - 1) / kScanTile;
+                k_wide_count<<<blocks_for(m), kBlock, 0, stream>>>(out.nodes, src + lo, m, cnt);
+                k_scan_block_sums<<<nbm, kBlock, 0, stream>>>(cnt, m, wsums);
+                k_scan_sums<<<1, kBlock, 0, stream>>>(wsums, nbm);
+                k_scan_final<<<nbm, kBlock, 0, stream>>>(cnt, m, wsums, off);
+                k_wide_emit<<<blocks_for(m), kBlock, 0, stream>>>(out.nodes, src, lo, m, off, hi, cap, out.wide);
+                launched += 5;
+                uint32_t total = 0;
+                werr = cudaMemcpyAsync(&total, wsums + nbm, 4, cudaMemcpyDeviceToHost, stream);
+                if (werr == cudaSuccess) werr = cudaStreamSynchronize(stream);
+                lo = hi; hi += total; levels += 1u;
+                if (hi > cap) { werr = cudaErrorUnknown; break; }
+            }
+            cudaFree(src);
+            LB_CHECK(werr);
+            out.num_wide = hi; out.wide_levels = levels;
+        }
         out.height = use_sah ? host[1] : 0u;     // 0 = not measured (Karras: bounded by the 30-bit key + index tie-break)
         if (use_sah && out.height > kMaxSahHeight) {
             // a degenerate scene (e.g. hundreds of coincident spheres) makes SAH peel one primitive per level; the

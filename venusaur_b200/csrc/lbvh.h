@@ -25,6 +25,7 @@ struct LbvhScene {
     uint32_t root_link = 0xFFFFFFFFu;
     uint32_t leaf_size = 0;
     float4* wide = nullptr;      // num_wide x 128 B: 4-wide nodes derived from the pairs (small scenes only), see lbvh_core.cuh
+    void* wide_alloc = nullptr;  // large scenes: the wide nodes have their own allocation
     uint32_t num_wide = 0, wide_levels = 0;
     uint32_t height = 0;         // levels of internal nodes (the traversal stack must hold that many entries)
     bool sah = false;            // splits chosen by the surface-area heuristic (small scenes) instead of Karras' spatial medians

@@ -174,6 +174,7 @@ namespace vn {
 
 constexpr uint32_t kWideEmpty = 0xFFFFFFFFu;
 constexpr uint32_t kWideMaxLevels = 20;    // 3 pushes per level + 1 <= kStackSize
+constexpr uint32_t kWideGlobalMaxLevels = 42;   // same bound for kWideStackSize (traversal from global memory)
 
 VN_HD float packed_area(const node_f4& a, const node_f4& b) { return box_area(a.x, a.y, a.z, b.x, b.y, b.z); }
 

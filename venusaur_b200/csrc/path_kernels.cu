@@ -102,6 +102,34 @@ __device__ __forceinline__ void closest_hit_wide_vote(const float4* __restrict__
     prim_out = prim;
 }
 
+// Scenes too large for shared memory: canonical 128-byte wide nodes from L2/HBM (vn_math.cuh::wide_global_step), same vote.
+template <bool kCount>
+__device__ __forceinline__ void closest_hit_wide_global_vote(const float4* __restrict__ wide, const float4* __restrict__ geom, uint32_t root_link,
+                                                             uint32_t leaf_vote, f3 o, f3 d, float& t_out, int& prim_out, TraceCounters& cnt) {
+    float tbest = kTMax;
+    int prim = -1;
+    const f3 idir = slab_idir(d);
+    const f3 ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
+    const float a = dot(d, d);
+    const float inv_a = rcp(a);
+    uint32_t stack[kWideStackSize];
+    int sp = 0;
+    uint32_t cur = root_link;
+    while (cur != kEmptyScene) {
+        const bool at_leaf = (cur & kLeafFlag) != 0u;
+        const unsigned act = __activemask();
+        const unsigned lm = __ballot_sync(act, at_leaf);
+        if (lm == act || (uint32_t)__popc(lm) >= leaf_vote) {
+            if (at_leaf) cur = leaf_step<kCount>(geom, cur, o, d, a, inv_a, tbest, prim, stack, sp, cnt);
+        } else if (!at_leaf) {
+            if (kCount) cnt.nodes += 1;
+            cur = wide_global_step(wide, cur, idir, ood, tbest, stack, sp);
+        }
+    }
+    t_out = tbest;
+    prim_out = prim;
+}
+
 template <bool kSmem, bool kCount, bool kOct, int kMaxThreads, bool kWide = false>
 __global__ void __launch_bounds__(kMaxThreads) k_render_persistent(const __grid_constant__ RenderLaunch p) {
     extern __shared__ float4 s_scene[];
@@ -192,7 +220,11 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_persistent(const __grid_
         }
         float t;
         int prim;
-        if (kWide && p.leaf_vote) closest_hit_wide_vote<kCount>(sc.nodes, node_f4s, sc.geom, p.wide_root, p.leaf_vote, st.o, st.d, t, prim, cnt);
+        if (kWide && !kSmem) {
+            if (p.leaf_vote) closest_hit_wide_global_vote<kCount>(p.wide, sc.geom, p.wide_root, p.leaf_vote, st.o, st.d, t, prim, cnt);
+            else closest_hit_wide_global<kCount>(p.wide, sc.geom, p.wide_root, st.o, st.d, t, prim, cnt);
+        }
+        else if (kWide && p.leaf_vote) closest_hit_wide_vote<kCount>(sc.nodes, node_f4s, sc.geom, p.wide_root, p.leaf_vote, st.o, st.d, t, prim, cnt);
         else if (kWide) closest_hit_wide<kCount>(sc.nodes, node_f4s, sc.geom, p.wide_root, st.o, st.d, t, prim, cnt);
         else closest_hit<kCount, kOct>(sc.nodes, sc.geom, sc.root_link, st.o, st.d, t, prim, cnt, node_f4s);
         n_seg += 1u;
@@ -314,6 +346,7 @@ inline uint32_t grid_for(uint64_t n, int threads) { return (uint32_t)((n + threa
 namespace {
 typedef void (*PathKernel)(const RenderLaunch);
 PathKernel pick_kernel(bool scene_in_smem, bool count, bool octant, bool wide = false) {
+    if (wide && !scene_in_smem) return count ? k_render_persistent<false, true, false, 256, true> : k_render_persistent<false, false, false, 256, true>;
     if (wide) return count ? k_render_persistent<true, true, false, 1024, true> : k_render_persistent<true, false, false, 1024, true>;
     if (scene_in_smem && octant) return count ? k_render_persistent<true, true, true, 1024> : k_render_persistent<true, false, true, 1024>;
     if (scene_in_smem) return count ? k_render_persistent<true, true, false, 256> : k_render_persistent<true, false, false, 256>;

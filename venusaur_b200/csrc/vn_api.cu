@@ -52,7 +52,10 @@ struct vn_context {
     // options
     uint32_t leaf_size = 0;           // 0 = auto: 3 with SAH splits (small scenes), 2 with Karras splits
     float aabb_pad = 0.01f;
-    uint32_t wide_max_prims = 16384;  // scenes up to this size also get 4-wide nodes (k_wide_build) for the shared-memory path kernel; 0 = never
+    uint32_t wide_max_prims = 16384;  // scenes up to this size also get 4-wide nodes (octant-sorted copies in shared memory when they fit); 0 = never.
+                                      // Larger values build them for any scene (one launch pair per level) for the opt-in "wide_global" traversal
+    bool wide_global = false;         // traverse canonical wide nodes from L2/HBM when the scene does not fit in shared memory (measured slower
+                                      // than the pair nodes on 1 M / 16 M spheres: 1.10 vs 1.45 and 0.69 vs 0.80 Grays/s)
     bool slot_kernel = false;         // default path kernel for wide-node scenes: slot-scheduled (slot_kernels.cu) instead of k_render_persistent
     int slot_slots = 3, slot_threads = 768;
     SlotTune slot_tune{20u, 12u, 8u, 20u, 20u};
@@ -240,8 +243,9 @@ int vn_set_option(vn_handle c, const char* name, double value) {
     else if (k == "smem_scene_limit") { VN_REQUIRE(c, value >= 0, "smem_scene_limit must be >= 0"); c->smem_scene_limit = (size_t)value; }
     else if (k == "wavefront_slots") { VN_REQUIRE(c, value >= 1024 && value <= (double)(1u << 26), "wavefront_slots out of range"); c->wavefront_slots = (uint32_t)value; free_wavefront(c->wf); c->wf_sample_floats_ = 0; }
     else if (k == "sah_max_prims") { VN_REQUIRE(c, value >= 0 && value <= 8192, "sah_max_prims must be in [0,8192]"); c->sah_max_prims = (uint32_t)value; c->bvh_valid = false; }
-    else if (k == "wide_max_prims") { VN_REQUIRE(c, value >= 0 && value <= 65536, "wide_max_prims must be in [0,65536]"); c->wide_max_prims = (uint32_t)value; c->bvh_valid = false; }
+    else if (k == "wide_max_prims") { VN_REQUIRE(c, value >= 0 && value <= (double)(1u << 28), "wide_max_prims must be in [0,2^28]"); c->wide_max_prims = (uint32_t)value; c->bvh_valid = false; }
     else if (k == "wide_nodes") { c->wide_nodes = value != 0; }
+    else if (k == "wide_global") { c->wide_global = value != 0; }
     else if (k == "leaf_vote") { VN_REQUIRE(c, value >= 0 && value <= 32, "leaf_vote must be in [0,32]"); c->leaf_vote = (uint32_t)value; }
     else if (k == "slot_kernel") { c->slot_kernel = value != 0; }
     else if (k == "slot_slots" || k == "slot_threads") {
@@ -296,7 +300,7 @@ int vn_build_bvh(vn_handle c) {
     // leaf_size 0 = auto.  Small (SAH-split) scenes: the smallest leaf whose 4-wide nodes still fit in shared memory next to the
     // spheres (one-sphere leaves need no sphere loop and test the fewest spheres; RTIOW: 238 wide nodes = 213 KB of the 227 KB);
     // larger scenes: 2.
-    const bool small = c->n_spheres >= 2 && c->n_spheres <= c->sah_max_prims && c->n_spheres <= c->wide_max_prims;
+    const bool small = c->n_spheres >= 2 && c->n_spheres <= c->sah_max_prims && c->n_spheres <= c->wide_max_prims && c->n_spheres <= 16384;
     int rc = 0;
     for (uint32_t leaf_size = c->leaf_size ? c->leaf_size : (small ? 1u : 2u);; leaf_size++) {
         rc = lbvh_build(c->d_spheres, c->n_spheres, leaf_size, c->aabb_pad, c->sah_max_prims, c->wide_max_prims, c->num_sms, c->stream, c->scene, c->bvh_ws, &launches, err);
@@ -584,10 +588,13 @@ int vn_render(vn_handle c, const vn_params* p) {
         // preferred: 4-wide nodes, octant-sorted, 8 copies in shared memory (half the traversal steps, no distance compare)
         const size_t wide_bytes = wide_smem_bytes(L.num_wide, L.num_spheres);
         cfg.wide = c->wide_nodes && L.wide && L.num_wide > 0 && c->scene.wide_levels <= kWideMaxLevels && wide_bytes + 2048 <= c->smem_optin;
+        // scenes too large for shared memory: the canonical wide nodes straight from L2/HBM (half the dependent fetches)
+        const bool wide_global = !cfg.wide && !cfg.scene_in_smem && c->wide_global && c->wide_nodes && L.wide && L.num_wide > 0 && c->scene.wide_levels <= kWideGlobalMaxLevels;
         if (cfg.wide) { cfg.scene_in_smem = true; cfg.octant = false; cfg.smem_bytes = wide_bytes; cfg.threads = 1024; }
+        else if (wide_global) { cfg.wide = true; cfg.octant = false; if (cfg.threads > 256) cfg.threads = 256; }
         else if (cfg.octant) { cfg.smem_bytes = oct_bytes; cfg.threads = 1024; }
         else if (cfg.threads > 256) cfg.threads = 256;
-        int per_sm = (cfg.octant || cfg.wide) ? 1 : c->blocks_per_sm;
+        int per_sm = (cfg.octant || (cfg.wide && cfg.scene_in_smem)) ? 1 : c->blocks_per_sm;
         if (per_sm <= 0) {
             per_sm = exact_build ? exact::max_blocks_per_sm(cfg.threads, cfg.smem_bytes, cfg.scene_in_smem, count, cfg.octant, cfg.wide)
                                  : fast::max_blocks_per_sm(cfg.threads, cfg.smem_bytes, cfg.scene_in_smem, count, cfg.octant, cfg.wide);

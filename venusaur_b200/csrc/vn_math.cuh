@@ -290,6 +290,7 @@ typedef f4 node_f4;
 constexpr uint32_t kLeafFlag = 0x80000000u;
 constexpr uint32_t kEmptyScene = 0xFFFFFFFFu;
 constexpr int kStackSize = 64;
+constexpr int kWideStackSize = 128;      // global wide nodes of large scenes: 3 pushes per level, Karras trees of 16 M spheres are ~40 levels deep
 constexpr float kTMin = 0.001f;   // RayTracer.cu:194
 constexpr float kTMax = 1e16f;    // RayTracer.cu:195
 
@@ -499,6 +500,71 @@ struct PathState {
     uint32_t seed;
     int depth;
 };
+
+// Closest hit over the CANONICAL 4-wide nodes in global memory (scenes too large for shared memory): child c of node i =
+// wide[8i + 2c] = {lo.xyz, link}, wide[8i + 2c + 1] = {hi.xyz, count} -- one 128-byte line per step instead of two dependent
+// 64-byte pair fetches.  No octant copies here (8 x 128 B x nodes would not stay in L2), so the step sorts the hit children
+// by entry distance: keys = distance bits with the child index in the two low mantissa bits, 5 compare-exchanges.
+VN_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+VN_HD uint32_t umax32(uint32_t a, uint32_t b) { return a < b ? b : a; }
+VN_HD uint32_t wide_global_step(const node_f4* __restrict__ wide, uint32_t cur, f3 idir, f3 ood, float tbest, uint32_t* stack, int& sp) {
+    const node_f4* __restrict__ p = wide + 8ull * cur;
+    uint32_t key[4], link[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int c = 0; c < 4; c++) {
+        const node_f4 lo = p[2 * c], hi = p[2 * c + 1];
+        float tn;
+        link[c] = f2u(lo.w);
+        // an empty slot's inverted box only fails the near/far form of the octant copies; min/max would turn it inside out
+        const bool h = box_hit(lo, hi, idir, ood, tbest, tn) && link[c] != kEmptyScene;
+        key[c] = h ? ((f2u(tn) & ~3u) | (uint32_t)c) : 0xFFFFFFFFu;    // tn >= 0: float bits order like unsigned integers
+    }
+    // sorting network for 4 keys, ascending: (0,1)(2,3)(0,2)(1,3)(1,2)
+    uint32_t a0 = umin32(key[0], key[1]), a1 = umax32(key[0], key[1]), a2 = umin32(key[2], key[3]), a3 = umax32(key[2], key[3]);
+    const uint32_t b0 = umin32(a0, a2), b2 = umax32(a0, a2), b1 = umin32(a1, a3), b3 = umax32(a1, a3);
+    const uint32_t c1 = umin32(b1, b2), c2 = umax32(b1, b2);
+    // push far to near, descend into the nearest
+    const uint32_t order[3] = {b3, c2, c1};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 3; i++) {
+        const uint32_t k = order[i];
+        const uint32_t idx = k & 3u;
+        const uint32_t l = idx == 0u ? link[0] : (idx == 1u ? link[1] : (idx == 2u ? link[2] : link[3]));
+        if (k != 0xFFFFFFFFu) stack[sp++] = l;
+    }
+    if (b0 == 0xFFFFFFFFu) return sp ? stack[--sp] : kEmptyScene;
+    const uint32_t idx = b0 & 3u;
+    return idx == 0u ? link[0] : (idx == 1u ? link[1] : (idx == 2u ? link[2] : link[3]));
+}
+template <bool kCount>
+VN_HD void closest_hit_wide_global(const node_f4* __restrict__ wide, const node_f4* __restrict__ geom, uint32_t root_link,
+                                   f3 o, f3 d, float& t_out, int& prim_out, TraceCounters& cnt) {
+    float tbest = kTMax;
+    int prim = -1;
+    {
+        const f3 idir = slab_idir(d);
+        const f3 ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
+        const float a = dot(d, d);
+        const float inv_a = rcp(a);
+        uint32_t stack[kWideStackSize];
+        int sp = 0;
+        uint32_t cur = root_link;
+        for (;;) {
+            while (!(cur & kLeafFlag)) {
+                if (kCount) cnt.nodes += 1;
+                cur = wide_global_step(wide, cur, idir, ood, tbest, stack, sp);
+            }
+            if (cur == kEmptyScene) break;
+            cur = leaf_step<kCount>(geom, cur, o, d, a, inv_a, tbest, prim, stack, sp, cnt);
+        }
+    }
+    t_out = tbest;
+    prim_out = prim;
+}
 
 // ---- shading programs, one per class of hit, on the hit POINT p (= o + d*t, RayTracer.cu:256).  shade_segment() below
 // composes them; the slot-scheduled kernel (slot_kernels.cu) calls them one class at a time.
