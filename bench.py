@@ -354,7 +354,10 @@ def run_ours(args):
             pass
         # issue-slot roofline: thread-instructions per segment from the budget model of SURVEY 8(d)
         # with V_node / V_sphere measured by the instrumented kernel on this very workload.
-        i_seg = 40.0 * v_node + 30.0 * v_sphere + 150.0
+        # Coefficients: pair nodes = SURVEY's budget; 4-wide nodes = SASS counts of the shipped kernel (node step 83 instructions,
+        # one sphere test ~60 incl. its share of IEEE sqrt/div, shade + RNG + camera ~270 per segment; profiles/).
+        wide = bool(info.scene_in_smem) and "wide_nodes=0" not in args.opt and len(ctx.read_wide_bvh()[0]) > 0 and v_node < 8.0
+        i_seg = (83.0 * v_node + 60.0 * v_sphere + 270.0) if wide else (40.0 * v_node + 30.0 * v_sphere + 150.0)
         f_clk = (clk.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0) * 1e6
         peak_tinst = 32 * 4 * n_sm * f_clk / 1e12
         per_gpu_rate = (my_segs / (sum(step_ms) * 1e-3))
@@ -386,8 +389,9 @@ def run_ours(args):
             "segments": int(tot_segs), "segments_per_path": tot_segs / float(width * height * spp * K * world),
             "roofline": {"bound": "issue", "achieved": achieved_tinst, "peak": peak_tinst, "unit": "Tinst/s (thread instructions)",
                          "frac": achieved_tinst / peak_tinst, "traffic": prof.get("dram_bytes_per_launch"),
-                         "model": "I_seg = 40*V_node + 30*V_sphere + 150 = %.0f thread-instructions/segment (V_node=%.2f, V_sphere=%.2f measured); "
-                                  "peak = 32 lanes x 4 schedulers x %d SMs x %.0f MHz (median SM clock during the run)" % (i_seg, v_node, v_sphere, n_sm, f_clk / 1e6),
+                         "model": "I_seg = %s = %.0f thread-instructions/segment (V_node=%.2f, V_sphere=%.2f measured); "
+                                  "peak = 32 lanes x 4 schedulers x %d SMs x %.0f MHz (median SM clock during the run)"
+                                  % ("83*V_node + 60*V_sphere + 270 (4-wide nodes)" if wide else "40*V_node + 30*V_sphere + 150 (pair nodes)", i_seg, v_node, v_sphere, n_sm, f_clk / 1e6),
                          "measured_inst_per_segment": prof.get("thread_inst_per_segment"),
                          "issue_slot_utilisation_ncu": prof.get("issue_slot_utilisation")},
             "roofline_hbm": {"bound": "hbm", "achieved": algo_bytes / (mean_step_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -395,8 +399,16 @@ def run_ours(args):
                              "note": "accum RMW + uchar4 store only (36 B/pixel/launch); BVH + spheres are staged in shared memory, so this "
                                      "path is not HBM-bound (of measured %s)" % ("peak" if peaks else "fallback")},
         }
+        if not info.scene_in_smem:
+            # scenes traversed from L2/HBM (C4 / C5): SURVEY 8(d) byte model, one pair visit = 2 x 32-byte nodes, one sphere = 32 bytes
+            b_seg = 64.0 * v_node + 32.0 * v_sphere
+            out["roofline_issue"] = out["roofline"]
+            out["roofline"] = {"bound": "hbm", "achieved": per_gpu_rate * b_seg / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                               "frac": per_gpu_rate * b_seg / 1e9 / hbm_peak, "traffic": None,
+                               "model": "B_seg = 64*V_node + 32*V_sphere = %.0f bytes/segment (V_node=%.2f pair visits, V_sphere=%.2f measured); node fetches "
+                                        "are random 64-byte pairs served by L2 (1 M spheres: 93 %% L2 hits) or HBM (16 M: 58 %%)" % (b_seg, v_node, v_sphere)}
         if world == 1 and not args.no_cpu_baseline:
-            rate, cores, sample, dt, _ = cpu_reference_rate(args.workload, 8)
+            rate, cores, sample, dt, _ = cpu_reference_rate(args.workload, 160 if scene_name == "rtiow" else 8)
             out["cpu_baseline"] = {"value": rate, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample, "seconds": dt}
         print(json.dumps(out))
     if dist is not None:

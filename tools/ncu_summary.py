@@ -12,6 +12,26 @@ def fl(x):
         return 0.0
 
 
+def sass_regions(rows, total_w, min_share=0.008):
+    """SASS view of the source page (no source correlation): runs of consecutive instructions with the same execution
+    count = one basic-block region; prints each region's share of the warp instructions and its mean active lanes."""
+    H = rows[1]
+    ia, isrc, ie, it = H.index("Address"), H.index("Source"), H.index("Instructions Executed"), H.index("Thread Instructions Executed")
+    data = [(r[ia], r[isrc], fl(r[ie]), fl(r[it])) for r in rows[2:] if len(r) > it]
+    tot = sum(x[2] for x in data)
+    print("--- SASS regions (runs of equal execution count): instruction range, instructions, executions per instruction, share of warp "
+          "instructions, mean active lanes, first instruction")
+    i = 0
+    while i < len(data):
+        j, s, st = i, 0.0, 0.0
+        while j < len(data) and abs(data[j][2] - data[i][2]) <= 0.03 * max(data[i][2], 1):
+            s += data[j][2]; st += data[j][3]; j += 1
+        if s / max(tot, 1) > min_share:
+            print("%4d-%4d n=%3d exec %.3e share %5.2f%% lanes %4.1f | %s" % (i, j - 1, j - i, data[i][2], 100 * s / tot, st / max(s, 1), data[i][1].strip()[:60]))
+        i = j
+    print("SASS instructions %d, warp instructions %.3e (kernel total %.3e)" % (len(data), tot, total_w))
+
+
 def main():
     raw, src = sys.argv[1], sys.argv[2]
     nlines = int(sys.argv[3]) if len(sys.argv) > 3 else 30
@@ -34,6 +54,9 @@ def main():
             print("  %-24s %s" % (h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")], d[h][0]))
     total_w = fl(d["smsp__inst_executed.sum"][0])
     rows = list(csv.reader(open(src)))
+    if len(rows) > 2 and rows[1] and rows[1][0] == "Address":
+        sass_regions(rows, total_w)
+        return
     hidx = [i for i, r in enumerate(rows) if r and r[0] == "Line No"]
     allrows = []
     for h in hidx:
