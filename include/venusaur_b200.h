@@ -61,7 +61,9 @@ enum {
     VN_NO_TONEMAP     = 1u << 3, /* do not write params.image */
     VN_WAVEFRONT      = 1u << 4, /* use the queue-based wavefront kernels instead of the persistent path kernel */
     VN_COUNTERS       = 1u << 5, /* instrumented launch: also count BVH node visits and sphere tests */
-    VN_ASYNC          = 1u << 6, /* do not synchronise the stream before returning (stats are then stale) */
+    VN_ASYNC          = 1u << 6, /* do not synchronise the stream before returning (stats are then stale).  With VN_IMAGE_HOST the
+                                    frame's D2H copy is pipelined on a second stream under the next vn_render's kernel: the host buffer
+                                    is complete after vn_synchronize (or two vn_render calls later); alternate between two host buffers */
     VN_POOL           = 1u << 8, /* use the shared-memory warp-pool wavefront kernel (pool_kernels.cu) */
     VN_SLOTS          = 1u << 9, /* use the slot-scheduled path kernel (slot_kernels.cu) when the scene qualifies (4-wide nodes in
                                     shared memory); otherwise the persistent kernel runs */

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 import venusaur_b200 as vb
-from venusaur_b200 import (VN_ACCUM_SUM, VN_COUNTERS, VN_EXACT, VN_FAST, VN_IMAGE_HOST, VN_NO_TONEMAP, VN_PERSISTENT, VN_POOL, VN_SLOTS,
+from venusaur_b200 import (VN_ACCUM_SUM, VN_ASYNC, VN_COUNTERS, VN_EXACT, VN_FAST, VN_IMAGE_HOST, VN_NO_TONEMAP, VN_PERSISTENT, VN_POOL, VN_SLOTS,
                            VN_WAVEFRONT)
 
 pytestmark = pytest.mark.gpu
@@ -494,6 +494,30 @@ def test_renderer_draw_progressive_accumulation(oracle_mod, rtiow):
     assert np.array_equal(r2.ctx.read_accum().view(np.uint32), want.view(np.uint32))
     r.Cleanup()
     r2.Cleanup()
+
+
+def test_pipelined_host_frames(rtiow_ctx):
+    """VN_IMAGE_HOST | VN_ASYNC: the D2H copy of frame k runs on a second stream under the kernel of frame k+1 (two
+    staging buffers).  After vn_synchronize every frame is what the synchronous call delivers."""
+    W, H, spp, depth = 320, 180, 4, 50
+    cam = vb.rtiow_camera(W, H)
+    want = []
+    rtiow_ctx.resize(W, H)
+    for k in range(5):
+        img = np.zeros((H, W, 4), np.uint8)
+        rtiow_ctx.render(rtiow_ctx.make_params(cam, W, H, spp, k + 1, depth, accum_count=k, image=ptr(img), flags=VN_IMAGE_HOST))
+        want.append(img)
+    acc_sync = rtiow_ctx.read_accum()
+    rtiow_ctx.reset_accum()
+    rtiow_ctx.reset_stats()
+    got = [np.zeros((H, W, 4), np.uint8) for _ in range(5)]
+    for k in range(5):
+        rtiow_ctx.render(rtiow_ctx.make_params(cam, W, H, spp, k + 1, depth, accum_count=k, image=ptr(got[k]), flags=VN_IMAGE_HOST | VN_ASYNC))
+    rtiow_ctx.synchronize()
+    assert np.array_equal(rtiow_ctx.read_accum().view(np.uint32), acc_sync.view(np.uint32))
+    for k in range(5):
+        assert np.array_equal(got[k], want[k]), "frame %d" % k
+    assert rtiow_ctx.stats().segments_total > 5 * W * H * spp
 
 
 def test_row_tiles_and_partial_sums(rtiow_ctx):

@@ -42,6 +42,13 @@ struct vn_context {
     float4* accum = nullptr;          // own or external
     uint32_t* image_tmp = nullptr;    // device staging for VN_IMAGE_HOST
     uint64_t image_tmp_pixels = 0;
+    // VN_IMAGE_HOST | VN_ASYNC: frame k's D2H runs on its own stream under frame k+1's kernel (two staging buffers)
+    uint32_t* image_pipe[2] = {nullptr, nullptr};
+    uint64_t image_pipe_pixels = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_frame[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    bool copied_valid[2] = {false, false};
+    int pipe_flip = 0;
 
     unsigned long long* d_counters = nullptr;   // 4 x u64 + work ticket (u32) at +32 bytes; [8..22) scheduler statistics of the slot kernel
     unsigned long long* h_counters = nullptr;   // pinned
@@ -210,6 +217,11 @@ int vn_create(int device, vn_handle* out) {
     c->smem_optin = prop.sharedMemPerBlockOptin;
     VN_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto& ev : c->ev) VN_CUDA(c, cudaEventCreate(&ev));
+    VN_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        VN_CUDA(c, cudaEventCreateWithFlags(&c->ev_frame[i], cudaEventDisableTiming));
+        VN_CUDA(c, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+    }
     VN_CUDA(c, cudaMalloc(&c->d_counters, 256));
     VN_CUDA(c, cudaMemset(c->d_counters, 0, 256));
     VN_CUDA(c, cudaHostAlloc(&c->h_counters, 256, cudaHostAllocDefault));
@@ -221,12 +233,15 @@ void vn_destroy(vn_handle c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     lbvh_free(c->scene);
     lbvh_workspace_free(c->bvh_ws);
     free_wavefront(c->wf); c->wf_sample_floats_ = 0;
     cudaFree(c->d_spheres); cudaFree(c->accum_own); cudaFree(c->image_tmp); cudaFree(c->d_counters);
     cudaFreeHost(c->h_counters);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    for (int i = 0; i < 2; i++) { cudaFree(c->image_pipe[i]); if (c->ev_frame[i]) cudaEventDestroy(c->ev_frame[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -436,12 +451,34 @@ static int collect_render_stats(vn_context* c) {
     return VN_OK;
 }
 
-int vn_synchronize(vn_handle c) {
-    VN_REQUIRE(c, c, "vn_synchronize: NULL handle");
-    VN_CUDA(c, cudaSetDevice(c->device));
+// kernels of the last vn_render done (statistics readable); pipelined frame copies may still be in flight
+static int sync_kernels(vn_context* c) {
     VN_CUDA(c, cudaStreamSynchronize(c->stream));
     VN_CUDA(c, cudaGetLastError());
     if (c->stats_pending) return collect_render_stats(c);
+    return VN_OK;
+}
+
+int vn_synchronize(vn_handle c) {
+    VN_REQUIRE(c, c, "vn_synchronize: NULL handle");
+    VN_CUDA(c, cudaSetDevice(c->device));
+    const int rc = sync_kernels(c);
+    if (rc != VN_OK) return rc;
+    VN_CUDA(c, cudaStreamSynchronize(c->copy_stream));     // VN_IMAGE_HOST | VN_ASYNC frames have landed in host memory
+    return VN_OK;
+}
+
+static int ensure_image_pipe(vn_context* c, uint64_t pixels) {
+    if (c->image_pipe_pixels >= pixels && c->image_pipe[0]) return VN_OK;
+    VN_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+    for (int i = 0; i < 2; i++) {
+        cudaFree(c->image_pipe[i]);
+        c->image_pipe[i] = nullptr;
+        c->copied_valid[i] = false;
+    }
+    c->image_pipe_pixels = 0;
+    for (int i = 0; i < 2; i++) VN_CUDA(c, cudaMalloc(&c->image_pipe[i], pixels * 4));
+    c->image_pipe_pixels = pixels;
     return VN_OK;
 }
 
@@ -522,14 +559,18 @@ int vn_render(vn_handle c, const vn_params* p) {
     RenderLaunch L;
     fill_launch(c, p, L);
     if (want_image) {
-        if (host_image) { const int rc = ensure_image_tmp(c, pixels); if (rc != VN_OK) return rc; L.image = c->image_tmp; }
+        if (host_image && (p->flags & VN_ASYNC)) { const int rc = ensure_image_pipe(c, pixels); if (rc != VN_OK) return rc; L.image = c->image_pipe[c->pipe_flip]; }
+        else if (host_image) { const int rc = ensure_image_tmp(c, pixels); if (rc != VN_OK) return rc; L.image = c->image_tmp; }
         else L.image = static_cast<uint32_t*>(p->image);
     }
     const bool exact_build = !(p->flags & VN_FAST);
     const bool count = (p->flags & VN_COUNTERS) != 0;
     uint32_t launches = 0;
 
-    if (c->stats_pending) { const int rc = vn_synchronize(c); if (rc != VN_OK) return rc; }
+    const bool pipelined = host_image && (p->flags & VN_ASYNC);
+    if (c->stats_pending) { const int rc = sync_kernels(c); if (rc != VN_OK) return rc; }
+    // the staging buffer of this frame was last read by the copy of two frames ago
+    if (pipelined && c->copied_valid[c->pipe_flip]) VN_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[c->pipe_flip], 0));
     VN_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 256, c->stream));
     VN_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
     if (p->flags & VN_WAVEFRONT) {
@@ -615,12 +656,23 @@ int vn_render(vn_handle c, const vn_params* p) {
         }
     }
     VN_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
-    if (host_image) VN_CUDA(c, cudaMemcpyAsync(p->image, c->image_tmp, pixels * 4, cudaMemcpyDeviceToHost, c->stream));
+    // (the 256-byte statistics copy goes first: queued behind the frame on the D2H engine it would delay the next launch)
     VN_CUDA(c, cudaMemcpyAsync(c->h_counters, c->d_counters, 256, cudaMemcpyDeviceToHost, c->stream));
+    if (pipelined) {
+        const int f = c->pipe_flip;
+        VN_CUDA(c, cudaEventRecord(c->ev_frame[f], c->stream));
+        VN_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_frame[f], 0));
+        VN_CUDA(c, cudaMemcpyAsync(p->image, c->image_pipe[f], pixels * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+        VN_CUDA(c, cudaEventRecord(c->ev_copied[f], c->copy_stream));
+        c->copied_valid[f] = true;
+        c->pipe_flip = f ^ 1;
+    } else if (host_image) {
+        VN_CUDA(c, cudaMemcpyAsync(p->image, c->image_tmp, pixels * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
     c->stats.kernel_launches = launches;
     c->stats.kernel_launches_total += launches;
     c->stats_pending = true;
-    if (!(p->flags & VN_ASYNC) || host_image) {
+    if (!(p->flags & VN_ASYNC)) {
         VN_CUDA(c, cudaStreamSynchronize(c->stream));
         VN_CUDA(c, cudaGetLastError());
         return collect_render_stats(c);
