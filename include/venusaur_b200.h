@@ -130,7 +130,12 @@ VN_API const char* vn_version(void);
 
 /* ---- scene: Renderer::CreateSBT (Renderer.h:452-520) + BuildAccelerationStructures (Renderer.h:160-255) ---- */
 VN_API int vn_set_spheres(vn_handle h, const vn_sphere* host_spheres, uint64_t n);
-VN_API int vn_set_option(vn_handle h, const char* name, double value); /* "leaf_size", "aabb_pad", "threads", "blocks_per_sm", "pool_slots", "pool_threads", "pool_service", "pool_leaf_batch", ... */
+/* Tuning knobs (defaults in brackets).  BVH: "leaf_size" [0 = auto], "aabb_pad" [0.01], "sah_max_prims" [4096: SAH splits up to this size],
+ * "wide_max_prims" [16384: 4-wide nodes up to this size].  Path kernel: "wide_nodes" [1], "octant_nodes" [1], "leaf_vote" [12: lanes waiting
+ * at a leaf that trigger the warp's leaf turn, 0 = while-while], "wide_global" [0], "threads", "blocks_per_sm", "smem_scene_limit".
+ * Experimental kernels: "slot_kernel" [0], "slot_slots", "slot_threads", "slot_tn|tl|tw|ts|tr"; "pool_slots", "pool_threads", "pool_service",
+ * "pool_leaf_batch"; "wavefront_slots".  Options that change the BVH invalidate it (call vn_build_bvh again). */
+VN_API int vn_set_option(vn_handle h, const char* name, double value);
 VN_API int vn_build_bvh(vn_handle h);
 VN_API int vn_get_bvh_info(vn_handle h, vn_bvh_info* out);
 VN_API int vn_read_bvh(vn_handle h, vn_node32* host_nodes, uint64_t cap_nodes, uint32_t* host_prim_order, uint64_t cap_prims);
