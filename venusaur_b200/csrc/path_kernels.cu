@@ -345,8 +345,10 @@ inline uint32_t grid_for(uint64_t n, int threads) { return (uint32_t)((n + threa
 
 namespace {
 typedef void (*PathKernel)(const RenderLaunch);
-PathKernel pick_kernel(bool scene_in_smem, bool count, bool octant, bool wide = false) {
+PathKernel pick_kernel(bool scene_in_smem, bool count, bool octant, bool wide = false, int threads = 1024) {
     if (wide && !scene_in_smem) return count ? k_render_persistent<false, true, false, 256, true> : k_render_persistent<false, false, false, 256, true>;
+    if (wide && threads <= 512) return count ? k_render_persistent<true, true, false, 512, true> : k_render_persistent<true, false, false, 512, true>;
+    if (wide && threads <= 768) return count ? k_render_persistent<true, true, false, 768, true> : k_render_persistent<true, false, false, 768, true>;
     if (wide) return count ? k_render_persistent<true, true, false, 1024, true> : k_render_persistent<true, false, false, 1024, true>;
     if (scene_in_smem && octant) return count ? k_render_persistent<true, true, true, 1024> : k_render_persistent<true, false, true, 1024>;
     if (scene_in_smem) return count ? k_render_persistent<true, true, false, 256> : k_render_persistent<true, false, false, 256>;
@@ -356,14 +358,14 @@ PathKernel pick_kernel(bool scene_in_smem, bool count, bool octant, bool wide = 
 
 int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool count, bool octant, bool wide) {
     int nb = 0;
-    PathKernel k = pick_kernel(scene_in_smem, count, octant, wide);
+    PathKernel k = pick_kernel(scene_in_smem, count, octant, wide, threads);
     if (smem_bytes > 48 * 1024 && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) return -1;
     const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, threads, smem_bytes);
     return e == cudaSuccess ? nb : -1;
 }
 
 cudaError_t launch_render_persistent(const RenderLaunch& p, const KernelConfig& cfg, cudaStream_t stream) {
-    PathKernel k = pick_kernel(cfg.scene_in_smem, cfg.count, cfg.octant, cfg.wide);
+    PathKernel k = pick_kernel(cfg.scene_in_smem, cfg.count, cfg.octant, cfg.wide, cfg.threads);
     if (cfg.smem_bytes > 48 * 1024) {
         const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes);
         if (e != cudaSuccess) return e;

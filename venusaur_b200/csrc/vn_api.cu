@@ -66,6 +66,7 @@ struct vn_context {
     bool slot_kernel = false;         // default path kernel for wide-node scenes: slot-scheduled (slot_kernels.cu) instead of k_render_persistent
     int slot_slots = 3, slot_threads = 768;
     SlotTune slot_tune{20u, 12u, 8u, 20u, 20u};
+    int wide_threads = 1024;          // CTA size of the wide-node path kernel (one CTA per SM): 512, 768 or 1024
     uint32_t leaf_vote = 12;          // see closest_hit_wide_vote (path_kernels.cu); 0 = while-while
     bool wide_nodes = true;           // use them when they fit in shared memory
     uint32_t sah_max_prims = 4096;    // scenes up to this size get SAH splits (k_sah_small); 0 = always Karras
@@ -261,6 +262,7 @@ int vn_set_option(vn_handle c, const char* name, double value) {
     else if (k == "wide_max_prims") { VN_REQUIRE(c, value >= 0 && value <= (double)(1u << 28), "wide_max_prims must be in [0,2^28]"); c->wide_max_prims = (uint32_t)value; c->bvh_valid = false; }
     else if (k == "wide_nodes") { c->wide_nodes = value != 0; }
     else if (k == "wide_global") { c->wide_global = value != 0; }
+    else if (k == "wide_threads") { VN_REQUIRE(c, value == 512 || value == 768 || value == 1024, "wide_threads must be 512, 768 or 1024"); c->wide_threads = (int)value; }
     else if (k == "leaf_vote") { VN_REQUIRE(c, value >= 0 && value <= 32, "leaf_vote must be in [0,32]"); c->leaf_vote = (uint32_t)value; }
     else if (k == "slot_kernel") { c->slot_kernel = value != 0; }
     else if (k == "slot_slots" || k == "slot_threads") {
@@ -319,8 +321,12 @@ int vn_build_bvh(vn_handle c) {
     int rc = 0;
     for (uint32_t leaf_size = c->leaf_size ? c->leaf_size : (small ? 1u : 2u);; leaf_size++) {
         rc = lbvh_build(c->d_spheres, c->n_spheres, leaf_size, c->aabb_pad, c->sah_max_prims, c->wide_max_prims, c->num_sms, c->stream, c->scene, c->bvh_ws, &launches, err);
-        if (rc != 0 || c->leaf_size || !small || leaf_size >= 4u) break;
+        if (rc != 0 || c->leaf_size || !small) break;
         if (c->scene.num_wide > 0 && c->scene.wide_levels <= kWideMaxLevels && wide_smem_bytes(c->scene.num_wide, (uint32_t)c->scene.n) + 2048 <= c->smem_optin) break;
+        if (leaf_size >= 4u) {      // the wide copies never fit: the pair nodes will be traversed, which like 3 spheres per leaf best
+            rc = lbvh_build(c->d_spheres, c->n_spheres, 3u, c->aabb_pad, c->sah_max_prims, c->wide_max_prims, c->num_sms, c->stream, c->scene, c->bvh_ws, &launches, err);
+            break;
+        }
     }
     if (rc != 0) return fail(c, rc == -1 ? VN_ERR_INVALID : VN_ERR_CUDA, "vn_build_bvh: " + err);
     VN_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
@@ -631,7 +637,7 @@ int vn_render(vn_handle c, const vn_params* p) {
         cfg.wide = c->wide_nodes && L.wide && L.num_wide > 0 && c->scene.wide_levels <= kWideMaxLevels && wide_bytes + 2048 <= c->smem_optin;
         // scenes too large for shared memory: the canonical wide nodes straight from L2/HBM (half the dependent fetches)
         const bool wide_global = !cfg.wide && !cfg.scene_in_smem && c->wide_global && c->wide_nodes && L.wide && L.num_wide > 0 && c->scene.wide_levels <= kWideGlobalMaxLevels;
-        if (cfg.wide) { cfg.scene_in_smem = true; cfg.octant = false; cfg.smem_bytes = wide_bytes; cfg.threads = 1024; }
+        if (cfg.wide) { cfg.scene_in_smem = true; cfg.octant = false; cfg.smem_bytes = wide_bytes; cfg.threads = c->wide_threads; }
         else if (wide_global) { cfg.wide = true; cfg.octant = false; if (cfg.threads > 256) cfg.threads = 256; }
         else if (cfg.octant) { cfg.smem_bytes = oct_bytes; cfg.threads = 1024; }
         else if (cfg.threads > 256) cfg.threads = 256;
