@@ -179,6 +179,55 @@ def test_lbvh_large_build_invariants(ctx, oracle_mod):
     assert ctx.bvh_info().scene_in_smem == 0
 
 
+def test_config5_scale_build_and_render(ctx):
+    """BASELINE configs[4] scale: 16 M spheres, 50 % dielectric (576 MB upload, ~0.7 GB of nodes).  Size-independent
+    properties: sorted Morton codes, every sphere in exactly one leaf, root box = scene box; a small depth-64 render is
+    deterministic, traces more than one segment per path and writes an opaque, non-black image."""
+    n = 16_000_000
+    spheres = vb.random_scene(n, 0x5EED0002, 250.0, 1)
+    ctx.set_spheres(spheres)
+    ctx.build_bvh()
+    codes = ctx.morton_codes()
+    assert (np.diff(codes.astype(np.int64)) >= 0).all()
+    del codes
+    nodes, order = ctx.read_bvh()
+    seen = np.zeros(n, np.uint8)
+    seen[order] = 1
+    assert int(seen.sum()) == n
+    r = np.abs(spheres["r"])
+    lo = np.array([(spheres[a] - r).min() for a in ("cx", "cy", "cz")])
+    hi = np.array([(spheres[a] + r).max() for a in ("cx", "cy", "cz")])
+    assert (nodes[1]["lo"] <= lo).all() and (nodes[1]["hi"] >= hi).all() and int(nodes[1]["aux"]) == n
+    leaves = nodes[2:][(nodes[2:]["link"] & 0x80000000) != 0]
+    assert int(leaves["aux"].sum()) == n
+    print("LBVH build 16M spheres: %.2f ms" % ctx.stats().ms_build)
+    del nodes, order, leaves, seen
+    W, H, spp = 256, 144, 4
+    cam = vb.Camera((0.0, 0.0, 500.0), 40.0, W / H, 0.0, 500.0)
+    cam.SetForward((0.0, 0.0, -1.0))
+    a, ia, sa = render(ctx, cam, W, H, spp, 1, 64)
+    b, ib, sb = render(ctx, cam, W, H, spp, 1, 64)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(ia, ib) and sa.segments == sb.segments
+    assert sa.paths == W * H * spp and sa.segments > 1.5 * sa.paths
+    assert ia[..., 3].min() == 255 and ia[..., :3].max() > 0 and np.isfinite(a).all()
+
+
+def test_config3_frame_row_shards_equal_full_frame(rtiow_ctx):
+    """BASELINE configs[2] frame size (3840x2160): rendering the frame as eight row shards (the second sharding axis of the
+    multi-GPU plan) gives bit for bit the full-frame accumulation buffer and the same segment count."""
+    W, H, spp, depth = 3840, 2160, 1, 50
+    cam = vb.rtiow_camera(W, H)
+    full, _, sf = render(rtiow_ctx, cam, W, H, spp, 9, depth, image=False)
+    rtiow_ctx.reset_accum()
+    segs = 0
+    for r in range(8):
+        rows = (r * H // 8, (r + 1) * H // 8)
+        rtiow_ctx.render(rtiow_ctx.make_params(cam, W, H, spp, 9, depth, flags=VN_NO_TONEMAP, rows=rows))
+        segs += rtiow_ctx.stats().segments
+    tiled = rtiow_ctx.read_accum()
+    assert segs == sf.segments and np.array_equal(full.view(np.uint32), tiled.view(np.uint32))
+
+
 # ------------------------------------------------------------------ traversal = brute force
 @pytest.mark.parametrize("scene_name", ["rtiow", "random20k"])
 def test_traversal_equals_brute_force(ctx, oracle_mod, rtiow, scene_name):
