@@ -264,6 +264,7 @@ def run_ours(args):
     ctx.render(ctx.make_params(cam, width, height, spp, 1, depth, flags=VN_COUNTERS | VN_NO_TONEMAP | (VN_FAST if args.fast else 0) | (VN_SLOTS if args.kernel == "slots" else 0)))
     cst = ctx.stats()
     sched = ctx.sched_counters() if args.kernel == "slots" else None
+    accel = ctx.last_accel() if args.kernel == "persistent" else 0      # 1 pair nodes, 2 wide nodes, 3 wide nodes from L2/HBM, 4 grid
     v_node = cst.node_visits / max(1, cst.segments)
     v_sphere = cst.sphere_tests / max(1, cst.segments)
 
@@ -361,8 +362,11 @@ def run_ours(args):
         # with V_node / V_sphere measured by the instrumented kernel on this very workload.
         # Coefficients: pair nodes = SURVEY's budget; 4-wide nodes = SASS counts of the shipped kernel (node step 83 instructions,
         # one sphere test ~60 incl. its share of IEEE sqrt/div, shade + RNG + camera ~270 per segment; profiles/).
-        wide = bool(info.scene_in_smem) and "wide_nodes=0" not in args.opt and len(ctx.read_wide_bvh()[0]) > 0 and v_node < 8.0
-        i_seg = (83.0 * v_node + 60.0 * v_sphere + 270.0) if wide else (40.0 * v_node + 30.0 * v_sphere + 150.0)
+        wide = accel == 2
+        if accel == 4:      # uniform grid + oversize list: V_node = cell steps (25 instructions each incl. the vote), 45 per sphere test,
+            i_seg = 25.0 * v_node + 45.0 * v_sphere + 300.0      # + shade / RNG / camera / ray-box clip and DDA set-up
+        else:
+            i_seg = (83.0 * v_node + 60.0 * v_sphere + 270.0) if wide else (40.0 * v_node + 30.0 * v_sphere + 150.0)
         f_clk = (clk.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0) * 1e6
         peak_tinst = 32 * 4 * n_sm * f_clk / 1e12
         per_gpu_rate = (my_segs / (sum(step_ms) * 1e-3))
@@ -381,7 +385,7 @@ def run_ours(args):
             "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": describe(args.workload, K), "parallelism": "subframe(sample-range) sharding x%d, scene+BVH replicated" % world,
-                       "kernel": args.kernel, "build": ("VN_FAST (relaxed numerics; not within the image tolerance)" if args.fast else "default IEEE build, bit-identical to the oracle"), "l2_flush": "256 MiB fill between timed steps",
+                       "kernel": args.kernel, "accel": {0: "n/a", 1: "BVH pair nodes", 2: "BVH 4-wide octant-sorted nodes (shared memory)", 3: "BVH 4-wide nodes (L2/HBM)", 4: "uniform grid + oversize list (shared memory)"}[accel], "build": ("VN_FAST (relaxed numerics; not within the image tolerance)" if args.fast else "default IEEE build, bit-identical to the oracle"), "l2_flush": "256 MiB fill between timed steps",
                        "scene_in_smem": bool(info.scene_in_smem), "bvh_nodes": int(info.num_nodes), "leaf_size": int(info.max_leaf_size),
                        "bvh_build_ms": build_ms, "reduce": (args.reduce if world > 1 else "none"), "reduce_ms": fin_ms,
                        "sched": ({k: [v[0], round(v[1], 2)] for k, v in sched.items()} if sched else None)},
@@ -396,7 +400,7 @@ def run_ours(args):
                          "frac": achieved_tinst / peak_tinst, "traffic": prof.get("dram_bytes_per_launch"),
                          "model": "I_seg = %s = %.0f thread-instructions/segment (V_node=%.2f, V_sphere=%.2f measured); "
                                   "peak = 32 lanes x 4 schedulers x %d SMs x %.0f MHz (median SM clock during the run)"
-                                  % ("83*V_node + 60*V_sphere + 270 (4-wide nodes)" if wide else "40*V_node + 30*V_sphere + 150 (pair nodes)", i_seg, v_node, v_sphere, n_sm, f_clk / 1e6),
+                                  % ("25*V_cell + 45*V_sphere + 300 (uniform grid + oversize list)" if accel == 4 else "83*V_node + 60*V_sphere + 270 (4-wide nodes)" if wide else "40*V_node + 30*V_sphere + 150 (pair nodes)", i_seg, v_node, v_sphere, n_sm, f_clk / 1e6),
                          "measured_inst_per_segment": prof.get("thread_inst_per_segment"),
                          "issue_slot_utilisation_ncu": prof.get("issue_slot_utilisation")},
             "roofline_hbm": {"bound": "hbm", "achieved": algo_bytes / (mean_step_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",

@@ -67,6 +67,7 @@ enum {
     VN_POOL           = 1u << 8, /* use the shared-memory warp-pool wavefront kernel (pool_kernels.cu) */
     VN_SLOTS          = 1u << 9, /* use the slot-scheduled path kernel (slot_kernels.cu) when the scene qualifies (4-wide nodes in
                                     shared memory); otherwise the persistent kernel runs */
+    VN_GRID           = 1u << 11, /* vn_trace_rays only: query the uniform grid + oversize list instead of the BVH */
     VN_PERSISTENT     = 1u << 10, /* force k_render_persistent even when the "slot_kernel" option makes the slot kernel the default */
     VN_FAST           = 1u << 7  /* relaxed-numerics build (FMA contraction, approximate rcp/rsqrt/sqrt, FP32 for the FP64
                                     fragments): a few % faster, PSNR > 60 dB vs the oracle but NOT within the 1e-3 per-pixel
@@ -131,7 +132,7 @@ VN_API const char* vn_version(void);
 /* ---- scene: Renderer::CreateSBT (Renderer.h:452-520) + BuildAccelerationStructures (Renderer.h:160-255) ---- */
 VN_API int vn_set_spheres(vn_handle h, const vn_sphere* host_spheres, uint64_t n);
 /* Tuning knobs (defaults in brackets).  BVH: "leaf_size" [0 = auto], "aabb_pad" [0.01], "sah_max_prims" [4096: SAH splits up to this size],
- * "wide_max_prims" [16384: 4-wide nodes up to this size].  Path kernel: "wide_nodes" [1], "octant_nodes" [1], "leaf_vote" [12: lanes waiting
+ * "wide_max_prims" [16384: 4-wide nodes up to this size], "accel" [0 = auto: grid when the scene suits it, 1 = BVH, 2 = grid], "grid_max_per_cell" [16].  Path kernel: "wide_nodes" [1], "octant_nodes" [1], "leaf_vote" [12: lanes waiting
  * at a leaf that trigger the warp's leaf turn, 0 = while-while], "wide_global" [0], "threads", "blocks_per_sm", "smem_scene_limit".
  * Experimental kernels: "slot_kernel" [0], "slot_slots", "slot_threads", "slot_tn|tl|tw|ts|tr"; "pool_slots", "pool_threads", "pool_service",
  * "pool_leaf_batch"; "wavefront_slots".  Options that change the BVH invalidate it (call vn_build_bvh again). */
@@ -139,6 +140,12 @@ VN_API int vn_set_option(vn_handle h, const char* name, double value);
 VN_API int vn_build_bvh(vn_handle h);
 VN_API int vn_get_bvh_info(vn_handle h, vn_bvh_info* out);
 VN_API int vn_read_bvh(vn_handle h, vn_node32* host_nodes, uint64_t cap_nodes, uint32_t* host_prim_order, uint64_t cap_prims);
+/* Second closest-hit structure for small scenes (<= 16384 spheres of similar size plus at most 8 oversize ones): a uniform grid over the
+ * Morton-sorted spheres + a list of oversize spheres every ray tests first.  Returns 1 and fills header104 = { float lo[3], inv_cell[3],
+ * cell[3], hi[3]; uint32 res[3], n_cells, n_refs, n_big, big[8] }, start[n_cells + 1], refs[n_refs] (sorted sphere indices); 0 when the
+ * scene has no grid ("accel" = 1, or it does not suit the structure). */
+VN_API int vn_read_grid(vn_handle h, void* header104, uint16_t* host_start, uint64_t cap_start, uint16_t* host_refs, uint64_t cap_refs);
+VN_API int vn_last_accel(vn_handle h);   /* what the last vn_render traversed: 1 pair nodes, 2 wide nodes, 3 wide nodes from L2/HBM, 4 grid */
 /* 4-wide nodes derived from the pairs for scenes traversed out of shared memory (<= "wide_max_prims" spheres): 128 B per
  * node = 4 x { {lo.xyz, link}, {hi.xyz, count} }; link = wide-node index, a leaf link as above, or 0xFFFFFFFF (empty slot).
  * num_nodes_out = 0 when the scene has none. */

@@ -33,7 +33,7 @@ def host_harness():
     os.makedirs(out, exist_ok=True)
     lib = os.path.join(out, "libhost_harness.so")
     srcs = [os.path.join(ROOT, "tests", "host_harness.cpp"), os.path.join(ROOT, "venusaur_b200", "csrc", "vn_math.cuh"),
-            os.path.join(ROOT, "venusaur_b200", "csrc", "lbvh_core.cuh")]
+            os.path.join(ROOT, "venusaur_b200", "csrc", "lbvh_core.cuh"), os.path.join(ROOT, "venusaur_b200", "csrc", "grid_core.cuh")]
     if not os.path.exists(lib) or any(os.path.getmtime(s) > os.path.getmtime(lib) for s in srcs):
         subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-I" + os.path.join(ROOT, "venusaur_b200", "csrc"),
                         "-o", lib, srcs[0]], check=True)
@@ -47,6 +47,9 @@ def host_harness():
     h.hh_render_mean.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     h.hh_set_oct.argtypes = [C.c_int]
     h.hh_set_wide.argtypes = [C.c_int]
+    h.hh_set_grid.argtypes = [C.c_int]
+    h.hh_build_grid.restype = C.c_int
+    h.hh_build_grid.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
     h.hh_set_sah_max.argtypes = [C.c_uint32]
     h.hh_build_wide.restype = C.c_uint64
     h.hh_build_wide.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_void_p, C.c_uint64, C.c_void_p]

@@ -6,6 +6,7 @@
 // g++ -O2 -std=c++17 -ffp-contract=off -fPIC -shared -Ivenusaur_b200/csrc tests/host_harness.cpp
 #define VN_EXACT 1
 #include "lbvh_core.cuh"
+#include "grid_core.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -23,6 +24,7 @@ struct hh_params {
 
 static uint32_t g_sah_max = 4096;   // same default as the library's "sah_max_prims" option
 static int g_use_oct = 0;
+static int g_use_grid = 0;         // hh_set_grid(1): closest hit through the uniform grid + oversize list
 static int g_use_wide = 0;         // hh_set_wide(2): canonical wide nodes with distance sort (closest_hit_wide_global); hh_set_wide(1): traverse the 4-wide octant-sorted nodes like k_render_persistent<.., kWide>
 static int g_seq_postpone = 0;   // hh_set_oct(1): traverse octant-mirrored node copies like k_render_persistent<.., kOct=true>
 
@@ -36,6 +38,9 @@ struct HostBvh {
     std::vector<node_f4> wide;        // canonical 4-wide nodes (8 float4 each), BFS order
     std::vector<node_f4> wide_oct;    // 8 octant-specialised copies (7 float4 per node)
     uint32_t wide_root = kEmptyScene, wide_levels = 0;
+    GridHeader grid;                  // uniform grid + oversize list (grid_core.cuh); grid_ok = the scene suits it
+    bool grid_ok = false;
+    std::vector<uint16_t> grid_start, grid_refs;
 };
 
 // Sequential emulation of k_sah_small (lbvh.cu): same per-element functions, same level-by-level order.
@@ -139,6 +144,32 @@ static void build_wide(HostBvh& B) {
     B.wide_oct.resize(8 * 7 * W);
     for (uint32_t k = 0; k < 8; k++)
         for (size_t j = 0; j < W; j++) wide_octant_node(&B.wide[8 * j], k, &B.wide_oct[(k * W + j) * 7]);
+}
+
+// Sequential emulation of grid_build (grid.cu): header on the host (the product computes it there too), then count / scan /
+// fill with every cell's references in ascending sphere order.
+static void build_grid(HostBvh& B) {
+    B.grid_ok = false; B.grid_start.clear(); B.grid_refs.clear();
+    const uint32_t n = (uint32_t)B.geom.size();
+    if (!grid_make_header(B.geom.data(), n, B.grid)) return;
+    GridHeader& g = B.grid;
+    std::vector<std::vector<uint32_t>> cells(g.n_cells);
+    for (uint32_t i = 0; i < n; i++) {
+        if (grid_is_big(g, i)) continue;
+        int c0[3], c1[3];
+        grid_sphere_cells(g, B.geom[i], c0, c1);
+        for (int z = c0[2]; z <= c1[2]; z++) for (int y = c0[1]; y <= c1[1]; y++) for (int x = c0[0]; x <= c1[0]; x++)
+            cells[grid_cell_index(g, x, y, z)].push_back(i);
+    }
+    size_t refs = 0;
+    for (auto& c : cells) refs += c.size();
+    if (refs > kGridMaxRefs) return;
+    g.n_refs = (uint32_t)refs;
+    B.grid_start.resize(g.n_cells + 1);
+    size_t off = 0;
+    for (uint32_t c = 0; c < g.n_cells; c++) { B.grid_start[c] = (uint16_t)off; for (uint32_t i : cells[c]) B.grid_refs.push_back((uint16_t)i); off += cells[c].size(); }
+    B.grid_start[g.n_cells] = (uint16_t)off;
+    B.grid_ok = true;
 }
 
 static void build(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pad_rel, HostBvh& B) {
@@ -258,11 +289,13 @@ static void build(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pad_
             B.nodes_oct[k * B.nodes.size() + 2 * j + 1] = fr;
         }
     build_wide(B);
+    build_grid(B);
 }
 
 template <bool kCount>
 static inline void hh_closest(const HostBvh& B, f3 o, f3 d, float& t, int& prim, TraceCounters& cnt) {
-    if (g_use_wide == 2 && B.wide_levels <= kWideGlobalMaxLevels) closest_hit_wide_global<kCount>(B.wide.data(), B.geom.data(), B.wide_root, o, d, t, prim, cnt);
+    if (g_use_grid && B.grid_ok) closest_hit_grid<kCount>(B.grid, B.grid_start.data(), B.grid_refs.data(), B.geom.data(), o, d, t, prim, cnt);
+    else if (g_use_wide == 2 && B.wide_levels <= kWideGlobalMaxLevels) closest_hit_wide_global<kCount>(B.wide.data(), B.geom.data(), B.wide_root, o, d, t, prim, cnt);
     else if (g_use_wide && B.wide_levels <= kWideMaxLevels && !B.wide_oct.empty()) closest_hit_wide<kCount>(B.wide_oct.data(), (uint32_t)(B.wide_oct.size() / 8), B.geom.data(), B.wide_root, o, d, t, prim, cnt);
     else if (g_use_oct) closest_hit<kCount, true>(B.nodes_oct.data(), B.geom.data(), B.root_link, o, d, t, prim, cnt, (uint32_t)B.nodes.size());
     else closest_hit<kCount, false>(B.nodes.data(), B.geom.data(), B.root_link, o, d, t, prim, cnt);
@@ -272,6 +305,18 @@ extern "C" {
 
 void hh_set_oct(int on) { g_use_oct = on; }
 void hh_set_wide(int on) { g_use_wide = on; }
+void hh_set_grid(int on) { g_use_grid = on; }
+// grid of the host build: header (80 bytes), start[n_cells + 1], refs[n_refs]; returns 1 when the scene suits the structure
+int hh_build_grid(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pad_rel, void* header_out, uint16_t* start_out, uint64_t cap_start,
+                  uint16_t* refs_out, uint64_t cap_refs) {
+    HostBvh B;
+    build(s, n, leaf_size, pad_rel, B);
+    if (!B.grid_ok) return 0;
+    if (header_out) memcpy(header_out, &B.grid, sizeof(GridHeader));
+    if (start_out) memcpy(start_out, B.grid_start.data(), std::min<uint64_t>(cap_start, B.grid_start.size()) * 2);
+    if (refs_out) memcpy(refs_out, B.grid_refs.data(), std::min<uint64_t>(cap_refs, B.grid_refs.size()) * 2);
+    return 1;
+}
 // canonical 4-wide nodes of the host build (8 float4 each); returns their number, *levels = breadth-first levels
 uint64_t hh_build_wide(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pad_rel, float* wide_out, uint64_t cap_nodes, uint32_t* levels) {
     HostBvh B;

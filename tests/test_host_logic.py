@@ -354,3 +354,77 @@ def test_wide_global_traversal_equals_pairs_on_cpu(host_harness, oracle_mod):
     assert np.array_equal(out[0][0], out[2][0]) and np.array_equal(out[0][1], out[2][1])
     assert (out[0][1] >= 0).sum() > 500
     assert out[2][2] < 0.6 * out[0][2] and out[2][3] < 1.05 * out[0][3]
+
+
+def _host_grid(host_harness, spheres):
+    """(header[26] uint32, start uint16, refs uint16) of the host emulation's grid, or None."""
+    hdr = np.zeros(26, np.uint32)
+    a = spheres.ctypes.data_as(C.c_void_p)
+    if not host_harness.hh_build_grid(a, len(spheres), 2, C.c_float(0.01), hdr.ctypes.data_as(C.c_void_p), None, 0, None, 0):
+        return None
+    start = np.zeros(int(hdr[15]) + 1, np.uint16)
+    refs = np.zeros(max(int(hdr[16]), 1), np.uint16)
+    host_harness.hh_build_grid(a, len(spheres), 2, C.c_float(0.01), hdr.ctypes.data_as(C.c_void_p), start.ctypes.data_as(C.c_void_p), len(start),
+                               refs.ctypes.data_as(C.c_void_p), len(refs))
+    return hdr, start, refs[:int(hdr[16])]
+
+
+def test_grid_invariants_and_traversal_on_cpu(host_harness, oracle_mod, rtiow):
+    """Uniform grid + oversize list (grid_core.cuh): RTIOW puts the ground and the three radius-1 spheres in the oversize
+    list and the 482 small ones in a one-layer grid; every small sphere is referenced by every cell its box touches, cell
+    lists are sorted; closest hits equal brute force (axis-parallel and -0 directions included); a whole render through
+    the grid is bit-identical to the oracle and needs fewer than half the traversal steps of the wide BVH."""
+    hdr, start, refs = _host_grid(host_harness, rtiow)
+    f = hdr.view(np.float32)
+    res, n_cells, n_refs, n_big = hdr[12:15], int(hdr[15]), int(hdr[16]), int(hdr[17])
+    assert n_big == 4 and int(res[1]) == 1 and n_cells == int(res[0]) * int(res[2]) and start[-1] == n_refs == len(refs)
+    assert (np.diff(start.astype(np.int64)) >= 0).all()
+    for c in range(n_cells):
+        lst = refs[start[c]:start[c + 1]]
+        assert (np.diff(lst.astype(np.int64)) > 0).all()
+    assert len(np.unique(refs)) == len(rtiow) - n_big
+    rng = np.random.RandomState(37)
+    for spheres, S in ((rtiow, 30.0), (np.ascontiguousarray(oracle_mod.random_scene(3000, 0x5EED0001, 30.0, 0)), 60.0)):
+        n = 30000
+        o = (rng.rand(n, 3).astype(np.float32) - np.float32(0.5)) * np.float32(S)
+        d = rng.randn(n, 3).astype(np.float32)
+        d[:100, 0] = 0.0
+        d[100:200, 1] = -0.0
+        d[200:300, 2] = 0.0
+        d[300:350, :2] = -0.0
+        out = {}
+        try:
+            for grid in (0, 1):
+                host_harness.hh_set_grid(grid)
+                t = np.zeros(n, np.float32)
+                p = np.zeros(n, np.int32)
+                nv, st = C.c_uint64(), C.c_uint64()
+                host_harness.hh_closest_hit(spheres.ctypes.data_as(C.c_void_p), len(spheres), 2, C.c_float(0.01), o.ctypes.data_as(C.c_void_p),
+                                            d.ctypes.data_as(C.c_void_p), n, t.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p),
+                                            C.byref(nv), C.byref(st))
+                out[grid] = (t, p)
+        finally:
+            host_harness.hh_set_grid(0)
+        assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+        t0, p0 = oracle_mod.Oracle(spheres).closest_hit(o, d, use_bvh=False)
+        assert np.array_equal(t0, out[1][0]) and np.array_equal(p0, out[1][1])
+    W, H, spp, sub, depth = 48, 27, 3, 5, 50
+    cam = oracle_mod.rtiow_camera(W, H)
+    hp = _hh_params(cam, W, H, spp, sub, depth)
+    orc = oracle_mod.Oracle(rtiow)
+    want, stats = orc.render_mean(orc.params(cam, W, H, spp, sub, depth, atten=oracle_mod.ATTEN_FORWARD, closest=oracle_mod.CLOSEST_BRUTE))
+    steps = {}
+    try:
+        for grid in (0, 1):
+            host_harness.hh_set_grid(grid)
+            host_harness.hh_set_wide(1)
+            mean = np.zeros((H, W, 4), np.float32)
+            segs, nv, st = C.c_uint64(), C.c_uint64(), C.c_uint64()
+            host_harness.hh_render_mean(rtiow.ctypes.data_as(C.c_void_p), len(rtiow), 1, C.c_float(0.01), C.byref(hp),
+                                        mean.ctypes.data_as(C.c_void_p), C.byref(segs), C.byref(nv), C.byref(st))
+            assert segs.value == stats.segments and np.array_equal(mean, want)
+            steps[grid] = nv.value / segs.value
+    finally:
+        host_harness.hh_set_grid(0)
+        host_harness.hh_set_wide(0)
+    assert steps[1] < 0.5 * steps[0]

@@ -6,7 +6,7 @@ the header-only C++17 drop-in classes in include/venusaur/.  This package is the
 """
 from .api import (Camera, Context, CUDAOutputBuffer, Exception, Renderer, Scene, random_scene, rtiow_camera,  # noqa: F401,A004
                   rtiow_final_scene)
-from ._lib import (VN_ACCUM_SUM, VN_ASYNC, VN_COUNTERS, VN_EXACT, VN_FAST, VN_IMAGE_HOST, VN_POOL, VN_SLOTS, VN_PERSISTENT, VN_NO_TONEMAP, VN_WAVEFRONT, lib_path,  # noqa: F401
+from ._lib import (VN_ACCUM_SUM, VN_ASYNC, VN_COUNTERS, VN_EXACT, VN_FAST, VN_IMAGE_HOST, VN_POOL, VN_SLOTS, VN_PERSISTENT, VN_GRID, VN_NO_TONEMAP, VN_WAVEFRONT, lib_path,  # noqa: F401
                    load)
 
 __all__ = ["Camera", "Context", "CUDAOutputBuffer", "Exception", "Renderer", "Scene", "random_scene", "rtiow_camera",

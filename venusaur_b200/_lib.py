@@ -50,7 +50,7 @@ VN_OK = 0
 VN_LAMBERTIAN, VN_METAL, VN_DIELECTRIC = 0, 1, 2
 VN_EXACT, VN_IMAGE_HOST, VN_ACCUM_SUM, VN_NO_TONEMAP = 1 << 0, 1 << 1, 1 << 2, 1 << 3
 VN_WAVEFRONT, VN_COUNTERS, VN_ASYNC, VN_FAST, VN_POOL = 1 << 4, 1 << 5, 1 << 6, 1 << 7, 1 << 8
-VN_SLOTS, VN_PERSISTENT = 1 << 9, 1 << 10
+VN_SLOTS, VN_PERSISTENT, VN_GRID = 1 << 9, 1 << 10, 1 << 11
 
 # name -> (restype, argtypes); must list every VN_API symbol of include/venusaur_b200.h (checked by tests)
 _P = C.POINTER
@@ -66,6 +66,8 @@ SIGNATURES = {
     "vn_get_bvh_info": (C.c_int, [C.c_void_p, _P(vn_bvh_info)]),
     "vn_read_bvh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
     "vn_read_sched_counters": (C.c_int, [C.c_void_p, _P(C.c_uint64)]),
+    "vn_read_grid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
+    "vn_last_accel": (C.c_int, [C.c_void_p]),
     "vn_read_wide_bvh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, _P(C.c_uint32), _P(C.c_uint32)]),
     "vn_resize": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "vn_reset_accum": (C.c_int, [C.c_void_p]),

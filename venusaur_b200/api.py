@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib as L
-from ._lib import (VN_ACCUM_SUM, VN_ASYNC, VN_COUNTERS, VN_DIELECTRIC, VN_EXACT, VN_FAST, VN_IMAGE_HOST, VN_POOL, VN_SLOTS, VN_PERSISTENT, VN_LAMBERTIAN,  # noqa: F401
+from ._lib import (VN_ACCUM_SUM, VN_ASYNC, VN_COUNTERS, VN_DIELECTRIC, VN_EXACT, VN_FAST, VN_IMAGE_HOST, VN_POOL, VN_SLOTS, VN_PERSISTENT, VN_GRID, VN_LAMBERTIAN,  # noqa: F401
                    VN_METAL, VN_NO_TONEMAP, VN_WAVEFRONT, vn_bvh_info, vn_node32, vn_params, vn_sphere, vn_stats)
 
 SPHERE_DTYPE = np.dtype([("cx", "f4"), ("cy", "f4"), ("cz", "f4"), ("r", "f4"), ("ax", "f4"), ("ay", "f4"),
@@ -168,6 +168,27 @@ class Context:
         order = np.zeros(info.num_spheres, np.uint32)
         self._check(self.lib.vn_read_bvh(self.h, _ptr(nodes), len(nodes), _ptr(order), len(order)), "vn_read_bvh")
         return nodes, order
+
+    def read_grid(self):
+        """(header dict, start[n_cells + 1] uint16, refs[n_refs] uint16) of the uniform grid + oversize list, or None when the scene has none."""
+        hdr = np.zeros(26, np.uint32)
+        if self._check_count(self.lib.vn_read_grid(self.h, _ptr(hdr), None, 0, None, 0), "vn_read_grid") == 0:
+            return None
+        f = hdr.view(np.float32)
+        h = {"lo": f[0:3].copy(), "inv_cell": f[3:6].copy(), "cell": f[6:9].copy(), "hi": f[9:12].copy(), "res": hdr[12:15].copy(),
+             "n_cells": int(hdr[15]), "n_refs": int(hdr[16]), "n_big": int(hdr[17]), "big": hdr[18:18 + int(hdr[17])].copy(), "raw": hdr.copy()}
+        start = np.zeros(h["n_cells"] + 1, np.uint16)
+        refs = np.zeros(max(h["n_refs"], 1), np.uint16)
+        self._check_count(self.lib.vn_read_grid(self.h, _ptr(hdr), _ptr(start), len(start), _ptr(refs), len(refs)), "vn_read_grid")
+        return h, start, refs[:h["n_refs"]]
+
+    def last_accel(self) -> int:
+        return int(self.lib.vn_last_accel(self.h))
+
+    def _check_count(self, rc, what):
+        if rc < 0:
+            self._check(rc, what)
+        return rc
 
     def read_wide_bvh(self):
         """(nodes[num_wide, 4, 2, 4] float32 -- child c = {lo.xyz, link}, {hi.xyz, count} --, levels); empty when the scene has no 4-wide nodes."""

@@ -27,6 +27,7 @@ UNITS = [
     # (source, object, extra flags)
     ("vn_api.cu", "vn_api.o", []),
     ("lbvh.cu", "lbvh.o", ["-fmad=false"]),
+    ("grid.cu", "grid.o", ["-fmad=false"]),
     ("path_kernels.cu", "path_exact.o", ["-DVN_EXACT=1", "-fmad=false"]),
     ("path_kernels.cu", "path_fast.o", ["-DVN_EXACT=0", "-fmad=true", "-ftz=true"]),
     ("wavefront.cu", "wavefront_exact.o", ["-DVN_EXACT=1", "-fmad=false"]),

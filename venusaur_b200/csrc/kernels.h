@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 #include "vn_math.cuh"
+#include "grid_core.cuh"
 
 namespace vn {
 
@@ -31,6 +32,9 @@ struct RenderLaunch {
     uint32_t root_link, num_nodes, num_spheres;
     const float4* wide;              // canonical 4-wide nodes (8 float4 each) or null; staged per octant by the path kernel
     uint32_t num_wide, wide_root;
+    GridHeader grid;                 // uniform grid + oversize list (kGrid kernels); grid_start/grid_refs are device arrays staged in shared memory
+    const uint16_t* grid_start;
+    const uint16_t* grid_refs;
     uint32_t leaf_vote;              // wide traversal: lanes waiting at a leaf that trigger the leaf turn (0 = while-while phases)
     unsigned long long* counters;    // [0] segments, [1] paths, [2] node visits, [3] sphere tests
     uint32_t* work_counter;          // persistent-thread work ticket
@@ -45,6 +49,7 @@ struct KernelConfig {
     bool count;                      // instrumented variant
     bool octant;                     // nodes staged 8x in shared memory, once per ray-direction octant (near/far-plane form)
     bool wide;                       // 4-wide octant-sorted nodes in shared memory (implies scene_in_smem; excludes octant)
+    bool grid;                       // uniform grid + oversize list in shared memory (excludes the others)
 };
 
 // Vote thresholds of the slot-scheduled kernel (slot_kernels.cu): an operation runs when that many lanes wait for it.
@@ -52,6 +57,7 @@ struct SlotTune { uint32_t node_threshold, leaf_threshold, switch_threshold, sha
 
 size_t scene_smem_bytes(uint32_t num_nodes, uint32_t num_spheres, uint32_t node_copies = 1);
 size_t wide_smem_bytes(uint32_t num_wide, uint32_t num_spheres);
+size_t grid_smem_bytes(uint32_t n_cells, uint32_t n_refs, uint32_t num_spheres);
 
 // Wavefront state: SoA queues in HBM (L2-resident at the default capacity), owned by the context.
 // One path slot = 48 bytes of ray state (o 12, d 12, throughput 12, seed 4, sample slot 4, depth 4).
@@ -82,7 +88,7 @@ struct WavefrontBuffers {
 constexpr int kWfArraysTotal = 2 * kWfStateArrays + 2 + 4;   // 4-byte arrays of `capacity` entries in the slab
 
 #define VN_DECLARE_KERNEL_API                                                                                          \
-    int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool count, bool octant, bool wide);              \
+    int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool count, bool octant, bool wide, bool grid);              \
     cudaError_t launch_render_persistent(const RenderLaunch& p, const KernelConfig& cfg, cudaStream_t stream);         \
     cudaError_t launch_tonemap(const float4* accum, float scale, uint32_t* image, uint64_t n, cudaStream_t stream);    \
     cudaError_t launch_reduce_tonemap_peers(const float4* const* peers, uint32_t n_peers, float scale, uint64_t begin, \
@@ -90,7 +96,7 @@ constexpr int kWfArraysTotal = 2 * kWfStateArrays + 2 + 4;   // 4-byte arrays of
     cudaError_t launch_test_rng(const uint32_t* v0, const uint32_t* v1, uint64_t n, uint32_t n_draws, uint32_t* seeds, \
                                 uint32_t* lcg_out, float* rnd_out, cudaStream_t stream);                               \
     cudaError_t launch_trace_rays(const RenderLaunch& scene, const float* o, const float* d, uint64_t n, float* t_out, \
-                                  int32_t* prim_out, const uint32_t* orig, cudaStream_t stream);                       \
+                                  int32_t* prim_out, const uint32_t* orig, bool grid, cudaStream_t stream);                     \
     cudaError_t launch_make_color(const float* rgb, uint64_t n, uint32_t* out, cudaStream_t stream);                   \
     cudaError_t launch_scatter(uint32_t type, float4 mat, const float* dirs, const float* normals,                     \
                                const uint8_t* front, const uint32_t* seeds, uint64_t n, float* dirs_out,               \

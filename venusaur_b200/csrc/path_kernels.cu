@@ -36,6 +36,10 @@ namespace vn {
 size_t scene_smem_bytes(uint32_t num_nodes, uint32_t num_spheres, uint32_t node_copies) {
     return (size_t)num_nodes * 32 * node_copies + (size_t)num_spheres * 32 + (((size_t)num_spheres + 15) & ~(size_t)15);
 }
+size_t grid_smem_bytes(uint32_t n_cells, uint32_t n_refs, uint32_t num_spheres) {
+    const size_t idx = (((size_t)n_cells + 1 + n_refs) * 2 + 15) & ~(size_t)15;
+    return idx + (size_t)num_spheres * 32 + (((size_t)num_spheres + 15) & ~(size_t)15);
+}
 size_t wide_smem_bytes(uint32_t num_wide, uint32_t num_spheres) {
     return (size_t)num_wide * 16 * kWideNodeF4 * 8 + (size_t)num_spheres * 32 + (((size_t)num_spheres + 15) & ~(size_t)15);
 }
@@ -102,6 +106,48 @@ __device__ __forceinline__ void closest_hit_wide_vote(const float4* __restrict__
     prim_out = prim;
 }
 
+// Closest hit through the uniform grid + oversize list (grid_core.cuh) with the same kind of vote: the oversize spheres are
+// tested by all lanes together; then every iteration is either a sphere turn (lanes with untested references in their current
+// cell test ONE sphere) or an advance turn (lanes whose cell is exhausted step the DDA to the next cell).
+template <bool kCount>
+__device__ __forceinline__ void closest_hit_grid_vote(const GridHeader& g, const uint16_t* __restrict__ start, const uint16_t* __restrict__ refs,
+                                                      const float4* __restrict__ geom, uint32_t sphere_vote, f3 o, f3 d, float& t_out, int& prim_out,
+                                                      TraceCounters& cnt) {
+    float tbest = kTMax;
+    int prim = -1;
+    const float a = dot(d, d);
+    const float inv_a = rcp(a);
+    for (uint32_t i = 0; i < g.n_big; i++) {
+        const uint32_t s = g.big[i];
+        const float4 sp = geom[s];
+        if (kCount) cnt.spheres += 1;
+        const float t = sphere_root(o, d, a, inv_a, sp.x, sp.y, sp.z, sp.w, kTMin, tbest);
+        if (t >= 0.0f) { tbest = t; prim = (int)s; }
+    }
+    GridRay r;
+    grid_ray_setup(g, start, o, d, tbest, r);
+    if (kCount && r.alive) cnt.nodes += 1;
+    while (r.alive) {
+        const bool at_sphere = r.q < r.q_end;
+        const unsigned act = __activemask();
+        const unsigned sm = __ballot_sync(act, at_sphere);
+        if (sm == act || (uint32_t)__popc(sm) >= sphere_vote) {
+            if (at_sphere) {
+                const uint32_t s = refs[r.q++];
+                const float4 sp = geom[s];
+                if (kCount) cnt.spheres += 1;
+                const float t = sphere_root(o, d, a, inv_a, sp.x, sp.y, sp.z, sp.w, kTMin, tbest);
+                if (t >= 0.0f) { tbest = t; prim = (int)s; }
+            }
+        } else if (!at_sphere) {
+            grid_ray_advance(g, start, tbest, r);
+            if (kCount && r.alive) cnt.nodes += 1;
+        }
+    }
+    t_out = tbest;
+    prim_out = prim;
+}
+
 // Scenes too large for shared memory: canonical 128-byte wide nodes from L2/HBM (vn_math.cuh::wide_global_step), same vote.
 template <bool kCount>
 __device__ __forceinline__ void closest_hit_wide_global_vote(const float4* __restrict__ wide, const float4* __restrict__ geom, uint32_t root_link,
@@ -130,12 +176,27 @@ __device__ __forceinline__ void closest_hit_wide_global_vote(const float4* __res
     prim_out = prim;
 }
 
-template <bool kSmem, bool kCount, bool kOct, int kMaxThreads, bool kWide = false>
+template <bool kSmem, bool kCount, bool kOct, int kMaxThreads, bool kWide = false, bool kGrid = false>
 __global__ void __launch_bounds__(kMaxThreads) k_render_persistent(const __grid_constant__ RenderLaunch p) {
     extern __shared__ float4 s_scene[];
     SceneView sc;
     const uint32_t node_f4s = kWide ? kWideNodeF4 * p.num_wide : 2 * p.num_nodes;
-    if (kSmem) {
+    const uint16_t* g_start = nullptr;
+    const uint16_t* g_refs = nullptr;
+    if (kGrid) {
+        // stage cell starts | references | geom | mat | type (RTIOW: 4.6 + 3.4 + 15.6 KB): the grid needs no node array at all
+        uint16_t* s_idx = reinterpret_cast<uint16_t*>(s_scene);
+        const uint32_t n_idx = p.grid.n_cells + 1u + p.grid.n_refs;
+        float4* s_geom = s_scene + (((size_t)n_idx * 2 + 15) / 16);
+        float4* s_mat = s_geom + p.num_spheres;
+        uint8_t* s_type = reinterpret_cast<uint8_t*>(s_mat + p.num_spheres);
+        for (uint32_t i = threadIdx.x; i <= p.grid.n_cells; i += blockDim.x) s_idx[i] = p.grid_start[i];
+        for (uint32_t i = threadIdx.x; i < p.grid.n_refs; i += blockDim.x) s_idx[p.grid.n_cells + 1u + i] = p.grid_refs[i];
+        for (uint32_t i = threadIdx.x; i < p.num_spheres; i += blockDim.x) { s_geom[i] = p.geom[i]; s_mat[i] = p.mat[i]; s_type[i] = p.type[i]; }
+        __syncthreads();
+        g_start = s_idx; g_refs = s_idx + p.grid.n_cells + 1u;
+        sc.nodes = nullptr; sc.geom = s_geom; sc.mat = s_mat; sc.type = s_type;
+    } else if (kSmem) {
         // stage nodes | geom | mat | type into shared memory with 128-bit copies
         float4* s_nodes = s_scene;
         float4* s_geom = s_nodes + (size_t)node_f4s * ((kOct || kWide) ? 8 : 1);
@@ -220,7 +281,8 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_persistent(const __grid_
         }
         float t;
         int prim;
-        if (kWide && !kSmem) {
+        if (kGrid) closest_hit_grid_vote<kCount>(p.grid, g_start, g_refs, sc.geom, p.leaf_vote ? p.leaf_vote : 33u, st.o, st.d, t, prim, cnt);
+        else if (kWide && !kSmem) {
             if (p.leaf_vote) closest_hit_wide_global_vote<kCount>(p.wide, sc.geom, p.wide_root, p.leaf_vote, st.o, st.d, t, prim, cnt);
             else closest_hit_wide_global<kCount>(p.wide, sc.geom, p.wide_root, st.o, st.d, t, prim, cnt);
         }
@@ -309,6 +371,19 @@ __global__ void k_trace_rays(const float4* __restrict__ nodes, const float4* __r
     prim_out[i] = prim >= 0 ? (int32_t)orig[prim] : -1;
 }
 
+__global__ void k_trace_rays_grid(const GridHeader g, const uint16_t* __restrict__ start, const uint16_t* __restrict__ refs, const float4* __restrict__ geom,
+                                  const float* __restrict__ o, const float* __restrict__ d, uint64_t n, float* __restrict__ t_out,
+                                  int32_t* __restrict__ prim_out, const uint32_t* __restrict__ orig) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float t;
+    int prim;
+    TraceCounters cnt{0u, 0u};
+    closest_hit_grid<false>(g, start, refs, geom, mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), t, prim, cnt);
+    t_out[i] = prim >= 0 ? t : -1.0f;
+    prim_out[i] = prim >= 0 ? (int32_t)orig[prim] : -1;
+}
+
 __global__ void k_make_color(const float* __restrict__ rgb, uint64_t n, uint32_t* __restrict__ out) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -345,7 +420,10 @@ inline uint32_t grid_for(uint64_t n, int threads) { return (uint32_t)((n + threa
 
 namespace {
 typedef void (*PathKernel)(const RenderLaunch);
-PathKernel pick_kernel(bool scene_in_smem, bool count, bool octant, bool wide = false, int threads = 1024) {
+PathKernel pick_kernel(bool scene_in_smem, bool count, bool octant, bool wide = false, int threads = 1024, bool grid = false) {
+    if (grid && threads <= 512) return count ? k_render_persistent<true, true, false, 512, false, true> : k_render_persistent<true, false, false, 512, false, true>;
+    if (grid && threads <= 768) return count ? k_render_persistent<true, true, false, 768, false, true> : k_render_persistent<true, false, false, 768, false, true>;
+    if (grid) return count ? k_render_persistent<true, true, false, 1024, false, true> : k_render_persistent<true, false, false, 1024, false, true>;
     if (wide && !scene_in_smem) return count ? k_render_persistent<false, true, false, 256, true> : k_render_persistent<false, false, false, 256, true>;
     if (wide && threads <= 512) return count ? k_render_persistent<true, true, false, 512, true> : k_render_persistent<true, false, false, 512, true>;
     if (wide && threads <= 768) return count ? k_render_persistent<true, true, false, 768, true> : k_render_persistent<true, false, false, 768, true>;
@@ -356,16 +434,16 @@ PathKernel pick_kernel(bool scene_in_smem, bool count, bool octant, bool wide = 
 }
 }  // namespace
 
-int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool count, bool octant, bool wide) {
+int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool count, bool octant, bool wide, bool grid) {
     int nb = 0;
-    PathKernel k = pick_kernel(scene_in_smem, count, octant, wide, threads);
+    PathKernel k = pick_kernel(scene_in_smem, count, octant, wide, threads, grid);
     if (smem_bytes > 48 * 1024 && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) return -1;
     const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, threads, smem_bytes);
     return e == cudaSuccess ? nb : -1;
 }
 
 cudaError_t launch_render_persistent(const RenderLaunch& p, const KernelConfig& cfg, cudaStream_t stream) {
-    PathKernel k = pick_kernel(cfg.scene_in_smem, cfg.count, cfg.octant, cfg.wide, cfg.threads);
+    PathKernel k = pick_kernel(cfg.scene_in_smem, cfg.count, cfg.octant, cfg.wide, cfg.threads, cfg.grid);
     if (cfg.smem_bytes > 48 * 1024) {
         const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes);
         if (e != cudaSuccess) return e;
@@ -398,9 +476,10 @@ cudaError_t launch_test_rng(const uint32_t* v0, const uint32_t* v1, uint64_t n, 
 }
 
 cudaError_t launch_trace_rays(const RenderLaunch& scene, const float* o, const float* d, uint64_t n, float* t_out, int32_t* prim_out,
-                              const uint32_t* orig, cudaStream_t stream) {
+                              const uint32_t* orig, bool grid, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    k_trace_rays<<<grid_for(n, 128), 128, 0, stream>>>(scene.nodes, scene.geom, scene.root_link, o, d, n, t_out, prim_out, orig);
+    if (grid) k_trace_rays_grid<<<grid_for(n, 128), 128, 0, stream>>>(scene.grid, scene.grid_start, scene.grid_refs, scene.geom, o, d, n, t_out, prim_out, orig);
+    else k_trace_rays<<<grid_for(n, 128), 128, 0, stream>>>(scene.nodes, scene.geom, scene.root_link, o, d, n, t_out, prim_out, orig);
     return cudaGetLastError();
 }
 

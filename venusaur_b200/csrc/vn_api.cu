@@ -13,6 +13,7 @@
 #include "../../include/venusaur/Camera.h"
 #include "../../include/venusaur/Scene.h"
 #include "kernels.h"
+#include "grid.h"
 #include "lbvh.h"
 #include "lbvh_core.cuh"
 
@@ -20,6 +21,7 @@ using namespace vn;
 
 #include <cstddef>
 static_assert(sizeof(vn_sphere) == 36 && sizeof(vn_node32) == 32, "ABI");
+static_assert(sizeof(GridHeader) == 104, "ABI (vn_read_grid)");
 static_assert(sizeof(vn_params) == 96 && offsetof(vn_params, origin) == 32 && offsetof(vn_params, flags) == 92, "ABI");
 static_assert(sizeof(vn_stats) == 64 && sizeof(vn_bvh_info) == 48, "ABI");
 
@@ -66,6 +68,10 @@ struct vn_context {
     bool slot_kernel = false;         // default path kernel for wide-node scenes: slot-scheduled (slot_kernels.cu) instead of k_render_persistent
     int slot_slots = 3, slot_threads = 768;
     SlotTune slot_tune{20u, 12u, 8u, 20u, 20u};
+    GridScene grid;                   // uniform grid + oversize list (small scenes), built behind the LBVH on the same sorted spheres
+    uint32_t accel = 0;               // closest-hit structure of the path kernel: 0 = auto (grid when the scene suits it), 1 = BVH, 2 = grid
+    uint32_t grid_max_per_cell = 16;  // a cell with more spheres than this disqualifies the grid (clustered scenes: the BVH adapts, a grid does not)
+    uint32_t last_accel = 0;          // what the last vn_render traversed: 1 pair nodes, 2 wide nodes (shared memory), 3 wide nodes (L2/HBM), 4 grid
     int wide_threads = 1024;          // CTA size of the wide-node path kernel (one CTA per SM): 512, 768 or 1024
     uint32_t leaf_vote = 12;          // see closest_hit_wide_vote (path_kernels.cu); 0 = while-while
     bool wide_nodes = true;           // use them when they fit in shared memory
@@ -149,6 +155,7 @@ int fill_launch(vn_context* c, const vn_params* p, RenderLaunch& L) {
     L.num_spheres = (uint32_t)c->scene.n;
     L.wide = c->scene.wide; L.num_wide = c->scene.num_wide; L.wide_root = 0u;
     L.leaf_vote = c->leaf_vote;
+    L.grid = c->grid.h; L.grid_start = c->grid.start; L.grid_refs = c->grid.refs;
     L.counters = c->d_counters;
     L.work_counter = reinterpret_cast<uint32_t*>(c->d_counters + 4);
     const uint32_t rows = L.row_end - L.row_begin;
@@ -236,6 +243,7 @@ void vn_destroy(vn_handle c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     lbvh_free(c->scene);
+    grid_free(c->grid);
     lbvh_workspace_free(c->bvh_ws);
     free_wavefront(c->wf); c->wf_sample_floats_ = 0;
     cudaFree(c->d_spheres); cudaFree(c->accum_own); cudaFree(c->image_tmp); cudaFree(c->d_counters);
@@ -262,6 +270,8 @@ int vn_set_option(vn_handle c, const char* name, double value) {
     else if (k == "wide_max_prims") { VN_REQUIRE(c, value >= 0 && value <= (double)(1u << 28), "wide_max_prims must be in [0,2^28]"); c->wide_max_prims = (uint32_t)value; c->bvh_valid = false; }
     else if (k == "wide_nodes") { c->wide_nodes = value != 0; }
     else if (k == "wide_global") { c->wide_global = value != 0; }
+    else if (k == "accel") { VN_REQUIRE(c, value == 0 || value == 1 || value == 2, "accel must be 0 (auto), 1 (BVH) or 2 (grid)"); c->accel = (uint32_t)value; c->bvh_valid = false; }
+    else if (k == "grid_max_per_cell") { VN_REQUIRE(c, value >= 1 && value <= 65535, "grid_max_per_cell must be in [1,65535]"); c->grid_max_per_cell = (uint32_t)value; c->bvh_valid = false; }
     else if (k == "wide_threads") { VN_REQUIRE(c, value == 512 || value == 768 || value == 1024, "wide_threads must be 512, 768 or 1024"); c->wide_threads = (int)value; }
     else if (k == "leaf_vote") { VN_REQUIRE(c, value >= 0 && value <= 32, "leaf_vote must be in [0,32]"); c->leaf_vote = (uint32_t)value; }
     else if (k == "slot_kernel") { c->slot_kernel = value != 0; }
@@ -329,6 +339,11 @@ int vn_build_bvh(vn_handle c) {
         }
     }
     if (rc != 0) return fail(c, rc == -1 ? VN_ERR_INVALID : VN_ERR_CUDA, "vn_build_bvh: " + err);
+    grid_free(c->grid);
+    if (c->accel != 1u && c->scene.geom) {
+        const int grc = grid_build(c->scene.geom, c->scene.n, c->grid_max_per_cell, c->stream, c->grid, &launches, err);
+        if (grc < 0) return fail(c, VN_ERR_CUDA, "vn_build_bvh: " + err);
+    }
     VN_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     VN_CUDA(c, cudaStreamSynchronize(c->stream));
     VN_CUDA(c, cudaEventElapsedTime(&c->stats.ms_build, c->ev[0], c->ev[1]));
@@ -366,6 +381,19 @@ int vn_read_sched_counters(vn_handle c, uint64_t* out14) {
     for (int i = 0; i < 14; i++) out14[i] = c->h_counters[8 + i];
     return VN_OK;
 }
+
+int vn_read_grid(vn_handle c, void* header104, uint16_t* host_start, uint64_t cap_start, uint16_t* host_refs, uint64_t cap_refs) {
+    VN_REQUIRE(c, c, "vn_read_grid: NULL handle");
+    VN_REQUIRE(c, c->bvh_valid, "vn_read_grid: no scene structure (call vn_build_bvh)");
+    if (!c->grid.valid) return 0;
+    VN_CUDA(c, cudaSetDevice(c->device));
+    if (header104) memcpy(header104, &c->grid.h, sizeof(GridHeader));
+    if (host_start) VN_CUDA(c, cudaMemcpy(host_start, c->grid.start, std::min<uint64_t>(cap_start, c->grid.h.n_cells + 1ull) * 2, cudaMemcpyDeviceToHost));
+    if (host_refs) VN_CUDA(c, cudaMemcpy(host_refs, c->grid.refs, std::min<uint64_t>(cap_refs, c->grid.h.n_refs) * 2, cudaMemcpyDeviceToHost));
+    return 1;
+}
+
+int vn_last_accel(vn_handle c) { return c ? (int)c->last_accel : 0; }
 
 int vn_read_wide_bvh(vn_handle c, float* host_nodes, uint64_t cap_nodes, uint32_t* num_nodes_out, uint32_t* levels_out) {
     VN_REQUIRE(c, c, "vn_read_wide_bvh: NULL handle");
@@ -637,17 +665,21 @@ int vn_render(vn_handle c, const vn_params* p) {
         cfg.wide = c->wide_nodes && L.wide && L.num_wide > 0 && c->scene.wide_levels <= kWideMaxLevels && wide_bytes + 2048 <= c->smem_optin;
         // scenes too large for shared memory: the canonical wide nodes straight from L2/HBM (half the dependent fetches)
         const bool wide_global = !cfg.wide && !cfg.scene_in_smem && c->wide_global && c->wide_nodes && L.wide && L.num_wide > 0 && c->scene.wide_levels <= kWideGlobalMaxLevels;
-        if (cfg.wide) { cfg.scene_in_smem = true; cfg.octant = false; cfg.smem_bytes = wide_bytes; cfg.threads = c->wide_threads; }
+        // small scenes of similar-sized spheres: uniform grid + oversize list (grid_core.cuh), 40 % of the BVH's instructions on RTIOW
+        cfg.grid = c->accel != 1u && c->grid.valid && grid_smem_bytes(c->grid.h.n_cells, c->grid.h.n_refs, L.num_spheres) + 2048 <= c->smem_optin;
+        if (cfg.grid) { cfg.scene_in_smem = true; cfg.octant = false; cfg.wide = false; cfg.smem_bytes = grid_smem_bytes(c->grid.h.n_cells, c->grid.h.n_refs, L.num_spheres); cfg.threads = c->wide_threads; }
+        else if (cfg.wide) { cfg.scene_in_smem = true; cfg.octant = false; cfg.smem_bytes = wide_bytes; cfg.threads = c->wide_threads; }
         else if (wide_global) { cfg.wide = true; cfg.octant = false; if (cfg.threads > 256) cfg.threads = 256; }
         else if (cfg.octant) { cfg.smem_bytes = oct_bytes; cfg.threads = 1024; }
         else if (cfg.threads > 256) cfg.threads = 256;
         int per_sm = (cfg.octant || (cfg.wide && cfg.scene_in_smem)) ? 1 : c->blocks_per_sm;
         if (per_sm <= 0) {
-            per_sm = exact_build ? exact::max_blocks_per_sm(cfg.threads, cfg.smem_bytes, cfg.scene_in_smem, count, cfg.octant, cfg.wide)
-                                 : fast::max_blocks_per_sm(cfg.threads, cfg.smem_bytes, cfg.scene_in_smem, count, cfg.octant, cfg.wide);
+            per_sm = exact_build ? exact::max_blocks_per_sm(cfg.threads, cfg.smem_bytes, cfg.scene_in_smem, count, cfg.octant, cfg.wide, cfg.grid)
+                                 : fast::max_blocks_per_sm(cfg.threads, cfg.smem_bytes, cfg.scene_in_smem, count, cfg.octant, cfg.wide, cfg.grid);
             if (per_sm <= 0) return fail(c, VN_ERR_CUDA, "vn_render: occupancy query failed for the path kernel");
         }
         cfg.blocks = c->num_sms * per_sm;
+        c->last_accel = cfg.grid ? 4u : (cfg.wide ? (cfg.scene_in_smem ? 2u : 3u) : 1u);
         // never launch more lanes than there is work
         const uint64_t max_blocks = ((uint64_t)L.total_work + cfg.threads - 1) / cfg.threads;
         if ((uint64_t)cfg.blocks > max_blocks) cfg.blocks = (int)std::max<uint64_t>(1, max_blocks);
@@ -867,8 +899,11 @@ int vn_trace_rays(vn_handle c, const float* origins, const float* dirs, uint64_t
     RenderLaunch L;
     memset(&L, 0, sizeof(L));
     L.nodes = c->scene.nodes; L.geom = c->scene.geom; L.root_link = c->scene.root_link;
-    VN_CUDA(c, !(flags & VN_FAST) ? exact::launch_trace_rays(L, o.as<float>(), d.as<float>(), n, t.as<float>(), pr.as<int32_t>(), c->scene.orig, c->stream)
-                                  : fast::launch_trace_rays(L, o.as<float>(), d.as<float>(), n, t.as<float>(), pr.as<int32_t>(), c->scene.orig, c->stream));
+    const bool use_grid = (flags & VN_GRID) != 0;
+    VN_REQUIRE(c, !use_grid || c->grid.valid, "vn_trace_rays: VN_GRID but the scene has no grid");
+    L.grid = c->grid.h; L.grid_start = c->grid.start; L.grid_refs = c->grid.refs;
+    VN_CUDA(c, !(flags & VN_FAST) ? exact::launch_trace_rays(L, o.as<float>(), d.as<float>(), n, t.as<float>(), pr.as<int32_t>(), c->scene.orig, use_grid, c->stream)
+                                  : fast::launch_trace_rays(L, o.as<float>(), d.as<float>(), n, t.as<float>(), pr.as<int32_t>(), c->scene.orig, use_grid, c->stream));
     VN_CUDA(c, cudaMemcpyAsync(t_out, t.p, 4 * n, cudaMemcpyDeviceToHost, c->stream));
     VN_CUDA(c, cudaMemcpyAsync(prim_out, pr.p, 4 * n, cudaMemcpyDeviceToHost, c->stream));
     VN_CUDA(c, cudaStreamSynchronize(c->stream));
