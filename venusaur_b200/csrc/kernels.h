@@ -35,6 +35,7 @@ struct RenderLaunch {
     GridHeader grid;                 // uniform grid + oversize list (kGrid kernels); grid_start/grid_refs are device arrays staged in shared memory
     const uint16_t* grid_start;
     const uint16_t* grid_refs;
+    uint32_t grid_vote;              // grid traversal: lanes holding an untested sphere that trigger the sphere turn (0 = while-while)
     uint32_t leaf_vote;              // wide traversal: lanes waiting at a leaf that trigger the leaf turn (0 = while-while phases)
     unsigned long long* counters;    // [0] segments, [1] paths, [2] node visits, [3] sphere tests
     uint32_t* work_counter;          // persistent-thread work ticket

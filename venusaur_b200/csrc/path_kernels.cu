@@ -127,6 +127,24 @@ __device__ __forceinline__ void closest_hit_grid_vote(const GridHeader& g, const
     GridRay r;
     grid_ray_setup(g, start, o, d, tbest, r);
     if (kCount && r.alive) cnt.nodes += 1;
+    if (sphere_vote == 0u) {
+        // while-while form: walk to the next cell that holds a sphere, then test one sphere
+        while (r.alive) {
+            while (r.alive && r.q >= r.q_end) {
+                grid_ray_advance(g, start, tbest, r);
+                if (kCount && r.alive) cnt.nodes += 1;
+            }
+            if (!r.alive) break;
+            const uint32_t s = refs[r.q++];
+            const float4 sp = geom[s];
+            if (kCount) cnt.spheres += 1;
+            const float t = sphere_root(o, d, a, inv_a, sp.x, sp.y, sp.z, sp.w, kTMin, tbest);
+            if (t >= 0.0f) { tbest = t; prim = (int)s; }
+        }
+        t_out = tbest;
+        prim_out = prim;
+        return;
+    }
     while (r.alive) {
         const bool at_sphere = r.q < r.q_end;
         const unsigned act = __activemask();
@@ -281,7 +299,7 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_persistent(const __grid_
         }
         float t;
         int prim;
-        if (kGrid) closest_hit_grid_vote<kCount>(p.grid, g_start, g_refs, sc.geom, p.leaf_vote ? p.leaf_vote : 33u, st.o, st.d, t, prim, cnt);
+        if (kGrid) closest_hit_grid_vote<kCount>(p.grid, g_start, g_refs, sc.geom, p.grid_vote, st.o, st.d, t, prim, cnt);
         else if (kWide && !kSmem) {
             if (p.leaf_vote) closest_hit_wide_global_vote<kCount>(p.wide, sc.geom, p.wide_root, p.leaf_vote, st.o, st.d, t, prim, cnt);
             else closest_hit_wide_global<kCount>(p.wide, sc.geom, p.wide_root, st.o, st.d, t, prim, cnt);

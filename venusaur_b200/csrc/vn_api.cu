@@ -69,7 +69,9 @@ struct vn_context {
     int slot_slots = 3, slot_threads = 768;
     SlotTune slot_tune{20u, 12u, 8u, 20u, 20u};
     GridScene grid;                   // uniform grid + oversize list (small scenes), built behind the LBVH on the same sorted spheres
-    uint32_t accel = 0;               // closest-hit structure of the path kernel: 0 = auto (grid when the scene suits it), 1 = BVH, 2 = grid
+    uint32_t accel = 1;               // closest-hit structure of the path kernel: 1 = BVH (default: what the north star specifies), 0 = auto (the grid
+                                      // when the scene suits it: +3..6 % on RTIOW), 2 = grid
+    uint32_t grid_vote = 0;           // see closest_hit_grid_vote (path_kernels.cu): 0 = while-while (fastest measured), n = voted sphere turns
     uint32_t grid_max_per_cell = 16;  // a cell with more spheres than this disqualifies the grid (clustered scenes: the BVH adapts, a grid does not)
     uint32_t last_accel = 0;          // what the last vn_render traversed: 1 pair nodes, 2 wide nodes (shared memory), 3 wide nodes (L2/HBM), 4 grid
     int wide_threads = 1024;          // CTA size of the wide-node path kernel (one CTA per SM): 512, 768 or 1024
@@ -155,6 +157,7 @@ int fill_launch(vn_context* c, const vn_params* p, RenderLaunch& L) {
     L.num_spheres = (uint32_t)c->scene.n;
     L.wide = c->scene.wide; L.num_wide = c->scene.num_wide; L.wide_root = 0u;
     L.leaf_vote = c->leaf_vote;
+    L.grid_vote = c->grid_vote;
     L.grid = c->grid.h; L.grid_start = c->grid.start; L.grid_refs = c->grid.refs;
     L.counters = c->d_counters;
     L.work_counter = reinterpret_cast<uint32_t*>(c->d_counters + 4);
@@ -271,6 +274,7 @@ int vn_set_option(vn_handle c, const char* name, double value) {
     else if (k == "wide_nodes") { c->wide_nodes = value != 0; }
     else if (k == "wide_global") { c->wide_global = value != 0; }
     else if (k == "accel") { VN_REQUIRE(c, value == 0 || value == 1 || value == 2, "accel must be 0 (auto), 1 (BVH) or 2 (grid)"); c->accel = (uint32_t)value; c->bvh_valid = false; }
+    else if (k == "grid_vote") { VN_REQUIRE(c, value >= 0 && value <= 33, "grid_vote must be in [0,33]"); c->grid_vote = (uint32_t)value; }
     else if (k == "grid_max_per_cell") { VN_REQUIRE(c, value >= 1 && value <= 65535, "grid_max_per_cell must be in [1,65535]"); c->grid_max_per_cell = (uint32_t)value; c->bvh_valid = false; }
     else if (k == "wide_threads") { VN_REQUIRE(c, value == 512 || value == 768 || value == 1024, "wide_threads must be 512, 768 or 1024"); c->wide_threads = (int)value; }
     else if (k == "leaf_vote") { VN_REQUIRE(c, value >= 0 && value <= 32, "leaf_vote must be in [0,32]"); c->leaf_vote = (uint32_t)value; }
