@@ -145,6 +145,9 @@ VN_API int vn_read_bvh(vn_handle h, vn_node32* host_nodes, uint64_t cap_nodes, u
  * cell[3], hi[3]; uint32 res[3], n_cells, n_refs, n_big, big[8] }, start[n_cells + 1], refs[n_refs] (sorted sphere indices); 0 when the
  * scene has no grid ("accel" = 1, or it does not suit the structure). */
 VN_API int vn_read_grid(vn_handle h, void* header104, uint16_t* host_start, uint64_t cap_start, uint16_t* host_refs, uint64_t cap_refs);
+/* Spheres left out of the wide nodes because nearly every ray enters their box (radius > 50 x median; RTIOW: the ground): the path kernel
+ * tests them before the traversal.  Returns their number (<= 8) and their sorted indices. */
+VN_API int vn_read_huge(vn_handle h, uint32_t* idx8);
 VN_API int vn_last_accel(vn_handle h);   /* what the last vn_render traversed: 1 pair nodes, 2 wide nodes, 3 wide nodes from L2/HBM, 4 grid */
 /* 4-wide nodes derived from the pairs for scenes traversed out of shared memory (<= "wide_max_prims" spheres): 128 B per
  * node = 4 x { {lo.xyz, link}, {hi.xyz, count} }; link = wide-node index, a leaf link as above, or 0xFFFFFFFF (empty slot).

@@ -48,6 +48,8 @@ def host_harness():
     h.hh_set_oct.argtypes = [C.c_int]
     h.hh_set_wide.argtypes = [C.c_int]
     h.hh_set_grid.argtypes = [C.c_int]
+    h.hh_huge_list.restype = C.c_uint32
+    h.hh_huge_list.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_void_p]
     h.hh_build_grid.restype = C.c_int
     h.hh_build_grid.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
     h.hh_set_sah_max.argtypes = [C.c_uint32]

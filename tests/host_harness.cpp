@@ -38,6 +38,8 @@ struct HostBvh {
     std::vector<node_f4> wide;        // canonical 4-wide nodes (8 float4 each), BFS order
     std::vector<node_f4> wide_oct;    // 8 octant-specialised copies (7 float4 per node)
     uint32_t wide_root = kEmptyScene, wide_levels = 0;
+    HugeList huge{};                  // spheres left out of the wide nodes (tested before the traversal)
+    uint32_t leaf_size = 0;
     GridHeader grid;                  // uniform grid + oversize list (grid_core.cuh); grid_ok = the scene suits it
     bool grid_ok = false;
     std::vector<uint16_t> grid_start, grid_refs;
@@ -116,6 +118,8 @@ static void sah_small_host(uint32_t n, const f4* cen, const f4* blo, const f4* b
 static void build_wide(HostBvh& B) {
     B.wide.clear(); B.wide_oct.clear(); B.wide_levels = 0;
     B.wide_root = B.root_link;
+    huge_list_from_geom(B.geom.data(), (uint32_t)B.geom.size(), B.leaf_size, B.huge);
+    if (B.geom.size() > 16384) B.huge = HugeList();          // the product only does this for the one-CTA wide build (<= 16384 spheres)
     if (B.root_link & kLeafFlag) return;                 // a single leaf (or the empty scene): no wide nodes
     B.wide_root = 0;
     std::vector<uint32_t> src{B.root_link};              // packed pair link of every wide node
@@ -129,7 +133,7 @@ static void build_wide(HostBvh& B) {
             B.wide.resize(8 * (e + 1), node_f4{0, 0, 0, 0});
             for (uint32_t c = 0; c < 4; c++) {
                 node_f4 a{3e38f, 3e38f, 3e38f, u2f(kWideEmpty)}, b{-3e38f, -3e38f, -3e38f, u2f(0u)};
-                if (c < n) {
+                if (c < n && !huge_leaf(f2u(B.nodes[2 * ch[c]].w), B.huge)) {
                     a = B.nodes[2 * ch[c]]; b = B.nodes[2 * ch[c] + 1];
                     const uint32_t link = f2u(a.w);
                     if (!(link & kLeafFlag)) { a.w = u2f((uint32_t)src.size()); src.push_back(link); }
@@ -174,6 +178,7 @@ static void build_grid(HostBvh& B) {
 
 static void build(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pad_rel, HostBvh& B) {
     B = HostBvh();
+    B.leaf_size = leaf_size;
     if (n == 0) { B.nodes.resize(4); return; }
     std::vector<f4> llo(n), lhi(n);
     float clo[3] = {INFINITY, INFINITY, INFINITY}, chi[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -295,8 +300,18 @@ static void build(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pad_
 template <bool kCount>
 static inline void hh_closest(const HostBvh& B, f3 o, f3 d, float& t, int& prim, TraceCounters& cnt) {
     if (g_use_grid && B.grid_ok) closest_hit_grid<kCount>(B.grid, B.grid_start.data(), B.grid_refs.data(), B.geom.data(), o, d, t, prim, cnt);
-    else if (g_use_wide == 2 && B.wide_levels <= kWideGlobalMaxLevels) closest_hit_wide_global<kCount>(B.wide.data(), B.geom.data(), B.wide_root, o, d, t, prim, cnt);
-    else if (g_use_wide && B.wide_levels <= kWideMaxLevels && !B.wide_oct.empty()) closest_hit_wide<kCount>(B.wide_oct.data(), (uint32_t)(B.wide_oct.size() / 8), B.geom.data(), B.wide_root, o, d, t, prim, cnt);
+    else if (g_use_wide == 2 && B.wide_levels <= kWideGlobalMaxLevels && B.huge.n == 0) closest_hit_wide_global<kCount>(B.wide.data(), B.geom.data(), B.wide_root, o, d, t, prim, cnt);
+    else if (g_use_wide && B.wide_levels <= kWideMaxLevels && !B.wide_oct.empty()) {
+        float t0 = kTMax; int prim0 = -1;
+        const float a = dot(d, d), inv_a = rcp(a);
+        for (uint32_t i = 0; i < B.huge.n; i++) {
+            const node_f4 g = B.geom[B.huge.idx[i]];
+            if (kCount) cnt.spheres += 1;
+            const float th = sphere_root(o, d, a, inv_a, g.x, g.y, g.z, g.w, kTMin, t0);
+            if (th >= 0.0f) { t0 = th; prim0 = (int)B.huge.idx[i]; }
+        }
+        closest_hit_wide<kCount>(B.wide_oct.data(), (uint32_t)(B.wide_oct.size() / 8), B.geom.data(), B.wide_root, o, d, t, prim, cnt, t0, prim0);
+    }
     else if (g_use_oct) closest_hit<kCount, true>(B.nodes_oct.data(), B.geom.data(), B.root_link, o, d, t, prim, cnt, (uint32_t)B.nodes.size());
     else closest_hit<kCount, false>(B.nodes.data(), B.geom.data(), B.root_link, o, d, t, prim, cnt);
 }
@@ -306,6 +321,13 @@ extern "C" {
 void hh_set_oct(int on) { g_use_oct = on; }
 void hh_set_wide(int on) { g_use_wide = on; }
 void hh_set_grid(int on) { g_use_grid = on; }
+// huge list of the host build (sorted sphere indices)
+uint32_t hh_huge_list(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pad_rel, uint32_t* idx8) {
+    HostBvh B;
+    build(s, n, leaf_size, pad_rel, B);
+    for (uint32_t i = 0; i < B.huge.n; i++) idx8[i] = B.huge.idx[i];
+    return B.huge.n;
+}
 // grid of the host build: header (80 bytes), start[n_cells + 1], refs[n_refs]; returns 1 when the scene suits the structure
 int hh_build_grid(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pad_rel, void* header_out, uint16_t* start_out, uint64_t cap_start,
                   uint16_t* refs_out, uint64_t cap_refs) {

@@ -344,6 +344,37 @@ def test_exact_build_other_launch_shapes(rtiow_ctx, oracle_mod, rtiow, sub, dept
     assert np.array_equal(acc.view(np.uint32), want.view(np.uint32))
 
 
+def test_default_options_huge_list_and_auto_leaf(ctx, oracle_mod, rtiow):
+    """What bench.py runs: leaf_size 0 (auto) picks one-sphere leaves for the RTIOW scene, the radius-1000 ground is left out
+    of the wide nodes and tested by every ray before the traversal (vn_read_huge), the wide copies fit in shared memory, and
+    the result is bit-identical to the oracle (brute force) and to the pair-node kernel that still reaches the ground through
+    its leaf; fewer divergent leaf visits show up as the same number of sphere tests."""
+    W, H, spp, depth = 240, 135, 5, 50
+    cam = vb.rtiow_camera(W, H)
+    ctx.set_option("leaf_size", 0)
+    try:
+        ctx.set_spheres(rtiow)
+        ctx.build_bvh()
+        info = ctx.bvh_info()
+        assert info.max_leaf_size == 1
+        huge = ctx.read_huge()
+        nodes, order = ctx.read_bvh()
+        assert len(huge) == 1 and abs(float(rtiow[order[huge[0]]]["r"])) == 1000.0
+        a, ia, sa = render(ctx, cam, W, H, spp, 3, depth, flags=VN_COUNTERS)
+        assert ctx.last_accel() == 2
+        ctx.set_option("wide_nodes", 0)
+        b, ib, sb = render(ctx, cam, W, H, spp, 3, depth, flags=VN_COUNTERS)
+        assert ctx.last_accel() == 1
+    finally:
+        ctx.set_option("wide_nodes", 1)
+        ctx.set_option("leaf_size", 2)
+    assert sa.segments == sb.segments and np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(ia, ib)
+    assert sa.sphere_tests >= sa.segments                       # every ray tests the ground
+    orc = oracle_mod.Oracle(rtiow)
+    want, ost = orc.render_mean(orc.params(cam.frame(), W, H, spp, 3, depth, atten=oracle_mod.ATTEN_FORWARD, closest=oracle_mod.CLOSEST_BRUTE))
+    assert ost.segments == sa.segments and np.array_equal(a.view(np.uint32), want.view(np.uint32))
+
+
 def test_octant_and_plain_persistent_kernels_agree(rtiow_ctx):
     """The persistent kernel with 8 octant-specialised node copies in shared memory (1024-thread CTAs) and the plain one
     (256-thread CTAs, lo/hi nodes) are bit-identical."""

@@ -257,6 +257,10 @@ def test_wide_nodes_invariants_on_cpu(host_harness, oracle_mod, rtiow, leaf):
     for spheres in (rtiow, np.ascontiguousarray(oracle_mod.random_scene(3000, 0x5EED0001, 30.0, 0)), np.ascontiguousarray(rtiow[:5])):
         wide, levels = _host_wide(host_harness, spheres, leaf)
         n = len(spheres)
+        idx8 = (C.c_uint32 * 8)()
+        n_huge = host_harness.hh_huge_list(spheres.ctypes.data_as(C.c_void_p), n, leaf, C.c_float(0.01), idx8)
+        huge = [int(idx8[i]) for i in range(n_huge)]
+        assert n_huge == (1 if (spheres is rtiow and leaf == 1) else 0)      # the radius-1000 ground, when leaves hold one sphere
         if n <= leaf:
             assert len(wide) == 0
             continue
@@ -281,8 +285,10 @@ def test_wide_nodes_invariants_on_cpu(host_harness, oracle_mod, rtiow, leaf):
                 else:
                     assert w < l < len(wide)          # breadth-first: children come later
                     refs[l] += 1
-            assert kids >= 2
-        assert (seen == 1).all() and (refs == 1).all()
+            assert kids >= (1 if huge else 2)
+        want_seen = np.ones(n, np.int32)
+        want_seen[huge] = 0                   # huge spheres are tested before the traversal, not through the wide nodes
+        assert np.array_equal(seen, want_seen) and (refs == 1).all()
         assert 1 <= levels <= 20
         assert len(wide) <= (n + 1) // 2 + 1
 

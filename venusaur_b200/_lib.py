@@ -68,6 +68,7 @@ SIGNATURES = {
     "vn_read_sched_counters": (C.c_int, [C.c_void_p, _P(C.c_uint64)]),
     "vn_read_grid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
     "vn_last_accel": (C.c_int, [C.c_void_p]),
+    "vn_read_huge": (C.c_int, [C.c_void_p, _P(C.c_uint32)]),
     "vn_read_wide_bvh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, _P(C.c_uint32), _P(C.c_uint32)]),
     "vn_resize": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "vn_reset_accum": (C.c_int, [C.c_void_p]),

@@ -182,6 +182,11 @@ class Context:
         self._check_count(self.lib.vn_read_grid(self.h, _ptr(hdr), _ptr(start), len(start), _ptr(refs), len(refs)), "vn_read_grid")
         return h, start, refs[:h["n_refs"]]
 
+    def read_huge(self):
+        idx = (C.c_uint32 * 8)()
+        n = self._check_count(self.lib.vn_read_huge(self.h, idx), "vn_read_huge")
+        return [int(idx[i]) for i in range(n)]
+
     def last_accel(self) -> int:
         return int(self.lib.vn_last_accel(self.h))
 

@@ -8,6 +8,7 @@
 
 #include "vn_math.cuh"
 #include "grid_core.cuh"
+#include "lbvh_core.cuh"
 
 namespace vn {
 
@@ -32,6 +33,7 @@ struct RenderLaunch {
     uint32_t root_link, num_nodes, num_spheres;
     const float4* wide;              // canonical 4-wide nodes (8 float4 each) or null; staged per octant by the path kernel
     uint32_t num_wide, wide_root;
+    HugeList huge;                   // spheres left out of the wide nodes: tested by every ray before the traversal (lbvh_core.cuh)
     GridHeader grid;                 // uniform grid + oversize list (kGrid kernels); grid_start/grid_refs are device arrays staged in shared memory
     const uint16_t* grid_start;
     const uint16_t* grid_refs;

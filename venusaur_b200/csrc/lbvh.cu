@@ -15,6 +15,7 @@
 #include "lbvh.h"
 
 #include <cstring>
+#include <vector>
 
 #include "lbvh_core.cuh"
 #include "radix_sort.cuh"
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(kBlock) k_pack(uint32_t n, const KarrasNode* _
 // deterministic (prefix sums, no atomics): each level's wide nodes open their pair (lbvh_core.cuh::wide_collapse) and
 // their internal children receive consecutive indices in entry order.  result[1] = wide nodes, result[2] = levels.
 __global__ void __launch_bounds__(kBlock) k_wide_build(const float4* __restrict__ nodes, uint32_t* src, uint32_t cap, float4* __restrict__ wide,
-                                                      uint32_t* __restrict__ result) {
+                                                      uint32_t* __restrict__ result, const HugeList huge) {
     __shared__ uint32_t s_warp[kBlock / 32];
     const uint32_t root_link = __float_as_uint(nodes[2].w);
     if (root_link & kLeafFlag) {            // a single leaf or the empty scene: nothing to widen
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(kBlock) k_wide_build(const float4* __restrict_
             if (e < hi) {
                 for (uint32_t c = 0; c < 4u; c++) {
                     float4 a = make_float4(3e38f, 3e38f, 3e38f, __uint_as_float(kWideEmpty)), b = make_float4(-3e38f, -3e38f, -3e38f, 0.0f);
-                    if (c < n) {
+                    if (c < n && !huge_leaf(__float_as_uint(nodes[2 * ch[c]].w), huge)) {     // huge spheres: tested before the traversal
                         a = nodes[2 * ch[c]]; b = nodes[2 * ch[c] + 1];
                         const uint32_t link = __float_as_uint(a.w);
                         if (!(link & kLeafFlag)) { if (at < cap) src[at] = link; a.w = __uint_as_float(at); at += 1u; }
@@ -548,8 +549,13 @@ int lbvh_build(const vn_sphere* d_spheres, uint64_t n64, uint32_t leaf_size, flo
         k_pack<<<blocks_for(n), kBlock, 0, stream>>>(n, kn, rank, ilo, ihi, leaf_lo, leaf_hi, leaf_size, out.nodes);
         launched += 1;
         if (want_wide) {
+            // huge spheres (host decision from one read-back of the sorted spheres: small scenes only) stay out of the wide nodes
+            std::vector<node_f4> hgeom(n);
+            LB_CHECK(cudaMemcpyAsync(hgeom.data(), out.geom, 16ull * n, cudaMemcpyDeviceToHost, stream));
+            LB_CHECK(cudaStreamSynchronize(stream));
+            huge_list_from_geom(hgeom.data(), n, leaf_size, out.huge);
             // sah_u32 is free again here (the SAH pass, if any, has been consumed by the second gather): queue of pair links
-            k_wide_build<<<1, kBlock, 0, stream>>>(out.nodes, sah_u32, n, out.wide, result);
+            k_wide_build<<<1, kBlock, 0, stream>>>(out.nodes, sah_u32, n, out.wide, result, out.huge);
             launched += 1;
         }
         // one host round trip at the end: kept-node count, root link, root bounds

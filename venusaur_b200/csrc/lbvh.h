@@ -8,6 +8,7 @@
 #include <string>
 
 #include "../../include/venusaur_b200.h"
+#include "lbvh_core.cuh"
 
 namespace vn {
 
@@ -27,6 +28,7 @@ struct LbvhScene {
     float4* wide = nullptr;      // num_wide x 128 B: 4-wide nodes derived from the pairs (small scenes only), see lbvh_core.cuh
     void* wide_alloc = nullptr;  // large scenes: the wide nodes have their own allocation
     uint32_t num_wide = 0, wide_levels = 0;
+    HugeList huge{};             // spheres left out of the wide nodes: every ray tests them before the traversal
     uint32_t height = 0;         // levels of internal nodes (the traversal stack must hold that many entries)
     bool sah = false;            // splits chosen by the surface-area heuristic (small scenes) instead of Karras' spatial medians
     float bounds_lo[3] = {0, 0, 0}, bounds_hi[3] = {0, 0, 0};

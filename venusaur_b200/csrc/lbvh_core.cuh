@@ -176,6 +176,21 @@ constexpr uint32_t kWideEmpty = 0xFFFFFFFFu;
 constexpr uint32_t kWideMaxLevels = 20;    // 3 pushes per level + 1 <= kStackSize
 constexpr uint32_t kWideGlobalMaxLevels = 42;   // same bound for kWideStackSize (traversal from global memory)
 
+// Spheres so large that nearly every ray enters their box (RTIOW's radius-1000 ground: radius > 50 x the median radius) are
+// left out of the WIDE nodes and tested by every ray before the traversal instead -- by all lanes of a warp together, where a
+// leaf visit costs a divergent leaf turn.  The pair nodes keep them, so every other kernel is unaffected.  Needs one-sphere
+// leaves (leaf_size 1, the automatic choice for small scenes); at most 8.
+constexpr uint32_t kHugeMax = 8;
+constexpr float kHugeFactor = 50.0f;
+struct HugeList { uint32_t n; uint32_t idx[kHugeMax]; };
+VN_HD bool huge_leaf(uint32_t link, const HugeList& h) {
+    if (!(link & kLeafFlag) || (link & 7u) != 0u || link == kWideEmpty) return false;
+    const uint32_t first = (link & 0x7FFFFFFFu) >> 3;
+    bool is = false;
+    for (uint32_t k = 0; k < kHugeMax; k++) is = is || (k < h.n && h.idx[k] == first);
+    return is;
+}
+
 VN_HD float packed_area(const node_f4& a, const node_f4& b) { return box_area(a.x, a.y, a.z, b.x, b.y, b.z); }
 
 // Opens the pair at `pair_link`; out[] = packed-node indices of the (2..4) children in stable left-to-right order.
@@ -226,4 +241,20 @@ VN_HD void wide_octant_node(const node_f4* __restrict__ canon /* 8 float4 */, ui
     for (int r = 0; r < 7; r++) { out[r].x = v[r][0]; out[r].y = v[r][1]; out[r].z = v[r][2]; out[r].w = v[r][3]; }
 }
 
+}  // namespace vn
+
+#include <algorithm>
+#include <vector>
+namespace vn {
+// host: the huge list from the sorted spheres {c.xyz, r} of a small scene with one-sphere leaves (empty otherwise)
+inline void huge_list_from_geom(const node_f4* geom, uint32_t n, uint32_t leaf_size, HugeList& h) {
+    h = HugeList();
+    if (leaf_size != 1u || n < 16u) return;
+    std::vector<float> r(n);
+    for (uint32_t i = 0; i < n; i++) r[i] = fabsf(geom[i].w);
+    std::vector<float> tmp = r;
+    std::nth_element(tmp.begin(), tmp.begin() + n / 2, tmp.end());
+    const float limit = kHugeFactor * tmp[n / 2];
+    for (uint32_t i = 0; i < n && h.n < kHugeMax; i++) if (r[i] > limit) h.idx[h.n++] = i;
+}
 }  // namespace vn

@@ -80,9 +80,9 @@ __device__ __forceinline__ void finish_pixel(const RenderLaunch& p, uint32_t pix
 template <bool kCount>
 __device__ __forceinline__ void closest_hit_wide_vote(const float4* __restrict__ wnodes, uint32_t oct_stride, const float4* __restrict__ geom,
                                                       uint32_t root_link, uint32_t leaf_vote, f3 o, f3 d, float& t_out, int& prim_out,
-                                                      TraceCounters& cnt) {
-    float tbest = kTMax;
-    int prim = -1;
+                                                      TraceCounters& cnt, float tbest0, int prim0) {
+    float tbest = tbest0;              // closest hit among the huge spheres (tested by the caller, all lanes together)
+    int prim = prim0;
     const f3 idir = slab_idir(d);
     const float4* __restrict__ wn = wnodes + ray_octant(d) * oct_stride;
     const f3 ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
@@ -169,9 +169,10 @@ __device__ __forceinline__ void closest_hit_grid_vote(const GridHeader& g, const
 // Scenes too large for shared memory: canonical 128-byte wide nodes from L2/HBM (vn_math.cuh::wide_global_step), same vote.
 template <bool kCount>
 __device__ __forceinline__ void closest_hit_wide_global_vote(const float4* __restrict__ wide, const float4* __restrict__ geom, uint32_t root_link,
-                                                             uint32_t leaf_vote, f3 o, f3 d, float& t_out, int& prim_out, TraceCounters& cnt) {
-    float tbest = kTMax;
-    int prim = -1;
+                                                             uint32_t leaf_vote, f3 o, f3 d, float& t_out, int& prim_out, TraceCounters& cnt,
+                                                             float tbest0, int prim0) {
+    float tbest = tbest0;
+    int prim = prim0;
     const f3 idir = slab_idir(d);
     const f3 ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
     const float a = dot(d, d);
@@ -300,12 +301,27 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_persistent(const __grid_
         float t;
         int prim;
         if (kGrid) closest_hit_grid_vote<kCount>(p.grid, g_start, g_refs, sc.geom, p.grid_vote, st.o, st.d, t, prim, cnt);
-        else if (kWide && !kSmem) {
-            if (p.leaf_vote) closest_hit_wide_global_vote<kCount>(p.wide, sc.geom, p.wide_root, p.leaf_vote, st.o, st.d, t, prim, cnt);
-            else closest_hit_wide_global<kCount>(p.wide, sc.geom, p.wide_root, st.o, st.d, t, prim, cnt);
+        else if (kWide) {
+            // the huge spheres first (RTIOW: the ground): one convergent sphere test instead of a leaf turn per ray
+            float t0 = kTMax;
+            int prim0 = -1;
+            if (p.huge.n) {
+                const float a = dot(st.d, st.d), inv_a = rcp(a);
+                for (uint32_t i = 0; i < p.huge.n; i++) {
+                    const uint32_t hs = p.huge.idx[i];
+                    const float4 g = sc.geom[hs];
+                    if (kCount) cnt.spheres += 1;
+                    const float th = sphere_root(st.o, st.d, a, inv_a, g.x, g.y, g.z, g.w, kTMin, t0);
+                    if (th >= 0.0f) { t0 = th; prim0 = (int)hs; }
+                }
+            }
+            if (!kSmem) {
+                if (p.leaf_vote) closest_hit_wide_global_vote<kCount>(p.wide, sc.geom, p.wide_root, p.leaf_vote, st.o, st.d, t, prim, cnt, t0, prim0);
+                else closest_hit_wide_global<kCount>(p.wide, sc.geom, p.wide_root, st.o, st.d, t, prim, cnt, t0, prim0);
+            }
+            else if (p.leaf_vote) closest_hit_wide_vote<kCount>(sc.nodes, node_f4s, sc.geom, p.wide_root, p.leaf_vote, st.o, st.d, t, prim, cnt, t0, prim0);
+            else closest_hit_wide<kCount>(sc.nodes, node_f4s, sc.geom, p.wide_root, st.o, st.d, t, prim, cnt, t0, prim0);
         }
-        else if (kWide && p.leaf_vote) closest_hit_wide_vote<kCount>(sc.nodes, node_f4s, sc.geom, p.wide_root, p.leaf_vote, st.o, st.d, t, prim, cnt);
-        else if (kWide) closest_hit_wide<kCount>(sc.nodes, node_f4s, sc.geom, p.wide_root, st.o, st.d, t, prim, cnt);
         else closest_hit<kCount, kOct>(sc.nodes, sc.geom, sc.root_link, st.o, st.d, t, prim, cnt, node_f4s);
         n_seg += 1u;
         if (kCount) { n_nodes += cnt.nodes; n_sph += cnt.spheres; cnt.nodes = 0; cnt.spheres = 0; }

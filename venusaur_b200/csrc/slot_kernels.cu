@@ -188,6 +188,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_render_slots(const __grid_consta
                 inv_a = rcp(a);
                 tbest = kTMax;
                 prim = -1;
+                for (uint32_t i = 0; i < p.huge.n; i++) {                  // huge spheres are not in the wide nodes (lbvh_core.cuh::HugeList)
+                    const uint32_t hs = p.huge.idx[i];
+                    const float4 g = s_geom[hs];
+                    if (kCount) cnt.spheres += 1;
+                    const float th = sphere_root(o, d, a, inv_a, g.x, g.y, g.z, g.w, kTMin, tbest);
+                    if (th >= 0.0f) { tbest = th; prim = (int)hs; }
+                }
                 sp = 0;
                 cur = p.wide_root;
                 cur_slot = j;

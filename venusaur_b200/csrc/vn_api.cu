@@ -156,6 +156,7 @@ int fill_launch(vn_context* c, const vn_params* p, RenderLaunch& L) {
     L.num_nodes = (uint32_t)c->scene.num_nodes;
     L.num_spheres = (uint32_t)c->scene.n;
     L.wide = c->scene.wide; L.num_wide = c->scene.num_wide; L.wide_root = 0u;
+    L.huge = c->scene.huge;
     L.leaf_vote = c->leaf_vote;
     L.grid_vote = c->grid_vote;
     L.grid = c->grid.h; L.grid_start = c->grid.start; L.grid_refs = c->grid.refs;
@@ -395,6 +396,13 @@ int vn_read_grid(vn_handle c, void* header104, uint16_t* host_start, uint64_t ca
     if (host_start) VN_CUDA(c, cudaMemcpy(host_start, c->grid.start, std::min<uint64_t>(cap_start, c->grid.h.n_cells + 1ull) * 2, cudaMemcpyDeviceToHost));
     if (host_refs) VN_CUDA(c, cudaMemcpy(host_refs, c->grid.refs, std::min<uint64_t>(cap_refs, c->grid.h.n_refs) * 2, cudaMemcpyDeviceToHost));
     return 1;
+}
+
+int vn_read_huge(vn_handle c, uint32_t* idx8) {
+    VN_REQUIRE(c, c, "vn_read_huge: NULL handle");
+    VN_REQUIRE(c, c->bvh_valid, "vn_read_huge: no BVH (call vn_build_bvh)");
+    for (uint32_t i = 0; idx8 && i < c->scene.huge.n; i++) idx8[i] = c->scene.huge.idx[i];
+    return (int)c->scene.huge.n;
 }
 
 int vn_last_accel(vn_handle c) { return c ? (int)c->last_accel : 0; }

@@ -459,9 +459,9 @@ VN_HD uint32_t leaf_step(const node_f4* __restrict__ geom, uint32_t cur, f3 o, f
 }
 template <bool kCount>
 VN_HD void closest_hit_wide(const node_f4* __restrict__ wnodes, uint32_t oct_stride, const node_f4* __restrict__ geom, uint32_t root_link,
-                            f3 o, f3 d, float& t_out, int& prim_out, TraceCounters& cnt) {
-    float tbest = kTMax;
-    int prim = -1;
+                            f3 o, f3 d, float& t_out, int& prim_out, TraceCounters& cnt, float tbest0 = kTMax, int prim0 = -1) {
+    float tbest = tbest0;              // closest hit among the huge spheres tested before the traversal (lbvh_core.cuh::HugeList)
+    int prim = prim0;
     {
         const f3 idir = slab_idir(d);
         const node_f4* __restrict__ wn = wnodes + ray_octant(d) * oct_stride;
@@ -542,9 +542,9 @@ VN_HD uint32_t wide_global_step(const node_f4* __restrict__ wide, uint32_t cur, 
 }
 template <bool kCount>
 VN_HD void closest_hit_wide_global(const node_f4* __restrict__ wide, const node_f4* __restrict__ geom, uint32_t root_link,
-                                   f3 o, f3 d, float& t_out, int& prim_out, TraceCounters& cnt) {
-    float tbest = kTMax;
-    int prim = -1;
+                                   f3 o, f3 d, float& t_out, int& prim_out, TraceCounters& cnt, float tbest0 = kTMax, int prim0 = -1) {
+    float tbest = tbest0;
+    int prim = prim0;
     {
         const f3 idir = slab_idir(d);
         const f3 ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
