@@ -433,8 +433,8 @@ struct Arena {
 };
 }  // namespace
 
-int lbvh_build(const vn_sphere* d_spheres, uint64_t n64, uint32_t leaf_size, float pad_rel, uint32_t sah_max_prims, uint32_t wide_max_prims, int num_sms,
-               cudaStream_t stream,
+int lbvh_build(const vn_sphere* d_spheres, uint64_t n64, uint32_t leaf_size, float pad_rel, uint32_t sah_max_prims, uint32_t wide_max_prims, float huge_factor,
+               int num_sms, cudaStream_t stream,
                LbvhScene& out, LbvhWorkspace& ws, uint32_t* launches, std::string& err) {
     lbvh_free(out);
     if (n64 > (1ull << 28)) { err = "too many spheres (limit 2^28)"; return -1; }
@@ -553,7 +553,7 @@ int lbvh_build(const vn_sphere* d_spheres, uint64_t n64, uint32_t leaf_size, flo
             std::vector<node_f4> hgeom(n);
             LB_CHECK(cudaMemcpyAsync(hgeom.data(), out.geom, 16ull * n, cudaMemcpyDeviceToHost, stream));
             LB_CHECK(cudaStreamSynchronize(stream));
-            huge_list_from_geom(hgeom.data(), n, leaf_size, out.huge);
+            huge_list_from_geom(hgeom.data(), n, leaf_size, out.huge, huge_factor);
             // sah_u32 is free again here (the SAH pass, if any, has been consumed by the second gather): queue of pair links
             k_wide_build<<<1, kBlock, 0, stream>>>(out.nodes, sah_u32, n, out.wide, result, out.huge);
             launched += 1;
@@ -606,7 +606,7 @@ int lbvh_build(const vn_sphere* d_spheres, uint64_t n64, uint32_t leaf_size, flo
             // a degenerate scene (e.g. hundreds of coincident spheres) makes SAH peel one primitive per level; the
             // traversal stack holds kStackSize entries, so fall back to Karras, whose height is bounded by the key width
             if (launches) *launches += launched;
-            return lbvh_build(d_spheres, n64, leaf_size, pad_rel, 0u, wide_max_prims, num_sms, stream, out, ws, launches, err);
+            return lbvh_build(d_spheres, n64, leaf_size, pad_rel, 0u, wide_max_prims, huge_factor, num_sms, stream, out, ws, launches, err);
         }
     }
     if (launches) *launches += launched;

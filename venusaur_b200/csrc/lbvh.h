@@ -44,8 +44,8 @@ struct LbvhWorkspace {
 void lbvh_workspace_free(LbvhWorkspace& ws);
 
 // Builds the packed LBVH for n spheres already resident on the device.  Returns 0 or a negative status with `err` set.
-int lbvh_build(const vn_sphere* d_spheres, uint64_t n, uint32_t leaf_size, float pad_rel, uint32_t sah_max_prims, uint32_t wide_max_prims, int num_sms,
-               cudaStream_t stream,
+int lbvh_build(const vn_sphere* d_spheres, uint64_t n, uint32_t leaf_size, float pad_rel, uint32_t sah_max_prims, uint32_t wide_max_prims, float huge_factor,
+               int num_sms, cudaStream_t stream,
                LbvhScene& out, LbvhWorkspace& ws, uint32_t* launches, std::string& err);
 
 // Onesweep sort of device (key, value) pairs; returns 0/1 = which buffer pair holds the result, or -1.

@@ -247,14 +247,15 @@ VN_HD void wide_octant_node(const node_f4* __restrict__ canon /* 8 float4 */, ui
 #include <vector>
 namespace vn {
 // host: the huge list from the sorted spheres {c.xyz, r} of a small scene with one-sphere leaves (empty otherwise)
-inline void huge_list_from_geom(const node_f4* geom, uint32_t n, uint32_t leaf_size, HugeList& h) {
+inline void huge_list_from_geom(const node_f4* geom, uint32_t n, uint32_t leaf_size, HugeList& h, float factor = kHugeFactor) {
     h = HugeList();
     if (leaf_size != 1u || n < 16u) return;
     std::vector<float> r(n);
     for (uint32_t i = 0; i < n; i++) r[i] = fabsf(geom[i].w);
     std::vector<float> tmp = r;
     std::nth_element(tmp.begin(), tmp.begin() + n / 2, tmp.end());
-    const float limit = kHugeFactor * tmp[n / 2];
+    if (!(factor > 0.0f)) return;
+    const float limit = factor * tmp[n / 2];
     for (uint32_t i = 0; i < n && h.n < kHugeMax; i++) if (r[i] > limit) h.idx[h.n++] = i;
 }
 }  // namespace vn

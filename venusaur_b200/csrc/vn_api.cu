@@ -74,6 +74,7 @@ struct vn_context {
     uint32_t grid_vote = 0;           // see closest_hit_grid_vote (path_kernels.cu): 0 = while-while (fastest measured), n = voted sphere turns
     uint32_t grid_max_per_cell = 16;  // a cell with more spheres than this disqualifies the grid (clustered scenes: the BVH adapts, a grid does not)
     uint32_t last_accel = 0;          // what the last vn_render traversed: 1 pair nodes, 2 wide nodes (shared memory), 3 wide nodes (L2/HBM), 4 grid
+    float huge_factor = 50.0f;        // spheres with radius > huge_factor x median are tested before the wide traversal (0 = none), lbvh_core.cuh::HugeList
     int wide_threads = 1024;          // CTA size of the wide-node path kernel (one CTA per SM): 512, 768 or 1024
     uint32_t leaf_vote = 12;          // see closest_hit_wide_vote (path_kernels.cu); 0 = while-while
     bool wide_nodes = true;           // use them when they fit in shared memory
@@ -277,6 +278,7 @@ int vn_set_option(vn_handle c, const char* name, double value) {
     else if (k == "accel") { VN_REQUIRE(c, value == 0 || value == 1 || value == 2, "accel must be 0 (auto), 1 (BVH) or 2 (grid)"); c->accel = (uint32_t)value; c->bvh_valid = false; }
     else if (k == "grid_vote") { VN_REQUIRE(c, value >= 0 && value <= 33, "grid_vote must be in [0,33]"); c->grid_vote = (uint32_t)value; }
     else if (k == "grid_max_per_cell") { VN_REQUIRE(c, value >= 1 && value <= 65535, "grid_max_per_cell must be in [1,65535]"); c->grid_max_per_cell = (uint32_t)value; c->bvh_valid = false; }
+    else if (k == "huge_factor") { VN_REQUIRE(c, value >= 0, "huge_factor must be >= 0"); c->huge_factor = (float)value; c->bvh_valid = false; }
     else if (k == "wide_threads") { VN_REQUIRE(c, value == 512 || value == 768 || value == 1024, "wide_threads must be 512, 768 or 1024"); c->wide_threads = (int)value; }
     else if (k == "leaf_vote") { VN_REQUIRE(c, value >= 0 && value <= 32, "leaf_vote must be in [0,32]"); c->leaf_vote = (uint32_t)value; }
     else if (k == "slot_kernel") { c->slot_kernel = value != 0; }
@@ -335,11 +337,11 @@ int vn_build_bvh(vn_handle c) {
     const bool small = c->n_spheres >= 2 && c->n_spheres <= c->sah_max_prims && c->n_spheres <= c->wide_max_prims && c->n_spheres <= 16384;
     int rc = 0;
     for (uint32_t leaf_size = c->leaf_size ? c->leaf_size : (small ? 1u : 2u);; leaf_size++) {
-        rc = lbvh_build(c->d_spheres, c->n_spheres, leaf_size, c->aabb_pad, c->sah_max_prims, c->wide_max_prims, c->num_sms, c->stream, c->scene, c->bvh_ws, &launches, err);
+        rc = lbvh_build(c->d_spheres, c->n_spheres, leaf_size, c->aabb_pad, c->sah_max_prims, c->wide_max_prims, c->huge_factor, c->num_sms, c->stream, c->scene, c->bvh_ws, &launches, err);
         if (rc != 0 || c->leaf_size || !small) break;
         if (c->scene.num_wide > 0 && c->scene.wide_levels <= kWideMaxLevels && wide_smem_bytes(c->scene.num_wide, (uint32_t)c->scene.n) + 2048 <= c->smem_optin) break;
         if (leaf_size >= 4u) {      // the wide copies never fit: the pair nodes will be traversed, which like 3 spheres per leaf best
-            rc = lbvh_build(c->d_spheres, c->n_spheres, 3u, c->aabb_pad, c->sah_max_prims, c->wide_max_prims, c->num_sms, c->stream, c->scene, c->bvh_ws, &launches, err);
+            rc = lbvh_build(c->d_spheres, c->n_spheres, 3u, c->aabb_pad, c->sah_max_prims, c->wide_max_prims, c->huge_factor, c->num_sms, c->stream, c->scene, c->bvh_ws, &launches, err);
             break;
         }
     }
