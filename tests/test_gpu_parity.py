@@ -404,7 +404,7 @@ def test_octant_and_plain_persistent_kernels_agree(rtiow_ctx):
     finally:
         rtiow_ctx.set_option("octant_nodes", 1)
         rtiow_ctx.set_option("wide_nodes", 1)
-        rtiow_ctx.set_option("leaf_vote", 12)
+        rtiow_ctx.set_option("leaf_vote", 0)
     assert se.segments == sf.segments == sa.segments
     assert np.array_equal(a.view(np.uint32), e.view(np.uint32)) and np.array_equal(ia, ie) and np.array_equal(a.view(np.uint32), f.view(np.uint32))
     assert sf.sphere_tests <= 1.02 * sc.sphere_tests and sf.node_visits < 0.55 * sc.node_visits
@@ -514,11 +514,11 @@ def test_grid_and_bvh_path_kernels_agree(rtiow_ctx, oracle_mod, rtiow):
     assert rtiow_ctx.last_accel() == 4
     ac, _, sac = render(rtiow_ctx, cam, W, H, spp, 2, depth, flags=VN_COUNTERS)
     try:
-        for threads in (512, 768):
+        for threads in (512, 1024):
             rtiow_ctx.set_option("wide_threads", threads)
             t, it, stt = render(rtiow_ctx, cam, W, H, spp, 2, depth)
             assert np.array_equal(a.view(np.uint32), t.view(np.uint32)) and stt.segments == sa.segments
-        rtiow_ctx.set_option("wide_threads", 1024)
+        rtiow_ctx.set_option("wide_threads", 768)
         for vote in (0, 1, 12, 33):
             rtiow_ctx.set_option("grid_vote", vote)
             t, it, stt = render(rtiow_ctx, cam, W, H, spp, 2, depth, flags=VN_COUNTERS)
@@ -532,7 +532,7 @@ def test_grid_and_bvh_path_kernels_agree(rtiow_ctx, oracle_mod, rtiow):
         assert rtiow_ctx.last_accel() == 2
         bc, _, sbc = render(rtiow_ctx, cam, W, H, spp, 2, depth, flags=VN_COUNTERS)
     finally:
-        rtiow_ctx.set_option("wide_threads", 1024)
+        rtiow_ctx.set_option("wide_threads", 768)
         rtiow_ctx.set_option("grid_vote", 0)
         rtiow_ctx.set_option("accel", 1)
     assert sa.segments == sb.segments == sac.segments == sbc.segments and sa.paths == sb.paths
@@ -805,7 +805,7 @@ def test_large_scene_from_hbm_matches_oracle(ctx, oracle_mod):
             if flags & VN_COUNTERS:
                 assert st.node_visits / st.segments < 30          # the wide nodes really were traversed (pairs: ~50)
         finally:
-            ctx.set_option("leaf_vote", 12)
+            ctx.set_option("leaf_vote", 0)
             ctx.set_option("wide_global", 0)
         # distant small spheres: grazing rays inside the float noise of the quadratic may be culled by one BVH and not
         # the other (tie/grazing order is unspecified in OptiX too) -- allow a handful of pixels

@@ -17,12 +17,12 @@ $B --steps 16 --opt accel=0 2>&1 | tail -1 > gpurun_out/bench_grid.log
 $B --steps 16 --opt huge_factor=0 2>&1 | tail -1 > gpurun_out/bench_nohuge.log
 $B --steps 16 --kernel slots --leaf-size 3 2>&1 | tail -1 > gpurun_out/bench_slots.log
 $B --steps 16 --opt wide_nodes=0 --opt sah_max_prims=0 --leaf-size 2 2>&1 | tail -1 > gpurun_out/bench_karras_pairs.log
-$B --steps 16 --opt leaf_vote=0 2>&1 | tail -1 > gpurun_out/bench_novote.log
+$B --steps 16 --opt leaf_vote=12 --opt wide_threads=1024 2>&1 | tail -1 > gpurun_out/bench_vote12.log
 $B --steps 16 --workload c1 2>&1 | tail -1 > gpurun_out/bench_c1.log
 $B --steps 8 --workload c3 2>&1 | tail -1 > gpurun_out/bench_c3_n1.log
 $B --steps 4 --workload c4 2>&1 | tail -1 > gpurun_out/bench_c4.log
 $B --steps 4 --workload c5 2>&1 | tail -1 > gpurun_out/bench_c5.log
-for f in grid nohuge slots karras_pairs novote c1 c3_n1 c4 c5; do python -c "
+for f in grid nohuge slots karras_pairs vote12 c1 c3_n1 c4 c5; do python -c "
 import json,sys
 try:
     d=json.loads(open('gpurun_out/bench_$f.log').read().strip().splitlines()[-1]); print('$f: %.0f Mrays/s e2e %.0f ms/step %.3f' % (d['value'], d['e2e']['value'], d['ms_per_step']))

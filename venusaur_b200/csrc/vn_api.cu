@@ -75,8 +75,8 @@ struct vn_context {
     uint32_t grid_max_per_cell = 16;  // a cell with more spheres than this disqualifies the grid (clustered scenes: the BVH adapts, a grid does not)
     uint32_t last_accel = 0;          // what the last vn_render traversed: 1 pair nodes, 2 wide nodes (shared memory), 3 wide nodes (L2/HBM), 4 grid
     float huge_factor = 50.0f;        // spheres with radius > huge_factor x median are tested before the wide traversal (0 = none), lbvh_core.cuh::HugeList
-    int wide_threads = 1024;          // CTA size of the wide-node path kernel (one CTA per SM): 512, 768 or 1024
-    uint32_t leaf_vote = 12;          // see closest_hit_wide_vote (path_kernels.cu); 0 = while-while
+    int wide_threads = 768;           // CTA size of the wide-node path kernel (one CTA per SM): 512, 768 or 1024
+    uint32_t leaf_vote = 0;           // see closest_hit_wide_vote (path_kernels.cu); 0 = while-while
     bool wide_nodes = true;           // use them when they fit in shared memory
     uint32_t sah_max_prims = 4096;    // scenes up to this size get SAH splits (k_sah_small); 0 = always Karras
     int threads = 256;
