@@ -414,6 +414,43 @@ def test_octant_and_plain_persistent_kernels_agree(rtiow_ctx):
     assert sc.node_visits == sd.node_visits and sc.sphere_tests == sd.sphere_tests
 
 
+@pytest.mark.parametrize("threads", [512, 768, 1024])
+def test_async_kernel_equals_persistent_kernel(ctx, oracle_mod, rtiow, threads):
+    """k_render_async (asynchronous shading: lanes keep their traversal state across the shading of other lanes, voted node /
+    leaf turns) only changes WHEN a lane takes its steps: accumulation buffer, image, segment / node / sphere counters are those
+    of k_render_persistent, and the accumulation buffer is the oracle's bit for bit -- for every threshold setting, CTA size,
+    ragged frames whose lanes retire early, and frames smaller than one warp."""
+    ctx.set_spheres(rtiow)
+    ctx.build_bvh()                                             # defaults: SAH, 4-wide nodes, huge list, one sphere per leaf
+    try:
+        ctx.set_option("wide_threads", threads)
+        for (W, H, spp, sub, depth) in ((200, 120, 6, 2, 50), (33, 17, 5, 9, 8), (5, 3, 3, 1, 50)):
+            cam = vb.rtiow_camera(W, H)
+            ctx.set_option("async_done", 0)
+            e, ie, se = render(ctx, cam, W, H, spp, sub, depth)
+            f, iff, sf = render(ctx, cam, W, H, spp, sub, depth, flags=VN_COUNTERS)
+            orc = oracle_mod.Oracle(rtiow)
+            want, ost = orc.render_mean(orc.params(cam.frame(), W, H, spp, sub, depth, atten=oracle_mod.ATTEN_FORWARD))
+            assert np.array_equal(e.view(np.uint32), want.view(np.uint32)) and se.segments == ost.segments
+            for done, node, leaf in ((32, 1, 1), (24, 8, 8), (1, 1, 1), (16, 32, 32), (28, 12, 4)):
+                ctx.set_option("async_done", done)
+                ctx.set_option("async_node", node)
+                ctx.set_option("async_leaf", leaf)
+                g, ig, sg = render(ctx, cam, W, H, spp, sub, depth)
+                assert ctx.last_accel() == 2                    # wide nodes in shared memory
+                assert np.array_equal(g.view(np.uint32), e.view(np.uint32)) and np.array_equal(ig, ie), (W, H, done, node, leaf)
+                assert (sg.segments, sg.paths) == (se.segments, se.paths)
+                h, ih, sh = render(ctx, cam, W, H, spp, sub, depth, flags=VN_COUNTERS)
+                assert np.array_equal(h.view(np.uint32), e.view(np.uint32))
+                assert (sh.segments, sh.node_visits, sh.sphere_tests) == (sf.segments, sf.node_visits, sf.sphere_tests)
+    finally:
+        ctx.set_option("async_done", 0)
+        ctx.set_option("async_node", 8)
+        ctx.set_option("async_leaf", 8)
+        ctx.set_option("wide_threads", 768)
+
+
+
 @pytest.mark.parametrize("slots,threads", [(3, 768), (2, 1024), (4, 512), (2, 768), (3, 512), (4, 384)])
 def test_slot_kernel_equals_persistent_kernel(rtiow_ctx, slots, threads):
     """The slot-scheduled kernel (K path slots per lane, warp-voted node / leaf / retire / shade-by-material / camera

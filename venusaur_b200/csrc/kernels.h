@@ -39,6 +39,7 @@ struct RenderLaunch {
     const uint16_t* grid_refs;
     uint32_t grid_vote;              // grid traversal: lanes holding an untested sphere that trigger the sphere turn (0 = while-while)
     uint32_t leaf_vote;              // wide traversal: lanes waiting at a leaf that trigger the leaf turn (0 = while-while phases)
+    uint32_t async_done, async_node, async_leaf;   // k_render_async: lanes with a finished ray that end a traversal burst; lanes that keep node steps / trigger a leaf turn
     unsigned long long* counters;    // [0] segments, [1] paths, [2] node visits, [3] sphere tests
     uint32_t* work_counter;          // persistent-thread work ticket
     uint32_t total_work, tiles_x;    // work items = 8x4 pixel tiles * 32
@@ -53,6 +54,7 @@ struct KernelConfig {
     bool octant;                     // nodes staged 8x in shared memory, once per ray-direction octant (near/far-plane form)
     bool wide;                       // 4-wide octant-sorted nodes in shared memory (implies scene_in_smem; excludes octant)
     bool grid;                       // uniform grid + oversize list in shared memory (excludes the others)
+    bool async = false;              // k_render_async (wide nodes in shared memory only): asynchronous shading, see path_kernels.cu
 };
 
 // Vote thresholds of the slot-scheduled kernel (slot_kernels.cu): an operation runs when that many lanes wait for it.

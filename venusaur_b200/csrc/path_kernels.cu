@@ -349,6 +349,167 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_persistent(const __grid_
     }
 }
 
+// k_render_async: the wide-node path kernel with ASYNCHRONOUS shading.  In k_render_persistent every lane of a warp traces one
+// segment per round and the round lasts as long as its slowest ray (RTIOW: 4.8 node steps per ray, but 13.7 node turns per round);
+// here a lane keeps its traversal state (current link, stack, closest hit) across the shading code, so the warp can leave the
+// traversal as soon as `async_done` lanes have finished, shade those and give them their next ray while the stragglers simply
+// continue in the next burst.  Inside the burst the turns are voted like closest_hit_wide_vote: a leaf turn when `async_leaf`
+// lanes wait at a leaf (or nobody stands on a node), else node steps for as long as `async_node` lanes stand on nodes.  Every lane
+// still walks its own pixel's samples in order and runs exactly the per-ray steps of closest_hit_wide(), so the result is
+// bit-identical to k_render_persistent; only the order in which a warp's lanes take their turns differs (tools/simt_sim_async.cpp
+// is the model the thresholds came from).  Lanes that run out of pixels stay in the loop as zombies until the whole warp is done,
+// which keeps every vote a full-mask __ballot_sync.
+template <bool kCount, int kMaxThreads>
+__global__ void __launch_bounds__(kMaxThreads) k_render_async(const __grid_constant__ RenderLaunch p) {
+    extern __shared__ float4 s_scene[];
+    SceneView sc;
+    const uint32_t node_f4s = kWideNodeF4 * p.num_wide;
+    {
+        float4* s_nodes = s_scene;
+        float4* s_geom = s_nodes + (size_t)node_f4s * 8;
+        float4* s_mat = s_geom + p.num_spheres;
+        uint8_t* s_type = reinterpret_cast<uint8_t*>(s_mat + p.num_spheres);
+        for (uint32_t i = threadIdx.x; i < 8u * p.num_wide; i += blockDim.x) {
+            const uint32_t k = i / p.num_wide, j = i - k * p.num_wide;
+            float4 canon[8], out[kWideNodeF4];
+#pragma unroll
+            for (int q = 0; q < 8; q++) canon[q] = p.wide[8ull * j + q];
+            wide_octant_node(canon, k, out);
+#pragma unroll
+            for (int q = 0; q < (int)kWideNodeF4; q++) s_nodes[(size_t)k * node_f4s + kWideNodeF4 * j + q] = out[q];
+        }
+        for (uint32_t i = threadIdx.x; i < p.num_spheres; i += blockDim.x) { s_geom[i] = p.geom[i]; s_mat[i] = p.mat[i]; }
+        for (uint32_t i = threadIdx.x; i < p.num_spheres; i += blockDim.x) s_type[i] = p.type[i];
+        __syncthreads();
+        sc.nodes = s_nodes; sc.geom = s_geom; sc.mat = s_mat; sc.type = s_type;
+    }
+    sc.root_link = p.root_link;
+    constexpr unsigned kFull = 0xFFFFFFFFu;
+
+    uint32_t pix = 0, px = 0, py = 0, cam_seed = 0, s_left = 0;
+    bool has_pixel = false, active = false, retired = false;
+    f3 sum = mk3(0.0f);
+    PathState st;
+    st.o = st.d = st.thr = mk3(0.0f); st.seed = 0; st.depth = 0;
+    uint32_t n_seg = 0, n_path = 0;
+    TraceCounters cnt{0u, 0u};
+    // traversal state, alive across the shading of other lanes
+    uint32_t stack[kStackSize];
+    int sp = 0;
+    uint32_t cur = kEmptyScene;
+    float tbest = kTMax;
+    int prim = -1;
+    f3 idir = mk3(0.0f), ood = mk3(0.0f);
+    const float4* __restrict__ wn = sc.nodes;
+    const uint32_t t_node = p.async_node, t_leaf = p.async_leaf;
+
+    for (;;) {
+        if (cur == kEmptyScene && !retired) {
+            if (active) {                                         // a finished traversal: shade it
+                n_seg += 1u;
+                f3 result;
+                if (!shade_segment(sc, st, tbest, prim, result)) {
+                    sum = sum + result;                           // pixel_color += prd.attenuation (RayTracer.cu:203)
+                    active = false;
+                }
+            }
+            if (!active) {
+                if (has_pixel && s_left == 0u) { finish_pixel(p, pix, sum); has_pixel = false; }
+                if (!has_pixel) {
+                    bool got = false;
+                    for (;;) {
+                        const uint32_t w = fetch_work(p.work_counter);
+                        if (w >= p.total_work) break;
+                        const uint32_t tile = w >> 5, in = w & 31u;
+                        const uint32_t ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+                        px = tx * 8u + (in & 7u);
+                        py = p.row_begin + ty * 4u + (in >> 3);
+                        if (px < p.width && py < p.row_end) { got = true; break; }
+                    }
+                    if (got) {
+                        pix = py * p.width + px;
+                        cam_seed = tea4(pix, p.subframe_index);   // RayTracer.cu:169
+                        sum = mk3(0.0f);
+                        s_left = p.spp;
+                        has_pixel = true;
+                    } else retired = true;                        // no pixels left: this lane only votes from now on
+                }
+                if (!retired) {
+                    camera_ray(p.cam, px, py, cam_seed, st.o, st.d);   // RayTracer.cu:173-177
+                    st.thr = mk3(1.0f);
+                    st.seed = cam_seed;                           // prd.seed = seed: a copy (RayTracer.cu:183)
+                    st.depth = (int)p.max_depth - 1;              // RayTracer.cu:184
+                    s_left -= 1u;
+                    active = true;
+                    n_path += 1u;
+                }
+            }
+            if (!retired) {
+                // start the next segment: the huge spheres first (lbvh_core.cuh::HugeList), then the traversal constants
+                tbest = kTMax;
+                prim = -1;
+                if (p.huge.n) {
+                    const float a = dot(st.d, st.d), inv_a = rcp(a);
+                    for (uint32_t i = 0; i < p.huge.n; i++) {
+                        const uint32_t hs = p.huge.idx[i];
+                        const float4 g = sc.geom[hs];
+                        if (kCount) cnt.spheres += 1;
+                        const float th = sphere_root(st.o, st.d, a, inv_a, g.x, g.y, g.z, g.w, kTMin, tbest);
+                        if (th >= 0.0f) { tbest = th; prim = (int)hs; }
+                    }
+                }
+                idir = slab_idir(st.d);
+                wn = sc.nodes + ray_octant(st.d) * node_f4s;
+                ood = mk3(st.o.x * idir.x, st.o.y * idir.y, st.o.z * idir.z);
+                sp = 0;
+                cur = p.wide_root;
+            }
+        }
+        const unsigned live = __ballot_sync(kFull, !retired);
+        if (live == 0u) break;
+        const uint32_t n_live = (uint32_t)__popc(live);
+        const uint32_t t_done = p.async_done < n_live ? p.async_done : n_live;
+        // traversal burst: voted node / leaf turns until t_done lanes hold a finished ray
+        for (;;) {
+            const bool done = cur == kEmptyScene;
+            const bool at_leaf = !done && (cur & kLeafFlag) != 0u;
+            const uint32_t nd = (uint32_t)__popc(__ballot_sync(kFull, done && !retired));
+            const uint32_t nl = (uint32_t)__popc(__ballot_sync(kFull, at_leaf));
+            if (nd >= t_done) break;
+            if (nl >= t_leaf || nd + nl == n_live) {
+                if (at_leaf) {
+                    const float a = dot(st.d, st.d);
+                    cur = leaf_step<kCount>(sc.geom, cur, st.o, st.d, a, rcp(a), tbest, prim, stack, sp, cnt);
+                }
+            } else {
+                for (;;) {
+                    const bool at_node = (cur & kLeafFlag) == 0u;
+                    if (at_node) {
+                        if (kCount) cnt.nodes += 1;
+                        cur = wide_node_step(wn, cur, idir, ood, tbest, stack, sp);
+                    }
+                    if ((uint32_t)__popc(__ballot_sync(kFull, (cur & kLeafFlag) == 0u)) < t_node) break;
+                }
+            }
+        }
+    }
+    {
+        unsigned long long seg = n_seg, path = n_path, nn = cnt.nodes, ns = cnt.spheres;
+        cg::coalesced_group g = cg::coalesced_threads();
+        seg = cg::reduce(g, seg, cg::plus<unsigned long long>());
+        path = cg::reduce(g, path, cg::plus<unsigned long long>());
+        if (kCount) {
+            nn = cg::reduce(g, nn, cg::plus<unsigned long long>());
+            ns = cg::reduce(g, ns, cg::plus<unsigned long long>());
+        }
+        if (g.thread_rank() == 0) {
+            atomicAdd(&p.counters[0], seg);
+            atomicAdd(&p.counters[1], path);
+            if (kCount) { atomicAdd(&p.counters[2], nn); atomicAdd(&p.counters[3], ns); }
+        }
+    }
+}
+
 // Kernel (3) of the north star when used stand-alone: image = make_color(accum * scale).  One pixel per thread:
 // a warp reads 512 contiguous bytes of float4 and writes 128 contiguous bytes of uchar4.
 __global__ void __launch_bounds__(256) k_tonemap(const float4* __restrict__ accum, float scale, uint32_t* __restrict__ image, uint64_t n) {
@@ -454,7 +615,12 @@ inline uint32_t grid_for(uint64_t n, int threads) { return (uint32_t)((n + threa
 
 namespace {
 typedef void (*PathKernel)(const RenderLaunch);
-PathKernel pick_kernel(bool scene_in_smem, bool count, bool octant, bool wide = false, int threads = 1024, bool grid = false) {
+PathKernel pick_kernel(bool scene_in_smem, bool count, bool octant, bool wide = false, int threads = 1024, bool grid = false, bool async = false) {
+    if (async && wide && scene_in_smem && !grid) {
+        if (threads <= 512) return count ? k_render_async<true, 512> : k_render_async<false, 512>;
+        if (threads <= 768) return count ? k_render_async<true, 768> : k_render_async<false, 768>;
+        return count ? k_render_async<true, 1024> : k_render_async<false, 1024>;
+    }
     if (grid && threads <= 512) return count ? k_render_persistent<true, true, false, 512, false, true> : k_render_persistent<true, false, false, 512, false, true>;
     if (grid && threads <= 768) return count ? k_render_persistent<true, true, false, 768, false, true> : k_render_persistent<true, false, false, 768, false, true>;
     if (grid) return count ? k_render_persistent<true, true, false, 1024, false, true> : k_render_persistent<true, false, false, 1024, false, true>;
@@ -470,14 +636,14 @@ PathKernel pick_kernel(bool scene_in_smem, bool count, bool octant, bool wide = 
 
 int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool count, bool octant, bool wide, bool grid) {
     int nb = 0;
-    PathKernel k = pick_kernel(scene_in_smem, count, octant, wide, threads, grid);
+    PathKernel k = pick_kernel(scene_in_smem, count, octant, wide, threads, grid, false);
     if (smem_bytes > 48 * 1024 && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) return -1;
     const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, threads, smem_bytes);
     return e == cudaSuccess ? nb : -1;
 }
 
 cudaError_t launch_render_persistent(const RenderLaunch& p, const KernelConfig& cfg, cudaStream_t stream) {
-    PathKernel k = pick_kernel(cfg.scene_in_smem, cfg.count, cfg.octant, cfg.wide, cfg.threads, cfg.grid);
+    PathKernel k = pick_kernel(cfg.scene_in_smem, cfg.count, cfg.octant, cfg.wide, cfg.threads, cfg.grid, cfg.async);
     if (cfg.smem_bytes > 48 * 1024) {
         const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes);
         if (e != cudaSuccess) return e;

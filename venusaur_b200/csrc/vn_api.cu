@@ -77,6 +77,8 @@ struct vn_context {
     float huge_factor = 50.0f;        // spheres with radius > huge_factor x median are tested before the wide traversal (0 = none), lbvh_core.cuh::HugeList
     int wide_threads = 768;           // CTA size of the wide-node path kernel (one CTA per SM): 512, 768 or 1024
     uint32_t leaf_vote = 0;           // see closest_hit_wide_vote (path_kernels.cu); 0 = while-while
+    uint32_t async_done = 0;          // k_render_async: a traversal burst ends when this many lanes hold a finished ray (0 = k_render_persistent)
+    uint32_t async_node = 8, async_leaf = 8;
     bool wide_nodes = true;           // use them when they fit in shared memory
     uint32_t sah_max_prims = 4096;    // scenes up to this size get SAH splits (k_sah_small); 0 = always Karras
     int threads = 256;
@@ -159,6 +161,7 @@ int fill_launch(vn_context* c, const vn_params* p, RenderLaunch& L) {
     L.wide = c->scene.wide; L.num_wide = c->scene.num_wide; L.wide_root = 0u;
     L.huge = c->scene.huge;
     L.leaf_vote = c->leaf_vote;
+    L.async_done = c->async_done; L.async_node = c->async_node; L.async_leaf = c->async_leaf;
     L.grid_vote = c->grid_vote;
     L.grid = c->grid.h; L.grid_start = c->grid.start; L.grid_refs = c->grid.refs;
     L.counters = c->d_counters;
@@ -280,6 +283,9 @@ int vn_set_option(vn_handle c, const char* name, double value) {
     else if (k == "grid_max_per_cell") { VN_REQUIRE(c, value >= 1 && value <= 65535, "grid_max_per_cell must be in [1,65535]"); c->grid_max_per_cell = (uint32_t)value; c->bvh_valid = false; }
     else if (k == "huge_factor") { VN_REQUIRE(c, value >= 0, "huge_factor must be >= 0"); c->huge_factor = (float)value; c->bvh_valid = false; }
     else if (k == "wide_threads") { VN_REQUIRE(c, value == 512 || value == 768 || value == 1024, "wide_threads must be 512, 768 or 1024"); c->wide_threads = (int)value; }
+    else if (k == "async_done") { VN_REQUIRE(c, value >= 0 && value <= 32, "async_done must be in [0,32]"); c->async_done = (uint32_t)value; }
+    else if (k == "async_node") { VN_REQUIRE(c, value >= 1 && value <= 32, "async_node must be in [1,32]"); c->async_node = (uint32_t)value; }
+    else if (k == "async_leaf") { VN_REQUIRE(c, value >= 1 && value <= 32, "async_leaf must be in [1,32]"); c->async_leaf = (uint32_t)value; }
     else if (k == "leaf_vote") { VN_REQUIRE(c, value >= 0 && value <= 32, "leaf_vote must be in [0,32]"); c->leaf_vote = (uint32_t)value; }
     else if (k == "slot_kernel") { c->slot_kernel = value != 0; }
     else if (k == "slot_slots" || k == "slot_threads") {
@@ -682,7 +688,7 @@ int vn_render(vn_handle c, const vn_params* p) {
         // small scenes of similar-sized spheres: uniform grid + oversize list (grid_core.cuh), 40 % of the BVH's instructions on RTIOW
         cfg.grid = c->accel != 1u && c->grid.valid && grid_smem_bytes(c->grid.h.n_cells, c->grid.h.n_refs, L.num_spheres) + 2048 <= c->smem_optin;
         if (cfg.grid) { cfg.scene_in_smem = true; cfg.octant = false; cfg.wide = false; cfg.smem_bytes = grid_smem_bytes(c->grid.h.n_cells, c->grid.h.n_refs, L.num_spheres); cfg.threads = c->wide_threads; }
-        else if (cfg.wide) { cfg.scene_in_smem = true; cfg.octant = false; cfg.smem_bytes = wide_bytes; cfg.threads = c->wide_threads; }
+        else if (cfg.wide) { cfg.scene_in_smem = true; cfg.octant = false; cfg.smem_bytes = wide_bytes; cfg.threads = c->wide_threads; cfg.async = c->async_done > 0u; }
         else if (wide_global) { cfg.wide = true; cfg.octant = false; if (cfg.threads > 256) cfg.threads = 256; }
         else if (cfg.octant) { cfg.smem_bytes = oct_bytes; cfg.threads = 1024; }
         else if (cfg.threads > 256) cfg.threads = 256;

@@ -415,14 +415,50 @@ __device__ __forceinline__ void push_if(uint32_t* stack, int& sp, uint32_t v, bo
     sp += pred ? 1 : 0;
 }
 #endif
+#if defined(__CUDA_ARCH__)
+// Two slab planes per instruction: Blackwell's packed FFMA2 (fma.rn.f32x2) computes {a0*b + c, a1*b + c} with one issue slot; each
+// half is the IEEE fma of the scalar form, so the traversal visits exactly the same nodes as the host emulation's fmaf().  The four
+// children's planes arrive as one float4 per axis (LDS.128 fills two aligned register pairs), the ray's reciprocal direction and
+// -origin/direction ride along as broadcast operands.
+__device__ __forceinline__ void fma2_bcast(float a0, float a1, float b, float c, float& r0, float& r1) {
+    unsigned long long A, B, C, D;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(B) : "f"(b));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(C) : "f"(c));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(D) : "l"(A), "l"(B), "l"(C));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(D));
+}
+__device__ __forceinline__ void slab4(const node_f4& q, float id, float nood, float& r0, float& r1, float& r2, float& r3) {
+    fma2_bcast(q.x, q.y, id, nood, r0, r1);
+    fma2_bcast(q.z, q.w, id, nood, r2, r3);
+}
+#endif
 // One step over a 4-wide node: returns the next node / leaf link (kEmptyScene when the ray is finished).
 VN_HD uint32_t wide_node_step(const node_f4* __restrict__ wn, uint32_t cur, f3 idir, f3 ood, float tbest, uint32_t* stack, int& sp) {
     const node_f4* __restrict__ p = wn + kWideNodeF4 * cur;
     const node_f4 nx = p[0], ny = p[1], nz = p[2], fx = p[3], fy = p[4], fz = p[5], lk = p[6];
+#if defined(__CUDA_ARCH__)
+    float ax[4], ay[4], az[4], bx[4], by[4], bz[4];
+    slab4(nx, idir.x, -ood.x, ax[0], ax[1], ax[2], ax[3]);
+    slab4(ny, idir.y, -ood.y, ay[0], ay[1], ay[2], ay[3]);
+    slab4(nz, idir.z, -ood.z, az[0], az[1], az[2], az[3]);
+    slab4(fx, idir.x, -ood.x, bx[0], bx[1], bx[2], bx[3]);
+    slab4(fy, idir.y, -ood.y, by[0], by[1], by[2], by[3]);
+    slab4(fz, idir.z, -ood.z, bz[0], bz[1], bz[2], bz[3]);
+    bool h[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const float tn = fmaxf(fmaxf(ax[c], ay[c]), fmaxf(az[c], 0.0f));
+        const float tf = fminf(fminf(bx[c], by[c]), fminf(bz[c], tbest));
+        h[c] = tn <= tf;
+    }
+    const bool h0 = h[0], h1 = h[1], h2 = h[2], h3 = h[3];
+#else
     const bool h0 = slab_hit(nx.x, ny.x, nz.x, fx.x, fy.x, fz.x, idir, ood, tbest);
     const bool h1 = slab_hit(nx.y, ny.y, nz.y, fx.y, fy.y, fz.y, idir, ood, tbest);
     const bool h2 = slab_hit(nx.z, ny.z, nz.z, fx.z, fy.z, fz.z, idir, ood, tbest);
     const bool h3 = slab_hit(nx.w, ny.w, nz.w, fx.w, fy.w, fz.w, idir, ood, tbest);
+#endif
     // the nearest hit child (static octant order) becomes the current node straight from registers; the others are
     // pushed far to near.  Only a step without any hit pays the stack load.
     const bool c3 = h3 && (h0 || h1 || h2), c2 = h2 && (h0 || h1), c1 = h1 && h0;
