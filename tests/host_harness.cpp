@@ -619,6 +619,21 @@ static void trace_sequence_pp(const SceneView& sc, f3 o, f3 d, std::vector<uint8
 }
 extern "C" void hh_set_seq_postpone(int on) { g_seq_postpone = on; }
 
+// rnd_pm1() of vn_math.cuh (three instructions on the GPU) against the literal -1 + 2*rnd form of RayTracer.cu:93-97, for every
+// 24-bit LCG output and a spread of upper bytes; returns the number of mismatching bit patterns (must be 0).
+extern "C" uint64_t hh_check_rnd_pm1() {
+    uint64_t bad = 0;
+    for (uint32_t hi = 0; hi < 256u; hi += 51u)
+        for (uint32_t n = 0; n < (1u << 24); n++) {
+            const uint32_t state = (hi << 24) | n;                      // the state AFTER the LCG step
+            const uint32_t prev = (state - 1013904223u) * 4276115653u;    // 1664525^-1 mod 2^32
+            uint32_t s1 = prev, s2 = prev;
+            const float a = rnd_pm1(s1), b = rnd_pm1_literal(s2);
+            bad += (f2u(a) != f2u(b)) || (s1 != s2) || (s1 != state);
+        }
+    return bad;
+}
+
 // Node / sphere visit counts for an externally built tree in the packed layout (BVH-quality studies).
 extern "C" void hh_visits_custom(const node_f4* nodes, uint32_t n_nodes, const hh_sphere* sorted, uint32_t n, const hh_params* P,
                                  uint64_t* segs_out, uint64_t* nodes_out, uint64_t* spheres_out) {

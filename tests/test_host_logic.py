@@ -210,6 +210,13 @@ def test_near_zero_float_threshold_equals_double_compare():
     assert np.array_equal(xs.astype(np.float64) < 1e-8, xs <= c)
 
 
+def test_rnd_pm1_short_form_equals_literal_form(host_harness):
+    """vn_math.cuh::rnd_pm1 forms random_float(seed, -1, 1) (RayTracer.cu:93-97) as float(int32((state << 8) ^ 2^31)) * 2^-31; it must
+    give the bits of -1 + 2 * (float(state & 0xFFFFFF) / 2^24) for every 24-bit output (and leave the same LCG state)."""
+    host_harness.hh_check_rnd_pm1.restype = C.c_uint64
+    assert host_harness.hh_check_rnd_pm1() == 0
+
+
 def test_octant_mirrored_traversal_equals_plain_on_cpu(host_harness, oracle_mod, rtiow):
     """k_render_persistent's octant-specialised node copies (near/far-plane form, no per-axis min/max) find exactly
     the same closest hits, and visit exactly as many nodes, as the plain lo/hi slab test."""

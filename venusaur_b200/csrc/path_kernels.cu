@@ -395,12 +395,14 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_async(const __grid_const
     TraceCounters cnt{0u, 0u};
     // traversal state, alive across the shading of other lanes
     uint32_t stack[kStackSize];
-    int sp = 0;
+    const uint32_t base = (uint32_t)__cvta_generic_to_local(stack);
+    uint32_t top = base;
     uint32_t cur = kEmptyScene;
     float tbest = kTMax;
     int prim = -1;
-    f3 idir = mk3(0.0f), ood = mk3(0.0f);
-    const float4* __restrict__ wn = sc.nodes;
+    SlabScale ss;
+    ss.sdir = ss.nsood = mk3(0.0f);
+    WideBase wb = wide_base(sc.nodes, 0u, node_f4s);
     const uint32_t t_node = p.async_node, t_leaf = p.async_leaf;
 
     for (;;) {
@@ -458,10 +460,10 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_async(const __grid_const
                         if (th >= 0.0f) { tbest = th; prim = (int)hs; }
                     }
                 }
-                idir = slab_idir(st.d);
-                wn = sc.nodes + ray_octant(st.d) * node_f4s;
-                ood = mk3(st.o.x * idir.x, st.o.y * idir.y, st.o.z * idir.z);
-                sp = 0;
+                const f3 idir = slab_idir(st.d);
+                wb = wide_base(sc.nodes, ray_octant(st.d), node_f4s);
+                ss = slab_scale(idir, mk3(st.o.x * idir.x, st.o.y * idir.y, st.o.z * idir.z), tbest);
+                top = base;
                 cur = p.wide_root;
             }
         }
@@ -478,15 +480,20 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_async(const __grid_const
             if (nd >= t_done) break;
             if (nl >= t_leaf || nd + nl == n_live) {
                 if (at_leaf) {
-                    const float a = dot(st.d, st.d);
-                    cur = leaf_step<kCount>(sc.geom, cur, st.o, st.d, a, rcp(a), tbest, prim, stack, sp, cnt);
+                    const float a = dot(st.d, st.d), t_before = tbest;
+                    leaf_test<kCount>(sc.geom, cur, st.o, st.d, a, rcp(a), tbest, prim, cnt);
+                    cur = stack_pop_dev(top, base);
+                    if (tbest != t_before) {                      // the slab test works in units of tbest: rescale
+                        const float g = __fdividef(t_before, tbest);
+                        ss.sdir = ss.sdir * g; ss.nsood = ss.nsood * g;
+                    }
                 }
             } else {
                 for (;;) {
                     const bool at_node = (cur & kLeafFlag) == 0u;
                     if (at_node) {
                         if (kCount) cnt.nodes += 1;
-                        cur = wide_node_step(wn, cur, idir, ood, tbest, stack, sp);
+                        cur = wide_node_step_dev(wb, cur, ss, top, base);
                     }
                     if ((uint32_t)__popc(__ballot_sync(kFull, (cur & kLeafFlag) == 0u)) < t_node) break;
                 }

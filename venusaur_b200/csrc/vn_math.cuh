@@ -107,8 +107,18 @@ VN_HD uint32_t lcg(uint32_t& prev) {
 }
 // (float)lcg / (float)0x01000000: dividing by 2^24 is exact, so multiplying by 2^-24 gives the same bits.
 VN_HD float rnd(uint32_t& prev) { return (float)lcg(prev) * 5.9604644775390625e-8f; }
-// random_float(seed,-1,1) = -1 + (1 - -1) * rnd (RayTracer.cu:93-97): 2*rnd and the sum are both exact.
-VN_HD float rnd_pm1(uint32_t& prev) { return -1.0f + 2.0f * rnd(prev); }
+// random_float(seed,-1,1) = -1 + (1 - -1) * rnd (RayTracer.cu:93-97).  With n = lcg & 0xFFFFFF every step of that expression is exact:
+// n * 2^-24, doubled, minus one = (n - 2^23) * 2^-23.  The same value comes out of three instructions instead of six: the
+// state shifted left by 8 drops the 8 bits the mask would clear, flipping bit 31 subtracts 2^31 in two's complement, so the
+// signed word is (n - 2^23) * 2^8 -- 24 significant bits, exactly convertible -- and 2^-31 scales it back (n = 2^23 gives +0 either
+// way).  The shift and the flip fold into the LCG's multiply-add.  Checked against the literal form for all 2^24 values of n in
+// tests/test_host_logic.py.
+VN_HD float rnd_pm1(uint32_t& prev) {
+    prev = 1664525u * prev + 1013904223u;
+    return (float)(int32_t)((prev << 8) ^ 0x80000000u) * 4.656612873077392578125e-10f;
+}
+// the literal form, kept for the test above
+VN_HD float rnd_pm1_literal(uint32_t& prev) { return -1.0f + 2.0f * rnd(prev); }
 
 // RayTracer.cu:117-125; draws sequenced x, y, z (the contract of SURVEY 3.4)
 VN_HD f3 random_in_unit_sphere(uint32_t& seed) {
@@ -176,9 +186,20 @@ VN_HD float sphere_root(f3 o, f3 d, float a, float inv_a, float cx, float cy, fl
     }
 #else
     (void)inv_a;
-    float root = (-half_b - sqrtd) / a;
-    if (root < t_min || t_max < root) {
-        root = (-half_b + sqrtd) / a;
+    // The IEEE quotient is only formed when its outcome is open: a numerator below 0.999 * t_min * a gives a root that is
+    // certainly < t_min (the true quotient is below t_min by more than the quotient's own rounding error), so the branch the
+    // reference takes is known without dividing.  That is the common case for a ray leaving the very sphere it is tested against
+    // (both numerators ~ 0: every bounce off the ground tests the ground again), where the division would also drop into its
+    // slow path for a zero / tiny numerator (ncu: 2.4 % of all warp instructions).  Same roots, same accept / reject decisions.
+    const float lo = (0.999f * t_min) * a;
+    float num = -half_b - sqrtd;
+    float root = -1.0f;
+    bool take = false;
+    if (num >= lo) { root = num / a; take = !(root < t_min || t_max < root); }
+    if (!take) {
+        num = -half_b + sqrtd;
+        if (!(num >= lo)) return -1.0f;
+        root = num / a;
         if (root < t_min || t_max < root) return -1.0f;
     }
 #endif
@@ -415,18 +436,21 @@ __device__ __forceinline__ void push_if(uint32_t* stack, int& sp, uint32_t v, bo
     sp += pred ? 1 : 0;
 }
 #endif
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 // Two slab planes per instruction: Blackwell's packed FFMA2 (fma.rn.f32x2) computes {a0*b + c, a1*b + c} with one issue slot; each
 // half is the IEEE fma of the scalar form, so the traversal visits exactly the same nodes as the host emulation's fmaf().  The four
 // children's planes arrive as one float4 per axis (LDS.128 fills two aligned register pairs), the ray's reciprocal direction and
 // -origin/direction ride along as broadcast operands.
 __device__ __forceinline__ void fma2_bcast(float a0, float a1, float b, float c, float& r0, float& r1) {
-    unsigned long long A, B, C, D;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
-    asm("mov.b64 %0, {%1, %1};" : "=l"(B) : "f"(b));
-    asm("mov.b64 %0, {%1, %1};" : "=l"(C) : "f"(c));
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(D) : "l"(A), "l"(B), "l"(C));
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(D));
+    // one asm block: the {b, b} / {c, c} packs stay next to the fma, where ptxas folds them into FFMA2's broadcast operands
+    // (as separate statements they are hoisted out of the traversal loop and cost four more live registers)
+    asm("{ .reg .b64 pa, pb, pc, pd;\n\t"
+        "mov.b64 pa, {%2, %3};\n\t"
+        "mov.b64 pb, {%4, %4};\n\t"
+        "mov.b64 pc, {%5, %5};\n\t"
+        "fma.rn.f32x2 pd, pa, pb, pc;\n\t"
+        "mov.b64 {%0, %1}, pd; }"
+        : "=f"(r0), "=f"(r1) : "f"(a0), "f"(a1), "f"(b), "f"(c));
 }
 __device__ __forceinline__ void slab4(const node_f4& q, float id, float nood, float& r0, float& r1, float& r2, float& r3) {
     fma2_bcast(q.x, q.y, id, nood, r0, r1);
@@ -476,6 +500,175 @@ VN_HD uint32_t wide_node_step(const node_f4* __restrict__ wn, uint32_t cur, f3 i
     if (!(h0 || h1 || h2 || h3)) next = sp ? stack[--sp] : kEmptyScene;
     return next;
 }
+// ---- the same step with the ray parameter NORMALISED by the closest hit so far (s = t / tbest) and saturating slab products.
+// The min/max, compare and select instructions of a node step run on the SM's half-rate ALU pipe, and the step above holds 39 of
+// them against 12 FFMA2 + 8 loads: the ALU pipe, not the issue slot, bounds it (ncu: alu 63 %, issue 80 %).  In normalised units
+// the valid interval of a slab is [0, 1], which is what FFMA.SAT clamps to for free: with the z planes saturated,
+//     tn = max(ax, ay, sat(az)) >= 0        tf = min(bx, by, sat(bz)) <= 1
+// need no clamp against 0 and tbest (8 FMNMX per step gone).  A box beyond tbest has tn >= 1 >= tf and a box behind the origin
+// has tf <= 0 <= tn, so the test is the STRICT tn < tf (an exact tie of two independently rounded products only occurs for a box
+// the ray grazes; boxes are padded, so a sphere that is hit is never lost).  Like slab_hit() this only has to be conservative;
+// the scale factors are refreshed whenever a leaf shortens tbest.
+struct SlabScale { f3 sdir, nsood; };            // idir / tbest,  -(o * idir) / tbest
+VN_HD SlabScale slab_scale(f3 idir, f3 ood, float tbest) {
+#if defined(__CUDA_ARCH__)
+    const float inv_t = __fdividef(1.0f, tbest);
+#else
+    const float inv_t = 1.0f / tbest;
+#endif
+    SlabScale r;
+    r.sdir = mk3(idir.x * inv_t, idir.y * inv_t, idir.z * inv_t);
+    r.nsood = mk3(-(ood.x * inv_t), -(ood.y * inv_t), -(ood.z * inv_t));
+    return r;
+}
+VN_HD float fma_sat(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+#else
+    return fminf(fmaxf(fmaf(a, b, c), 0.0f), 1.0f);          // NaN -> 0 like .sat
+#endif
+}
+// The octant's node copy as the traversal loop sees it.  On the GPU it is a 32-bit shared-memory byte address laundered through an
+// empty asm: left as pointer arithmetic, the compiler re-derives it from the ray direction inside the loop (7 ALU instructions per
+// step) rather than keep it in a register.  Loads are explicit ld.shared.v4 with immediate offsets: one IMAD + 7 LDS.128 per step.
+#if defined(__CUDACC__)
+struct WideBase { uint32_t addr; };
+__device__ __forceinline__ WideBase wide_base(const node_f4* wnodes, uint32_t octant, uint32_t oct_stride) {
+    WideBase b;
+    b.addr = (uint32_t)__cvta_generic_to_shared(wnodes + (size_t)octant * oct_stride);
+    asm volatile("" : "+r"(b.addr));
+    return b;
+}
+template <int kOff>
+__device__ __forceinline__ node_f4 lds_f4(uint32_t addr) {
+    node_f4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr), "n"(kOff));
+    return v;
+}
+#else
+struct WideBase { const node_f4* p; };
+inline WideBase wide_base(const node_f4* wnodes, uint32_t octant, uint32_t oct_stride) { WideBase b; b.p = wnodes + (size_t)octant * oct_stride; return b; }
+#endif
+#if !defined(__CUDACC__)
+// host emulation of the step (tests/host_harness.cpp); the GPU runs wide_node_step_dev() below: same arithmetic, same order
+inline uint32_t wide_node_step_sat(WideBase wb, uint32_t cur, const SlabScale& sc, uint32_t* stack, int& sp) {
+    const node_f4* __restrict__ p = wb.p + kWideNodeF4 * cur;
+    const node_f4 nx = p[0], ny = p[1], nz = p[2], fx = p[3], fy = p[4], fz = p[5], lk = p[6];
+    float ax[4], ay[4], bx[4], by[4];
+#if defined(__CUDA_ARCH__)
+    slab4(nx, sc.sdir.x, sc.nsood.x, ax[0], ax[1], ax[2], ax[3]);
+    slab4(ny, sc.sdir.y, sc.nsood.y, ay[0], ay[1], ay[2], ay[3]);
+    slab4(fx, sc.sdir.x, sc.nsood.x, bx[0], bx[1], bx[2], bx[3]);
+    slab4(fy, sc.sdir.y, sc.nsood.y, by[0], by[1], by[2], by[3]);
+#else
+    ax[0] = fmaf(nx.x, sc.sdir.x, sc.nsood.x); ax[1] = fmaf(nx.y, sc.sdir.x, sc.nsood.x); ax[2] = fmaf(nx.z, sc.sdir.x, sc.nsood.x); ax[3] = fmaf(nx.w, sc.sdir.x, sc.nsood.x);
+    ay[0] = fmaf(ny.x, sc.sdir.y, sc.nsood.y); ay[1] = fmaf(ny.y, sc.sdir.y, sc.nsood.y); ay[2] = fmaf(ny.z, sc.sdir.y, sc.nsood.y); ay[3] = fmaf(ny.w, sc.sdir.y, sc.nsood.y);
+    bx[0] = fmaf(fx.x, sc.sdir.x, sc.nsood.x); bx[1] = fmaf(fx.y, sc.sdir.x, sc.nsood.x); bx[2] = fmaf(fx.z, sc.sdir.x, sc.nsood.x); bx[3] = fmaf(fx.w, sc.sdir.x, sc.nsood.x);
+    by[0] = fmaf(fy.x, sc.sdir.y, sc.nsood.y); by[1] = fmaf(fy.y, sc.sdir.y, sc.nsood.y); by[2] = fmaf(fy.z, sc.sdir.y, sc.nsood.y); by[3] = fmaf(fy.w, sc.sdir.y, sc.nsood.y);
+#endif
+    const float az[4] = {fma_sat(nz.x, sc.sdir.z, sc.nsood.z), fma_sat(nz.y, sc.sdir.z, sc.nsood.z), fma_sat(nz.z, sc.sdir.z, sc.nsood.z), fma_sat(nz.w, sc.sdir.z, sc.nsood.z)};
+    const float bz[4] = {fma_sat(fz.x, sc.sdir.z, sc.nsood.z), fma_sat(fz.y, sc.sdir.z, sc.nsood.z), fma_sat(fz.z, sc.sdir.z, sc.nsood.z), fma_sat(fz.w, sc.sdir.z, sc.nsood.z)};
+    bool h[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int c = 0; c < 4; c++) h[c] = fmaxf(fmaxf(ax[c], ay[c]), az[c]) < fminf(fminf(bx[c], by[c]), bz[c]);
+    const bool h0 = h[0], h1 = h[1], h2 = h[2], h3 = h[3];
+    const bool c3 = h3 && (h0 || h1 || h2), c2 = h2 && (h0 || h1), c1 = h1 && h0;
+#if defined(__CUDA_ARCH__)
+    push_if(stack, sp, f2u(lk.w), c3);
+    push_if(stack, sp, f2u(lk.z), c2);
+    push_if(stack, sp, f2u(lk.y), c1);
+#else
+    if (c3) stack[sp++] = f2u(lk.w);
+    if (c2) stack[sp++] = f2u(lk.z);
+    if (c1) stack[sp++] = f2u(lk.y);
+#endif
+    uint32_t next = h0 ? f2u(lk.x) : (h1 ? f2u(lk.y) : (h2 ? f2u(lk.z) : f2u(lk.w)));
+    if (!(h0 || h1 || h2 || h3)) next = sp ? stack[--sp] : kEmptyScene;
+    return next;
+}
+#endif
+#if defined(__CUDACC__)
+// Device form of the step: the traversal stack is addressed by its local-memory byte address (`top` = first free word, `base` =
+// bottom), and the select / push / pop logic is written out in PTX: four compares, three predicated stores whose addresses advance
+// by 4 * hit, and -- only when the nearest child (slot 0 of the octant order) was missed -- a predicated pop of the entry just
+// pushed (or of an older one).  20 instructions where the compiler's version of `h3 && (h0 || h1 || h2)` etc. took 33, 14 of them on
+// the ALU pipe instead of 23.  Same visiting order as wide_node_step(): hit children far to near onto the stack, nearest first.
+__device__ __forceinline__ uint32_t wide_node_step_dev(WideBase wb, uint32_t cur, const SlabScale& sc, uint32_t& top, uint32_t base) {
+    const uint32_t pa = wb.addr + cur * (kWideNodeF4 * 16u);
+    const node_f4 nx = lds_f4<0>(pa), ny = lds_f4<16>(pa), nz = lds_f4<32>(pa), fx = lds_f4<48>(pa), fy = lds_f4<64>(pa), fz = lds_f4<80>(pa), lk = lds_f4<96>(pa);
+    float ax[4], ay[4], bx[4], by[4];
+    slab4(nx, sc.sdir.x, sc.nsood.x, ax[0], ax[1], ax[2], ax[3]);
+    slab4(ny, sc.sdir.y, sc.nsood.y, ay[0], ay[1], ay[2], ay[3]);
+    slab4(fx, sc.sdir.x, sc.nsood.x, bx[0], bx[1], bx[2], bx[3]);
+    slab4(fy, sc.sdir.y, sc.nsood.y, by[0], by[1], by[2], by[3]);
+    const float az[4] = {fma_sat(nz.x, sc.sdir.z, sc.nsood.z), fma_sat(nz.y, sc.sdir.z, sc.nsood.z), fma_sat(nz.z, sc.sdir.z, sc.nsood.z), fma_sat(nz.w, sc.sdir.z, sc.nsood.z)};
+    const float bz[4] = {fma_sat(fz.x, sc.sdir.z, sc.nsood.z), fma_sat(fz.y, sc.sdir.z, sc.nsood.z), fma_sat(fz.z, sc.sdir.z, sc.nsood.z), fma_sat(fz.w, sc.sdir.z, sc.nsood.z)};
+    float tn[4], tf[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) { tn[c] = fmaxf(fmaxf(ax[c], ay[c]), az[c]); tf[c] = fminf(fminf(bx[c], by[c]), bz[c]); }
+    uint32_t next;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred h0, h1, h2, h3, q;\n\t"
+        ".reg .u32 n;\n\t"
+        "setp.lt.f32 h3, %2, %3;\n\t"
+        "setp.lt.f32 h2, %4, %5;\n\t"
+        "setp.lt.f32 h1, %6, %7;\n\t"
+        "setp.lt.f32 h0, %8, %9;\n\t"
+        "@h3 st.local.u32 [%1], %10;\n\t"
+        "selp.u32 n, 4, 0, h3;\n\t"
+        "add.u32 %1, %1, n;\n\t"
+        "@h2 st.local.u32 [%1], %11;\n\t"
+        "selp.u32 n, 4, 0, h2;\n\t"
+        "add.u32 %1, %1, n;\n\t"
+        "@h1 st.local.u32 [%1], %12;\n\t"
+        "selp.u32 n, 4, 0, h1;\n\t"
+        "add.u32 %1, %1, n;\n\t"
+        "setp.gt.u32 q, %1, %14;\n\t"
+        "and.pred q, q, !h0;\n\t"
+        "selp.u32 %0, %13, 0xFFFFFFFF, h0;\n\t"
+        "@q ld.local.u32 %0, [%1+-4];\n\t"
+        "@q add.u32 %1, %1, -4;\n\t"
+        "}"
+        : "=r"(next), "+r"(top)
+        : "f"(tn[3]), "f"(tf[3]), "f"(tn[2]), "f"(tf[2]), "f"(tn[1]), "f"(tf[1]), "f"(tn[0]), "f"(tf[0]),
+          "r"(f2u(lk.w)), "r"(f2u(lk.z)), "r"(f2u(lk.y)), "r"(f2u(lk.x)), "r"(base)
+        : "memory");
+    return next;
+}
+__device__ __forceinline__ uint32_t stack_pop_dev(uint32_t& top, uint32_t base) {
+    uint32_t next;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "setp.gt.u32 q, %1, %2;\n\t"
+        "mov.u32 %0, 0xFFFFFFFF;\n\t"
+        "@q ld.local.u32 %0, [%1+-4];\n\t"
+        "@q add.u32 %1, %1, -4;\n\t"
+        "}"
+        : "=r"(next), "+r"(top) : "r"(base) : "memory");
+    return next;
+}
+#endif
+// the sphere tests of one leaf (RayTracer.cu:229-270 on each of its <= 8 spheres)
+template <bool kCount>
+VN_HD void leaf_test(const node_f4* __restrict__ geom, uint32_t cur, f3 o, f3 d, float a, float inv_a, float& tbest, int& prim, TraceCounters& cnt) {
+    const uint32_t first = (cur & 0x7FFFFFFFu) >> 3;
+    const uint32_t count = (cur & 7u) + 1u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (uint32_t k = 0; k < count; k++) {
+        const node_f4 g = geom[first + k];
+        if (kCount) cnt.spheres += 1;
+        const float t = sphere_root(o, d, a, inv_a, g.x, g.y, g.z, g.w, kTMin, tbest);
+        if (t >= 0.0f) { tbest = t; prim = (int)(first + k); }
+    }
+}
 // One leaf: the reference's ray/sphere test on its (<= 8) spheres; returns the next link.
 template <bool kCount>
 VN_HD uint32_t leaf_step(const node_f4* __restrict__ geom, uint32_t cur, f3 o, f3 d, float a, float inv_a, float& tbest, int& prim,
@@ -498,24 +691,53 @@ VN_HD void closest_hit_wide(const node_f4* __restrict__ wnodes, uint32_t oct_str
                             f3 o, f3 d, float& t_out, int& prim_out, TraceCounters& cnt, float tbest0 = kTMax, int prim0 = -1) {
     float tbest = tbest0;              // closest hit among the huge spheres tested before the traversal (lbvh_core.cuh::HugeList)
     int prim = prim0;
+#if defined(__CUDA_ARCH__)
     {
         const f3 idir = slab_idir(d);
-        const node_f4* __restrict__ wn = wnodes + ray_octant(d) * oct_stride;
+        const f3 ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
+        const float a = dot(d, d);
+        const float inv_a = rcp(a);
+        uint32_t stack[kStackSize];
+        const uint32_t base = (uint32_t)__cvta_generic_to_local(stack);
+        uint32_t top = base;
+        uint32_t cur = root_link;
+        SlabScale ss = slab_scale(idir, ood, tbest);
+        const WideBase wb = wide_base(wnodes, ray_octant(d), oct_stride);
+        for (;;) {
+            while (!(cur & kLeafFlag)) {
+                if (kCount) cnt.nodes += 1;
+                cur = wide_node_step_dev(wb, cur, ss, top, base);
+            }
+            if (cur == kEmptyScene) break;
+            const float t_before = tbest;
+            leaf_test<kCount>(geom, cur, o, d, a, inv_a, tbest, prim, cnt);
+            cur = stack_pop_dev(top, base);
+            if (tbest != t_before) ss = slab_scale(idir, ood, tbest);
+        }
+    }
+#elif !defined(__CUDACC__)
+    {
+        const f3 idir = slab_idir(d);
         const f3 ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
         const float a = dot(d, d);
         const float inv_a = rcp(a);
         uint32_t stack[kStackSize];
         int sp = 0;
         uint32_t cur = root_link;
+        SlabScale ss = slab_scale(idir, ood, tbest);
+        const WideBase wb = wide_base(wnodes, ray_octant(d), oct_stride);
         for (;;) {
             while (!(cur & kLeafFlag)) {
                 if (kCount) cnt.nodes += 1;
-                cur = wide_node_step(wn, cur, idir, ood, tbest, stack, sp);
+                cur = wide_node_step_sat(wb, cur, ss, stack, sp);
             }
             if (cur == kEmptyScene) break;
+            const float t_before = tbest;
             cur = leaf_step<kCount>(geom, cur, o, d, a, inv_a, tbest, prim, stack, sp, cnt);
+            if (tbest != t_before) ss = slab_scale(idir, ood, tbest);
         }
     }
+#endif
     t_out = tbest;
     prim_out = prim;
 }
