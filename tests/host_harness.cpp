@@ -22,6 +22,7 @@ struct hh_params {
     float origin[3], u[3], v[3], w[3], lens_radius;
 };
 
+static inline node_f4 dielectric_mat(float ir) { const DielectricConsts dc = dielectric_consts(ir); return node_f4{dc.ir, dc.inv_ir, dc.r0_front, dc.r0_back}; }
 static uint32_t g_sah_max = 4096;   // same default as the library's "sah_max_prims" option
 static int g_use_oct = 0;
 static int g_use_grid = 0;         // hh_set_grid(1): closest hit through the uniform grid + oversize list
@@ -197,7 +198,7 @@ static void build(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pad_
         const hh_sphere& p = s[idx[i]];
         B.codes[i] = codes[idx[i]];
         B.geom[i] = node_f4{p.cx, p.cy, p.cz, p.r};
-        B.mat[i] = p.type == 2 ? node_f4{p.fuzz_or_ir, 0, 0, 0} : node_f4{p.ax, p.ay, p.az, p.fuzz_or_ir};
+        B.mat[i] = p.type == 2 ? dielectric_mat(p.fuzz_or_ir) : node_f4{p.ax, p.ay, p.az, p.fuzz_or_ir};
         B.type[i] = (uint8_t)p.type;
         const float pad = fabsf(p.r) * (1.0f + pad_rel) + 1e-6f;
         llo[i] = f4{p.cx - pad, p.cy - pad, p.cz - pad, 0};
@@ -228,7 +229,7 @@ static void build(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pad_
         for (uint32_t i = 0; i < n; i++) {
             const hh_sphere& p = s[final_idx[i]];
             B.geom[i] = node_f4{p.cx, p.cy, p.cz, p.r};
-            B.mat[i] = p.type == 2 ? node_f4{p.fuzz_or_ir, 0, 0, 0} : node_f4{p.ax, p.ay, p.az, p.fuzz_or_ir};
+            B.mat[i] = p.type == 2 ? dielectric_mat(p.fuzz_or_ir) : node_f4{p.ax, p.ay, p.az, p.fuzz_or_ir};
             B.type[i] = (uint8_t)p.type;
             const float pad = fabsf(p.r) * (1.0f + pad_rel) + 1e-6f;
             llo[i] = f4{p.cx - pad, p.cy - pad, p.cz - pad, 0};
@@ -641,7 +642,7 @@ extern "C" void hh_visits_custom(const node_f4* nodes, uint32_t n_nodes, const h
     std::vector<uint8_t> type(n);
     for (uint32_t i = 0; i < n; i++) {
         geom[i] = node_f4{sorted[i].cx, sorted[i].cy, sorted[i].cz, sorted[i].r};
-        mat[i] = sorted[i].type == 2 ? node_f4{sorted[i].fuzz_or_ir, 0, 0, 0} : node_f4{sorted[i].ax, sorted[i].ay, sorted[i].az, sorted[i].fuzz_or_ir};
+        mat[i] = sorted[i].type == 2 ? dielectric_mat(sorted[i].fuzz_or_ir) : node_f4{sorted[i].ax, sorted[i].ay, sorted[i].az, sorted[i].fuzz_or_ir};
         type[i] = (uint8_t)sorted[i].type;
     }
     (void)n_nodes;

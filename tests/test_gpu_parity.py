@@ -447,7 +447,7 @@ def test_async_kernel_equals_persistent_kernel(ctx, oracle_mod, rtiow, threads):
         ctx.set_option("async_done", 0)
         ctx.set_option("async_node", 8)
         ctx.set_option("async_leaf", 8)
-        ctx.set_option("wide_threads", 768)
+        ctx.set_option("wide_threads", 1024)
 
 
 
@@ -555,7 +555,7 @@ def test_grid_and_bvh_path_kernels_agree(rtiow_ctx, oracle_mod, rtiow):
             rtiow_ctx.set_option("wide_threads", threads)
             t, it, stt = render(rtiow_ctx, cam, W, H, spp, 2, depth)
             assert np.array_equal(a.view(np.uint32), t.view(np.uint32)) and stt.segments == sa.segments
-        rtiow_ctx.set_option("wide_threads", 768)
+        rtiow_ctx.set_option("wide_threads", 1024)
         for vote in (0, 1, 12, 33):
             rtiow_ctx.set_option("grid_vote", vote)
             t, it, stt = render(rtiow_ctx, cam, W, H, spp, 2, depth, flags=VN_COUNTERS)
@@ -569,7 +569,7 @@ def test_grid_and_bvh_path_kernels_agree(rtiow_ctx, oracle_mod, rtiow):
         assert rtiow_ctx.last_accel() == 2
         bc, _, sbc = render(rtiow_ctx, cam, W, H, spp, 2, depth, flags=VN_COUNTERS)
     finally:
-        rtiow_ctx.set_option("wide_threads", 768)
+        rtiow_ctx.set_option("wide_threads", 1024)
         rtiow_ctx.set_option("grid_vote", 0)
         rtiow_ctx.set_option("accel", 1)
     assert sa.segments == sb.segments == sac.segments == sbc.segments and sa.paths == sb.paths

@@ -85,7 +85,12 @@ __global__ void __launch_bounds__(kBlock) k_gather(const vn_sphere* __restrict__
     const vn_sphere p = s[src];
     geom[i] = make_float4(p.cx, p.cy, p.cz, p.r);
     // MaterialData (RayTracer.h:27-38): {albedo, fuzz} or {ir} aliasing albedo.x
-    mat[i] = p.type == VN_DIELECTRIC ? make_float4(p.fuzz_or_ir, 0.0f, 0.0f, 0.0f) : make_float4(p.ax, p.ay, p.az, p.fuzz_or_ir);
+    if (p.type == VN_DIELECTRIC) {
+        const DielectricConsts dc = dielectric_consts(p.fuzz_or_ir);      // vn_math.cuh: 1/ir and Schlick's r0 for both faces, IEEE
+        mat[i] = make_float4(dc.ir, dc.inv_ir, dc.r0_front, dc.r0_back);
+    } else {
+        mat[i] = make_float4(p.ax, p.ay, p.az, p.fuzz_or_ir);
+    }
     type[i] = (uint8_t)p.type;
     orig[i] = src;
     // |r| (sphere.h:17-28 computes fabsf(radius) and then forgets to use it) plus a pad that keeps the slab

@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_async(const __grid_const
                     leaf_test<kCount>(sc.geom, cur, st.o, st.d, a, rcp(a), tbest, prim, cnt);
                     cur = stack_pop_dev(top, base);
                     if (tbest != t_before) {                      // the slab test works in units of tbest: rescale
-                        const float g = __fdividef(t_before, tbest);
+                        const float g = t_before * rcp_approx(tbest);
                         ss.sdir = ss.sdir * g; ss.nsood = ss.nsood * g;
                     }
                 }

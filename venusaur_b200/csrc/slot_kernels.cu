@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_render_slots(const __grid_consta
                         cont = shade_opaque(type, mt, unit_direction, n, st);
                         if (cont) { SLOT_F(kTr, j) = st.thr.x; SLOT_F(kTg, j) = st.thr.y; SLOT_F(kTb, j) = st.thr.z; }
                     } else {
-                        st.d = scatter_dielectric(normalize(st.d), n, front, mt.x, st.seed);
+                        { DielectricConsts dc; dc.ir = mt.x; dc.inv_ir = mt.y; dc.r0_front = mt.z; dc.r0_back = mt.w; st.d = scatter_dielectric(normalize(st.d), n, front, dc, st.seed); }
                         cont = true;
                     }
                     if (cont) {

@@ -75,7 +75,7 @@ struct vn_context {
     uint32_t grid_max_per_cell = 16;  // a cell with more spheres than this disqualifies the grid (clustered scenes: the BVH adapts, a grid does not)
     uint32_t last_accel = 0;          // what the last vn_render traversed: 1 pair nodes, 2 wide nodes (shared memory), 3 wide nodes (L2/HBM), 4 grid
     float huge_factor = 50.0f;        // spheres with radius > huge_factor x median are tested before the wide traversal (0 = none), lbvh_core.cuh::HugeList
-    int wide_threads = 768;           // CTA size of the wide-node path kernel (one CTA per SM): 512, 768 or 1024
+    int wide_threads = 1024;          // CTA size of the wide-node path kernel (one CTA per SM): 512, 768 or 1024 (64 registers per lane at 1024)
     uint32_t leaf_vote = 0;           // see closest_hit_wide_vote (path_kernels.cu); 0 = while-while
     uint32_t async_done = 0;          // k_render_async: a traversal burst ends when this many lanes hold a finished ray (0 = k_render_persistent)
     uint32_t async_node = 8, async_leaf = 8;

@@ -236,10 +236,12 @@ VN_HD bool scatter_metal(f3 unit_direction, f3 n, float fuzz, f3 in_unit_sphere,
     return dot(dir_out, n) > 0.0f;
 }
 
-// reflectance, RayTracer.cu:373-379 (__powf there)
-VN_HD float reflectance(float cosine, float ref_idx) {
+// reflectance, RayTracer.cu:373-379 (__powf there).  r0 = ((1 - ref_idx) / (1 + ref_idx))^2 only depends on the sphere, see below.
+VN_HD float schlick_r0(float ref_idx) {
     float r0 = fdiv(1.0f - ref_idx, 1.0f + ref_idx);
-    r0 = r0 * r0;
+    return r0 * r0;
+}
+VN_HD float reflectance_r0(float cosine, float r0) {
 #if VN_FAST_DEVICE
     float x = 1.0f - cosine;
     float x2 = x * x;
@@ -252,25 +254,49 @@ VN_HD float reflectance(float cosine, float ref_idx) {
     return r0 + (1.0f - r0) * (float)(x2 * x2 * x);
 #endif
 }
+VN_HD float reflectance(float cosine, float ref_idx) { return reflectance_r0(cosine, schlick_r0(ref_idx)); }
+
+// What __closesthit__dielectric derives from the sphere's index of refraction alone, formed once per sphere by the BVH builder with
+// the very operations of RayTracer.cu:398-401,375-376 (IEEE division) and stored in the sphere's material record:
+// {ir, 1/ir, r0(1/ir) for a front-face hit, r0(ir) for a back-face hit}.  Per hit that removes two IEEE divisions from a branch
+// that runs at 2-3 active lanes.
+struct DielectricConsts { float ir, inv_ir, r0_front, r0_back; };
+VN_HD DielectricConsts dielectric_consts(float ir) {
+    DielectricConsts c;
+    c.ir = ir;
+    c.inv_ir = 1.0f / ir;
+    c.r0_front = schlick_r0(c.inv_ir);
+    c.r0_back = schlick_r0(ir);
+    return c;
+}
 
 // __closesthit__dielectric, RayTracer.cu:398-414
-VN_HD f3 scatter_dielectric(f3 unit_direction, f3 n, bool front, float ir, uint32_t& seed) {
-    float refraction_ratio = front ? rcp(ir) : ir;
+VN_HD f3 scatter_dielectric(f3 unit_direction, f3 n, bool front, const DielectricConsts& dc, uint32_t& seed) {
+    const float refraction_ratio = front ? dc.inv_ir : dc.ir;
 #if VN_FAST_DEVICE
     float cos_theta = fminf(dot(-unit_direction, n), 1.0f);
     float sin2 = 1.0f - cos_theta * cos_theta;
     bool cannot_refract = refraction_ratio * refraction_ratio * sin2 > 1.0f;
     float cos_f = cos_theta;
 #else
-    double cos_theta = (double)fminf(dot(-unit_direction, n), 1.0f);
-    double sin_theta = sqrt(1.0 - cos_theta * cos_theta);
-    bool cannot_refract = (double)refraction_ratio * sin_theta > 1.0;
-    float cos_f = (float)cos_theta;
+    const float cos_f = fminf(dot(-unit_direction, n), 1.0f);
+    // ratio * sin_theta > 1.0 in double (RayTracer.cu:404-408).  sin_theta = sqrt(1 - cos^2) <= 1 and the product of two doubles
+    // <= 1 rounds to <= 1, so a ratio <= 1 (entering glass) can never refuse to refract: the FP64 square root is only needed for
+    // the other case.
+    bool cannot_refract = false;
+    if (refraction_ratio > 1.0f) {
+        const double cos_theta = (double)cos_f;
+        const double sin_theta = sqrt(1.0 - cos_theta * cos_theta);
+        cannot_refract = (double)refraction_ratio * sin_theta > 1.0;
+    }
 #endif
     // `cannot_refract || reflectance > random_float` short-circuits: no draw when cannot_refract
     bool do_reflect = cannot_refract;
-    if (!do_reflect) do_reflect = reflectance(cos_f, refraction_ratio) > rnd(seed);
+    if (!do_reflect) do_reflect = reflectance_r0(cos_f, front ? dc.r0_front : dc.r0_back) > rnd(seed);
     return do_reflect ? reflect(unit_direction, n) : refract(unit_direction, n, refraction_ratio);
+}
+VN_HD f3 scatter_dielectric(f3 unit_direction, f3 n, bool front, float ir, uint32_t& seed) {
+    return scatter_dielectric(unit_direction, n, front, dielectric_consts(ir), seed);
 }
 
 // __miss__ms, RayTracer.cu:442-450.  0.5*(y+1.0) in double then narrowed == the float expression below
@@ -341,16 +367,23 @@ VN_HD bool box_hit(const node_f4& lo, const node_f4& hi, f3 idir, f3 ood, float 
 // o*idir - plane*idir = inf - inf = NaN, which the NaN-dropping min/max could turn into a wrongly culled box; keeping
 // |d| >= 1e-30 keeps every product finite and the test conservative.  The slab test only has to be conservative (the
 // boxes are padded), so the reciprocal itself is the approximate MUFU.RCP in both builds.
+// Approximate reciprocal for the (conservative) slab test: one MUFU.RCP.  __fdividef(1, x) without -ftz wraps the MUFU in a
+// denormal-rescue sequence (6 instructions); the operands here are never denormal (|d| >= 1e-30 below, tbest >= 1e-3).
+VN_HD float rcp_approx(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
 VN_HD f3 slab_idir(f3 d) {
     const float tiny = 1e-30f;
     const float dx = fabsf(d.x) < tiny ? copysignf(tiny, d.x) : d.x;
     const float dy = fabsf(d.y) < tiny ? copysignf(tiny, d.y) : d.y;
     const float dz = fabsf(d.z) < tiny ? copysignf(tiny, d.z) : d.z;
-#if defined(__CUDA_ARCH__)
-    return mk3(__fdividef(1.0f, dx), __fdividef(1.0f, dy), __fdividef(1.0f, dz));
-#else
-    return mk3(1.0f / dx, 1.0f / dy, 1.0f / dz);
-#endif
+    return mk3(rcp_approx(dx), rcp_approx(dy), rcp_approx(dz));
 }
 
 // Same test against a node stored in NEAR/FAR-plane form for the ray's direction octant (see k_render_persistent:
@@ -511,11 +544,7 @@ VN_HD uint32_t wide_node_step(const node_f4* __restrict__ wn, uint32_t cur, f3 i
 // the scale factors are refreshed whenever a leaf shortens tbest.
 struct SlabScale { f3 sdir, nsood; };            // idir / tbest,  -(o * idir) / tbest
 VN_HD SlabScale slab_scale(f3 idir, f3 ood, float tbest) {
-#if defined(__CUDA_ARCH__)
-    const float inv_t = __fdividef(1.0f, tbest);
-#else
-    const float inv_t = 1.0f / tbest;
-#endif
+    const float inv_t = rcp_approx(tbest);
     SlabScale r;
     r.sdir = mk3(idir.x * inv_t, idir.y * inv_t, idir.z * inv_t);
     r.nsood = mk3(-(ood.x * inv_t), -(ood.y * inv_t), -(ood.z * inv_t));
@@ -748,7 +777,7 @@ VN_HD void closest_hit_wide(const node_f4* __restrict__ wnodes, uint32_t oct_str
 struct SceneView {
     const node_f4* nodes;
     const node_f4* geom;     // {cx, cy, cz, r}, sorted order
-    const node_f4* mat;      // {albedo.xyz | ir, fuzz}
+    const node_f4* mat;      // {albedo.xyz, fuzz} or, for glass, {ir, 1/ir, r0 front, r0 back} (DielectricConsts)
     const uint8_t* type;
     uint32_t root_link;
 };
@@ -868,7 +897,9 @@ VN_HD bool shade_segment(const SceneView& sc, PathState& st, float t, int prim, 
     if (type != 2u) {
         if (!shade_opaque(type, m, unit_direction, n, st)) { result = mk3(0.0f); return false; }
     } else {
-        st.d = scatter_dielectric(unit_direction, n, front, m.x, st.seed);
+        DielectricConsts dc;
+        dc.ir = m.x; dc.inv_ir = m.y; dc.r0_front = m.z; dc.r0_back = m.w;    // written by the builder (lbvh.cu::k_gather)
+        st.d = scatter_dielectric(unit_direction, n, front, dc, st.seed);
     }
     st.o = p;
     st.depth -= 1;
