@@ -360,20 +360,21 @@ def run_ours(args):
             pass
         # issue-slot roofline: thread-instructions per segment from the budget model of SURVEY 8(d)
         # with V_node / V_sphere measured by the instrumented kernel on this very workload.
-        # Coefficients: pair nodes = SURVEY's budget; 4-wide nodes = SASS counts of the shipped kernel (node step 83 instructions,
-        # one sphere test ~60 incl. its share of IEEE sqrt/div, shade + RNG + camera ~270 per segment; profiles/).
+        # Coefficients: pair nodes = SURVEY's budget; 4-wide nodes = SASS counts of the shipped kernel (node step 53 instructions,
+        # one sphere test ~100 with its leaf / pop overhead and IEEE sqrt + div, shade + RNG + camera + ray set-up ~230 per segment;
+        # profiles/r01s3_path_kernel_ncu.txt: 694 thread-instructions per segment measured, this model gives 697).
         wide = accel == 2
         if accel == 4:      # uniform grid + oversize list: V_node = cell steps (25 instructions each incl. the vote), 45 per sphere test,
             i_seg = 25.0 * v_node + 45.0 * v_sphere + 300.0      # + shade / RNG / camera / ray-box clip and DDA set-up
         else:
-            i_seg = (83.0 * v_node + 60.0 * v_sphere + 270.0) if wide else (40.0 * v_node + 30.0 * v_sphere + 150.0)
+            i_seg = (53.0 * v_node + 100.0 * v_sphere + 230.0) if wide else (40.0 * v_node + 30.0 * v_sphere + 150.0)
         f_clk = (clk.get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0) * 1e6
         peak_tinst = 32 * 4 * n_sm * f_clk / 1e12
         per_gpu_rate = (my_segs / (sum(step_ms) * 1e-3))
         achieved_tinst = per_gpu_rate * i_seg / 1e12
         prof = {}
         try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r01s2_trace_kernel.json")))
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r01s3_trace_kernel.json")))
         except (OSError, ValueError):
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
@@ -400,7 +401,7 @@ def run_ours(args):
                          "frac": achieved_tinst / peak_tinst, "traffic": prof.get("dram_bytes_per_launch"),
                          "model": "I_seg = %s = %.0f thread-instructions/segment (V_node=%.2f, V_sphere=%.2f measured); "
                                   "peak = 32 lanes x 4 schedulers x %d SMs x %.0f MHz (median SM clock during the run)"
-                                  % ("25*V_cell + 45*V_sphere + 300 (uniform grid + oversize list)" if accel == 4 else "83*V_node + 60*V_sphere + 270 (4-wide nodes)" if wide else "40*V_node + 30*V_sphere + 150 (pair nodes)", i_seg, v_node, v_sphere, n_sm, f_clk / 1e6),
+                                  % ("25*V_cell + 45*V_sphere + 300 (uniform grid + oversize list)" if accel == 4 else "53*V_node + 100*V_sphere + 230 (4-wide nodes)" if wide else "40*V_node + 30*V_sphere + 150 (pair nodes)", i_seg, v_node, v_sphere, n_sm, f_clk / 1e6),
                          "measured_inst_per_segment": prof.get("thread_inst_per_segment"),
                          "issue_slot_utilisation_ncu": prof.get("issue_slot_utilisation")},
             "roofline_hbm": {"bound": "hbm", "achieved": algo_bytes / (mean_step_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",

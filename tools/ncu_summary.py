@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Summarises an exported ncu report: key raw metrics + the hottest source lines (needs -lineinfo).
-usage: ncu_summary.py raw.csv source.csv [n_lines]"""
+usage: ncu_summary.py raw.csv source.csv [n_lines] [--json out.json segments_per_launch "kernel description" "source note"]"""
 import csv
 import sys
 
@@ -32,18 +32,47 @@ def sass_regions(rows, total_w, min_share=0.008):
     print("SASS instructions %d, warp instructions %.3e (kernel total %.3e)" % (len(data), tot, total_w))
 
 
+def write_json(d, out, segments, kernel, source):
+    """The numbers bench.py quotes in its roofline object (profiles/rNN_trace_kernel.json)."""
+    import json
+    g = lambda k: fl(d[k][0]) if k in d else 0.0
+    unit = lambda k: d[k][1] if k in d else ""
+    def nbytes(k):
+        v, u = g(k), unit(k).lower()
+        return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+    ms = g("gpu__time_duration.sum") * {"ms": 1, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(unit("gpu__time_duration.sum"), 1)
+    w = g("smsp__inst_executed.sum")
+    lanes = g("smsp__thread_inst_executed_per_inst_executed.ratio")
+    cyc = g("sm__cycles_elapsed.avg")
+    shw = g("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum")
+    j = {"kernel": kernel, "source": source, "duration_ms": ms, "warp_inst": w, "avg_active_threads_per_inst": lanes,
+         "segments_per_launch": segments, "thread_inst_per_segment": w * lanes / segments, "warp_inst_per_segment": w / segments,
+         "issue_slot_utilisation": g("smsp__issue_active.avg.pct_of_peak_sustained_active") / 100.0, "lane_efficiency": lanes / 32.0,
+         "alu_pipe_utilisation": g("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active") / 100.0,
+         "fma_pipe_utilisation": g("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active") / 100.0,
+         "dram_bytes_per_launch": nbytes("dram__bytes_read.sum") + nbytes("dram__bytes_write.sum"),
+         "shared_wavefronts": shw, "shared_wavefronts_per_cycle_per_sm": shw / max(cyc, 1) / max(g("launch__grid_size"), 1) if g("launch__grid_size") <= 148 else shw / max(cyc, 1) / 148,
+         "registers": int(g("launch__registers_per_thread")), "threads_per_cta": int(g("launch__block_size")), "ctas_per_sm": 1}
+    json.dump(j, open(out, "w"), indent=1)
+
+
 def main():
     raw, src = sys.argv[1], sys.argv[2]
-    nlines = int(sys.argv[3]) if len(sys.argv) > 3 else 30
+    nlines = int(sys.argv[3]) if len(sys.argv) > 3 and not sys.argv[3].startswith("--") else 30
     rows = list(csv.reader(open(raw)))
     hdr, units, vals = rows[0], rows[1], rows[2]
     d = {h: (vals[i], units[i]) for i, h in enumerate(hdr)}
+    if "--json" in sys.argv:
+        k = sys.argv.index("--json")
+        write_json(d, sys.argv[k + 1], float(sys.argv[k + 2]), sys.argv[k + 3], sys.argv[k + 4])
     keys = ["Kernel Name", "gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
             "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
             "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers",
             "launch__occupancy_limit_shared_mem", "dram__bytes_read.sum", "dram__bytes_write.sum", "sm__cycles_elapsed.avg",
             "smsp__sass_average_branch_targets_threads_uniform.pct", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-            "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum",
+            "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+            "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+            "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum",
             "smsp__inst_executed_op_shared_ld.sum"]
     for k in keys:
         if k in d:
