@@ -132,8 +132,10 @@ VN_API const char* vn_version(void);
 /* ---- scene: Renderer::CreateSBT (Renderer.h:452-520) + BuildAccelerationStructures (Renderer.h:160-255) ---- */
 VN_API int vn_set_spheres(vn_handle h, const vn_sphere* host_spheres, uint64_t n);
 /* Tuning knobs (defaults in brackets).  BVH: "leaf_size" [0 = auto], "aabb_pad" [0.01], "sah_max_prims" [4096: SAH splits up to this size],
- * "wide_max_prims" [16384: 4-wide nodes up to this size], "accel" [1 = BVH; 0 = auto: the uniform grid when the scene suits it, 2 = grid], "huge_factor" [50], "grid_max_per_cell" [16].  Path kernel: "wide_nodes" [1], "octant_nodes" [1], "leaf_vote" [12: lanes waiting
- * at a leaf that trigger the warp's leaf turn, 0 = while-while], "wide_global" [0], "threads", "blocks_per_sm", "smem_scene_limit".
+ * "wide_max_prims" [16384: 4-wide nodes up to this size], "accel" [1 = BVH; 0 = auto: the uniform grid when the scene suits it, 2 = grid], "huge_factor" [50], "grid_max_per_cell" [16].  Path kernel: "wide_nodes" [1], "octant_nodes" [1], "leaf_vote" [0 = while-while; n: lanes waiting
+ * at a leaf that trigger the warp's leaf turn], "wide_threads" [1024], "async_done" [26: k_render_async, a traversal burst ends when that many lanes of the
+ * warp hold a finished ray; 0 = k_render_persistent, every round waits for its slowest ray], "async_node" [0 = no votes inside a phase; n: node steps while n
+ * lanes stand on nodes], "async_leaf" [8], "wide_global" [0], "threads", "blocks_per_sm", "smem_scene_limit".
  * Experimental kernels: "slot_kernel" [0], "slot_slots", "slot_threads", "slot_tn|tl|tw|ts|tr"; "pool_slots", "pool_threads", "pool_service",
  * "pool_leaf_batch"; "wavefront_slots".  Options that change the BVH invalidate it (call vn_build_bvh again). */
 VN_API int vn_set_option(vn_handle h, const char* name, double value);

@@ -402,7 +402,7 @@ void hh_render_mean(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pa
     cam.v_unit = normalize(cam.v);
     cam.lens_radius = P->lens_radius;
     cam.wm1 = (float)(P->width - 1); cam.hm1 = (float)(P->height - 1);
-    cam.inv_wm1 = 1.0f / cam.wm1; cam.inv_hm1 = 1.0f / cam.hm1;
+    cam.inv_wm1 = 1.0f / cam.wm1; cam.inv_hm1 = 1.0f / cam.hm1; cam.div_exact = (div_by_const_ok(cam.wm1) && div_by_const_ok(cam.hm1)) ? 1u : 0u;
     uint64_t segs = 0, nv = 0, stt = 0;
     const float inv_spp = 1.0f / (float)P->spp;
     for (uint32_t px = 0; px < P->width * P->height; px++) {
@@ -464,7 +464,7 @@ extern "C" void hh_visit_histogram(const hh_sphere* s, uint32_t n, uint32_t leaf
     cam.u_unit = normalize(cam.u); cam.v_unit = normalize(cam.v);
     cam.lens_radius = P->lens_radius;
     cam.wm1 = (float)(P->width - 1); cam.hm1 = (float)(P->height - 1);
-    cam.inv_wm1 = 1.0f / cam.wm1; cam.inv_hm1 = 1.0f / cam.hm1;
+    cam.inv_wm1 = 1.0f / cam.wm1; cam.inv_hm1 = 1.0f / cam.hm1; cam.div_exact = (div_by_const_ok(cam.wm1) && div_by_const_ok(cam.hm1)) ? 1u : 0u;
     for (uint32_t px = 0; px < P->width * P->height; px++) {
         uint32_t seed = tea4(px, P->subframe_index);
         for (uint32_t k = 0; k < P->spp; k++) {
@@ -558,7 +558,7 @@ extern "C" uint64_t hh_step_sequences(const hh_sphere* s, uint32_t n, uint32_t l
     cam.u_unit = normalize(cam.u); cam.v_unit = normalize(cam.v);
     cam.lens_radius = P->lens_radius;
     cam.wm1 = (float)(P->width - 1); cam.hm1 = (float)(P->height - 1);
-    cam.inv_wm1 = 1.0f / cam.wm1; cam.inv_hm1 = 1.0f / cam.hm1;
+    cam.inv_wm1 = 1.0f / cam.wm1; cam.inv_hm1 = 1.0f / cam.hm1; cam.div_exact = (div_by_const_ok(cam.wm1) && div_by_const_ok(cam.hm1)) ? 1u : 0u;
     std::vector<uint8_t> seq;
     // pixel-major like the persistent kernel: each pixel's samples/segments are consecutive; 254 separates pixels
     for (uint32_t px = 0; px < P->width * P->height; px++) {
@@ -620,6 +620,23 @@ static void trace_sequence_pp(const SceneView& sc, f3 o, f3 d, std::vector<uint8
 }
 extern "C" void hh_set_seq_postpone(int on) { g_seq_postpone = on; }
 
+// div_by_const() against the IEEE quotient for the jitter expression 2 * (px + k * 2^-24) / b, every px in [0, b] and `per_px`
+// jitters each (edge values + a LCG sweep); returns the number of mismatches.  For divisors that fail div_by_const_ok() the
+// caller expects to see mismatches -- that is what the guard is for.
+extern "C" uint64_t hh_check_div_by_const(uint32_t b_int, uint32_t per_px) {
+    const float b = (float)b_int, rb = 1.0f / b;
+    uint64_t bad = 0;
+    uint32_t s = 12345u + b_int;
+    for (uint32_t px = 0; px <= b_int; px++)
+        for (uint32_t j = 0; j < per_px; j++) {
+            uint32_t k;
+            if (j == 0) k = 0; else if (j == 1) k = 1; else if (j == 2) k = 0xFFFFFFu; else if (j == 3) k = 0x800000u; else k = lcg(s);
+            const float a = 2.0f * ((float)px + (float)k * 5.9604644775390625e-8f);
+            bad += f2u(div_by_const(a, b, rb)) != f2u(a / b);
+        }
+    return bad;
+}
+
 // rnd_pm1() of vn_math.cuh (three instructions on the GPU) against the literal -1 + 2*rnd form of RayTracer.cu:93-97, for every
 // 24-bit LCG output and a spread of upper bytes; returns the number of mismatching bit patterns (must be 0).
 extern "C" uint64_t hh_check_rnd_pm1() {
@@ -653,7 +670,7 @@ extern "C" void hh_visits_custom(const node_f4* nodes, uint32_t n_nodes, const h
     cam.u_unit = normalize(cam.u); cam.v_unit = normalize(cam.v);
     cam.lens_radius = P->lens_radius;
     cam.wm1 = (float)(P->width - 1); cam.hm1 = (float)(P->height - 1);
-    cam.inv_wm1 = 1.0f / cam.wm1; cam.inv_hm1 = 1.0f / cam.hm1;
+    cam.inv_wm1 = 1.0f / cam.wm1; cam.inv_hm1 = 1.0f / cam.hm1; cam.div_exact = (div_by_const_ok(cam.wm1) && div_by_const_ok(cam.hm1)) ? 1u : 0u;
     uint64_t segs = 0, nv = 0, sv = 0;
     for (uint32_t px = 0; px < P->width * P->height; px++) {
         uint32_t seed = tea4(px, P->subframe_index);

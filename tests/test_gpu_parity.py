@@ -432,7 +432,7 @@ def test_async_kernel_equals_persistent_kernel(ctx, oracle_mod, rtiow, threads):
             orc = oracle_mod.Oracle(rtiow)
             want, ost = orc.render_mean(orc.params(cam.frame(), W, H, spp, sub, depth, atten=oracle_mod.ATTEN_FORWARD))
             assert np.array_equal(e.view(np.uint32), want.view(np.uint32)) and se.segments == ost.segments
-            for done, node, leaf in ((32, 1, 1), (24, 8, 8), (1, 1, 1), (16, 32, 32), (28, 12, 4)):
+            for done, node, leaf in ((32, 1, 1), (24, 8, 8), (1, 1, 1), (16, 32, 32), (28, 12, 4), (28, 0, 8), (1, 0, 8), (32, 0, 8)):
                 ctx.set_option("async_done", done)
                 ctx.set_option("async_node", node)
                 ctx.set_option("async_leaf", leaf)

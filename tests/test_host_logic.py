@@ -217,6 +217,15 @@ def test_rnd_pm1_short_form_equals_literal_form(host_harness):
     assert host_harness.hh_check_rnd_pm1() == 0
 
 
+def test_div_by_const_equals_ieee_division(host_harness):
+    """camera_ray divides by float(width - 1) / float(height - 1) (RayTracer.cu:173-174); vn_math.cuh::div_by_const gives the same bits
+    with one multiply and two fmas whenever div_by_const_ok() accepts the divisor (significand not all ones)."""
+    host_harness.hh_check_div_by_const.restype = C.c_uint64
+    host_harness.hh_check_div_by_const.argtypes = [C.c_uint32, C.c_uint32]
+    for b in (1919, 1079, 3839, 2159, 399, 224, 1199, 799, 199, 119, 32, 16, 4, 1, 2, 5, 1000, 4096, 47, 99):
+        assert host_harness.hh_check_div_by_const(b, 4096 if b > 300 else 65536) == 0, b
+
+
 def test_octant_mirrored_traversal_equals_plain_on_cpu(host_harness, oracle_mod, rtiow):
     """k_render_persistent's octant-specialised node copies (near/far-plane form, no per-axis min/max) find exactly
     the same closest hits, and visit exactly as many nodes, as the plain lo/hi slab test."""

@@ -46,6 +46,7 @@ struct Sim {
     SceneView sc;
     double cost = 0, c_node = 0, c_leaf = 0, c_shade = 0, c_sched = 0;
     uint64_t hist[2][64] = {{0}};
+    uint64_t ph_node[8] = {0}, ph_lanes[8] = {0}, ph_leaf[8] = {0}, ph_leaf_lanes[8] = {0}, rounds = 0;
     uint64_t segs = 0, n_node_ops = 0, n_leaf_ops = 0, n_shade_ops = 0, lanes_node = 0, lanes_leaf = 0, lanes_shade = 0;
 
     bool fetch(Lane& L) {
@@ -272,12 +273,15 @@ struct Sim {
         if (policy == 0) {
             // shipped kernel: shade/regen for everybody, then while-while to completion
             cost += shade_phase(w);
+            int phase = 0;
             for (;;) {
                 count(w, nN, nL, nD, nLive);
                 if (nN == 0 && nL == 0) break;
-                while (nN) { cost += node_op(w); count(w, nN, nL, nD, nLive); }
-                if (nL) cost += leaf_op(w);
+                while (nN) { cost += node_op(w); ph_node[std::min(phase, 7)]++; ph_lanes[std::min(phase, 7)] += nN; count(w, nN, nL, nD, nLive); }
+                if (nL) { cost += leaf_op(w); ph_leaf[std::min(phase, 7)]++; ph_leaf_lanes[std::min(phase, 7)] += nL; }
+                phase++;
             }
+            rounds++;
             return true;
         }
         // asynchronous: one operation per quantum, chosen by thresholds
@@ -327,6 +331,7 @@ int main(int argc, char** argv) {
            policy, Tn, Tl, Td, S.B.huge.n, S.B.wide_oct.size() / 56, (unsigned long long)S.segs, S.cost / S.segs, S.c_node / S.segs, S.c_leaf / S.segs,
            S.c_shade / S.segs, S.c_sched / S.segs, (double)S.n_node_ops / S.segs, (double)S.n_leaf_ops / S.segs, (double)S.n_shade_ops / S.segs,
            (double)S.lanes_node / S.n_node_ops, (double)S.lanes_leaf / S.n_leaf_ops, (double)S.lanes_shade / S.n_shade_ops);
+    if (getenv("PHASES")) for (int k = 0; k < 8; k++) printf("phase %d: node ops/round %.2f (lanes %.1f)  leaf ops/round %.2f (lanes %.1f)\n", k, (double)S.ph_node[k] / S.rounds, S.ph_node[k] ? (double)S.ph_lanes[k] / S.ph_node[k] : 0.0, (double)S.ph_leaf[k] / S.rounds, S.ph_leaf[k] ? (double)S.ph_leaf_lanes[k] / S.ph_leaf[k] : 0.0);
     if (getenv("HIST")) for (int k = 0; k < 2; k++) { uint64_t tot = 0, sum = 0; for (int i = 0; i < 64; i++) { tot += S.hist[k][i]; sum += i * S.hist[k][i]; } printf("%s rays %llu mean steps %.2f:", k ? "secondary" : "primary", (unsigned long long)tot, (double)sum / tot); double cum = 0; for (int i = 0; i < 40; i++) { cum += S.hist[k][i]; printf(" %d:%.3f", i, cum / tot); } printf("\n"); }
     if (policy >= 3) {
         const char* nm[9] = {"", "node", "leaf", "resolve", "", "camera", "opaque", "dielectric", "start"};

@@ -43,7 +43,18 @@ struct RenderLaunch {
     unsigned long long* counters;    // [0] segments, [1] paths, [2] node visits, [3] sphere tests
     uint32_t* work_counter;          // persistent-thread work ticket
     uint32_t total_work, tiles_x;    // work items = 8x4 pixel tiles * 32
+    uint32_t tiles_x_inv;            // floor(2^32 / tiles_x): tile / tiles_x = __umulhi(tile, tiles_x_inv) plus at most two corrections (tile_row_col)
 };
+
+// tile index -> (row, column) of the 8x4-pixel work tile without the 25-instruction integer division (the quotient estimate is at most
+// two short for any 32-bit tile index; exact for tiles_x = 1, where floor(2^32 / 1) does not fit and 0xFFFFFFFF is stored)
+__device__ __forceinline__ void tile_row_col(uint32_t tile, uint32_t tiles_x, uint32_t tiles_x_inv, uint32_t& ty, uint32_t& tx) {
+    uint32_t q = __umulhi(tile, tiles_x_inv);
+    uint32_t r = tile - q * tiles_x;
+    if (r >= tiles_x) { q += 1u; r -= tiles_x; }
+    if (r >= tiles_x) { q += 1u; r -= tiles_x; }
+    ty = q; tx = r;
+}
 
 struct KernelConfig {
     int threads;

@@ -278,7 +278,8 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_persistent(const __grid_
                     const uint32_t w = fetch_work(p.work_counter);
                     if (w >= p.total_work) break;
                     const uint32_t tile = w >> 5, in = w & 31u;
-                    const uint32_t ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+                    uint32_t ty, tx;
+                        tile_row_col(tile, p.tiles_x, p.tiles_x_inv, ty, tx);
                     px = tx * 8u + (in & 7u);
                     py = p.row_begin + ty * 4u + (in >> 3);
                     if (px < p.width && py < p.row_end) { got = true; break; }
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_persistent(const __grid_
 // bit-identical to k_render_persistent; only the order in which a warp's lanes take their turns differs (tools/simt_sim_async.cpp
 // is the model the thresholds came from).  Lanes that run out of pixels stay in the loop as zombies until the whole warp is done,
 // which keeps every vote a full-mask __ballot_sync.
-template <bool kCount, int kMaxThreads>
+template <bool kCount, int kMaxThreads, bool kPhase = false>
 __global__ void __launch_bounds__(kMaxThreads) k_render_async(const __grid_constant__ RenderLaunch p) {
     extern __shared__ float4 s_scene[];
     SceneView sc;
@@ -423,7 +424,8 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_async(const __grid_const
                         const uint32_t w = fetch_work(p.work_counter);
                         if (w >= p.total_work) break;
                         const uint32_t tile = w >> 5, in = w & 31u;
-                        const uint32_t ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+                        uint32_t ty, tx;
+                        tile_row_col(tile, p.tiles_x, p.tiles_x_inv, ty, tx);
                         px = tx * 8u + (in & 7u);
                         py = p.row_begin + ty * 4u + (in >> 3);
                         if (px < p.width && py < p.row_end) { got = true; break; }
@@ -471,6 +473,30 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_async(const __grid_const
         if (live == 0u) break;
         const uint32_t n_live = (uint32_t)__popc(live);
         const uint32_t t_done = p.async_done < n_live ? p.async_done : n_live;
+        if (kPhase) {
+            // phase form: the while-while phases of closest_hit_wide() without any vote inside them -- every lane descends until it
+            // holds a leaf (divergent loop, no ballot), the lanes at a leaf test it -- and ONE vote per phase: the burst ends as soon
+            // as t_done lanes are finished.  A round of the persistent kernel spends 5.8 of its 13.2 node turns and 1.7 of its 2.7
+            // leaf turns in second and later phases that only ~4 lanes take part in; here those stragglers ride along with the next
+            // burst of everybody else.
+            for (;;) {
+                while ((cur & kLeafFlag) == 0u) {
+                    if (kCount) cnt.nodes += 1;
+                    cur = wide_node_step_dev(wb, cur, ss, top, base);
+                }
+                if (cur != kEmptyScene) {
+                    const float a = dot(st.d, st.d), t_before = tbest;
+                    leaf_test<kCount>(sc.geom, cur, st.o, st.d, a, rcp(a), tbest, prim, cnt);
+                    cur = stack_pop_dev(top, base);
+                    if (tbest != t_before) {
+                        const float g = t_before * rcp_approx(tbest);
+                        ss.sdir = ss.sdir * g; ss.nsood = ss.nsood * g;
+                    }
+                }
+                if ((uint32_t)__popc(__ballot_sync(kFull, cur == kEmptyScene && !retired)) >= t_done) break;
+            }
+            continue;
+        }
         // traversal burst: voted node / leaf turns until t_done lanes hold a finished ray
         for (;;) {
             const bool done = cur == kEmptyScene;
@@ -622,8 +648,12 @@ inline uint32_t grid_for(uint64_t n, int threads) { return (uint32_t)((n + threa
 
 namespace {
 typedef void (*PathKernel)(const RenderLaunch);
-PathKernel pick_kernel(bool scene_in_smem, bool count, bool octant, bool wide = false, int threads = 1024, bool grid = false, bool async = false) {
+PathKernel pick_kernel(bool scene_in_smem, bool count, bool octant, bool wide = false, int threads = 1024, bool grid = false, bool async = false, bool phase = false) {
     if (async && wide && scene_in_smem && !grid) {
+        if (phase) {
+            if (threads <= 768) return count ? k_render_async<true, 768, true> : k_render_async<false, 768, true>;
+            return count ? k_render_async<true, 1024, true> : k_render_async<false, 1024, true>;
+        }
         if (threads <= 512) return count ? k_render_async<true, 512> : k_render_async<false, 512>;
         if (threads <= 768) return count ? k_render_async<true, 768> : k_render_async<false, 768>;
         return count ? k_render_async<true, 1024> : k_render_async<false, 1024>;
@@ -650,7 +680,7 @@ int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool c
 }
 
 cudaError_t launch_render_persistent(const RenderLaunch& p, const KernelConfig& cfg, cudaStream_t stream) {
-    PathKernel k = pick_kernel(cfg.scene_in_smem, cfg.count, cfg.octant, cfg.wide, cfg.threads, cfg.grid, cfg.async);
+    PathKernel k = pick_kernel(cfg.scene_in_smem, cfg.count, cfg.octant, cfg.wide, cfg.threads, cfg.grid, cfg.async, cfg.async && p.async_node == 0u);
     if (cfg.smem_bytes > 48 * 1024) {
         const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes);
         if (e != cudaSuccess) return e;

@@ -77,8 +77,8 @@ struct vn_context {
     float huge_factor = 50.0f;        // spheres with radius > huge_factor x median are tested before the wide traversal (0 = none), lbvh_core.cuh::HugeList
     int wide_threads = 1024;          // CTA size of the wide-node path kernel (one CTA per SM): 512, 768 or 1024 (64 registers per lane at 1024)
     uint32_t leaf_vote = 0;           // see closest_hit_wide_vote (path_kernels.cu); 0 = while-while
-    uint32_t async_done = 0;          // k_render_async: a traversal burst ends when this many lanes hold a finished ray (0 = k_render_persistent)
-    uint32_t async_node = 8, async_leaf = 8;
+    uint32_t async_done = 26;         // k_render_async: a traversal burst ends when this many lanes hold a finished ray (0 = k_render_persistent)
+    uint32_t async_node = 0, async_leaf = 8;   // async_node 0 = phase form (no votes inside the node / leaf phases), the default
     bool wide_nodes = true;           // use them when they fit in shared memory
     uint32_t sah_max_prims = 4096;    // scenes up to this size get SAH splits (k_sah_small); 0 = always Karras
     int threads = 256;
@@ -143,6 +143,7 @@ int fill_launch(vn_context* c, const vn_params* p, RenderLaunch& L) {
     L.cam.hm1 = (float)(p->height - 1u);
     L.cam.inv_wm1 = 1.0f / L.cam.wm1;
     L.cam.inv_hm1 = 1.0f / L.cam.hm1;
+    L.cam.div_exact = (div_by_const_ok(L.cam.wm1) && div_by_const_ok(L.cam.hm1)) ? 1u : 0u;
     L.width = p->width; L.height = p->height;
     L.spp = p->samples_per_pixel;
     L.subframe_index = p->subframe_index;
@@ -168,6 +169,7 @@ int fill_launch(vn_context* c, const vn_params* p, RenderLaunch& L) {
     L.work_counter = reinterpret_cast<uint32_t*>(c->d_counters + 4);
     const uint32_t rows = L.row_end - L.row_begin;
     L.tiles_x = (p->width + 7u) / 8u;
+    L.tiles_x_inv = L.tiles_x > 1u ? (uint32_t)(0x100000000ull / L.tiles_x) : 0xFFFFFFFFu;
     L.total_work = L.tiles_x * ((rows + 3u) / 4u) * 32u;
     return VN_OK;
 }
@@ -284,7 +286,7 @@ int vn_set_option(vn_handle c, const char* name, double value) {
     else if (k == "huge_factor") { VN_REQUIRE(c, value >= 0, "huge_factor must be >= 0"); c->huge_factor = (float)value; c->bvh_valid = false; }
     else if (k == "wide_threads") { VN_REQUIRE(c, value == 512 || value == 768 || value == 1024, "wide_threads must be 512, 768 or 1024"); c->wide_threads = (int)value; }
     else if (k == "async_done") { VN_REQUIRE(c, value >= 0 && value <= 32, "async_done must be in [0,32]"); c->async_done = (uint32_t)value; }
-    else if (k == "async_node") { VN_REQUIRE(c, value >= 1 && value <= 32, "async_node must be in [1,32]"); c->async_node = (uint32_t)value; }
+    else if (k == "async_node") { VN_REQUIRE(c, value >= 0 && value <= 32, "async_node must be in [0,32] (0 = phase form: no votes inside the node / leaf phases)"); c->async_node = (uint32_t)value; }
     else if (k == "async_leaf") { VN_REQUIRE(c, value >= 1 && value <= 32, "async_leaf must be in [1,32]"); c->async_leaf = (uint32_t)value; }
     else if (k == "leaf_vote") { VN_REQUIRE(c, value >= 0 && value <= 32, "leaf_vote must be in [0,32]"); c->leaf_vote = (uint32_t)value; }
     else if (k == "slot_kernel") { c->slot_kernel = value != 0; }

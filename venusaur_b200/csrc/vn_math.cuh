@@ -46,6 +46,14 @@ VN_HD f3 operator*(f3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
 VN_HD f3 operator*(float s, f3 a) { return mk3(a.x * s, a.y * s, a.z * s); }
 VN_HD float dot(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }            // vec_math.h:527-530
 
+VN_HD uint32_t f2u_early(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    union { float f; uint32_t u; } c; c.f = f; return c.u;
+#endif
+}
+
 // ---- mode-dependent scalar primitives
 VN_HD float rcp(float a) {
 #if VN_FAST_DEVICE
@@ -148,8 +156,21 @@ struct Camera {
     f3 u_unit, v_unit;       // normalize(params.u), normalize(params.v): loop invariants of get_ray (RayTracer.cu:155-156)
     float lens_radius;
     float wm1, hm1;          // float(width-1), float(height-1)
-    float inv_wm1, inv_hm1;  // FAST build only
+    float inv_wm1, inv_hm1;  // RN(1 / wm1), RN(1 / hm1): the FAST build multiplies by them, the IEEE build uses them in div_by_const()
+    uint32_t div_exact;      // both divisors satisfy div_by_const_ok()
 };
+
+// a / b for the two per-launch constants of the jitter below (b = float(width - 1), float(height - 1)) without the 10-instruction
+// IEEE division: with rb = RN(1 / b) formed once on the host, q = RN(a * rb) is within an ulp of the quotient, r = a - q * b is exact
+// in one fma, and RN(q + r * rb) is the correctly rounded a / b (Markstein's theorem; it needs a divisor whose significand is not
+// all ones, which is what Camera::div_exact records -- otherwise the plain division runs).  tests/test_host_logic.py compares it
+// with a / b over every pixel column of the usual widths and 2^12 jitters each.
+VN_HD float div_by_const(float a, float b, float rb) {
+    const float q = a * rb;
+    const float r = fmaf(-q, b, a);
+    return fmaf(r, rb, q);
+}
+VN_HD bool div_by_const_ok(float b) { return b >= 1.0f && b < 16777216.0f && (f2u_early(b) & 0x007FFFFFu) != 0x007FFFFFu; }
 
 // get_ray + the jitter of __raygen__rg: RayTracer.cu:151-161,173-174
 VN_HD void camera_ray(const Camera& c, uint32_t px, uint32_t py, uint32_t& seed, f3& origin, f3& direction) {
@@ -159,8 +180,9 @@ VN_HD void camera_ray(const Camera& c, uint32_t px, uint32_t py, uint32_t& seed,
     float s = 2.0f * ((float)px + ju) * c.inv_wm1 - 1.0f;
     float t = 2.0f * ((float)py + jv) * c.inv_hm1 - 1.0f;
 #else
-    float s = 2.0f * ((float)px + ju) / c.wm1 - 1.0f;
-    float t = 2.0f * ((float)py + jv) / c.hm1 - 1.0f;
+    const float su = 2.0f * ((float)px + ju), tv = 2.0f * ((float)py + jv);
+    float s = (c.div_exact ? div_by_const(su, c.wm1, c.inv_wm1) : su / c.wm1) - 1.0f;
+    float t = (c.div_exact ? div_by_const(tv, c.hm1, c.inv_hm1) : tv / c.hm1) - 1.0f;
 #endif
     float dx, dy;
     random_in_unit_disk(seed, dx, dy);
