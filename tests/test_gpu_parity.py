@@ -414,6 +414,44 @@ def test_octant_and_plain_persistent_kernels_agree(rtiow_ctx):
     assert sc.node_visits == sd.node_visits and sc.sphere_tests == sd.sphere_tests
 
 
+def test_cost_ordered_tiles_do_not_change_the_image(ctx, rtiow):
+    """vn_render hands the 8x4-pixel tiles out most expensive first once it has seen one launch of a view (vn_api.cu::prepare_tile_order):
+    the first launch counts ray segments per tile, the second sorts and uses the order.  Pixels are independent, so every launch of
+    the same subframe gives the same bits as the row-major schedule (`tile_order` = 0), also after the view changes and for row shards."""
+    ctx.set_spheres(rtiow)
+    ctx.build_bvh()
+    W, H, spp, depth = 640, 360, 4, 50                          # 7200 tiles >= 32 per SM: the schedule is active
+    try:
+        for kernel_opts in ({"async_done": 26, "async_node": 0}, {"async_done": 0}):
+            for k, v in kernel_opts.items():
+                ctx.set_option(k, v)
+            cam = vb.rtiow_camera(W, H)
+            ctx.set_option("tile_order", 0)
+            ref, iref, sref = render(ctx, cam, W, H, spp, 3, depth)
+            ctx.set_option("tile_order", 1)
+            for launch in range(3):                             # collect, sort + use, use
+                a, ia, sa = render(ctx, cam, W, H, spp, 3, depth)
+                assert np.array_equal(a.view(np.uint32), ref.view(np.uint32)) and np.array_equal(ia, iref), launch
+                assert (sa.segments, sa.paths) == (sref.segments, sref.paths)
+            c, ic, sc = render(ctx, cam, W, H, spp, 3, depth, flags=VN_COUNTERS)
+            assert np.array_equal(c.view(np.uint32), ref.view(np.uint32))
+            # a row shard is a different view (its own order); the shard equals the rows of the full frame
+            rows = (120, 300)
+            for launch in range(3):
+                b, ib, sb = render(ctx, cam, W, H, spp, 3, depth, rows=rows)
+                assert np.array_equal(b[rows[0]:rows[1]].view(np.uint32), ref[rows[0]:rows[1]].view(np.uint32)), launch
+            # another camera invalidates the order
+            cam2 = vb.rtiow_camera(W, H)
+            cam2.SetPosition((10.0, 3.0, 5.0))
+            d1, _, _ = render(ctx, cam2, W, H, spp, 5, depth)
+            d2, _, _ = render(ctx, cam2, W, H, spp, 5, depth)
+            assert np.array_equal(d1.view(np.uint32), d2.view(np.uint32))
+    finally:
+        ctx.set_option("tile_order", 1)
+        ctx.set_option("async_done", 26)
+        ctx.set_option("async_node", 0)
+
+
 @pytest.mark.parametrize("threads", [512, 768, 1024])
 def test_async_kernel_equals_persistent_kernel(ctx, oracle_mod, rtiow, threads):
     """k_render_async (asynchronous shading: lanes keep their traversal state across the shading of other lanes, voted node /
@@ -444,8 +482,8 @@ def test_async_kernel_equals_persistent_kernel(ctx, oracle_mod, rtiow, threads):
                 assert np.array_equal(h.view(np.uint32), e.view(np.uint32))
                 assert (sh.segments, sh.node_visits, sh.sphere_tests) == (sf.segments, sf.node_visits, sf.sphere_tests)
     finally:
-        ctx.set_option("async_done", 0)
-        ctx.set_option("async_node", 8)
+        ctx.set_option("async_done", 26)
+        ctx.set_option("async_node", 0)
         ctx.set_option("async_leaf", 8)
         ctx.set_option("wide_threads", 1024)
 

@@ -1,0 +1,30 @@
+#!/usr/bin/env python
+"""How much of a launch is drain?  Runs the instrumented path kernel (VN_COUNTERS) on the headline workload and reads the launch
+timeline it leaves in the scheduler-statistics words: start, first lane that found the ticket counter exhausted, mean and max
+warp end.  GPU only."""
+import ctypes as C, os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import venusaur_b200 as vb
+from venusaur_b200 import VN_COUNTERS, VN_NO_TONEMAP
+
+def main():
+    ctx = vb.Context(0)
+    ctx.set_spheres(vb.rtiow_final_scene()); ctx.build_bvh()
+    for (W, H) in ((1920, 1080), (3840, 2160)):
+        cam = vb.rtiow_camera(W, H)
+        for rep in range(3):
+            ctx.render(ctx.make_params(cam, W, H, 16, 1 + rep, 50, flags=VN_COUNTERS | VN_NO_TONEMAP))
+            st = ctx.stats()
+            raw = (C.c_uint64 * 14)()
+            ctx._check(ctx.lib.vn_read_sched_counters(ctx.h, raw), "vn_read_sched_counters")
+            M = (1 << 64) - 1
+            start, exhaust, end, sum_end, nw = M - raw[0], M - raw[1], raw[2], raw[3], raw[4]
+            mean_end = sum_end / max(nw, 1)
+            print("%dx%d rep %d: ms_render %.3f | kernel %.3f ms, tickets exhausted at %.3f ms (%.1f %%), mean warp end %.3f ms, drain %.3f ms; lane-time lost in the drain ~ %.1f %% of the launch"
+                  % (W, H, rep, st.ms_render, (end - start) / 1e6, (exhaust - start) / 1e6, 100.0 * (exhaust - start) / (end - start),
+                     (mean_end - start) / 1e6, (end - exhaust) / 1e6, 100.0 * (end - mean_end) / (end - start)))
+    ctx.close()
+
+if __name__ == "__main__":
+    main()

@@ -265,19 +265,25 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_persistent(const __grid_
     f3 sum = mk3(0.0f);
     PathState st;
     st.o = st.d = st.thr = mk3(0.0f); st.seed = 0; st.depth = 0;
-    uint32_t n_seg = 0, n_path = 0;
+    uint32_t n_seg = 0, n_path = 0, seg0 = 0;    // seg0: n_seg when the current pixel started (tile cost feedback)
     TraceCounters cnt{0u, 0u};
     unsigned long long n_nodes = 0, n_sph = 0;
 
     for (;;) {
         if (!active) {
-            if (has_pixel && s_left == 0u) { finish_pixel(p, pix, sum); has_pixel = false; }
+            if (has_pixel && s_left == 0u) {
+                finish_pixel(p, pix, sum);
+                if (p.tile_cost) atomicAdd(p.tile_cost + ((py - p.row_begin) >> 2) * p.tiles_x + (px >> 3), n_seg - seg0);
+                has_pixel = false;
+            }
             if (!has_pixel) {
                 bool got = false;
                 for (;;) {
                     const uint32_t w = fetch_work(p.work_counter);
                     if (w >= p.total_work) break;
-                    const uint32_t tile = w >> 5, in = w & 31u;
+                    uint32_t tile = w >> 5;
+                    const uint32_t in = w & 31u;
+                    if (p.tile_order) tile = __ldg(p.tile_order + tile);
                     uint32_t ty, tx;
                         tile_row_col(tile, p.tiles_x, p.tiles_x_inv, ty, tx);
                     px = tx * 8u + (in & 7u);
@@ -287,6 +293,7 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_persistent(const __grid_
                 if (!got) break;                                  // no pixels left: this lane retires
                 pix = py * p.width + px;
                 cam_seed = tea4(pix, p.subframe_index);           // RayTracer.cu:169
+                seg0 = n_seg;
                 sum = mk3(0.0f);
                 s_left = p.spp;
                 has_pixel = true;
@@ -360,6 +367,12 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_persistent(const __grid_
 // bit-identical to k_render_persistent; only the order in which a warp's lanes take their turns differs (tools/simt_sim_async.cpp
 // is the model the thresholds came from).  Lanes that run out of pixels stay in the loop as zombies until the whole warp is done,
 // which keeps every vote a full-mask __ballot_sync.
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 template <bool kCount, int kMaxThreads, bool kPhase = false>
 __global__ void __launch_bounds__(kMaxThreads) k_render_async(const __grid_constant__ RenderLaunch p) {
     extern __shared__ float4 s_scene[];
@@ -386,13 +399,16 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_async(const __grid_const
     }
     sc.root_link = p.root_link;
     constexpr unsigned kFull = 0xFFFFFFFFu;
+    // instrumented variant: launch timeline in counters[8..11) (read with vn_read_sched_counters): ~min start, ~min time at which a lane
+    // found the ticket counter exhausted, max end -- the share of a launch spent draining (lanes idle behind the last pixels)
+    if (kCount && threadIdx.x == 0) atomicMax(&p.counters[8], ~global_ns());
 
     uint32_t pix = 0, px = 0, py = 0, cam_seed = 0, s_left = 0;
     bool has_pixel = false, active = false, retired = false;
     f3 sum = mk3(0.0f);
     PathState st;
     st.o = st.d = st.thr = mk3(0.0f); st.seed = 0; st.depth = 0;
-    uint32_t n_seg = 0, n_path = 0;
+    uint32_t n_seg = 0, n_path = 0, seg0 = 0;    // seg0: n_seg when the current pixel started (tile cost feedback)
     TraceCounters cnt{0u, 0u};
     // traversal state, alive across the shading of other lanes
     uint32_t stack[kStackSize];
@@ -417,13 +433,19 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_async(const __grid_const
                 }
             }
             if (!active) {
-                if (has_pixel && s_left == 0u) { finish_pixel(p, pix, sum); has_pixel = false; }
+                if (has_pixel && s_left == 0u) {
+                    finish_pixel(p, pix, sum);
+                    if (p.tile_cost) atomicAdd(p.tile_cost + ((py - p.row_begin) >> 2) * p.tiles_x + (px >> 3), n_seg - seg0);
+                    has_pixel = false;
+                }
                 if (!has_pixel) {
                     bool got = false;
                     for (;;) {
                         const uint32_t w = fetch_work(p.work_counter);
                         if (w >= p.total_work) break;
-                        const uint32_t tile = w >> 5, in = w & 31u;
+                        uint32_t tile = w >> 5;
+                        const uint32_t in = w & 31u;
+                        if (p.tile_order) tile = __ldg(p.tile_order + tile);
                         uint32_t ty, tx;
                         tile_row_col(tile, p.tiles_x, p.tiles_x_inv, ty, tx);
                         px = tx * 8u + (in & 7u);
@@ -433,10 +455,11 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_async(const __grid_const
                     if (got) {
                         pix = py * p.width + px;
                         cam_seed = tea4(pix, p.subframe_index);   // RayTracer.cu:169
+                        seg0 = n_seg;
                         sum = mk3(0.0f);
                         s_left = p.spp;
                         has_pixel = true;
-                    } else retired = true;                        // no pixels left: this lane only votes from now on
+                    } else { retired = true; if (kCount) atomicMax(&p.counters[9], ~global_ns()); }   // no pixels left: this lane only votes from now on
                 }
                 if (!retired) {
                     camera_ray(p.cam, px, py, cam_seed, st.o, st.d);   // RayTracer.cu:173-177
@@ -526,6 +549,12 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_async(const __grid_const
             }
         }
     }
+    if (kCount && (threadIdx.x & 31u) == 0u) {
+        const unsigned long long t = global_ns();
+        atomicMax(&p.counters[10], t);
+        atomicAdd(&p.counters[11], t + (~p.counters[9]) * 0ull);          // sum of warp end times (mean end = sum / warps)
+        atomicAdd(&p.counters[12], 1ull);
+    }
     {
         unsigned long long seg = n_seg, path = n_path, nn = cnt.nodes, ns = cnt.spheres;
         cg::coalesced_group g = cg::coalesced_threads();
@@ -541,6 +570,16 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_async(const __grid_const
             if (kCount) { atomicAdd(&p.counters[2], nn); atomicAdd(&p.counters[3], ns); }
         }
     }
+}
+
+// Sort keys of the cost-ordered tile schedule: most expensive tile first = smallest key; 24 bits are plenty (a tile's cost is the
+// number of ray segments its 32 pixels took in one launch).
+__global__ void __launch_bounds__(256) k_tile_keys(const uint32_t* __restrict__ cost, uint32_t n, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t c = cost[i] < 0x00FFFFFFu ? cost[i] : 0x00FFFFFFu;
+    keys[i] = 0x00FFFFFFu - c;
+    vals[i] = i;
 }
 
 // Kernel (3) of the north star when used stand-alone: image = make_color(accum * scale).  One pixel per thread:
@@ -686,6 +725,12 @@ cudaError_t launch_render_persistent(const RenderLaunch& p, const KernelConfig& 
         if (e != cudaSuccess) return e;
     }
     k<<<cfg.blocks, cfg.threads, cfg.smem_bytes, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tile_keys(const uint32_t* cost, uint32_t n, uint32_t* keys, uint32_t* vals, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    k_tile_keys<<<(n + 255u) / 256u, 256, 0, stream>>>(cost, n, keys, vals);
     return cudaGetLastError();
 }
 

@@ -77,6 +77,15 @@ struct vn_context {
     float huge_factor = 50.0f;        // spheres with radius > huge_factor x median are tested before the wide traversal (0 = none), lbvh_core.cuh::HugeList
     int wide_threads = 1024;          // CTA size of the wide-node path kernel (one CTA per SM): 512, 768 or 1024 (64 registers per lane at 1024)
     uint32_t leaf_vote = 0;           // see closest_hit_wide_vote (path_kernels.cu); 0 = while-while
+    // cost-ordered tile schedule (prepare_tile_order): per-tile ray segments of the previous launch of the same view, sorted descending
+    uint32_t tile_order_opt = 1;      // "tile_order": 0 = row-major tickets
+    uint32_t* d_tile_cost = nullptr;  // [tile_cap]
+    uint32_t* d_tile_sort = nullptr;  // [4 * tile_cap]: keys, values and their alternates for the radix sort
+    const uint32_t* d_tile_order = nullptr;
+    uint32_t tile_cap = 0;
+    int tile_state = 0;               // 0: nothing known (the next launch collects costs), 1: costs collected (sort before the next launch), 2: order valid
+    struct TileSig { uint32_t w, h, r0, r1, spp, depth; float cam[13]; uint64_t epoch; } tile_sig{};
+    uint64_t bvh_epoch = 0;
     uint32_t async_done = 26;         // k_render_async: a traversal burst ends when this many lanes hold a finished ray (0 = k_render_persistent)
     uint32_t async_node = 0, async_leaf = 8;   // async_node 0 = phase form (no votes inside the node / leaf phases), the default
     bool wide_nodes = true;           // use them when they fit in shared memory
@@ -168,6 +177,7 @@ int fill_launch(vn_context* c, const vn_params* p, RenderLaunch& L) {
     L.counters = c->d_counters;
     L.work_counter = reinterpret_cast<uint32_t*>(c->d_counters + 4);
     const uint32_t rows = L.row_end - L.row_begin;
+    L.tile_order = nullptr; L.tile_cost = nullptr;
     L.tiles_x = (p->width + 7u) / 8u;
     L.tiles_x_inv = L.tiles_x > 1u ? (uint32_t)(0x100000000ull / L.tiles_x) : 0xFFFFFFFFu;
     L.total_work = L.tiles_x * ((rows + 3u) / 4u) * 32u;
@@ -256,7 +266,7 @@ void vn_destroy(vn_handle c) {
     grid_free(c->grid);
     lbvh_workspace_free(c->bvh_ws);
     free_wavefront(c->wf); c->wf_sample_floats_ = 0;
-    cudaFree(c->d_spheres); cudaFree(c->accum_own); cudaFree(c->image_tmp); cudaFree(c->d_counters);
+    cudaFree(c->d_tile_cost); cudaFree(c->d_tile_sort); cudaFree(c->d_spheres); cudaFree(c->accum_own); cudaFree(c->image_tmp); cudaFree(c->d_counters);
     cudaFreeHost(c->h_counters);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (int i = 0; i < 2; i++) { cudaFree(c->image_pipe[i]); if (c->ev_frame[i]) cudaEventDestroy(c->ev_frame[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
@@ -285,6 +295,7 @@ int vn_set_option(vn_handle c, const char* name, double value) {
     else if (k == "grid_max_per_cell") { VN_REQUIRE(c, value >= 1 && value <= 65535, "grid_max_per_cell must be in [1,65535]"); c->grid_max_per_cell = (uint32_t)value; c->bvh_valid = false; }
     else if (k == "huge_factor") { VN_REQUIRE(c, value >= 0, "huge_factor must be >= 0"); c->huge_factor = (float)value; c->bvh_valid = false; }
     else if (k == "wide_threads") { VN_REQUIRE(c, value == 512 || value == 768 || value == 1024, "wide_threads must be 512, 768 or 1024"); c->wide_threads = (int)value; }
+    else if (k == "tile_order") { c->tile_order_opt = value != 0 ? 1u : 0u; c->tile_state = 0; }
     else if (k == "async_done") { VN_REQUIRE(c, value >= 0 && value <= 32, "async_done must be in [0,32]"); c->async_done = (uint32_t)value; }
     else if (k == "async_node") { VN_REQUIRE(c, value >= 0 && value <= 32, "async_node must be in [0,32] (0 = phase form: no votes inside the node / leaf phases)"); c->async_node = (uint32_t)value; }
     else if (k == "async_leaf") { VN_REQUIRE(c, value >= 1 && value <= 32, "async_leaf must be in [1,32]"); c->async_leaf = (uint32_t)value; }
@@ -364,6 +375,7 @@ int vn_build_bvh(vn_handle c) {
     VN_CUDA(c, cudaEventElapsedTime(&c->stats.ms_build, c->ev[0], c->ev[1]));
     c->stats.kernel_launches_total += launches;
     c->bvh_valid = true;
+    c->bvh_epoch += 1;
     return VN_OK;
 }
 
@@ -597,6 +609,50 @@ static bool use_slot_kernel(const vn_context* c, const vn_params* p, const Rende
     return exact::slot_smem_bytes(L.num_wide, L.num_spheres, c->slot_slots, c->slot_threads) + 1024 <= c->smem_optin;
 }
 
+// Longest-processing-time-first schedule for the persistent path kernels.  Lanes take 8x4-pixel tiles from a global ticket; with
+// row-major tickets a launch ends with ~0.7 ms (11 % of a 1080p launch, measured with tools/tail_probe.py) in which the tickets
+// are gone and ever fewer lanes finish the expensive pixels (glass: paths of up to max_depth segments) they took late.  Progressive
+// rendering launches the same view again and again (Renderer::Draw, Renderer.h:35-78), so the first launch of a view counts every
+// tile's ray segments, the tiles are sorted by that cost (hand-written radix sort, radix_sort.cuh) and later launches hand them out
+// most expensive first: the drain then consists of the cheapest pixels.  Pixels are independent, so the image does not change.
+static int prepare_tile_order(vn_handle c, const vn_params* p, RenderLaunch& L) {
+    L.tile_order = nullptr;
+    L.tile_cost = nullptr;
+    const uint32_t n_tiles = L.total_work / 32u;
+    if (!c->tile_order_opt || n_tiles < (uint32_t)c->num_sms * 32u) return VN_OK;      // small frames: every lane gets at most one tile anyway
+    vn_context::TileSig sig{};
+    sig.w = p->width; sig.h = p->height; sig.r0 = L.row_begin; sig.r1 = L.row_end; sig.spp = p->samples_per_pixel; sig.depth = p->max_depth;
+    const float cam[13] = {p->origin[0], p->origin[1], p->origin[2], p->u[0], p->u[1], p->u[2], p->v[0], p->v[1], p->v[2], p->w[0], p->w[1], p->w[2], p->lens_radius};
+    memcpy(sig.cam, cam, sizeof cam);
+    sig.epoch = c->bvh_epoch;
+    if (n_tiles > c->tile_cap) {
+        cudaFree(c->d_tile_cost); cudaFree(c->d_tile_sort);
+        c->d_tile_cost = nullptr; c->d_tile_sort = nullptr; c->tile_cap = 0; c->tile_state = 0;
+        VN_CUDA(c, cudaMalloc(&c->d_tile_cost, (size_t)n_tiles * 4));
+        VN_CUDA(c, cudaMalloc(&c->d_tile_sort, (size_t)n_tiles * 16));
+        c->tile_cap = n_tiles;
+    }
+    if (memcmp(&sig, &c->tile_sig, sizeof sig) != 0) { c->tile_sig = sig; c->tile_state = 0; }
+    if (c->tile_state == 0) {
+        VN_CUDA(c, cudaMemsetAsync(c->d_tile_cost, 0, (size_t)n_tiles * 4, c->stream));
+        L.tile_cost = c->d_tile_cost;
+        c->tile_state = 1;
+        return VN_OK;
+    }
+    if (c->tile_state == 1) {
+        uint32_t *k0 = c->d_tile_sort, *v0 = k0 + c->tile_cap, *k1 = v0 + c->tile_cap, *v1 = k1 + c->tile_cap;
+        VN_CUDA(c, exact::launch_tile_keys(c->d_tile_cost, n_tiles, k0, v0, c->stream));
+        std::string err;
+        uint32_t launches = 0;
+        const int which = radix_sort_pairs_device(k0, v0, k1, v1, n_tiles, 24, c->num_sms, c->stream, &launches, err);
+        if (which < 0) return fail(c, VN_ERR_CUDA, "vn_render: tile order sort failed: " + err);
+        c->d_tile_order = which ? v1 : v0;
+        c->tile_state = 2;
+    }
+    L.tile_order = c->d_tile_order;
+    return VN_OK;
+}
+
 int vn_render(vn_handle c, const vn_params* p) {
     VN_REQUIRE(c, c && p, "vn_render: NULL argument");
     VN_REQUIRE(c, c->bvh_valid, "vn_render: no BVH (call vn_set_spheres + vn_build_bvh; Renderer::Init does both)");
@@ -674,6 +730,7 @@ int vn_render(vn_handle c, const vn_params* p) {
         VN_CUDA(c, exact_build ? exact::launch_accumulate_samples(L, c->wf.sample_rgb, c->stream) : fast::launch_accumulate_samples(L, c->wf.sample_rgb, c->stream));
         launches += 2;
     } else {
+        { const int rc = prepare_tile_order(c, p, L); if (rc != VN_OK) return rc; }
         KernelConfig cfg;
         cfg.threads = c->threads;
         cfg.count = count;
