@@ -356,6 +356,10 @@ def run_ours(args):
         # which loop structure the wide-node path kernel ran with (library defaults unless --opt overrides them)
         _o = dict(kv.split("=", 1) for kv in args.opt if "=" in kv)
         _ad, _an = int(float(_o.get("async_done", 26))), int(float(_o.get("async_node", 0)))
+        _to = int(float(_o.get("tile_order", 1)))
+        tile_order = (None if args.kernel != "persistent" else
+                      "row-major tickets" if _to == 0 else
+                      "8x4-pixel tiles handed out most expensive first (ray segments per tile counted by the first launch of the view, i.e. during warm-up)")
         schedule = None
         if args.kernel == "persistent" and accel == 2:
             schedule = ("k_render_persistent: every round waits for its slowest ray" if _ad == 0 else
@@ -393,7 +397,7 @@ def run_ours(args):
             "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": describe(args.workload, K), "parallelism": "subframe(sample-range) sharding x%d, scene+BVH replicated" % world,
-                       "kernel": args.kernel, "schedule": schedule, "accel": {0: "n/a", 1: "BVH pair nodes", 2: "BVH 4-wide octant-sorted nodes (shared memory)", 3: "BVH 4-wide nodes (L2/HBM)", 4: "uniform grid + oversize list (shared memory)"}[accel], "build": ("VN_FAST (relaxed numerics; not within the image tolerance)" if args.fast else "default IEEE build, bit-identical to the oracle"), "l2_flush": "256 MiB fill between timed steps",
+                       "kernel": args.kernel, "schedule": schedule, "tile_order": tile_order, "accel": {0: "n/a", 1: "BVH pair nodes", 2: "BVH 4-wide octant-sorted nodes (shared memory)", 3: "BVH 4-wide nodes (L2/HBM)", 4: "uniform grid + oversize list (shared memory)"}[accel], "build": ("VN_FAST (relaxed numerics; not within the image tolerance)" if args.fast else "default IEEE build, bit-identical to the oracle"), "l2_flush": "256 MiB fill between timed steps",
                        "scene_in_smem": bool(info.scene_in_smem), "bvh_nodes": int(info.num_nodes), "leaf_size": int(info.max_leaf_size),
                        "bvh_build_ms": build_ms, "reduce": (args.reduce if world > 1 else "none"), "reduce_ms": fin_ms,
                        "sched": ({k: [v[0], round(v[1], 2)] for k, v in sched.items()} if sched else None)},

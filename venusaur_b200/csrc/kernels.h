@@ -44,7 +44,8 @@ struct RenderLaunch {
     uint32_t* work_counter;          // persistent-thread work ticket
     uint32_t total_work, tiles_x;    // work items = 8x4 pixel tiles * 32
     const uint32_t* tile_order;      // ticket >> 5 -> tile index, most expensive tiles first (null = row-major); see vn_api.cu::prepare_tile_order
-    uint32_t* tile_cost;             // when non-null the kernel adds every finished pixel's ray segments to its tile's entry
+    uint32_t* tile_cost;             // when non-null the kernel records every finished pixel's ray segments in its tile's entries:
+    uint32_t tile_cost_stride;       //   tile_cost[tile] += segments, tile_cost[tile_cost_stride + tile] = max(.., segments)
     uint32_t tiles_x_inv;            // floor(2^32 / tiles_x): tile / tiles_x = __umulhi(tile, tiles_x_inv) plus at most two corrections (tile_row_col)
 };
 
@@ -109,7 +110,7 @@ constexpr int kWfArraysTotal = 2 * kWfStateArrays + 2 + 4;   // 4-byte arrays of
     int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool count, bool octant, bool wide, bool grid);              \
     cudaError_t launch_render_persistent(const RenderLaunch& p, const KernelConfig& cfg, cudaStream_t stream);         \
     cudaError_t launch_tonemap(const float4* accum, float scale, uint32_t* image, uint64_t n, cudaStream_t stream);    \
-    cudaError_t launch_tile_keys(const uint32_t* cost, uint32_t n, uint32_t* keys, uint32_t* vals, cudaStream_t stream); \
+    cudaError_t launch_tile_keys(const uint32_t* cost, uint32_t stride, uint32_t n, uint32_t mode, uint32_t* keys, uint32_t* vals, cudaStream_t stream); \
     cudaError_t launch_reduce_tonemap_peers(const float4* const* peers, uint32_t n_peers, float scale, uint64_t begin, \
                                             uint64_t end, float4* accum_out, uint32_t* image, cudaStream_t stream);    \
     cudaError_t launch_test_rng(const uint32_t* v0, const uint32_t* v1, uint64_t n, uint32_t n_draws, uint32_t* seeds, \

@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_persistent(const __grid_
         if (!active) {
             if (has_pixel && s_left == 0u) {
                 finish_pixel(p, pix, sum);
-                if (p.tile_cost) atomicAdd(p.tile_cost + ((py - p.row_begin) >> 2) * p.tiles_x + (px >> 3), n_seg - seg0);
+                if (p.tile_cost) { uint32_t* tc = p.tile_cost + ((py - p.row_begin) >> 2) * p.tiles_x + (px >> 3); atomicAdd(tc, n_seg - seg0); atomicMax(tc + p.tile_cost_stride, n_seg - seg0); }
                 has_pixel = false;
             }
             if (!has_pixel) {
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_async(const __grid_const
             if (!active) {
                 if (has_pixel && s_left == 0u) {
                     finish_pixel(p, pix, sum);
-                    if (p.tile_cost) atomicAdd(p.tile_cost + ((py - p.row_begin) >> 2) * p.tiles_x + (px >> 3), n_seg - seg0);
+                    if (p.tile_cost) { uint32_t* tc = p.tile_cost + ((py - p.row_begin) >> 2) * p.tiles_x + (px >> 3); atomicAdd(tc, n_seg - seg0); atomicMax(tc + p.tile_cost_stride, n_seg - seg0); }
                     has_pixel = false;
                 }
                 if (!has_pixel) {
@@ -572,12 +572,16 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_async(const __grid_const
     }
 }
 
-// Sort keys of the cost-ordered tile schedule: most expensive tile first = smallest key; 24 bits are plenty (a tile's cost is the
-// number of ray segments its 32 pixels took in one launch).
-__global__ void __launch_bounds__(256) k_tile_keys(const uint32_t* __restrict__ cost, uint32_t n, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+// Sort keys of the cost-ordered tile schedule: most urgent tile first = smallest key.  A tile's urgency is its total cost (ray segments
+// of its 32 pixels in one launch, mode 1), its most expensive pixel (mode 2), or the larger of the total / 8 and the most expensive
+// pixel (mode 3: a cheap tile that holds one glass pixel must not be handed out last).  24 key bits are plenty.
+__global__ void __launch_bounds__(256) k_tile_keys(const uint32_t* __restrict__ cost, uint32_t stride, uint32_t n, uint32_t mode, uint32_t* __restrict__ keys,
+                                                   uint32_t* __restrict__ vals) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const uint32_t c = cost[i] < 0x00FFFFFFu ? cost[i] : 0x00FFFFFFu;
+    const uint32_t sum = cost[i], mx = cost[stride + i];
+    uint32_t c = mode == 2u ? mx : (mode == 3u ? max(sum >> 3, mx) : sum);
+    c = c < 0x00FFFFFFu ? c : 0x00FFFFFFu;
     keys[i] = 0x00FFFFFFu - c;
     vals[i] = i;
 }
@@ -728,9 +732,9 @@ cudaError_t launch_render_persistent(const RenderLaunch& p, const KernelConfig& 
     return cudaGetLastError();
 }
 
-cudaError_t launch_tile_keys(const uint32_t* cost, uint32_t n, uint32_t* keys, uint32_t* vals, cudaStream_t stream) {
+cudaError_t launch_tile_keys(const uint32_t* cost, uint32_t stride, uint32_t n, uint32_t mode, uint32_t* keys, uint32_t* vals, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    k_tile_keys<<<(n + 255u) / 256u, 256, 0, stream>>>(cost, n, keys, vals);
+    k_tile_keys<<<(n + 255u) / 256u, 256, 0, stream>>>(cost, stride, n, mode, keys, vals);
     return cudaGetLastError();
 }
 

@@ -78,8 +78,8 @@ struct vn_context {
     int wide_threads = 1024;          // CTA size of the wide-node path kernel (one CTA per SM): 512, 768 or 1024 (64 registers per lane at 1024)
     uint32_t leaf_vote = 0;           // see closest_hit_wide_vote (path_kernels.cu); 0 = while-while
     // cost-ordered tile schedule (prepare_tile_order): per-tile ray segments of the previous launch of the same view, sorted descending
-    uint32_t tile_order_opt = 1;      // "tile_order": 0 = row-major tickets
-    uint32_t* d_tile_cost = nullptr;  // [tile_cap]
+    uint32_t tile_order_opt = 1;      // "tile_order": 0 = row-major tickets, 1 = tiles sorted by the ray segments of their 32 pixels, 2 = by their most expensive pixel, 3 = by max(sum / 8, most expensive pixel)
+    uint32_t* d_tile_cost = nullptr;  // [2 * tile_cap]: sum | max of the pixels' ray segments
     uint32_t* d_tile_sort = nullptr;  // [4 * tile_cap]: keys, values and their alternates for the radix sort
     const uint32_t* d_tile_order = nullptr;
     uint32_t tile_cap = 0;
@@ -177,7 +177,7 @@ int fill_launch(vn_context* c, const vn_params* p, RenderLaunch& L) {
     L.counters = c->d_counters;
     L.work_counter = reinterpret_cast<uint32_t*>(c->d_counters + 4);
     const uint32_t rows = L.row_end - L.row_begin;
-    L.tile_order = nullptr; L.tile_cost = nullptr;
+    L.tile_order = nullptr; L.tile_cost = nullptr; L.tile_cost_stride = c->tile_cap;
     L.tiles_x = (p->width + 7u) / 8u;
     L.tiles_x_inv = L.tiles_x > 1u ? (uint32_t)(0x100000000ull / L.tiles_x) : 0xFFFFFFFFu;
     L.total_work = L.tiles_x * ((rows + 3u) / 4u) * 32u;
@@ -295,7 +295,7 @@ int vn_set_option(vn_handle c, const char* name, double value) {
     else if (k == "grid_max_per_cell") { VN_REQUIRE(c, value >= 1 && value <= 65535, "grid_max_per_cell must be in [1,65535]"); c->grid_max_per_cell = (uint32_t)value; c->bvh_valid = false; }
     else if (k == "huge_factor") { VN_REQUIRE(c, value >= 0, "huge_factor must be >= 0"); c->huge_factor = (float)value; c->bvh_valid = false; }
     else if (k == "wide_threads") { VN_REQUIRE(c, value == 512 || value == 768 || value == 1024, "wide_threads must be 512, 768 or 1024"); c->wide_threads = (int)value; }
-    else if (k == "tile_order") { c->tile_order_opt = value != 0 ? 1u : 0u; c->tile_state = 0; }
+    else if (k == "tile_order") { VN_REQUIRE(c, value >= 0 && value <= 3, "tile_order must be 0..3"); c->tile_order_opt = (uint32_t)value; c->tile_state = 0; }
     else if (k == "async_done") { VN_REQUIRE(c, value >= 0 && value <= 32, "async_done must be in [0,32]"); c->async_done = (uint32_t)value; }
     else if (k == "async_node") { VN_REQUIRE(c, value >= 0 && value <= 32, "async_node must be in [0,32] (0 = phase form: no votes inside the node / leaf phases)"); c->async_node = (uint32_t)value; }
     else if (k == "async_leaf") { VN_REQUIRE(c, value >= 1 && value <= 32, "async_leaf must be in [1,32]"); c->async_leaf = (uint32_t)value; }
@@ -628,20 +628,21 @@ static int prepare_tile_order(vn_handle c, const vn_params* p, RenderLaunch& L) 
     if (n_tiles > c->tile_cap) {
         cudaFree(c->d_tile_cost); cudaFree(c->d_tile_sort);
         c->d_tile_cost = nullptr; c->d_tile_sort = nullptr; c->tile_cap = 0; c->tile_state = 0;
-        VN_CUDA(c, cudaMalloc(&c->d_tile_cost, (size_t)n_tiles * 4));
+        VN_CUDA(c, cudaMalloc(&c->d_tile_cost, (size_t)n_tiles * 8));
         VN_CUDA(c, cudaMalloc(&c->d_tile_sort, (size_t)n_tiles * 16));
         c->tile_cap = n_tiles;
     }
     if (memcmp(&sig, &c->tile_sig, sizeof sig) != 0) { c->tile_sig = sig; c->tile_state = 0; }
     if (c->tile_state == 0) {
-        VN_CUDA(c, cudaMemsetAsync(c->d_tile_cost, 0, (size_t)n_tiles * 4, c->stream));
+        VN_CUDA(c, cudaMemsetAsync(c->d_tile_cost, 0, (size_t)c->tile_cap * 8, c->stream));
         L.tile_cost = c->d_tile_cost;
+        L.tile_cost_stride = c->tile_cap;
         c->tile_state = 1;
         return VN_OK;
     }
     if (c->tile_state == 1) {
         uint32_t *k0 = c->d_tile_sort, *v0 = k0 + c->tile_cap, *k1 = v0 + c->tile_cap, *v1 = k1 + c->tile_cap;
-        VN_CUDA(c, exact::launch_tile_keys(c->d_tile_cost, n_tiles, k0, v0, c->stream));
+        VN_CUDA(c, exact::launch_tile_keys(c->d_tile_cost, c->tile_cap, n_tiles, c->tile_order_opt, k0, v0, c->stream));
         std::string err;
         uint32_t launches = 0;
         const int which = radix_sort_pairs_device(k0, v0, k1, v1, n_tiles, 24, c->num_sms, c->stream, &launches, err);
