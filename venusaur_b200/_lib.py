@@ -116,6 +116,8 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    # rebuild only when the sources' CONTENT differs from what the library was built from (build.py keeps a hash next to the .so);
+    # build() itself is serialised by a file lock, so one process per GPU may all land here at once
     if not os.path.exists(_build.LIB) or (os.path.isdir(_build.CSRC) and not _build.up_to_date() and _build.shutil.which("nvcc")):
         _build.build()
     lib = C.CDLL(_build.LIB)

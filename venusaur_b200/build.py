@@ -47,19 +47,37 @@ def nvcc() -> str:
 
 
 def _sources() -> list[str]:
-    out = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    out = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
     inc = os.path.join(HERE, "..", "include")
-    for root, _, files in os.walk(inc):
-        out += [os.path.join(root, f) for f in files]
+    for root, _, files in sorted(os.walk(inc)):
+        out += [os.path.join(root, f) for f in sorted(files)]
     out.append(os.path.abspath(__file__))
     return out
 
 
+STAMP = LIB + ".srchash"
+
+
+def source_hash() -> str:
+    """Content hash of everything the library is built from.  File times do not survive a copy of the tree (a snapshot sent to
+    another machine arrives with fresh mtimes in arbitrary order), contents do."""
+    import hashlib
+    h = hashlib.sha256()
+    for path in _sources():
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def up_to_date() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return False
-    t = os.path.getmtime(LIB)
-    return all(os.path.getmtime(s) <= t for s in _sources())
+    try:
+        with open(STAMP) as f:
+            return f.read().strip() == source_hash()
+    except OSError:
+        return False
 
 
 def _run(cmd: list[str]) -> None:
@@ -69,20 +87,39 @@ def _run(cmd: list[str]) -> None:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Builds the library unless it is up to date.  Safe against concurrent callers (one process per GPU all importing the package
+    at once): an exclusive file lock serialises them, the objects and the library are written under process-private names and
+    renamed into place, and whoever gets the lock second finds the work done."""
     if not force and up_to_date():
         return LIB
+    import fcntl
     os.makedirs(OBJ, exist_ok=True)
-    cc = nvcc()
-    jobs = []
-    for src, obj, extra in UNITS:
-        cmd = [cc, *ARCH, *COMMON, *extra, "-c", os.path.join(CSRC, src), "-o", os.path.join(OBJ, obj)]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
-        jobs.append(cmd)
-    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
-        list(ex.map(_run, jobs))
-    objs = [os.path.join(OBJ, obj) for _, obj, _ in UNITS]
-    _run([cc, *ARCH, "-shared", "-o", LIB, *objs])
+    with open(os.path.join(OBJ, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and up_to_date():
+                return LIB
+            cc = nvcc()
+            tag = ".%d.tmp" % os.getpid()
+            jobs = []
+            for src, obj, extra in UNITS:
+                cmd = [cc, *ARCH, *COMMON, *extra, "-c", os.path.join(CSRC, src), "-o", os.path.join(OBJ, obj + tag + ".o")]
+                if verbose:
+                    cmd.insert(1, "-Xptxas=-v")
+                jobs.append(cmd)
+            with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+                list(ex.map(_run, jobs))
+            objs = []
+            for _, obj, _ in UNITS:
+                os.replace(os.path.join(OBJ, obj + tag + ".o"), os.path.join(OBJ, obj))
+                objs.append(os.path.join(OBJ, obj))
+            _run([cc, *ARCH, "-shared", "-o", LIB + tag, *objs])
+            os.replace(LIB + tag, LIB)
+            with open(STAMP + tag, "w") as f:
+                f.write(source_hash())
+            os.replace(STAMP + tag, STAMP)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 
