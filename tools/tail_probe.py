@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """How much of a launch is drain?  Runs the instrumented path kernel (VN_COUNTERS) on the headline workload and reads the launch
-timeline it leaves in the scheduler-statistics words: start, first lane that found the ticket counter exhausted, mean and max
-warp end.  GPU only."""
+timeline it leaves in the scheduler-statistics words: start, first lane that found the ticket counter exhausted, last warp's end.
+The first launch of a view runs with row-major tickets (and counts the tiles' costs), the following ones with the cost-ordered
+tiles (vn_api.cu::prepare_tile_order).  GPU only."""
 import ctypes as C, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -19,11 +20,10 @@ def main():
             raw = (C.c_uint64 * 14)()
             ctx._check(ctx.lib.vn_read_sched_counters(ctx.h, raw), "vn_read_sched_counters")
             M = (1 << 64) - 1
-            start, exhaust, end, sum_end, nw = M - raw[0], M - raw[1], raw[2], raw[3], raw[4]
-            mean_end = sum_end / max(nw, 1)
-            print("%dx%d rep %d: ms_render %.3f | kernel %.3f ms, tickets exhausted at %.3f ms (%.1f %%), mean warp end %.3f ms, drain %.3f ms; lane-time lost in the drain ~ %.1f %% of the launch"
+            start, exhaust, end = M - raw[0], M - raw[1], raw[2]
+            print("%dx%d launch %d: ms_render %.3f | kernel %.3f ms, tickets exhausted at %.3f ms (%.1f %%), drain %.3f ms"
                   % (W, H, rep, st.ms_render, (end - start) / 1e6, (exhaust - start) / 1e6, 100.0 * (exhaust - start) / (end - start),
-                     (mean_end - start) / 1e6, (end - exhaust) / 1e6, 100.0 * (end - mean_end) / (end - start)))
+                     (end - exhaust) / 1e6))
     ctx.close()
 
 if __name__ == "__main__":
