@@ -210,6 +210,45 @@ def test_near_zero_float_threshold_equals_double_compare():
     assert np.array_equal(xs.astype(np.float64) < 1e-8, xs <= c)
 
 
+def test_library_staleness_is_decided_by_content_not_by_file_times(tmp_path):
+    """venusaur_b200/build.py: a copy of the tree arrives with fresh file times (that made eight ranks rebuild into the same objects at
+    once); whether the library is current is decided by a hash of the sources kept next to it."""
+    import venusaur_b200.build as b
+    assert os.path.exists(b.LIB) and os.path.exists(b.STAMP), "build the library first (python -m venusaur_b200.build)"
+    assert b.up_to_date()
+    src = os.path.join(b.CSRC, "vn_math.cuh")
+    st = os.stat(src)
+    try:
+        os.utime(src, None)                                   # newer than the library: still current
+        assert b.up_to_date()
+        with open(b.STAMP) as f:
+            good = f.read()
+        with open(b.STAMP, "w") as f:
+            f.write("0" * 64)                                 # a different content hash: stale
+        assert not b.up_to_date()
+        with open(b.STAMP, "w") as f:
+            f.write(good)
+        assert b.up_to_date()
+    finally:
+        os.utime(src, (st.st_atime, st.st_mtime))
+
+
+def test_tile_index_by_multiply_high():
+    """kernels.h::tile_row_col: tile / tiles_x through floor(2^32 / tiles_x) and at most two corrections, for any 32-bit tile index."""
+    rng = np.random.default_rng(7)
+    for d in (1, 2, 3, 5, 7, 50, 240, 480, 2048, 65535, 100000):
+        inv = (2 ** 32 // d) if d > 1 else 0xFFFFFFFF
+        t = np.concatenate([rng.integers(0, 2 ** 32, 200000, dtype=np.uint64), np.arange(0, 5000, dtype=np.uint64),
+                            np.uint64(2 ** 32 - 1) - np.arange(0, 5000, dtype=np.uint64)])
+        q = (t * np.uint64(inv)) >> np.uint64(32)
+        r = t - q * np.uint64(d)
+        for _ in range(2):
+            m = r >= d
+            q = q + m
+            r = r - m * np.uint64(d)
+        assert (q == t // d).all() and (r == t % d).all(), d
+
+
 def test_rnd_pm1_short_form_equals_literal_form(host_harness):
     """vn_math.cuh::rnd_pm1 forms random_float(seed, -1, 1) (RayTracer.cu:93-97) as float(int32((state << 8) ^ 2^31)) * 2^-31; it must
     give the bits of -1 + 2 * (float(state & 0xFFFFFF) / 2^24) for every 24-bit output (and leave the same LCG state)."""

@@ -6,6 +6,14 @@
 //
 //   g++ -O2 -std=c++17 -ffp-contract=off -w -Ivenusaur_b200/csrc -o /tmp/simt/sim_async tools/simt_sim_async.cpp
 //   /tmp/simt/sim_async /tmp/simt/rtiow.bin /tmp/simt/cam_1920.bin 1920 1080 16 <n_warps> <policy> [Tn Tl Td]
+// (scene = the hh_sphere array of the RTIOW scene, camera = 13 floats origin|u|v|w|lens: dump them with tests/oracle_lib.py.)
+// Policies: 0 = the persistent kernel's rounds; 1 = one voted operation per quantum; 2 = node bursts (Tn) + leaf votes (Tl) + early
+// shading (Td); Tn 1, Tl 33 = the phase form of k_render_async; 3 / 4 = greedy fine-grained operations with one ray per lane.
+// Environment: PHASES=1 per-phase node / leaf statistics; HIST=1 node steps per ray; TNSTACK=1 stack entries carry their entry
+// distance and are culled at the pop; C_NODE / C_SCHED / THR override costs and thresholds; FULL=1 the whole frame with n_warps
+// resident warps (4736 = 148 SMs x 32) instead of a strided sample; DUMP_COST=file per-tile ray segments (sum | max | dielectric
+// hits); TILE_ORDER=file a uint32 tile order for the tickets (how the cost-ordered schedule of vn_api.cu::prepare_tile_order was
+// checked before it was built: row-major 54.1 -> cost-sorted 49.2 model warp-instructions per segment; measured 5.72 -> 5.24 G).
 #include "../tests/host_harness.cpp"
 
 #include <cstdio>
@@ -35,6 +43,7 @@ struct Lane {
     f3 idir, ood;
     const node_f4* wn = nullptr;
     int nsteps = 0; bool primary = false;
+    uint32_t cur_tile = 0, seg_pixel = 0, diel_pixel = 0; bool cur_tile_valid = false;
     float tstack[kStackSize];
 };
 
@@ -49,11 +58,21 @@ struct Sim {
     uint64_t ph_node[8] = {0}, ph_lanes[8] = {0}, ph_leaf[8] = {0}, ph_leaf_lanes[8] = {0}, rounds = 0;
     uint64_t segs = 0, n_node_ops = 0, n_leaf_ops = 0, n_shade_ops = 0, lanes_node = 0, lanes_leaf = 0, lanes_shade = 0;
 
+    std::vector<uint32_t> tile_order, tile_cost, tile_max, tile_diel;
+    void close_pixel(Lane& L) {
+        if (!L.cur_tile_valid) return;
+        if (tile_cost.size()) { tile_cost[L.cur_tile] += L.seg_pixel; tile_max[L.cur_tile] = std::max(tile_max[L.cur_tile], L.seg_pixel); tile_diel[L.cur_tile] += L.diel_pixel; }
+        L.cur_tile_valid = false;
+    }
     bool fetch(Lane& L) {
+        close_pixel(L);
         for (;;) {
             if (next_ticket >= max_tickets) return false;
             const uint32_t w = next_ticket++;
-            const uint32_t tile = (uint32_t)(((uint64_t)(w >> 5) * tile_stride) % n_tiles), in = w & 31u;
+            uint32_t tile = (uint32_t)(((uint64_t)(w >> 5) * tile_stride) % n_tiles);
+            const uint32_t in = w & 31u;
+            if (tile_order.size()) tile = tile_order[w >> 5];
+            L.cur_tile = tile; L.cur_tile_valid = true; L.seg_pixel = 0; L.diel_pixel = 0;
             const uint32_t ty = tile / tiles_x, tx = tile - ty * tiles_x;
             L.px = tx * 8u + (in & 7u);
             L.py = ty * 4u + (in >> 3);
@@ -97,7 +116,8 @@ struct Sim {
             if (L.ph != DONE && L.ph != NEED) continue;
             any = true; n++;
             if (L.ph == DONE) {
-                segs++;
+                segs++; L.seg_pixel++;
+                if (L.prim >= 0 && B.type[L.prim] == 2u) L.diel_pixel++;
                 f3 result;
                 const uint32_t seed0 = L.st.seed;
                 const int prim = L.prim;
@@ -321,6 +341,9 @@ int main(int argc, char** argv) {
     S.tiles_x = (S.W + 7) / 8; S.tiles_y = (S.H + 3) / 4; S.n_tiles = S.tiles_x * S.tiles_y;
     S.tile_stride = 7919;                                   // prime: the simulated tickets sample the whole frame
     S.max_tickets = (uint32_t)n_warps * 32u * (uint32_t)per_warp;
+    if (getenv("FULL")) { S.tile_stride = 1; S.max_tickets = S.n_tiles * 32u; }           // the whole frame, row-major unless TILE_ORDER
+    if (getenv("TILE_ORDER")) { FILE* f = fopen(getenv("TILE_ORDER"), "rb"); S.tile_order.resize(S.n_tiles); fread(S.tile_order.data(), 4, S.n_tiles, f); fclose(f); }
+    if (getenv("DUMP_COST")) { S.tile_cost.assign(S.n_tiles, 0); S.tile_max.assign(S.n_tiles, 0); S.tile_diel.assign(S.n_tiles, 0); }
     std::vector<Lane> lanes((size_t)n_warps * 32);
     bool any = true;
     while (any) {
@@ -331,6 +354,7 @@ int main(int argc, char** argv) {
            policy, Tn, Tl, Td, S.B.huge.n, S.B.wide_oct.size() / 56, (unsigned long long)S.segs, S.cost / S.segs, S.c_node / S.segs, S.c_leaf / S.segs,
            S.c_shade / S.segs, S.c_sched / S.segs, (double)S.n_node_ops / S.segs, (double)S.n_leaf_ops / S.segs, (double)S.n_shade_ops / S.segs,
            (double)S.lanes_node / S.n_node_ops, (double)S.lanes_leaf / S.n_leaf_ops, (double)S.lanes_shade / S.n_shade_ops);
+    if (getenv("DUMP_COST")) { for (auto& L : lanes) S.close_pixel(L); FILE* f = fopen(getenv("DUMP_COST"), "wb"); fwrite(S.tile_cost.data(), 4, S.n_tiles, f); fwrite(S.tile_max.data(), 4, S.n_tiles, f); fwrite(S.tile_diel.data(), 4, S.n_tiles, f); fclose(f); }
     if (getenv("PHASES")) for (int k = 0; k < 8; k++) printf("phase %d: node ops/round %.2f (lanes %.1f)  leaf ops/round %.2f (lanes %.1f)\n", k, (double)S.ph_node[k] / S.rounds, S.ph_node[k] ? (double)S.ph_lanes[k] / S.ph_node[k] : 0.0, (double)S.ph_leaf[k] / S.rounds, S.ph_leaf[k] ? (double)S.ph_leaf_lanes[k] / S.ph_leaf[k] : 0.0);
     if (getenv("HIST")) for (int k = 0; k < 2; k++) { uint64_t tot = 0, sum = 0; for (int i = 0; i < 64; i++) { tot += S.hist[k][i]; sum += i * S.hist[k][i]; } printf("%s rays %llu mean steps %.2f:", k ? "secondary" : "primary", (unsigned long long)tot, (double)sum / tot); double cum = 0; for (int i = 0; i < 40; i++) { cum += S.hist[k][i]; printf(" %d:%.3f", i, cum / tot); } printf("\n"); }
     if (policy >= 3) {
