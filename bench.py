@@ -363,7 +363,8 @@ def run_ours(args):
         schedule = None
         if args.kernel == "persistent" and accel == 2:
             schedule = ("k_render_persistent: every round waits for its slowest ray" if _ad == 0 else
-                        "k_render_async, %s: a traversal burst ends when %d lanes hold a finished ray" % ("phase form" if _an == 0 else "voted turns", _ad))
+                        "k_render_async, %s: a traversal burst ends when %d lanes hold a finished ray%s" % ("phase form" if _an == 0 else "voted turns", _ad,
+                        "; warps own whole 8x4 tiles" if (_an == 0 and int(float(_o.get("warp_tiles", 1)))) else ""))
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

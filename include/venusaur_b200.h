@@ -135,7 +135,8 @@ VN_API int vn_set_spheres(vn_handle h, const vn_sphere* host_spheres, uint64_t n
  * "wide_max_prims" [16384: 4-wide nodes up to this size], "accel" [1 = BVH; 0 = auto: the uniform grid when the scene suits it, 2 = grid], "huge_factor" [50], "grid_max_per_cell" [16].  Path kernel: "wide_nodes" [1], "octant_nodes" [1], "leaf_vote" [0 = while-while; n: lanes waiting
  * at a leaf that trigger the warp's leaf turn], "wide_threads" [1024], "async_done" [26: k_render_async, a traversal burst ends when that many lanes of the
  * warp hold a finished ray; 0 = k_render_persistent, every round waits for its slowest ray], "async_node" [0 = no votes inside a phase; n: node steps while n
- * lanes stand on nodes], "async_leaf" [8], "tile_order" [1: once a view has been
+ * lanes stand on nodes], "async_leaf" [8], "warp_tiles" [1: in the phase form a warp takes a whole 8x4-pixel tile with one ticket and hands the pixels to its own
+ * lanes; 0 = every lane takes single pixels from the global ticket], "tile_order" [1: once a view has been
  * rendered once, its 8x4-pixel tiles are handed out most expensive first (ray segments per tile, counted by that first launch); 0 = row-major, 2 = by the most
  * expensive pixel, 3 = max(sum / 8, most expensive pixel)], "wide_global" [0], "threads", "blocks_per_sm", "smem_scene_limit".
  * Experimental kernels: "slot_kernel" [0], "slot_slots", "slot_threads", "slot_tn|tl|tw|ts|tr"; "pool_slots", "pool_threads", "pool_service",

@@ -422,7 +422,7 @@ def test_cost_ordered_tiles_do_not_change_the_image(ctx, rtiow):
     ctx.build_bvh()
     W, H, spp, depth = 640, 360, 4, 50                          # 7200 tiles >= 32 per SM: the schedule is active
     try:
-        for kernel_opts in ({"async_done": 26, "async_node": 0}, {"async_done": 0}):
+        for kernel_opts in ({"async_done": 26, "async_node": 0, "warp_tiles": 0}, {"async_done": 26, "async_node": 0, "warp_tiles": 1}, {"async_done": 0, "warp_tiles": 0}):
             for k, v in kernel_opts.items():
                 ctx.set_option(k, v)
             cam = vb.rtiow_camera(W, H)
@@ -450,6 +450,7 @@ def test_cost_ordered_tiles_do_not_change_the_image(ctx, rtiow):
         ctx.set_option("tile_order", 1)
         ctx.set_option("async_done", 26)
         ctx.set_option("async_node", 0)
+        ctx.set_option("warp_tiles", 1)
 
 
 @pytest.mark.parametrize("threads", [512, 768, 1024])
@@ -481,7 +482,18 @@ def test_async_kernel_equals_persistent_kernel(ctx, oracle_mod, rtiow, threads):
                 h, ih, sh = render(ctx, cam, W, H, spp, sub, depth, flags=VN_COUNTERS)
                 assert np.array_equal(h.view(np.uint32), e.view(np.uint32))
                 assert (sh.segments, sh.node_visits, sh.sphere_tests) == (sf.segments, sf.node_visits, sf.sphere_tests)
+                if node == 0:
+                    # warp-owned tiles: one ticket per 8x4 tile, the warp hands the pixels to its own lanes
+                    ctx.set_option("warp_tiles", 1)
+                    w, iw, sw = render(ctx, cam, W, H, spp, sub, depth)
+                    w2, _, sw2 = render(ctx, cam, W, H, spp, sub, depth, flags=VN_COUNTERS)
+                    ctx.set_option("warp_tiles", 0)
+                    assert np.array_equal(w.view(np.uint32), e.view(np.uint32)) and np.array_equal(iw, ie), (W, H, done, "warp_tiles")
+                    assert np.array_equal(w2.view(np.uint32), e.view(np.uint32))
+                    assert (sw.segments, sw.paths) == (se.segments, se.paths)
+                    assert (sw2.segments, sw2.node_visits, sw2.sphere_tests) == (sf.segments, sf.node_visits, sf.sphere_tests)
     finally:
+        ctx.set_option("warp_tiles", 1)
         ctx.set_option("async_done", 26)
         ctx.set_option("async_node", 0)
         ctx.set_option("async_leaf", 8)

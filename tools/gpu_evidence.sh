@@ -19,6 +19,7 @@ $B --steps 16 --opt accel=0 2>&1 | tail -1 > gpurun_out/${P}_bench_grid.json
 $B --steps 16 --opt huge_factor=0 2>&1 | tail -1 > gpurun_out/${P}_bench_nohuge.json
 $B --steps 16 --opt async_done=0 2>&1 | tail -1 > gpurun_out/${P}_bench_persistent.json
 $B --steps 16 --opt tile_order=0 2>&1 | tail -1 > gpurun_out/${P}_bench_rowmajor.json
+$B --steps 16 --opt warp_tiles=0 2>&1 | tail -1 > gpurun_out/${P}_bench_lane_tickets.json
 $B --steps 16 --opt async_done=24 --opt async_node=8 2>&1 | tail -1 > gpurun_out/${P}_bench_async_voted.json
 $B --steps 16 --opt wide_threads=768 2>&1 | tail -1 > gpurun_out/${P}_bench_768.json
 $B --steps 16 --opt wide_nodes=0 --opt sah_max_prims=0 --leaf-size 2 2>&1 | tail -1 > gpurun_out/${P}_bench_karras_pairs.json
@@ -26,7 +27,7 @@ $B --steps 16 --workload c1 2>&1 | tail -1 > gpurun_out/${P}_bench_c1.json
 $B --steps 8 --workload c3 2>&1 | tail -1 > gpurun_out/${P}_bench_c3_n1.json
 $B --steps 4 --workload c4 2>&1 | tail -1 > gpurun_out/${P}_bench_c4.json
 $B --steps 4 --workload c5 2>&1 | tail -1 > gpurun_out/${P}_bench_c5.json
-for f in grid nohuge persistent rowmajor async_voted 768 karras_pairs c1 c3_n1 c4 c5; do python -c "
+for f in grid nohuge persistent rowmajor lane_tickets async_voted 768 karras_pairs c1 c3_n1 c4 c5; do python -c "
 import json,sys
 try:
     d=json.loads(open('gpurun_out/${P}_bench_$f.json').read().strip().splitlines()[-1]); print('$f: %.0f Mrays/s e2e %.0f ms/step %.3f' % (d['value'], d['e2e']['value'], d['ms_per_step']))

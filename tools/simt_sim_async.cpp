@@ -64,7 +64,31 @@ struct Sim {
         if (tile_cost.size()) { tile_cost[L.cur_tile] += L.seg_pixel; tile_max[L.cur_tile] = std::max(tile_max[L.cur_tile], L.seg_pixel); tile_diel[L.cur_tile] += L.diel_pixel; }
         L.cur_tile_valid = false;
     }
+    // WARPTILE=1: a warp takes whole tiles (one global ticket per tile) and its lanes take the tile's pixels in order, so the lanes
+    // of a warp always hold pixels of the same one or two tiles
+    int warptile = 0;
+    std::vector<uint32_t> w_tile, w_cursor;
+    uint32_t next_tile = 0;
+    bool fetch_warptile(Lane& L, int w) {
+        close_pixel(L);
+        for (;;) {
+            if (w_cursor[w] >= 32u) {
+                if (next_tile >= n_tiles) return false;
+                const uint32_t t = next_tile++;
+                w_tile[w] = tile_order.size() ? tile_order[t] : t;
+                w_cursor[w] = 0;
+            }
+            const uint32_t tile = w_tile[w], in = w_cursor[w]++;
+            L.cur_tile = tile; L.cur_tile_valid = true; L.seg_pixel = 0; L.diel_pixel = 0;
+            const uint32_t ty = tile / tiles_x, tx = tile - ty * tiles_x;
+            L.px = tx * 8u + (in & 7u);
+            L.py = ty * 4u + (in >> 3);
+            if (L.px < W && L.py < H) return true;
+        }
+    }
+    int cur_warp = 0;
     bool fetch(Lane& L) {
+        if (warptile) return fetch_warptile(L, cur_warp);
         close_pixel(L);
         for (;;) {
             if (next_ticket >= max_tickets) return false;
@@ -341,6 +365,7 @@ int main(int argc, char** argv) {
     S.tiles_x = (S.W + 7) / 8; S.tiles_y = (S.H + 3) / 4; S.n_tiles = S.tiles_x * S.tiles_y;
     S.tile_stride = 7919;                                   // prime: the simulated tickets sample the whole frame
     S.max_tickets = (uint32_t)n_warps * 32u * (uint32_t)per_warp;
+    if (getenv("WARPTILE")) { S.warptile = 1; S.w_tile.assign(n_warps, 0); S.w_cursor.assign(n_warps, 32u); }
     if (getenv("FULL")) { S.tile_stride = 1; S.max_tickets = S.n_tiles * 32u; }           // the whole frame, row-major unless TILE_ORDER
     if (getenv("TILE_ORDER")) { FILE* f = fopen(getenv("TILE_ORDER"), "rb"); S.tile_order.resize(S.n_tiles); fread(S.tile_order.data(), 4, S.n_tiles, f); fclose(f); }
     if (getenv("DUMP_COST")) { S.tile_cost.assign(S.n_tiles, 0); S.tile_max.assign(S.n_tiles, 0); S.tile_diel.assign(S.n_tiles, 0); }
@@ -348,7 +373,7 @@ int main(int argc, char** argv) {
     bool any = true;
     while (any) {
         any = false;
-        for (int w = 0; w < n_warps; w++) any |= S.step_warp(&lanes[(size_t)w * 32], policy, Tn, Tl, Td);
+        for (int w = 0; w < n_warps; w++) { S.cur_warp = w; any |= S.step_warp(&lanes[(size_t)w * 32], policy, Tn, Tl, Td); }
     }
     printf("policy %d Tn %d Tl %d Td %d: huge %u wide nodes %zu | segments %llu  warp-inst/seg %.2f  (node %.2f leaf %.2f shade %.2f sched %.2f) | ops/seg node %.3f leaf %.3f shade %.3f | lanes node %.1f leaf %.1f shade %.1f\n",
            policy, Tn, Tl, Td, S.B.huge.n, S.B.wide_oct.size() / 56, (unsigned long long)S.segs, S.cost / S.segs, S.c_node / S.segs, S.c_leaf / S.segs,

@@ -69,6 +69,7 @@ struct KernelConfig {
     bool wide;                       // 4-wide octant-sorted nodes in shared memory (implies scene_in_smem; excludes octant)
     bool grid;                       // uniform grid + oversize list in shared memory (excludes the others)
     bool async = false;              // k_render_async (wide nodes in shared memory only): asynchronous shading, see path_kernels.cu
+    bool warp_tiles = false;         // phase form only: warps own whole 8x4 tiles (one ticket per tile) instead of lanes taking single pixels
 };
 
 // Vote thresholds of the slot-scheduled kernel (slot_kernels.cu): an operation runs when that many lanes wait for it.

@@ -373,7 +373,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
     return t;
 }
 
-template <bool kCount, int kMaxThreads, bool kPhase = false>
+template <bool kCount, int kMaxThreads, bool kPhase = false, bool kWarpTile = false>
 __global__ void __launch_bounds__(kMaxThreads) k_render_async(const __grid_constant__ RenderLaunch p) {
     extern __shared__ float4 s_scene[];
     SceneView sc;
@@ -421,6 +421,7 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_async(const __grid_const
     ss.sdir = ss.nsood = mk3(0.0f);
     WideBase wb = wide_base(sc.nodes, 0u, node_f4s);
     const uint32_t t_node = p.async_node, t_leaf = p.async_leaf;
+    uint32_t w_tile = 0u, w_cursor = 32u;          // kWarpTile: the warp's current tile and the next pixel of it to hand out (warp-uniform)
 
     for (;;) {
         if (cur == kEmptyScene && !retired) {
@@ -438,7 +439,7 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_async(const __grid_const
                     if (p.tile_cost) { uint32_t* tc = p.tile_cost + ((py - p.row_begin) >> 2) * p.tiles_x + (px >> 3); atomicAdd(tc, n_seg - seg0); atomicMax(tc + p.tile_cost_stride, n_seg - seg0); }
                     has_pixel = false;
                 }
-                if (!has_pixel) {
+                if (!kWarpTile && !has_pixel) {
                     bool got = false;
                     for (;;) {
                         const uint32_t w = fetch_work(p.work_counter);
@@ -461,7 +462,7 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_async(const __grid_const
                         has_pixel = true;
                     } else { retired = true; if (kCount) atomicMax(&p.counters[9], ~global_ns()); }   // no pixels left: this lane only votes from now on
                 }
-                if (!retired) {
+                if (!kWarpTile && !retired) {
                     camera_ray(p.cam, px, py, cam_seed, st.o, st.d);   // RayTracer.cu:173-177
                     st.thr = mk3(1.0f);
                     st.seed = cam_seed;                           // prd.seed = seed: a copy (RayTracer.cu:183)
@@ -471,8 +472,76 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_async(const __grid_const
                     n_path += 1u;
                 }
             }
-            if (!retired) {
+            if (!kWarpTile && !retired) {
                 // start the next segment: the huge spheres first (lbvh_core.cuh::HugeList), then the traversal constants
+                tbest = kTMax;
+                prim = -1;
+                if (p.huge.n) {
+                    const float a = dot(st.d, st.d), inv_a = rcp(a);
+                    for (uint32_t i = 0; i < p.huge.n; i++) {
+                        const uint32_t hs = p.huge.idx[i];
+                        const float4 g = sc.geom[hs];
+                        if (kCount) cnt.spheres += 1;
+                        const float th = sphere_root(st.o, st.d, a, inv_a, g.x, g.y, g.z, g.w, kTMin, tbest);
+                        if (th >= 0.0f) { tbest = th; prim = (int)hs; }
+                    }
+                }
+                const f3 idir = slab_idir(st.d);
+                wb = wide_base(sc.nodes, ray_octant(st.d), node_f4s);
+                ss = slab_scale(idir, mk3(st.o.x * idir.x, st.o.y * idir.y, st.o.z * idir.z), tbest);
+                top = base;
+                cur = p.wide_root;
+            }
+        }
+        if (kWarpTile) {
+            // Warp-owned tiles: the warp takes a whole 8x4 tile with ONE global ticket and hands its 32 pixels to its own lanes, in
+            // order, as they become free -- the lanes of a warp then always hold pixels of the same one or two tiles (coherent
+            // primary rays, similar materials) instead of whatever tickets happened to be next when each lane asked
+            // (tools/simt_sim_async.cpp, WARPTILE=1: 49.2 -> 46.1 model warp-instructions per segment on top of the cost order).
+            const bool wants_ray = cur == kEmptyScene && !retired;      // shaded above (or fresh): needs its next segment
+            bool need = wants_ray && !active && !has_pixel;
+            unsigned m = __ballot_sync(kFull, need);
+            while (m) {
+                if (w_cursor >= 32u) {                                  // warp-uniform: the current tile is handed out
+                    uint32_t t = 0u;
+                    if ((threadIdx.x & 31u) == 0u) t = atomicAdd(p.work_counter, 1u);
+                    t = __shfl_sync(kFull, t, 0);
+                    if (t >= (p.total_work >> 5)) {                     // no tiles left: the asking lanes only vote from now on
+                        if (need) { retired = true; if (kCount) atomicMax(&p.counters[9], ~global_ns()); }
+                        break;
+                    }
+                    w_tile = p.tile_order ? __ldg(p.tile_order + t) : t;
+                    w_cursor = 0u;
+                }
+                const uint32_t in = w_cursor + (uint32_t)__popc(m & ((1u << (threadIdx.x & 31u)) - 1u));
+                if (need && in < 32u) {
+                    uint32_t ty, tx;
+                    tile_row_col(w_tile, p.tiles_x, p.tiles_x_inv, ty, tx);
+                    px = tx * 8u + (in & 7u);
+                    py = p.row_begin + ty * 4u + (in >> 3);
+                    if (px < p.width && py < p.row_end) {
+                        need = false;
+                        pix = py * p.width + px;
+                        cam_seed = tea4(pix, p.subframe_index);   // RayTracer.cu:169
+                        seg0 = n_seg;
+                        sum = mk3(0.0f);
+                        s_left = p.spp;
+                        has_pixel = true;
+                    }
+                }
+                w_cursor = min(32u, w_cursor + (uint32_t)__popc(m));
+                m = __ballot_sync(kFull, need);
+            }
+            if (wants_ray && !retired) {
+                if (!active) {
+                    camera_ray(p.cam, px, py, cam_seed, st.o, st.d);   // RayTracer.cu:173-177
+                    st.thr = mk3(1.0f);
+                    st.seed = cam_seed;                           // prd.seed = seed: a copy (RayTracer.cu:183)
+                    st.depth = (int)p.max_depth - 1;              // RayTracer.cu:184
+                    s_left -= 1u;
+                    active = true;
+                    n_path += 1u;
+                }
                 tbest = kTMax;
                 prim = -1;
                 if (p.huge.n) {
@@ -691,8 +760,12 @@ inline uint32_t grid_for(uint64_t n, int threads) { return (uint32_t)((n + threa
 
 namespace {
 typedef void (*PathKernel)(const RenderLaunch);
-PathKernel pick_kernel(bool scene_in_smem, bool count, bool octant, bool wide = false, int threads = 1024, bool grid = false, bool async = false, bool phase = false) {
+PathKernel pick_kernel(bool scene_in_smem, bool count, bool octant, bool wide = false, int threads = 1024, bool grid = false, bool async = false, bool phase = false, bool warp_tiles = false) {
     if (async && wide && scene_in_smem && !grid) {
+        if (phase && warp_tiles) {
+            if (threads <= 768) return count ? k_render_async<true, 768, true, true> : k_render_async<false, 768, true, true>;
+            return count ? k_render_async<true, 1024, true, true> : k_render_async<false, 1024, true, true>;
+        }
         if (phase) {
             if (threads <= 768) return count ? k_render_async<true, 768, true> : k_render_async<false, 768, true>;
             return count ? k_render_async<true, 1024, true> : k_render_async<false, 1024, true>;
@@ -723,7 +796,7 @@ int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool c
 }
 
 cudaError_t launch_render_persistent(const RenderLaunch& p, const KernelConfig& cfg, cudaStream_t stream) {
-    PathKernel k = pick_kernel(cfg.scene_in_smem, cfg.count, cfg.octant, cfg.wide, cfg.threads, cfg.grid, cfg.async, cfg.async && p.async_node == 0u);
+    PathKernel k = pick_kernel(cfg.scene_in_smem, cfg.count, cfg.octant, cfg.wide, cfg.threads, cfg.grid, cfg.async, cfg.async && p.async_node == 0u, cfg.warp_tiles);
     if (cfg.smem_bytes > 48 * 1024) {
         const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes);
         if (e != cudaSuccess) return e;
