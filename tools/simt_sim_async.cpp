@@ -81,11 +81,12 @@ struct Sim {
             const uint32_t tile = w_tile[w], in = w_cursor[w]++;
             L.cur_tile = tile; L.cur_tile_valid = true; L.seg_pixel = 0; L.diel_pixel = 0;
             const uint32_t ty = tile / tiles_x, tx = tile - ty * tiles_x;
-            L.px = tx * 8u + (in & 7u);
-            L.py = ty * 4u + (in >> 3);
+            L.px = tx * tile_w + (in % tile_w);
+            L.py = ty * (32u / tile_w) + (in / tile_w);
             if (L.px < W && L.py < H) return true;
         }
     }
+    uint32_t tile_w = 8;        // TILE_W: tile shape tile_w x (32 / tile_w), WARPTILE mode only
     int cur_warp = 0;
     bool fetch(Lane& L) {
         if (warptile) return fetch_warptile(L, cur_warp);
@@ -365,6 +366,7 @@ int main(int argc, char** argv) {
     S.tiles_x = (S.W + 7) / 8; S.tiles_y = (S.H + 3) / 4; S.n_tiles = S.tiles_x * S.tiles_y;
     S.tile_stride = 7919;                                   // prime: the simulated tickets sample the whole frame
     S.max_tickets = (uint32_t)n_warps * 32u * (uint32_t)per_warp;
+    if (getenv("TILE_W")) { S.tile_w = atoi(getenv("TILE_W")); S.tiles_x = (S.W + S.tile_w - 1) / S.tile_w; S.tiles_y = (S.H + 32 / S.tile_w - 1) / (32 / S.tile_w); S.n_tiles = S.tiles_x * S.tiles_y; }
     if (getenv("WARPTILE")) { S.warptile = 1; S.w_tile.assign(n_warps, 0); S.w_cursor.assign(n_warps, 32u); }
     if (getenv("FULL")) { S.tile_stride = 1; S.max_tickets = S.n_tiles * 32u; }           // the whole frame, row-major unless TILE_ORDER
     if (getenv("TILE_ORDER")) { FILE* f = fopen(getenv("TILE_ORDER"), "rb"); S.tile_order.resize(S.n_tiles); fread(S.tile_order.data(), 4, S.n_tiles, f); fclose(f); }
