@@ -14,6 +14,9 @@
 //     larger scenes are traversed straight from L2/HBM through the same code (128-bit __ldg loads).
 //   * the accumulate step (RayTracer.cu:206-215) is fused at the end of each pixel; sRGB + quantise (:216) is the
 //     coalesced k_tonemap launched right behind (one pixel per thread, 128-byte uchar4 stores per warp).
+//   * k_render_async (the default for scenes whose 4-wide nodes fit in shared memory) is the same per-lane machinery with the
+//     round structure relaxed: traversal state survives the shading code, a burst ends when enough lanes are finished, warps
+//     own whole 8x4 tiles, and vn_api.cu hands the tiles out most expensive first.
 #include <cooperative_groups.h>
 #include <cooperative_groups/reduce.h>
 
