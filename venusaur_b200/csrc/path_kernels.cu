@@ -402,8 +402,9 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_async(const __grid_const
     }
     sc.root_link = p.root_link;
     constexpr unsigned kFull = 0xFFFFFFFFu;
-    // instrumented variant: launch timeline in counters[8..11) (read with vn_read_sched_counters): ~min start, ~min time at which a lane
-    // found the ticket counter exhausted, max end -- the share of a launch spent draining (lanes idle behind the last pixels)
+    // instrumented variant: launch timeline in counters[8..11) (the words the slot kernel uses for its scheduler statistics, read with
+    // vn_read_sched_counters): ~min start, ~min time at which a lane found the tickets exhausted, max warp end -- tools/tail_probe.py
+    // turns them into the share of a launch spent draining (lanes idle behind the last pixels)
     if (kCount && threadIdx.x == 0) atomicMax(&p.counters[8], ~global_ns());
 
     uint32_t pix = 0, px = 0, py = 0, cam_seed = 0, s_left = 0;
@@ -621,12 +622,7 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_async(const __grid_const
             }
         }
     }
-    if (kCount && (threadIdx.x & 31u) == 0u) {
-        const unsigned long long t = global_ns();
-        atomicMax(&p.counters[10], t);
-        atomicAdd(&p.counters[11], t + (~p.counters[9]) * 0ull);          // sum of warp end times (mean end = sum / warps)
-        atomicAdd(&p.counters[12], 1ull);
-    }
+    if (kCount && (threadIdx.x & 31u) == 0u) atomicMax(&p.counters[10], global_ns());
     {
         unsigned long long seg = n_seg, path = n_path, nn = cnt.nodes, ns = cnt.spheres;
         cg::coalesced_group g = cg::coalesced_threads();

@@ -52,7 +52,7 @@ struct vn_context {
     bool copied_valid[2] = {false, false};
     int pipe_flip = 0;
 
-    unsigned long long* d_counters = nullptr;   // 4 x u64 + work ticket (u32) at +32 bytes; [8..22) scheduler statistics of the slot kernel
+    unsigned long long* d_counters = nullptr;   // 4 x u64 + work ticket (u32) at +32 bytes; [8..22) scheduler statistics of the slot kernel, or [8..11) the launch timeline of the instrumented k_render_async
     unsigned long long* h_counters = nullptr;   // pinned
 
     WavefrontBuffers wf;
