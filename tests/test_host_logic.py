@@ -249,6 +249,49 @@ def test_tile_index_by_multiply_high():
         assert (q == t // d).all() and (r == t % d).all(), d
 
 
+def test_warp_owned_tile_protocol_hands_out_every_pixel_once():
+    """Model of the pixel fetch of k_render_async<.., kWarpTile> (path_kernels.cu): a warp takes whole 8x4 tiles from one global
+    counter and hands their 32 slots to the asking lanes by ballot rank and a warp-uniform cursor; slots outside a ragged frame are
+    skipped (the lane keeps asking); when the tiles run out the asking lanes retire.  Whatever the pattern of asking lanes, every
+    in-frame pixel must be handed out exactly once and every lane must end up retired."""
+    rng = np.random.default_rng(3)
+    for (W, H, row_begin, row_end, n_warps) in ((33, 17, 0, 17, 3), (64, 40, 4, 29, 5), (8, 4, 0, 4, 2), (100, 7, 0, 7, 40), (5, 3, 0, 3, 1)):
+        tiles_x, rows = (W + 7) // 8, row_end - row_begin
+        n_tiles = tiles_x * ((rows + 3) // 4)
+        counter = 0
+        owner = {}
+        w_tile, w_cursor = [0] * n_warps, [32] * n_warps
+        busy = np.zeros((n_warps, 32), np.int64)                 # rounds a lane still works on its pixel
+        retired = np.zeros((n_warps, 32), bool)
+        for step in range(100000):
+            if retired.all():
+                break
+            for w in range(n_warps):
+                busy[w] = np.maximum(busy[w] - 1, 0)
+                need = (busy[w] == 0) & ~retired[w]
+                while need.any():                                # while (m)
+                    m = need.copy()                              # the ballot the ranks and the cursor advance are taken from
+                    if w_cursor[w] >= 32:
+                        t = counter
+                        counter += 1
+                        if t >= n_tiles:
+                            retired[w] |= need
+                            break
+                        w_tile[w], w_cursor[w] = t, 0
+                    slot = w_cursor[w] + np.cumsum(m) - m        # w_cursor + popc(m & lanemask_lt)
+                    for lane in np.nonzero(m & (slot < 32))[0]:
+                        ty, tx = divmod(w_tile[w], tiles_x)
+                        px, py = tx * 8 + (int(slot[lane]) & 7), row_begin + ty * 4 + (int(slot[lane]) >> 3)
+                        if px < W and py < row_end:
+                            assert (px, py) not in owner
+                            owner[(px, py)] = (w, int(lane))
+                            need[lane] = False
+                            busy[w, lane] = int(rng.integers(1, 6))
+                    w_cursor[w] = min(32, w_cursor[w] + int(m.sum()))
+        assert retired.all()
+        assert len(owner) == W * rows and all(row_begin <= y < row_end and 0 <= x < W for x, y in owner)
+
+
 def test_rnd_pm1_short_form_equals_literal_form(host_harness):
     """vn_math.cuh::rnd_pm1 forms random_float(seed, -1, 1) (RayTracer.cu:93-97) as float(int32((state << 8) ^ 2^31)) * 2^-31; it must
     give the bits of -1 + 2 * (float(state & 0xFFFFFF) / 2^24) for every 24-bit output (and leave the same LCG state)."""
