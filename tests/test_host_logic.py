@@ -102,6 +102,30 @@ def test_product_math_equals_oracle_on_cpu(host_harness, oracle_mod, rtiow, leaf
     assert nv.value / segs.value < 20      # the LBVH actually prunes
 
 
+@pytest.mark.parametrize("mix,depth,wide", [(1, 64, 1), (0, 50, 1), (1, 64, 0)])
+def test_product_math_equals_oracle_on_glass_heavy_random_scene(host_harness, oracle_mod, mix, depth, wide):
+    """The same bit-for-bit comparison away from RTIOW: 400 random spheres (mix 1 = 50 % glass, configs[4]'s material mix), seen from
+    inside the cloud with odd frame sizes -- long dielectric chains (ratio > 1 exits, total internal reflection), the per-sphere
+    dielectric constants, the quotient shortcuts of sphere_root and the jitter division by width - 1 = 36, height - 1 = 22."""
+    W, H, spp, sub = 37, 23, 4, 5
+    spheres = np.ascontiguousarray(oracle_mod.random_scene(400, 0x5EED0002, 1.2, mix))
+    cam = oracle_mod.camera((0.1, 0.05, 2.6), (0.0, 0.0, -1.0), 40.0, W / H, 0.05, 2.5)
+    hp = _hh_params(cam, W, H, spp, sub, depth)
+    mean = np.zeros((H, W, 4), np.float32)
+    segs, nv, st = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    host_harness.hh_set_wide(wide)
+    try:
+        host_harness.hh_render_mean(spheres.ctypes.data_as(C.c_void_p), len(spheres), 1 if wide else 2, C.c_float(0.01), C.byref(hp),
+                                    mean.ctypes.data_as(C.c_void_p), C.byref(segs), C.byref(nv), C.byref(st))
+    finally:
+        host_harness.hh_set_wide(0)
+    orc = oracle_mod.Oracle(spheres)
+    want, stats = orc.render_mean(orc.params(cam, W, H, spp, sub, depth, atten=oracle_mod.ATTEN_FORWARD, closest=oracle_mod.CLOSEST_BRUTE))
+    assert segs.value == stats.segments
+    assert np.array_equal(mean.view(np.uint32), want.view(np.uint32))
+    assert stats.segments > 3 * W * H * spp                 # paths really bounce around in there
+
+
 def _check_bvh(nodes, order, spheres, leaf_size, pad_rel=0.01):
     """Structural invariants of the packed 32-byte-node LBVH."""
     n = len(spheres)
