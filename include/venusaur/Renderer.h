@@ -17,6 +17,9 @@
 #include <string>
 
 #include "CUDAOutputBuffer.h"
+#include <utility>
+#include <vector>
+
 #include "Camera.h"
 #include "Exception.h"
 #include "Scene.h"
@@ -35,6 +38,7 @@ public:
         if (!m_handle) {
             if (vn_create(m_device, &m_handle) != VN_OK) throw Exception(std::string("vn_create failed: ") + vn_last_error(nullptr));
         }
+        for (const auto& kv : m_options) VN_CHECK(m_handle, vn_set_option(m_handle, kv.first.c_str(), kv.second));
         const std::vector<vn_sphere> flat = scene.Flatten();            // CreateSBT, Renderer.h:452-520
         VN_CHECK(m_handle, vn_set_spheres(m_handle, flat.data(), flat.size()));
         VN_CHECK(m_handle, vn_build_bvh(m_handle));                     // BuildAccelerationStructures, Renderer.h:160-255
@@ -91,12 +95,21 @@ public:
     void SetMaxDepth(uint32_t max_depth) { m_maxDepth = max_depth; }
     void SetSamplesPerPixel(uint32_t spp) { m_samplesPerPixel = spp; }
     void SetFlags(uint32_t flags) { m_flags = flags; }
+    // a tuning knob of the library (vn_set_option, include/venusaur_b200.h): applied at once when the renderer is initialised, and
+    // (again) by every Init; knobs that shape the BVH take effect with the next Init
+    void SetOption(const std::string& name, double value) {
+        bool known = false;
+        for (auto& kv : m_options) if (kv.first == name) { kv.second = value; known = true; }
+        if (!known) m_options.emplace_back(name, value);
+        if (m_handle) VN_CHECK(m_handle, vn_set_option(m_handle, name.c_str(), value));
+    }
     uint32_t SubframeIndex() const { return m_subframe_index; }
     vn_handle Handle() const { return m_handle; }
     vn_stats Stats() const { vn_stats s{}; if (m_handle) vn_get_stats(m_handle, &s); return s; }
 
 private:
     vn_handle m_handle = nullptr;
+    std::vector<std::pair<std::string, double>> m_options;
     int m_device = 0;
     uint32_t m_width = 0, m_height = 0;
     uint32_t m_subframe_index = 0;

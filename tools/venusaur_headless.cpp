@@ -10,6 +10,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "venusaur/Renderer.h"
 
@@ -17,6 +19,7 @@ int main(int argc, char** argv) {
     int width = 1200, height = 800, frames = 16, max_depth = 4, spp = 16, device = 0;   // Core.cpp:27-28, Renderer.h:53, RayTracer.cu:172
     std::string out = "frame.ppm";
     bool exact = false, wavefront = false;
+    std::vector<std::pair<std::string, double>> options;
     for (int i = 1; i < argc; i++) {
         auto next = [&](const char* name) { if (i + 1 >= argc) { fprintf(stderr, "%s needs a value\n", name); exit(2); } return argv[++i]; };
         if (!strcmp(argv[i], "--width")) width = atoi(next("--width"));
@@ -28,7 +31,13 @@ int main(int argc, char** argv) {
         else if (!strcmp(argv[i], "--out")) out = next("--out");
         else if (!strcmp(argv[i], "--exact")) exact = true;
         else if (!strcmp(argv[i], "--wavefront")) wavefront = true;
-        else { fprintf(stderr, "usage: %s [--width W] [--height H] [--frames N] [--spp S] [--max-depth D] [--device I] [--exact] [--wavefront] [--out file.ppm]\n", argv[0]); return 2; }
+        else if (!strcmp(argv[i], "--opt")) {                      // library tuning knob name=value (include/venusaur_b200.h)
+            const std::string kv = next("--opt");
+            const size_t eq = kv.find('=');
+            if (eq == std::string::npos) { fprintf(stderr, "--opt needs name=value\n"); return 2; }
+            options.emplace_back(kv.substr(0, eq), atof(kv.c_str() + eq + 1));
+        }
+        else { fprintf(stderr, "usage: %s [--width W] [--height H] [--frames N] [--spp S] [--max-depth D] [--device I] [--exact] [--wavefront] [--opt name=value]... [--out file.ppm]\n", argv[0]); return 2; }
     }
     try {
         // Core.cpp:21-31
@@ -38,6 +47,7 @@ int main(int argc, char** argv) {
         Renderer renderer;
         renderer.SetDevice(device);
         renderer.SetMaxDepth(static_cast<uint32_t>(max_depth));
+        for (const auto& kv : options) renderer.SetOption(kv.first, kv.second);
         renderer.SetSamplesPerPixel(static_cast<uint32_t>(spp));
         uint32_t flags = 0;
         if (exact) flags |= VN_EXACT;
