@@ -225,10 +225,12 @@ def run_ours(args):
         return ctx.make_params(cam, width, height, spp, subframe_of(step), depth, accum_count=step, image=image.data_ptr(), flags=kflag | VN_ASYNC)
 
     def barrier():
+        # the library renders on its own non-blocking stream, which NCCL never waits on: drain it BEFORE the process-group barrier,
+        # so that passing the barrier means every rank's kernels (e.g. its partial sums) are complete
+        ctx.synchronize()
+        torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
-        torch.cuda.synchronize()
-        ctx.synchronize()
 
     # peer mapping for the fused reduce+tonemap (one process per GPU => CUDA IPC handles, exchanged over the NCCL group)
     peer_ptrs, peer_image = None, None

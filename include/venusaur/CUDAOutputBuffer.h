@@ -25,7 +25,11 @@ enum class CUDAOutputBufferType { CUDA_DEVICE = 0, GL_INTEROP = 1, ZERO_COPY = 2
 template <typename PIXEL_FORMAT>
 class CUDAOutputBuffer {
 public:
-    CUDAOutputBuffer(CUDAOutputBufferType type, int32_t width, int32_t height) : m_type(type) {
+    // (type, width, height) as in the reference (CUDAOutputBuffer.h:68); device_idx is an extension -- the reference allocates on
+    // device 0 in its constructor and setDevice() afterwards only affects later calls (CUDAOutputBuffer.h:90,104-110).  Here
+    // setDevice() on a buffer that already holds pixels moves the allocation, so a buffer can never be mapped on one device and
+    // freed or copied under another.
+    CUDAOutputBuffer(CUDAOutputBufferType type, int32_t width, int32_t height, int32_t device_idx = 0) : m_type(type), m_device_idx(device_idx) {
         if (type == CUDAOutputBufferType::GL_INTEROP)
             throw Exception("CUDAOutputBuffer: GL_INTEROP needs an OpenGL context; use CUDA_DEVICE or ZERO_COPY");
         resize(width, height);
@@ -34,7 +38,14 @@ public:
     CUDAOutputBuffer(const CUDAOutputBuffer&) = delete;
     CUDAOutputBuffer& operator=(const CUDAOutputBuffer&) = delete;
 
-    void setDevice(int32_t device_idx) { m_device_idx = device_idx; }
+    void setDevice(int32_t device_idx) {
+        if (device_idx == m_device_idx) return;
+        const int32_t w = m_width, h = m_height;
+        release();                       // frees under the device that owns the pixels
+        m_device_idx = device_idx;
+        m_width = m_height = 0;
+        if (w > 0 && h > 0) resize(w, h);
+    }
     void setStream(CUstream stream) { m_stream = stream; }
 
     void resize(int32_t width, int32_t height) {
@@ -86,7 +97,7 @@ private:
     PIXEL_FORMAT* m_host_zcopy_pixels = nullptr;
     std::vector<PIXEL_FORMAT> m_host_pixels;
     CUstream m_stream = nullptr;
-    int32_t m_device_idx = 0;
+    int32_t m_device_idx = 0;            // the device that owns m_device_pixels
 };
 
 }  // namespace venusaur

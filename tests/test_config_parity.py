@@ -1,0 +1,110 @@
+"""Oracle parity at the real size of every BASELINE.json config, with the library's DEFAULT options, through vn_render.
+
+The full frames of configs[1..4] are hours of CPU time for the oracle, so each test renders the whole frame on the GPU and
+compares a seeded sample of it -- 64 tiles of 32x32 pixels, the very list bench.py times its CPU arm on (bench.sample_pixels) --
+with Oracle.render_mean(pixels=...), the CPU restatement of RayTracer.cu:163-217 for exactly those pixels.  Pixels are independent
+(the seed is tea<4>(pixel, subframe), RayTracer.cu:169), so the sample is as strict per pixel as the full frame.
+
+Bars: RTIOW frames (configs[1], [2]) bit-identical accumulation buffer; the synthetic scenes (configs[3], [4]) bit-identical too
+since the per-sphere box gate made the closest hit a function of (ray, sphere) alone -- the test prints the
+budget it measured (mismatching pixels, worst relative error) and fails on any mismatch above the stated budget."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import venusaur_b200 as vb
+from venusaur_b200 import VN_COUNTERS, VN_IMAGE_HOST, VN_NO_TONEMAP
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402  (sample_pixels, WORKLOADS, SCENES: the benchmark's own definitions)
+
+
+@pytest.fixture(scope="module")
+def dctx():
+    """A fresh handle: library defaults, nothing inherited from other tests' vn_set_option calls."""
+    c = vb.Context(0)
+    yield c
+    c.close()
+
+
+def _scene_and_camera(workload, oracle_mod):
+    width, height, spp, depth, scene = bench.WORKLOADS[workload]
+    if scene == "rtiow":
+        spheres = vb.rtiow_final_scene()
+        cam = vb.rtiow_camera(width, height)
+    else:
+        n, seed, S, mix = bench.SCENES[scene]
+        spheres = vb.random_scene(n, seed, S, mix)
+        cam = vb.Camera((0.0, 0.0, 2.0 * S), 40.0, width / height, 0.0, 2.0 * S)
+        cam.SetForward((0.0, 0.0, -1.0))
+    return width, height, spp, depth, spheres, cam
+
+
+def _compare(acc, want, px, width, name, budget_pixels):
+    got = acc.reshape(-1, 4)[px]
+    ref = want.reshape(-1, 4)[px]
+    bad = (got.view(np.uint32) != ref.view(np.uint32)).any(axis=-1)
+    rel = np.abs(got[:, :3] - ref[:, :3]) / np.maximum(np.abs(ref[:, :3]), 1e-3)
+    print("%s: %d sampled pixels, %d differ from the oracle (budget %d), worst relative error %.3g"
+          % (name, len(px), int(bad.sum()), budget_pixels, float(rel.max()) if len(rel) else 0.0))
+    assert int(bad.sum()) <= budget_pixels, "%s: %d pixels differ from the oracle (first: pixel %d)" % (name, int(bad.sum()), int(px[np.argmax(bad)]))
+    return bad
+
+
+@pytest.mark.parametrize("workload,subframes", [("c2", (1, 37)), ("c3", (256,))])
+def test_rtiow_full_size_frames_match_oracle_on_sampled_tiles(dctx, oracle_mod, workload, subframes):
+    """configs[1] (1920x1080) and configs[2] (3840x2160), 16 spp per launch, depth 50, default options = what bench.py runs
+    (k_render_async over the shared-memory wide nodes, huge list, warp-owned cost-ordered tiles).  Each launch is checked on its own
+    (accum_count = 0), and for configs[1] the progressive blend of RayTracer.cu:208-213 over three launches as well."""
+    width, height, spp, depth, spheres, cam = _scene_and_camera(workload, oracle_mod)
+    dctx.set_spheres(spheres)
+    dctx.build_bvh()
+    assert dctx.bvh_info().max_leaf_size == 1                       # the default (auto) leaf size for RTIOW
+    px = bench.sample_pixels(width, height)
+    orc = oracle_mod.Oracle(oracle_mod.rtiow_final_scene())
+    ocam = cam.frame()
+    for sub in subframes:
+        img = np.zeros((height, width, 4), np.uint8)
+        dctx.render(dctx.make_params(cam, width, height, spp, sub, depth, image=img.ctypes.data, flags=VN_IMAGE_HOST))
+        assert dctx.last_accel() == 2                               # wide nodes from shared memory: the headline kernel
+        acc = dctx.read_accum()
+        want, ost = orc.render_mean(orc.params(ocam, width, height, spp, sub, depth, atten=oracle_mod.ATTEN_FORWARD), pixels=px)
+        _compare(acc, want, px, width, "%s subframe %d" % (workload, sub), 0)
+        _, wimg = oracle_mod.accumulate_tonemap(None, want, False, 1.0)
+        d = np.abs(img.reshape(-1, 4)[px].astype(np.int32) - wimg.reshape(-1, 4)[px].astype(np.int32))
+        assert d.max() <= 1 and (d > 0).mean() < 2e-3               # device powf vs glibc powf: one code value
+    if workload == "c2":
+        # progressive accumulation, three launches of the same view (the second and third run with the cost-ordered tile schedule)
+        dctx.reset_accum()
+        want_acc = np.zeros((height, width, 4), np.float32)
+        for k in range(3):
+            dctx.render(dctx.make_params(cam, width, height, spp, k + 1, depth, accum_count=k, flags=VN_NO_TONEMAP))
+            mean, _ = orc.render_mean(orc.params(ocam, width, height, spp, k + 1, depth, atten=oracle_mod.ATTEN_FORWARD), pixels=px)
+            want_acc, _ = oracle_mod.accumulate_tonemap(want_acc, mean, k > 0, np.float32(1.0) / np.float32(k + 1))
+        _compare(dctx.read_accum(), want_acc, px, width, "c2 progressive x3", 0)
+
+
+@pytest.mark.parametrize("workload,n_px,budget", [("c4", 0, 0), ("c5", 2048, 0)])
+def test_synthetic_scenes_full_size_match_oracle(dctx, oracle_mod, workload, n_px, budget):
+    """configs[3] (1 M spheres, 80/15/5 mix, depth 50) and configs[4] (16 M spheres, 50 % glass, depth 64) at 1920x1080, 16 spp,
+    default options: nodes and spheres are traversed from L2 / HBM.  configs[3] is compared on the 64 sampled tiles, configs[4]
+    on 2048 seeded pixels (the oracle's own BVH over 16 M spheres takes half a minute to build)."""
+    width, height, spp, depth, spheres, cam = _scene_and_camera(workload, oracle_mod)
+    dctx.set_spheres(spheres)
+    dctx.build_bvh()
+    assert dctx.bvh_info().scene_in_smem == 0
+    px = bench.sample_pixels(width, height) if n_px == 0 else np.random.RandomState(99).randint(0, width * height, size=n_px).astype(np.uint32)
+    dctx.render(dctx.make_params(cam, width, height, spp, 1, depth, flags=VN_NO_TONEMAP | VN_COUNTERS))
+    st = dctx.stats()
+    acc = dctx.read_accum()
+    assert st.paths == width * height * spp and np.isfinite(acc).all()
+    orc = oracle_mod.Oracle(spheres)
+    want, ost = orc.render_mean(orc.params(cam.frame(), width, height, spp, 1, depth, atten=oracle_mod.ATTEN_FORWARD, closest=oracle_mod.CLOSEST_BVH), pixels=px)
+    print("%s: GPU %.2f segments/path over the frame, oracle %.2f over the sample; GPU %.1f node steps, %.2f sphere tests per segment"
+          % (workload, st.segments / st.paths, ost.segments / ost.paths, st.node_visits / st.segments, st.sphere_tests / st.segments))
+    _compare(acc, want, px, width, workload, budget)

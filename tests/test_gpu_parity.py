@@ -815,6 +815,24 @@ def test_row_tiles_and_partial_sums(rtiow_ctx):
     assert np.abs(img.astype(np.int32) - want.astype(np.int32)).max() <= 1
 
 
+@pytest.mark.parametrize("flags", [0, VN_ASYNC])
+def test_row_shards_into_one_host_image(rtiow_ctx, flags):
+    """VN_IMAGE_HOST with a row range copies back ONLY the rendered rows: three row shards rendered into one host image give the
+    full frame's image, and rows outside a shard keep what the caller had there (synchronous and pipelined copies)."""
+    W, H, spp, depth = 96, 54, 4, 50
+    cam = vb.rtiow_camera(W, H)
+    want = np.zeros((H, W, 4), np.uint8)
+    rtiow_ctx.render(rtiow_ctx.make_params(cam, W, H, spp, 2, depth, image=ptr(want), flags=VN_IMAGE_HOST))
+    rtiow_ctx.reset_accum()
+    got = np.full((H, W, 4), 7, np.uint8)
+    for rows in ((0, 17), (17, 18), (30, 54)):
+        rtiow_ctx.render(rtiow_ctx.make_params(cam, W, H, spp, 2, depth, image=ptr(got), flags=VN_IMAGE_HOST | flags, rows=rows))
+    rtiow_ctx.synchronize()
+    assert np.array_equal(got[:18], want[:18]) and np.array_equal(got[30:], want[30:])
+    assert (got[18:30] == 7).all()                              # never rendered, never overwritten
+    rtiow_ctx.reset_accum()
+
+
 def test_fused_peer_reduce_tonemap_single_gpu(rtiow_ctx):
     """vn_reduce_tonemap_peers with 'peers' that live on the same GPU: sum in rank order + tonemap of a row slice."""
     W, H = 64, 40

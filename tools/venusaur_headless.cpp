@@ -54,8 +54,7 @@ int main(int argc, char** argv) {
         if (wavefront) flags |= VN_WAVEFRONT;
         renderer.SetFlags(flags);
         renderer.Init(scene, "");                                                   // Core.cpp:246
-        CUDAOutputBuffer<uchar4> output_buffer(CUDAOutputBufferType::CUDA_DEVICE, width, height);   // Core.cpp:252
-        output_buffer.setDevice(device);
+        CUDAOutputBuffer<uchar4> output_buffer(CUDAOutputBufferType::CUDA_DEVICE, width, height, device);   // Core.cpp:252 (+ the device)
         camera.SetForward(lookat - lookfrom);                                       // Core.cpp:355
 
         unsigned long long segments = 0;

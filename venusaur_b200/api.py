@@ -369,7 +369,14 @@ class CUDAOutputBuffer:
         self._stream = stream
 
     def setDevice(self, device_idx: int):
+        if device_idx == self.m_device_idx:
+            return
+        w, h = self.m_width, self.m_height
+        self._free()                       # under the device that owns the pixels
         self.m_device_idx = device_idx
+        self.m_width = self.m_height = 0
+        if w and h:
+            self.resize(w, h)
 
     def resize(self, width: int, height: int):
         width, height = max(1, width), max(1, height)

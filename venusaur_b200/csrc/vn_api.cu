@@ -84,7 +84,7 @@ struct vn_context {
     const uint32_t* d_tile_order = nullptr;
     uint32_t tile_cap = 0;
     int tile_state = 0;               // 0: nothing known (the next launch collects costs), 1: costs collected (sort before the next launch), 2: order valid
-    struct TileSig { uint32_t w, h, r0, r1, spp, depth; float cam[13]; uint64_t epoch; } tile_sig{};
+    struct TileSig { uint32_t w, h, r0, r1, spp, depth; float cam[13]; uint32_t pad_; uint64_t epoch; } tile_sig{};   // no implicit padding
     uint64_t bvh_epoch = 0;
     uint32_t warp_tiles = 1;          // "warp_tiles": k_render_async phase form hands whole tiles to warps (see path_kernels.cu); 0 = lanes take single pixels
     uint32_t async_done = 26;         // k_render_async: a traversal burst ends when this many lanes hold a finished ray (0 = k_render_persistent)
@@ -202,6 +202,31 @@ struct DevBuf {
 };
 }  // namespace
 
+extern "C" void vn_destroy(vn_handle c);
+
+// everything vn_create allocates; on failure the caller destroys the half-built context
+static int create_resources(vn_context* c) {
+    VN_CUDA(c, cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    VN_CUDA(c, cudaGetDeviceProperties(&prop, c->device));
+    if (prop.major < 10)
+        return fail(c, VN_ERR_NO_DEVICE, std::string("vn_create: device '") + prop.name + "' is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                             "; this library contains sm_100a code only");
+    c->num_sms = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    VN_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto& ev : c->ev) VN_CUDA(c, cudaEventCreate(&ev));
+    VN_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        VN_CUDA(c, cudaEventCreateWithFlags(&c->ev_frame[i], cudaEventDisableTiming));
+        VN_CUDA(c, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+    }
+    VN_CUDA(c, cudaMalloc(&c->d_counters, 256));
+    VN_CUDA(c, cudaMemset(c->d_counters, 0, 256));
+    VN_CUDA(c, cudaHostAlloc(&c->h_counters, 256, cudaHostAllocDefault));
+    return VN_OK;
+}
+
 extern "C" {
 
 const char* vn_version(void) { return "venusaur_b200 0.1 (sm_100a)"; }
@@ -233,27 +258,11 @@ int vn_create(int device, vn_handle* out) {
     if (device < 0 || device >= n) return fail(nullptr, VN_ERR_INVALID, "vn_create: device index out of range");
     vn_context* c = new vn_context();
     c->device = device;
-    VN_CUDA(c, cudaSetDevice(device));
-    cudaDeviceProp prop;
-    VN_CUDA(c, cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) {
-        std::string msg = std::string("vn_create: device '") + prop.name + "' is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
-                          "; this library contains sm_100a code only";
-        delete c;
-        return fail(nullptr, VN_ERR_NO_DEVICE, msg);
+    const int rc = create_resources(c);
+    if (rc != VN_OK) {                   // the message is already in the global slot (vn_last_error(NULL)); nothing may leak
+        vn_destroy(c);
+        return rc;
     }
-    c->num_sms = prop.multiProcessorCount;
-    c->smem_optin = prop.sharedMemPerBlockOptin;
-    VN_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    for (auto& ev : c->ev) VN_CUDA(c, cudaEventCreate(&ev));
-    VN_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) {
-        VN_CUDA(c, cudaEventCreateWithFlags(&c->ev_frame[i], cudaEventDisableTiming));
-        VN_CUDA(c, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
-    }
-    VN_CUDA(c, cudaMalloc(&c->d_counters, 256));
-    VN_CUDA(c, cudaMemset(c->d_counters, 0, 256));
-    VN_CUDA(c, cudaHostAlloc(&c->h_counters, 256, cudaHostAllocDefault));
     *out = c;
     return VN_OK;
 }
@@ -349,6 +358,9 @@ int vn_build_bvh(vn_handle c) {
     VN_REQUIRE(c, c, "vn_build_bvh: NULL handle");
     VN_REQUIRE(c, c->have_spheres, "vn_build_bvh: call vn_set_spheres first");
     VN_CUDA(c, cudaSetDevice(c->device));
+    // a rebuild frees the old scene arrays before it can fail: nothing may render from them until the new build has succeeded
+    c->bvh_valid = false;
+    grid_free(c->grid);
     std::string err;
     uint32_t launches = 0;
     VN_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
@@ -367,7 +379,6 @@ int vn_build_bvh(vn_handle c) {
         }
     }
     if (rc != 0) return fail(c, rc == -1 ? VN_ERR_INVALID : VN_ERR_CUDA, "vn_build_bvh: " + err);
-    grid_free(c->grid);
     if (c->accel != 1u && c->scene.geom) {
         const int grc = grid_build(c->scene.geom, c->scene.n, c->grid_max_per_cell, c->stream, c->grid, &launches, err);
         if (grc < 0) return fail(c, VN_ERR_CUDA, "vn_build_bvh: " + err);
@@ -622,7 +633,8 @@ static int prepare_tile_order(vn_handle c, const vn_params* p, RenderLaunch& L) 
     L.tile_cost = nullptr;
     const uint32_t n_tiles = L.total_work / 32u;
     if (!c->tile_order_opt || n_tiles < (uint32_t)c->num_sms * 32u) return VN_OK;      // small frames: every lane gets at most one tile anyway
-    vn_context::TileSig sig{};
+    vn_context::TileSig sig;
+    memset(&sig, 0, sizeof sig);          // the struct is compared with memcmp: padding bytes must be defined
     sig.w = p->width; sig.h = p->height; sig.r0 = L.row_begin; sig.r1 = L.row_end; sig.spp = p->samples_per_pixel; sig.depth = p->max_depth;
     const float cam[13] = {p->origin[0], p->origin[1], p->origin[2], p->u[0], p->u[1], p->u[2], p->v[0], p->v[1], p->v[2], p->w[0], p->w[1], p->w[2], p->lens_radius};
     memcpy(sig.cam, cam, sizeof cam);
@@ -634,7 +646,7 @@ static int prepare_tile_order(vn_handle c, const vn_params* p, RenderLaunch& L) 
         VN_CUDA(c, cudaMalloc(&c->d_tile_sort, (size_t)n_tiles * 16));
         c->tile_cap = n_tiles;
     }
-    if (memcmp(&sig, &c->tile_sig, sizeof sig) != 0) { c->tile_sig = sig; c->tile_state = 0; }
+    if (memcmp(&sig, &c->tile_sig, sizeof sig) != 0) { memcpy(&c->tile_sig, &sig, sizeof sig); c->tile_state = 0; }
     if (c->tile_state == 0) {
         VN_CUDA(c, cudaMemsetAsync(c->d_tile_cost, 0, (size_t)c->tile_cap * 8, c->stream));
         L.tile_cost = c->d_tile_cost;
@@ -776,18 +788,20 @@ int vn_render(vn_handle c, const vn_params* p) {
         }
     }
     VN_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    // only the rows this launch rendered were tonemapped into the staging buffer: copy those and leave the caller's other rows alone
+    const uint64_t row_px0 = (uint64_t)L.row_begin * L.width, row_px = (uint64_t)(L.row_end - L.row_begin) * L.width;
     // (the 256-byte statistics copy goes first: queued behind the frame on the D2H engine it would delay the next launch)
     VN_CUDA(c, cudaMemcpyAsync(c->h_counters, c->d_counters, 256, cudaMemcpyDeviceToHost, c->stream));
     if (pipelined) {
         const int f = c->pipe_flip;
         VN_CUDA(c, cudaEventRecord(c->ev_frame[f], c->stream));
         VN_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_frame[f], 0));
-        VN_CUDA(c, cudaMemcpyAsync(p->image, c->image_pipe[f], pixels * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+        VN_CUDA(c, cudaMemcpyAsync(static_cast<uint32_t*>(p->image) + row_px0, c->image_pipe[f] + row_px0, row_px * 4, cudaMemcpyDeviceToHost, c->copy_stream));
         VN_CUDA(c, cudaEventRecord(c->ev_copied[f], c->copy_stream));
         c->copied_valid[f] = true;
         c->pipe_flip = f ^ 1;
     } else if (host_image) {
-        VN_CUDA(c, cudaMemcpyAsync(p->image, c->image_tmp, pixels * 4, cudaMemcpyDeviceToHost, c->stream));
+        VN_CUDA(c, cudaMemcpyAsync(static_cast<uint32_t*>(p->image) + row_px0, c->image_tmp + row_px0, row_px * 4, cudaMemcpyDeviceToHost, c->stream));
     }
     c->stats.kernel_launches = launches;
     c->stats.kernel_launches_total += launches;
