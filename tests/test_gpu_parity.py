@@ -422,7 +422,8 @@ def test_cost_ordered_tiles_do_not_change_the_image(ctx, rtiow):
     ctx.build_bvh()
     W, H, spp, depth = 640, 360, 4, 50                          # 7200 tiles >= 32 per SM: the schedule is active
     try:
-        for kernel_opts in ({"async_done": 26, "async_node": 0, "warp_tiles": 0}, {"async_done": 26, "async_node": 0, "warp_tiles": 1}, {"async_done": 0, "warp_tiles": 0}):
+        for kernel_opts in ({"async_done": 26, "async_node": 0, "warp_tiles": 0}, {"async_done": 26, "async_node": 0, "warp_tiles": 1, "lean": 0},
+                            {"async_done": 26, "async_node": 0, "warp_tiles": 1, "lean": 1}, {"async_done": 0, "warp_tiles": 0}):
             for k, v in kernel_opts.items():
                 ctx.set_option(k, v)
             cam = vb.rtiow_camera(W, H)
@@ -451,6 +452,7 @@ def test_cost_ordered_tiles_do_not_change_the_image(ctx, rtiow):
         ctx.set_option("async_done", 26)
         ctx.set_option("async_node", 0)
         ctx.set_option("warp_tiles", 1)
+        ctx.set_option("lean", 1)
 
 
 @pytest.mark.parametrize("threads", [512, 768, 1024])
@@ -483,17 +485,21 @@ def test_async_kernel_equals_persistent_kernel(ctx, oracle_mod, rtiow, threads):
                 assert np.array_equal(h.view(np.uint32), e.view(np.uint32))
                 assert (sh.segments, sh.node_visits, sh.sphere_tests) == (sf.segments, sf.node_visits, sf.sphere_tests)
                 if node == 0:
-                    # warp-owned tiles: one ticket per 8x4 tile, the warp hands the pixels to its own lanes
-                    ctx.set_option("warp_tiles", 1)
-                    w, iw, sw = render(ctx, cam, W, H, spp, sub, depth)
-                    w2, _, sw2 = render(ctx, cam, W, H, spp, sub, depth, flags=VN_COUNTERS)
-                    ctx.set_option("warp_tiles", 0)
-                    assert np.array_equal(w.view(np.uint32), e.view(np.uint32)) and np.array_equal(iw, ie), (W, H, done, "warp_tiles")
-                    assert np.array_equal(w2.view(np.uint32), e.view(np.uint32))
-                    assert (sw.segments, sw.paths) == (se.segments, se.paths)
-                    assert (sw2.segments, sw2.node_visits, sw2.sphere_tests) == (sf.segments, sf.node_visits, sf.sphere_tests)
+                    # warp-owned tiles: one ticket per 8x4 tile, the warp hands the pixels to its own lanes -- in k_render_async
+                    # (lean = 0) and in k_render_lean, the default: 16-bit links, next node chosen in registers, per-warp statistics
+                    for lean in (0, 1):
+                        ctx.set_option("warp_tiles", 1)
+                        ctx.set_option("lean", lean)
+                        w, iw, sw = render(ctx, cam, W, H, spp, sub, depth)
+                        w2, _, sw2 = render(ctx, cam, W, H, spp, sub, depth, flags=VN_COUNTERS)
+                        ctx.set_option("warp_tiles", 0)
+                        assert np.array_equal(w.view(np.uint32), e.view(np.uint32)) and np.array_equal(iw, ie), (W, H, done, "warp_tiles", lean)
+                        assert np.array_equal(w2.view(np.uint32), e.view(np.uint32))
+                        assert (sw.segments, sw.paths) == (se.segments, se.paths)
+                        assert (sw2.segments, sw2.paths, sw2.node_visits, sw2.sphere_tests) == (sf.segments, sf.paths, sf.node_visits, sf.sphere_tests)
     finally:
         ctx.set_option("warp_tiles", 1)
+        ctx.set_option("lean", 1)
         ctx.set_option("async_done", 26)
         ctx.set_option("async_node", 0)
         ctx.set_option("async_leaf", 8)

@@ -70,6 +70,7 @@ struct KernelConfig {
     bool grid;                       // uniform grid + oversize list in shared memory (excludes the others)
     bool async = false;              // k_render_async (wide nodes in shared memory only): asynchronous shading, see path_kernels.cu
     bool warp_tiles = false;         // phase form only: warps own whole 8x4 tiles (one ticket per tile) instead of lanes taking single pixels
+    bool lean = false;               // k_render_lean: the phase form with warp-owned tiles, 16-bit links and no per-lane statistics (path_kernels.cu)
 };
 
 // Vote thresholds of the slot-scheduled kernel (slot_kernels.cu): an operation runs when that many lanes wait for it.

@@ -640,6 +640,192 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_async(const __grid_const
     }
 }
 
+// k_render_lean: k_render_async in its default form (while-while phases, ONE vote per phase, warps own whole 8x4 tiles) rebuilt around
+// what ncu said the warps of that kernel wait for (profiles/r01s3_path_kernel_ncu.txt: long_scoreboard 2.7 warps per issue cycle): LOCAL
+// MEMORY.  At 1024 threads a lane has 64 registers; k_render_async keeps 38 words of path / pixel / traversal state alive across a node
+// step that itself needs 34, so six words (the pixel's sum, its sample counter, the camera seed, the segment counter) were spilled, and
+// the 64-word traversal stack lives in local memory as well -- 32 warps x (6 + ~10 stack levels) x 128-byte lines against the 28 KB of
+// L1 that 227 KB of shared memory leave: a quarter of those loads went to L2.  Here
+//   * the per-lane statistics are gone: segments and paths are counted per warp (popc of the vote that already exists), the per-pixel
+//     segment count for the cost-ordered tile schedule only exists in the kCost variant (the first launch of a view);
+//   * pixel coordinates travel as one word, the lane's scheduling state as one word;
+//   * links are 16 bits (vn_math.cuh::link16): two stack entries per word, a sentinel instead of the emptiness test, and the next node
+//     is chosen in registers (wide_node_step16_dev) -- the stack is only read when no child was hit.
+// Every lane walks its pixel's samples in order and every ray takes exactly the steps of closest_hit_wide(): the accumulation buffer
+// is bit-identical to k_render_persistent / k_render_async (tests/test_gpu_parity.py).  Needs spp, max_depth, width, height < 65536 and
+// < 4096 spheres (vn_api.cu falls back to k_render_async otherwise).
+enum LeanState : uint32_t { kLaneNoPixel = 0u, kLaneIdle = 1u, kLaneActive = 2u, kLaneRetired = 3u };
+
+template <bool kCount, bool kCost, int kMaxThreads>
+__global__ void __launch_bounds__(kMaxThreads) k_render_lean(const __grid_constant__ RenderLaunch p) {
+    extern __shared__ float4 s_scene[];
+    SceneView sc;
+    const uint32_t node_f4s = kWideNodeF4 * p.num_wide;
+    {
+        float4* s_nodes = s_scene;
+        float4* s_geom = s_nodes + (size_t)node_f4s * 8;
+        float4* s_mat = s_geom + p.num_spheres;
+        uint8_t* s_type = reinterpret_cast<uint8_t*>(s_mat + p.num_spheres);
+        for (uint32_t i = threadIdx.x; i < 8u * p.num_wide; i += blockDim.x) {
+            const uint32_t k = i / p.num_wide, j = i - k * p.num_wide;
+            float4 canon[8], out[kWideNodeF4];
+#pragma unroll
+            for (int q = 0; q < 8; q++) canon[q] = p.wide[8ull * j + q];
+            wide_octant_node(canon, k, out);
+            out[6] = make_float4(u2f(link16(f2u(out[6].x))), u2f(link16(f2u(out[6].y))), u2f(link16(f2u(out[6].z))), u2f(link16(f2u(out[6].w))));
+#pragma unroll
+            for (int q = 0; q < (int)kWideNodeF4; q++) s_nodes[(size_t)k * node_f4s + kWideNodeF4 * j + q] = out[q];
+        }
+        for (uint32_t i = threadIdx.x; i < p.num_spheres; i += blockDim.x) { s_geom[i] = p.geom[i]; s_mat[i] = p.mat[i]; }
+        for (uint32_t i = threadIdx.x; i < p.num_spheres; i += blockDim.x) s_type[i] = p.type[i];
+        __syncthreads();
+        sc.nodes = s_nodes; sc.geom = s_geom; sc.mat = s_mat; sc.type = s_type;
+    }
+    sc.root_link = p.root_link;
+    constexpr unsigned kFull = 0xFFFFFFFFu;
+    if (kCount && threadIdx.x == 0) atomicMax(&p.counters[8], ~global_ns());     // launch timeline, see k_render_async
+
+    uint32_t pxy = 0u;                 // py << 16 | px of the lane's pixel
+    uint32_t cam_seed = 0u, s_left = 0u;
+    uint32_t lane_state = kLaneNoPixel;
+    f3 sum = mk3(0.0f);
+    PathState st;
+    st.o = st.d = st.thr = mk3(0.0f); st.seed = 0; st.depth = 0;
+    uint32_t w_seg = 0u, w_path = 0u;  // warp-uniform: segments shaded / camera rays started by this warp
+    uint32_t px_seg = 0u;              // kCost: ray segments of the current pixel (tile cost feedback)
+    TraceCounters cnt{0u, 0u};
+    // traversal state, alive across the shading of other lanes
+    uint16_t stack[kStackSize];
+    const uint32_t base = (uint32_t)__cvta_generic_to_local(stack);
+    stack[0] = (uint16_t)kDone16;      // the sentinel: popping it ends the traversal
+    uint32_t top = base + 2u;
+    uint32_t cur = kDone16;
+    float tbest = kTMax;
+    int prim = -1;
+    SlabScale ss;
+    ss.sdir = ss.nsood = mk3(0.0f);
+    WideBase wb = wide_base(sc.nodes, 0u, node_f4s);
+    uint32_t w_tile = 0u, w_cursor = 32u;          // the warp's current tile and the next pixel of it to hand out (warp-uniform)
+
+    for (;;) {
+        const bool fin = cur == kDone16 && lane_state != kLaneRetired;     // holds a finished traversal, or no ray at all
+        const bool shading = fin && lane_state == kLaneActive;
+        w_seg += (uint32_t)__popc(__ballot_sync(kFull, shading));
+        if (shading) {
+            if (kCost) px_seg += 1u;
+            f3 result;
+            if (!shade_segment(sc, st, tbest, prim, result)) {
+                sum = sum + result;                               // pixel_color += prd.attenuation (RayTracer.cu:203)
+                lane_state = kLaneIdle;
+            }
+        }
+        if (fin && lane_state == kLaneIdle && s_left == 0u) {
+            const uint32_t px = pxy & 0xFFFFu, py = pxy >> 16;
+            finish_pixel(p, py * p.width + px, sum);
+            if (kCost) { uint32_t* tc = p.tile_cost + ((py - p.row_begin) >> 2) * p.tiles_x + (px >> 3); atomicAdd(tc, px_seg); atomicMax(tc + p.tile_cost_stride, px_seg); }
+            lane_state = kLaneNoPixel;
+        }
+        // warp-owned tiles (see k_render_async): one global ticket per 8x4 tile, pixels handed to the asking lanes in order
+        {
+            bool need = fin && lane_state == kLaneNoPixel;
+            unsigned m = __ballot_sync(kFull, need);
+            while (m) {
+                if (w_cursor >= 32u) {
+                    uint32_t t = 0u;
+                    if ((threadIdx.x & 31u) == 0u) t = atomicAdd(p.work_counter, 1u);
+                    t = __shfl_sync(kFull, t, 0);
+                    if (t >= (p.total_work >> 5)) {               // no tiles left: the asking lanes only vote from now on
+                        if (need) { lane_state = kLaneRetired; if (kCount) atomicMax(&p.counters[9], ~global_ns()); }
+                        break;
+                    }
+                    w_tile = p.tile_order ? __ldg(p.tile_order + t) : t;
+                    w_cursor = 0u;
+                }
+                const uint32_t in = w_cursor + (uint32_t)__popc(m & ((1u << (threadIdx.x & 31u)) - 1u));
+                if (need && in < 32u) {
+                    uint32_t ty, tx;
+                    tile_row_col(w_tile, p.tiles_x, p.tiles_x_inv, ty, tx);
+                    const uint32_t px = tx * 8u + (in & 7u), py = p.row_begin + ty * 4u + (in >> 3);
+                    if (px < p.width && py < p.row_end) {
+                        need = false;
+                        pxy = (py << 16) | px;
+                        cam_seed = tea4(py * p.width + px, p.subframe_index);   // RayTracer.cu:169
+                        sum = mk3(0.0f);
+                        s_left = p.spp;
+                        if (kCost) px_seg = 0u;
+                        lane_state = kLaneIdle;
+                    }
+                }
+                w_cursor = min(32u, w_cursor + (uint32_t)__popc(m));
+                m = __ballot_sync(kFull, need);
+            }
+        }
+        const bool launching = fin && lane_state == kLaneIdle;             // (a lane that just got a pixel, or whose path just ended)
+        w_path += (uint32_t)__popc(__ballot_sync(kFull, launching));
+        if (fin && lane_state != kLaneRetired) {
+            if (launching) {
+                camera_ray(p.cam, pxy & 0xFFFFu, pxy >> 16, cam_seed, st.o, st.d);   // RayTracer.cu:173-177
+                st.thr = mk3(1.0f);
+                st.seed = cam_seed;                               // prd.seed = seed: a copy (RayTracer.cu:183)
+                st.depth = (int)p.max_depth - 1;                  // RayTracer.cu:184
+                s_left -= 1u;
+                lane_state = kLaneActive;
+            }
+            // start the next segment: the huge spheres first (lbvh_core.cuh::HugeList), then the traversal constants
+            tbest = kTMax;
+            prim = -1;
+            if (p.huge.n) {
+                const float a = dot(st.d, st.d), inv_a = rcp(a);
+                for (uint32_t i = 0; i < p.huge.n; i++) {
+                    const uint32_t hs = p.huge.idx[i];
+                    const float4 g = sc.geom[hs];
+                    if (kCount) cnt.spheres += 1;
+                    const float th = sphere_root(st.o, st.d, a, inv_a, g.x, g.y, g.z, g.w, kTMin, tbest);
+                    if (th >= 0.0f) { tbest = th; prim = (int)hs; }
+                }
+            }
+            const f3 idir = slab_idir(st.d);
+            wb = wide_base(sc.nodes, ray_octant(st.d), node_f4s);
+            ss = slab_scale(idir, mk3(st.o.x * idir.x, st.o.y * idir.y, st.o.z * idir.z), tbest);
+            top = base + 2u;
+            cur = p.wide_root;
+        }
+        const unsigned live = __ballot_sync(kFull, lane_state != kLaneRetired);
+        if (live == 0u) break;
+        const uint32_t n_live = (uint32_t)__popc(live);
+        const uint32_t t_done = p.async_done < n_live ? p.async_done : n_live;
+        // one traversal burst: while-while phases, one vote per phase; it ends as soon as t_done lanes hold a finished ray
+        for (;;) {
+            while ((cur & kLeaf16) == 0u) {
+                if (kCount) cnt.nodes += 1;
+                cur = wide_node_step16_dev(wb, cur, ss, top);
+            }
+            if (cur != kDone16) {
+                const float a = dot(st.d, st.d), t_before = tbest;
+                leaf_test16<kCount>(sc.geom, cur, st.o, st.d, a, rcp(a), tbest, prim, cnt);
+                cur = stack_pop16_dev(top);
+                if (tbest != t_before) {                          // the slab test works in units of tbest: rescale
+                    const float g = t_before * rcp_approx(tbest);
+                    ss.sdir = ss.sdir * g; ss.nsood = ss.nsood * g;
+                }
+            }
+            if ((uint32_t)__popc(__ballot_sync(kFull, cur == kDone16 && lane_state != kLaneRetired)) >= t_done) break;
+        }
+    }
+    if (kCount && (threadIdx.x & 31u) == 0u) atomicMax(&p.counters[10], global_ns());
+    if (kCount) {
+        unsigned long long nn = cnt.nodes, ns = cnt.spheres;
+        cg::coalesced_group g = cg::coalesced_threads();
+        nn = cg::reduce(g, nn, cg::plus<unsigned long long>());
+        ns = cg::reduce(g, ns, cg::plus<unsigned long long>());
+        if (g.thread_rank() == 0) { atomicAdd(&p.counters[2], nn); atomicAdd(&p.counters[3], ns); }
+    }
+    if ((threadIdx.x & 31u) == 0u) {
+        atomicAdd(&p.counters[0], (unsigned long long)w_seg);
+        atomicAdd(&p.counters[1], (unsigned long long)w_path);
+    }
+}
+
 // Sort keys of the cost-ordered tile schedule: most urgent tile first = smallest key.  A tile's urgency is its total cost (ray segments
 // of its 32 pixels in one launch, mode 1), its most expensive pixel (mode 2), or the larger of the total / 8 and the most expensive
 // pixel (mode 3: a cheap tile that holds one glass pixel must not be handed out last).  24 key bits are plenty.
@@ -759,7 +945,12 @@ inline uint32_t grid_for(uint64_t n, int threads) { return (uint32_t)((n + threa
 
 namespace {
 typedef void (*PathKernel)(const RenderLaunch);
-PathKernel pick_kernel(bool scene_in_smem, bool count, bool octant, bool wide = false, int threads = 1024, bool grid = false, bool async = false, bool phase = false, bool warp_tiles = false) {
+PathKernel pick_kernel(bool scene_in_smem, bool count, bool octant, bool wide = false, int threads = 1024, bool grid = false, bool async = false, bool phase = false, bool warp_tiles = false,
+                       bool lean = false, bool cost = false) {
+    if (lean && async && phase && warp_tiles && wide && scene_in_smem && !grid) {
+        if (threads <= 768) return count ? (cost ? k_render_lean<true, true, 768> : k_render_lean<true, false, 768>) : (cost ? k_render_lean<false, true, 768> : k_render_lean<false, false, 768>);
+        return count ? (cost ? k_render_lean<true, true, 1024> : k_render_lean<true, false, 1024>) : (cost ? k_render_lean<false, true, 1024> : k_render_lean<false, false, 1024>);
+    }
     if (async && wide && scene_in_smem && !grid) {
         if (phase && warp_tiles) {
             if (threads <= 768) return count ? k_render_async<true, 768, true, true> : k_render_async<false, 768, true, true>;
@@ -795,7 +986,8 @@ int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool c
 }
 
 cudaError_t launch_render_persistent(const RenderLaunch& p, const KernelConfig& cfg, cudaStream_t stream) {
-    PathKernel k = pick_kernel(cfg.scene_in_smem, cfg.count, cfg.octant, cfg.wide, cfg.threads, cfg.grid, cfg.async, cfg.async && p.async_node == 0u, cfg.warp_tiles);
+    PathKernel k = pick_kernel(cfg.scene_in_smem, cfg.count, cfg.octant, cfg.wide, cfg.threads, cfg.grid, cfg.async, cfg.async && p.async_node == 0u, cfg.warp_tiles,
+                               cfg.lean, p.tile_cost != nullptr);
     if (cfg.smem_bytes > 48 * 1024) {
         const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes);
         if (e != cudaSuccess) return e;

@@ -86,6 +86,7 @@ struct vn_context {
     int tile_state = 0;               // 0: nothing known (the next launch collects costs), 1: costs collected (sort before the next launch), 2: order valid
     struct TileSig { uint32_t w, h, r0, r1, spp, depth; float cam[13]; uint32_t pad_; uint64_t epoch; } tile_sig{};   // no implicit padding
     uint64_t bvh_epoch = 0;
+    uint32_t lean = 1;                // "lean": k_render_lean (16-bit links, no per-lane statistics, no spills) when the launch qualifies; 0 = k_render_async
     uint32_t warp_tiles = 1;          // "warp_tiles": k_render_async phase form hands whole tiles to warps (see path_kernels.cu); 0 = lanes take single pixels
     uint32_t async_done = 26;         // k_render_async: a traversal burst ends when this many lanes hold a finished ray (0 = k_render_persistent)
     uint32_t async_node = 0, async_leaf = 8;   // async_node 0 = phase form (no votes inside the node / leaf phases), the default
@@ -307,6 +308,7 @@ int vn_set_option(vn_handle c, const char* name, double value) {
     else if (k == "wide_threads") { VN_REQUIRE(c, value == 512 || value == 768 || value == 1024, "wide_threads must be 512, 768 or 1024"); c->wide_threads = (int)value; }
     else if (k == "tile_order") { VN_REQUIRE(c, value >= 0 && value <= 3, "tile_order must be 0..3"); c->tile_order_opt = (uint32_t)value; c->tile_state = 0; }
     else if (k == "warp_tiles") { c->warp_tiles = value != 0 ? 1u : 0u; }
+    else if (k == "lean") { c->lean = value != 0 ? 1u : 0u; }
     else if (k == "async_done") { VN_REQUIRE(c, value >= 0 && value <= 32, "async_done must be in [0,32]"); c->async_done = (uint32_t)value; }
     else if (k == "async_node") { VN_REQUIRE(c, value >= 0 && value <= 32, "async_node must be in [0,32] (0 = phase form: no votes inside the node / leaf phases)"); c->async_node = (uint32_t)value; }
     else if (k == "async_leaf") { VN_REQUIRE(c, value >= 1 && value <= 32, "async_leaf must be in [1,32]"); c->async_leaf = (uint32_t)value; }
@@ -762,7 +764,9 @@ int vn_render(vn_handle c, const vn_params* p) {
         // small scenes of similar-sized spheres: uniform grid + oversize list (grid_core.cuh), 40 % of the BVH's instructions on RTIOW
         cfg.grid = c->accel != 1u && c->grid.valid && grid_smem_bytes(c->grid.h.n_cells, c->grid.h.n_refs, L.num_spheres) + 2048 <= c->smem_optin;
         if (cfg.grid) { cfg.scene_in_smem = true; cfg.octant = false; cfg.wide = false; cfg.smem_bytes = grid_smem_bytes(c->grid.h.n_cells, c->grid.h.n_refs, L.num_spheres); cfg.threads = c->wide_threads; }
-        else if (cfg.wide) { cfg.scene_in_smem = true; cfg.octant = false; cfg.smem_bytes = wide_bytes; cfg.threads = c->wide_threads; cfg.async = c->async_done > 0u; cfg.warp_tiles = cfg.async && c->async_node == 0u && c->warp_tiles != 0u; }
+        else if (cfg.wide) { cfg.scene_in_smem = true; cfg.octant = false; cfg.smem_bytes = wide_bytes; cfg.threads = c->wide_threads; cfg.async = c->async_done > 0u; cfg.warp_tiles = cfg.async && c->async_node == 0u && c->warp_tiles != 0u;
+            cfg.lean = cfg.warp_tiles && c->lean != 0u && cfg.threads >= 768 && L.num_spheres < kLink16MaxPrims && L.num_wide < 32768u && p->samples_per_pixel < 65536u &&
+                       p->max_depth < 65536u && p->width < 65536u && p->height < 65536u; }
         else if (wide_global) { cfg.wide = true; cfg.octant = false; if (cfg.threads > 256) cfg.threads = 256; }
         else if (cfg.octant) { cfg.smem_bytes = oct_bytes; cfg.threads = 1024; }
         else if (cfg.threads > 256) cfg.threads = 256;

@@ -705,6 +705,100 @@ __device__ __forceinline__ uint32_t stack_pop_dev(uint32_t& top, uint32_t base) 
     return next;
 }
 #endif
+// ---- 16-bit links (k_render_lean, path_kernels.cu).  The traversal stack of the kernels above lives in local memory: 64 words per
+// lane, i.e. one 128-byte line per warp and stack level, next to 227 KB of shared memory that leave the SM 28 KB of L1 -- ncu
+// (profiles/r01s3_path_kernel_ncu.txt) showed the warps waiting for those loads more than for anything else (long_scoreboard 2.7
+// warps per issue cycle; 24 % of the loads missed L1).  A scene whose wide nodes fit in shared memory has < 32768 nodes and < 4096
+// spheres, so a link fits 16 bits: bit 15 = leaf (or done), leaf = 0x8000 | first << 3 | (count - 1), done / empty = 0xFFFF.  Two
+// stack entries then share a word, the stack's footprint in L1 halves, and with kDone16 parked at the bottom of the stack a pop
+// needs no emptiness test: popping the sentinel IS "traversal finished".
+constexpr uint32_t kLeaf16 = 0x8000u;
+constexpr uint32_t kDone16 = 0xFFFFu;
+constexpr uint32_t kLink16MaxPrims = 4096u;
+VN_HD uint32_t link16(uint32_t link) {
+    if (link == kEmptyScene) return kDone16;
+    if (link & kLeafFlag) return kLeaf16 | (link & 0x7FFFu);         // first << 3 | (count - 1), first < 4096
+    return link;                                                      // wide-node index
+}
+#if defined(__CUDACC__)
+// wide_node_step_dev() with 16-bit links and the next node chosen in registers: the nearest hit child (slot order = the octant's
+// front-to-back order) becomes the current node directly, only the OTHER hit children are pushed (far to near), and the stack is read
+// only when no child was hit.  The step above pushed every hit child but slot 0 and popped the nearest one straight back whenever
+// slot 0 was missed -- 70 % of all steps went through a dependent store/load pair in local memory.  Same visiting order.
+__device__ __forceinline__ uint32_t wide_node_step16_dev(WideBase wb, uint32_t cur, const SlabScale& sc, uint32_t& top) {
+    const uint32_t pa = wb.addr + cur * (kWideNodeF4 * 16u);
+    const node_f4 nx = lds_f4<0>(pa), ny = lds_f4<16>(pa), nz = lds_f4<32>(pa), fx = lds_f4<48>(pa), fy = lds_f4<64>(pa), fz = lds_f4<80>(pa), lk = lds_f4<96>(pa);
+    float ax[4], ay[4], bx[4], by[4];
+    slab4(nx, sc.sdir.x, sc.nsood.x, ax[0], ax[1], ax[2], ax[3]);
+    slab4(ny, sc.sdir.y, sc.nsood.y, ay[0], ay[1], ay[2], ay[3]);
+    slab4(fx, sc.sdir.x, sc.nsood.x, bx[0], bx[1], bx[2], bx[3]);
+    slab4(fy, sc.sdir.y, sc.nsood.y, by[0], by[1], by[2], by[3]);
+    const float az[4] = {fma_sat(nz.x, sc.sdir.z, sc.nsood.z), fma_sat(nz.y, sc.sdir.z, sc.nsood.z), fma_sat(nz.z, sc.sdir.z, sc.nsood.z), fma_sat(nz.w, sc.sdir.z, sc.nsood.z)};
+    const float bz[4] = {fma_sat(fz.x, sc.sdir.z, sc.nsood.z), fma_sat(fz.y, sc.sdir.z, sc.nsood.z), fma_sat(fz.z, sc.sdir.z, sc.nsood.z), fma_sat(fz.w, sc.sdir.z, sc.nsood.z)};
+    float tn[4], tf[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) { tn[c] = fmaxf(fmaxf(ax[c], ay[c]), az[c]); tf[c] = fminf(fminf(bx[c], by[c]), bz[c]); }
+    uint32_t next;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred h0, h1, h2, h3, t01, t012, c1, c2, c3, any;\n\t"
+        ".reg .u32 n;\n\t"
+        "setp.lt.f32 h3, %2, %3;\n\t"
+        "setp.lt.f32 h2, %4, %5;\n\t"
+        "setp.lt.f32 h1, %6, %7;\n\t"
+        "setp.lt.f32 h0, %8, %9;\n\t"
+        "or.pred t01, h0, h1;\n\t"
+        "or.pred t012, t01, h2;\n\t"
+        "and.pred c3, h3, t012;\n\t"
+        "and.pred c2, h2, t01;\n\t"
+        "and.pred c1, h1, h0;\n\t"
+        "or.pred any, t012, h3;\n\t"
+        "@c3 st.local.b16 [%1], %10;\n\t"          // (a 32-bit source register: the low half is stored)
+        "selp.u32 n, 2, 0, c3;\n\t"
+        "add.u32 %1, %1, n;\n\t"
+        "@c2 st.local.b16 [%1], %11;\n\t"
+        "selp.u32 n, 2, 0, c2;\n\t"
+        "add.u32 %1, %1, n;\n\t"
+        "@c1 st.local.b16 [%1], %12;\n\t"
+        "selp.u32 n, 2, 0, c1;\n\t"
+        "add.u32 %1, %1, n;\n\t"
+        "selp.u32 %0, %11, %10, h2;\n\t"
+        "selp.u32 %0, %12, %0, h1;\n\t"
+        "selp.u32 %0, %13, %0, h0;\n\t"
+        "@!any ld.local.u16 %0, [%1+-2];\n\t"      // (zero-extended into the 32-bit register)
+        "@!any add.u32 %1, %1, -2;\n\t"
+        "}"
+        : "=&r"(next), "+r"(top)
+        : "f"(tn[3]), "f"(tf[3]), "f"(tn[2]), "f"(tf[2]), "f"(tn[1]), "f"(tf[1]), "f"(tn[0]), "f"(tf[0]),
+          "r"(f2u(lk.w)), "r"(f2u(lk.z)), "r"(f2u(lk.y)), "r"(f2u(lk.x))
+        : "memory");
+    return next;
+}
+// pop with the sentinel at the bottom of the stack: no emptiness test (see kDone16)
+__device__ __forceinline__ uint32_t stack_pop16_dev(uint32_t& top) {
+    uint32_t next;
+    asm volatile(
+        "ld.local.u16 %0, [%1+-2];\n\t"
+        "add.u32 %1, %1, -2;"
+        : "=r"(next), "+r"(top) : : "memory");
+    return next;
+}
+#endif
+// the sphere tests of one leaf reached through a 16-bit link
+template <bool kCount>
+VN_HD void leaf_test16(const node_f4* __restrict__ geom, uint32_t cur, f3 o, f3 d, float a, float inv_a, float& tbest, int& prim, TraceCounters& cnt) {
+    const uint32_t first = (cur & 0x7FFFu) >> 3;
+    const uint32_t count = (cur & 7u) + 1u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (uint32_t k = 0; k < count; k++) {
+        const node_f4 g = geom[first + k];
+        if (kCount) cnt.spheres += 1;
+        const float t = sphere_root(o, d, a, inv_a, g.x, g.y, g.z, g.w, kTMin, tbest);
+        if (t >= 0.0f) { tbest = t; prim = (int)(first + k); }
+    }
+}
 // the sphere tests of one leaf (RayTracer.cu:229-270 on each of its <= 8 spheres)
 template <bool kCount>
 VN_HD void leaf_test(const node_f4* __restrict__ geom, uint32_t cur, f3 o, f3 d, float a, float inv_a, float& tbest, int& prim, TraceCounters& cnt) {
