@@ -21,6 +21,7 @@
 #include <cooperative_groups/reduce.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "kernels.h"
 #include "lbvh_core.cuh"
@@ -656,12 +657,14 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_async(const __grid_const
 // < 4096 spheres (vn_api.cu falls back to k_render_async otherwise).
 enum LeanState : uint32_t { kLaneNoPixel = 0u, kLaneIdle = 1u, kLaneActive = 2u, kLaneRetired = 3u };
 
-template <bool kCount, bool kCost, int kMaxThreads>
-__global__ void __launch_bounds__(kMaxThreads) k_render_lean(const __grid_constant__ RenderLaunch p) {
+template <bool kCount, bool kCost, int kMaxThreads, bool kGlobal = false, int kMinBlocks = 1>
+__global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const __grid_constant__ RenderLaunch p) {
     extern __shared__ float4 s_scene[];
     SceneView sc;
     const uint32_t node_f4s = kWideNodeF4 * p.num_wide;
-    {
+    if (kGlobal) {
+        sc.nodes = p.nodes; sc.geom = p.geom; sc.mat = p.mat; sc.type = p.type;
+    } else {
         float4* s_nodes = s_scene;
         float4* s_geom = s_nodes + (size_t)node_f4s * 8;
         float4* s_mat = s_geom + p.num_spheres;
@@ -694,21 +697,26 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_lean(const __grid_consta
     uint32_t w_seg = 0u, w_path = 0u;  // warp-uniform: segments shaded / camera rays started by this warp
     uint32_t px_seg = 0u;              // kCost: ray segments of the current pixel (tile cost feedback)
     TraceCounters cnt{0u, 0u};
-    // traversal state, alive across the shading of other lanes
-    uint16_t stack[kStackSize];
+    // traversal state, alive across the shading of other lanes.  kGlobal: pair nodes from L2 / HBM, 32-bit links (kEmptyScene = done).
+    typedef typename std::conditional<kGlobal, uint32_t, uint16_t>::type StackWord;
+    constexpr uint32_t kDone = kGlobal ? kEmptyScene : kDone16;
+    constexpr uint32_t kLeafBit = kGlobal ? kLeafFlag : kLeaf16;
+    constexpr uint32_t kWordBytes = (uint32_t)sizeof(StackWord);
+    StackWord stack[kStackSize + 2];
     const uint32_t base = (uint32_t)__cvta_generic_to_local(stack);
-    stack[0] = (uint16_t)kDone16;      // the sentinel: popping it ends the traversal
-    uint32_t top = base + 2u;
-    uint32_t cur = kDone16;
+    stack[0] = (StackWord)kDone;       // never a live entry: the word a pop of the last entry refills `tos` from
+    uint32_t top = base + kWordBytes;
+    uint32_t tos = kDone;              // the newest stack entry (vn_math.cuh::wide_node_step16_dev); kDone = the sentinel that ends the traversal
+    uint32_t cur = kDone;
     float tbest = kTMax;
     int prim = -1;
-    SlabScale ss;
+    SlabScale ss;                      // shared-memory wide nodes: idir / tbest, -(o * idir) / tbest; kGlobal: idir, o * idir
     ss.sdir = ss.nsood = mk3(0.0f);
     WideBase wb = wide_base(sc.nodes, 0u, node_f4s);
     uint32_t w_tile = 0u, w_cursor = 32u;          // the warp's current tile and the next pixel of it to hand out (warp-uniform)
 
     for (;;) {
-        const bool fin = cur == kDone16 && lane_state != kLaneRetired;     // holds a finished traversal, or no ray at all
+        const bool fin = cur == kDone && lane_state != kLaneRetired;       // holds a finished traversal, or no ray at all
         const bool shading = fin && lane_state == kLaneActive;
         w_seg += (uint32_t)__popc(__ballot_sync(kFull, shading));
         if (shading) {
@@ -774,36 +782,69 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_lean(const __grid_consta
             // start the next segment: the huge spheres first (lbvh_core.cuh::HugeList), then the traversal constants
             tbest = kTMax;
             prim = -1;
-            if (p.huge.n) {
-                const float a = dot(st.d, st.d), inv_a = rcp(a);
-                for (uint32_t i = 0; i < p.huge.n; i++) {
-                    const uint32_t hs = p.huge.idx[i];
-                    const float4 g = sc.geom[hs];
-                    if (kCount) cnt.spheres += 1;
-                    const float th = sphere_root(st.o, st.d, a, inv_a, g.x, g.y, g.z, g.w, kTMin, tbest);
-                    if (th >= 0.0f) { tbest = th; prim = (int)hs; }
-                }
-            }
             const f3 idir = slab_idir(st.d);
-            wb = wide_base(sc.nodes, ray_octant(st.d), node_f4s);
-            ss = slab_scale(idir, mk3(st.o.x * idir.x, st.o.y * idir.y, st.o.z * idir.z), tbest);
-            top = base + 2u;
-            cur = p.wide_root;
+            if (kGlobal) {
+                ss.sdir = idir;
+                ss.nsood = mk3(st.o.x * idir.x, st.o.y * idir.y, st.o.z * idir.z);
+                cur = p.root_link;
+            } else {
+                if (p.huge.n) {
+                    const float a = dot(st.d, st.d), inv_a = rcp(a);
+                    for (uint32_t i = 0; i < p.huge.n; i++) {
+                        const uint32_t hs = p.huge.idx[i];
+                        const float4 g = sc.geom[hs];
+                        if (kCount) cnt.spheres += 1;
+                        const float th = sphere_root(st.o, st.d, a, inv_a, g.x, g.y, g.z, g.w, kTMin, tbest);
+                        if (th >= 0.0f) { tbest = th; prim = (int)hs; }
+                    }
+                }
+                wb = wide_base(sc.nodes, ray_octant(st.d), node_f4s);
+                ss = slab_scale(idir, mk3(st.o.x * idir.x, st.o.y * idir.y, st.o.z * idir.z), tbest);
+                cur = p.wide_root;
+            }
+            top = base + kWordBytes;
+            tos = kDone;
         }
         const unsigned live = __ballot_sync(kFull, lane_state != kLaneRetired);
         if (live == 0u) break;
         const uint32_t n_live = (uint32_t)__popc(live);
         const uint32_t t_done = p.async_done < n_live ? p.async_done : n_live;
+        if (kGlobal) {
+            // Nodes from L2 / HBM: every node step is a dependent fetch of ~300-800 cycles and a ray takes 20 steps to its first leaf in a
+            // scene of a million spheres, so the turns are VOTED: all lanes standing on a node step together; the lanes holding a leaf
+            // wait until async_leaf of them do (or nobody stands on a node), then test their spheres together; the burst ends when
+            // t_done lanes hold a finished ray.  A lane is never idle for longer than the others need to reach their next leaf -- in
+            // k_render_persistent every lane of a warp waited for the warp's slowest RAY (ncu on 1 M spheres: 4.8 of 32 lanes active).
+            const uint32_t t_leaf = p.async_leaf;
+            for (;;) {
+                if ((cur & kLeafBit) == 0u) {
+                    if (kCount) cnt.nodes += 1;
+                    cur = pair_node_step_dev(sc.nodes, cur, ss.sdir, ss.nsood, tbest, top, tos);
+                }
+                const bool at_leaf = (cur & kLeafBit) != 0u && cur != kDone;
+                const unsigned lm = __ballot_sync(kFull, at_leaf);
+                const unsigned nm = __ballot_sync(kFull, (cur & kLeafBit) == 0u);
+                if (nm == 0u || (uint32_t)__popc(lm) >= t_leaf) {
+                    if (at_leaf) {
+                        const float a = dot(st.d, st.d);
+                        leaf_test<kCount>(sc.geom, cur, st.o, st.d, a, rcp(a), tbest, prim, cnt);
+                        cur = stack_pop32_dev(top, tos);
+                    }
+                }
+                if ((uint32_t)__popc(__ballot_sync(kFull, cur == kDone && lane_state != kLaneRetired)) >= t_done) break;
+            }
+            continue;
+        }
         // one traversal burst: while-while phases, one vote per phase; it ends as soon as t_done lanes hold a finished ray
         for (;;) {
             while ((cur & kLeaf16) == 0u) {
                 if (kCount) cnt.nodes += 1;
-                cur = wide_node_step16_dev(wb, cur, ss, top);
+                cur = wide_node_step16_dev(wb, cur, ss, top, tos);
             }
             if (cur != kDone16) {
                 const float a = dot(st.d, st.d), t_before = tbest;
                 leaf_test16<kCount>(sc.geom, cur, st.o, st.d, a, rcp(a), tbest, prim, cnt);
-                cur = stack_pop16_dev(top);
+                cur = stack_pop16_dev(top, tos);
                 if (tbest != t_before) {                          // the slab test works in units of tbest: rescale
                     const float g = t_before * rcp_approx(tbest);
                     ss.sdir = ss.sdir * g; ss.nsood = ss.nsood * g;
@@ -947,6 +988,9 @@ namespace {
 typedef void (*PathKernel)(const RenderLaunch);
 PathKernel pick_kernel(bool scene_in_smem, bool count, bool octant, bool wide = false, int threads = 1024, bool grid = false, bool async = false, bool phase = false, bool warp_tiles = false,
                        bool lean = false, bool cost = false) {
+    if (lean && !scene_in_smem && !wide && !grid) {        // pair nodes from L2 / HBM, asynchronous (k_render_lean<kGlobal>)
+        return count ? (cost ? k_render_lean<true, true, 256, true, 4> : k_render_lean<true, false, 256, true, 4>) : (cost ? k_render_lean<false, true, 256, true, 4> : k_render_lean<false, false, 256, true, 4>);
+    }
     if (lean && async && phase && warp_tiles && wide && scene_in_smem && !grid) {
         if (threads <= 768) return count ? (cost ? k_render_lean<true, true, 768> : k_render_lean<true, false, 768>) : (cost ? k_render_lean<false, true, 768> : k_render_lean<false, false, 768>);
         return count ? (cost ? k_render_lean<true, true, 1024> : k_render_lean<true, false, 1024>) : (cost ? k_render_lean<false, true, 1024> : k_render_lean<false, false, 1024>);
@@ -977,9 +1021,9 @@ PathKernel pick_kernel(bool scene_in_smem, bool count, bool octant, bool wide = 
 }
 }  // namespace
 
-int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool count, bool octant, bool wide, bool grid) {
+int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool count, bool octant, bool wide, bool grid, bool lean) {
     int nb = 0;
-    PathKernel k = pick_kernel(scene_in_smem, count, octant, wide, threads, grid, false);
+    PathKernel k = pick_kernel(scene_in_smem, count, octant, wide, threads, grid, false, false, false, lean);
     if (smem_bytes > 48 * 1024 && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) return -1;
     const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, threads, smem_bytes);
     return e == cudaSuccess ? nb : -1;

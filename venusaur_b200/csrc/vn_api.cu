@@ -770,10 +770,12 @@ int vn_render(vn_handle c, const vn_params* p) {
         else if (wide_global) { cfg.wide = true; cfg.octant = false; if (cfg.threads > 256) cfg.threads = 256; }
         else if (cfg.octant) { cfg.smem_bytes = oct_bytes; cfg.threads = 1024; }
         else if (cfg.threads > 256) cfg.threads = 256;
+        // scenes traversed from L2 / HBM (pair nodes): the asynchronous form of the path kernel (k_render_lean<kGlobal>, 256-thread CTAs)
+        if (!cfg.scene_in_smem && !cfg.wide && !cfg.grid && c->lean != 0u && c->async_done > 0u && p->width < 65536u && p->height < 65536u) { cfg.lean = true; cfg.threads = 256; }
         int per_sm = (cfg.octant || (cfg.wide && cfg.scene_in_smem)) ? 1 : c->blocks_per_sm;
         if (per_sm <= 0) {
-            per_sm = exact_build ? exact::max_blocks_per_sm(cfg.threads, cfg.smem_bytes, cfg.scene_in_smem, count, cfg.octant, cfg.wide, cfg.grid)
-                                 : fast::max_blocks_per_sm(cfg.threads, cfg.smem_bytes, cfg.scene_in_smem, count, cfg.octant, cfg.wide, cfg.grid);
+            per_sm = exact_build ? exact::max_blocks_per_sm(cfg.threads, cfg.smem_bytes, cfg.scene_in_smem, count, cfg.octant, cfg.wide, cfg.grid, cfg.lean)
+                                 : fast::max_blocks_per_sm(cfg.threads, cfg.smem_bytes, cfg.scene_in_smem, count, cfg.octant, cfg.wide, cfg.grid, cfg.lean);
             if (per_sm <= 0) return fail(c, VN_ERR_CUDA, "vn_render: occupancy query failed for the path kernel");
         }
         cfg.blocks = c->num_sms * per_sm;

@@ -725,7 +725,7 @@ VN_HD uint32_t link16(uint32_t link) {
 // front-to-back order) becomes the current node directly, only the OTHER hit children are pushed (far to near), and the stack is read
 // only when no child was hit.  The step above pushed every hit child but slot 0 and popped the nearest one straight back whenever
 // slot 0 was missed -- 70 % of all steps went through a dependent store/load pair in local memory.  Same visiting order.
-__device__ __forceinline__ uint32_t wide_node_step16_dev(WideBase wb, uint32_t cur, const SlabScale& sc, uint32_t& top) {
+__device__ __forceinline__ uint32_t wide_node_step16_dev(WideBase wb, uint32_t cur, const SlabScale& sc, uint32_t& top, uint32_t& tos) {
     const uint32_t pa = wb.addr + cur * (kWideNodeF4 * 16u);
     const node_f4 nx = lds_f4<0>(pa), ny = lds_f4<16>(pa), nz = lds_f4<32>(pa), fx = lds_f4<48>(pa), fy = lds_f4<64>(pa), fz = lds_f4<80>(pa), lk = lds_f4<96>(pa);
     float ax[4], ay[4], bx[4], by[4];
@@ -738,49 +738,100 @@ __device__ __forceinline__ uint32_t wide_node_step16_dev(WideBase wb, uint32_t c
     float tn[4], tf[4];
 #pragma unroll
     for (int c = 0; c < 4; c++) { tn[c] = fmaxf(fmaxf(ax[c], ay[c]), az[c]); tf[c] = fminf(fminf(bx[c], by[c]), bz[c]); }
+    // The newest stack entry lives in a register (`tos`), the older ones in local memory below `top`: a push stores the old top entry and
+    // keeps the new one, a pop hands out the register at once and refills it with a load whose latency nobody waits for -- the loaded
+    // value is first needed by the NEXT pop or push, a node step (or a sphere test) later.
     uint32_t next;
     asm volatile(
         "{\n\t"
         ".reg .pred h0, h1, h2, h3, t01, t012, c1, c2, c3, any;\n\t"
         ".reg .u32 n;\n\t"
-        "setp.lt.f32 h3, %2, %3;\n\t"
-        "setp.lt.f32 h2, %4, %5;\n\t"
-        "setp.lt.f32 h1, %6, %7;\n\t"
-        "setp.lt.f32 h0, %8, %9;\n\t"
+        "setp.lt.f32 h3, %3, %4;\n\t"
+        "setp.lt.f32 h2, %5, %6;\n\t"
+        "setp.lt.f32 h1, %7, %8;\n\t"
+        "setp.lt.f32 h0, %9, %10;\n\t"
         "or.pred t01, h0, h1;\n\t"
         "or.pred t012, t01, h2;\n\t"
         "and.pred c3, h3, t012;\n\t"
         "and.pred c2, h2, t01;\n\t"
         "and.pred c1, h1, h0;\n\t"
         "or.pred any, t012, h3;\n\t"
-        "@c3 st.local.b16 [%1], %10;\n\t"          // (a 32-bit source register: the low half is stored)
+        "@c3 st.local.b16 [%1], %2;\n\t"           // (a 32-bit source register: the low half is stored)
+        "selp.u32 %2, %11, %2, c3;\n\t"
         "selp.u32 n, 2, 0, c3;\n\t"
         "add.u32 %1, %1, n;\n\t"
-        "@c2 st.local.b16 [%1], %11;\n\t"
+        "@c2 st.local.b16 [%1], %2;\n\t"
+        "selp.u32 %2, %12, %2, c2;\n\t"
         "selp.u32 n, 2, 0, c2;\n\t"
         "add.u32 %1, %1, n;\n\t"
-        "@c1 st.local.b16 [%1], %12;\n\t"
+        "@c1 st.local.b16 [%1], %2;\n\t"
+        "selp.u32 %2, %13, %2, c1;\n\t"
         "selp.u32 n, 2, 0, c1;\n\t"
         "add.u32 %1, %1, n;\n\t"
-        "selp.u32 %0, %11, %10, h2;\n\t"
-        "selp.u32 %0, %12, %0, h1;\n\t"
-        "selp.u32 %0, %13, %0, h0;\n\t"
-        "@!any ld.local.u16 %0, [%1+-2];\n\t"      // (zero-extended into the 32-bit register)
+        "selp.u32 %0, %12, %11, h2;\n\t"
+        "selp.u32 %0, %13, %0, h1;\n\t"
+        "selp.u32 %0, %14, %0, h0;\n\t"
+        "@!any mov.u32 %0, %2;\n\t"
+        "@!any ld.local.u16 %2, [%1+-2];\n\t"      // (zero-extended into the 32-bit register)
         "@!any add.u32 %1, %1, -2;\n\t"
         "}"
-        : "=&r"(next), "+r"(top)
+        : "=&r"(next), "+r"(top), "+r"(tos)
         : "f"(tn[3]), "f"(tf[3]), "f"(tn[2]), "f"(tf[2]), "f"(tn[1]), "f"(tf[1]), "f"(tn[0]), "f"(tf[0]),
           "r"(f2u(lk.w)), "r"(f2u(lk.z)), "r"(f2u(lk.y)), "r"(f2u(lk.x))
         : "memory");
     return next;
 }
-// pop with the sentinel at the bottom of the stack: no emptiness test (see kDone16)
-__device__ __forceinline__ uint32_t stack_pop16_dev(uint32_t& top) {
-    uint32_t next;
+// pop: the register entry is the result, the refill load runs behind it.  The bottom of the stack holds kDone16, so no emptiness test.
+__device__ __forceinline__ uint32_t stack_pop16_dev(uint32_t& top, uint32_t& tos) {
+    const uint32_t next = tos;
     asm volatile(
         "ld.local.u16 %0, [%1+-2];\n\t"
         "add.u32 %1, %1, -2;"
-        : "=r"(next), "+r"(top) : : "memory");
+        : "=r"(tos), "+r"(top) : : "memory");
+    return next;
+}
+#endif
+#if defined(__CUDACC__)
+// One step over a PAIR node fetched from L2 / HBM (k_render_lean<kGlobal>): the two children's boxes arrive as one 64-byte line, the
+// nearer hit child becomes the current node, the other one is pushed; like the 16-bit stack above, the newest entry lives in a register
+// and the bottom of the stack holds kEmptyScene, so a pop needs no emptiness test and nobody waits for its refill load.  Same test,
+// same order as the loop of closest_hit(): the closest hit it finds is the same.
+__device__ __forceinline__ uint32_t pair_node_step_dev(const node_f4* __restrict__ nodes, uint32_t cur, f3 idir, f3 ood, float tbest, uint32_t& top, uint32_t& tos) {
+    const node_f4* __restrict__ q = nodes + 2ull * cur;
+    const node_f4 l0 = __ldg(q), l1 = __ldg(q + 1), r0 = __ldg(q + 2), r1 = __ldg(q + 3);
+    float tl, tr;
+    const bool hl = box_hit(l0, l1, idir, ood, tbest, tl);
+    const bool hr = box_hit(r0, r1, idir, ood, tbest, tr);
+    const uint32_t ll = f2u(l0.w), lr = f2u(r0.w);
+    const bool left_first = tl <= tr;
+    const uint32_t near = (hl && (!hr || left_first)) ? ll : lr;
+    const uint32_t far = left_first ? lr : ll;
+    uint32_t next = near;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred both, none;\n\t"
+        ".reg .u32 n;\n\t"
+        "setp.ne.u32 both, %4, 0;\n\t"
+        "setp.ne.u32 none, %5, 0;\n\t"
+        "@both st.local.u32 [%1], %2;\n\t"
+        "selp.u32 %2, %3, %2, both;\n\t"
+        "selp.u32 n, 4, 0, both;\n\t"
+        "add.u32 %1, %1, n;\n\t"
+        "@none mov.u32 %0, %2;\n\t"
+        "@none ld.local.u32 %2, [%1+-4];\n\t"
+        "@none add.u32 %1, %1, -4;\n\t"
+        "}"
+        : "+r"(next), "+r"(top), "+r"(tos)
+        : "r"(far), "r"((uint32_t)(hl && hr)), "r"((uint32_t)(!hl && !hr))
+        : "memory");
+    return next;
+}
+__device__ __forceinline__ uint32_t stack_pop32_dev(uint32_t& top, uint32_t& tos) {
+    const uint32_t next = tos;
+    asm volatile(
+        "ld.local.u32 %0, [%1+-4];\n\t"
+        "add.u32 %1, %1, -4;"
+        : "=r"(tos), "+r"(top) : : "memory");
     return next;
 }
 #endif
