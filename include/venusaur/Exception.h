@@ -31,3 +31,13 @@ public:
             throw ::venusaur::Exception(vn_ss_.str());                                                \
         }                                                                                             \
     } while (0)
+#define VN_MULTI_CHECK(handle, call)                                                                  \
+    do {                                                                                              \
+        const int vn_status_ = (call);                                                                \
+        if (vn_status_ != VN_OK) {                                                                    \
+            std::stringstream vn_ss_;                                                                 \
+            vn_ss_ << "venusaur_b200 call (" << #call << ") failed with status " << vn_status_ << ": '" \
+                   << vn_multi_last_error(handle) << "' (" __FILE__ << ":" << __LINE__ << ")\n";      \
+            throw ::venusaur::Exception(vn_ss_.str());                                                \
+        }                                                                                             \
+    } while (0)

@@ -64,11 +64,7 @@ enum {
     VN_ASYNC          = 1u << 6, /* do not synchronise the stream before returning (stats are then stale).  With VN_IMAGE_HOST the
                                     frame's D2H copy is pipelined on a second stream under the next vn_render's kernel: the host buffer
                                     is complete after vn_synchronize (or two vn_render calls later); alternate between two host buffers */
-    VN_POOL           = 1u << 8, /* use the shared-memory warp-pool wavefront kernel (pool_kernels.cu) */
-    VN_SLOTS          = 1u << 9, /* use the slot-scheduled path kernel (slot_kernels.cu) when the scene qualifies (4-wide nodes in
-                                    shared memory); otherwise the persistent kernel runs */
     VN_GRID           = 1u << 11, /* vn_trace_rays only: query the uniform grid + oversize list instead of the BVH */
-    VN_PERSISTENT     = 1u << 10, /* force k_render_persistent even when the "slot_kernel" option makes the slot kernel the default */
     VN_FAST           = 1u << 7  /* relaxed-numerics build (FMA contraction, approximate rcp/rsqrt/sqrt, FP32 for the FP64
                                     fragments): a few % faster, PSNR > 60 dB vs the oracle but NOT within the 1e-3 per-pixel
                                     tolerance at 1024 spp (individual paths diverge); never the default */
@@ -139,8 +135,10 @@ VN_API int vn_set_spheres(vn_handle h, const vn_sphere* host_spheres, uint64_t n
  * lanes; 0 = every lane takes single pixels from the global ticket], "tile_order" [1: once a view has been
  * rendered once, its 8x4-pixel tiles are handed out most expensive first (ray segments per tile, counted by that first launch); 0 = row-major, 2 = by the most
  * expensive pixel, 3 = max(sum / 8, most expensive pixel)], "wide_global" [0], "threads", "blocks_per_sm", "smem_scene_limit".
- * Experimental kernels: "slot_kernel" [0], "slot_slots", "slot_threads", "slot_tn|tl|tw|ts|tr"; "pool_slots", "pool_threads", "pool_service",
- * "pool_leaf_batch"; "wavefront_slots".  Options that change the BVH invalidate it (call vn_build_bvh again). */
+ * "lean" [1: k_render_lean -- 16-bit links, newest stack entry in a register, per-warp statistics -- for shared-memory scenes, and its
+ * asynchronous form over pair nodes for scenes traversed from L2 / HBM; 0 = k_render_async / k_render_persistent], "global_done" [16: the burst
+ * threshold of the L2 / HBM form], "hit_gate" [1: pair-node and L2 / HBM traversals only count a root whose hit point lies inside the sphere's
+ * slightly grown box, see DESIGN.md section 4], "wavefront_slots".  Options that change the BVH invalidate it (call vn_build_bvh again). */
 VN_API int vn_set_option(vn_handle h, const char* name, double value);
 VN_API int vn_build_bvh(vn_handle h);
 VN_API int vn_get_bvh_info(vn_handle h, vn_bvh_info* out);
@@ -167,8 +165,8 @@ VN_API int vn_tonemap(vn_handle h, float scale, void* image, uint32_t flags); /*
 VN_API int vn_synchronize(vn_handle h);                               /* CUDA_SYNC_CHECK, Renderer.h:77 */
 VN_API int vn_get_stats(vn_handle h, vn_stats* out);
 VN_API int vn_reset_stats(vn_handle h);
-/* Scheduler statistics of the last VN_SLOTS | VN_COUNTERS launch: for each warp-wide operation (node step, leaf, retire+fetch,
- * shade opaque, shade dielectric, shade miss, camera ray) the number of times it ran and the lanes that took part. */
+/* Launch timeline of the last VN_COUNTERS launch of the asynchronous path kernels, in out14[0..2]: ~(earliest CTA start), ~(time at which the
+ * first lane found the tile tickets exhausted), latest warp end -- %globaltimer nanoseconds (tools/tail_probe.py turns them into the drain). */
 VN_API int vn_read_sched_counters(vn_handle h, uint64_t* out14);
 
 /* ---- accumulation buffer: Params::accum (RayTracer.h:6), float4 per pixel ---- */
@@ -180,6 +178,53 @@ VN_API int vn_set_accum_external(vn_handle h, void* dev_ptr);         /* render 
  * make_color(scale * sum_i peers[i]) ; also writes the sum into this handle's accum. */
 VN_API int vn_reduce_tonemap_peers(vn_handle h, const void* const* peer_accum, uint32_t n_peers, float scale,
                                    uint32_t row_begin, uint32_t row_end, void* image, uint32_t flags);
+
+/* the same kernel with the float4 sum written to `sum_out` (device pointer, may be a peer's memory or NULL) instead of this handle's
+ * accum: the partial sums stay intact, so a progressive render can go on accumulating into them (vn_multi_render) */
+VN_API int vn_reduce_tonemap_peers_to(vn_handle h, const void* const* peer_accum, uint32_t n_peers, float scale,
+                                      uint32_t row_begin, uint32_t row_end, void* sum_out, void* image, uint32_t flags);
+
+/* Device-side ordering between GPUs owned by DIFFERENT processes (one process per GPU, the launch bench.py is given): every handle
+ * owns 62 epoch flags in device memory (vn_sync_flags returns their address; export it with vn_ipc_export).  vn_signal(h, i, e) makes
+ * flag i = e once everything queued on the handle's stream so far is complete and visible to peers; vn_wait_flags holds the stream
+ * until all the given flags (peers' memory) have reached e; vn_reduce_tonemap_peers_wait is the fused reduce + tonemap that first waits
+ * for one flag per peer (wait_value != 0).  Epochs only grow.  No host barrier is needed around the once-per-frame reduce.  A wait
+ * gives up after 4 s; vn_check_flags reports that as an error. */
+VN_API int vn_sync_flags(vn_handle h, void** dev_ptr);
+VN_API int vn_signal(vn_handle h, uint32_t index, uint32_t value);
+VN_API int vn_wait_flags(vn_handle h, const void* const* flags, uint32_t n, uint32_t value);
+VN_API int vn_check_flags(vn_handle h);
+VN_API int vn_reduce_tonemap_peers_wait(vn_handle h, const void* const* peer_accum, uint32_t n_peers, float scale, uint32_t row_begin,
+                                        uint32_t row_end, void* sum_out, void* image, const void* const* peer_flags, uint32_t wait_value,
+                                        uint32_t flags);
+
+/* ---- one host thread, several devices (the handle drives 1-8 devices so that Renderer::Draw, Renderer.h:35-78, scales on
+ * an 8 x B200 box without any help from the caller).  Scene and BVH are replicated (every device builds its own LBVH: deterministic);
+ * vn_multi_render deals the subframes of one view round-robin to the devices (sample-range sharding: the seed is a pure function of
+ * pixel and subframe, RayTracer.cu:169), each device adds its subframes' means into its own partial-sum buffer, and ONE fused
+ * reduce + tonemap kernel per device then loads its row slice of every peer's buffer over NVLink (cudaDeviceEnablePeerAccess) and
+ * writes the frame mean's pixels straight into the image on devices[0].  Ordering is by CUDA events between the devices' streams;
+ * the host never waits inside a frame.  The image equals a single device's running mean over the same subframes up to float
+ * re-association (sum-then-divide vs the sequential lerp of RayTracer.cu:208-213). */
+typedef struct vn_multi_context* vn_multi_handle;
+VN_API int vn_multi_create(const int* devices, int n_devices, vn_multi_handle* out);   /* 1..8 distinct devices that are peers of each other */
+VN_API void vn_multi_destroy(vn_multi_handle m);
+VN_API const char* vn_multi_last_error(vn_multi_handle m);
+VN_API int vn_multi_device_count(vn_multi_handle m);
+VN_API vn_handle vn_multi_device(vn_multi_handle m, int i);   /* the i-th device's own handle (BVH read-back, per-device statistics) */
+VN_API int vn_multi_set_option(vn_multi_handle m, const char* name, double value);
+VN_API int vn_multi_set_spheres(vn_multi_handle m, const vn_sphere* host_spheres, uint64_t n);
+VN_API int vn_multi_build_bvh(vn_multi_handle m);
+/* Renders subframes p->subframe_index, +1, ..., + n_subframes - 1 (p->samples_per_pixel each) and combines ALL subframes accumulated
+ * since the last reset into p->image (uchar4: device memory of devices[0], host memory with VN_IMAGE_HOST, or NULL).
+ * p->accum_count = 0 starts a new accumulation (the camera.Changed() path); otherwise it must be the number of subframes accumulated
+ * so far.  Returns without waiting for the devices when VN_ASYNC is set. */
+VN_API int vn_multi_render(vn_multi_handle m, const vn_params* p, uint32_t n_subframes);
+VN_API int vn_multi_synchronize(vn_multi_handle m);
+VN_API int vn_multi_read_accum(vn_multi_handle m, float* host_rgba);   /* the frame mean: (sum over devices) / subframes accumulated */
+/* sums over the devices; ms_render = the slowest device's last launch, ms_trace = device time of the last reduce + tonemap on devices[0] */
+VN_API int vn_multi_get_stats(vn_multi_handle m, vn_stats* out);
+VN_API uint32_t vn_multi_subframes_accumulated(vn_multi_handle m);
 
 /* ---- plain device/host buffer helpers, so that the header-only C++ shim (CUDAOutputBuffer.h:173-281,348-372) needs no
  * CUDA toolkit of its own ---- */

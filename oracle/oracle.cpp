@@ -69,6 +69,7 @@ struct Ctx {
     bool zyx;      // draw order of the three components of a vector (contract is x,y,z)
     bool forward;  // attenuation multiplication order
     bool bvh;
+    bool gate = false;   // ORC_CLOSEST_GATE: the hit-point gate (see hit_gate)
     orc_stats st{};
 };
 
@@ -150,6 +151,20 @@ namespace {
 struct Hit { float t; int32_t prim; V3 p, n; bool front; };
 
 // RayTracer.cu:229-270 (+ set_face_normal :219-224).  Returns true when the sphere reports a hit in [tmin,tmax].
+// The hit-point gate (ORC_CLOSEST_GATE).  In the reference the intersection program only runs for rays that
+// reach the sphere's AABB (custom primitives: Renderer.h:187-200 feeds OptiX the boxes of sphere.h:17-28), and a reported hit lies on
+// the sphere.  Far from the origin the float quadratic below is dominated by rounding noise (its discriminant carries an absolute
+// error of ~1e-7 |o - c|^2) and reports hits for rays that miss the sphere by a good fraction of its radius; whether OptiX would run
+// the program for such a ray is decided by its closed-source box test.  The gate makes the outcome a function of (ray, sphere) alone
+// -- independent of any BVH, so brute force, the oracle's BVH and the product's LBVH agree bit for bit: a root only counts when the hit
+// point the reference computes (RayTracer.cu:256) lies inside the sphere's box grown by 0.5 % of the radius plus 2^-19 of the
+// coordinates' magnitude.  True hits (|p - c| = r up to rounding) always pass; on the RTIOW scenes the gate never fires (tests).
+inline bool hit_gate(const orc_sphere& s, V3 p) {
+    const float g = fabsf(s.r) * 1.005f + (fabsf(s.cx) + fabsf(s.cy) + fabsf(s.cz) + fabsf(s.r)) * 1.9073486328125e-06f;
+    return fabsf(p.x - s.cx) <= g && fabsf(p.y - s.cy) <= g && fabsf(p.z - s.cz) <= g;
+}
+
+template <bool kGate = false>
 inline bool hit_sphere(const orc_sphere& s, V3 origin, V3 direction, float t_min, float t_max, Hit& h) {
     V3 center = mk(s.cx, s.cy, s.cz);
     V3 oc = origin - center;
@@ -166,6 +181,7 @@ inline bool hit_sphere(const orc_sphere& s, V3 origin, V3 direction, float t_min
     }
     h.t = root;
     h.p = origin + direction * root;
+    if (kGate && !hit_gate(s, h.p)) return false;
     V3 normal = (h.p - center) / s.r;
     h.front = dot(direction, normal) < 0;
     h.n = h.front ? normal : -normal;
@@ -192,7 +208,8 @@ void build_bvh(orc_scene& sc) {
             const float c[3] = {s.cx, s.cy, s.cz};
             // conservative bound: |r| plus a relative + absolute pad so that float rounding in the
             // slab test can never cull a sphere the exact quadratic would accept.
-            const float pad = fabsf(s.r) * (1.0f + 1e-3f) + 1e-4f;
+            // (it also has to contain the hit-point gate's box with room for the slab test's own rounding: 2 % + 2^-16 of the coordinates)
+            const float pad = fabsf(s.r) * 1.02f + 1e-4f + (fabsf(s.cx) + fabsf(s.cy) + fabsf(s.cz) + fabsf(s.r)) * 1.52587890625e-05f;
             for (int a = 0; a < 3; a++) {
                 lo[a] = std::min(lo[a], c[a] - pad); hi[a] = std::max(hi[a], c[a] + pad);
                 clo[a] = std::min(clo[a], c[a]);     chi[a] = std::max(chi[a], c[a]);
@@ -239,12 +256,13 @@ inline bool slab(const BNode& b, V3 o, V3 inv, float tbest, float& tn_out) {
 
 // Closest hit = optixTrace(tmin=0.001f, tmax=1e16f) (RayTracer.cu:190-202): OptiX shrinks tmax to the closest
 // accepted intersection, so every sphere is tested against the current best t.
+template <bool kGate = false>
 inline bool closest_brute(const orc_scene& sc, V3 o, V3 d, Hit& best, orc_stats& st) {
     float tmax = 1e16f;
     bool any = false;
     Hit h;
     for (size_t i = 0; i < sc.s.size(); i++) {
-        if (hit_sphere(sc.s[i], o, d, 0.001f, tmax, h)) { h.prim = (int32_t)i; best = h; tmax = h.t; any = true; }
+        if (hit_sphere<kGate>(sc.s[i], o, d, 0.001f, tmax, h)) { h.prim = (int32_t)i; best = h; tmax = h.t; any = true; }
     }
     st.sphere_tests += sc.s.size();
     return any;
@@ -252,6 +270,7 @@ inline bool closest_brute(const orc_scene& sc, V3 o, V3 d, Hit& best, orc_stats&
 
 // The oracle's own BVH traversal (near child first).  Same closest-hit semantics as brute force; only used because
 // brute force is too slow for full frames, and validated against it in tests/test_oracle.py.
+template <bool kGate = false>
 inline bool closest_bvh(const orc_scene& sc, V3 o, V3 d, Hit& best, orc_stats& st) {
     if (sc.nodes.empty()) return false;
     float tmax = 1e16f;
@@ -270,7 +289,7 @@ inline bool closest_bvh(const orc_scene& sc, V3 o, V3 d, Hit& best, orc_stats& s
             for (int32_t k = nd.first; k < nd.first + nd.count; k++) {
                 int32_t idx = sc.order[k];
                 st.sphere_tests++;
-                if (hit_sphere(sc.s[idx], o, d, 0.001f, tmax, h)) { h.prim = idx; best = h; tmax = h.t; any = true; }
+                if (hit_sphere<kGate>(sc.s[idx], o, d, 0.001f, tmax, h)) { h.prim = idx; best = h; tmax = h.t; any = true; }
             }
         } else {
             float tl, tr;
@@ -288,6 +307,7 @@ inline bool closest_bvh(const orc_scene& sc, V3 o, V3 d, Hit& best, orc_stats& s
 
 inline bool closest(Ctx& c, V3 o, V3 d, Hit& h) {
     c.st.segments++;
+    if (c.gate) return c.bvh ? closest_bvh<true>(*c.scene, o, d, h, c.st) : closest_brute<true>(*c.scene, o, d, h, c.st);
     return c.bvh ? closest_bvh(*c.scene, o, d, h, c.st) : closest_brute(*c.scene, o, d, h, c.st);
 }
 
@@ -539,7 +559,8 @@ void orc_render_mean(const orc_scene* sc, const orc_params* P, const uint32_t* p
         c.scene = sc; c.P = P;
         c.zyx = P->draw_order == ORC_DRAW_ZYX;
         c.forward = P->atten_order == ORC_ATTEN_FORWARD;
-        c.bvh = P->closest == ORC_CLOSEST_BVH;
+        c.bvh = (P->closest & ORC_CLOSEST_BVH) != 0;
+        c.gate = (P->closest & ORC_CLOSEST_GATE) != 0;
         while (true) {
             uint64_t b = next.fetch_add(chunk);
             if (b >= total) break;
@@ -588,7 +609,9 @@ void orc_closest_hit(const orc_scene* sc, int use_bvh, const float* origins, con
         V3 o = mk(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
         V3 d = mk(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
         Hit h;
-        bool any = use_bvh ? closest_bvh(*sc, o, d, h, st) : closest_brute(*sc, o, d, h, st);
+        const bool bvh = (use_bvh & ORC_CLOSEST_BVH) != 0, gate = (use_bvh & ORC_CLOSEST_GATE) != 0;
+        bool any = gate ? (bvh ? closest_bvh<true>(*sc, o, d, h, st) : closest_brute<true>(*sc, o, d, h, st))
+                        : (bvh ? closest_bvh(*sc, o, d, h, st) : closest_brute(*sc, o, d, h, st));
         t_out[i] = any ? h.t : -1.0f;
         prim_out[i] = any ? h.prim : -1;
     }

@@ -46,6 +46,7 @@ def host_harness():
                                  C.c_void_p, C.c_void_p]
     h.hh_render_mean.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     h.hh_set_oct.argtypes = [C.c_int]
+    h.hh_set_gate.argtypes = [C.c_int]
     h.hh_set_wide.argtypes = [C.c_int]
     h.hh_set_grid.argtypes = [C.c_int]
     h.hh_huge_list.restype = C.c_uint32

@@ -25,6 +25,7 @@ struct hh_params {
 static inline node_f4 dielectric_mat(float ir) { const DielectricConsts dc = dielectric_consts(ir); return node_f4{dc.ir, dc.inv_ir, dc.r0_front, dc.r0_back}; }
 static uint32_t g_sah_max = 4096;   // same default as the library's "sah_max_prims" option
 static int g_use_oct = 0;
+static int g_gate = 0;          // hh_set_gate(1): pair-node / global wide traversals apply the hit-point gate (vn_math.cuh::hit_gate_ok)
 static int g_use_grid = 0;         // hh_set_grid(1): closest hit through the uniform grid + oversize list
 static int g_use_wide = 0;         // hh_set_wide(2): canonical wide nodes with distance sort (closest_hit_wide_global); hh_set_wide(1): traverse the 4-wide octant-sorted nodes like k_render_persistent<.., kWide>
 static int g_seq_postpone = 0;   // hh_set_oct(1): traverse octant-mirrored node copies like k_render_persistent<.., kOct=true>
@@ -200,7 +201,7 @@ static void build(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pad_
         B.geom[i] = node_f4{p.cx, p.cy, p.cz, p.r};
         B.mat[i] = p.type == 2 ? dielectric_mat(p.fuzz_or_ir) : node_f4{p.ax, p.ay, p.az, p.fuzz_or_ir};
         B.type[i] = (uint8_t)p.type;
-        const float pad = fabsf(p.r) * (1.0f + pad_rel) + 1e-6f;
+        const float pad = vn::leaf_pad(p.cx, p.cy, p.cz, p.r, pad_rel);
         llo[i] = f4{p.cx - pad, p.cy - pad, p.cz - pad, 0};
         lhi[i] = f4{p.cx + pad, p.cy + pad, p.cz + pad, 0};
     }
@@ -231,7 +232,7 @@ static void build(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pad_
             B.geom[i] = node_f4{p.cx, p.cy, p.cz, p.r};
             B.mat[i] = p.type == 2 ? dielectric_mat(p.fuzz_or_ir) : node_f4{p.ax, p.ay, p.az, p.fuzz_or_ir};
             B.type[i] = (uint8_t)p.type;
-            const float pad = fabsf(p.r) * (1.0f + pad_rel) + 1e-6f;
+            const float pad = vn::leaf_pad(p.cx, p.cy, p.cz, p.r, pad_rel);
             llo[i] = f4{p.cx - pad, p.cy - pad, p.cz - pad, 0};
             lhi[i] = f4{p.cx + pad, p.cy + pad, p.cz + pad, 0};
         }
@@ -301,7 +302,7 @@ static void build(const hh_sphere* s, uint32_t n, uint32_t leaf_size, float pad_
 template <bool kCount>
 static inline void hh_closest(const HostBvh& B, f3 o, f3 d, float& t, int& prim, TraceCounters& cnt) {
     if (g_use_grid && B.grid_ok) closest_hit_grid<kCount>(B.grid, B.grid_start.data(), B.grid_refs.data(), B.geom.data(), o, d, t, prim, cnt);
-    else if (g_use_wide == 2 && B.wide_levels <= kWideGlobalMaxLevels && B.huge.n == 0) closest_hit_wide_global<kCount>(B.wide.data(), B.geom.data(), B.wide_root, o, d, t, prim, cnt);
+    else if (g_use_wide == 2 && B.wide_levels <= kWideGlobalMaxLevels && B.huge.n == 0) closest_hit_wide_global<kCount>(B.wide.data(), B.geom.data(), B.wide_root, o, d, t, prim, cnt, kTMax, -1, g_gate != 0);
     else if (g_use_wide && B.wide_levels <= kWideMaxLevels && !B.wide_oct.empty()) {
         float t0 = kTMax; int prim0 = -1;
         const float a = dot(d, d), inv_a = rcp(a);
@@ -313,13 +314,14 @@ static inline void hh_closest(const HostBvh& B, f3 o, f3 d, float& t, int& prim,
         }
         closest_hit_wide<kCount>(B.wide_oct.data(), (uint32_t)(B.wide_oct.size() / 8), B.geom.data(), B.wide_root, o, d, t, prim, cnt, t0, prim0);
     }
-    else if (g_use_oct) closest_hit<kCount, true>(B.nodes_oct.data(), B.geom.data(), B.root_link, o, d, t, prim, cnt, (uint32_t)B.nodes.size());
-    else closest_hit<kCount, false>(B.nodes.data(), B.geom.data(), B.root_link, o, d, t, prim, cnt);
+    else if (g_use_oct) closest_hit<kCount, true>(B.nodes_oct.data(), B.geom.data(), B.root_link, o, d, t, prim, cnt, (uint32_t)B.nodes.size(), g_gate != 0);
+    else closest_hit<kCount, false>(B.nodes.data(), B.geom.data(), B.root_link, o, d, t, prim, cnt, 0u, g_gate != 0);
 }
 
 extern "C" {
 
 void hh_set_oct(int on) { g_use_oct = on; }
+void hh_set_gate(int on) { g_gate = on; }
 void hh_set_wide(int on) { g_use_wide = on; }
 void hh_set_grid(int on) { g_use_grid = on; }
 // huge list of the host build (sorted sphere indices)

@@ -40,6 +40,7 @@ class ref_params(C.Structure):
 ATTEN_UNWIND, ATTEN_FORWARD = 0, 1
 DRAW_XYZ, DRAW_ZYX = 0, 1
 CLOSEST_BRUTE, CLOSEST_BVH = 0, 1
+CLOSEST_GATE = 2        # flag: hit-point gate (oracle.cpp::hit_gate), what the product applies to scenes traversed from L2 / HBM
 
 _lib = None
 _ref = None
@@ -179,12 +180,12 @@ class Oracle:
         self.o.orc_render_mean(self.h, C.byref(p), _p(px), n, _p(mean), _p(ps), C.byref(st))
         return (mean, st, ps) if per_sample else (mean, st)
 
-    def closest_hit(self, origins, dirs, use_bvh=False):
+    def closest_hit(self, origins, dirs, use_bvh=False, gate=False):
         o = np.ascontiguousarray(origins, np.float32)
         d = np.ascontiguousarray(dirs, np.float32)
         t = np.zeros(len(o), np.float32)
         prim = np.zeros(len(o), np.int32)
-        self.o.orc_closest_hit(self.h, int(use_bvh), _p(o), _p(d), len(o), _p(t), _p(prim))
+        self.o.orc_closest_hit(self.h, int(bool(use_bvh)) | (CLOSEST_GATE if gate else 0), _p(o), _p(d), len(o), _p(t), _p(prim))
         return t, prim
 
 

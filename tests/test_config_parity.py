@@ -5,9 +5,13 @@ compares a seeded sample of it -- 64 tiles of 32x32 pixels, the very list bench.
 with Oracle.render_mean(pixels=...), the CPU restatement of RayTracer.cu:163-217 for exactly those pixels.  Pixels are independent
 (the seed is tea<4>(pixel, subframe), RayTracer.cu:169), so the sample is as strict per pixel as the full frame.
 
-Bars: RTIOW frames (configs[1], [2]) bit-identical accumulation buffer; the synthetic scenes (configs[3], [4]) bit-identical too
-since the per-sphere box gate made the closest hit a function of (ray, sphere) alone -- the test prints the
-budget it measured (mismatching pixels, worst relative error) and fails on any mismatch above the stated budget."""
+Bars: bit-identical accumulation buffer on every config.  The synthetic scenes (configs[3], [4]) are seen from 100-750 units away,
+where the float quadratic of RayTracer.cu:239-253 is dominated by rounding noise (its discriminant carries an absolute error of
+~1e-7 |o - c|^2, the size of r^2): rays that miss a sphere by up to half its radius can "hit" it, and which of those phantom hits are
+reported would depend on the boxes of whatever BVH sits in front of the intersection test (measured before the gate existed: 0.4 % of
+the pixels of configs[3] and 12 % of configs[4] differed between the LBVH and the oracle's BVH).  The hit-point gate (DESIGN.md section 4:
+a root only counts when its hit point lies inside the sphere's slightly grown box) makes the closest hit a function of (ray, sphere)
+alone; oracle (ORC_CLOSEST_GATE) and kernels apply it, and the tests below demand zero mismatching pixels."""
 import os
 import sys
 
@@ -45,14 +49,17 @@ def _scene_and_camera(workload, oracle_mod):
     return width, height, spp, depth, spheres, cam
 
 
-def _compare(acc, want, px, width, name, budget_pixels):
+def _compare(acc, want, px, width, name, budget_frac):
     got = acc.reshape(-1, 4)[px]
     ref = want.reshape(-1, 4)[px]
     bad = (got.view(np.uint32) != ref.view(np.uint32)).any(axis=-1)
-    rel = np.abs(got[:, :3] - ref[:, :3]) / np.maximum(np.abs(ref[:, :3]), 1e-3)
-    print("%s: %d sampled pixels, %d differ from the oracle (budget %d), worst relative error %.3g"
-          % (name, len(px), int(bad.sum()), budget_pixels, float(rel.max()) if len(rel) else 0.0))
+    budget_pixels = int(budget_frac * len(px))
+    mean_rel = float(np.abs(got[:, :3].astype(np.float64).mean(axis=0) - ref[:, :3].astype(np.float64).mean(axis=0)).max() /
+                     max(float(ref[:, :3].astype(np.float64).mean()), 1e-9))
+    print("%s: %d sampled pixels, %d differ from the oracle (%.3f %%, budget %d), mean radiance of the sample differs by %.2e relative"
+          % (name, len(px), int(bad.sum()), 100.0 * bad.mean(), budget_pixels, mean_rel))
     assert int(bad.sum()) <= budget_pixels, "%s: %d pixels differ from the oracle (first: pixel %d)" % (name, int(bad.sum()), int(px[np.argmax(bad)]))
+    assert mean_rel < 1e-3
     return bad
 
 
@@ -74,7 +81,7 @@ def test_rtiow_full_size_frames_match_oracle_on_sampled_tiles(dctx, oracle_mod, 
         assert dctx.last_accel() == 2                               # wide nodes from shared memory: the headline kernel
         acc = dctx.read_accum()
         want, ost = orc.render_mean(orc.params(ocam, width, height, spp, sub, depth, atten=oracle_mod.ATTEN_FORWARD), pixels=px)
-        _compare(acc, want, px, width, "%s subframe %d" % (workload, sub), 0)
+        _compare(acc, want, px, width, "%s subframe %d" % (workload, sub), 0.0)
         _, wimg = oracle_mod.accumulate_tonemap(None, want, False, 1.0)
         d = np.abs(img.reshape(-1, 4)[px].astype(np.int32) - wimg.reshape(-1, 4)[px].astype(np.int32))
         assert d.max() <= 1 and (d > 0).mean() < 2e-3               # device powf vs glibc powf: one code value
@@ -86,14 +93,14 @@ def test_rtiow_full_size_frames_match_oracle_on_sampled_tiles(dctx, oracle_mod, 
             dctx.render(dctx.make_params(cam, width, height, spp, k + 1, depth, accum_count=k, flags=VN_NO_TONEMAP))
             mean, _ = orc.render_mean(orc.params(ocam, width, height, spp, k + 1, depth, atten=oracle_mod.ATTEN_FORWARD), pixels=px)
             want_acc, _ = oracle_mod.accumulate_tonemap(want_acc, mean, k > 0, np.float32(1.0) / np.float32(k + 1))
-        _compare(dctx.read_accum(), want_acc, px, width, "c2 progressive x3", 0)
+        _compare(dctx.read_accum(), want_acc, px, width, "c2 progressive x3", 0.0)
 
 
-@pytest.mark.parametrize("workload,n_px,budget", [("c4", 0, 0), ("c5", 2048, 0)])
+@pytest.mark.parametrize("workload,n_px,budget", [("c4", 0, 0.0), ("c5", 8192, 0.0)])
 def test_synthetic_scenes_full_size_match_oracle(dctx, oracle_mod, workload, n_px, budget):
     """configs[3] (1 M spheres, 80/15/5 mix, depth 50) and configs[4] (16 M spheres, 50 % glass, depth 64) at 1920x1080, 16 spp,
     default options: nodes and spheres are traversed from L2 / HBM.  configs[3] is compared on the 64 sampled tiles, configs[4]
-    on 2048 seeded pixels (the oracle's own BVH over 16 M spheres takes half a minute to build)."""
+    on 8192 seeded pixels (the oracle's own BVH over 16 M spheres takes half a minute to build)."""
     width, height, spp, depth, spheres, cam = _scene_and_camera(workload, oracle_mod)
     dctx.set_spheres(spheres)
     dctx.build_bvh()
@@ -104,7 +111,7 @@ def test_synthetic_scenes_full_size_match_oracle(dctx, oracle_mod, workload, n_p
     acc = dctx.read_accum()
     assert st.paths == width * height * spp and np.isfinite(acc).all()
     orc = oracle_mod.Oracle(spheres)
-    want, ost = orc.render_mean(orc.params(cam.frame(), width, height, spp, 1, depth, atten=oracle_mod.ATTEN_FORWARD, closest=oracle_mod.CLOSEST_BVH), pixels=px)
+    want, ost = orc.render_mean(orc.params(cam.frame(), width, height, spp, 1, depth, atten=oracle_mod.ATTEN_FORWARD, closest=oracle_mod.CLOSEST_BVH | oracle_mod.CLOSEST_GATE), pixels=px)
     print("%s: GPU %.2f segments/path over the frame, oracle %.2f over the sample; GPU %.1f node steps, %.2f sphere tests per segment"
           % (workload, st.segments / st.paths, ost.segments / ost.paths, st.node_visits / st.segments, st.sphere_tests / st.segments))
     _compare(acc, want, px, width, workload, budget)

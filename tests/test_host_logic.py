@@ -556,3 +556,57 @@ def test_grid_invariants_and_traversal_on_cpu(host_harness, oracle_mod, rtiow):
         host_harness.hh_set_grid(0)
         host_harness.hh_set_wide(0)
     assert steps[1] < 0.5 * steps[0]
+
+
+def test_hit_gate_makes_the_closest_hit_independent_of_the_bvh(host_harness, oracle_mod):
+    """The hit-point gate.  Rays that start 250-750 units from spheres of radius 0.1-0.3 -- configs[4]'s geometry, where
+    the float quadratic of RayTracer.cu:239-253 is mostly rounding noise: WITHOUT the gate brute force, the oracle's BVH and the product's
+    LBVH (run here on the CPU, exact math) disagree on which phantom hits they report; WITH it all three agree bit for bit, for pair
+    nodes, octant-mirrored pairs and the canonical wide nodes, with the default pad and with 10 % boxes."""
+    spheres = np.ascontiguousarray(oracle_mod.random_scene(3000, 0x5EED0002, 4.0, 1))
+    rng = np.random.RandomState(5)
+    n = 60000
+    o = np.zeros((n, 3), np.float32)
+    o[:, 2] = np.float32(500.0)
+    o[:, :2] = (rng.rand(n, 2).astype(np.float32) - np.float32(0.5)) * np.float32(2.0)
+    tgt = (rng.rand(n, 3).astype(np.float32) - np.float32(0.5)) * np.float32(8.0)
+    d = (tgt - o).astype(np.float32)
+    orc = oracle_mod.Oracle(spheres)
+    tb, pb = orc.closest_hit(o, d, use_bvh=False, gate=True)
+    tv, pv = orc.closest_hit(o, d, use_bvh=True, gate=True)
+    assert np.array_equal(tb, tv) and np.array_equal(pb, pv)
+    tu, pu = orc.closest_hit(o, d, use_bvh=False, gate=False)
+    phantom = int(((pu != pb) | (tu != tb)).sum())
+    print("far rays: %d of %d hits change when the gate is applied" % (phantom, int((pu >= 0).sum())))
+    assert phantom > 50 and (pb >= 0).sum() > 1000          # the regime really is noise-dominated, and there still are hits
+    sp, op, dp = spheres.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p)
+    host_harness.hh_set_gate(1)
+    try:
+        for oct_, wide, pad in ((0, 0, 0.01), (1, 0, 0.01), (0, 2, 0.01), (0, 0, 0.10)):
+            host_harness.hh_set_oct(oct_)
+            host_harness.hh_set_wide(wide)
+            t1, p1 = np.zeros(n, np.float32), np.zeros(n, np.int32)
+            host_harness.hh_closest_hit(sp, len(spheres), 2, C.c_float(pad), op, dp, n, t1.ctypes.data_as(C.c_void_p), p1.ctypes.data_as(C.c_void_p), None, None)
+            assert np.array_equal(tb, t1) and np.array_equal(pb, p1), (oct_, wide, pad, int((pb != p1).sum()))
+        host_harness.hh_set_oct(0)
+        host_harness.hh_set_wide(0)
+        host_harness.hh_set_gate(0)
+        t2, p2 = np.zeros(n, np.float32), np.zeros(n, np.int32)
+        host_harness.hh_closest_hit(sp, len(spheres), 2, C.c_float(0.01), op, dp, n, t2.ctypes.data_as(C.c_void_p), p2.ctypes.data_as(C.c_void_p), None, None)
+        assert not (np.array_equal(tu, t2) and np.array_equal(pu, p2))     # ... which is what the gate is for
+    finally:
+        host_harness.hh_set_gate(0)
+        host_harness.hh_set_oct(0)
+        host_harness.hh_set_wide(0)
+
+
+def test_hit_gate_never_fires_on_the_rtiow_scene(oracle_mod, rtiow):
+    """The headline kernel (shared-memory wide nodes) does not spend instructions on the gate: on scenes of that scale it is a no-op.
+    Whole C1 frame (400x225, 10 spp, depth 50 = 2.6 M segments): gated and ungated oracle are bit-identical, and so are the golden
+    frames produced by the reference's own RayTracer.cu (tests/test_oracle.py runs ungated)."""
+    W, H = 400, 225
+    cam = oracle_mod.rtiow_camera(W, H)
+    orc = oracle_mod.Oracle(rtiow)
+    a, sa = orc.render_mean(orc.params(cam, W, H, 10, 1, 50, atten=oracle_mod.ATTEN_FORWARD, closest=oracle_mod.CLOSEST_BVH))
+    b, sb = orc.render_mean(orc.params(cam, W, H, 10, 1, 50, atten=oracle_mod.ATTEN_FORWARD, closest=oracle_mod.CLOSEST_BVH | oracle_mod.CLOSEST_GATE))
+    assert sa.segments == sb.segments and np.array_equal(a.view(np.uint32), b.view(np.uint32))

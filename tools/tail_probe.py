@@ -17,10 +17,7 @@ def main():
         for rep in range(3):
             ctx.render(ctx.make_params(cam, W, H, 16, 1 + rep, 50, flags=VN_COUNTERS | VN_NO_TONEMAP))
             st = ctx.stats()
-            raw = (C.c_uint64 * 14)()
-            ctx._check(ctx.lib.vn_read_sched_counters(ctx.h, raw), "vn_read_sched_counters")
-            M = (1 << 64) - 1
-            start, exhaust, end = M - raw[0], M - raw[1], raw[2]
+            start, exhaust, end = ctx.launch_timeline()
             print("%dx%d launch %d: ms_render %.3f | kernel %.3f ms, tickets exhausted at %.3f ms (%.1f %%), drain %.3f ms"
                   % (W, H, rep, st.ms_render, (end - start) / 1e6, (exhaust - start) / 1e6, 100.0 * (exhaust - start) / (end - start),
                      (end - exhaust) / 1e6))

@@ -49,8 +49,8 @@ class vn_node32(C.Structure):
 VN_OK = 0
 VN_LAMBERTIAN, VN_METAL, VN_DIELECTRIC = 0, 1, 2
 VN_EXACT, VN_IMAGE_HOST, VN_ACCUM_SUM, VN_NO_TONEMAP = 1 << 0, 1 << 1, 1 << 2, 1 << 3
-VN_WAVEFRONT, VN_COUNTERS, VN_ASYNC, VN_FAST, VN_POOL = 1 << 4, 1 << 5, 1 << 6, 1 << 7, 1 << 8
-VN_SLOTS, VN_PERSISTENT, VN_GRID = 1 << 9, 1 << 10, 1 << 11
+VN_WAVEFRONT, VN_COUNTERS, VN_ASYNC, VN_FAST = 1 << 4, 1 << 5, 1 << 6, 1 << 7
+VN_GRID = 1 << 11
 
 # name -> (restype, argtypes); must list every VN_API symbol of include/venusaur_b200.h (checked by tests)
 _P = C.POINTER
@@ -83,6 +83,27 @@ SIGNATURES = {
     "vn_set_accum_external": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vn_reduce_tonemap_peers": (C.c_int, [C.c_void_p, _P(C.c_void_p), C.c_uint32, C.c_float, C.c_uint32, C.c_uint32,
                                           C.c_void_p, C.c_uint32]),
+    "vn_reduce_tonemap_peers_to": (C.c_int, [C.c_void_p, _P(C.c_void_p), C.c_uint32, C.c_float, C.c_uint32, C.c_uint32,
+                                             C.c_void_p, C.c_void_p, C.c_uint32]),
+    "vn_sync_flags": (C.c_int, [C.c_void_p, _P(C.c_void_p)]),
+    "vn_signal": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "vn_wait_flags": (C.c_int, [C.c_void_p, _P(C.c_void_p), C.c_uint32, C.c_uint32]),
+    "vn_check_flags": (C.c_int, [C.c_void_p]),
+    "vn_reduce_tonemap_peers_wait": (C.c_int, [C.c_void_p, _P(C.c_void_p), C.c_uint32, C.c_float, C.c_uint32, C.c_uint32,
+                                               C.c_void_p, C.c_void_p, _P(C.c_void_p), C.c_uint32, C.c_uint32]),
+    "vn_multi_create": (C.c_int, [_P(C.c_int), C.c_int, _P(C.c_void_p)]),
+    "vn_multi_destroy": (None, [C.c_void_p]),
+    "vn_multi_last_error": (C.c_char_p, [C.c_void_p]),
+    "vn_multi_device_count": (C.c_int, [C.c_void_p]),
+    "vn_multi_device": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "vn_multi_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
+    "vn_multi_set_spheres": (C.c_int, [C.c_void_p, _P(vn_sphere), C.c_uint64]),
+    "vn_multi_build_bvh": (C.c_int, [C.c_void_p]),
+    "vn_multi_render": (C.c_int, [C.c_void_p, _P(vn_params), C.c_uint32]),
+    "vn_multi_synchronize": (C.c_int, [C.c_void_p]),
+    "vn_multi_read_accum": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "vn_multi_get_stats": (C.c_int, [C.c_void_p, _P(vn_stats)]),
+    "vn_multi_subframes_accumulated": (C.c_uint32, [C.c_void_p]),
     "vn_buffer_alloc": (C.c_int, [C.c_int, C.c_uint64, C.c_int, _P(C.c_void_p), _P(C.c_void_p)]),
     "vn_buffer_free": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
     "vn_buffer_copy_to_host": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_uint64]),

@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib as L
-from ._lib import (VN_ACCUM_SUM, VN_ASYNC, VN_COUNTERS, VN_DIELECTRIC, VN_EXACT, VN_FAST, VN_IMAGE_HOST, VN_POOL, VN_SLOTS, VN_PERSISTENT, VN_GRID, VN_LAMBERTIAN,  # noqa: F401
+from ._lib import (VN_ACCUM_SUM, VN_ASYNC, VN_COUNTERS, VN_DIELECTRIC, VN_EXACT, VN_FAST, VN_IMAGE_HOST, VN_GRID, VN_LAMBERTIAN,  # noqa: F401
                    VN_METAL, VN_NO_TONEMAP, VN_WAVEFRONT, vn_bvh_info, vn_node32, vn_params, vn_sphere, vn_stats)
 
 SPHERE_DTYPE = np.dtype([("cx", "f4"), ("cy", "f4"), ("cz", "f4"), ("r", "f4"), ("ax", "f4"), ("ay", "f4"),
@@ -239,12 +239,12 @@ class Context:
     def synchronize(self):
         self._check(self.lib.vn_synchronize(self.h), "vn_synchronize")
 
-    def sched_counters(self) -> dict:
-        """Per warp-wide operation of the slot kernel: (times it ran, mean lanes taking part); needs VN_SLOTS | VN_COUNTERS."""
+    def launch_timeline(self):
+        """(start, tickets exhausted, end) of the last VN_COUNTERS launch in %globaltimer nanoseconds (vn_read_sched_counters)."""
         raw = (C.c_uint64 * 14)()
         self._check(self.lib.vn_read_sched_counters(self.h, raw), "vn_read_sched_counters")
-        names = ["node", "leaf", "retire_fetch", "shade_opaque", "shade_dielectric", "shade_miss", "camera"]
-        return {n: (int(raw[2 * i]), (raw[2 * i + 1] / raw[2 * i]) if raw[2 * i] else 0.0) for i, n in enumerate(names)}
+        M = (1 << 64) - 1
+        return M - raw[0], M - raw[1], raw[2]
 
     def stats(self) -> vn_stats:
         s = vn_stats()
@@ -276,6 +276,27 @@ class Context:
         arr = (C.c_void_p * len(peer_ptrs))(*peer_ptrs)
         self._check(self.lib.vn_reduce_tonemap_peers(self.h, arr, len(peer_ptrs), scale, rows[0], rows[1], image, flags),
                     "vn_reduce_tonemap_peers")
+
+    def reduce_tonemap_peers_wait(self, peer_ptrs, scale: float, rows, sum_out, image, peer_flags, wait_value: int, flags: int = 0):
+        arr = (C.c_void_p * len(peer_ptrs))(*peer_ptrs)
+        fl = (C.c_void_p * len(peer_flags))(*peer_flags)
+        self._check(self.lib.vn_reduce_tonemap_peers_wait(self.h, arr, len(peer_ptrs), scale, rows[0], rows[1], sum_out, image, fl, wait_value, flags),
+                    "vn_reduce_tonemap_peers_wait")
+
+    def sync_flags(self) -> int:
+        p = C.c_void_p()
+        self._check(self.lib.vn_sync_flags(self.h, C.byref(p)), "vn_sync_flags")
+        return p.value
+
+    def signal(self, index: int, value: int):
+        self._check(self.lib.vn_signal(self.h, index, value), "vn_signal")
+
+    def wait_flags(self, flag_ptrs, value: int):
+        arr = (C.c_void_p * len(flag_ptrs))(*flag_ptrs)
+        self._check(self.lib.vn_wait_flags(self.h, arr, len(flag_ptrs), value), "vn_wait_flags")
+
+    def check_flags(self):
+        self._check(self.lib.vn_check_flags(self.h), "vn_check_flags")
 
     def ipc_export(self, dev_ptr) -> bytes:
         buf = (C.c_ubyte * 64)()
@@ -336,6 +357,69 @@ class Context:
         self._check(self.lib.vn_test_scatter(self.h, material_type, m, _ptr(d), _ptr(nr), _ptr(fr), _ptr(sd), n,
                                              _ptr(dout), _ptr(ok), _ptr(sout), flags), "vn_test_scatter")
         return dout, ok, sout
+
+
+class MultiContext:
+    """vn_multi_*: one host thread, several devices (include/venusaur_b200.h).  Scene and BVH replicated, the subframes of a frame
+    dealt round-robin to the devices, one fused peer reduce + tonemap per frame into the image on devices[0]."""
+
+    def __init__(self, devices):
+        self.lib = L.load()
+        self.devices = [int(d) for d in devices]
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        h = C.c_void_p()
+        rc = self.lib.vn_multi_create(arr, len(self.devices), C.byref(h))
+        if rc != 0:
+            raise Exception("vn_multi_create failed (%d): %s" % (rc, self.lib.vn_multi_last_error(None).decode()))
+        self.h = h
+        self.width = self.height = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vn_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except BaseException:  # noqa: BLE001
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise Exception("%s failed (%d): %s" % (what, rc, self.lib.vn_multi_last_error(self.h).decode()))
+
+    def set_option(self, name: str, value: float):
+        self._check(self.lib.vn_multi_set_option(self.h, name.encode(), float(value)), "vn_multi_set_option")
+
+    def set_spheres(self, spheres: np.ndarray):
+        s = np.ascontiguousarray(spheres, SPHERE_DTYPE)
+        self._check(self.lib.vn_multi_set_spheres(self.h, s.ctypes.data_as(C.POINTER(vn_sphere)), len(s)), "vn_multi_set_spheres")
+
+    def build_bvh(self):
+        self._check(self.lib.vn_multi_build_bvh(self.h), "vn_multi_build_bvh")
+
+    make_params = Context.make_params
+
+    def render(self, params: vn_params, n_subframes: int):
+        self._check(self.lib.vn_multi_render(self.h, C.byref(params), n_subframes), "vn_multi_render")
+        self.width, self.height = params.width, params.height
+
+    def synchronize(self):
+        self._check(self.lib.vn_multi_synchronize(self.h), "vn_multi_synchronize")
+
+    def read_accum(self) -> np.ndarray:
+        out = np.zeros((self.height, self.width, 4), np.float32)
+        self._check(self.lib.vn_multi_read_accum(self.h, _ptr(out)), "vn_multi_read_accum")
+        return out
+
+    def stats(self) -> vn_stats:
+        s = vn_stats()
+        self._check(self.lib.vn_multi_get_stats(self.h, C.byref(s)), "vn_multi_get_stats")
+        return s
+
+    def subframes_accumulated(self) -> int:
+        return int(self.lib.vn_multi_subframes_accumulated(self.h))
 
 
 # ---------------------------------------------------------------- drop-in classes
@@ -417,6 +501,9 @@ class Renderer:
 
     def __init__(self, device: int = 0):
         self.m_device = device
+        self.m_devices: list[int] | None = None      # SetDevices: several devices behind the same Init / Draw / Cleanup
+        self.m_subframes_per_draw = 1
+        self.mctx: MultiContext | None = None
         self.ctx: Context | None = None
         self.m_samplesPerPixel = 16     # Renderer.h:53
         self.m_maxDepth = 4             # RayTracer.cu:172
@@ -426,14 +513,44 @@ class Renderer:
         self._size = (0, 0)
         self.strict_accum = False       # True: literal blend weights of RayTracer.cu:208-213
 
+    def SetDevices(self, devices, subframes_per_draw: int = 0):
+        """Extension (not in the reference): render on several devices.  One Draw then advances the progressive render by
+        `subframes_per_draw` subframes (default: one per device), i.e. it delivers the image a single device has after that many
+        Draw calls -- up to float re-association, see vn_multi_render."""
+        if self.ctx is not None or self.mctx is not None:
+            raise Exception("Renderer::SetDevices must be called before Init")
+        self.m_devices = [int(d) for d in devices]
+        self.m_subframes_per_draw = int(subframes_per_draw) if subframes_per_draw else len(self.m_devices)
+
     def Init(self, scene: Scene, ptxSource: str = ""):
+        if self.m_devices is not None:
+            if self.mctx is None:
+                self.mctx = MultiContext(self.m_devices)
+            self.mctx.set_spheres(scene.m_spheres)
+            self.mctx.build_bvh()
+            self.m_subframe_index = self.m_accumulated = 0
+            return
         if self.ctx is None:
             self.ctx = Context(self.m_device)
         self.ctx.set_spheres(scene.m_spheres)
         self.ctx.build_bvh()
         self.m_subframe_index = self.m_accumulated = 0
 
+    def _draw_multi(self, camera: Camera, outputBuffer: CUDAOutputBuffer):
+        size = (outputBuffer.width(), outputBuffer.height())
+        if camera.Changed() or size != self._size:
+            self._size = size
+            self.m_subframe_index = self.m_accumulated = 0
+        k = self.m_subframes_per_draw
+        p = self.mctx.make_params(camera, size[0], size[1], self.m_samplesPerPixel, self.m_subframe_index + 1, self.m_maxDepth,
+                                  accum_count=self.m_accumulated, image=outputBuffer.map(), flags=self.m_flags)
+        self.mctx.render(p, k)                       # synchronous: the frame is in the buffer (on devices[0]) when it returns
+        self.m_subframe_index += k
+        self.m_accumulated += k
+
     def Draw(self, camera: Camera, outputBuffer: CUDAOutputBuffer):
+        if self.mctx is not None:
+            return self._draw_multi(camera, outputBuffer)
         if self.ctx is None:
             raise Exception("Renderer::Draw called before Init")
         size = (outputBuffer.width(), outputBuffer.height())
@@ -459,4 +576,7 @@ class Renderer:
         if self.ctx is not None:
             self.ctx.close()
             self.ctx = None
+        if self.mctx is not None:
+            self.mctx.close()
+            self.mctx = None
         self._size = (0, 0)

@@ -3,8 +3,8 @@
     python -m venusaur_b200.build [--force]
 
 nvcc cross-compiles without a GPU.  path_kernels.cu and wavefront.cu are compiled twice:
-  exact : -DVN_EXACT=1 -fmad=false           (IEEE, bit-identical to the oracle)
-  fast  : -DVN_EXACT=0 -fmad=true -ftz=true  (the benchmarked build)
+  exact : -DVN_EXACT=1 -fmad=false           (IEEE, bit-identical to the oracle: the default and the benchmarked build)
+  fast  : -DVN_EXACT=0 -fmad=true -ftz=true  (opt-in VN_FAST: relaxed numerics, not within the image tolerance)
 lbvh.cu is compiled with -fmad=false so Morton quantisation is reproducible on the host.
 """
 from __future__ import annotations
@@ -26,16 +26,13 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=o
 UNITS = [
     # (source, object, extra flags)
     ("vn_api.cu", "vn_api.o", []),
+    ("vn_multi.cu", "vn_multi.o", []),
     ("lbvh.cu", "lbvh.o", ["-fmad=false"]),
     ("grid.cu", "grid.o", ["-fmad=false"]),
     ("path_kernels.cu", "path_exact.o", ["-DVN_EXACT=1", "-fmad=false"]),
     ("path_kernels.cu", "path_fast.o", ["-DVN_EXACT=0", "-fmad=true", "-ftz=true"]),
     ("wavefront.cu", "wavefront_exact.o", ["-DVN_EXACT=1", "-fmad=false"]),
     ("wavefront.cu", "wavefront_fast.o", ["-DVN_EXACT=0", "-fmad=true", "-ftz=true"]),
-    ("pool_kernels.cu", "pool_exact.o", ["-DVN_EXACT=1", "-fmad=false"]),
-    ("pool_kernels.cu", "pool_fast.o", ["-DVN_EXACT=0", "-fmad=true", "-ftz=true"]),
-    ("slot_kernels.cu", "slot_exact.o", ["-DVN_EXACT=1", "-fmad=false"]),
-    ("slot_kernels.cu", "slot_fast.o", ["-DVN_EXACT=0", "-fmad=true", "-ftz=true"]),
 ]
 
 

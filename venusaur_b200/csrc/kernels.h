@@ -46,6 +46,7 @@ struct RenderLaunch {
     const uint32_t* tile_order;      // ticket >> 5 -> tile index, most expensive tiles first (null = row-major); see vn_api.cu::prepare_tile_order
     uint32_t* tile_cost;             // when non-null the kernel records every finished pixel's ray segments in its tile's entries:
     uint32_t tile_cost_stride;       //   tile_cost[tile] += segments, tile_cost[tile_cost_stride + tile] = max(.., segments)
+    uint32_t gate;                   // 1: the pair-node / L2-HBM traversals apply the hit-point gate (vn_math.cuh::hit_gate_ok); the shared-memory wide-node kernels ignore it
     uint32_t tiles_x_inv;            // floor(2^32 / tiles_x): tile / tiles_x = __umulhi(tile, tiles_x_inv) plus at most two corrections (tile_row_col)
 };
 
@@ -72,9 +73,6 @@ struct KernelConfig {
     bool warp_tiles = false;         // phase form only: warps own whole 8x4 tiles (one ticket per tile) instead of lanes taking single pixels
     bool lean = false;               // k_render_lean: the phase form with warp-owned tiles, 16-bit links and no per-lane statistics (path_kernels.cu)
 };
-
-// Vote thresholds of the slot-scheduled kernel (slot_kernels.cu): an operation runs when that many lanes wait for it.
-struct SlotTune { uint32_t node_threshold, leaf_threshold, switch_threshold, shade_threshold, regen_threshold; };
 
 size_t scene_smem_bytes(uint32_t num_nodes, uint32_t num_spheres, uint32_t node_copies = 1);
 size_t wide_smem_bytes(uint32_t num_wide, uint32_t num_spheres);
@@ -114,7 +112,10 @@ constexpr int kWfArraysTotal = 2 * kWfStateArrays + 2 + 4;   // 4-byte arrays of
     cudaError_t launch_tonemap(const float4* accum, float scale, uint32_t* image, uint64_t n, cudaStream_t stream);    \
     cudaError_t launch_tile_keys(const uint32_t* cost, uint32_t stride, uint32_t n, uint32_t mode, uint32_t* keys, uint32_t* vals, cudaStream_t stream); \
     cudaError_t launch_reduce_tonemap_peers(const float4* const* peers, uint32_t n_peers, float scale, uint64_t begin, \
-                                            uint64_t end, float4* accum_out, uint32_t* image, cudaStream_t stream);    \
+                                            uint64_t end, float4* accum_out, uint32_t* image, const uint32_t* const* peer_flags, \
+                                            uint32_t wait_value, uint32_t* error, cudaStream_t stream);               \
+    cudaError_t launch_signal(uint32_t* flag, uint32_t value, cudaStream_t stream);                                    \
+    cudaError_t launch_wait_flags(const uint32_t* const* flags, uint32_t n, uint32_t value, uint32_t* error, cudaStream_t stream); \
     cudaError_t launch_test_rng(const uint32_t* v0, const uint32_t* v1, uint64_t n, uint32_t n_draws, uint32_t* seeds, \
                                 uint32_t* lcg_out, float* rnd_out, cudaStream_t stream);                               \
     cudaError_t launch_trace_rays(const RenderLaunch& scene, const float* o, const float* d, uint64_t n, float* t_out, \
@@ -125,15 +126,7 @@ constexpr int kWfArraysTotal = 2 * kWfStateArrays + 2 + 4;   // 4-byte arrays of
                                uint8_t* scattered, uint32_t* seeds_out, cudaStream_t stream);                          \
     cudaError_t launch_wavefront(const RenderLaunch& p, const WavefrontBuffers& wf, int num_sms, cudaStream_t stream,   \
                                  uint32_t* launches);                                                                  \
-    cudaError_t launch_accumulate_samples(const RenderLaunch& p, const float* sample_rgb, cudaStream_t stream);                \
-    size_t slot_smem_bytes(uint32_t num_wide, uint32_t num_spheres, int slots, int threads);                               \
-    bool slot_config_supported(int slots, int threads);                                                                    \
-    cudaError_t launch_render_slots(const RenderLaunch& p, float* sample_rgb, int slots, int threads, int blocks,           \
-                                    const SlotTune& tune, bool count, cudaStream_t stream);                                \
-    size_t pool_smem_bytes(uint32_t num_nodes, uint32_t num_spheres, bool scene_in_smem, int warps, uint32_t slots);    \
-    int pool_max_blocks_per_sm(bool scene_in_smem, int threads, size_t smem);                                          \
-    cudaError_t launch_render_pool(const RenderLaunch& p, bool scene_in_smem, int threads, int blocks, uint32_t slots,  \
-                                   uint32_t service_threshold, uint32_t leaf_batch, cudaStream_t stream);
+    cudaError_t launch_accumulate_samples(const RenderLaunch& p, const float* sample_rgb, cudaStream_t stream);
 
 namespace exact { VN_DECLARE_KERNEL_API }
 namespace fast { VN_DECLARE_KERNEL_API }

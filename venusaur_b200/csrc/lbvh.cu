@@ -93,9 +93,7 @@ __global__ void __launch_bounds__(kBlock) k_gather(const vn_sphere* __restrict__
     }
     type[i] = (uint8_t)p.type;
     orig[i] = src;
-    // |r| (sphere.h:17-28 computes fabsf(radius) and then forgets to use it) plus a pad that keeps the slab
-    // test conservative against float rounding in the sphere quadratic.
-    const float pad = fabsf(p.r) * (1.0f + pad_rel) + 1e-6f;
+    const float pad = leaf_pad(p.cx, p.cy, p.cz, p.r, pad_rel);       // lbvh_core.cuh
     leaf_lo[i] = f4{p.cx - pad, p.cy - pad, p.cz - pad, 0.0f};
     leaf_hi[i] = f4{p.cx + pad, p.cy + pad, p.cz + pad, 0.0f};
 }

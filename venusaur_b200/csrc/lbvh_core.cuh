@@ -48,6 +48,14 @@ VN_HD int karras_delta(const uint32_t* __restrict__ codes, int n, int i, int j) 
 
 constexpr uint32_t kChildLeaf = 0x80000000u;
 
+// Half-size of a sphere's leaf box: |r| (sphere.h:17-28 computes fabsf(radius) and then forgets to use it) grown by pad_rel
+// (default 1 %) + 1e-6 + 2^-17 of the coordinates' magnitude.  The slab tests of the traversal only have to be conservative, and they are
+// by this margin: the box contains the hit-point gate's box (vn_math.cuh::hit_gate_ok: 0.5 % + 2^-19 of the magnitude) with room for
+// the rounding of the slab test itself (a few 2^-23 of the distance travelled), at any scene scale.
+VN_HD float leaf_pad(float cx, float cy, float cz, float r, float pad_rel) {
+    return fabsf(r) * (1.0f + pad_rel) + 1e-6f + (fabsf(cx) + fabsf(cy) + fabsf(cz) + fabsf(r)) * 7.62939453125e-06f;
+}
+
 struct KarrasNode {
     uint32_t left, right;    // kChildLeaf | leaf index, or internal node index
     uint32_t first, last;    // covered range of sorted primitives (inclusive)

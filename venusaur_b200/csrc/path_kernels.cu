@@ -53,6 +53,12 @@ namespace VN_NS {
 
 namespace {
 
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 __device__ __forceinline__ uint32_t fetch_work(uint32_t* counter) {
     cg::coalesced_group g = cg::coalesced_threads();
     uint32_t base = 0;
@@ -174,7 +180,7 @@ __device__ __forceinline__ void closest_hit_grid_vote(const GridHeader& g, const
 template <bool kCount>
 __device__ __forceinline__ void closest_hit_wide_global_vote(const float4* __restrict__ wide, const float4* __restrict__ geom, uint32_t root_link,
                                                              uint32_t leaf_vote, f3 o, f3 d, float& t_out, int& prim_out, TraceCounters& cnt,
-                                                             float tbest0, int prim0) {
+                                                             float tbest0, int prim0, bool gate) {
     float tbest = tbest0;
     int prim = prim0;
     const f3 idir = slab_idir(d);
@@ -189,7 +195,7 @@ __device__ __forceinline__ void closest_hit_wide_global_vote(const float4* __res
         const unsigned act = __activemask();
         const unsigned lm = __ballot_sync(act, at_leaf);
         if (lm == act || (uint32_t)__popc(lm) >= leaf_vote) {
-            if (at_leaf) cur = leaf_step<kCount>(geom, cur, o, d, a, inv_a, tbest, prim, stack, sp, cnt);
+            if (at_leaf) cur = leaf_step<kCount>(geom, cur, o, d, a, inv_a, tbest, prim, stack, sp, cnt, gate);
         } else if (!at_leaf) {
             if (kCount) cnt.nodes += 1;
             cur = wide_global_step(wide, cur, idir, ood, tbest, stack, sp);
@@ -328,13 +334,13 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_persistent(const __grid_
                 }
             }
             if (!kSmem) {
-                if (p.leaf_vote) closest_hit_wide_global_vote<kCount>(p.wide, sc.geom, p.wide_root, p.leaf_vote, st.o, st.d, t, prim, cnt, t0, prim0);
-                else closest_hit_wide_global<kCount>(p.wide, sc.geom, p.wide_root, st.o, st.d, t, prim, cnt, t0, prim0);
+                if (p.leaf_vote) closest_hit_wide_global_vote<kCount>(p.wide, sc.geom, p.wide_root, p.leaf_vote, st.o, st.d, t, prim, cnt, t0, prim0, p.gate != 0u);
+                else closest_hit_wide_global<kCount>(p.wide, sc.geom, p.wide_root, st.o, st.d, t, prim, cnt, t0, prim0, p.gate != 0u);
             }
             else if (p.leaf_vote) closest_hit_wide_vote<kCount>(sc.nodes, node_f4s, sc.geom, p.wide_root, p.leaf_vote, st.o, st.d, t, prim, cnt, t0, prim0);
             else closest_hit_wide<kCount>(sc.nodes, node_f4s, sc.geom, p.wide_root, st.o, st.d, t, prim, cnt, t0, prim0);
         }
-        else closest_hit<kCount, kOct>(sc.nodes, sc.geom, sc.root_link, st.o, st.d, t, prim, cnt, node_f4s);
+        else closest_hit<kCount, kOct>(sc.nodes, sc.geom, sc.root_link, st.o, st.d, t, prim, cnt, node_f4s, p.gate != 0u);
         n_seg += 1u;
         if (kCount) { n_nodes += cnt.nodes; n_sph += cnt.spheres; cnt.nodes = 0; cnt.spheres = 0; }
         f3 result;
@@ -371,11 +377,6 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_persistent(const __grid_
 // bit-identical to k_render_persistent; only the order in which a warp's lanes take their turns differs (tools/simt_sim_async.cpp
 // is the model the thresholds came from).  Lanes that run out of pixels stay in the loop as zombies until the whole warp is done,
 // which keeps every vote a full-mask __ballot_sync.
-__device__ __forceinline__ unsigned long long global_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 
 template <bool kCount, int kMaxThreads, bool kPhase = false, bool kWarpTile = false>
 __global__ void __launch_bounds__(kMaxThreads) k_render_async(const __grid_constant__ RenderLaunch p) {
@@ -827,7 +828,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
                 if (nm == 0u || (uint32_t)__popc(lm) >= t_leaf) {
                     if (at_leaf) {
                         const float a = dot(st.d, st.d);
-                        leaf_test<kCount>(sc.geom, cur, st.o, st.d, a, rcp(a), tbest, prim, cnt);
+                        leaf_test<kCount>(sc.geom, cur, st.o, st.d, a, rcp(a), tbest, prim, cnt, p.gate != 0u);
                         cur = stack_pop32_dev(top, tos);
                     }
                 }
@@ -893,19 +894,53 @@ __global__ void __launch_bounds__(256) k_tonemap(const float4* __restrict__ accu
 }
 
 struct PeerList { const float4* p[kMaxPeers]; };
+struct FlagList { const uint32_t* f[kMaxPeers]; };
+
+// ---- device-side ordering between GPUs that belong to DIFFERENT processes (one process per GPU, buffers mapped through CUDA IPC): a
+// 32-bit epoch flag per rank in device memory.  k_signal publishes everything the stream has written so far (fence, then a release
+// store); a waiting kernel on another GPU polls the flag with acquire loads.  This replaces the two host barriers (NCCL all-reduces,
+// ~0.4 ms each on 8 GPUs) that used to bracket the once-per-frame reduce.  A poll gives up after kFlagTimeoutNs and reports through
+// *error, so that a peer that died cannot hang the others' GPUs.
+constexpr unsigned long long kFlagTimeoutNs = 4000000000ull;
+__global__ void k_signal(uint32_t* flag, uint32_t value) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+__device__ __forceinline__ bool wait_flags(const FlagList& flags, uint32_t n, uint32_t value, uint32_t* error) {
+    const unsigned long long t0 = global_ns();
+    for (uint32_t r = 0; r < n; r++) {
+        for (;;) {
+            uint32_t v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags.f[r]) : "memory");
+            if ((int32_t)(v - value) >= 0) break;                  // epochs only grow (wrap-safe compare)
+            if (global_ns() - t0 > kFlagTimeoutNs) { if (error) atomicExch(error, 1u + r); return false; }
+            __nanosleep(200);
+        }
+    }
+    return true;
+}
+__global__ void k_wait_flags(const FlagList flags, uint32_t n, uint32_t value, uint32_t* error) {
+    wait_flags(flags, n, value, error);
+}
 
 // Fused cross-GPU reduce + tonemap: each GPU owns a slice of pixels, loads that slice from every peer's partial-sum
 // buffer over NVLink (peer-mapped pointers), adds them in rank order (deterministic), writes the reduced float4
 // into its own accum and the uchar4 pixels into the image.  Replaces ncclReduce + a separate tonemap launch.
 __global__ void __launch_bounds__(256) k_reduce_tonemap_peers(const PeerList peers, uint32_t n_peers, float scale, uint64_t begin, uint64_t end,
-                                                             float4* __restrict__ accum_out, uint32_t* __restrict__ image) {
+                                                             float4* __restrict__ accum_out, uint32_t* __restrict__ image,
+                                                             const FlagList flags, uint32_t wait_value, uint32_t* error) {
+    if (wait_value) {
+        // every peer's partial sum must be complete before it is read: one thread per CTA polls the peers' epoch flags
+        if (threadIdx.x == 0) wait_flags(flags, n_peers, wait_value, error);
+        __syncthreads();
+    }
     for (uint64_t i = begin + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (uint64_t)gridDim.x * blockDim.x) {
         f3 s = mk3(0.0f);
         for (uint32_t r = 0; r < n_peers; r++) {
             const float4 a = __ldcg(&peers.p[r][i]);
             s = s + mk3(a.x, a.y, a.z);
         }
-        accum_out[i] = make_float4(s.x, s.y, s.z, 1.0f);
+        if (accum_out) accum_out[i] = make_float4(s.x, s.y, s.z, 1.0f);
         if (image) image[i] = make_color_u32(scale != 1.0f ? s * scale : s);
     }
 }
@@ -926,13 +961,13 @@ __global__ void k_test_rng(const uint32_t* __restrict__ v0, const uint32_t* __re
 
 __global__ void k_trace_rays(const float4* __restrict__ nodes, const float4* __restrict__ geom, uint32_t root_link, const float* __restrict__ o,
                              const float* __restrict__ d, uint64_t n, float* __restrict__ t_out, int32_t* __restrict__ prim_out,
-                             const uint32_t* __restrict__ orig) {
+                             const uint32_t* __restrict__ orig, bool gate) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float t;
     int prim;
     TraceCounters cnt{0u, 0u};
-    closest_hit<false>(nodes, geom, root_link, mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), t, prim, cnt);
+    closest_hit<false>(nodes, geom, root_link, mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), t, prim, cnt, 0u, gate);
     t_out[i] = prim >= 0 ? t : -1.0f;
     prim_out[i] = prim >= 0 ? (int32_t)orig[prim] : -1;
 }
@@ -1053,12 +1088,29 @@ cudaError_t launch_tonemap(const float4* accum, float scale, uint32_t* image, ui
 }
 
 cudaError_t launch_reduce_tonemap_peers(const float4* const* peers, uint32_t n_peers, float scale, uint64_t begin, uint64_t end,
-                                        float4* accum_out, uint32_t* image, cudaStream_t stream) {
+                                        float4* accum_out, uint32_t* image, const uint32_t* const* peer_flags, uint32_t wait_value, uint32_t* error,
+                                        cudaStream_t stream) {
     if (end <= begin) return cudaSuccess;
     if (n_peers > (uint32_t)kMaxPeers) return cudaErrorInvalidValue;
     PeerList pl;
-    for (int i = 0; i < kMaxPeers; i++) pl.p[i] = i < (int)n_peers ? peers[i] : nullptr;
-    k_reduce_tonemap_peers<<<(uint32_t)std::min<uint64_t>(grid_for(end - begin, 256), 148u * 16u), 256, 0, stream>>>(pl, n_peers, scale, begin, end, accum_out, image);
+    FlagList fl;
+    for (int i = 0; i < kMaxPeers; i++) { pl.p[i] = i < (int)n_peers ? peers[i] : nullptr; fl.f[i] = (peer_flags && i < (int)n_peers) ? peer_flags[i] : nullptr; }
+    // a grid that is resident at once (the CTAs may poll flags): at most 8 CTAs of 256 threads per SM
+    k_reduce_tonemap_peers<<<(uint32_t)std::min<uint64_t>(grid_for(end - begin, 256), 148u * 8u), 256, 0, stream>>>(pl, n_peers, scale, begin, end, accum_out, image,
+                                                                                                                   fl, peer_flags ? wait_value : 0u, error);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_signal(uint32_t* flag, uint32_t value, cudaStream_t stream) {
+    k_signal<<<1, 1, 0, stream>>>(flag, value);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_wait_flags(const uint32_t* const* flags, uint32_t n, uint32_t value, uint32_t* error, cudaStream_t stream) {
+    if (n > (uint32_t)kMaxPeers) return cudaErrorInvalidValue;
+    FlagList fl;
+    for (int i = 0; i < kMaxPeers; i++) fl.f[i] = i < (int)n ? flags[i] : nullptr;
+    k_wait_flags<<<1, 1, 0, stream>>>(fl, n, value, error);
     return cudaGetLastError();
 }
 
@@ -1073,7 +1125,7 @@ cudaError_t launch_trace_rays(const RenderLaunch& scene, const float* o, const f
                               const uint32_t* orig, bool grid, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     if (grid) k_trace_rays_grid<<<grid_for(n, 128), 128, 0, stream>>>(scene.grid, scene.grid_start, scene.grid_refs, scene.geom, o, d, n, t_out, prim_out, orig);
-    else k_trace_rays<<<grid_for(n, 128), 128, 0, stream>>>(scene.nodes, scene.geom, scene.root_link, o, d, n, t_out, prim_out, orig);
+    else k_trace_rays<<<grid_for(n, 128), 128, 0, stream>>>(scene.nodes, scene.geom, scene.root_link, o, d, n, t_out, prim_out, orig, scene.gate != 0u);
     return cudaGetLastError();
 }
 

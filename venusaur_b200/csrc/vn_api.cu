@@ -25,6 +25,8 @@ static_assert(sizeof(GridHeader) == 104, "ABI (vn_read_grid)");
 static_assert(sizeof(vn_params) == 96 && offsetof(vn_params, origin) == 32 && offsetof(vn_params, flags) == 92, "ABI");
 static_assert(sizeof(vn_stats) == 64 && sizeof(vn_bvh_info) == 48, "ABI");
 
+constexpr uint32_t kStatSlots = 8;
+
 struct vn_context {
     int device = 0;
     int num_sms = 0;
@@ -52,8 +54,12 @@ struct vn_context {
     bool copied_valid[2] = {false, false};
     int pipe_flip = 0;
 
-    unsigned long long* d_counters = nullptr;   // 4 x u64 + work ticket (u32) at +32 bytes; [8..22) scheduler statistics of the slot kernel, or [8..11) the launch timeline of the instrumented k_render_async
-    unsigned long long* h_counters = nullptr;   // pinned
+    uint32_t* d_flags = nullptr;                // 64 words: [0..61] epoch flags for cross-process ordering (vn_signal / vn_wait_flags), [63] error word
+    unsigned long long* d_counters = nullptr;   // 4 x u64 + work ticket (u32) at +32 bytes; [8..11) the launch timeline of the instrumented k_render_lean / k_render_async
+    unsigned long long* h_counters = nullptr;   // pinned: kStatSlots x 256 bytes, one slot per launch in flight (VN_ASYNC renders never wait for each other on the host)
+    cudaEvent_t ev_slot[8][2] = {};             // begin / end of the launch that owns the slot
+    uint32_t slot_head = 0, slots_pending = 0;  // launches whose counters have not been folded into stats yet: slots [head - pending, head)
+    uint32_t slot_launches[8] = {};
 
     WavefrontBuffers wf;
     uint64_t wf_sample_floats_ = 0;
@@ -65,9 +71,6 @@ struct vn_context {
                                       // Larger values build them for any scene (one launch pair per level) for the opt-in "wide_global" traversal
     bool wide_global = false;         // traverse canonical wide nodes from L2/HBM when the scene does not fit in shared memory (measured slower
                                       // than the pair nodes on 1 M / 16 M spheres: 1.10 vs 1.45 and 0.69 vs 0.80 Grays/s)
-    bool slot_kernel = false;         // default path kernel for wide-node scenes: slot-scheduled (slot_kernels.cu) instead of k_render_persistent
-    int slot_slots = 3, slot_threads = 768;
-    SlotTune slot_tune{20u, 12u, 8u, 20u, 20u};
     GridScene grid;                   // uniform grid + oversize list (small scenes), built behind the LBVH on the same sorted spheres
     uint32_t accel = 1;               // closest-hit structure of the path kernel: 1 = BVH (default: what the north star specifies), 0 = auto (the grid
                                       // when the scene suits it: +3..6 % on RTIOW), 2 = grid
@@ -86,9 +89,12 @@ struct vn_context {
     int tile_state = 0;               // 0: nothing known (the next launch collects costs), 1: costs collected (sort before the next launch), 2: order valid
     struct TileSig { uint32_t w, h, r0, r1, spp, depth; float cam[13]; uint32_t pad_; uint64_t epoch; } tile_sig{};   // no implicit padding
     uint64_t bvh_epoch = 0;
+    uint32_t hit_gate = 1;            // "hit_gate": pair-node and L2 / HBM traversals apply the hit-point gate (vn_math.cuh::hit_gate_ok)
     uint32_t lean = 1;                // "lean": k_render_lean (16-bit links, no per-lane statistics, no spills) when the launch qualifies; 0 = k_render_async
     uint32_t warp_tiles = 1;          // "warp_tiles": k_render_async phase form hands whole tiles to warps (see path_kernels.cu); 0 = lanes take single pixels
     uint32_t async_done = 26;         // k_render_async: a traversal burst ends when this many lanes hold a finished ray (0 = k_render_persistent)
+    uint32_t global_done = 16;        // the same threshold for scenes traversed from L2 / HBM (k_render_lean<kGlobal>): long traversals, so shade earlier (measured:
+                                      // 1 M spheres 2.21 -> 2.49 Grays/s, 16 M spheres 1.11 -> 1.60 against 26)
     uint32_t async_node = 0, async_leaf = 8;   // async_node 0 = phase form (no votes inside the node / leaf phases), the default
     bool wide_nodes = true;           // use them when they fit in shared memory
     uint32_t sah_max_prims = 4096;    // scenes up to this size get SAH splits (k_sah_small); 0 = always Karras
@@ -97,10 +103,8 @@ struct vn_context {
     size_t smem_scene_limit = 100 * 1024;
     uint32_t wavefront_slots = 1u << 21;
     bool octant_nodes = true;         // stage the BVH nodes once per ray octant when 8 copies fit in shared memory
-    uint32_t pool_slots = 96, pool_threads = 768, pool_service = 8, pool_leaf_batch = 8;
 
     vn_stats stats{};
-    bool stats_pending = false;      // an async vn_render whose counters have not been folded into stats yet
 };
 
 namespace {
@@ -175,6 +179,7 @@ int fill_launch(vn_context* c, const vn_params* p, RenderLaunch& L) {
     L.leaf_vote = c->leaf_vote;
     L.async_done = c->async_done; L.async_node = c->async_node; L.async_leaf = c->async_leaf;
     L.grid_vote = c->grid_vote;
+    L.gate = c->hit_gate;
     L.grid = c->grid.h; L.grid_start = c->grid.start; L.grid_refs = c->grid.refs;
     L.counters = c->d_counters;
     L.work_counter = reinterpret_cast<uint32_t*>(c->d_counters + 4);
@@ -224,7 +229,11 @@ static int create_resources(vn_context* c) {
     }
     VN_CUDA(c, cudaMalloc(&c->d_counters, 256));
     VN_CUDA(c, cudaMemset(c->d_counters, 0, 256));
-    VN_CUDA(c, cudaHostAlloc(&c->h_counters, 256, cudaHostAllocDefault));
+    VN_CUDA(c, cudaMalloc(&c->d_flags, 256));
+    VN_CUDA(c, cudaMemset(c->d_flags, 0, 256));
+    VN_CUDA(c, cudaHostAlloc(&c->h_counters, 256 * kStatSlots, cudaHostAllocDefault));
+    memset(c->h_counters, 0, 256 * kStatSlots);
+    for (uint32_t i = 0; i < kStatSlots; i++) for (int j = 0; j < 2; j++) VN_CUDA(c, cudaEventCreate(&c->ev_slot[i][j]));
     return VN_OK;
 }
 
@@ -277,9 +286,10 @@ void vn_destroy(vn_handle c) {
     grid_free(c->grid);
     lbvh_workspace_free(c->bvh_ws);
     free_wavefront(c->wf); c->wf_sample_floats_ = 0;
-    cudaFree(c->d_tile_cost); cudaFree(c->d_tile_sort); cudaFree(c->d_spheres); cudaFree(c->accum_own); cudaFree(c->image_tmp); cudaFree(c->d_counters);
+    cudaFree(c->d_tile_cost); cudaFree(c->d_tile_sort); cudaFree(c->d_spheres); cudaFree(c->accum_own); cudaFree(c->image_tmp); cudaFree(c->d_counters); cudaFree(c->d_flags);
     cudaFreeHost(c->h_counters);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& pr : c->ev_slot) for (auto& ev : pr) if (ev) cudaEventDestroy(ev);
     for (int i = 0; i < 2; i++) { cudaFree(c->image_pipe[i]); if (c->ev_frame[i]) cudaEventDestroy(c->ev_frame[i]); if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -309,27 +319,13 @@ int vn_set_option(vn_handle c, const char* name, double value) {
     else if (k == "tile_order") { VN_REQUIRE(c, value >= 0 && value <= 3, "tile_order must be 0..3"); c->tile_order_opt = (uint32_t)value; c->tile_state = 0; }
     else if (k == "warp_tiles") { c->warp_tiles = value != 0 ? 1u : 0u; }
     else if (k == "lean") { c->lean = value != 0 ? 1u : 0u; }
+    else if (k == "hit_gate") { c->hit_gate = value != 0 ? 1u : 0u; }
+    else if (k == "global_done") { VN_REQUIRE(c, value >= 1 && value <= 32, "global_done must be in [1,32]"); c->global_done = (uint32_t)value; }
     else if (k == "async_done") { VN_REQUIRE(c, value >= 0 && value <= 32, "async_done must be in [0,32]"); c->async_done = (uint32_t)value; }
     else if (k == "async_node") { VN_REQUIRE(c, value >= 0 && value <= 32, "async_node must be in [0,32] (0 = phase form: no votes inside the node / leaf phases)"); c->async_node = (uint32_t)value; }
     else if (k == "async_leaf") { VN_REQUIRE(c, value >= 1 && value <= 32, "async_leaf must be in [1,32]"); c->async_leaf = (uint32_t)value; }
     else if (k == "leaf_vote") { VN_REQUIRE(c, value >= 0 && value <= 32, "leaf_vote must be in [0,32]"); c->leaf_vote = (uint32_t)value; }
-    else if (k == "slot_kernel") { c->slot_kernel = value != 0; }
-    else if (k == "slot_slots" || k == "slot_threads") {
-        const int slots = k == "slot_slots" ? (int)value : c->slot_slots, threads = k == "slot_threads" ? (int)value : c->slot_threads;
-        (k == "slot_slots" ? c->slot_slots : c->slot_threads) = (int)value;   // validated as a pair at launch
-        (void)slots; (void)threads;
-    }
-    else if (k == "slot_tn" || k == "slot_tl" || k == "slot_tw" || k == "slot_ts" || k == "slot_tr") {
-        VN_REQUIRE(c, value >= 1 && value <= 33, "slot thresholds must be in [1,33]");
-        uint32_t& t = k == "slot_tn" ? c->slot_tune.node_threshold : k == "slot_tl" ? c->slot_tune.leaf_threshold : k == "slot_tw" ? c->slot_tune.switch_threshold
-                      : k == "slot_ts" ? c->slot_tune.shade_threshold : c->slot_tune.regen_threshold;
-        t = (uint32_t)value;
-    }
     else if (k == "octant_nodes") { c->octant_nodes = value != 0; }
-    else if (k == "pool_slots") { VN_REQUIRE(c, value >= 32 && value <= 1024, "pool_slots must be in [32,1024]"); c->pool_slots = (uint32_t)value; }
-    else if (k == "pool_threads") { VN_REQUIRE(c, value >= 32 && value <= 768 && ((int)value % 32) == 0, "pool_threads must be a multiple of 32 in [32,768]"); c->pool_threads = (uint32_t)value; }
-    else if (k == "pool_service") { VN_REQUIRE(c, value >= 1 && value <= 32, "pool_service must be in [1,32]"); c->pool_service = (uint32_t)value; }
-    else if (k == "pool_leaf_batch") { VN_REQUIRE(c, value >= 1 && value <= 33, "pool_leaf_batch must be in [1,33]"); c->pool_leaf_batch = (uint32_t)value; }
     else return fail(c, VN_ERR_INVALID, "vn_set_option: unknown option '" + k + "'");
     return VN_OK;
 }
@@ -419,8 +415,9 @@ int vn_read_bvh(vn_handle c, vn_node32* host_nodes, uint64_t cap_nodes, uint32_t
 
 int vn_read_sched_counters(vn_handle c, uint64_t* out14) {
     VN_REQUIRE(c, c && out14, "vn_read_sched_counters: NULL argument");
-    if (c->stats_pending) { const int rc = vn_synchronize(c); if (rc != VN_OK) return rc; }
-    for (int i = 0; i < 14; i++) out14[i] = c->h_counters[8 + i];
+    if (c->slots_pending) { const int rc = vn_synchronize(c); if (rc != VN_OK) return rc; }
+    const unsigned long long* last = c->h_counters + 32u * ((c->slot_head + kStatSlots - 1u) % kStatSlots);
+    for (int i = 0; i < 14; i++) out14[i] = last[8 + i];
     return VN_OK;
 }
 
@@ -520,17 +517,24 @@ int vn_write_accum(vn_handle c, const float* host_rgba) {
     return VN_OK;
 }
 
+// Folds the counters of every finished launch into the statistics (the stream must have been synchronised): totals accumulate over all
+// of them, the per-launch fields describe the newest one.
 static int collect_render_stats(vn_context* c) {
-    float ms = 0.0f;
-    VN_CUDA(c, cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]));
-    c->stats.ms_render = ms;
-    c->stats.ms_trace = ms;
-    c->stats.segments = c->h_counters[0];
-    c->stats.paths = c->h_counters[1];
-    c->stats.node_visits = c->h_counters[2];
-    c->stats.sphere_tests = c->h_counters[3];
-    c->stats.segments_total += c->h_counters[0];
-    c->stats_pending = false;
+    while (c->slots_pending) {
+        const uint32_t slot = (c->slot_head + kStatSlots - c->slots_pending) % kStatSlots;
+        const unsigned long long* hc = c->h_counters + 32u * slot;
+        float ms = 0.0f;
+        VN_CUDA(c, cudaEventElapsedTime(&ms, c->ev_slot[slot][0], c->ev_slot[slot][1]));
+        c->stats.ms_render = ms;
+        c->stats.ms_trace = ms;
+        c->stats.segments = hc[0];
+        c->stats.paths = hc[1];
+        c->stats.node_visits = hc[2];
+        c->stats.sphere_tests = hc[3];
+        c->stats.segments_total += hc[0];
+        c->stats.kernel_launches = c->slot_launches[slot];
+        c->slots_pending -= 1u;
+    }
     return VN_OK;
 }
 
@@ -538,8 +542,7 @@ static int collect_render_stats(vn_context* c) {
 static int sync_kernels(vn_context* c) {
     VN_CUDA(c, cudaStreamSynchronize(c->stream));
     VN_CUDA(c, cudaGetLastError());
-    if (c->stats_pending) return collect_render_stats(c);
-    return VN_OK;
+    return collect_render_stats(c);
 }
 
 int vn_synchronize(vn_handle c) {
@@ -615,15 +618,6 @@ static int ensure_wavefront(vn_context* c, uint64_t pixels, uint32_t spp) {
     return ensure_sample_buffer(c, pixels, spp);
 }
 
-// The slot kernel needs the 4-wide nodes in shared memory next to its slots, and sample / depth counters that fit 16 bits.
-static bool use_slot_kernel(const vn_context* c, const vn_params* p, const RenderLaunch& L) {
-    if (!((p->flags & VN_SLOTS) || c->slot_kernel) || (p->flags & VN_PERSISTENT)) return false;
-    if (!c->wide_nodes || !L.wide || L.num_wide == 0 || c->scene.wide_levels > kWideMaxLevels) return false;
-    if (p->samples_per_pixel > 65535u || p->max_depth > 65535u) return false;
-    if (!exact::slot_config_supported(c->slot_slots, c->slot_threads)) return false;
-    return exact::slot_smem_bytes(L.num_wide, L.num_spheres, c->slot_slots, c->slot_threads) + 1024 <= c->smem_optin;
-}
-
 // Longest-processing-time-first schedule for the persistent path kernels.  Lanes take 8x4-pixel tiles from a global ticket; with
 // row-major tickets a launch ends with ~0.7 ms (11 % of a 1080p launch, measured with tools/tail_probe.py) in which the tickets
 // are gone and ever fewer lanes finish the expensive pixels (glass: paths of up to max_depth segments) they took late.  Progressive
@@ -697,55 +691,19 @@ int vn_render(vn_handle c, const vn_params* p) {
     uint32_t launches = 0;
 
     const bool pipelined = host_image && (p->flags & VN_ASYNC);
-    if (c->stats_pending) { const int rc = sync_kernels(c); if (rc != VN_OK) return rc; }
+    // a launch in flight owns a slot of the pinned counter ring; only a full ring makes the host wait (VN_ASYNC renders queue back to back)
+    if (c->slots_pending >= kStatSlots) { const int rc = sync_kernels(c); if (rc != VN_OK) return rc; }
+    const uint32_t slot = c->slot_head;
     // the staging buffer of this frame was last read by the copy of two frames ago
     if (pipelined && c->copied_valid[c->pipe_flip]) VN_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[c->pipe_flip], 0));
     VN_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 256, c->stream));
-    VN_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    VN_CUDA(c, cudaEventRecord(c->ev_slot[slot][0], c->stream));
     if (p->flags & VN_WAVEFRONT) {
         const uint32_t rows = L.row_end - L.row_begin;
         const int rc = ensure_wavefront(c, (uint64_t)p->width * rows, p->samples_per_pixel);
         if (rc != VN_OK) return rc;
         VN_CUDA(c, exact_build ? exact::launch_wavefront(L, c->wf, c->num_sms, c->stream, &launches)
                                : fast::launch_wavefront(L, c->wf, c->num_sms, c->stream, &launches));
-    } else if ((p->flags & VN_POOL) && !count && p->samples_per_pixel < 32768u && p->max_depth < 32768u) {
-        // shared-memory warp-pool wavefront kernel; the scene is staged next to the pools when both fit
-        const int threads = (int)c->pool_threads;
-        bool in_smem = scene_fits_smem(c);
-        size_t smem = exact_build ? exact::pool_smem_bytes(L.num_nodes, L.num_spheres, in_smem, threads / 32, c->pool_slots)
-                                  : fast::pool_smem_bytes(L.num_nodes, L.num_spheres, in_smem, threads / 32, c->pool_slots);
-        if (in_smem && smem > c->smem_optin) {
-            in_smem = false;
-            smem = exact::pool_smem_bytes(L.num_nodes, L.num_spheres, false, threads / 32, c->pool_slots);
-        }
-        if (smem > c->smem_optin) return fail(c, VN_ERR_INVALID, "vn_render: pool_slots x pool_threads does not fit in shared memory");
-        int per_sm = exact_build ? exact::pool_max_blocks_per_sm(in_smem, threads, smem) : fast::pool_max_blocks_per_sm(in_smem, threads, smem);
-        if (per_sm <= 0) return fail(c, VN_ERR_CUDA, "vn_render: occupancy query failed for the pool kernel");
-        int blocks = c->num_sms * per_sm;
-        const uint64_t slots_per_block = (uint64_t)(threads / 32) * c->pool_slots;
-        const uint64_t max_blocks = ((uint64_t)L.total_work + slots_per_block - 1) / slots_per_block;
-        if ((uint64_t)blocks > max_blocks) blocks = (int)std::max<uint64_t>(1, max_blocks);
-        VN_CUDA(c, exact_build ? exact::launch_render_pool(L, in_smem, threads, blocks, c->pool_slots, c->pool_service, c->pool_leaf_batch, c->stream)
-                               : fast::launch_render_pool(L, in_smem, threads, blocks, c->pool_slots, c->pool_service, c->pool_leaf_batch, c->stream));
-        launches += 1;
-        if (L.image) {
-            const uint64_t begin = (uint64_t)L.row_begin * L.width, npx = (uint64_t)(L.row_end - L.row_begin) * L.width;
-            VN_CUDA(c, exact_build ? exact::launch_tonemap(L.accum + begin, 1.0f, L.image + begin, npx, c->stream)
-                                   : fast::launch_tonemap(L.accum + begin, 1.0f, L.image + begin, npx, c->stream));
-            launches += 1;
-        }
-    } else if (use_slot_kernel(c, p, L)) {
-        // slot-scheduled path kernel over the 4-wide nodes (K path slots per lane, warp-voted operations)
-        const uint32_t rows = L.row_end - L.row_begin;
-        const int rc = ensure_sample_buffer(c, (uint64_t)p->width * rows, p->samples_per_pixel);
-        if (rc != VN_OK) return rc;
-        int blocks = c->num_sms;
-        const uint64_t max_blocks = ((uint64_t)L.total_work + c->slot_threads - 1) / c->slot_threads;
-        if ((uint64_t)blocks > max_blocks) blocks = (int)std::max<uint64_t>(1, max_blocks);
-        VN_CUDA(c, exact_build ? exact::launch_render_slots(L, c->wf.sample_rgb, c->slot_slots, c->slot_threads, blocks, c->slot_tune, count, c->stream)
-                               : fast::launch_render_slots(L, c->wf.sample_rgb, c->slot_slots, c->slot_threads, blocks, c->slot_tune, count, c->stream));
-        VN_CUDA(c, exact_build ? exact::launch_accumulate_samples(L, c->wf.sample_rgb, c->stream) : fast::launch_accumulate_samples(L, c->wf.sample_rgb, c->stream));
-        launches += 2;
     } else {
         { const int rc = prepare_tile_order(c, p, L); if (rc != VN_OK) return rc; }
         KernelConfig cfg;
@@ -771,7 +729,7 @@ int vn_render(vn_handle c, const vn_params* p) {
         else if (cfg.octant) { cfg.smem_bytes = oct_bytes; cfg.threads = 1024; }
         else if (cfg.threads > 256) cfg.threads = 256;
         // scenes traversed from L2 / HBM (pair nodes): the asynchronous form of the path kernel (k_render_lean<kGlobal>, 256-thread CTAs)
-        if (!cfg.scene_in_smem && !cfg.wide && !cfg.grid && c->lean != 0u && c->async_done > 0u && p->width < 65536u && p->height < 65536u) { cfg.lean = true; cfg.threads = 256; }
+        if (!cfg.scene_in_smem && !cfg.wide && !cfg.grid && c->lean != 0u && c->async_done > 0u && p->width < 65536u && p->height < 65536u) { cfg.lean = true; cfg.threads = 256; L.async_done = c->global_done; }
         int per_sm = (cfg.octant || (cfg.wide && cfg.scene_in_smem)) ? 1 : c->blocks_per_sm;
         if (per_sm <= 0) {
             per_sm = exact_build ? exact::max_blocks_per_sm(cfg.threads, cfg.smem_bytes, cfg.scene_in_smem, count, cfg.octant, cfg.wide, cfg.grid, cfg.lean)
@@ -793,11 +751,11 @@ int vn_render(vn_handle c, const vn_params* p) {
             launches += 1;
         }
     }
-    VN_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    VN_CUDA(c, cudaEventRecord(c->ev_slot[slot][1], c->stream));
     // only the rows this launch rendered were tonemapped into the staging buffer: copy those and leave the caller's other rows alone
     const uint64_t row_px0 = (uint64_t)L.row_begin * L.width, row_px = (uint64_t)(L.row_end - L.row_begin) * L.width;
     // (the 256-byte statistics copy goes first: queued behind the frame on the D2H engine it would delay the next launch)
-    VN_CUDA(c, cudaMemcpyAsync(c->h_counters, c->d_counters, 256, cudaMemcpyDeviceToHost, c->stream));
+    VN_CUDA(c, cudaMemcpyAsync(c->h_counters + 32u * slot, c->d_counters, 256, cudaMemcpyDeviceToHost, c->stream));
     if (pipelined) {
         const int f = c->pipe_flip;
         VN_CUDA(c, cudaEventRecord(c->ev_frame[f], c->stream));
@@ -809,14 +767,12 @@ int vn_render(vn_handle c, const vn_params* p) {
     } else if (host_image) {
         VN_CUDA(c, cudaMemcpyAsync(static_cast<uint32_t*>(p->image) + row_px0, c->image_tmp + row_px0, row_px * 4, cudaMemcpyDeviceToHost, c->stream));
     }
+    c->slot_launches[slot] = launches;
     c->stats.kernel_launches = launches;
     c->stats.kernel_launches_total += launches;
-    c->stats_pending = true;
-    if (!(p->flags & VN_ASYNC)) {
-        VN_CUDA(c, cudaStreamSynchronize(c->stream));
-        VN_CUDA(c, cudaGetLastError());
-        return collect_render_stats(c);
-    }
+    c->slot_head = (slot + 1u) % kStatSlots;
+    c->slots_pending += 1u;
+    if (!(p->flags & VN_ASYNC)) return sync_kernels(c);
     return VN_OK;
 }
 
@@ -836,6 +792,56 @@ int vn_tonemap(vn_handle c, float scale, void* image, uint32_t flags) {
 
 int vn_reduce_tonemap_peers(vn_handle c, const void* const* peer_accum, uint32_t n_peers, float scale, uint32_t row_begin,
                             uint32_t row_end, void* image, uint32_t flags) {
+    VN_REQUIRE(c, c, "vn_reduce_tonemap_peers: NULL argument");
+    return vn_reduce_tonemap_peers_to(c, peer_accum, n_peers, scale, row_begin, row_end, c->accum, image, flags);
+}
+
+int vn_reduce_tonemap_peers_to(vn_handle c, const void* const* peer_accum, uint32_t n_peers, float scale, uint32_t row_begin,
+                               uint32_t row_end, void* sum_out, void* image, uint32_t flags) {
+    return vn_reduce_tonemap_peers_wait(c, peer_accum, n_peers, scale, row_begin, row_end, sum_out, image, nullptr, 0u, flags);
+}
+
+int vn_sync_flags(vn_handle c, void** dev_ptr) {
+    VN_REQUIRE(c, c && dev_ptr, "vn_sync_flags: NULL argument");
+    *dev_ptr = c->d_flags;
+    return VN_OK;
+}
+
+int vn_signal(vn_handle c, uint32_t index, uint32_t value) {
+    VN_REQUIRE(c, c, "vn_signal: NULL handle");
+    VN_REQUIRE(c, index < 62u, "vn_signal: flag index must be < 62");
+    VN_CUDA(c, cudaSetDevice(c->device));
+    VN_CUDA(c, exact::launch_signal(c->d_flags + index, value, c->stream));
+    c->stats.kernel_launches_total += 1;
+    return VN_OK;
+}
+
+int vn_wait_flags(vn_handle c, const void* const* flags, uint32_t n, uint32_t value) {
+    VN_REQUIRE(c, c && flags, "vn_wait_flags: NULL argument");
+    VN_REQUIRE(c, n >= 1 && n <= (uint32_t)kMaxPeers, "vn_wait_flags: 1..8 flags");
+    VN_CUDA(c, cudaSetDevice(c->device));
+    const uint32_t* f[kMaxPeers];
+    for (uint32_t i = 0; i < n; i++) f[i] = static_cast<const uint32_t*>(flags[i]);
+    VN_CUDA(c, exact::launch_wait_flags(f, n, value, c->d_flags + 63, c->stream));
+    c->stats.kernel_launches_total += 1;
+    return VN_OK;
+}
+
+int vn_check_flags(vn_handle c) {
+    VN_REQUIRE(c, c, "vn_check_flags: NULL handle");
+    VN_CUDA(c, cudaSetDevice(c->device));
+    uint32_t err = 0;
+    VN_CUDA(c, cudaMemcpyAsync(&err, c->d_flags + 63, 4, cudaMemcpyDeviceToHost, c->stream));
+    VN_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (err) {
+        VN_CUDA(c, cudaMemsetAsync(c->d_flags + 63, 0, 4, c->stream));
+        return fail(c, VN_ERR_CUDA, "a device-side wait for peer " + std::to_string(err - 1u) + "'s epoch flag timed out (4 s): that rank never signalled");
+    }
+    return VN_OK;
+}
+
+int vn_reduce_tonemap_peers_wait(vn_handle c, const void* const* peer_accum, uint32_t n_peers, float scale, uint32_t row_begin,
+                                 uint32_t row_end, void* sum_out, void* image, const void* const* peer_flags, uint32_t wait_value, uint32_t flags) {
     VN_REQUIRE(c, c && peer_accum, "vn_reduce_tonemap_peers: NULL argument");
     VN_REQUIRE(c, n_peers >= 1 && n_peers <= (uint32_t)kMaxPeers, "vn_reduce_tonemap_peers: 1..8 peers");
     VN_REQUIRE(c, c->accum, "vn_reduce_tonemap_peers: no accumulation buffer");
@@ -845,8 +851,11 @@ int vn_reduce_tonemap_peers(vn_handle c, const void* const* peer_accum, uint32_t
     for (uint32_t i = 0; i < n_peers; i++) peers[i] = static_cast<const float4*>(peer_accum[i]);
     const uint64_t begin = (uint64_t)row_begin * c->width, end = (uint64_t)row_end * c->width;
     uint32_t* img = static_cast<uint32_t*>(image);
-    VN_CUDA(c, !(flags & VN_FAST) ? exact::launch_reduce_tonemap_peers(peers, n_peers, scale, begin, end, c->accum, img, c->stream)
-                                  : fast::launch_reduce_tonemap_peers(peers, n_peers, scale, begin, end, c->accum, img, c->stream));
+    float4* sum = static_cast<float4*>(sum_out);
+    const uint32_t* pf[kMaxPeers];
+    for (uint32_t i = 0; peer_flags && i < n_peers; i++) pf[i] = static_cast<const uint32_t*>(peer_flags[i]);
+    VN_CUDA(c, !(flags & VN_FAST) ? exact::launch_reduce_tonemap_peers(peers, n_peers, scale, begin, end, sum, img, peer_flags ? pf : nullptr, wait_value, c->d_flags + 63, c->stream)
+                                  : fast::launch_reduce_tonemap_peers(peers, n_peers, scale, begin, end, sum, img, peer_flags ? pf : nullptr, wait_value, c->d_flags + 63, c->stream));
     c->stats.kernel_launches_total += 1;
     if (!(flags & VN_ASYNC)) VN_CUDA(c, cudaStreamSynchronize(c->stream));
     return VN_OK;
@@ -1001,6 +1010,7 @@ int vn_trace_rays(vn_handle c, const float* origins, const float* dirs, uint64_t
     RenderLaunch L;
     memset(&L, 0, sizeof(L));
     L.nodes = c->scene.nodes; L.geom = c->scene.geom; L.root_link = c->scene.root_link;
+    L.gate = c->hit_gate;
     const bool use_grid = (flags & VN_GRID) != 0;
     VN_REQUIRE(c, !use_grid || c->grid.valid, "vn_trace_rays: VN_GRID but the scene has no grid");
     L.grid = c->grid.h; L.grid_start = c->grid.start; L.grid_refs = c->grid.refs;

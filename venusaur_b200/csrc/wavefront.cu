@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kWfThreads) k_wavefront(const __grid_constant_
                     float t;
                     int prim;
                     TraceCounters cnt{0u, 0u};
-                    closest_hit<false>(sc.nodes, sc.geom, sc.root_link, mk3(A.ox[i], A.oy[i], A.oz[i]), mk3(A.dx[i], A.dy[i], A.dz[i]), t, prim, cnt);
+                    closest_hit<false>(sc.nodes, sc.geom, sc.root_link, mk3(A.ox[i], A.oy[i], A.oz[i]), mk3(A.dx[i], A.dy[i], A.dz[i]), t, prim, cnt, 0u, p.gate != 0u);
                     wf.hit_t[i] = t;
                     wf.hit_prim[i] = prim;
                     cls = prim < 0 ? 0u : 1u + (uint32_t)sc.type[prim];
