@@ -137,10 +137,15 @@ VN_API int vn_set_spheres(vn_handle h, const vn_sphere* host_spheres, uint64_t n
  * expensive pixel, 3 = max(sum / 8, most expensive pixel)], "wide_global" [0], "threads", "blocks_per_sm", "smem_scene_limit".
  * "lean" [1: k_render_lean -- 16-bit links, newest stack entry in a register, per-warp statistics -- for shared-memory scenes, and its
  * asynchronous form over pair nodes for scenes traversed from L2 / HBM; 0 = k_render_async / k_render_persistent], "global_done" [16: the burst
- * threshold of the L2 / HBM form], "hit_gate" [1: pair-node and L2 / HBM traversals only count a root whose hit point lies inside the sphere's
- * slightly grown box, see DESIGN.md section 4], "wavefront_slots".  Options that change the BVH invalidate it (call vn_build_bvh again). */
+ * threshold of the L2 / HBM form], "hit_gate" [1: scenes traversed from L2 / HBM only count a root whose hit point lies inside the sphere's slightly
+ * grown box; 0 = never; 2 = the pair-node kernels also on small scenes], "wavefront_slots".  Options that change the BVH invalidate it (call vn_build_bvh again). */
 VN_API int vn_set_option(vn_handle h, const char* name, double value);
 VN_API int vn_build_bvh(vn_handle h);
+/* The spheres moved or changed material (same count, same order as in vn_set_spheres): uploads the records and refits the existing BVH --
+ * same hierarchy, new boxes, 4-5 launches instead of a build (moving spheres).  The closest hit stays exact for any
+ * motion; traversal cost grows as spheres leave their old neighbourhoods: call vn_build_bvh now and then.  Falls back to a full build
+ * when the hierarchy is not at hand (very large scenes' wide nodes, the uniform grid).  vn_stats.ms_build reports the refit. */
+VN_API int vn_update_spheres(vn_handle h, const vn_sphere* host_spheres, uint64_t n);
 VN_API int vn_get_bvh_info(vn_handle h, vn_bvh_info* out);
 VN_API int vn_read_bvh(vn_handle h, vn_node32* host_nodes, uint64_t cap_nodes, uint32_t* host_prim_order, uint64_t cap_prims);
 /* Second closest-hit structure for small scenes (<= 16384 spheres of similar size plus at most 8 oversize ones): a uniform grid over the

@@ -99,6 +99,24 @@ def main():
                             prev=prev, accum=acc, image=img, segments=np.uint64(seg), width=W, height=H, spp=SPP, subframe=sub,
                             max_depth=depth, origin=cam[0], u=cam[1], v=cam[2], w=cam[3], lens=cam[4])
         print("golden sub=%d depth=%d segments=%d" % (sub, depth, seg))
+    # ---- negative radius (sphere.h:17-28): RTIOW's hollow-glass trick -- a second dielectric sphere of radius -0.9 inside
+    # the big glass sphere, whose normal (p - c) / r (RayTracer.cu:257) points inwards.  Seen from close by, depth 50.
+    hollow = ol.hollow_glass_scene(spheres)
+    cam = ol.camera((3.0, 1.6, 4.0), (-3.0, -0.6, -4.0), 25.0, W / H, 0.02, 5.0)
+    for sub, depth in [(2, 50)]:
+        P = ol.ref_params()
+        P.width, P.height, P.samples_per_pixel, P.subframe_index = W, H, SPP, sub
+        P.origin, P.u, P.v, P.w, P.lens_radius = ol.c_float3(*cam[0]), ol.c_float3(*cam[1]), ol.c_float3(*cam[2]), ol.c_float3(*cam[3]), float(cam[4])
+        prev = (np.random.RandomState(8).rand(H, W, 4).astype(np.float32))
+        prev[..., 3] = 1.0
+        acc = prev.copy()
+        img = np.zeros((H, W, 4), np.uint8)
+        seg = r.ref_render(hollow.ctypes.data_as(C.c_void_p), len(hollow), C.byref(P), None, 0, acc.ctypes.data_as(C.c_void_p),
+                           img.ctypes.data_as(C.c_void_p), depth, 8)
+        np.savez_compressed(os.path.join(HERE, "ref_render_hollow_%dx%d_spp%d_sub%d_depth%d.npz" % (W, H, SPP, sub, depth)),
+                            prev=prev, accum=acc, image=img, segments=np.uint64(seg), width=W, height=H, spp=SPP, subframe=sub,
+                            max_depth=depth, origin=cam[0], u=cam[1], v=cam[2], w=cam[3], lens=cam[4])
+        print("golden hollow sub=%d depth=%d segments=%d" % (sub, depth, seg))
     np.save(os.path.join(HERE, "rtiow_final_scene.npy"), spheres)
     print("wrote", sorted(os.listdir(HERE)))
 

@@ -126,6 +126,16 @@ def rtiow_final_scene() -> np.ndarray:
     return s
 
 
+def hollow_glass_scene(rtiow: np.ndarray) -> np.ndarray:
+    """The RTIOW final scene + a dielectric sphere of radius -0.9 inside the big glass sphere at (0, 1, 0): the book's hollow-glass
+    trick, a NEGATIVE radius (sphere.h:17-28; the normal (p - c) / r of RayTracer.cu:257 then points inwards)."""
+    glass = [i for i in range(len(rtiow)) if rtiow["type"][i] == 2 and rtiow["r"][i] == 1.0]
+    assert len(glass) == 1
+    extra = rtiow[glass[0]:glass[0] + 1].copy()
+    extra["r"] = np.float32(-0.9)
+    return np.ascontiguousarray(np.concatenate([rtiow, extra]))
+
+
 def random_scene(n, seed, S, mix) -> np.ndarray:
     s = np.zeros(n, SPHERE_DTYPE)
     load().orc_scene_random(_p(s), n, seed, S, mix)

@@ -243,25 +243,30 @@ def test_traversal_equals_brute_force(ctx, oracle_mod, rtiow, scene_name):
     # ground truth: brute force over all spheres with the hit-point gate (what vn_trace_rays applies); on the RTIOW
     # scene the gate never fires, i.e. the result is also the ungated brute force's
     t0, p0 = orc.closest_hit(o, d, use_bvh=False, gate=True)
+    def same_hits(ta, pa, tb, pb):
+        # the generator produces a few identical spheres (tea<4> collisions): which of two coincident spheres is reported depends on the
+        # order they are tested in, so equal means the same distance and the same sphere RECORD
+        return np.array_equal(ta, tb) and np.array_equal(pa >= 0, pb >= 0) and np.array_equal(spheres[np.maximum(pa, 0)], spheres[np.maximum(pb, 0)])
     tv, pv = orc.closest_hit(o, d, use_bvh=True, gate=True)     # the oracle's own BVH agrees with its brute force
-    assert np.array_equal(t0, tv) and np.array_equal(p0, pv)
+    assert same_hits(t0, p0, tv, pv)
     tu, pu = orc.closest_hit(o, d, use_bvh=False, gate=False)
     if scene_name == "rtiow":
         assert np.array_equal(t0, tu) and np.array_equal(p0, pu)
+        t0, p0 = tu, pu                                         # (a scene in shared memory is traversed without the gate)
     else:
         # origins up to 40 units from 0.1-0.3 radius spheres: the float quadratic of RayTracer.cu:239-253 then has an error of several % of
         # r^2 and reports a few phantom hits whose hit point lies outside the sphere's box: those are what the gate removes
         print("random20k: the gate removes %d phantom hits of %d" % (int(((pu >= 0) & ((pu != p0) | (tu != t0))).sum()), int((pu >= 0).sum())))
     t1, p1 = ctx.trace_rays(o, d, VN_EXACT)
     assert (p0 >= 0).sum() > n // 20
-    assert np.array_equal(p0, p1) and np.array_equal(t0, t1)    # IEEE build: bit-exact, whatever the scene
+    assert same_hits(t0, p0, t1, p1)                            # IEEE build: bit-exact, whatever the scene
     if scene_name != "rtiow":
         ctx.set_option("aabb_pad", 0.10)                        # any conservative box gives the same answer
         ctx.build_bvh()
         t3, p3 = ctx.trace_rays(o, d, VN_EXACT)
         ctx.set_option("aabb_pad", 0.01)
         ctx.build_bvh()
-        assert np.array_equal(p0, p3) and np.array_equal(t0, t3)
+        assert same_hits(t0, p0, t3, p3)
     t2, p2 = ctx.trace_rays(o, d, VN_FAST)                      # relaxed build: same hits up to float noise
     same = p0 == p2
     assert same.mean() > 0.998
@@ -858,13 +863,13 @@ def test_large_scene_from_hbm_matches_oracle(ctx, oracle_mod):
             acc, _, st = render(ctx, cam, W, H, 4, 1, 64, flags=flags, image=False)
             if (flags & VN_COUNTERS) and opts.get("wide_global"):
                 assert st.node_visits / st.segments < 30          # the wide nodes really were traversed (pairs: ~50)
-            if not opts:
+            if not opts and not (flags & VN_WAVEFRONT):
                 assert ctx.last_accel() == 1
                 if first is None:
                     first = (acc.copy(), st.segments)
                 else:                                             # the instrumented variant counts the same segments, same image
                     assert np.array_equal(acc.view(np.uint32), first[0].view(np.uint32)) and st.segments == first[1] and st.node_visits > st.segments
-            elif "lean" in opts or "global_done" in opts:         # same rays, same steps per ray: identical to the default schedule
+            elif "lean" in opts or "global_done" in opts or (flags & VN_WAVEFRONT):   # same rays, same steps per ray: identical to the default schedule
                 assert np.array_equal(acc.view(np.uint32), first[0].view(np.uint32)) and st.segments == first[1], opts
         finally:
             ctx.set_option("leaf_vote", 0)
@@ -961,3 +966,118 @@ def test_cpp_dropin_renders_same_image(oracle_mod, rtiow):
         want, wimg = oracle_mod.accumulate_tonemap(want, mean, k > 0, np.float32(1.0) / np.float32(k + 1))
     assert np.abs(img.astype(np.int32) - wimg.astype(np.int32)).max() <= 1
     assert int(r.stdout.strip()) == ost.segments
+
+
+# ------------------------------------------------------------------ scene generality
+def test_negative_radius_hollow_glass(ctx, oracle_mod, rtiow):
+    """RTIOW's hollow glass sphere: a dielectric of radius -0.9 inside the big glass sphere (sphere.h:17-28 keeps the sign; the normal
+    (p - c) / r of RayTracer.cu:257 flips).  The oracle is pinned on this very scene by the reference's own programs
+    (tests/golden/ref_render_hollow_*.npz); the kernels -- default options (wide nodes, huge list), pair nodes, wavefront -- reproduce the
+    oracle bit for bit, and vn_trace_rays equals brute force."""
+    spheres = oracle_mod.hollow_glass_scene(rtiow)
+    W, H, spp, sub, depth = 200, 112, 8, 2, 50
+    cam = vb.Camera((3.0, 1.6, 4.0), 25.0, W / H, 0.02, 5.0)
+    cam.SetForward((-3.0, -0.6, -4.0))
+    orc = oracle_mod.Oracle(spheres)
+    want, ost = orc.render_mean(orc.params(cam.frame(), W, H, spp, sub, depth, atten=oracle_mod.ATTEN_FORWARD, closest=oracle_mod.CLOSEST_BRUTE))
+    try:
+        for opts, flags in (({"leaf_size": 0}, 0), ({"leaf_size": 2, "wide_nodes": 0}, 0), ({"leaf_size": 2}, VN_WAVEFRONT)):
+            for k, v in opts.items():
+                ctx.set_option(k, v)
+            ctx.set_spheres(spheres)
+            ctx.build_bvh()
+            acc, _, st = render(ctx, cam, W, H, spp, sub, depth, flags=flags, image=False)
+            assert st.segments == ost.segments, opts
+            assert np.array_equal(acc.view(np.uint32), want.view(np.uint32)), opts
+        rng = np.random.RandomState(3)
+        o = np.array([0.0, 1.0, 0.0], np.float32) + (rng.rand(20000, 3).astype(np.float32) - np.float32(0.5)) * np.float32(3.0)   # inside and around the shells
+        d = rng.randn(20000, 3).astype(np.float32)
+        t0, p0 = orc.closest_hit(o, d, use_bvh=False)
+        t1, p1 = ctx.trace_rays(o, d, VN_EXACT)
+        assert np.array_equal(t0, t1) and np.array_equal(p0, p1) and (p0 == len(spheres) - 1).sum() > 1000     # the inner shell is hit from both sides
+    finally:
+        ctx.set_option("wide_nodes", 1)
+        ctx.set_option("leaf_size", 2)
+
+
+@pytest.mark.parametrize("scene_name", ["rtiow", "random50k"])
+def test_update_spheres_refits_the_bvh(ctx, oracle_mod, rtiow, scene_name):
+    """vn_update_spheres: the spheres moved, the hierarchy stays (refit-only rebuild: gather, bottom-up refit, pack, wide nodes).  After
+    every motion step the traversal equals brute force over the MOVED spheres and the frame equals the oracle's, bit for bit -- also
+    when spheres have wandered far from their old neighbourhoods -- and a full rebuild gives the same frame."""
+    if scene_name == "rtiow":
+        spheres = rtiow.copy()
+        ctx.set_option("leaf_size", 0)
+        W, H, spp, depth = 160, 90, 4, 50
+        cam = vb.rtiow_camera(W, H)
+        amp = (0.05, 0.4, 3.0)
+    else:
+        spheres = np.ascontiguousarray(oracle_mod.random_scene(50000, 0x5EED0003, 12.0, 0))
+        ctx.set_option("leaf_size", 2)
+        W, H, spp, depth = 96, 54, 2, 50
+        cam = vb.Camera((0.0, 0.0, 24.0), 40.0, W / H, 0.0, 24.0)
+        cam.SetForward((0.0, 0.0, -1.0))
+        amp = (0.05, 1.0)
+    gated = oracle_mod.CLOSEST_GATE if scene_name != "rtiow" else 0
+    ctx.set_spheres(spheres)
+    ctx.build_bvh()
+    build_ms = ctx.stats().ms_build
+    rng = np.random.RandomState(23)
+    moved = spheres.copy()
+    small = np.abs(moved["r"]) < 10.0                           # (the RTIOW ground stays where it is)
+    try:
+        for step, a in enumerate(amp):
+            for axis in ("cx", "cy", "cz"):
+                moved[axis][small] = (moved[axis][small] + (rng.rand(int(small.sum())).astype(np.float32) - np.float32(0.5)) * np.float32(2.0 * a)).astype(np.float32)
+            ctx.update_spheres(moved)
+            refit_ms = ctx.stats().ms_build
+            orc = oracle_mod.Oracle(moved)
+            o = (rng.rand(20000, 3).astype(np.float32) - np.float32(0.5)) * np.float32(30.0)
+            if scene_name == "rtiow":
+                o[:, 1] = np.abs(o[:, 1]) * np.float32(0.1) + np.float32(0.05)
+            d = rng.randn(20000, 3).astype(np.float32)
+            t0, p0 = orc.closest_hit(o, d, use_bvh=False, gate=bool(gated))
+            t1, p1 = ctx.trace_rays(o, d, VN_EXACT)
+            assert np.array_equal(t0, t1) and np.array_equal(moved[np.maximum(p0, 0)], moved[np.maximum(p1, 0)]) and np.array_equal(p0 >= 0, p1 >= 0), (scene_name, step)
+            acc, _, st = render(ctx, cam, W, H, spp, 1 + step, depth, image=False)
+            want, ost = orc.render_mean(orc.params(cam.frame(), W, H, spp, 1 + step, depth, atten=oracle_mod.ATTEN_FORWARD, closest=oracle_mod.CLOSEST_BVH | gated))
+            assert st.segments == ost.segments and np.array_equal(acc.view(np.uint32), want.view(np.uint32)), (scene_name, step)
+            print("%s step %d (+-%.2f): refit %.3f ms (build %.3f ms)" % (scene_name, step, a, refit_ms, build_ms))
+        ctx.build_bvh()                                         # the same scene through a fresh hierarchy
+        acc2, _, st2 = render(ctx, cam, W, H, spp, len(amp), depth, image=False)
+        assert np.array_equal(acc2.view(np.uint32), acc.view(np.uint32)) and st2.segments == st.segments
+        with pytest.raises(vb.Exception):
+            ctx.update_spheres(moved[:-1])                      # another count is another scene: vn_set_spheres
+    finally:
+        ctx.set_option("leaf_size", 2)
+
+
+def test_headless_driver_writes_the_oracles_picture(oracle_mod, rtiow, tmp_path):
+    """tools/venusaur_headless.cpp -- the headless replacement of Core.cpp's frame loop (same objects, same call
+    sequence Scene / Camera / Renderer::Init / CUDAOutputBuffer / Renderer::Draw per frame / getHostPointer) -- is compiled against the
+    drop-in headers, run, and its PPM compared with the oracle's frame: three Draws = the running mean of subframes 1..3."""
+    W, H, frames, depth = 96, 54, 3, 8
+    libdir = os.path.dirname(vb.lib_path())
+    exe, ppm = str(tmp_path / "venusaur_headless"), str(tmp_path / "frame.ppm")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tools", "venusaur_headless.cpp"), "-o", exe,
+                    "-L" + libdir, "-lvenusaur_b200", "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([exe, "--width", str(W), "--height", str(H), "--frames", str(frames), "--max-depth", str(depth), "--device", "0", "--out", ppm],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    raw = open(ppm, "rb").read()
+    header = ("P6\n%d %d\n255\n" % (W, H)).encode()
+    assert raw.startswith(header) and len(raw) == len(header) + W * H * 3
+    img = np.frombuffer(raw[len(header):], np.uint8).reshape(H, W, 3)[::-1]      # the PPM's first row is the TOP of the picture, row 0 the bottom
+    cam = oracle_mod.rtiow_camera(W, H)
+    orc = oracle_mod.Oracle(rtiow)
+    want, segs = np.zeros((H, W, 4), np.float32), 0
+    for k in range(frames):
+        mean, ost = orc.render_mean(orc.params(cam, W, H, 16, k + 1, depth, atten=oracle_mod.ATTEN_FORWARD))
+        want, wimg = oracle_mod.accumulate_tonemap(want, mean, k > 0, np.float32(1.0) / np.float32(k + 1))
+        segs += ost.segments
+    assert np.abs(img.astype(np.int32) - wimg[..., :3].astype(np.int32)).max() <= 1
+    assert info["segments"] == segs and info["frames"] == frames and info["spheres"] == len(rtiow)
+    # an unknown option is an error, not a silent default
+    bad = subprocess.run([exe, "--frames", "1", "--opt", "no_such_knob=1", "--out", ""], capture_output=True, text=True)
+    assert bad.returncode != 0 and "no_such_knob" in bad.stderr

@@ -610,3 +610,31 @@ def test_hit_gate_never_fires_on_the_rtiow_scene(oracle_mod, rtiow):
     a, sa = orc.render_mean(orc.params(cam, W, H, 10, 1, 50, atten=oracle_mod.ATTEN_FORWARD, closest=oracle_mod.CLOSEST_BVH))
     b, sb = orc.render_mean(orc.params(cam, W, H, 10, 1, 50, atten=oracle_mod.ATTEN_FORWARD, closest=oracle_mod.CLOSEST_BVH | oracle_mod.CLOSEST_GATE))
     assert sa.segments == sb.segments and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize("wide,leaf", [(0, 2), (1, 1), (0, 1)])
+def test_negative_radius_hollow_glass_on_cpu(host_harness, oracle_mod, rtiow, wide, leaf):
+    """a NEGATIVE radius (sphere.h:17-28; RTIOW's hollow glass sphere).  The reference's own programs pin the oracle on
+    this scene (tests/golden/ref_render_hollow_*.npz); here the product's math and LBVH (|r| boxes, signed r in the normal
+    (p - c) / r of RayTracer.cu:257), run on the CPU, reproduce the oracle bit for bit -- pair nodes and the 4-wide nodes with the
+    huge list, two coincident centres included."""
+    W, H, spp, sub, depth = 48, 27, 4, 2, 50
+    spheres = oracle_mod.hollow_glass_scene(rtiow)
+    cam = oracle_mod.camera((3.0, 1.6, 4.0), (-3.0, -0.6, -4.0), 25.0, W / H, 0.02, 5.0)
+    hp = _hh_params(cam, W, H, spp, sub, depth)
+    mean = np.zeros((H, W, 4), np.float32)
+    segs, nv, st = C.c_uint64(), C.c_uint64(), C.c_uint64()
+    host_harness.hh_set_wide(wide)
+    try:
+        host_harness.hh_render_mean(spheres.ctypes.data_as(C.c_void_p), len(spheres), leaf, C.c_float(0.01), C.byref(hp),
+                                    mean.ctypes.data_as(C.c_void_p), C.byref(segs), C.byref(nv), C.byref(st))
+    finally:
+        host_harness.hh_set_wide(0)
+    orc = oracle_mod.Oracle(spheres)
+    want, stats = orc.render_mean(orc.params(cam, W, H, spp, sub, depth, atten=oracle_mod.ATTEN_FORWARD, closest=oracle_mod.CLOSEST_BRUTE))
+    assert segs.value == stats.segments
+    assert np.array_equal(mean.view(np.uint32), want.view(np.uint32))
+    # the inner surface really takes part: without the extra sphere the picture is another one
+    plain = oracle_mod.Oracle(rtiow)
+    other, _ = plain.render_mean(orc.params(cam, W, H, spp, sub, depth, atten=oracle_mod.ATTEN_FORWARD, closest=oracle_mod.CLOSEST_BRUTE))
+    assert (other.view(np.uint32) != want.view(np.uint32)).any(axis=-1).mean() > 0.05

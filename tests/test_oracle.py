@@ -87,8 +87,9 @@ def test_oracle_equals_reference_programs(oracle_mod, rtiow, path):
     g = np.load(path)
     W, H, spp, sub, depth = int(g["width"]), int(g["height"]), int(g["spp"]), int(g["subframe"]), int(g["max_depth"])
     cam = (g["origin"], g["u"], g["v"], g["w"], g["lens"])
-    orc = oracle_mod.Oracle(rtiow)
-    for closest in (oracle_mod.CLOSEST_BRUTE, oracle_mod.CLOSEST_BVH):
+    # ref_render_hollow_*: the scene with a negative-radius sphere (hollow glass), see gen_golden.py
+    orc = oracle_mod.Oracle(oracle_mod.hollow_glass_scene(rtiow) if "hollow" in os.path.basename(path) else rtiow)
+    for closest in (oracle_mod.CLOSEST_BRUTE, oracle_mod.CLOSEST_BVH, oracle_mod.CLOSEST_BVH | oracle_mod.CLOSEST_GATE):
         p = orc.params(cam, W, H, spp, sub, depth, atten=oracle_mod.ATTEN_UNWIND, draw=oracle_mod.DRAW_ZYX, closest=closest)
         mean, st = orc.render_mean(p)
         assert st.segments == int(g["segments"])

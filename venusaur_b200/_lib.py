@@ -61,6 +61,7 @@ SIGNATURES = {
     "vn_device_count": (C.c_int, []),
     "vn_version": (C.c_char_p, []),
     "vn_set_spheres": (C.c_int, [C.c_void_p, _P(vn_sphere), C.c_uint64]),
+    "vn_update_spheres": (C.c_int, [C.c_void_p, _P(vn_sphere), C.c_uint64]),
     "vn_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_double]),
     "vn_build_bvh": (C.c_int, [C.c_void_p]),
     "vn_get_bvh_info": (C.c_int, [C.c_void_p, _P(vn_bvh_info)]),

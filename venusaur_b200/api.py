@@ -157,6 +157,11 @@ class Context:
     def build_bvh(self):
         self._check(self.lib.vn_build_bvh(self.h), "vn_build_bvh")
 
+    def update_spheres(self, spheres: np.ndarray):
+        """Moved / re-coloured spheres (same count and order): upload + refit of the existing BVH."""
+        s = np.ascontiguousarray(spheres, SPHERE_DTYPE)
+        self._check(self.lib.vn_update_spheres(self.h, s.ctypes.data_as(C.POINTER(vn_sphere)), len(s)), "vn_update_spheres")
+
     def bvh_info(self) -> vn_bvh_info:
         info = vn_bvh_info()
         self._check(self.lib.vn_get_bvh_info(self.h, C.byref(info)), "vn_get_bvh_info")

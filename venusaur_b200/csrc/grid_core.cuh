@@ -29,7 +29,11 @@ struct GridHeader {                          // 104 bytes, lives in constant mem
 
 // radius used for cell overlap: |r| + 1 % + an absolute epsilon of the cell size (the DDA below is float arithmetic: a ray that
 // clips a cell by less than that must still find the sphere in the neighbouring cell)
-VN_HD float grid_pad_radius(float r, float min_cell) { return fabsf(r) * 1.01f + 1e-4f * min_cell; }
+// (+ 2^-17 of the coordinates' magnitude, like the BVH's leaf boxes, lbvh_core.cuh::leaf_pad: grazing hits whose float quadratic is noise
+// at the scale of the coordinates -- 33 of 272 M segments on the RTIOW frame, all on the radius-1000 ground -- are found by both structures)
+VN_HD float grid_pad_radius(const node_f4& s, float min_cell) {
+    return fabsf(s.w) * 1.01f + 1e-4f * min_cell + (fabsf(s.x) + fabsf(s.y) + fabsf(s.z) + fabsf(s.w)) * 7.62939453125e-06f;
+}
 
 VN_HD int grid_cell_coord(float p, float lo, float inv_cell, uint32_t res) {
     const float q = floorf((p - lo) * inv_cell);
@@ -40,7 +44,7 @@ VN_HD int grid_cell_coord(float p, float lo, float inv_cell, uint32_t res) {
 // Cell range covered by a (non-oversize) sphere.
 VN_HD void grid_sphere_cells(const GridHeader& g, const node_f4& s, int* c0, int* c1) {
     const float min_cell = fminf(g.cell[0], fminf(g.cell[1], g.cell[2]));
-    const float r = grid_pad_radius(s.w, min_cell);
+    const float r = grid_pad_radius(s, min_cell);
     const float c[3] = {s.x, s.y, s.z};
     for (int a = 0; a < 3; a++) {
         c0[a] = grid_cell_coord(c[a] - r, g.lo[a], g.inv_cell[a], g.res[a]);

@@ -40,6 +40,8 @@ void lbvh_free(LbvhScene& sc);
 struct LbvhWorkspace {
     void* ptr = nullptr;
     size_t bytes = 0;
+    uint64_t topology_n = 0;     // != 0: the workspace still holds the hierarchy (Karras nodes, parents, ranks) of the last build of that many spheres
+    bool topology_wide = false;
 };
 void lbvh_workspace_free(LbvhWorkspace& ws);
 
@@ -47,6 +49,10 @@ void lbvh_workspace_free(LbvhWorkspace& ws);
 int lbvh_build(const vn_sphere* d_spheres, uint64_t n, uint32_t leaf_size, float pad_rel, uint32_t sah_max_prims, uint32_t wide_max_prims, float huge_factor,
                int num_sms, cudaStream_t stream,
                LbvhScene& out, LbvhWorkspace& ws, uint32_t* launches, std::string& err);
+
+// The spheres moved: same hierarchy, new boxes (see lbvh.cu).  0 = done, 1 = not possible (rebuild), negative = error.
+int lbvh_refit(const vn_sphere* d_spheres, float pad_rel, float huge_factor, cudaStream_t stream, LbvhScene& out, LbvhWorkspace& ws,
+               uint32_t* launches, std::string& err);
 
 // Onesweep sort of device (key, value) pairs; returns 0/1 = which buffer pair holds the result, or -1.
 int radix_sort_pairs_device(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, uint32_t n, int key_bits, int num_sms,

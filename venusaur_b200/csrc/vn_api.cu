@@ -89,7 +89,8 @@ struct vn_context {
     int tile_state = 0;               // 0: nothing known (the next launch collects costs), 1: costs collected (sort before the next launch), 2: order valid
     struct TileSig { uint32_t w, h, r0, r1, spp, depth; float cam[13]; uint32_t pad_; uint64_t epoch; } tile_sig{};   // no implicit padding
     uint64_t bvh_epoch = 0;
-    uint32_t hit_gate = 1;            // "hit_gate": pair-node and L2 / HBM traversals apply the hit-point gate (vn_math.cuh::hit_gate_ok)
+    uint32_t hit_gate = 1;            // "hit_gate": 1 = scenes traversed from L2 / HBM apply the hit-point gate (vn_math.cuh::hit_gate_ok), 0 = never,
+                                      // 2 = the pair-node kernels apply it to small scenes too (the shared-memory wide-node kernels never do)
     uint32_t lean = 1;                // "lean": k_render_lean (16-bit links, no per-lane statistics, no spills) when the launch qualifies; 0 = k_render_async
     uint32_t warp_tiles = 1;          // "warp_tiles": k_render_async phase form hands whole tiles to warps (see path_kernels.cu); 0 = lanes take single pixels
     uint32_t async_done = 26;         // k_render_async: a traversal burst ends when this many lanes hold a finished ray (0 = k_render_persistent)
@@ -144,6 +145,11 @@ void free_wavefront(WavefrontBuffers& w) {
     w = WavefrontBuffers();
 }
 
+bool scene_fits_smem(const vn_context* c) {
+    const size_t need = scene_smem_bytes((uint32_t)c->scene.num_nodes, (uint32_t)c->scene.n);
+    return c->scene.n > 0 && need <= c->smem_scene_limit && need + 1024 <= c->smem_optin;
+}
+
 int fill_launch(vn_context* c, const vn_params* p, RenderLaunch& L) {
     memset(&L, 0, sizeof(L));
     L.cam.origin = to_f3(p->origin);
@@ -179,7 +185,7 @@ int fill_launch(vn_context* c, const vn_params* p, RenderLaunch& L) {
     L.leaf_vote = c->leaf_vote;
     L.async_done = c->async_done; L.async_node = c->async_node; L.async_leaf = c->async_leaf;
     L.grid_vote = c->grid_vote;
-    L.gate = c->hit_gate;
+    L.gate = (c->hit_gate == 2u || (c->hit_gate == 1u && !scene_fits_smem(c))) ? 1u : 0u;
     L.grid = c->grid.h; L.grid_start = c->grid.start; L.grid_refs = c->grid.refs;
     L.counters = c->d_counters;
     L.work_counter = reinterpret_cast<uint32_t*>(c->d_counters + 4);
@@ -189,11 +195,6 @@ int fill_launch(vn_context* c, const vn_params* p, RenderLaunch& L) {
     L.tiles_x_inv = L.tiles_x > 1u ? (uint32_t)(0x100000000ull / L.tiles_x) : 0xFFFFFFFFu;
     L.total_work = L.tiles_x * ((rows + 3u) / 4u) * 32u;
     return VN_OK;
-}
-
-bool scene_fits_smem(const vn_context* c) {
-    const size_t need = scene_smem_bytes((uint32_t)c->scene.num_nodes, (uint32_t)c->scene.n);
-    return c->scene.n > 0 && need <= c->smem_scene_limit && need + 1024 <= c->smem_optin;
 }
 
 }  // namespace
@@ -319,7 +320,7 @@ int vn_set_option(vn_handle c, const char* name, double value) {
     else if (k == "tile_order") { VN_REQUIRE(c, value >= 0 && value <= 3, "tile_order must be 0..3"); c->tile_order_opt = (uint32_t)value; c->tile_state = 0; }
     else if (k == "warp_tiles") { c->warp_tiles = value != 0 ? 1u : 0u; }
     else if (k == "lean") { c->lean = value != 0 ? 1u : 0u; }
-    else if (k == "hit_gate") { c->hit_gate = value != 0 ? 1u : 0u; }
+    else if (k == "hit_gate") { VN_REQUIRE(c, value == 0 || value == 1 || value == 2, "hit_gate must be 0, 1 or 2"); c->hit_gate = (uint32_t)value; }
     else if (k == "global_done") { VN_REQUIRE(c, value >= 1 && value <= 32, "global_done must be in [1,32]"); c->global_done = (uint32_t)value; }
     else if (k == "async_done") { VN_REQUIRE(c, value >= 0 && value <= 32, "async_done must be in [0,32]"); c->async_done = (uint32_t)value; }
     else if (k == "async_node") { VN_REQUIRE(c, value >= 0 && value <= 32, "async_node must be in [0,32] (0 = phase form: no votes inside the node / leaf phases)"); c->async_node = (uint32_t)value; }
@@ -381,6 +382,31 @@ int vn_build_bvh(vn_handle c) {
         const int grc = grid_build(c->scene.geom, c->scene.n, c->grid_max_per_cell, c->stream, c->grid, &launches, err);
         if (grc < 0) return fail(c, VN_ERR_CUDA, "vn_build_bvh: " + err);
     }
+    VN_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+    VN_CUDA(c, cudaStreamSynchronize(c->stream));
+    VN_CUDA(c, cudaEventElapsedTime(&c->stats.ms_build, c->ev[0], c->ev[1]));
+    c->stats.kernel_launches_total += launches;
+    c->bvh_valid = true;
+    c->bvh_epoch += 1;
+    return VN_OK;
+}
+
+int vn_update_spheres(vn_handle c, const vn_sphere* host_spheres, uint64_t n) {
+    VN_REQUIRE(c, c && host_spheres, "vn_update_spheres: NULL argument");
+    VN_REQUIRE(c, c->have_spheres && n == c->n_spheres && n > 0, "vn_update_spheres: the sphere count must be the one given to vn_set_spheres");
+    for (uint64_t i = 0; i < n; i++) VN_REQUIRE(c, host_spheres[i].type <= 2u, "vn_update_spheres: material type must be 0, 1 or 2");
+    VN_CUDA(c, cudaSetDevice(c->device));
+    VN_CUDA(c, cudaStreamSynchronize(c->stream));                 // no launch may still be reading the old records through the BVH arrays
+    VN_CUDA(c, cudaMemcpyAsync(c->d_spheres, host_spheres, n * sizeof(vn_sphere), cudaMemcpyHostToDevice, c->stream));
+    if (!c->bvh_valid) return VN_OK;
+    // refit-only rebuild: same hierarchy, new boxes (lbvh.cu::lbvh_refit); a full build when the hierarchy is no longer at hand
+    c->bvh_valid = false;
+    std::string err;
+    uint32_t launches = 0;
+    VN_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    const int rc = lbvh_refit(c->d_spheres, c->aabb_pad, c->huge_factor, c->stream, c->scene, c->bvh_ws, &launches, err);
+    if (rc < 0) return fail(c, VN_ERR_CUDA, "vn_update_spheres: " + err);
+    if (rc == 1 || c->grid.valid) return vn_build_bvh(c);
     VN_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     VN_CUDA(c, cudaStreamSynchronize(c->stream));
     VN_CUDA(c, cudaEventElapsedTime(&c->stats.ms_build, c->ev[0], c->ev[1]));
@@ -1010,7 +1036,7 @@ int vn_trace_rays(vn_handle c, const float* origins, const float* dirs, uint64_t
     RenderLaunch L;
     memset(&L, 0, sizeof(L));
     L.nodes = c->scene.nodes; L.geom = c->scene.geom; L.root_link = c->scene.root_link;
-    L.gate = c->hit_gate;
+    L.gate = (c->hit_gate == 2u || (c->hit_gate == 1u && !scene_fits_smem(c))) ? 1u : 0u;
     const bool use_grid = (flags & VN_GRID) != 0;
     VN_REQUIRE(c, !use_grid || c->grid.valid, "vn_trace_rays: VN_GRID but the scene has no grid");
     L.grid = c->grid.h; L.grid_start = c->grid.start; L.grid_refs = c->grid.refs;
