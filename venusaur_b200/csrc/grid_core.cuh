@@ -175,7 +175,7 @@ VN_HD void grid_ray_advance(const GridHeader& g, const uint16_t* __restrict__ st
 // Whole closest-hit query (host tests, trace-rays entry point; the path kernel inlines the same pieces around a warp vote).
 template <bool kCount>
 VN_HD void closest_hit_grid(const GridHeader& g, const uint16_t* __restrict__ start, const uint16_t* __restrict__ refs,
-                            const node_f4* __restrict__ geom, f3 o, f3 d, float& t_out, int& prim_out, TraceCounters& cnt) {
+                            const node_f4* __restrict__ geom, f3 o, f3 d, float& t_out, int& prim_out, TraceCounters& cnt, bool gate = false) {
     float tbest = kTMax;
     int prim = -1;
     const float a = dot(d, d);
@@ -185,7 +185,7 @@ VN_HD void closest_hit_grid(const GridHeader& g, const uint16_t* __restrict__ st
         const node_f4 sp = geom[s];
         if (kCount) cnt.spheres += 1;
         const float t = sphere_root(o, d, a, inv_a, sp.x, sp.y, sp.z, sp.w, kTMin, tbest);
-        if (t >= 0.0f) { tbest = t; prim = (int)s; }
+        if (t >= 0.0f && (!gate || hit_gate_ok(o, d, t, sp.x, sp.y, sp.z, sp.w))) { tbest = t; prim = (int)s; }
     }
     if (g.n_cells != 0u) {
         GridRay r;
@@ -197,7 +197,7 @@ VN_HD void closest_hit_grid(const GridHeader& g, const uint16_t* __restrict__ st
                 const node_f4 sp = geom[s];
                 if (kCount) cnt.spheres += 1;
                 const float t = sphere_root(o, d, a, inv_a, sp.x, sp.y, sp.z, sp.w, kTMin, tbest);
-                if (t >= 0.0f) { tbest = t; prim = (int)s; }
+                if (t >= 0.0f && (!gate || hit_gate_ok(o, d, t, sp.x, sp.y, sp.z, sp.w))) { tbest = t; prim = (int)s; }
             }
             grid_ray_advance(g, start, tbest, r);
         }

@@ -122,7 +122,7 @@ __device__ __forceinline__ void closest_hit_wide_vote(const float4* __restrict__
 template <bool kCount>
 __device__ __forceinline__ void closest_hit_grid_vote(const GridHeader& g, const uint16_t* __restrict__ start, const uint16_t* __restrict__ refs,
                                                       const float4* __restrict__ geom, uint32_t sphere_vote, f3 o, f3 d, float& t_out, int& prim_out,
-                                                      TraceCounters& cnt) {
+                                                      TraceCounters& cnt, bool gate) {
     float tbest = kTMax;
     int prim = -1;
     const float a = dot(d, d);
@@ -132,7 +132,7 @@ __device__ __forceinline__ void closest_hit_grid_vote(const GridHeader& g, const
         const float4 sp = geom[s];
         if (kCount) cnt.spheres += 1;
         const float t = sphere_root(o, d, a, inv_a, sp.x, sp.y, sp.z, sp.w, kTMin, tbest);
-        if (t >= 0.0f) { tbest = t; prim = (int)s; }
+        if (t >= 0.0f && (!gate || hit_gate_ok(o, d, t, sp.x, sp.y, sp.z, sp.w))) { tbest = t; prim = (int)s; }
     }
     GridRay r;
     grid_ray_setup(g, start, o, d, tbest, r);
@@ -149,7 +149,7 @@ __device__ __forceinline__ void closest_hit_grid_vote(const GridHeader& g, const
             const float4 sp = geom[s];
             if (kCount) cnt.spheres += 1;
             const float t = sphere_root(o, d, a, inv_a, sp.x, sp.y, sp.z, sp.w, kTMin, tbest);
-            if (t >= 0.0f) { tbest = t; prim = (int)s; }
+            if (t >= 0.0f && (!gate || hit_gate_ok(o, d, t, sp.x, sp.y, sp.z, sp.w))) { tbest = t; prim = (int)s; }
         }
         t_out = tbest;
         prim_out = prim;
@@ -165,7 +165,7 @@ __device__ __forceinline__ void closest_hit_grid_vote(const GridHeader& g, const
                 const float4 sp = geom[s];
                 if (kCount) cnt.spheres += 1;
                 const float t = sphere_root(o, d, a, inv_a, sp.x, sp.y, sp.z, sp.w, kTMin, tbest);
-                if (t >= 0.0f) { tbest = t; prim = (int)s; }
+                if (t >= 0.0f && (!gate || hit_gate_ok(o, d, t, sp.x, sp.y, sp.z, sp.w))) { tbest = t; prim = (int)s; }
             }
         } else if (!at_sphere) {
             grid_ray_advance(g, start, tbest, r);
@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_persistent(const __grid_
         }
         float t;
         int prim;
-        if (kGrid) closest_hit_grid_vote<kCount>(p.grid, g_start, g_refs, sc.geom, p.grid_vote, st.o, st.d, t, prim, cnt);
+        if (kGrid) closest_hit_grid_vote<kCount>(p.grid, g_start, g_refs, sc.geom, p.grid_vote, st.o, st.d, t, prim, cnt, p.gate != 0u);
         else if (kWide) {
             // the huge spheres first (RTIOW: the ground): one convergent sphere test instead of a leaf turn per ray
             float t0 = kTMax;
@@ -974,13 +974,13 @@ __global__ void k_trace_rays(const float4* __restrict__ nodes, const float4* __r
 
 __global__ void k_trace_rays_grid(const GridHeader g, const uint16_t* __restrict__ start, const uint16_t* __restrict__ refs, const float4* __restrict__ geom,
                                   const float* __restrict__ o, const float* __restrict__ d, uint64_t n, float* __restrict__ t_out,
-                                  int32_t* __restrict__ prim_out, const uint32_t* __restrict__ orig) {
+                                  int32_t* __restrict__ prim_out, const uint32_t* __restrict__ orig, bool gate) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float t;
     int prim;
     TraceCounters cnt{0u, 0u};
-    closest_hit_grid<false>(g, start, refs, geom, mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), t, prim, cnt);
+    closest_hit_grid<false>(g, start, refs, geom, mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]), t, prim, cnt, gate);
     t_out[i] = prim >= 0 ? t : -1.0f;
     prim_out[i] = prim >= 0 ? (int32_t)orig[prim] : -1;
 }
@@ -1124,7 +1124,7 @@ cudaError_t launch_test_rng(const uint32_t* v0, const uint32_t* v1, uint64_t n, 
 cudaError_t launch_trace_rays(const RenderLaunch& scene, const float* o, const float* d, uint64_t n, float* t_out, int32_t* prim_out,
                               const uint32_t* orig, bool grid, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    if (grid) k_trace_rays_grid<<<grid_for(n, 128), 128, 0, stream>>>(scene.grid, scene.grid_start, scene.grid_refs, scene.geom, o, d, n, t_out, prim_out, orig);
+    if (grid) k_trace_rays_grid<<<grid_for(n, 128), 128, 0, stream>>>(scene.grid, scene.grid_start, scene.grid_refs, scene.geom, o, d, n, t_out, prim_out, orig, scene.gate != 0u);
     else k_trace_rays<<<grid_for(n, 128), 128, 0, stream>>>(scene.nodes, scene.geom, scene.root_link, o, d, n, t_out, prim_out, orig, scene.gate != 0u);
     return cudaGetLastError();
 }
