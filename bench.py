@@ -256,12 +256,13 @@ def run_ours(args):
         allh = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(allh, mine)
         peer_ptrs, flag_base = [], []
+        B = ctx.IPC_BYTES                                 # handle of the allocation + offset of the tensor inside it
         for r in range(world):
             hb = bytes(allh[r].cpu().tolist())
-            peer_ptrs.append(accum.data_ptr() if r == rank else ctx.ipc_open(hb[:64]))
-            flag_base.append(my_flags if r == rank else ctx.ipc_open(hb[192:256]))
+            peer_ptrs.append(accum.data_ptr() if r == rank else ctx.ipc_open(hb[:B]))
+            flag_base.append(my_flags if r == rank else ctx.ipc_open(hb[3 * B:4 * B]))
             if r == 0:
-                peer_images = [images[i].data_ptr() for i in range(2)] if rank == 0 else [ctx.ipc_open(hb[64:128]), ctx.ipc_open(hb[128:192])]
+                peer_images = [images[i].data_ptr() for i in range(2)] if rank == 0 else [ctx.ipc_open(hb[B:2 * B]), ctx.ipc_open(hb[2 * B:3 * B])]
         peer_flag0 = [b for b in flag_base]              # flag 0: "my partial sums are complete"
         peer_flag1 = [b + 4 for b in flag_base]          # flag 1: "my reduce kernel is done (it no longer reads anybody's sums)"
 

@@ -173,6 +173,9 @@ VN_API int vn_reset_stats(vn_handle h);
 /* Launch timeline of the last VN_COUNTERS launch of the asynchronous path kernels, in out14[0..2]: ~(earliest CTA start), ~(time at which the
  * first lane found the tile tickets exhausted), latest warp end -- %globaltimer nanoseconds (tools/tail_probe.py turns them into the drain). */
 VN_API int vn_read_sched_counters(vn_handle h, uint64_t* out14);
+/* Drain histogram of the last VN_COUNTERS launch of k_render_lean: out[b] = lanes that ran out of work in the b-th 8.192 us bin after their
+ * CTA started, out[1024 + b] = the ray segments of the last pixels those lanes finished (filled by the cost-collecting launch of a view). */
+VN_API int vn_read_timeline(vn_handle h, uint32_t* out2048);
 
 /* ---- accumulation buffer: Params::accum (RayTracer.h:6), float4 per pixel ---- */
 VN_API int vn_read_accum(vn_handle h, float* host_rgba);              /* D2H, width*height*4 floats */
@@ -239,7 +242,10 @@ VN_API int vn_buffer_copy_to_host(int device, void* host_dst, const void* dev_sr
 VN_API int vn_stream_synchronize(int device, void* cuda_stream);
 VN_API void* vn_stream(vn_handle h);                                  /* the handle's cudaStream_t */
 /* CUDA IPC, to map another process's accumulation buffer for vn_reduce_tonemap_peers (one process per GPU) */
-VN_API int vn_ipc_export(vn_handle h, void* dev_ptr, unsigned char handle_out[64]);
+VN_API int vn_ipc_export(vn_handle h, void* dev_ptr, unsigned char handle_out[64]);     /* dev_ptr must be the base of its allocation */
+/* for a pointer INSIDE an allocation (e.g. a tensor of a caching allocator): the allocation's handle + the pointer's offset in it;
+ * the peer adds the offset to what vn_ipc_open returns */
+VN_API int vn_ipc_export_at(vn_handle h, void* dev_ptr, unsigned char handle_out[64], uint64_t* offset_out);
 VN_API int vn_ipc_open(vn_handle h, const unsigned char handle_in[64], void** dev_ptr);
 VN_API int vn_ipc_close(vn_handle h, void* dev_ptr);
 

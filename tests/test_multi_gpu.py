@@ -173,12 +173,13 @@ mine = torch.tensor(list(ctx.ipc_export(accum.data_ptr())) + list(ctx.ipc_export
 allh = [torch.empty_like(mine) for _ in range(world)]
 dist.all_gather(allh, mine)
 ptrs, fl, img0 = [], [], None
+B = ctx.IPC_BYTES
 for r in range(world):
     hb = bytes(allh[r].cpu().tolist())
-    ptrs.append(accum.data_ptr() if r == rank else ctx.ipc_open(hb[:64]))
-    fl.append(flags if r == rank else ctx.ipc_open(hb[128:192]))
+    ptrs.append(accum.data_ptr() if r == rank else ctx.ipc_open(hb[:B]))
+    fl.append(flags if r == rank else ctx.ipc_open(hb[2 * B:3 * B]))
     if r == 0:
-        img0 = image.data_ptr() if rank == 0 else ctx.ipc_open(hb[64:128])
+        img0 = image.data_ptr() if rank == 0 else ctx.ipc_open(hb[B:2 * B])
 ok = True
 for frame in range(2):                                   # two frames: the epoch flags are reused with a growing epoch
     ctx.reset_accum()

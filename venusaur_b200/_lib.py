@@ -67,6 +67,7 @@ SIGNATURES = {
     "vn_get_bvh_info": (C.c_int, [C.c_void_p, _P(vn_bvh_info)]),
     "vn_read_bvh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
     "vn_read_sched_counters": (C.c_int, [C.c_void_p, _P(C.c_uint64)]),
+    "vn_read_timeline": (C.c_int, [C.c_void_p, _P(C.c_uint32)]),
     "vn_read_grid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
     "vn_last_accel": (C.c_int, [C.c_void_p]),
     "vn_read_huge": (C.c_int, [C.c_void_p, _P(C.c_uint32)]),
@@ -111,6 +112,7 @@ SIGNATURES = {
     "vn_stream_synchronize": (C.c_int, [C.c_int, C.c_void_p]),
     "vn_stream": (C.c_void_p, [C.c_void_p]),
     "vn_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vn_ipc_export_at": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, _P(C.c_uint64)]),
     "vn_ipc_open": (C.c_int, [C.c_void_p, C.c_void_p, _P(C.c_void_p)]),
     "vn_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "vn_scene_rtiow_final": (C.c_uint32, [_P(vn_sphere), C.c_uint32]),

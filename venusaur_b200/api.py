@@ -251,6 +251,13 @@ class Context:
         M = (1 << 64) - 1
         return M - raw[0], M - raw[1], raw[2]
 
+    def timeline(self):
+        """(lanes retired, segments of their last pixels) per 8.192 us bin of the last VN_COUNTERS launch (vn_read_timeline)."""
+        raw = (C.c_uint32 * 2048)()
+        self._check(self.lib.vn_read_timeline(self.h, raw), "vn_read_timeline")
+        a = np.frombuffer(raw, np.uint32).copy()
+        return a[:1024], a[1024:]
+
     def stats(self) -> vn_stats:
         s = vn_stats()
         self._check(self.lib.vn_get_stats(self.h, C.byref(s)), "vn_get_stats")
@@ -303,16 +310,26 @@ class Context:
     def check_flags(self):
         self._check(self.lib.vn_check_flags(self.h), "vn_check_flags")
 
+    IPC_BYTES = 72
+
     def ipc_export(self, dev_ptr) -> bytes:
+        """72 bytes for the peer's ipc_open: the CUDA IPC handle of the ALLOCATION that holds dev_ptr + dev_ptr's offset inside it (a
+        tensor of torch's caching allocator usually sits in the middle of a segment it shares with other tensors)."""
         buf = (C.c_ubyte * 64)()
-        self._check(self.lib.vn_ipc_export(self.h, dev_ptr, buf), "vn_ipc_export")
-        return bytes(buf)
+        off = C.c_uint64()
+        self._check(self.lib.vn_ipc_export_at(self.h, dev_ptr, buf, C.byref(off)), "vn_ipc_export_at")
+        return bytes(buf) + int(off.value).to_bytes(8, "little")
 
     def ipc_open(self, handle: bytes) -> int:
-        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
-        p = C.c_void_p()
-        self._check(self.lib.vn_ipc_open(self.h, buf, C.byref(p)), "vn_ipc_open")
-        return p.value
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle[:64])
+        off = int.from_bytes(handle[64:72], "little") if len(handle) >= 72 else 0
+        key = bytes(handle[:64])
+        opened = self.__dict__.setdefault("_ipc_opened", {})
+        if key not in opened:              # one allocation may be opened only once per process
+            p = C.c_void_p()
+            self._check(self.lib.vn_ipc_open(self.h, buf, C.byref(p)), "vn_ipc_open")
+            opened[key] = p.value
+        return opened[key] + off
 
     def ipc_close(self, dev_ptr):
         self._check(self.lib.vn_ipc_close(self.h, dev_ptr), "vn_ipc_close")

@@ -46,6 +46,8 @@ struct RenderLaunch {
     const uint32_t* tile_order;      // ticket >> 5 -> tile index, most expensive tiles first (null = row-major); see vn_api.cu::prepare_tile_order
     uint32_t* tile_cost;             // when non-null the kernel records every finished pixel's ray segments in its tile's entries:
     uint32_t tile_cost_stride;       //   tile_cost[tile] += segments, tile_cost[tile_cost_stride + tile] = max(.., segments)
+    uint32_t* timeline;              // instrumented launches of k_render_lean: [0..1024) lanes retired per 8 us bin since the CTA's start, [1024..2048) the ray
+                                     // segments of the last pixel those lanes finished (0 outside the cost-collecting launch); null otherwise
     uint32_t gate;                   // 1: the pair-node / L2-HBM traversals apply the hit-point gate (vn_math.cuh::hit_gate_ok); the shared-memory wide-node kernels ignore it
     uint32_t tiles_x_inv;            // floor(2^32 / tiles_x): tile / tiles_x = __umulhi(tile, tiles_x_inv) plus at most two corrections (tile_row_col)
 };

@@ -697,6 +697,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
     st.o = st.d = st.thr = mk3(0.0f); st.seed = 0; st.depth = 0;
     uint32_t w_seg = 0u, w_path = 0u;  // warp-uniform: segments shaded / camera rays started by this warp
     uint32_t px_seg = 0u;              // kCost: ray segments of the current pixel (tile cost feedback)
+    uint32_t last_seg = 0u;            // kCount: ray segments of the pixel this lane finished last (launch timeline)
+    const unsigned long long t_start = kCount ? global_ns() : 0ull;
     TraceCounters cnt{0u, 0u};
     // traversal state, alive across the shading of other lanes.  kGlobal: pair nodes from L2 / HBM, 32-bit links (kEmptyScene = done).
     typedef typename std::conditional<kGlobal, uint32_t, uint16_t>::type StackWord;
@@ -732,6 +734,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
             const uint32_t px = pxy & 0xFFFFu, py = pxy >> 16;
             finish_pixel(p, py * p.width + px, sum);
             if (kCost) { uint32_t* tc = p.tile_cost + ((py - p.row_begin) >> 2) * p.tiles_x + (px >> 3); atomicAdd(tc, px_seg); atomicMax(tc + p.tile_cost_stride, px_seg); }
+            if (kCount && kCost) last_seg = px_seg;
             lane_state = kLaneNoPixel;
         }
         // warp-owned tiles (see k_render_async): one global ticket per 8x4 tile, pixels handed to the asking lanes in order
@@ -744,7 +747,18 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
                     if ((threadIdx.x & 31u) == 0u) t = atomicAdd(p.work_counter, 1u);
                     t = __shfl_sync(kFull, t, 0);
                     if (t >= (p.total_work >> 5)) {               // no tiles left: the asking lanes only vote from now on
-                        if (need) { lane_state = kLaneRetired; if (kCount) atomicMax(&p.counters[9], ~global_ns()); }
+                        if (need) {
+                            lane_state = kLaneRetired;
+                            if (kCount) {
+                                const unsigned long long now = global_ns();
+                                atomicMax(&p.counters[9], ~now);
+                                if (p.timeline) {
+                                    const uint32_t bin = (uint32_t)min((unsigned long long)1023u, (now - t_start) >> 13);
+                                    atomicAdd(p.timeline + bin, 1u);
+                                    atomicAdd(p.timeline + 1024u + bin, last_seg);
+                                }
+                            }
+                        }
                         break;
                     }
                     w_tile = p.tile_order ? __ldg(p.tile_order + t) : t;

@@ -54,6 +54,7 @@ struct vn_context {
     bool copied_valid[2] = {false, false};
     int pipe_flip = 0;
 
+    uint32_t* d_timeline = nullptr;             // 2048 words, VN_COUNTERS launches of k_render_lean (kernels.h::RenderLaunch::timeline)
     uint32_t* d_flags = nullptr;                // 64 words: [0..61] epoch flags for cross-process ordering (vn_signal / vn_wait_flags), [63] error word
     unsigned long long* d_counters = nullptr;   // 4 x u64 + work ticket (u32) at +32 bytes; [8..11) the launch timeline of the instrumented k_render_lean / k_render_async
     unsigned long long* h_counters = nullptr;   // pinned: kStatSlots x 256 bytes, one slot per launch in flight (VN_ASYNC renders never wait for each other on the host)
@@ -185,6 +186,7 @@ int fill_launch(vn_context* c, const vn_params* p, RenderLaunch& L) {
     L.leaf_vote = c->leaf_vote;
     L.async_done = c->async_done; L.async_node = c->async_node; L.async_leaf = c->async_leaf;
     L.grid_vote = c->grid_vote;
+    L.timeline = nullptr;
     L.gate = (c->hit_gate == 2u || (c->hit_gate == 1u && !scene_fits_smem(c))) ? 1u : 0u;
     L.grid = c->grid.h; L.grid_start = c->grid.start; L.grid_refs = c->grid.refs;
     L.counters = c->d_counters;
@@ -230,6 +232,8 @@ static int create_resources(vn_context* c) {
     }
     VN_CUDA(c, cudaMalloc(&c->d_counters, 256));
     VN_CUDA(c, cudaMemset(c->d_counters, 0, 256));
+    VN_CUDA(c, cudaMalloc(&c->d_timeline, 8192));
+    VN_CUDA(c, cudaMemset(c->d_timeline, 0, 8192));
     VN_CUDA(c, cudaMalloc(&c->d_flags, 256));
     VN_CUDA(c, cudaMemset(c->d_flags, 0, 256));
     VN_CUDA(c, cudaHostAlloc(&c->h_counters, 256 * kStatSlots, cudaHostAllocDefault));
@@ -287,7 +291,7 @@ void vn_destroy(vn_handle c) {
     grid_free(c->grid);
     lbvh_workspace_free(c->bvh_ws);
     free_wavefront(c->wf); c->wf_sample_floats_ = 0;
-    cudaFree(c->d_tile_cost); cudaFree(c->d_tile_sort); cudaFree(c->d_spheres); cudaFree(c->accum_own); cudaFree(c->image_tmp); cudaFree(c->d_counters); cudaFree(c->d_flags);
+    cudaFree(c->d_tile_cost); cudaFree(c->d_tile_sort); cudaFree(c->d_spheres); cudaFree(c->accum_own); cudaFree(c->image_tmp); cudaFree(c->d_counters); cudaFree(c->d_flags); cudaFree(c->d_timeline);
     cudaFreeHost(c->h_counters);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (auto& pr : c->ev_slot) for (auto& ev : pr) if (ev) cudaEventDestroy(ev);
@@ -444,6 +448,14 @@ int vn_read_sched_counters(vn_handle c, uint64_t* out14) {
     if (c->slots_pending) { const int rc = vn_synchronize(c); if (rc != VN_OK) return rc; }
     const unsigned long long* last = c->h_counters + 32u * ((c->slot_head + kStatSlots - 1u) % kStatSlots);
     for (int i = 0; i < 14; i++) out14[i] = last[8 + i];
+    return VN_OK;
+}
+
+int vn_read_timeline(vn_handle c, uint32_t* out2048) {
+    VN_REQUIRE(c, c && out2048, "vn_read_timeline: NULL argument");
+    VN_CUDA(c, cudaSetDevice(c->device));
+    VN_CUDA(c, cudaMemcpyAsync(out2048, c->d_timeline, 8192, cudaMemcpyDeviceToHost, c->stream));
+    VN_CUDA(c, cudaStreamSynchronize(c->stream));
     return VN_OK;
 }
 
@@ -715,6 +727,7 @@ int vn_render(vn_handle c, const vn_params* p) {
     const bool exact_build = !(p->flags & VN_FAST);
     const bool count = (p->flags & VN_COUNTERS) != 0;
     uint32_t launches = 0;
+    if (count) { L.timeline = c->d_timeline; VN_CUDA(c, cudaMemsetAsync(c->d_timeline, 0, 8192, c->stream)); }
 
     const bool pipelined = host_image && (p->flags & VN_ASYNC);
     // a launch in flight owns a slot of the pinned counter ring; only a full ring makes the host wait (VN_ASYNC renders queue back to back)
@@ -934,13 +947,35 @@ int vn_stream_synchronize(int device, void* cuda_stream) {
     return VN_OK;
 }
 
-int vn_ipc_export(vn_handle c, void* dev_ptr, unsigned char handle_out[64]) {
-    VN_REQUIRE(c, c && dev_ptr && handle_out, "vn_ipc_export: NULL argument");
+// A CUDA IPC handle names a whole ALLOCATION: for a pointer into the middle of one (a tensor carved out of a caching allocator's
+// segment) cudaIpcGetMemHandle silently returns the handle of the segment, and the peer that opens it gets the segment's base.
+// vn_ipc_export_at reports the pointer's offset inside its allocation (driver entry point cuMemGetAddressRange, looked up at run
+// time: no link-time dependency on libcuda); vn_ipc_export refuses pointers that are not the base of theirs.
+int vn_ipc_export_at(vn_handle c, void* dev_ptr, unsigned char handle_out[64], uint64_t* offset_out) {
+    VN_REQUIRE(c, c && dev_ptr && handle_out && offset_out, "vn_ipc_export_at: NULL argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
     VN_CUDA(c, cudaSetDevice(c->device));
+    typedef int (*GetRange)(unsigned long long*, size_t*, unsigned long long);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    VN_CUDA(c, cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres));
+    VN_REQUIRE(c, fn && qres == cudaDriverEntryPointSuccess, "vn_ipc_export_at: cuMemGetAddressRange is not available");
+    unsigned long long base = 0;
+    size_t size = 0;
+    const int drc = reinterpret_cast<GetRange>(fn)(&base, &size, (unsigned long long)(uintptr_t)dev_ptr);
+    VN_REQUIRE(c, drc == 0 && base != 0, "vn_ipc_export_at: not a device allocation");
     cudaIpcMemHandle_t hd;
-    VN_CUDA(c, cudaIpcGetMemHandle(&hd, dev_ptr));
+    VN_CUDA(c, cudaIpcGetMemHandle(&hd, reinterpret_cast<void*>((uintptr_t)base)));
     memcpy(handle_out, &hd, 64);
+    *offset_out = (uint64_t)((unsigned long long)(uintptr_t)dev_ptr - base);
+    return VN_OK;
+}
+
+int vn_ipc_export(vn_handle c, void* dev_ptr, unsigned char handle_out[64]) {
+    uint64_t offset = 0;
+    const int rc = vn_ipc_export_at(c, dev_ptr, handle_out, &offset);
+    if (rc != VN_OK) return rc;
+    VN_REQUIRE(c, offset == 0, "vn_ipc_export: the pointer is not the base of its allocation (an IPC handle names the whole allocation): use vn_ipc_export_at");
     return VN_OK;
 }
 
