@@ -134,10 +134,10 @@ VN_API int vn_set_spheres(vn_handle h, const vn_sphere* host_spheres, uint64_t n
  * lanes stand on nodes], "async_leaf" [8], "warp_tiles" [1: in the phase form a warp takes a whole 8x4-pixel tile with one ticket and hands the pixels to its own
  * lanes; 0 = every lane takes single pixels from the global ticket], "tile_order" [1: once a view has been
  * rendered once, its 8x4-pixel tiles are handed out most expensive first (ray segments per tile, counted by that first launch); 0 = row-major, 2 = by the most
- * expensive pixel, 3 = max(sum / 8, most expensive pixel)], "wide_global" [0], "threads", "blocks_per_sm", "smem_scene_limit".
+ * expensive pixel, 3 = max(sum / 8, most expensive pixel), 4 = like 1 with the tiles in which no path hit anything last], "wide_global" [0], "threads", "blocks_per_sm", "smem_scene_limit".
  * "lean" [1: k_render_lean -- 16-bit links, newest stack entry in a register, per-warp statistics -- for shared-memory scenes, and its
  * asynchronous form over pair nodes for scenes traversed from L2 / HBM; 0 = k_render_async / k_render_persistent], "global_done" [16: the burst
- * threshold of the L2 / HBM form], "hit_gate" [1: scenes traversed from L2 / HBM only count a root whose hit point lies inside the sphere's slightly
+ * threshold of the L2 / HBM form], "global_ctas" [5: its CTAs of 256 threads per SM, 4..6], "hit_gate" [1: scenes traversed from L2 / HBM only count a root whose hit point lies inside the sphere's slightly
  * grown box; 0 = never; 2 = the pair-node kernels also on small scenes], "wavefront_slots".  Options that change the BVH invalidate it (call vn_build_bvh again). */
 VN_API int vn_set_option(vn_handle h, const char* name, double value);
 VN_API int vn_build_bvh(vn_handle h);

@@ -885,12 +885,17 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
 // Sort keys of the cost-ordered tile schedule: most urgent tile first = smallest key.  A tile's urgency is its total cost (ray segments
 // of its 32 pixels in one launch, mode 1), its most expensive pixel (mode 2), or the larger of the total / 8 and the most expensive
 // pixel (mode 3: a cheap tile that holds one glass pixel must not be handed out last).  24 key bits are plenty.
-__global__ void __launch_bounds__(256) k_tile_keys(const uint32_t* __restrict__ cost, uint32_t stride, uint32_t n, uint32_t mode, uint32_t* __restrict__ keys,
+// Mode 4 (the default): by total cost, but tiles in which NO path ever hit anything (their most expensive pixel cost exactly spp segments: sky)
+// go last, whatever their order among themselves.  Their cost is deterministic -- spp segments per pixel, every launch -- whereas a tile that
+// was cheap in the collecting launch but touches a glass silhouette can hold a 100-segment pixel in the next one; handed out among the last,
+// such pixels were the thin tail that kept a launch alive for its last 0.19 ms (tools/tail_probe.py: 0.6 % of the lanes, 3.6 % of the time).
+__global__ void __launch_bounds__(256) k_tile_keys(const uint32_t* __restrict__ cost, uint32_t stride, uint32_t n, uint32_t mode, uint32_t spp, uint32_t* __restrict__ keys,
                                                    uint32_t* __restrict__ vals) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t sum = cost[i], mx = cost[stride + i];
     uint32_t c = mode == 2u ? mx : (mode == 3u ? max(sum >> 3, mx) : sum);
+    if (mode == 4u) c = mx > spp ? sum + 1u : 0u;
     c = c < 0x00FFFFFFu ? c : 0x00FFFFFFu;
     keys[i] = 0x00FFFFFFu - c;
     vals[i] = i;
@@ -1036,8 +1041,10 @@ inline uint32_t grid_for(uint64_t n, int threads) { return (uint32_t)((n + threa
 namespace {
 typedef void (*PathKernel)(const RenderLaunch);
 PathKernel pick_kernel(bool scene_in_smem, bool count, bool octant, bool wide = false, int threads = 1024, bool grid = false, bool async = false, bool phase = false, bool warp_tiles = false,
-                       bool lean = false, bool cost = false) {
-    if (lean && !scene_in_smem && !wide && !grid) {        // pair nodes from L2 / HBM, asynchronous (k_render_lean<kGlobal>)
+                       bool lean = false, bool cost = false, int global_ctas = 4) {
+    if (lean && !scene_in_smem && !wide && !grid) {        // pair nodes from L2 / HBM, asynchronous (k_render_lean<kGlobal>); 4, 5 or 6 CTAs of 256 threads per SM (64 / 48 / 40 registers)
+        if (global_ctas >= 6) return count ? (cost ? k_render_lean<true, true, 256, true, 6> : k_render_lean<true, false, 256, true, 6>) : (cost ? k_render_lean<false, true, 256, true, 6> : k_render_lean<false, false, 256, true, 6>);
+        if (global_ctas == 5) return count ? (cost ? k_render_lean<true, true, 256, true, 5> : k_render_lean<true, false, 256, true, 5>) : (cost ? k_render_lean<false, true, 256, true, 5> : k_render_lean<false, false, 256, true, 5>);
         return count ? (cost ? k_render_lean<true, true, 256, true, 4> : k_render_lean<true, false, 256, true, 4>) : (cost ? k_render_lean<false, true, 256, true, 4> : k_render_lean<false, false, 256, true, 4>);
     }
     if (lean && async && phase && warp_tiles && wide && scene_in_smem && !grid) {
@@ -1070,9 +1077,9 @@ PathKernel pick_kernel(bool scene_in_smem, bool count, bool octant, bool wide = 
 }
 }  // namespace
 
-int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool count, bool octant, bool wide, bool grid, bool lean) {
+int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool count, bool octant, bool wide, bool grid, bool lean, int global_ctas) {
     int nb = 0;
-    PathKernel k = pick_kernel(scene_in_smem, count, octant, wide, threads, grid, false, false, false, lean);
+    PathKernel k = pick_kernel(scene_in_smem, count, octant, wide, threads, grid, false, false, false, lean, false, global_ctas);
     if (smem_bytes > 48 * 1024 && cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) return -1;
     const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, threads, smem_bytes);
     return e == cudaSuccess ? nb : -1;
@@ -1080,7 +1087,7 @@ int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool c
 
 cudaError_t launch_render_persistent(const RenderLaunch& p, const KernelConfig& cfg, cudaStream_t stream) {
     PathKernel k = pick_kernel(cfg.scene_in_smem, cfg.count, cfg.octant, cfg.wide, cfg.threads, cfg.grid, cfg.async, cfg.async && p.async_node == 0u, cfg.warp_tiles,
-                               cfg.lean, p.tile_cost != nullptr);
+                               cfg.lean, p.tile_cost != nullptr, cfg.global_ctas);
     if (cfg.smem_bytes > 48 * 1024) {
         const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes);
         if (e != cudaSuccess) return e;
@@ -1089,9 +1096,9 @@ cudaError_t launch_render_persistent(const RenderLaunch& p, const KernelConfig& 
     return cudaGetLastError();
 }
 
-cudaError_t launch_tile_keys(const uint32_t* cost, uint32_t stride, uint32_t n, uint32_t mode, uint32_t* keys, uint32_t* vals, cudaStream_t stream) {
+cudaError_t launch_tile_keys(const uint32_t* cost, uint32_t stride, uint32_t n, uint32_t mode, uint32_t spp, uint32_t* keys, uint32_t* vals, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    k_tile_keys<<<(n + 255u) / 256u, 256, 0, stream>>>(cost, stride, n, mode, keys, vals);
+    k_tile_keys<<<(n + 255u) / 256u, 256, 0, stream>>>(cost, stride, n, mode, spp, keys, vals);
     return cudaGetLastError();
 }
 

@@ -82,7 +82,7 @@ struct vn_context {
     int wide_threads = 1024;          // CTA size of the wide-node path kernel (one CTA per SM): 512, 768 or 1024 (64 registers per lane at 1024)
     uint32_t leaf_vote = 0;           // see closest_hit_wide_vote (path_kernels.cu); 0 = while-while
     // cost-ordered tile schedule (prepare_tile_order): per-tile ray segments of the previous launch of the same view, sorted descending
-    uint32_t tile_order_opt = 1;      // "tile_order": 0 = row-major tickets, 1 = tiles sorted by the ray segments of their 32 pixels, 2 = by their most expensive pixel, 3 = by max(sum / 8, most expensive pixel)
+    uint32_t tile_order_opt = 1;      // "tile_order": 0 = row-major tickets, 1 = tiles sorted by the ray segments of their 32 pixels, 2 = by their most expensive pixel, 3 = by max(sum / 8, most expensive pixel), 4 = like 1 with the all-miss tiles last
     uint32_t* d_tile_cost = nullptr;  // [2 * tile_cap]: sum | max of the pixels' ray segments
     uint32_t* d_tile_sort = nullptr;  // [4 * tile_cap]: keys, values and their alternates for the radix sort
     const uint32_t* d_tile_order = nullptr;
@@ -95,6 +95,8 @@ struct vn_context {
     uint32_t lean = 1;                // "lean": k_render_lean (16-bit links, no per-lane statistics, no spills) when the launch qualifies; 0 = k_render_async
     uint32_t warp_tiles = 1;          // "warp_tiles": k_render_async phase form hands whole tiles to warps (see path_kernels.cu); 0 = lanes take single pixels
     uint32_t async_done = 26;         // k_render_async: a traversal burst ends when this many lanes hold a finished ray (0 = k_render_persistent)
+    int global_ctas = 5;              // "global_ctas": 4, 5 or 6 CTAs of 256 threads per SM for the L2 / HBM form (64 / 48 / 40 registers: more warps to hide latency,
+                                      // a few spills each; measured 4 / 5 / 6: 1 M spheres 3046 / 3037 / 2961, 16 M spheres 1726 / 1765 / 1779 Mrays/s)
     uint32_t global_done = 16;        // the same threshold for scenes traversed from L2 / HBM (k_render_lean<kGlobal>): long traversals, so shade earlier (measured:
                                       // 1 M spheres 2.21 -> 2.49 Grays/s, 16 M spheres 1.11 -> 1.60 against 26)
     uint32_t async_node = 0, async_leaf = 8;   // async_node 0 = phase form (no votes inside the node / leaf phases), the default
@@ -321,10 +323,11 @@ int vn_set_option(vn_handle c, const char* name, double value) {
     else if (k == "grid_max_per_cell") { VN_REQUIRE(c, value >= 1 && value <= 65535, "grid_max_per_cell must be in [1,65535]"); c->grid_max_per_cell = (uint32_t)value; c->bvh_valid = false; }
     else if (k == "huge_factor") { VN_REQUIRE(c, value >= 0, "huge_factor must be >= 0"); c->huge_factor = (float)value; c->bvh_valid = false; }
     else if (k == "wide_threads") { VN_REQUIRE(c, value == 512 || value == 768 || value == 1024, "wide_threads must be 512, 768 or 1024"); c->wide_threads = (int)value; }
-    else if (k == "tile_order") { VN_REQUIRE(c, value >= 0 && value <= 3, "tile_order must be 0..3"); c->tile_order_opt = (uint32_t)value; c->tile_state = 0; }
+    else if (k == "tile_order") { VN_REQUIRE(c, value >= 0 && value <= 4, "tile_order must be 0..4"); c->tile_order_opt = (uint32_t)value; c->tile_state = 0; }
     else if (k == "warp_tiles") { c->warp_tiles = value != 0 ? 1u : 0u; }
     else if (k == "lean") { c->lean = value != 0 ? 1u : 0u; }
     else if (k == "hit_gate") { VN_REQUIRE(c, value == 0 || value == 1 || value == 2, "hit_gate must be 0, 1 or 2"); c->hit_gate = (uint32_t)value; }
+    else if (k == "global_ctas") { VN_REQUIRE(c, value == 4 || value == 5 || value == 6, "global_ctas must be 4, 5 or 6"); c->global_ctas = (int)value; }
     else if (k == "global_done") { VN_REQUIRE(c, value >= 1 && value <= 32, "global_done must be in [1,32]"); c->global_done = (uint32_t)value; }
     else if (k == "async_done") { VN_REQUIRE(c, value >= 0 && value <= 32, "async_done must be in [0,32]"); c->async_done = (uint32_t)value; }
     else if (k == "async_node") { VN_REQUIRE(c, value >= 0 && value <= 32, "async_node must be in [0,32] (0 = phase form: no votes inside the node / leaf phases)"); c->async_node = (uint32_t)value; }
@@ -690,7 +693,7 @@ static int prepare_tile_order(vn_handle c, const vn_params* p, RenderLaunch& L) 
     }
     if (c->tile_state == 1) {
         uint32_t *k0 = c->d_tile_sort, *v0 = k0 + c->tile_cap, *k1 = v0 + c->tile_cap, *v1 = k1 + c->tile_cap;
-        VN_CUDA(c, exact::launch_tile_keys(c->d_tile_cost, c->tile_cap, n_tiles, c->tile_order_opt, k0, v0, c->stream));
+        VN_CUDA(c, exact::launch_tile_keys(c->d_tile_cost, c->tile_cap, n_tiles, c->tile_order_opt, p->samples_per_pixel, k0, v0, c->stream));
         std::string err;
         uint32_t launches = 0;
         const int which = radix_sort_pairs_device(k0, v0, k1, v1, n_tiles, 24, c->num_sms, c->stream, &launches, err);
@@ -768,11 +771,11 @@ int vn_render(vn_handle c, const vn_params* p) {
         else if (cfg.octant) { cfg.smem_bytes = oct_bytes; cfg.threads = 1024; }
         else if (cfg.threads > 256) cfg.threads = 256;
         // scenes traversed from L2 / HBM (pair nodes): the asynchronous form of the path kernel (k_render_lean<kGlobal>, 256-thread CTAs)
-        if (!cfg.scene_in_smem && !cfg.wide && !cfg.grid && c->lean != 0u && c->async_done > 0u && p->width < 65536u && p->height < 65536u) { cfg.lean = true; cfg.threads = 256; L.async_done = c->global_done; }
+        if (!cfg.scene_in_smem && !cfg.wide && !cfg.grid && c->lean != 0u && c->async_done > 0u && p->width < 65536u && p->height < 65536u) { cfg.lean = true; cfg.threads = 256; cfg.global_ctas = c->global_ctas; L.async_done = c->global_done; }
         int per_sm = (cfg.octant || (cfg.wide && cfg.scene_in_smem)) ? 1 : c->blocks_per_sm;
         if (per_sm <= 0) {
-            per_sm = exact_build ? exact::max_blocks_per_sm(cfg.threads, cfg.smem_bytes, cfg.scene_in_smem, count, cfg.octant, cfg.wide, cfg.grid, cfg.lean)
-                                 : fast::max_blocks_per_sm(cfg.threads, cfg.smem_bytes, cfg.scene_in_smem, count, cfg.octant, cfg.wide, cfg.grid, cfg.lean);
+            per_sm = exact_build ? exact::max_blocks_per_sm(cfg.threads, cfg.smem_bytes, cfg.scene_in_smem, count, cfg.octant, cfg.wide, cfg.grid, cfg.lean, cfg.global_ctas)
+                                 : fast::max_blocks_per_sm(cfg.threads, cfg.smem_bytes, cfg.scene_in_smem, count, cfg.octant, cfg.wide, cfg.grid, cfg.lean, cfg.global_ctas);
             if (per_sm <= 0) return fail(c, VN_ERR_CUDA, "vn_render: occupancy query failed for the path kernel");
         }
         cfg.blocks = c->num_sms * per_sm;
