@@ -176,6 +176,8 @@ VN_API int vn_read_sched_counters(vn_handle h, uint64_t* out14);
 /* Drain histogram of the last VN_COUNTERS launch of k_render_lean: out[b] = lanes that ran out of work in the b-th 8.192 us bin after their
  * CTA started, out[1024 + b] = the ray segments of the last pixels those lanes finished (filled by the cost-collecting launch of a view). */
 VN_API int vn_read_timeline(vn_handle h, uint32_t* out2048);
+/* The same plus out[2048 + b] = work tiles fetched in bin b and out[3072 + b] = ray segments shaded in bin b: the launch's throughput over time. */
+VN_API int vn_read_timeline_ex(vn_handle h, uint32_t* out4096);
 
 /* ---- accumulation buffer: Params::accum (RayTracer.h:6), float4 per pixel ---- */
 VN_API int vn_read_accum(vn_handle h, float* host_rgba);              /* D2H, width*height*4 floats */

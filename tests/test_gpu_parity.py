@@ -512,6 +512,61 @@ def test_async_kernel_equals_persistent_kernel(ctx, oracle_mod, rtiow, threads):
 
 
 
+def test_sample_stealing_keeps_the_accumulation_buffer(ctx, oracle_mod, rtiow):
+    """Drain of k_render_lean: once the tile tickets are exhausted, idle lanes of a warp trace single samples of pixels other lanes of the
+    warp still hold (camera seed chain replayed, radiance handed back and summed by the owner in sample order).  It only changes WHO traces
+    a sample: accumulation buffer, image, segment and path counts are those of the kernel without stealing and the oracle's -- frames
+    of a few tiles (every warp is in its drain from the start), ragged frames, spp from 1 to 100, progressive launches, row shards, and
+    a scene traversed from L2 / HBM (k_render_lean<kGlobal>)."""
+    ctx.set_spheres(rtiow)
+    ctx.build_bvh()
+    try:
+        ctx.set_option("steal_smem", 1)                          # (off by default for scenes traversed from shared memory)
+        for (W, H, spp, sub, depth) in ((64, 36, 16, 3, 50), (33, 17, 37, 1, 50), (8, 4, 100, 2, 12), (200, 120, 2, 5, 50), (40, 30, 1, 1, 50)):
+            cam = vb.rtiow_camera(W, H)
+            ctx.set_option("steal", 0)
+            e, ie, se = render(ctx, cam, W, H, spp, sub, depth)
+            ctx.set_option("steal", 1)
+            g, ig, sg = render(ctx, cam, W, H, spp, sub, depth)
+            g2, _, sg2 = render(ctx, cam, W, H, spp, sub, depth, flags=VN_COUNTERS)
+            assert np.array_equal(g.view(np.uint32), e.view(np.uint32)) and np.array_equal(ig, ie), (W, H, spp)
+            assert np.array_equal(g2.view(np.uint32), e.view(np.uint32))
+            assert (sg.segments, sg.paths) == (se.segments, se.paths) == (sg2.segments, sg2.paths)
+            ctx.set_option("steal", 3)                            # lanes keep their last two samples
+            g3, _, sg3 = render(ctx, cam, W, H, spp, sub, depth)
+            assert np.array_equal(g3.view(np.uint32), e.view(np.uint32)) and (sg3.segments, sg3.paths) == (se.segments, se.paths)
+            orc = oracle_mod.Oracle(rtiow)
+            want, ost = orc.render_mean(orc.params(cam.frame(), W, H, spp, sub, depth, atten=oracle_mod.ATTEN_FORWARD))
+            assert np.array_equal(g.view(np.uint32), want.view(np.uint32)) and sg.segments == ost.segments
+        # progressive accumulation + row shards
+        W, H = 96, 50
+        cam = vb.rtiow_camera(W, H)
+        outs = []
+        for steal in (0, 1):
+            ctx.set_option("steal", steal)
+            render(ctx, cam, W, H, 8, 1, 50)
+            render(ctx, cam, W, H, 8, 2, 50, accum_count=1, rows=(0, 23))
+            a, i, _ = render(ctx, cam, W, H, 8, 2, 50, accum_count=1, rows=(23, 50))
+            outs.append((a, i))
+        assert np.array_equal(outs[0][0].view(np.uint32), outs[1][0].view(np.uint32)) and np.array_equal(outs[0][1], outs[1][1])
+        # a scene that is traversed from L2 / HBM
+        ctx.set_spheres(vb.random_scene(50_000, 0x5EED0077, 60.0, 1))
+        ctx.build_bvh()
+        assert ctx.bvh_info().scene_in_smem == 0
+        cam = vb.Camera((0.0, 0.0, 120.0), 40.0, 96 / 54, 0.0, 120.0)
+        cam.SetForward((0.0, 0.0, -1.0))
+        res = []
+        for steal in (0, 1):
+            ctx.set_option("steal", steal)
+            a, i, st = render(ctx, cam, 96, 54, 16, 1, 64)
+            assert ctx.last_accel() == 1
+            res.append((a, i, st.segments, st.paths))
+        assert np.array_equal(res[0][0].view(np.uint32), res[1][0].view(np.uint32)) and np.array_equal(res[0][1], res[1][1]) and res[0][2:] == res[1][2:]
+    finally:
+        ctx.set_option("steal", 1)
+        ctx.set_option("steal_smem", 0)
+
+
 def test_grid_matches_cpu_emulation_and_brute_force(ctx, host_harness, oracle_mod, rtiow):
     """The uniform grid + oversize list (grid.cu: one CTA, count / scan / fill / per-cell sort) is byte for byte the host
     emulation's; closest hits through it (vn_trace_rays with VN_GRID) are brute force's, axis-parallel and -0 directions

@@ -14,9 +14,11 @@ def main():
     ctx = vb.Context(0)
     for kv in sys.argv[1:]:
         k, v = kv.split("=")
+        if k in ("profile", "only"):
+            continue
         ctx.set_option(k, float(v))
     ctx.set_spheres(vb.rtiow_final_scene()); ctx.build_bvh()
-    for (W, H) in ((1920, 1080), (3840, 2160)):
+    for (W, H) in (((1920, 1080),) if "only=1080" in sys.argv else ((1920, 1080), (3840, 2160))):
         cam = vb.rtiow_camera(W, H)
         for rep in range(3):
             ctx.render(ctx.make_params(cam, W, H, 16, 1 + rep, 50, flags=VN_COUNTERS | VN_NO_TONEMAP))
@@ -25,7 +27,7 @@ def main():
             print("%dx%d launch %d: ms_render %.3f | kernel %.3f ms, tickets exhausted at %.3f ms (%.1f %%), drain %.3f ms"
                   % (W, H, rep, st.ms_render, (end - start) / 1e6, (exhaust - start) / 1e6, 100.0 * (exhaust - start) / (end - start),
                      (end - exhaust) / 1e6))
-            lanes, segs = ctx.timeline()
+            lanes, segs, tiles, shaded = ctx.timeline_ex()
             if lanes.sum():
                 total = int(lanes.sum())
                 nz = np.nonzero(lanes)[0]
@@ -41,6 +43,17 @@ def main():
                     sg = int(segs[b:b + step].sum())
                     print("   %.3f ms: %6d lanes retire (%5.1f %% still busy)%s" % (b * 8.192e-3, n, 100.0 * alive[min(b + step - 1, last)] / total,
                                                                                   ("  mean segments of their last pixel %.0f" % (sg / n)) if (n and sg) else ""))
+            if shaded.sum() and "profile=1" in sys.argv:
+                nzs = np.nonzero(shaded)[0]
+                lastb = int(nzs[-1])
+                stepb = max(1, (lastb + 1) // 40)
+                print("   throughput over time (bin start ms: Msegments/s, tiles fetched)")
+                for b in range(0, lastb + 1, stepb):
+                    print("   %.3f ms: %8.0f Mseg/s  %6d tiles" % (b * 8.192e-3, shaded[b:b + stepb].sum() / (min(stepb, lastb + 1 - b) * 8.192), int(tiles[b:b + stepb].sum())))
+                tail0 = max(0, int(np.nonzero(lanes)[0][0]) - 12) if lanes.sum() else 0
+                print("   the end of the launch, bin by bin")
+                for b in range(tail0, lastb + 1):
+                    print("   %.3f ms: %8.0f Mseg/s  %6d tiles  %6d lanes retire" % (b * 8.192e-3, shaded[b] / 8.192, int(tiles[b]), int(lanes[b])))
     ctx.close()
 
 if __name__ == "__main__":

@@ -68,6 +68,7 @@ SIGNATURES = {
     "vn_read_bvh": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
     "vn_read_sched_counters": (C.c_int, [C.c_void_p, _P(C.c_uint64)]),
     "vn_read_timeline": (C.c_int, [C.c_void_p, _P(C.c_uint32)]),
+    "vn_read_timeline_ex": (C.c_int, [C.c_void_p, _P(C.c_uint32)]),
     "vn_read_grid": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]),
     "vn_last_accel": (C.c_int, [C.c_void_p]),
     "vn_read_huge": (C.c_int, [C.c_void_p, _P(C.c_uint32)]),

@@ -258,6 +258,13 @@ class Context:
         a = np.frombuffer(raw, np.uint32).copy()
         return a[:1024], a[1024:]
 
+    def timeline_ex(self):
+        """(lanes retired, segments of their last pixels, tiles fetched, segments shaded) per 8.192 us bin of the last VN_COUNTERS launch."""
+        raw = (C.c_uint32 * 4096)()
+        self._check(self.lib.vn_read_timeline_ex(self.h, raw), "vn_read_timeline_ex")
+        a = np.frombuffer(raw, np.uint32).copy()
+        return a[:1024], a[1024:2048], a[2048:3072], a[3072:]
+
     def stats(self) -> vn_stats:
         s = vn_stats()
         self._check(self.lib.vn_get_stats(self.h, C.byref(s)), "vn_get_stats")

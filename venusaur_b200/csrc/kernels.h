@@ -48,6 +48,9 @@ struct RenderLaunch {
     uint32_t tile_cost_stride;       //   tile_cost[tile] += segments, tile_cost[tile_cost_stride + tile] = max(.., segments)
     uint32_t* timeline;              // instrumented launches of k_render_lean: [0..1024) lanes retired per 8 us bin since the CTA's start, [1024..2048) the ray
                                      // segments of the last pixel those lanes finished (0 outside the cost-collecting launch); null otherwise
+    uint32_t steal;                  // k_render_lean: >= 1 = sample stealing inside a warp during the drain (path_kernels.cu): the fewest samples a lane must have left to give one away
+    float4* steal_scratch;           //   one slot of spp + 1 float4 per lane of the grid: [0] the owner's prefix sum (.w = first sample of the suffix), [1 + k] sample k's radiance
+    uint32_t* steal_count;           //   per slot: parts handed in (bit 31: the owner's prefix); zero between launches
     uint32_t gate;                   // 1: the pair-node / L2-HBM traversals apply the hit-point gate (vn_math.cuh::hit_gate_ok); the shared-memory wide-node kernels ignore it
     uint32_t tiles_x_inv;            // floor(2^32 / tiles_x): tile / tiles_x = __umulhi(tile, tiles_x_inv) plus at most two corrections (tile_row_col)
 };

@@ -656,9 +656,232 @@ __global__ void __launch_bounds__(kMaxThreads) k_render_async(const __grid_const
 // Every lane walks its pixel's samples in order and every ray takes exactly the steps of closest_hit_wide(): the accumulation buffer
 // is bit-identical to k_render_persistent / k_render_async (tests/test_gpu_parity.py).  Needs spp, max_depth, width, height < 65536 and
 // < 4096 spheres (vn_api.cu falls back to k_render_async otherwise).
+// Drain (sample stealing).  Once the tile tickets are exhausted a warp's lanes run dry one by one while the warp keeps paying whole
+// iterations for the few lanes that still hold pixels -- measured (tools/tail_probe.py profile=1): the last 0.3 ms of a 5.4 ms launch, 5 % of
+// its lane-time, the very end being single pixels whose 16 paths bounce through glass for 150 segments.  From then on a lane without work
+// takes over ONE SAMPLE of a pixel another lane of its warp still holds: the camera seed chain (RayTracer.cu:169-183: prd.seed is a copy, the
+// path's draws never feed back into it) is replayed without tracing up to that sample and the path is traced as usual.  Samples are taken
+// from the END of the owner's range (most samples left first), so a split pixel is a prefix the owner sums in its registers, in order,
+// plus a suffix of single samples.  Nobody waits for anybody: the helper writes its sample's radiance into the owner's scratch slot
+// (RenderLaunch::steal_scratch, one slot of spp + 1 float4 per lane of the grid -- a lane owns at most one pixel after the tickets ran out), the
+// owner writes its prefix sum there when it has started all the samples it kept, and whoever arrives last (one atomic counter per slot) adds
+// the suffix to the prefix in sample order -- pixel_color += prd.attenuation (RayTracer.cu:203) sees the samples in the reference's order, so the
+// accumulation buffer keeps its bits.  s_left: [15:0] samples the lane still has to start itself, [25:16] helper: its sample index / owner:
+// samples given away, [30:26] helper: the owner's lane, [31] helper.
 enum LeanState : uint32_t { kLaneNoPixel = 0u, kLaneIdle = 1u, kLaneActive = 2u, kLaneRetired = 3u };
+// the draws of one get_ray (camera_ray: jitter u, v and the lens rejection loop) without the ray
+__device__ __forceinline__ void camera_skip(uint32_t& seed) {
+    (void)rnd(seed); (void)rnd(seed);
+    float dx, dy;
+    random_in_unit_disk(seed, dx, dy);
+}
 
-template <bool kCount, bool kCost, int kMaxThreads, bool kGlobal = false, int kMinBlocks = 1>
+// the warp's statistics at the end of k_render_lean (or of its drain)
+template <bool kCount>
+__device__ __forceinline__ void lean_epilogue(const RenderLaunch& p, const TraceCounters& cnt, uint32_t w_seg, uint32_t w_path) {
+    if (kCount && (threadIdx.x & 31u) == 0u) atomicMax(&p.counters[10], global_ns());
+    if (kCount) {
+        unsigned long long nn = cnt.nodes, ns = cnt.spheres;
+        cg::coalesced_group g = cg::coalesced_threads();
+        nn = cg::reduce(g, nn, cg::plus<unsigned long long>());
+        ns = cg::reduce(g, ns, cg::plus<unsigned long long>());
+        if (g.thread_rank() == 0) { atomicAdd(&p.counters[2], nn); atomicAdd(&p.counters[3], ns); }
+    }
+    if ((threadIdx.x & 31u) == 0u) {
+        atomicAdd(&p.counters[0], (unsigned long long)w_seg);
+        atomicAdd(&p.counters[1], (unsigned long long)w_path);
+    }
+}
+// The drain of k_render_lean: what a warp does once it has found the tile tickets exhausted (see the comment above LeanState).  First the
+// traversals in flight are finished, then the warp works in rounds -- shade, hand pixels in, take samples over, start paths, trace every
+// active lane's segment to its end -- so that no lane carries traversal state (stack pointer, node, slab constants: 12 registers) across the
+// code that redistributes the samples.  With that code inside the first loop, or behind a call, the compiler took the first loop's
+// warp-uniform counters out of the uniform registers and spilled the pixel's sum (measured: -1.7 % on the whole launch); the rounds cost the
+// drain a little lane utilisation instead, where most lanes idle anyway.
+template <bool kCount, bool kGlobal>
+__device__ __forceinline__ void lean_finish_traversal(const RenderLaunch& p, const SceneView& sc, const PathState& st, uint32_t& cur, uint32_t& top, uint32_t& tos,
+                                                      float& tbest, int& prim, SlabScale& ss, const WideBase& wb, TraceCounters& cnt) {
+    if (kGlobal) {
+        while (cur != kEmptyScene) {
+            if ((cur & kLeafFlag) == 0u) {
+                if (kCount) cnt.nodes += 1;
+                cur = pair_node_step_dev(sc.nodes, cur, ss.sdir, ss.nsood, tbest, top, tos);
+            } else {
+                const float a = dot(st.d, st.d);
+                leaf_test<kCount>(sc.geom, cur, st.o, st.d, a, rcp(a), tbest, prim, cnt, p.gate != 0u);
+                cur = stack_pop32_dev(top, tos);
+            }
+        }
+    } else {
+        for (;;) {
+            while ((cur & kLeaf16) == 0u) {
+                if (kCount) cnt.nodes += 1;
+                cur = wide_node_step16_dev(wb, cur, ss, top, tos);
+            }
+            if (cur == kDone16) break;
+            const float a = dot(st.d, st.d), t_before = tbest;
+            leaf_test16<kCount>(sc.geom, cur, st.o, st.d, a, rcp(a), tbest, prim, cnt);
+            cur = stack_pop16_dev(top, tos);
+            if (tbest != t_before) {                              // the slab test works in units of tbest: rescale
+                const float g = t_before * rcp_approx(tbest);
+                ss.sdir = ss.sdir * g; ss.nsood = ss.nsood * g;
+            }
+        }
+    }
+}
+template <bool kCount, bool kCost, bool kGlobal>
+__device__ __forceinline__ void lean_drain(const RenderLaunch& p, const SceneView& sc, uint32_t node_f4s, uint32_t base, uint32_t& pxy, uint32_t& cam_seed, uint32_t& s_left,
+                                           uint32_t& lane_state, f3& sum, PathState& st, uint32_t& cur, uint32_t& top, uint32_t& tos, float& tbest, int& prim, SlabScale& ss,
+                                           WideBase& wb, uint32_t& px_seg, uint32_t& last_seg, unsigned long long t_start) {
+    uint32_t w_seg = 0u, w_path = 0u;                             // (the first loop has added its counts to the launch's statistics)
+    TraceCounters cnt{0u, 0u};
+    constexpr unsigned kFull = 0xFFFFFFFFu;
+    constexpr uint32_t kDone = kGlobal ? kEmptyScene : kDone16;
+    constexpr uint32_t kWordBytes = kGlobal ? 4u : 2u;
+    // (the cost-collecting launch attributes ray segments to the lane's own pixel: no stealing there)
+    const bool steal_on = !kCost && p.steal != 0u && p.steal_scratch != nullptr;
+    volatile uint32_t park[6];
+    lean_finish_traversal<kCount, kGlobal>(p, sc, st, cur, top, tos, tbest, prim, ss, wb, cnt);
+    for (;;) {
+        const bool shading = lane_state == kLaneActive;           // every active lane holds a finished traversal
+        {
+            const uint32_t n_shade = (uint32_t)__popc(__ballot_sync(kFull, shading));
+            w_seg += n_shade;
+            if (kCount && p.timeline && n_shade && (threadIdx.x & 31u) == 0u)
+                atomicAdd(p.timeline + 3072u + (uint32_t)min((unsigned long long)1023u, (global_ns() - t_start) >> 13), n_shade);
+        }
+        if (shading) {
+            if (kCost || kCount) px_seg += 1u;
+            f3 result;
+            if (!shade_segment(sc, st, tbest, prim, result)) {
+                sum = sum + result;                               // pixel_color += prd.attenuation (RayTracer.cu:203)
+                lane_state = kLaneIdle;
+            }
+        }
+        bool retire = false;
+        if (lane_state == kLaneIdle && s_left == 0u) {            // a whole pixel
+            const uint32_t px = pxy & 0xFFFFu, py = pxy >> 16;
+            finish_pixel(p, py * p.width + px, sum);
+            if (kCost) { uint32_t* tc = p.tile_cost + ((py - p.row_begin) >> 2) * p.tiles_x + (px >> 3); atomicAdd(tc, px_seg); atomicMax(tc + p.tile_cost_stride, px_seg); }
+            if (kCount) last_seg = px_seg;
+            retire = true;
+        } else if (lane_state == kLaneIdle && (s_left & 0xFFFFu) == 0u) {
+            // a part of a split pixel: hand it in, the last one to arrive sums
+            const uint32_t lane0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
+            const bool helper = (s_left >> 31) != 0u;
+            const uint32_t g = lane0 + (helper ? ((s_left >> 26) & 31u) : (threadIdx.x & 31u));
+            float4* slot = p.steal_scratch + (size_t)g * (p.spp + 1u);
+            uint32_t first = 0xFFFFFFFFu;                         // != 0xFFFFFFFF: this lane arrived last; first sample of the suffix
+            if (helper) {
+                __stcg(slot + 1u + ((s_left >> 16) & 0x3FFu), make_float4(sum.x, sum.y, sum.z, 0.0f));
+                __threadfence();
+                const uint32_t v = atomicAdd(p.steal_count + g, 1u);
+                if (v & 0x80000000u) {                            // the owner has handed its prefix in: slot[0].w = first sample of the suffix
+                    __threadfence();
+                    const uint32_t j_end = __float_as_uint(__ldcg(slot).w);
+                    if ((v & 0x7FFFFFFFu) + 1u == p.spp - j_end) first = j_end;
+                }
+            } else {
+                const uint32_t n_out = (s_left >> 16) & 0x3FFu;
+                __stcg(slot, make_float4(sum.x, sum.y, sum.z, __uint_as_float(p.spp - n_out)));
+                __threadfence();
+                if (atomicAdd(p.steal_count + g, 0x80000000u) == n_out) first = p.spp - n_out;
+            }
+            if (first != 0xFFFFFFFFu) {
+                __threadfence();
+                const float4 b = __ldcg(slot);
+                f3 total = mk3(b.x, b.y, b.z);
+                for (uint32_t k = first; k < p.spp; k++) { const float4 r = __ldcg(slot + 1u + k); total = total + mk3(r.x, r.y, r.z); }   // RayTracer.cu:203, in order
+                finish_pixel(p, (pxy >> 16) * p.width + (pxy & 0xFFFFu), total);
+                p.steal_count[g] = 0u;                            // (the slot is not used again in this launch)
+            }
+            retire = true;
+        }
+        if (retire) {
+            lane_state = kLaneRetired;
+            if (kCount && p.timeline) {
+                const uint32_t bin = (uint32_t)min((unsigned long long)1023u, (global_ns() - t_start) >> 13);
+                atomicAdd(p.timeline + bin, 1u);
+                atomicAdd(p.timeline + 1024u + bin, last_seg);
+            }
+        }
+        if (steal_on) {
+            unsigned thieves = __ballot_sync(kFull, lane_state == kLaneRetired);
+            if (thieves) {
+                // samples a lane can give away: the ones it has not started, less the one an idle lane starts itself right below
+                uint32_t avail = 0u;
+                if ((lane_state == kLaneIdle || lane_state == kLaneActive) && (s_left >> 31) == 0u) avail = (s_left & 0xFFFFu) - (lane_state == kLaneIdle ? 1u : 0u);
+                while (thieves) {
+                    const uint32_t best = __reduce_max_sync(kFull, (avail << 5) | (threadIdx.x & 31u));
+                    if ((best >> 5) < p.steal) break;             // (p.steal >= 1: the fewest samples a lane must have left to give one away)
+                    const int d = (int)(best & 31u);
+                    const uint32_t n = min((uint32_t)__popc(thieves), best >> 5);
+                    const uint32_t d_s = __shfl_sync(kFull, s_left, d), d_seed = __shfl_sync(kFull, cam_seed, d), d_pxy = __shfl_sync(kFull, pxy, d);
+                    const uint32_t d_out = (d_s >> 16) & 0x3FFu, d_own = d_s & 0xFFFFu;
+                    const uint32_t rank = (uint32_t)__popc(thieves & ((1u << (threadIdx.x & 31u)) - 1u));
+                    if (lane_state == kLaneRetired && rank < n) {
+                        const uint32_t k = p.spp - d_out - 1u - rank;     // from the end of the owner's range
+                        uint32_t sd = d_seed;                              // the owner's seed stands before sample spp - d_out - d_own
+                        for (uint32_t j = p.spp - d_out - d_own; j < k; j++) camera_skip(sd);
+                        cam_seed = sd;
+                        pxy = d_pxy;
+                        sum = mk3(0.0f);
+                        s_left = 0x80000000u | ((uint32_t)d << 26) | (k << 16) | 1u;
+                        lane_state = kLaneIdle;
+                    }
+                    if ((int)(threadIdx.x & 31u) == d) { s_left = s_left - n + (n << 16); avail -= n; }
+                    thieves = __ballot_sync(kFull, lane_state == kLaneRetired);
+                }
+            }
+        }
+        const bool launching = lane_state == kLaneIdle;          // (a lane that just took a sample, or whose path just ended)
+        w_path += (uint32_t)__popc(__ballot_sync(kFull, launching));
+        if (launching) {
+            camera_ray(p.cam, pxy & 0xFFFFu, pxy >> 16, cam_seed, st.o, st.d);   // RayTracer.cu:173-177
+            st.thr = mk3(1.0f);
+            st.seed = cam_seed;                                   // prd.seed = seed: a copy (RayTracer.cu:183)
+            st.depth = (int)p.max_depth - 1;                      // RayTracer.cu:184
+            s_left -= 1u;
+            lane_state = kLaneActive;
+        }
+        if (__ballot_sync(kFull, lane_state == kLaneActive) == 0u) break;
+        // the pixel's state waits in local memory while the segment is traced (explicitly: left to the register allocator, the drain's
+        // copy of the traversal made it spill the pixel's sum and the warp's counters in the FIRST loop as well)
+        park[0] = pxy; park[1] = cam_seed; park[2] = s_left; park[3] = __float_as_uint(sum.x); park[4] = __float_as_uint(sum.y); park[5] = __float_as_uint(sum.z);
+        if (lane_state == kLaneActive) {
+            // the segment, traced to its end: the huge spheres first (lbvh_core.cuh::HugeList), then the traversal
+            tbest = kTMax;
+            prim = -1;
+            const f3 idir = slab_idir(st.d);
+            if (kGlobal) {
+                ss.sdir = idir;
+                ss.nsood = mk3(st.o.x * idir.x, st.o.y * idir.y, st.o.z * idir.z);
+                cur = p.root_link;
+            } else {
+                if (p.huge.n) {
+                    const float a = dot(st.d, st.d), inv_a = rcp(a);
+                    for (uint32_t i = 0; i < p.huge.n; i++) {
+                        const uint32_t hs = p.huge.idx[i];
+                        const float4 g = sc.geom[hs];
+                        if (kCount) cnt.spheres += 1;
+                        const float th = sphere_root(st.o, st.d, a, inv_a, g.x, g.y, g.z, g.w, kTMin, tbest);
+                        if (th >= 0.0f) { tbest = th; prim = (int)hs; }
+                    }
+                }
+                wb = wide_base(sc.nodes, ray_octant(st.d), node_f4s);
+                ss = slab_scale(idir, mk3(st.o.x * idir.x, st.o.y * idir.y, st.o.z * idir.z), tbest);
+                cur = p.wide_root;
+            }
+            top = base + kWordBytes;
+            tos = kDone;
+            lean_finish_traversal<kCount, kGlobal>(p, sc, st, cur, top, tos, tbest, prim, ss, wb, cnt);
+        }
+        pxy = park[0]; cam_seed = park[1]; s_left = park[2]; sum = mk3(__uint_as_float(park[3]), __uint_as_float(park[4]), __uint_as_float(park[5]));
+    }
+    lean_epilogue<kCount>(p, cnt, w_seg, w_path);
+}
+
+template <bool kCount, bool kCost, int kMaxThreads, bool kGlobal = false, int kMinBlocks = 1, bool kDrain = false>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const __grid_constant__ RenderLaunch p) {
     extern __shared__ float4 s_scene[];
     SceneView sc;
@@ -716,14 +939,20 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
     SlabScale ss;                      // shared-memory wide nodes: idir / tbest, -(o * idir) / tbest; kGlobal: idir, o * idir
     ss.sdir = ss.nsood = mk3(0.0f);
     WideBase wb = wide_base(sc.nodes, 0u, node_f4s);
-    uint32_t w_tile = 0u, w_cursor = 32u;          // the warp's current tile and the next pixel of it to hand out (warp-uniform)
+    uint32_t w_ox = 0u, w_oy = 0u, w_cursor = 32u; // the warp's current tile (its first pixel) and the next pixel of it to hand out (warp-uniform)
+    uint32_t t_seed = 0u;                          // camera seed of pixel (lane) of that tile
 
     for (;;) {
         const bool fin = cur == kDone && lane_state != kLaneRetired;       // holds a finished traversal, or no ray at all
         const bool shading = fin && lane_state == kLaneActive;
-        w_seg += (uint32_t)__popc(__ballot_sync(kFull, shading));
+        {
+            const uint32_t n_shade = (uint32_t)__popc(__ballot_sync(kFull, shading));
+            w_seg += n_shade;
+            if (kCount && p.timeline && n_shade && (threadIdx.x & 31u) == 0u)       // instrumented launches: throughput over time
+                atomicAdd(p.timeline + 3072u + (uint32_t)min((unsigned long long)1023u, (global_ns() - t_start) >> 13), n_shade);
+        }
         if (shading) {
-            if (kCost) px_seg += 1u;
+            if (kCost || kCount) px_seg += 1u;
             f3 result;
             if (!shade_segment(sc, st, tbest, prim, result)) {
                 sum = sum + result;                               // pixel_color += prd.attenuation (RayTracer.cu:203)
@@ -734,7 +963,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
             const uint32_t px = pxy & 0xFFFFu, py = pxy >> 16;
             finish_pixel(p, py * p.width + px, sum);
             if (kCost) { uint32_t* tc = p.tile_cost + ((py - p.row_begin) >> 2) * p.tiles_x + (px >> 3); atomicAdd(tc, px_seg); atomicMax(tc + p.tile_cost_stride, px_seg); }
-            if (kCount && kCost) last_seg = px_seg;
+            if (kCount) last_seg = px_seg;
             lane_state = kLaneNoPixel;
         }
         // warp-owned tiles (see k_render_async): one global ticket per 8x4 tile, pixels handed to the asking lanes in order
@@ -746,7 +975,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
                     uint32_t t = 0u;
                     if ((threadIdx.x & 31u) == 0u) t = atomicAdd(p.work_counter, 1u);
                     t = __shfl_sync(kFull, t, 0);
-                    if (t >= (p.total_work >> 5)) {               // no tiles left: the asking lanes only vote from now on
+                    if (t >= (p.total_work >> 5)) {               // no tiles left: the asking lanes only vote from now on (or help, see above)
+                        if (kDrain) w_cursor = 33u;               // (> 32: this warp has seen the tickets exhausted and leaves the loop below)
                         if (need) {
                             lane_state = kLaneRetired;
                             if (kCount) {
@@ -761,21 +991,29 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
                         }
                         break;
                     }
-                    w_tile = p.tile_order ? __ldg(p.tile_order + t) : t;
+                    const uint32_t tile = p.tile_order ? __ldg(p.tile_order + t) : t;
                     w_cursor = 0u;
+                    // every lane forms the camera seed of "its" pixel of the new tile (pixel i of the tile by lane i) while the warp is
+                    // converged; the lanes that take a pixel pick its seed up with one shuffle.  Formed by the taker, the 70 instructions
+                    // of tea<4> ran at 1.6 active lanes 1.3 M times per launch (ncu: 2.9 % of all warp instructions), now once per tile.
+                    uint32_t ty, tx;
+                    tile_row_col(tile, p.tiles_x, p.tiles_x_inv, ty, tx);
+                    w_ox = tx * 8u; w_oy = p.row_begin + ty * 4u;
+                    t_seed = tea4((w_oy + ((threadIdx.x & 31u) >> 3)) * p.width + w_ox + (threadIdx.x & 7u), p.subframe_index);   // RayTracer.cu:169
+                    if (kCount && p.timeline && (threadIdx.x & 31u) == 0u)
+                        atomicAdd(p.timeline + 2048u + (uint32_t)min((unsigned long long)1023u, (global_ns() - t_start) >> 13), 1u);
                 }
                 const uint32_t in = w_cursor + (uint32_t)__popc(m & ((1u << (threadIdx.x & 31u)) - 1u));
+                const uint32_t in_seed = __shfl_sync(kFull, t_seed, (int)(in & 31u));
                 if (need && in < 32u) {
-                    uint32_t ty, tx;
-                    tile_row_col(w_tile, p.tiles_x, p.tiles_x_inv, ty, tx);
-                    const uint32_t px = tx * 8u + (in & 7u), py = p.row_begin + ty * 4u + (in >> 3);
+                    const uint32_t px = w_ox + (in & 7u), py = w_oy + (in >> 3);
                     if (px < p.width && py < p.row_end) {
                         need = false;
                         pxy = (py << 16) | px;
-                        cam_seed = tea4(py * p.width + px, p.subframe_index);   // RayTracer.cu:169
+                        cam_seed = in_seed;
                         sum = mk3(0.0f);
                         s_left = p.spp;
-                        if (kCost) px_seg = 0u;
+                        if (kCost || kCount) px_seg = 0u;
                         lane_state = kLaneIdle;
                     }
                 }
@@ -784,8 +1022,9 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
             }
         }
         const bool launching = fin && lane_state == kLaneIdle;             // (a lane that just got a pixel, or whose path just ended)
+        const bool starting = fin && lane_state != kLaneRetired;
         w_path += (uint32_t)__popc(__ballot_sync(kFull, launching));
-        if (fin && lane_state != kLaneRetired) {
+        if (starting) {
             if (launching) {
                 camera_ray(p.cam, pxy & 0xFFFFu, pxy >> 16, cam_seed, st.o, st.d);   // RayTracer.cu:173-177
                 st.thr = mk3(1.0f);
@@ -848,6 +1087,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
                 }
                 if ((uint32_t)__popc(__ballot_sync(kFull, cur == kDone && lane_state != kLaneRetired)) >= t_done) break;
             }
+            if (kDrain && w_cursor > 32u) break;                           // (see the end of the loop)
             continue;
         }
         // one traversal burst: while-while phases, one vote per phase; it ends as soon as t_done lanes hold a finished ray
@@ -867,19 +1107,10 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
             }
             if ((uint32_t)__popc(__ballot_sync(kFull, cur == kDone16 && lane_state != kLaneRetired)) >= t_done) break;
         }
+        if (kDrain && w_cursor > 32u) break;                               // the tickets are exhausted: the rest of the launch is lean_drain()
     }
-    if (kCount && (threadIdx.x & 31u) == 0u) atomicMax(&p.counters[10], global_ns());
-    if (kCount) {
-        unsigned long long nn = cnt.nodes, ns = cnt.spheres;
-        cg::coalesced_group g = cg::coalesced_threads();
-        nn = cg::reduce(g, nn, cg::plus<unsigned long long>());
-        ns = cg::reduce(g, ns, cg::plus<unsigned long long>());
-        if (g.thread_rank() == 0) { atomicAdd(&p.counters[2], nn); atomicAdd(&p.counters[3], ns); }
-    }
-    if ((threadIdx.x & 31u) == 0u) {
-        atomicAdd(&p.counters[0], (unsigned long long)w_seg);
-        atomicAdd(&p.counters[1], (unsigned long long)w_path);
-    }
+    lean_epilogue<kCount>(p, cnt, w_seg, w_path);
+    if (kDrain && w_cursor > 32u) lean_drain<kCount, kCost, kGlobal>(p, sc, node_f4s, base, pxy, cam_seed, s_left, lane_state, sum, st, cur, top, tos, tbest, prim, ss, wb, px_seg, last_seg, t_start);
 }
 
 // Sort keys of the cost-ordered tile schedule: most urgent tile first = smallest key.  A tile's urgency is its total cost (ray segments
@@ -1041,13 +1272,22 @@ inline uint32_t grid_for(uint64_t n, int threads) { return (uint32_t)((n + threa
 namespace {
 typedef void (*PathKernel)(const RenderLaunch);
 PathKernel pick_kernel(bool scene_in_smem, bool count, bool octant, bool wide = false, int threads = 1024, bool grid = false, bool async = false, bool phase = false, bool warp_tiles = false,
-                       bool lean = false, bool cost = false, int global_ctas = 4) {
+                       bool lean = false, bool cost = false, int global_ctas = 4, bool drain = false) {
     if (lean && !scene_in_smem && !wide && !grid) {        // pair nodes from L2 / HBM, asynchronous (k_render_lean<kGlobal>); 4, 5 or 6 CTAs of 256 threads per SM (64 / 48 / 40 registers)
+        if (drain && !cost) {                              // with the sample-stealing drain (lean_drain)
+            if (global_ctas >= 6) return count ? k_render_lean<true, false, 256, true, 6, true> : k_render_lean<false, false, 256, true, 6, true>;
+            if (global_ctas == 5) return count ? k_render_lean<true, false, 256, true, 5, true> : k_render_lean<false, false, 256, true, 5, true>;
+            return count ? k_render_lean<true, false, 256, true, 4, true> : k_render_lean<false, false, 256, true, 4, true>;
+        }
         if (global_ctas >= 6) return count ? (cost ? k_render_lean<true, true, 256, true, 6> : k_render_lean<true, false, 256, true, 6>) : (cost ? k_render_lean<false, true, 256, true, 6> : k_render_lean<false, false, 256, true, 6>);
         if (global_ctas == 5) return count ? (cost ? k_render_lean<true, true, 256, true, 5> : k_render_lean<true, false, 256, true, 5>) : (cost ? k_render_lean<false, true, 256, true, 5> : k_render_lean<false, false, 256, true, 5>);
         return count ? (cost ? k_render_lean<true, true, 256, true, 4> : k_render_lean<true, false, 256, true, 4>) : (cost ? k_render_lean<false, true, 256, true, 4> : k_render_lean<false, false, 256, true, 4>);
     }
     if (lean && async && phase && warp_tiles && wide && scene_in_smem && !grid) {
+        if (drain && !cost) {
+            if (threads <= 768) return count ? k_render_lean<true, false, 768, false, 1, true> : k_render_lean<false, false, 768, false, 1, true>;
+            return count ? k_render_lean<true, false, 1024, false, 1, true> : k_render_lean<false, false, 1024, false, 1, true>;
+        }
         if (threads <= 768) return count ? (cost ? k_render_lean<true, true, 768> : k_render_lean<true, false, 768>) : (cost ? k_render_lean<false, true, 768> : k_render_lean<false, false, 768>);
         return count ? (cost ? k_render_lean<true, true, 1024> : k_render_lean<true, false, 1024>) : (cost ? k_render_lean<false, true, 1024> : k_render_lean<false, false, 1024>);
     }
@@ -1087,7 +1327,7 @@ int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool c
 
 cudaError_t launch_render_persistent(const RenderLaunch& p, const KernelConfig& cfg, cudaStream_t stream) {
     PathKernel k = pick_kernel(cfg.scene_in_smem, cfg.count, cfg.octant, cfg.wide, cfg.threads, cfg.grid, cfg.async, cfg.async && p.async_node == 0u, cfg.warp_tiles,
-                               cfg.lean, p.tile_cost != nullptr, cfg.global_ctas);
+                               cfg.lean, p.tile_cost != nullptr, cfg.global_ctas, p.steal != 0u && p.steal_scratch != nullptr);
     if (cfg.smem_bytes > 48 * 1024) {
         const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes);
         if (e != cudaSuccess) return e;
