@@ -567,6 +567,34 @@ def test_sample_stealing_keeps_the_accumulation_buffer(ctx, oracle_mod, rtiow):
         ctx.set_option("steal_smem", 0)
 
 
+def test_split_frames_keep_the_accumulation_buffer(ctx, oracle_mod, rtiow):
+    """"split_tail": the cheap end of the cost-ordered tile list is rendered by a second launch on another stream that overlaps the first
+    launch's drain.  Disjoint tiles, same kernel: accumulation buffer, image and counters are those of the single launch,
+    for every fraction, over progressive launches of one view (the first collects the tile costs and is never split)."""
+    ctx.set_spheres(rtiow)
+    ctx.build_bvh()
+    W, H, spp, depth = 640, 360, 4, 50                          # 7200 tiles > 32 per SM: the tile order is active
+    cam = vb.rtiow_camera(W, H)
+    try:
+        ref = None
+        for frac in (0.0, 0.3, 0.05, 0.9):
+            ctx.set_option("split_tail", frac)
+            ctx.set_option("tile_order", 1)                       # (resets the view: the next launch collects costs again)
+            outs = []
+            render(ctx, cam, W, H, spp, 1, depth)
+            for sub in (2, 3):
+                a, i, st = render(ctx, cam, W, H, spp, sub, depth, accum_count=sub - 1)
+                outs.append((a.copy(), i.copy(), st.segments, st.paths))
+            if ref is None:
+                ref = outs
+            else:
+                for (a, i, sg, pt), (ra, ri, rsg, rpt) in zip(outs, ref):
+                    assert np.array_equal(a.view(np.uint32), ra.view(np.uint32)) and np.array_equal(i, ri) and (sg, pt) == (rsg, rpt), frac
+    finally:
+        ctx.set_option("split_tail", 0.0)
+        ctx.set_option("tile_order", 1)
+
+
 def test_grid_matches_cpu_emulation_and_brute_force(ctx, host_harness, oracle_mod, rtiow):
     """The uniform grid + oversize list (grid.cu: one CTA, count / scan / fill / per-cell sort) is byte for byte the host
     emulation's; closest hits through it (vn_trace_rays with VN_GRID) are brute force's, axis-parallel and -0 directions

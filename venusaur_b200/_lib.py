@@ -145,7 +145,10 @@ def load() -> C.CDLL:
     # build() itself is serialised by a file lock, so one process per GPU may all land here at once
     if not os.path.exists(_build.LIB) or (os.path.isdir(_build.CSRC) and not _build.up_to_date() and _build.shutil.which("nvcc")):
         _build.build()
-    lib = C.CDLL(_build.LIB)
+    path = _build.LIB
+    if os.environ.get("VN_EXPERIMENT"):        # a compile-time variant built by `python -m venusaur_b200.build --exp N` (A/B measurements)
+        path = os.path.join(_build.HERE, "libvenusaur_b200_exp%d.so" % int(os.environ["VN_EXPERIMENT"]))
+    lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)     # AttributeError if the symbol is not exported: fail loudly
         fn.restype = res

@@ -120,6 +120,27 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_experiment(n: int) -> str:
+    """A second library next to the shipped one, compiled with -DVN_EXP=n (code under `#if VN_EXP == n` in csrc/): A/B measurements of
+    compile-time variants within one visit to the GPU (VN_EXPERIMENT=n selects it in _lib.load()).  Test infrastructure only."""
+    cc = nvcc()
+    out = os.path.join(HERE, "libvenusaur_b200_exp%d.so" % n)
+    odir = os.path.join(OBJ, "exp%d" % n)
+    os.makedirs(odir, exist_ok=True)
+    jobs, objs = [], []
+    for src, obj, extra in UNITS:
+        o = os.path.join(odir, obj)
+        jobs.append([cc, *ARCH, *COMMON, *extra, "-DVN_EXP=%d" % n, "-c", os.path.join(CSRC, src), "-o", o])
+        objs.append(o)
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+        list(ex.map(_run, jobs))
+    _run([cc, *ARCH, "-shared", "-o", out, *objs])
+    return out
+
+
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    print(path)
+    if "--exp" in sys.argv:
+        print(build_experiment(int(sys.argv[sys.argv.index("--exp") + 1])))
+    else:
+        path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+        print(path)

@@ -913,7 +913,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
     if (kCount && threadIdx.x == 0) atomicMax(&p.counters[8], ~global_ns());     // launch timeline, see k_render_async
 
     uint32_t pxy = 0u;                 // py << 16 | px of the lane's pixel
-    uint32_t cam_seed = 0u, s_left = 0u;
+    uint32_t cam_seed = 0u;
+    uint32_t sd = 0u;                  // samples of the pixel the lane still has to start << 16 | depth budget left of its path (prd.depth): one register
     uint32_t lane_state = kLaneNoPixel;
     f3 sum = mk3(0.0f);
     PathState st;
@@ -954,12 +955,15 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
         if (shading) {
             if (kCost || kCount) px_seg += 1u;
             f3 result;
+            st.depth = (int)(sd & 0xFFFFu);
             if (!shade_segment(sc, st, tbest, prim, result)) {
                 sum = sum + result;                               // pixel_color += prd.attenuation (RayTracer.cu:203)
                 lane_state = kLaneIdle;
+            } else {
+                sd -= 1u;                                         // (shade_segment's prd.depth - 1 of a path that goes on, RayTracer.cu:314,361,417)
             }
         }
-        if (fin && lane_state == kLaneIdle && s_left == 0u) {
+        if (fin && lane_state == kLaneIdle && sd < 0x10000u) {
             const uint32_t px = pxy & 0xFFFFu, py = pxy >> 16;
             finish_pixel(p, py * p.width + px, sum);
             if (kCost) { uint32_t* tc = p.tile_cost + ((py - p.row_begin) >> 2) * p.tiles_x + (px >> 3); atomicAdd(tc, px_seg); atomicMax(tc + p.tile_cost_stride, px_seg); }
@@ -1012,7 +1016,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
                         pxy = (py << 16) | px;
                         cam_seed = in_seed;
                         sum = mk3(0.0f);
-                        s_left = p.spp;
+                        sd = p.spp << 16;
                         if (kCost || kCount) px_seg = 0u;
                         lane_state = kLaneIdle;
                     }
@@ -1029,8 +1033,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
                 camera_ray(p.cam, pxy & 0xFFFFu, pxy >> 16, cam_seed, st.o, st.d);   // RayTracer.cu:173-177
                 st.thr = mk3(1.0f);
                 st.seed = cam_seed;                               // prd.seed = seed: a copy (RayTracer.cu:183)
-                st.depth = (int)p.max_depth - 1;                  // RayTracer.cu:184
-                s_left -= 1u;
+                sd = ((sd - 0x10000u) & 0xFFFF0000u) | (p.max_depth - 1u);   // one sample less to start; prd.depth = max_depth - 1 (RayTracer.cu:184)
                 lane_state = kLaneActive;
             }
             // start the next segment: the huge spheres first (lbvh_core.cuh::HugeList), then the traversal constants
@@ -1110,6 +1113,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
         if (kDrain && w_cursor > 32u) break;                               // the tickets are exhausted: the rest of the launch is lean_drain()
     }
     lean_epilogue<kCount>(p, cnt, w_seg, w_path);
+    uint32_t s_left = sd >> 16;
+    st.depth = (int)(sd & 0xFFFFu);
     if (kDrain && w_cursor > 32u) lean_drain<kCount, kCost, kGlobal>(p, sc, node_f4s, base, pxy, cam_seed, s_left, lane_state, sum, st, cur, top, tos, tbest, prim, ss, wb, px_seg, last_seg, t_start);
 }
 
