@@ -480,9 +480,8 @@ def run_ours(args):
             schedule = ("k_render_persistent: every round waits for its slowest ray" if _ad == 0 else
                         "%s, %s: a traversal burst ends when %d lanes hold a finished ray%s" % ("k_render_lean" if (_lean and _an == 0 and int(float(_o.get("warp_tiles", 1)))) else "k_render_async",
                         "phase form" if _an == 0 else "voted turns", _ad, "; warps own whole 8x4 tiles" if (_an == 0 and int(float(_o.get("warp_tiles", 1)))) else ""))
-            _st = float(_o.get("split_tail", 0.15))
-            if _lean and _ad and _st > 0:
-                schedule += "; a frame = two launches of the kernel: the cheapest %.0f %% of the cost-ordered tiles go to a second launch on another stream that overlaps the first one's drain" % (100 * _st)
+            if _lean and _ad and float(_o.get("split_tail", 0.5)) > 0:
+                schedule += "; a frame = two launches of the kernel: the tiles that saw nothing but sky when the view's costs were collected go to a second launch on another stream that overlaps the first one's drain"
         elif args.kernel == "persistent" and accel == 1 and not info.scene_in_smem:
             schedule = ("k_render_lean<global>: asynchronous shading, voted node / leaf turns, a burst ends when %d lanes hold a finished ray" % int(float(_o.get("global_done", 16)))
                         if (_lean and _ad) else "k_render_persistent: every round waits for its slowest ray")

@@ -116,7 +116,7 @@ constexpr int kWfArraysTotal = 2 * kWfStateArrays + 2 + 4;   // 4-byte arrays of
     int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool count, bool octant, bool wide, bool grid, bool lean, int global_ctas); \
     cudaError_t launch_render_persistent(const RenderLaunch& p, const KernelConfig& cfg, cudaStream_t stream);         \
     cudaError_t launch_tonemap(const float4* accum, float scale, uint32_t* image, uint64_t n, cudaStream_t stream);    \
-    cudaError_t launch_tile_keys(const uint32_t* cost, uint32_t stride, uint32_t n, uint32_t mode, uint32_t spp, uint32_t* keys, uint32_t* vals, cudaStream_t stream); \
+    cudaError_t launch_tile_keys(const uint32_t* cost, uint32_t stride, uint32_t n, uint32_t mode, uint32_t spp, uint32_t* keys, uint32_t* vals, uint32_t* n_all_miss, cudaStream_t stream); \
     cudaError_t launch_reduce_tonemap_peers(const float4* const* peers, uint32_t n_peers, float scale, uint64_t begin, \
                                             uint64_t end, float4* accum_out, uint32_t* image, const uint32_t* const* peer_flags, \
                                             uint32_t wait_value, uint32_t* error, cudaStream_t stream);               \

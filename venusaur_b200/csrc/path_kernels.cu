@@ -1125,13 +1125,19 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
 // go last, whatever their order among themselves.  Their cost is deterministic -- spp segments per pixel, every launch -- whereas a tile that
 // was cheap in the collecting launch but touches a glass silhouette can hold a 100-segment pixel in the next one; handed out among the last,
 // such pixels were the thin tail that kept a launch alive for its last 0.19 ms (tools/tail_probe.py: 0.6 % of the lanes, 3.6 % of the time).
+// In every mode the tiles in which no path hit anything end up last, and *n_all_miss counts them: a split frame (vn_api.cu, "split_tail") hands
+// exactly those to its second launch.
 __global__ void __launch_bounds__(256) k_tile_keys(const uint32_t* __restrict__ cost, uint32_t stride, uint32_t n, uint32_t mode, uint32_t spp, uint32_t* __restrict__ keys,
-                                                   uint32_t* __restrict__ vals) {
+                                                   uint32_t* __restrict__ vals, uint32_t* __restrict__ n_all_miss) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool all_miss = i < n && cost[stride + i] <= spp;
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, all_miss);
+    if ((threadIdx.x & 31u) == 0u && m) atomicAdd(n_all_miss, (uint32_t)__popc(m));
     if (i >= n) return;
     const uint32_t sum = cost[i], mx = cost[stride + i];
     uint32_t c = mode == 2u ? mx : (mode == 3u ? max(sum >> 3, mx) : sum);
-    if (mode == 4u) c = mx > spp ? sum + 1u : 0u;
+    if (mode == 4u) c = sum + 1u;
+    if (all_miss) c = 0u;
     c = c < 0x00FFFFFFu ? c : 0x00FFFFFFu;
     keys[i] = 0x00FFFFFFu - c;
     vals[i] = i;
@@ -1341,9 +1347,9 @@ cudaError_t launch_render_persistent(const RenderLaunch& p, const KernelConfig& 
     return cudaGetLastError();
 }
 
-cudaError_t launch_tile_keys(const uint32_t* cost, uint32_t stride, uint32_t n, uint32_t mode, uint32_t spp, uint32_t* keys, uint32_t* vals, cudaStream_t stream) {
+cudaError_t launch_tile_keys(const uint32_t* cost, uint32_t stride, uint32_t n, uint32_t mode, uint32_t spp, uint32_t* keys, uint32_t* vals, uint32_t* n_all_miss, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
-    k_tile_keys<<<(n + 255u) / 256u, 256, 0, stream>>>(cost, stride, n, mode, spp, keys, vals);
+    k_tile_keys<<<(n + 255u) / 256u, 256, 0, stream>>>(cost, stride, n, mode, spp, keys, vals, n_all_miss);
     return cudaGetLastError();
 }
 

@@ -5,6 +5,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -92,18 +93,20 @@ struct vn_context {
     uint32_t* d_tile_sort = nullptr;  // [4 * tile_cap]: keys, values and their alternates for the radix sort
     const uint32_t* d_tile_order = nullptr;
     uint32_t tile_cap = 0;
+    uint32_t tile_all_miss = 0;       // tiles of the current view in which no path hit anything while the costs were collected: the tail of d_tile_order
     int tile_state = 0;               // 0: nothing known (the next launch collects costs), 1: costs collected (sort before the next launch), 2: order valid
     struct TileSig { uint32_t w, h, r0, r1, spp, depth; float cam[13]; uint32_t pad_; uint64_t epoch; } tile_sig{};   // no implicit padding
     uint64_t bvh_epoch = 0;
     uint32_t hit_gate = 1;            // "hit_gate": 1 = scenes traversed from L2 / HBM apply the hit-point gate (vn_math.cuh::hit_gate_ok), 0 = never,
                                       // 2 = the pair-node kernels apply it to small scenes too (the shared-memory wide-node kernels never do)
     uint32_t lean = 1;                // "lean": k_render_lean (16-bit links, no per-lane statistics, no spills) when the launch qualifies; 0 = k_render_async
-    float split_tail = 0.15f;         // "split_tail": fraction of the cost-ordered tiles (its cheap end) that a launch of the shared-memory path kernel hands to a SECOND
+    float split_tail = 0.5f;          // "split_tail": fraction of the cost-ordered tiles (its cheap end) that a launch of the shared-memory path kernel hands to a SECOND
                                       // launch on another stream.  The first launch's drain -- a few lanes per SM finishing their last, heavy pixels while the rest of
                                       // the GPU idles -- then overlaps the second launch, whose CTAs start on every SM the first one leaves; the second launch's own
-                                      // tiles (sky, cheap and uniform) drain in a few tens of microseconds.  Measured on RTIOW 1080p: 0 / 0.15 / 0.25 / 0.35 of the tiles ->
-                                      // 18.82 / 18.95 / 18.20 / 17.81 Grays/s (a CTA of the second launch needs the whole SM's shared memory: it only starts once
-                                      // the first launch's CTA there has retired ALL its warps, so a large second launch just waits); 0 = one launch
+                                      // tiles drain in a few tens of microseconds.  Only tiles that saw nothing but sky while the view's costs were collected qualify
+                                      // (uniform and cheap); the value caps their share.  Measured on RTIOW 1080p with a fixed fraction of the cost-ordered tiles:
+                                      // 0 / 0.10 / 0.15 / 0.18 / 0.25 -> 5.13 / 5.09 / 5.09 / 5.31 / 5.33 ms per launch: beyond the sky (~17 % of the tiles) the second
+                                      // launch has a heavy tail of its own; 0 = one launch
     uint32_t steal = 1;               // "steal": once the tile tickets are exhausted, idle lanes of a warp take single samples of the pixels its other lanes still hold
                                       // (k_render_lean's drain, path_kernels.cu::lean_drain); the value = the fewest samples a lane must have left to give one away, 0 = off
     uint32_t steal_smem = 0;          // "steal_smem": also for scenes traversed from shared memory.  Off: measured on RTIOW 1080p the drain shrinks from 0.39 to 0.28 ms
@@ -725,12 +728,17 @@ static int prepare_tile_order(vn_handle c, const vn_params* p, RenderLaunch& L) 
     }
     if (c->tile_state == 1) {
         uint32_t *k0 = c->d_tile_sort, *v0 = k0 + c->tile_cap, *k1 = v0 + c->tile_cap, *v1 = k1 + c->tile_cap;
-        VN_CUDA(c, exact::launch_tile_keys(c->d_tile_cost, c->tile_cap, n_tiles, c->tile_order_opt, p->samples_per_pixel, k0, v0, c->stream));
+        uint32_t* d_all_miss = reinterpret_cast<uint32_t*>(c->d_counters + 6);     // (a free word of the counter block; the launch's memset comes later)
+        VN_CUDA(c, cudaMemsetAsync(d_all_miss, 0, 4, c->stream));
+        VN_CUDA(c, exact::launch_tile_keys(c->d_tile_cost, c->tile_cap, n_tiles, c->tile_order_opt, p->samples_per_pixel, k0, v0, d_all_miss, c->stream));
         std::string err;
         uint32_t launches = 0;
         const int which = radix_sort_pairs_device(k0, v0, k1, v1, n_tiles, 24, c->num_sms, c->stream, &launches, err);
         if (which < 0) return fail(c, VN_ERR_CUDA, "vn_render: tile order sort failed: " + err);
         c->d_tile_order = which ? v1 : v0;
+        // once per view: how many tiles saw nothing but sky in the collecting launch (they are the end of the order)
+        VN_CUDA(c, cudaMemcpyAsync(&c->tile_all_miss, d_all_miss, 4, cudaMemcpyDeviceToHost, c->stream));
+        VN_CUDA(c, cudaStreamSynchronize(c->stream));
         c->tile_state = 2;
     }
     L.tile_order = c->d_tile_order;
@@ -838,19 +846,34 @@ int vn_render(vn_handle c, const vn_params* p) {
         // split frame: the cheap end of the cost-ordered tile list goes to a second launch on tail_stream (same kernel, own ticket counter, the
         // statistics add up in the same counters); everything behind it on c->stream waits for both
         const uint32_t n_tiles = L.total_work / 32u;
-        const uint32_t n_tail = (L.tile_order && !count && cfg.lean && cfg.scene_in_smem && c->split_tail > 0.0f) ? (uint32_t)((double)n_tiles * c->split_tail) : 0u;
+        // ... and only tiles that saw nothing but sky when the costs were collected: uniform, cheap, no pixel that bounces for a millisecond --
+        // a second launch that holds heavy-tailed tiles ends later than the first (measured: +0.2 ms as soon as it reached beyond the sky)
+        const uint32_t n_tail = (L.tile_order && !count && cfg.lean && cfg.scene_in_smem && c->split_tail > 0.0f)
+                                    ? std::min(c->tile_all_miss, (uint32_t)((double)n_tiles * c->split_tail)) : 0u;
         if (n_tail > 0u && n_tail < n_tiles) {
             RenderLaunch T = L;
             T.tile_order = L.tile_order + (n_tiles - n_tail);
             T.total_work = n_tail * 32u;
             T.work_counter = reinterpret_cast<uint32_t*>(c->d_counters + 5);
             L.total_work = (n_tiles - n_tail) * 32u;
+            static const bool debug_split = getenv("VN_DEBUG_SPLIT") != nullptr;      // prints the two launches' end times (host sync: measurements only)
+            cudaEvent_t dbg[3] = {nullptr, nullptr, nullptr};
+            if (debug_split) { for (auto& e : dbg) cudaEventCreate(&e); cudaEventRecord(dbg[0], c->stream); }
             VN_CUDA(c, cudaEventRecord(c->ev_tail[0], c->stream));
             VN_CUDA(c, exact_build ? exact::launch_render_persistent(L, cfg, c->stream) : fast::launch_render_persistent(L, cfg, c->stream));
+            if (debug_split) cudaEventRecord(dbg[1], c->stream);
             VN_CUDA(c, cudaStreamWaitEvent(c->tail_stream, c->ev_tail[0], 0));
             VN_CUDA(c, exact_build ? exact::launch_render_persistent(T, cfg, c->tail_stream) : fast::launch_render_persistent(T, cfg, c->tail_stream));
+            if (debug_split) cudaEventRecord(dbg[2], c->tail_stream);
             VN_CUDA(c, cudaEventRecord(c->ev_tail[1], c->tail_stream));
             VN_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_tail[1], 0));
+            if (debug_split) {
+                cudaEventSynchronize(dbg[1]); cudaEventSynchronize(dbg[2]);
+                float a = 0.0f, b = 0.0f;
+                cudaEventElapsedTime(&a, dbg[0], dbg[1]); cudaEventElapsedTime(&b, dbg[0], dbg[2]);
+                fprintf(stderr, "split frame: first launch (%u tiles) ends at %.3f ms, second (%u tiles) at %.3f ms\n", n_tiles - n_tail, a, n_tail, b);
+                for (auto& e : dbg) cudaEventDestroy(e);
+            }
             L.total_work = n_tiles * 32u;
             launches += 1;
         } else {
