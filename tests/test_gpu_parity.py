@@ -590,8 +590,26 @@ def test_split_frames_keep_the_accumulation_buffer(ctx, oracle_mod, rtiow):
             else:
                 for (a, i, sg, pt), (ra, ri, rsg, rpt) in zip(outs, ref):
                     assert np.array_equal(a.view(np.uint32), ra.view(np.uint32)) and np.array_equal(i, ri) and (sg, pt) == (rsg, rpt), frac
+        # a camera move: the collecting launch of the new view hands its tiles out in the previous view's order ("tile_guess"); same buffers
+        cam2 = vb.Camera((12.0, 2.5, 4.0), 20.0, W / H, 0.1, 10.0)
+        cam2.SetForward((-12.0, -2.5, -4.0))
+        res = []
+        for guess in (0, 1):
+            ctx.set_option("split_tail", 0.5)
+            ctx.set_option("tile_guess", guess)
+            ctx.set_option("tile_order", 1)
+            for sub in (1, 2):
+                render(ctx, cam, W, H, spp, sub, depth, accum_count=sub - 1)
+            outs = []
+            for sub in (1, 2, 3):
+                a, i, st = render(ctx, cam2, W, H, spp, sub, depth, accum_count=sub - 1)
+                outs.append((a.copy(), i.copy(), st.segments, st.paths))
+            res.append(outs)
+        for (a, i, sg, pt), (ra, ri, rsg, rpt) in zip(res[0], res[1]):
+            assert np.array_equal(a.view(np.uint32), ra.view(np.uint32)) and np.array_equal(i, ri) and (sg, pt) == (rsg, rpt)
     finally:
-        ctx.set_option("split_tail", 0.0)
+        ctx.set_option("split_tail", 0.5)
+        ctx.set_option("tile_guess", 1)
         ctx.set_option("tile_order", 1)
 
 
