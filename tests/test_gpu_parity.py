@@ -728,6 +728,24 @@ def test_wavefront_equals_persistent_kernel(rtiow_ctx, oracle_mod, rtiow):
     assert abs(int(s1.segments) - int(s2.segments)) < 0.01 * s1.segments and np.abs(f1 - f2).mean() < 5e-3
 
 
+def test_wavefront_on_wide_nodes(ctx, oracle_mod, rtiow):
+    """The wavefront kernel's extend phase on the path kernels' closest-hit structure (huge-sphere list + 4-wide octant-sorted nodes in shared
+    memory, one 1024-thread CTA per SM) and on the pair nodes ("wavefront_wide" = 0): same accumulation buffer as the default kernel."""
+    ctx.set_spheres(rtiow)
+    ctx.build_bvh()
+    W, H, spp, depth = 240, 135, 5, 50
+    cam = vb.rtiow_camera(W, H)
+    try:
+        a, ia, sa = render(ctx, cam, W, H, spp, 3, depth)
+        for wide in (1, 0):
+            ctx.set_option("wavefront_wide", wide)
+            b, ib, sb = render(ctx, cam, W, H, spp, 3, depth, flags=VN_WAVEFRONT)
+            assert ctx.last_accel() == (2 if wide else 1)
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(ia, ib) and (sa.segments, sa.paths) == (sb.segments, sb.paths), wide
+    finally:
+        ctx.set_option("wavefront_wide", 0)
+
+
 def _image_metrics(got, want):
     got, want = got[..., :3].astype(np.float64), want[..., :3].astype(np.float64)
     rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-12)

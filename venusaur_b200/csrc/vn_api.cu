@@ -128,6 +128,9 @@ struct vn_context {
     int blocks_per_sm = 0;            // 0 = occupancy
     size_t smem_scene_limit = 100 * 1024;
     uint32_t wavefront_slots = 1u << 21;
+    uint32_t wavefront_wide = 0;      // "wavefront_wide": the wavefront kernel's extend phase traverses the path kernels' 4-wide nodes in shared memory (one 1024-thread CTA per SM).
+                                      // Measured on RTIOW 1080p: 6.1 Grays/s against 7.1 on the pair nodes (several 256-thread CTAs per SM) and 19.0 for k_render_lean on the
+                                      // same wide nodes: the queue traffic and the four grid barriers per bounce bound this schedule, not its closest-hit structure
     bool octant_nodes = true;         // stage the BVH nodes once per ray octant when 8 copies fit in shared memory
 
     vn_stats stats{};
@@ -353,6 +356,7 @@ int vn_set_option(vn_handle c, const char* name, double value) {
     else if (k == "tile_order") { VN_REQUIRE(c, value >= 0 && value <= 4, "tile_order must be 0..4"); c->tile_order_opt = (uint32_t)value; c->tile_state = 0; }
     else if (k == "warp_tiles") { c->warp_tiles = value != 0 ? 1u : 0u; }
     else if (k == "tile_guess") { c->tile_guess_opt = value != 0 ? 1u : 0u; }
+    else if (k == "wavefront_wide") { c->wavefront_wide = value != 0 ? 1u : 0u; }
     else if (k == "split_tail") { VN_REQUIRE(c, value >= 0 && value <= 0.9, "split_tail must be in [0,0.9]"); c->split_tail = (float)value; }
     else if (k == "steal_smem") { c->steal_smem = value != 0 ? 1u : 0u; }
     else if (k == "steal") { VN_REQUIRE(c, value >= 0 && value <= 1023, "steal must be in [0,1023]"); c->steal = (uint32_t)value; }
@@ -798,6 +802,10 @@ int vn_render(vn_handle c, const vn_params* p) {
         const uint32_t rows = L.row_end - L.row_begin;
         const int rc = ensure_wavefront(c, (uint64_t)p->width * rows, p->samples_per_pixel);
         if (rc != VN_OK) return rc;
+        // the wide nodes of the path kernels when their eight octant copies fit in shared memory ("wavefront_wide"), else the pair nodes
+        if (!(c->wavefront_wide && c->wide_nodes && L.wide && L.num_wide > 0 && c->scene.wide_levels <= kWideMaxLevels &&
+              wide_smem_bytes(L.num_wide, L.num_spheres) + 2048 <= c->smem_optin)) { L.wide = nullptr; L.num_wide = 0; }
+        c->last_accel = L.wide ? 2u : 1u;
         VN_CUDA(c, exact_build ? exact::launch_wavefront(L, c->wf, c->num_sms, c->stream, &launches)
                                : fast::launch_wavefront(L, c->wf, c->num_sms, c->stream, &launches));
     } else {

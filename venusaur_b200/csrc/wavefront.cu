@@ -37,13 +37,13 @@ namespace VN_NS {
 
 namespace {
 
-constexpr int kWfThreads = 256;
-constexpr int kWfWarps = kWfThreads / 32;
+constexpr int kWfThreads = 256;      // CTA size of the pair-node variants; the wide-node variant (one CTA per SM, scene copies fill its shared memory) runs 1024
 
 __device__ __forceinline__ uint32_t ld_count(const uint32_t* p) { return __ldcg(p); }
 
 // Block-wide stream compaction step: returns this thread's output position for a `flag`ged item, after reserving
 // the block's span with one atomicAdd on *global_count.  All threads of the block must call it.
+template <int kWfWarps>
 __device__ __forceinline__ uint32_t block_reserve(bool flag, uint32_t* global_count, uint32_t* s_warp /*[kWfWarps]*/, uint32_t* s_base) {
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t mask = __ballot_sync(0xffffffffu, flag);
@@ -62,8 +62,12 @@ __device__ __forceinline__ uint32_t block_reserve(bool flag, uint32_t* global_co
     return pos;
 }
 
-template <bool kSmem>
-__global__ void __launch_bounds__(kWfThreads) k_wavefront(const __grid_constant__ RenderLaunch p, const __grid_constant__ WavefrontBuffers wf) {
+// kWide: the extend phase traverses the 4-wide, octant-sorted nodes of the path kernels (eight copies in shared memory, lbvh_core.cuh::
+// wide_octant_node) after the huge-sphere list -- the same closest-hit structure as k_render_lean, so that wavefront against megakernel is a
+// comparison of SCHEDULES (round 1 compared this kernel on pair nodes with a megakernel on wide nodes).
+template <bool kSmem, bool kWide, int kThreads>
+__global__ void __launch_bounds__(kThreads) k_wavefront(const __grid_constant__ RenderLaunch p, const __grid_constant__ WavefrontBuffers wf) {
+    constexpr int kWfWarps = kThreads / 32;
     cg::grid_group grid = cg::this_grid();
     extern __shared__ float4 s_scene[];
     __shared__ uint32_t s_warp[kWfWarps];
@@ -71,7 +75,26 @@ __global__ void __launch_bounds__(kWfThreads) k_wavefront(const __grid_constant_
     __shared__ uint32_t s_ticket;
 
     SceneView sc;
-    if (kSmem) {
+    const uint32_t node_f4s = kWideNodeF4 * p.num_wide;
+    if (kWide) {
+        float4* s_nodes = s_scene;
+        float4* s_geom = s_nodes + (size_t)node_f4s * 8;
+        float4* s_mat = s_geom + p.num_spheres;
+        uint8_t* s_type = reinterpret_cast<uint8_t*>(s_mat + p.num_spheres);
+        for (uint32_t i = threadIdx.x; i < 8u * p.num_wide; i += blockDim.x) {
+            const uint32_t k = i / p.num_wide, j = i - k * p.num_wide;
+            float4 canon[8], out[kWideNodeF4];
+#pragma unroll
+            for (int q = 0; q < 8; q++) canon[q] = p.wide[8ull * j + q];
+            wide_octant_node(canon, k, out);
+#pragma unroll
+            for (int q = 0; q < (int)kWideNodeF4; q++) s_nodes[(size_t)k * node_f4s + kWideNodeF4 * j + q] = out[q];
+        }
+        for (uint32_t i = threadIdx.x; i < p.num_spheres; i += blockDim.x) { s_geom[i] = p.geom[i]; s_mat[i] = p.mat[i]; }
+        for (uint32_t i = threadIdx.x; i < p.num_spheres; i += blockDim.x) s_type[i] = p.type[i];
+        __syncthreads();
+        sc.nodes = s_nodes; sc.geom = s_geom; sc.mat = s_mat; sc.type = s_type;
+    } else if (kSmem) {
         float4* s_nodes = s_scene;
         float4* s_geom = s_nodes + 2 * (size_t)p.num_nodes;
         float4* s_mat = s_geom + p.num_spheres;
@@ -134,7 +157,7 @@ __global__ void __launch_bounds__(kWfThreads) k_wavefront(const __grid_constant_
         {
             const WfState A = wf.st[cur];
             for (;;) {
-                if (threadIdx.x == 0) s_ticket = atomicAdd(&C[kWfTicketExtend], (uint32_t)kWfThreads);
+                if (threadIdx.x == 0) s_ticket = atomicAdd(&C[kWfTicketExtend], (uint32_t)kThreads);
                 __syncthreads();
                 const uint32_t base = s_ticket;
                 __syncthreads();
@@ -146,7 +169,23 @@ __global__ void __launch_bounds__(kWfThreads) k_wavefront(const __grid_constant_
                     float t;
                     int prim;
                     TraceCounters cnt{0u, 0u};
-                    closest_hit<false>(sc.nodes, sc.geom, sc.root_link, mk3(A.ox[i], A.oy[i], A.oz[i]), mk3(A.dx[i], A.dy[i], A.dz[i]), t, prim, cnt, 0u, p.gate != 0u);
+                    const f3 ro = mk3(A.ox[i], A.oy[i], A.oz[i]), rd = mk3(A.dx[i], A.dy[i], A.dz[i]);
+                    if (kWide) {
+                        float t0 = kTMax;
+                        int prim0 = -1;
+                        if (p.huge.n) {                           // the huge spheres first (lbvh_core.cuh::HugeList), as in the path kernels
+                            const float a = dot(rd, rd), inv_a = rcp(a);
+                            for (uint32_t h = 0; h < p.huge.n; h++) {
+                                const uint32_t hs = p.huge.idx[h];
+                                const float4 g = sc.geom[hs];
+                                const float th = sphere_root(ro, rd, a, inv_a, g.x, g.y, g.z, g.w, kTMin, t0);
+                                if (th >= 0.0f) { t0 = th; prim0 = (int)hs; }
+                            }
+                        }
+                        closest_hit_wide<false>(sc.nodes, node_f4s, sc.geom, p.wide_root, ro, rd, t, prim, cnt, t0, prim0);
+                    } else {
+                        closest_hit<false>(sc.nodes, sc.geom, sc.root_link, ro, rd, t, prim, cnt, 0u, p.gate != 0u);
+                    }
                     wf.hit_t[i] = t;
                     wf.hit_prim[i] = prim;
                     cls = prim < 0 ? 0u : 1u + (uint32_t)sc.type[prim];
@@ -155,7 +194,7 @@ __global__ void __launch_bounds__(kWfThreads) k_wavefront(const __grid_constant_
 #pragma unroll
                 for (uint32_t m = 0; m < 4u; m++) {
                     const bool mine = cls == m;
-                    const uint32_t pos = block_reserve(mine, &C[kWfCountMat + m], s_warp, &s_base);
+                    const uint32_t pos = block_reserve<kWfWarps>(mine, &C[kWfCountMat + m], s_warp, &s_base);
                     if (mine) wf.mat_queue[m][pos] = i;
                 }
             }
@@ -170,7 +209,7 @@ __global__ void __launch_bounds__(kWfThreads) k_wavefront(const __grid_constant_
             for (uint32_t m = 0; m < 4u; m++) {
                 const uint32_t n_m = ld_count(&C[kWfCountMat + m]);
                 for (;;) {
-                    if (threadIdx.x == 0) s_ticket = atomicAdd(&C[kWfTicketShade + m], (uint32_t)kWfThreads);
+                    if (threadIdx.x == 0) s_ticket = atomicAdd(&C[kWfTicketShade + m], (uint32_t)kThreads);
                     __syncthreads();
                     const uint32_t base = s_ticket;
                     __syncthreads();
@@ -194,7 +233,7 @@ __global__ void __launch_bounds__(kWfThreads) k_wavefront(const __grid_constant_
                             out[0] = result.x; out[1] = result.y; out[2] = result.z;
                         }
                     }
-                    const uint32_t pos = block_reserve(cont, &C[kWfCountNext], s_warp, &s_base);
+                    const uint32_t pos = block_reserve<kWfWarps>(cont, &C[kWfCountNext], s_warp, &s_base);
                     if (cont) {
                         B.ox[pos] = st.o.x; B.oy[pos] = st.o.y; B.oz[pos] = st.o.z;
                         B.dx[pos] = st.d.x; B.dy[pos] = st.d.y; B.dz[pos] = st.d.z;
@@ -248,20 +287,20 @@ __global__ void __launch_bounds__(256) k_wf_accumulate(const __grid_constant__ R
     }
 }
 
-template <bool kSmem>
+template <bool kSmem, bool kWide, int kThreads>
 cudaError_t launch_wf(const RenderLaunch& p, const WavefrontBuffers& wf, int num_sms, size_t smem, cudaStream_t stream) {
     cudaError_t e;
     if (smem > 48 * 1024) {
-        e = cudaFuncSetAttribute(k_wavefront<kSmem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(k_wavefront<kSmem, kWide, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wavefront<kSmem>, kWfThreads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_wavefront<kSmem, kWide, kThreads>, kThreads, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-    dim3 grid((unsigned)(num_sms * per_sm)), block(kWfThreads);
+    dim3 grid((unsigned)(num_sms * per_sm)), block(kThreads);
     void* args[] = {(void*)&p, (void*)&wf};
-    return cudaLaunchCooperativeKernel((const void*)k_wavefront<kSmem>, grid, block, args, smem, stream);
+    return cudaLaunchCooperativeKernel((const void*)k_wavefront<kSmem, kWide, kThreads>, grid, block, args, smem, stream);
 }
 
 }  // namespace
@@ -270,7 +309,10 @@ cudaError_t launch_wavefront(const RenderLaunch& p, const WavefrontBuffers& wf, 
     if (wf.capacity < p.spp) return cudaErrorInvalidValue;
     const size_t need = scene_smem_bytes(p.num_nodes, p.num_spheres);
     const bool in_smem = p.num_spheres > 0 && need <= 100 * 1024;
-    cudaError_t e = in_smem ? launch_wf<true>(p, wf, num_sms, need, stream) : launch_wf<false>(p, wf, num_sms, 0, stream);
+    // the wide nodes of the path kernels when their eight octant copies fit (the caller clears p.wide otherwise): one 1024-thread CTA per SM
+    const size_t need_wide = p.wide && p.num_wide ? wide_smem_bytes(p.num_wide, p.num_spheres) : 0;
+    cudaError_t e = need_wide ? launch_wf<true, true, 1024>(p, wf, num_sms, need_wide, stream)
+                              : (in_smem ? launch_wf<true, false, kWfThreads>(p, wf, num_sms, need, stream) : launch_wf<false, false, kWfThreads>(p, wf, num_sms, 0, stream));
     if (e != cudaSuccess) return e;
     const uint32_t region_pixels = p.width * (p.row_end - p.row_begin);
     const uint32_t blocks = (uint32_t)std::min<uint64_t>(((uint64_t)region_pixels + 255) / 256, (uint64_t)num_sms * 16);
