@@ -850,6 +850,9 @@ int vn_render(vn_handle c, const vn_params* p) {
             // scratch slots of the drain's sample stealing: one per lane of the grid (a few tens of MB; 180 GB of HBM)
             const size_t lanes = (size_t)cfg.blocks * cfg.threads;
             const size_t need = lanes * (p->samples_per_pixel + 1u) * sizeof(float4);
+            if (need > ((size_t)1 << 30)) {
+                // (hundreds of samples per pixel and launch: the slots would take gigabytes, and launches that long do not need the drain shortened)
+            } else {
             if (need > c->steal_scratch_cap) {
                 VN_CUDA(c, cudaStreamSynchronize(c->stream));
                 cudaFree(c->d_steal_scratch); c->d_steal_scratch = nullptr; c->steal_scratch_cap = 0;
@@ -864,6 +867,7 @@ int vn_render(vn_handle c, const vn_params* p) {
                 VN_CUDA(c, cudaMemsetAsync(c->d_steal_count, 0, c->steal_count_cap, c->stream));
             }
             L.steal_scratch = c->d_steal_scratch; L.steal_count = c->d_steal_count;
+            }
         }
         // split frame: the cheap end of the cost-ordered tile list goes to a second launch on tail_stream (same kernel, own ticket counter, the
         // statistics add up in the same counters); everything behind it on c->stream waits for both
