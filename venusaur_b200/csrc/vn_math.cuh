@@ -4,9 +4,9 @@
 // Two builds of every kernel are made from this one header:
 //   VN_EXACT=1  compiled with -fmad=false: each float operation is one IEEE-754 binary32 op in the order the
 //               reference writes it (RayTracer.cu / vec_math.h), FP64 where the reference uses FP64.  Bit-identical
-//               to the host oracle; used by the parity tests.
-//   VN_EXACT=0  the FAST build that is benchmarked: FMA contraction, approximate reciprocal / rsqrt, FP32
-//               replacements for the FP64 fragments.  Checked statistically against the same oracle.
+//               to the host oracle: the DEFAULT build, the one bench.py measures and the parity tests check.
+//   VN_EXACT=0  the opt-in relaxed build (VN_FAST): FMA contraction, approximate reciprocal / rsqrt, FP32
+//               replacements for the FP64 fragments.  Checked statistically against the same oracle; not within the image tolerance.
 // The header also compiles as plain C++ (g++) so that tests can run the exact math on the CPU; that host build
 // is test-only -- the library itself has no CPU path.
 //
@@ -1042,7 +1042,7 @@ VN_HD void closest_hit_wide_global(const node_f4* __restrict__ wide, const node_
 }
 
 // ---- shading programs, one per class of hit, on the hit POINT p (= o + d*t, RayTracer.cu:256).  shade_segment() below
-// composes them; the slot-scheduled kernel (slot_kernels.cu) calls them one class at a time.
+// composes them.
 VN_HD f3 hit_point(f3 o, f3 d, float t) { return o + d * t; }
 // normal + face-forwarding of hit_frame() for a known hit point (RayTracer.cu:257-258, 219-224)
 VN_HD void hit_normal(f3 p, f3 d, const node_f4& g, f3& n, bool& front) {
