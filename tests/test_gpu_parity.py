@@ -562,8 +562,29 @@ def test_sample_stealing_keeps_the_accumulation_buffer(ctx, oracle_mod, rtiow):
             assert ctx.last_accel() == 1
             res.append((a, i, st.segments, st.paths))
         assert np.array_equal(res[0][0].view(np.uint32), res[1][0].view(np.uint32)) and np.array_equal(res[0][1], res[1][1]) and res[0][2:] == res[1][2:]
+        # sample-range units ("units": a tile's samples handed out in 2 or 4 ranges, sum and camera seed carried from range to range through
+        # memory) with and without the stealing drain, progressive launches of one view (the first one collects the tile costs: whole tiles),
+        # spp that 4 does not divide (falls back to 2 ranges), and a row shard
+        W, H = 352, 180                                           # 1980 tiles > 8 per SM: units are active
+        cam = vb.Camera((0.0, 0.0, 120.0), 40.0, W / H, 0.0, 120.0)
+        cam.SetForward((0.0, 0.0, -1.0))
+        ref = None
+        for units, steal, spp in ((1, 0, 8), (4, 0, 8), (4, 1, 8), (2, 1, 8), (8, 1, 8), (16, 1, 8), (1, 0, 6), (4, 1, 6)):
+            ctx.set_option("units", units)
+            ctx.set_option("steal", steal)
+            ctx.set_option("tile_order", 1)                       # (forget the view: the next launch collects costs again)
+            outs = []
+            for sub in (1, 2, 3):
+                a, i, st = render(ctx, cam, W, H, spp, sub, 24, accum_count=sub - 1, rows=(0, H) if sub < 3 else (0, 92))
+                outs.append((a.copy(), i.copy(), st.segments, st.paths))
+            if units == 1:
+                ref = outs
+            else:
+                for (a, i, sg, pt), (ra, ri, rsg, rpt) in zip(outs, ref):
+                    assert np.array_equal(a.view(np.uint32), ra.view(np.uint32)) and np.array_equal(i, ri) and (sg, pt) == (rsg, rpt), (units, steal, spp)
     finally:
         ctx.set_option("steal", 1)
+        ctx.set_option("units", 4)
         ctx.set_option("steal_smem", 0)
 
 

@@ -14,14 +14,22 @@ def main():
     ctx = vb.Context(0)
     for kv in sys.argv[1:]:
         k, v = kv.split("=")
-        if k in ("profile", "only"):
+        if k in ("profile", "only", "scene"):
             continue
         ctx.set_option(k, float(v))
-    ctx.set_spheres(vb.rtiow_final_scene()); ctx.build_bvh()
-    for (W, H) in (((1920, 1080),) if "only=1080" in sys.argv else ((1920, 1080), (3840, 2160))):
+    big = [kv for kv in sys.argv[1:] if kv.startswith("scene=")]              # scene=1m | 16m: bench.py's synthetic scenes (L2 / HBM traversal)
+    if big:
+        n, seed, S, mix = {"1m": (1_000_000, 0x5EED0001, 100.0, 0), "16m": (16_000_000, 0x5EED0002, 250.0, 1)}[big[0].split("=")[1]]
+        ctx.set_spheres(vb.random_scene(n, seed, S, mix)); ctx.build_bvh()
+    else:
+        ctx.set_spheres(vb.rtiow_final_scene()); ctx.build_bvh()
+    for (W, H) in (((1920, 1080),) if ("only=1080" in sys.argv or big) else ((1920, 1080), (3840, 2160))):
         cam = vb.rtiow_camera(W, H)
+        if big:
+            cam = vb.Camera((0.0, 0.0, 2.0 * S), 40.0, W / H, 0.0, 2.0 * S)
+            cam.SetForward((0.0, 0.0, -1.0))
         for rep in range(3):
-            ctx.render(ctx.make_params(cam, W, H, 16, 1 + rep, 50, flags=VN_COUNTERS | VN_NO_TONEMAP))
+            ctx.render(ctx.make_params(cam, W, H, 16, 1 + rep, 64 if big else 50, flags=VN_COUNTERS | VN_NO_TONEMAP))
             st = ctx.stats()
             start, exhaust, end = ctx.launch_timeline()
             print("%dx%d launch %d: ms_render %.3f | kernel %.3f ms, tickets exhausted at %.3f ms (%.1f %%), drain %.3f ms"

@@ -48,6 +48,11 @@ struct RenderLaunch {
     uint32_t tile_cost_stride;       //   tile_cost[tile] += segments, tile_cost[tile_cost_stride + tile] = max(.., segments)
     uint32_t* timeline;              // instrumented launches of k_render_lean: [0..1024) lanes retired per 8 us bin since the CTA's start, [1024..2048) the ray
                                      // segments of the last pixel those lanes finished (0 outside the cost-collecting launch); null otherwise
+    uint32_t units_log2;             // k_render_lean<kGlobal>: the work items are (tile, unit) with a tile's spp samples cut into 1 << units_log2 sample ranges; the item
+                                     //   list in tile_order carries tile | unit << 24 (path_kernels.cu, "sample-range units"); 0 = whole tiles
+    float4* carry;                   //   per pixel (tile-major: tile * 32 + position in the tile): {sum so far, camera seed} handed from a unit to the next
+    uint32_t* unit_flag;             //   per pixel: unit_epoch + number of finished units of this launch
+    uint32_t unit_epoch;             //   (a multiple of 32 that grows with every launch: no memset between launches)
     uint32_t steal;                  // k_render_lean: >= 1 = sample stealing inside a warp during the drain (path_kernels.cu): the fewest samples a lane must have left to give one away
     float4* steal_scratch;           //   one slot of spp + 1 float4 per lane of the grid: [0] the owner's prefix sum (.w = first sample of the suffix), [1 + k] sample k's radiance
     uint32_t* steal_count;           //   per slot: parts handed in (bit 31: the owner's prefix); zero between launches
@@ -116,6 +121,7 @@ constexpr int kWfArraysTotal = 2 * kWfStateArrays + 2 + 4;   // 4-byte arrays of
     int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool count, bool octant, bool wide, bool grid, bool lean, int global_ctas); \
     cudaError_t launch_render_persistent(const RenderLaunch& p, const KernelConfig& cfg, cudaStream_t stream);         \
     cudaError_t launch_tonemap(const float4* accum, float scale, uint32_t* image, uint64_t n, cudaStream_t stream);    \
+    cudaError_t launch_unit_items(const uint32_t* order, uint32_t n, uint32_t units_log2, uint32_t* items, cudaStream_t stream); \
     cudaError_t launch_tile_keys(const uint32_t* cost, uint32_t stride, uint32_t n, uint32_t mode, uint32_t spp, uint32_t* keys, uint32_t* vals, uint32_t* n_all_miss, cudaStream_t stream); \
     cudaError_t launch_reduce_tonemap_peers(const float4* const* peers, uint32_t n_peers, float scale, uint64_t begin, \
                                             uint64_t end, float4* accum_out, uint32_t* image, const uint32_t* const* peer_flags, \

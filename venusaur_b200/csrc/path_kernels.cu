@@ -698,6 +698,29 @@ __device__ __forceinline__ void lean_epilogue(const RenderLaunch& p, const Trace
 // code that redistributes the samples.  With that code inside the first loop, or behind a call, the compiler took the first loop's
 // warp-uniform counters out of the uniform registers and spilled the pixel's sum (measured: -1.7 % on the whole launch); the rounds cost the
 // drain a little lane utilisation instead, where most lanes idle anyway.
+// Sample-range units (k_render_lean<kGlobal>).  A pixel of a million-sphere scene costs a lane 16 samples x 23 segments x a dozen dependent
+// L2 fetches each: ~20 ms, one tenth of the launch -- whatever the tile order, the launch ends with whole pixels started late (measured, 1 M
+// spheres: tickets exhausted after 76 % of the launch; 86 % with the sample-stealing drain).  So the work items of those scenes are
+// (tile, unit): a tile's spp samples are cut into 2, 4, 8 or 16 ranges, handed out as separate tickets -- all first ranges, then all second ranges, ...
+// A unit hands the pixel on through memory: {sum so far, camera seed} in `carry`, and a per-pixel flag that says how many units are done; the
+// warp that draws (tile, u) starts it once the flags of the tile's 32 pixels say u (it keeps the ticket and asks again in its next iteration
+// otherwise: it never spins, the unit it waits for may be in flight in its own lanes).  The samples of a pixel are still summed in sample
+// order by whoever holds the pixel, from the carried sum on: the accumulation buffer keeps its bits.  The lane's unit (0..15) rides in the
+// free bits of pxy (frames are < 16384 pixels wide and high): bits 14-15 and 30-31.
+__device__ __forceinline__ uint32_t unit_px(uint32_t pxy) { return pxy & 0x3FFFu; }
+__device__ __forceinline__ uint32_t unit_py(uint32_t pxy) { return (pxy >> 16) & 0x3FFFu; }
+__device__ __forceinline__ uint32_t unit_of(uint32_t pxy) { return ((pxy >> 14) & 3u) | ((pxy >> 28) & 12u); }
+__device__ __forceinline__ uint32_t unit_samples(const RenderLaunch& p, uint32_t) { return p.spp >> p.units_log2; }
+__device__ __forceinline__ void finish_unit(const RenderLaunch& p, uint32_t pxy, f3 sum, uint32_t seed_after) {
+    const uint32_t px = unit_px(pxy), py = unit_py(pxy), u = unit_of(pxy);
+    if (u + 1u == (1u << p.units_log2)) { finish_pixel(p, py * p.width + px, sum); return; }
+    const uint32_t ry = py - p.row_begin;
+    const uint32_t ci = ((ry >> 2) * p.tiles_x + (px >> 3)) * 32u + (ry & 3u) * 8u + (px & 7u);
+    __stcg(p.carry + ci, make_float4(sum.x, sum.y, sum.z, __uint_as_float(seed_after)));
+    __threadfence();
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.unit_flag + ci), "r"(p.unit_epoch + u + 1u) : "memory");
+}
+
 template <bool kCount, bool kGlobal>
 __device__ __forceinline__ void lean_finish_traversal(const RenderLaunch& p, const SceneView& sc, const PathState& st, uint32_t& cur, uint32_t& top, uint32_t& tos,
                                                       float& tbest, int& prim, SlabScale& ss, const WideBase& wb, TraceCounters& cnt) {
@@ -740,6 +763,7 @@ __device__ __forceinline__ void lean_drain(const RenderLaunch& p, const SceneVie
     constexpr uint32_t kWordBytes = kGlobal ? 4u : 2u;
     // (the cost-collecting launch attributes ray segments to the lane's own pixel: no stealing there)
     const bool steal_on = !kCost && p.steal != 0u && p.steal_scratch != nullptr;
+    constexpr bool kUnits = kGlobal;                               // sample-range units (see finish_unit): the lane's unit rides in pxy
     volatile uint32_t park[6];
     lean_finish_traversal<kCount, kGlobal>(p, sc, st, cur, top, tos, tbest, prim, ss, wb, cnt);
     for (;;) {
@@ -759,9 +783,9 @@ __device__ __forceinline__ void lean_drain(const RenderLaunch& p, const SceneVie
             }
         }
         bool retire = false;
-        if (lane_state == kLaneIdle && s_left == 0u) {            // a whole pixel
-            const uint32_t px = pxy & 0xFFFFu, py = pxy >> 16;
-            finish_pixel(p, py * p.width + px, sum);
+        if (lane_state == kLaneIdle && s_left == 0u) {            // a whole pixel (or a whole unit of it)
+            const uint32_t px = kUnits ? unit_px(pxy) : (pxy & 0xFFFFu), py = kUnits ? unit_py(pxy) : (pxy >> 16);
+            if (kUnits) finish_unit(p, pxy, sum, cam_seed); else finish_pixel(p, py * p.width + px, sum);
             if (kCost) { uint32_t* tc = p.tile_cost + ((py - p.row_begin) >> 2) * p.tiles_x + (px >> 3); atomicAdd(tc, px_seg); atomicMax(tc + p.tile_cost_stride, px_seg); }
             if (kCount) last_seg = px_seg;
             retire = true;
@@ -771,29 +795,32 @@ __device__ __forceinline__ void lean_drain(const RenderLaunch& p, const SceneVie
             const bool helper = (s_left >> 31) != 0u;
             const uint32_t g = lane0 + (helper ? ((s_left >> 26) & 31u) : (threadIdx.x & 31u));
             float4* slot = p.steal_scratch + (size_t)g * (p.spp + 1u);
+            const uint32_t m_s = kUnits ? unit_samples(p, pxy) : p.spp;   // samples of the pixel's unit (indices below are relative to its first)
             uint32_t first = 0xFFFFFFFFu;                         // != 0xFFFFFFFF: this lane arrived last; first sample of the suffix
             if (helper) {
-                __stcg(slot + 1u + ((s_left >> 16) & 0x3FFu), make_float4(sum.x, sum.y, sum.z, 0.0f));
+                // (.w: the camera seed behind this sample -- the last sample's is what the pixel's next unit starts from)
+                __stcg(slot + 1u + ((s_left >> 16) & 0x3FFu), make_float4(sum.x, sum.y, sum.z, __uint_as_float(cam_seed)));
                 __threadfence();
                 const uint32_t v = atomicAdd(p.steal_count + g, 1u);
                 if (v & 0x80000000u) {                            // the owner has handed its prefix in: slot[0].w = first sample of the suffix
                     __threadfence();
                     const uint32_t j_end = __float_as_uint(__ldcg(slot).w);
-                    if ((v & 0x7FFFFFFFu) + 1u == p.spp - j_end) first = j_end;
+                    if ((v & 0x7FFFFFFFu) + 1u == m_s - j_end) first = j_end;
                 }
             } else {
                 const uint32_t n_out = (s_left >> 16) & 0x3FFu;
-                __stcg(slot, make_float4(sum.x, sum.y, sum.z, __uint_as_float(p.spp - n_out)));
+                __stcg(slot, make_float4(sum.x, sum.y, sum.z, __uint_as_float(m_s - n_out)));
                 __threadfence();
-                if (atomicAdd(p.steal_count + g, 0x80000000u) == n_out) first = p.spp - n_out;
+                if (atomicAdd(p.steal_count + g, 0x80000000u) == n_out) first = m_s - n_out;
             }
             if (first != 0xFFFFFFFFu) {
                 __threadfence();
                 const float4 b = __ldcg(slot);
                 f3 total = mk3(b.x, b.y, b.z);
-                for (uint32_t k = first; k < p.spp; k++) { const float4 r = __ldcg(slot + 1u + k); total = total + mk3(r.x, r.y, r.z); }   // RayTracer.cu:203, in order
-                finish_pixel(p, (pxy >> 16) * p.width + (pxy & 0xFFFFu), total);
-                p.steal_count[g] = 0u;                            // (the slot is not used again in this launch)
+                uint32_t seed_after = 0u;
+                for (uint32_t k = first; k < m_s; k++) { const float4 r = __ldcg(slot + 1u + k); total = total + mk3(r.x, r.y, r.z); seed_after = __float_as_uint(r.w); }   // RayTracer.cu:203, in order
+                if (kUnits) finish_unit(p, pxy, total, seed_after); else finish_pixel(p, (pxy >> 16) * p.width + (pxy & 0xFFFFu), total);
+                p.steal_count[g] = 0u;                            // (a lane owns one pixel in the drain: the slot is not used again in this launch)
             }
             retire = true;
         }
@@ -819,10 +846,11 @@ __device__ __forceinline__ void lean_drain(const RenderLaunch& p, const SceneVie
                     const uint32_t d_s = __shfl_sync(kFull, s_left, d), d_seed = __shfl_sync(kFull, cam_seed, d), d_pxy = __shfl_sync(kFull, pxy, d);
                     const uint32_t d_out = (d_s >> 16) & 0x3FFu, d_own = d_s & 0xFFFFu;
                     const uint32_t rank = (uint32_t)__popc(thieves & ((1u << (threadIdx.x & 31u)) - 1u));
+                    const uint32_t m_d = kUnits ? unit_samples(p, d_pxy) : p.spp;   // samples of the owner's unit
                     if (lane_state == kLaneRetired && rank < n) {
-                        const uint32_t k = p.spp - d_out - 1u - rank;     // from the end of the owner's range
-                        uint32_t sd = d_seed;                              // the owner's seed stands before sample spp - d_out - d_own
-                        for (uint32_t j = p.spp - d_out - d_own; j < k; j++) camera_skip(sd);
+                        const uint32_t k = m_d - d_out - 1u - rank;       // from the end of the owner's range
+                        uint32_t sd = d_seed;                              // the owner's seed stands before sample m_d - d_out - d_own
+                        for (uint32_t j = m_d - d_out - d_own; j < k; j++) camera_skip(sd);
                         cam_seed = sd;
                         pxy = d_pxy;
                         sum = mk3(0.0f);
@@ -837,7 +865,7 @@ __device__ __forceinline__ void lean_drain(const RenderLaunch& p, const SceneVie
         const bool launching = lane_state == kLaneIdle;          // (a lane that just took a sample, or whose path just ended)
         w_path += (uint32_t)__popc(__ballot_sync(kFull, launching));
         if (launching) {
-            camera_ray(p.cam, pxy & 0xFFFFu, pxy >> 16, cam_seed, st.o, st.d);   // RayTracer.cu:173-177
+            camera_ray(p.cam, kUnits ? unit_px(pxy) : (pxy & 0xFFFFu), kUnits ? unit_py(pxy) : (pxy >> 16), cam_seed, st.o, st.d);   // RayTracer.cu:173-177
             st.thr = mk3(1.0f);
             st.seed = cam_seed;                                   // prd.seed = seed: a copy (RayTracer.cu:183)
             st.depth = (int)p.max_depth - 1;                      // RayTracer.cu:184
@@ -941,6 +969,9 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
     ss.sdir = ss.nsood = mk3(0.0f);
     WideBase wb = wide_base(sc.nodes, 0u, node_f4s);
     uint32_t w_ox = 0u, w_oy = 0u, w_cursor = 32u; // the warp's current tile (its first pixel) and the next pixel of it to hand out (warp-uniform)
+    constexpr bool kUnits = kGlobal;               // sample-range units (see finish_unit above); runtime switch: p.units_log2
+    uint32_t w_item = 0u;                          // kUnits: the warp's current work item (tile | unit << 24) ...
+    bool w_pending = false;                        // ... drawn but not started: the tile's previous unit is not complete yet
     uint32_t t_seed = 0u;                          // camera seed of pixel (lane) of that tile
 
     for (;;) {
@@ -964,8 +995,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
             }
         }
         if (fin && lane_state == kLaneIdle && sd < 0x10000u) {
-            const uint32_t px = pxy & 0xFFFFu, py = pxy >> 16;
-            finish_pixel(p, py * p.width + px, sum);
+            const uint32_t px = kUnits ? unit_px(pxy) : (pxy & 0xFFFFu), py = kUnits ? unit_py(pxy) : (pxy >> 16);
+            if (kUnits) finish_unit(p, pxy, sum, cam_seed); else finish_pixel(p, py * p.width + px, sum);
             if (kCost) { uint32_t* tc = p.tile_cost + ((py - p.row_begin) >> 2) * p.tiles_x + (px >> 3); atomicAdd(tc, px_seg); atomicMax(tc + p.tile_cost_stride, px_seg); }
             if (kCount) last_seg = px_seg;
             lane_state = kLaneNoPixel;
@@ -977,9 +1008,11 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
             while (m) {
                 if (w_cursor >= 32u) {
                     uint32_t t = 0u;
+                    if (!(kUnits && w_pending)) {
                     if ((threadIdx.x & 31u) == 0u) t = atomicAdd(p.work_counter, 1u);
                     t = __shfl_sync(kFull, t, 0);
-                    if (t >= (p.total_work >> 5)) {               // no tiles left: the asking lanes only vote from now on (or help, see above)
+                    }
+                    if (!(kUnits && w_pending) && t >= (p.total_work >> 5)) {   // no tiles left: the asking lanes only vote from now on (or help, see above)
                         if (kDrain) w_cursor = 33u;               // (> 32: this warp has seen the tickets exhausted and leaves the loop below)
                         if (need) {
                             lane_state = kLaneRetired;
@@ -995,15 +1028,31 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
                         }
                         break;
                     }
-                    const uint32_t tile = p.tile_order ? __ldg(p.tile_order + t) : t;
-                    w_cursor = 0u;
+                    if (!(kUnits && w_pending)) w_item = p.tile_order ? __ldg(p.tile_order + t) : t;
+                    const uint32_t tile = kUnits ? (w_item & 0x00FFFFFFu) : w_item;
                     // every lane forms the camera seed of "its" pixel of the new tile (pixel i of the tile by lane i) while the warp is
                     // converged; the lanes that take a pixel pick its seed up with one shuffle.  Formed by the taker, the 70 instructions
                     // of tea<4> ran at 1.6 active lanes 1.3 M times per launch (ncu: 2.9 % of all warp instructions), now once per tile.
                     uint32_t ty, tx;
                     tile_row_col(tile, p.tiles_x, p.tiles_x_inv, ty, tx);
                     w_ox = tx * 8u; w_oy = p.row_begin + ty * 4u;
-                    t_seed = tea4((w_oy + ((threadIdx.x & 31u) >> 3)) * p.width + w_ox + (threadIdx.x & 7u), p.subframe_index);   // RayTracer.cu:169
+                    if (kUnits && (w_item >> 24) != 0u) {
+                        // a later unit of the tile: its pixels' sums and seeds come from the unit before -- once ALL of them are there
+                        const uint32_t lpx = w_ox + (threadIdx.x & 7u), lpy = w_oy + ((threadIdx.x & 31u) >> 3);
+                        const uint32_t ci = tile * 32u + (threadIdx.x & 31u);
+                        bool ready = true;
+                        if (lpx < p.width && lpy < p.row_end) {
+                            uint32_t f;
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(p.unit_flag + ci) : "memory");
+                            ready = (int32_t)(f - (p.unit_epoch + (w_item >> 24))) >= 0;
+                        }
+                        w_pending = __all_sync(kFull, ready) == 0;
+                        if (w_pending) break;                      // (the askers stay without a pixel and ask again in the warp's next iteration)
+                        t_seed = (lpx < p.width && lpy < p.row_end) ? __float_as_uint(__ldcg(&p.carry[ci].w)) : 0u;
+                    } else {
+                        t_seed = tea4((w_oy + ((threadIdx.x & 31u) >> 3)) * p.width + w_ox + (threadIdx.x & 7u), p.subframe_index);   // RayTracer.cu:169
+                    }
+                    w_cursor = 0u;
                     if (kCount && p.timeline && (threadIdx.x & 31u) == 0u)
                         atomicAdd(p.timeline + 2048u + (uint32_t)min((unsigned long long)1023u, (global_ns() - t_start) >> 13), 1u);
                 }
@@ -1017,6 +1066,12 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
                         cam_seed = in_seed;
                         sum = mk3(0.0f);
                         sd = p.spp << 16;
+                        if (kUnits && p.units_log2) {
+                            const uint32_t u = w_item >> 24;
+                            pxy |= ((u & 3u) << 14) | ((u & 12u) << 28);
+                            sd = (p.spp >> p.units_log2) << 16;
+                            if (u) { const float4 c = __ldcg(p.carry + (w_item & 0x00FFFFFFu) * 32u + in); sum = mk3(c.x, c.y, c.z); }
+                        }
                         if (kCost || kCount) px_seg = 0u;
                         lane_state = kLaneIdle;
                     }
@@ -1030,7 +1085,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
         w_path += (uint32_t)__popc(__ballot_sync(kFull, launching));
         if (starting) {
             if (launching) {
-                camera_ray(p.cam, pxy & 0xFFFFu, pxy >> 16, cam_seed, st.o, st.d);   // RayTracer.cu:173-177
+                camera_ray(p.cam, kUnits ? unit_px(pxy) : (pxy & 0xFFFFu), kUnits ? unit_py(pxy) : (pxy >> 16), cam_seed, st.o, st.d);   // RayTracer.cu:173-177
                 st.thr = mk3(1.0f);
                 st.seed = cam_seed;                               // prd.seed = seed: a copy (RayTracer.cu:183)
                 sd = ((sd - 0x10000u) & 0xFFFF0000u) | (p.max_depth - 1u);   // one sample less to start; prd.depth = max_depth - 1 (RayTracer.cu:184)
@@ -1141,6 +1196,14 @@ __global__ void __launch_bounds__(256) k_tile_keys(const uint32_t* __restrict__ 
     c = c < 0x00FFFFFFu ? c : 0x00FFFFFFu;
     keys[i] = 0x00FFFFFFu - c;
     vals[i] = i;
+}
+
+// Work items of a launch with sample-range units (finish_unit above): all first units in tile order, then all second units, ...
+__global__ void __launch_bounds__(256) k_unit_items(const uint32_t* __restrict__ order, uint32_t n, uint32_t units_log2, uint32_t* __restrict__ items) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (n << units_log2)) return;
+    const uint32_t u = i / n, j = i - u * n;
+    items[i] = (order ? order[j] : j) | (u << 24);
 }
 
 // Kernel (3) of the north star when used stand-alone: image = make_color(accum * scale).  One pixel per thread:
@@ -1350,6 +1413,12 @@ cudaError_t launch_render_persistent(const RenderLaunch& p, const KernelConfig& 
 cudaError_t launch_tile_keys(const uint32_t* cost, uint32_t stride, uint32_t n, uint32_t mode, uint32_t spp, uint32_t* keys, uint32_t* vals, uint32_t* n_all_miss, cudaStream_t stream) {
     if (n == 0) return cudaSuccess;
     k_tile_keys<<<(n + 255u) / 256u, 256, 0, stream>>>(cost, stride, n, mode, spp, keys, vals, n_all_miss);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unit_items(const uint32_t* order, uint32_t n, uint32_t units_log2, uint32_t* items, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    k_unit_items<<<((n << units_log2) + 255u) / 256u, 256, 0, stream>>>(order, n, units_log2, items);
     return cudaGetLastError();
 }
 

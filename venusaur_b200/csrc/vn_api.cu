@@ -57,6 +57,11 @@ struct vn_context {
     bool copied_valid[2] = {false, false};
     int pipe_flip = 0;
 
+    uint32_t* d_unit_items = nullptr;           // sample-range units of k_render_lean<kGlobal> (kernels.h::RenderLaunch::units_log2): the launch's work items,
+    float4* d_unit_carry = nullptr;             //   the per-pixel hand-over {sum, seed} and
+    uint32_t* d_unit_flag = nullptr;            //   the per-pixel count of finished units (epoch-tagged)
+    size_t unit_tiles_cap = 0;
+    uint32_t unit_epoch = 0;
     float4* d_steal_scratch = nullptr;          // sample stealing in the drain of k_render_lean (kernels.h::RenderLaunch::steal_scratch): lanes x (spp + 1) float4
     uint32_t* d_steal_count = nullptr;          // one counter per lane of the grid, zero between launches
     size_t steal_scratch_cap = 0, steal_count_cap = 0;
@@ -110,6 +115,8 @@ struct vn_context {
                                       // (uniform and cheap); the value caps their share.  Measured on RTIOW 1080p with a fixed fraction of the cost-ordered tiles:
                                       // 0 / 0.10 / 0.15 / 0.18 / 0.25 -> 5.13 / 5.09 / 5.09 / 5.31 / 5.33 ms per launch: beyond the sky (~17 % of the tiles) the second
                                       // launch has a heavy tail of its own; 0 = one launch
+    uint32_t units = 4;               // "units": scenes traversed from L2 / HBM hand a tile's samples out in this many ranges (1, 2, 4, 8 or 16; path_kernels.cu, finish_unit):
+                                      // a pixel of a million-sphere scene is 20 ms of one lane's time, and a launch ends with whole pixels that were started late
     uint32_t steal = 1;               // "steal": once the tile tickets are exhausted, idle lanes of a warp take single samples of the pixels its other lanes still hold
                                       // (k_render_lean's drain, path_kernels.cu::lean_drain); the value = the fewest samples a lane must have left to give one away, 0 = off
     uint32_t steal_smem = 0;          // "steal_smem": also for scenes traversed from shared memory.  Off: measured on RTIOW 1080p the drain shrinks from 0.39 to 0.28 ms
@@ -321,7 +328,7 @@ void vn_destroy(vn_handle c) {
     grid_free(c->grid);
     lbvh_workspace_free(c->bvh_ws);
     free_wavefront(c->wf); c->wf_sample_floats_ = 0;
-    cudaFree(c->d_tile_cost); cudaFree(c->d_tile_sort); cudaFree(c->d_spheres); cudaFree(c->accum_own); cudaFree(c->image_tmp); cudaFree(c->d_counters); cudaFree(c->d_flags); cudaFree(c->d_timeline); cudaFree(c->d_steal_scratch); cudaFree(c->d_steal_count);
+    cudaFree(c->d_tile_cost); cudaFree(c->d_tile_sort); cudaFree(c->d_spheres); cudaFree(c->accum_own); cudaFree(c->image_tmp); cudaFree(c->d_counters); cudaFree(c->d_flags); cudaFree(c->d_timeline); cudaFree(c->d_steal_scratch); cudaFree(c->d_steal_count); cudaFree(c->d_unit_items); cudaFree(c->d_unit_carry); cudaFree(c->d_unit_flag);
     cudaFreeHost(c->h_counters);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (auto& pr : c->ev_slot) for (auto& ev : pr) if (ev) cudaEventDestroy(ev);
@@ -358,6 +365,7 @@ int vn_set_option(vn_handle c, const char* name, double value) {
     else if (k == "tile_guess") { c->tile_guess_opt = value != 0 ? 1u : 0u; }
     else if (k == "wavefront_wide") { c->wavefront_wide = value != 0 ? 1u : 0u; }
     else if (k == "split_tail") { VN_REQUIRE(c, value >= 0 && value <= 0.9, "split_tail must be in [0,0.9]"); c->split_tail = (float)value; }
+    else if (k == "units") { VN_REQUIRE(c, value == 1 || value == 2 || value == 4 || value == 8 || value == 16, "units must be 1, 2, 4, 8 or 16"); c->units = (uint32_t)value; }
     else if (k == "steal_smem") { c->steal_smem = value != 0 ? 1u : 0u; }
     else if (k == "steal") { VN_REQUIRE(c, value >= 0 && value <= 1023, "steal must be in [0,1023]"); c->steal = (uint32_t)value; }
     else if (k == "lean") { c->lean = value != 0 ? 1u : 0u; }
@@ -845,6 +853,37 @@ int vn_render(vn_handle c, const vn_params* p) {
         // never launch more lanes than there is work
         const uint64_t max_blocks = ((uint64_t)L.total_work + cfg.threads - 1) / cfg.threads;
         if ((uint64_t)cfg.blocks > max_blocks) cfg.blocks = (int)std::max<uint64_t>(1, max_blocks);
+        L.units_log2 = 0u; L.carry = nullptr; L.unit_flag = nullptr; L.unit_epoch = 0u;
+        {
+            // sample-range units for the L2 / HBM form of k_render_lean: every tile's samples in 2 or 4 ranges, all first ranges first
+            uint32_t lu = c->units >= 16u ? 4u : (c->units >= 8u ? 3u : (c->units >= 4u ? 2u : (c->units >= 2u ? 1u : 0u)));
+            while (lu > 0u && (p->samples_per_pixel % (1u << lu)) != 0u) lu -= 1u;
+            const uint32_t n_tiles_u = L.total_work / 32u;
+            if (lu > 0u && cfg.lean && !cfg.scene_in_smem && !L.tile_cost && p->width < 16384u && p->height < 16384u && n_tiles_u < (1u << 22) &&
+                n_tiles_u >= (uint32_t)c->num_sms * 8u) {
+                if (n_tiles_u > c->unit_tiles_cap) {
+                    VN_CUDA(c, cudaStreamSynchronize(c->stream));
+                    cudaFree(c->d_unit_items); cudaFree(c->d_unit_carry); cudaFree(c->d_unit_flag);
+                    c->d_unit_items = nullptr; c->d_unit_carry = nullptr; c->d_unit_flag = nullptr; c->unit_tiles_cap = 0;
+                    VN_CUDA(c, cudaMalloc(&c->d_unit_items, (size_t)n_tiles_u * 16 * sizeof(uint32_t)));
+                    VN_CUDA(c, cudaMalloc(&c->d_unit_carry, (size_t)n_tiles_u * 32 * sizeof(float4)));
+                    VN_CUDA(c, cudaMalloc(&c->d_unit_flag, (size_t)n_tiles_u * 32 * sizeof(uint32_t)));
+                    VN_CUDA(c, cudaMemsetAsync(c->d_unit_flag, 0, (size_t)n_tiles_u * 32 * sizeof(uint32_t), c->stream));
+                    c->unit_tiles_cap = n_tiles_u;
+                    c->unit_epoch = 0;
+                }
+                c->unit_epoch += 32u;
+                if (c->unit_epoch > 0x7FFFFF00u) {               // (once in 2^28 launches: start over)
+                    VN_CUDA(c, cudaMemsetAsync(c->d_unit_flag, 0, c->unit_tiles_cap * 32 * sizeof(uint32_t), c->stream));
+                    c->unit_epoch = 32u;
+                }
+                VN_CUDA(c, exact::launch_unit_items(L.tile_order, n_tiles_u, lu, c->d_unit_items, c->stream));
+                L.tile_order = c->d_unit_items;
+                L.total_work = (n_tiles_u << lu) * 32u;
+                L.units_log2 = lu; L.carry = c->d_unit_carry; L.unit_flag = c->d_unit_flag; L.unit_epoch = c->unit_epoch;
+                launches += 1;
+            }
+        }
         L.steal_scratch = nullptr; L.steal_count = nullptr;
         if (cfg.lean && c->steal != 0u && (!cfg.scene_in_smem || c->steal_smem != 0u) && p->samples_per_pixel > 1u && p->samples_per_pixel < 1024u) {
             // scratch slots of the drain's sample stealing: one per lane of the grid (a few tens of MB; 180 GB of HBM)
