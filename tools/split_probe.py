@@ -9,7 +9,7 @@ ctx = vb.Context(0)
 ctx.set_spheres(vb.rtiow_final_scene()); ctx.build_bvh()
 W, H = 1920, 1080
 cam = vb.rtiow_camera(W, H)
-defaults = {"split_tail": 0.5, "tile_guess": 1, "tile_order": 1, "steal_smem": 0, "steal": 1, "async_done": 26, "wide_threads": 1024}
+defaults = {"split_tail": 0.5, "tile_guess": 1, "tile_order": 1, "steal_smem": 0, "steal": 1, "async_done": 26, "wide_threads": 1024, "units": 4}
 for arg in sys.argv[1:] or [""]:
     opts = dict(defaults)
     for kv in arg.split():
