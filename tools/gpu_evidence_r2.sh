@@ -39,6 +39,13 @@ timeout 1500 ncu --set full --clock-control none --import-source on -k regex:k_r
 ncu -i gpurun_out/${P}_prof_$c.ncu-rep --page raw --csv > gpurun_out/${P}_raw_$c.csv 2>/dev/null
 ncu -i gpurun_out/${P}_prof_$c.ncu-rep --page source --csv > gpurun_out/${P}_src_$c.csv 2>/dev/null
 done
+echo "=== throughput over time (instrumented launches)"
+timeout 300 python tools/tail_probe.py profile=1 only=1080 > gpurun_out/${P}_throughput_over_time.txt 2>&1
+timeout 600 python tools/tail_probe.py scene=1m units=1 steal=0 | grep "launch [12]:" > gpurun_out/${P}_drain_1m.txt 2>&1
+timeout 600 python tools/tail_probe.py scene=1m units=1 | grep "launch [12]:" >> gpurun_out/${P}_drain_1m.txt 2>&1
+timeout 600 python tools/tail_probe.py scene=1m | grep "launch [12]:" >> gpurun_out/${P}_drain_1m.txt 2>&1
+VN_DEBUG_SPLIT=1 timeout 300 python tools/split_probe.py "split_tail=0" "split_tail=0.5" > gpurun_out/${P}_split_probe.txt 2>&1
+timeout 300 python tools/guess_probe.py > gpurun_out/${P}_guess_probe.txt 2>&1
 echo "=== drain"
 timeout 200 python tools/tail_probe.py 2>&1 | grep "launch" | tee gpurun_out/${P}_tail_probe.txt
 ls -la gpurun_out/${P}_* | awk '{print $5, $9}'
