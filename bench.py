@@ -560,6 +560,12 @@ def run_ours(args):
             # 0.9 GB) is anchored on HBM with ncu's dram__bytes as `traffic`.  Both kernels are in fact bound by SIMT divergence and latency.
             b_seg = 64.0 * v_node + 32.0 * v_sphere
             out["roofline_issue"] = out["roofline"]
+            sub = prof.get("c4" if n_prims <= 2_000_000 else "c5", {})         # the ncu summary of THIS kernel on this scene (profiles/r02_trace_kernel.json)
+            out["roofline_issue"]["traffic"] = sub.get("dram_bytes_per_launch")
+            out["roofline_issue"]["ncu"] = {"source": prof_file, "note": "copied from the committed ncu summary of the same kernel on the same scene, not measured in this run",
+                                            "thread_inst_per_segment": sub.get("thread_inst_per_segment"), "issue_slot_utilisation": sub.get("issue_slot_utilisation"),
+                                            "avg_active_lanes": sub.get("avg_active_threads_per_inst"), "l2_sector_hit_rate_pct": sub.get("lts__t_sector_hit_rate.pct"),
+                                            "dram_bytes_per_launch": sub.get("dram_bytes_per_launch"), "l2_bytes_from_sms_per_launch": sub.get("l2_bytes_from_sms_per_launch")}
             l2_resident = n_prims <= 2_000_000
             # ncu's L2 peak for reads that come from the SMs: lts__t_sectors_srcunit_tex.peak_sustained = 2 sectors / cycle / slice; the capture in
             # profiles/r02_c4_trace_kernel_ncu.txt reads 78.3 sectors/ns = 10.85 % of it, i.e. a peak of 23.1 TB/s
@@ -567,8 +573,8 @@ def run_ours(args):
             out["roofline"] = {"bound": "l2" if l2_resident else "hbm", "achieved": per_gpu_rate * b_seg / 1e9, "peak": peak_bw, "unit": "GB/s",
                                "frac": per_gpu_rate * b_seg / 1e9 / peak_bw, "traffic": prof.get("c4_l2_bytes_per_launch" if l2_resident else "c5_dram_bytes_per_launch"),
                                "model": "B_seg = 64*V_node + 32*V_sphere = %.0f algorithmic bytes/segment (V_node=%.2f pair visits, V_sphere=%.2f measured in this run); %s"
-                                        % (b_seg, v_node, v_sphere, "served by L2 (ncu: 92-94 %% L2 hits, 61 %% L1 hits); peak = ncu's lts__t_sectors_srcunit_tex peak (2 sectors/cycle/slice = 23.1 TB/s), see profiles/README.md" if l2_resident
-                                           else "served by HBM (ncu: 53 %% L2 hits); peak = measured HBM copy bandwidth")}
+                                        % (b_seg, v_node, v_sphere, "served by L2 (ncu: 83-94 %% L2 hits); `traffic` = ncu's L2 sectors from the SMs x 32 B per launch; peak = ncu's lts__t_sectors_srcunit_tex peak (2 sectors/cycle/slice = 23.1 TB/s), see profiles/README.md" if l2_resident
+                                           else "served by HBM (ncu: 45-53 %% L2 hits); `traffic` = ncu's dram__bytes per launch; peak = measured HBM copy bandwidth")}
         if world == 1 and not args.no_cpu_baseline:
             rate, cores, sample, dt, _ = cpu_reference_rate(args.workload, 160 if scene_name == "rtiow" else 8)
             out["cpu_baseline"] = {"value": rate, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample, "seconds": dt}
