@@ -30,7 +30,8 @@ except Exception as e: print('$f FAILED', e)
 echo "=== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${P}_launches_bench_steps2.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --strong-subframes 0 > gpurun_out/${P}_ncu_launches.log 2>&1
 echo "=== ncu full (headline)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_render_lean -s 4 -c 1 -f -o gpurun_out/${P}_prof python bench.py --steps 2 --warmup 3 --no-cpu-baseline --strong-subframes 0 > gpurun_out/${P}_ncu_full.log 2>&1
+# (one launch per frame for the capture: with split frames every second launch of the kernel is the cheap sky part)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_render_lean -s 4 -c 1 -f -o gpurun_out/${P}_prof python bench.py --steps 2 --warmup 3 --no-cpu-baseline --strong-subframes 0 --opt split_tail=0 > gpurun_out/${P}_ncu_full.log 2>&1
 ncu -i gpurun_out/${P}_prof.ncu-rep --page raw --csv > gpurun_out/${P}_raw.csv 2>/dev/null
 ncu -i gpurun_out/${P}_prof.ncu-rep --page source --csv > gpurun_out/${P}_src.csv 2>/dev/null
 for c in c4 c5; do
