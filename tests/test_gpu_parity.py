@@ -562,6 +562,13 @@ def test_sample_stealing_keeps_the_accumulation_buffer(ctx, oracle_mod, rtiow):
             assert ctx.last_accel() == 1
             res.append((a, i, st.segments, st.paths))
         assert np.array_equal(res[0][0].view(np.uint32), res[1][0].view(np.uint32)) and np.array_equal(res[0][1], res[1][1]) and res[0][2:] == res[1][2:]
+        # the quantised pairs (32-byte nodes, 16-bit planes over the root box: larger boxes, other steps, same hits) against the packed fp32 pairs
+        ctx.set_option("qnodes", 0)
+        ctx.build_bvh()
+        a0, i0, st0 = render(ctx, cam, 96, 54, 16, 1, 64)
+        assert np.array_equal(a0.view(np.uint32), res[1][0].view(np.uint32)) and np.array_equal(i0, res[1][1]) and (st0.segments, st0.paths) == res[1][2:]
+        ctx.set_option("qnodes", 1)
+        ctx.build_bvh()
         # sample-range units ("units": a tile's samples handed out in 2 or 4 ranges, sum and camera seed carried from range to range through
         # memory) with and without the stealing drain, progressive launches of one view (the first one collects the tile costs: whole tiles),
         # spp that 4 does not divide (falls back to 2 ranges), and a row shard

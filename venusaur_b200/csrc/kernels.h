@@ -48,6 +48,8 @@ struct RenderLaunch {
     uint32_t tile_cost_stride;       //   tile_cost[tile] += segments, tile_cost[tile_cost_stride + tile] = max(.., segments)
     uint32_t* timeline;              // instrumented launches of k_render_lean: [0..1024) lanes retired per 8 us bin since the CTA's start, [1024..2048) the ray
                                      // segments of the last pixel those lanes finished (0 outside the cost-collecting launch); null otherwise
+    const uint4* qnodes;             // k_render_lean<kGlobal>: the quantised pairs (lbvh.cu::k_quantize_pairs) or null: one 256-bit load per traversal step
+    float q_lo[3], q_scale[3];       //   plane = q * q_scale + q_lo (the root box and its extent / 65535)
     uint32_t units_log2;             // k_render_lean<kGlobal>: the work items are (tile, unit) with a tile's spp samples cut into 1 << units_log2 sample ranges; the item
                                      //   list in tile_order carries tile | unit << 24 (path_kernels.cu, "sample-range units"); 0 = whole tiles
     float4* carry;                   //   per pixel (tile-major: tile * 32 + position in the tile): {sum so far, camera seed} handed from a unit to the next

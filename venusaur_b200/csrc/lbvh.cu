@@ -414,6 +414,7 @@ inline uint32_t blocks_for(uint64_t n) { return (uint32_t)((n + kBlock - 1) / kB
 void lbvh_free(LbvhScene& sc) {
     cudaFree(sc.arena);
     cudaFree(sc.wide_alloc);
+    cudaFree(sc.qnodes);
     sc = LbvhScene();
 }
 
@@ -673,6 +674,53 @@ int lbvh_refit(const vn_sphere* d_spheres, float pad_rel, float huge_factor, cud
     return 0;
 fail:
     return -2;
+}
+
+// ---- quantised pair nodes.  A pair of the packed hierarchy is 64 bytes -- two 256-bit requests per traversal step, and the traversal of
+// scenes that live in L2 / HBM is bound by the memory system's request rate (anything that ADDS requests loses).  The same
+// pair in 32 bytes: the twelve planes of the two child boxes as 16-bit fixed point over the ROOT box (lo rounded down and hi rounded up, one
+// more quantum of slack each, which covers every rounding of the decode), then the two links.  No per-node origin or exponent: a plane
+// is q * scale + root_lo, so its slab parameter is q * (scale * idir) + (root_lo - o) * idir with both factors formed once per RAY
+// (vn_math.cuh::pair_node_step_q_dev).  One quantum is extent / 65535: 3 mm on the 200-unit scene, 8 mm on the 500-unit one, against sphere
+// radii of 0.1-0.3.  Entry `cur` and `cur + 1` of the uint4 array hold the pair whose packed nodes are `cur` and `cur + 1`.
+__global__ void __launch_bounds__(256) k_quantize_pairs(const float4* __restrict__ nodes, uint32_t num_nodes, uint4* __restrict__ q) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;          // pair index: packed nodes 2p, 2p + 1
+    if (p < 1u || 2u * p + 1u >= num_nodes) return;
+    const float4 rlo = nodes[2], rhi = nodes[3];                           // node 1 = the root: the box everything is quantised over
+    const float lo3[3] = {rlo.x, rlo.y, rlo.z}, hi3[3] = {rhi.x, rhi.y, rhi.z};
+    float inv[3];
+    for (int a = 0; a < 3; a++) { const float e = hi3[a] - lo3[a]; inv[a] = e > 0.0f ? 65535.0f / e : 0.0f; }
+    uint32_t w[8];
+    uint32_t qv[12];
+    for (uint32_t c = 0; c < 2u; c++) {
+        const float4 lo = nodes[2u * (2u * p + c)], hi = nodes[2u * (2u * p + c) + 1u];
+        const float l3[3] = {lo.x, lo.y, lo.z}, h3[3] = {hi.x, hi.y, hi.z};
+        for (int a = 0; a < 3; a++) {
+            const float ql = floorf((l3[a] - lo3[a]) * inv[a]) - 1.0f, qh = ceilf((h3[a] - lo3[a]) * inv[a]) + 1.0f;
+            qv[6u * c + a] = (uint32_t)fminf(fmaxf(ql, 0.0f), 65535.0f);
+            qv[6u * c + 3 + a] = (uint32_t)fminf(fmaxf(qh, 0.0f), 65535.0f);
+        }
+        w[6u + c] = __float_as_uint(lo.w);
+    }
+    for (int k = 0; k < 6; k++) w[k] = qv[2 * k] | (qv[2 * k + 1] << 16);
+    q[2u * p] = make_uint4(w[0], w[1], w[2], w[3]);
+    q[2u * p + 1u] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+int lbvh_quantize(LbvhScene& sc, cudaStream_t stream, uint32_t* launches, std::string& err) {
+    if (!sc.nodes || sc.num_nodes < 4) return 0;
+    if (sc.qnodes_cap < sc.num_nodes) {
+        cudaFree(sc.qnodes); sc.qnodes = nullptr; sc.qnodes_cap = 0;
+        const cudaError_t e = cudaMalloc(&sc.qnodes, sc.num_nodes * sizeof(uint4));
+        if (e != cudaSuccess) { err = std::string("cudaMalloc(quantised nodes): ") + cudaGetErrorString(e); return -2; }
+        sc.qnodes_cap = sc.num_nodes;
+    }
+    const uint32_t pairs = (uint32_t)(sc.num_nodes / 2);
+    k_quantize_pairs<<<(pairs + 255u) / 256u, 256, 0, stream>>>(sc.nodes, (uint32_t)sc.num_nodes, sc.qnodes);
+    if (launches) *launches += 1;
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("k_quantize_pairs: ") + cudaGetErrorString(e); return -2; }
+    return 0;
 }
 
 int radix_sort_pairs_device(uint32_t* k0, uint32_t* v0, uint32_t* k1, uint32_t* v1, uint32_t n, int key_bits, int num_sms,

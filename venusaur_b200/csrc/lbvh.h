@@ -32,7 +32,12 @@ struct LbvhScene {
     uint32_t height = 0;         // levels of internal nodes (the traversal stack must hold that many entries)
     bool sah = false;            // splits chosen by the surface-area heuristic (small scenes) instead of Karras' spatial medians
     float bounds_lo[3] = {0, 0, 0}, bounds_hi[3] = {0, 0, 0};
+    uint4* qnodes = nullptr;     // optional (lbvh_quantize): the pairs again, 32 B each = one 256-bit load: child boxes as 16-bit fixed point over the root box
+    uint64_t qnodes_cap = 0;     //   (uint4 entries allocated)
 };
+
+// Quantised copy of the packed pair nodes for scenes traversed from L2 / HBM (see lbvh.cu::k_quantize_pairs).  0 or a negative status.
+int lbvh_quantize(LbvhScene& sc, cudaStream_t stream, uint32_t* launches, std::string& err);
 
 void lbvh_free(LbvhScene& sc);
 

@@ -728,7 +728,7 @@ __device__ __forceinline__ void lean_finish_traversal(const RenderLaunch& p, con
         while (cur != kEmptyScene) {
             if ((cur & kLeafFlag) == 0u) {
                 if (kCount) cnt.nodes += 1;
-                cur = pair_node_step_dev(sc.nodes, cur, ss.sdir, ss.nsood, tbest, top, tos);
+                cur = p.qnodes ? pair_node_step_q_dev(p.qnodes, cur, ss.sdir, ss.nsood, tbest, top, tos) : pair_node_step_dev(sc.nodes, cur, ss.sdir, ss.nsood, tbest, top, tos);
             } else {
                 const float a = dot(st.d, st.d);
                 leaf_test<kCount>(sc.geom, cur, st.o, st.d, a, rcp(a), tbest, prim, cnt, p.gate != 0u);
@@ -882,8 +882,13 @@ __device__ __forceinline__ void lean_drain(const RenderLaunch& p, const SceneVie
             prim = -1;
             const f3 idir = slab_idir(st.d);
             if (kGlobal) {
-                ss.sdir = idir;
-                ss.nsood = mk3(st.o.x * idir.x, st.o.y * idir.y, st.o.z * idir.z);
+                if (p.qnodes) {                                   // quantised pairs: slab parameter of plane q = q * sdir + nsood
+                    ss.sdir = mk3(p.q_scale[0] * idir.x, p.q_scale[1] * idir.y, p.q_scale[2] * idir.z);
+                    ss.nsood = mk3((p.q_lo[0] - st.o.x) * idir.x, (p.q_lo[1] - st.o.y) * idir.y, (p.q_lo[2] - st.o.z) * idir.z);
+                } else {
+                    ss.sdir = idir;
+                    ss.nsood = mk3(st.o.x * idir.x, st.o.y * idir.y, st.o.z * idir.z);
+                }
                 cur = p.root_link;
             } else {
                 if (p.huge.n) {
@@ -1096,8 +1101,13 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
             prim = -1;
             const f3 idir = slab_idir(st.d);
             if (kGlobal) {
-                ss.sdir = idir;
-                ss.nsood = mk3(st.o.x * idir.x, st.o.y * idir.y, st.o.z * idir.z);
+                if (p.qnodes) {                                   // quantised pairs: slab parameter of plane q = q * sdir + nsood
+                    ss.sdir = mk3(p.q_scale[0] * idir.x, p.q_scale[1] * idir.y, p.q_scale[2] * idir.z);
+                    ss.nsood = mk3((p.q_lo[0] - st.o.x) * idir.x, (p.q_lo[1] - st.o.y) * idir.y, (p.q_lo[2] - st.o.z) * idir.z);
+                } else {
+                    ss.sdir = idir;
+                    ss.nsood = mk3(st.o.x * idir.x, st.o.y * idir.y, st.o.z * idir.z);
+                }
                 cur = p.root_link;
             } else {
                 if (p.huge.n) {
@@ -1131,7 +1141,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
             for (;;) {
                 if ((cur & kLeafBit) == 0u) {
                     if (kCount) cnt.nodes += 1;
-                    cur = pair_node_step_dev(sc.nodes, cur, ss.sdir, ss.nsood, tbest, top, tos);
+                    cur = p.qnodes ? pair_node_step_q_dev(p.qnodes, cur, ss.sdir, ss.nsood, tbest, top, tos) : pair_node_step_dev(sc.nodes, cur, ss.sdir, ss.nsood, tbest, top, tos);
                 }
                 const bool at_leaf = (cur & kLeafBit) != 0u && cur != kDone;
                 const unsigned lm = __ballot_sync(kFull, at_leaf);

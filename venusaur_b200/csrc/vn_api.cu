@@ -115,6 +115,8 @@ struct vn_context {
                                       // (uniform and cheap); the value caps their share.  Measured on RTIOW 1080p with a fixed fraction of the cost-ordered tiles:
                                       // 0 / 0.10 / 0.15 / 0.18 / 0.25 -> 5.13 / 5.09 / 5.09 / 5.31 / 5.33 ms per launch: beyond the sky (~17 % of the tiles) the second
                                       // launch has a heavy tail of its own; 0 = one launch
+    uint32_t qnodes_opt = 1;          // "qnodes": scenes traversed from L2 / HBM are traversed through the quantised pairs (32 bytes = one 256-bit request per step
+                                      // instead of two; 16-bit planes over the root box); 0 = the packed fp32 pairs
     uint32_t units = 4;               // "units": scenes traversed from L2 / HBM hand a tile's samples out in this many ranges (1, 2, 4, 8 or 16; path_kernels.cu, finish_unit):
                                       // a pixel of a million-sphere scene is 20 ms of one lane's time, and a launch ends with whole pixels that were started late
     uint32_t steal = 1;               // "steal": once the tile tickets are exhausted, idle lanes of a warp take single samples of the pixels its other lanes still hold
@@ -221,6 +223,16 @@ int fill_launch(vn_context* c, const vn_params* p, RenderLaunch& L) {
     L.async_done = c->async_done; L.async_node = c->async_node; L.async_leaf = c->async_leaf;
     L.grid_vote = c->grid_vote;
     L.steal = c->steal;
+    L.qnodes = nullptr;
+    for (int a = 0; a < 3; a++) { L.q_lo[a] = 0.0f; L.q_scale[a] = 0.0f; }
+    if (c->qnodes_opt && c->scene.qnodes && !scene_fits_smem(c)) {
+        L.qnodes = c->scene.qnodes;
+        for (int a = 0; a < 3; a++) {
+            const float e = c->scene.bounds_hi[a] - c->scene.bounds_lo[a];
+            L.q_lo[a] = c->scene.bounds_lo[a];
+            L.q_scale[a] = e > 0.0f ? e / 65535.0f : 0.0f;
+        }
+    }
     L.timeline = nullptr;
     L.gate = (c->hit_gate == 2u || (c->hit_gate == 1u && !scene_fits_smem(c))) ? 1u : 0u;
     L.grid = c->grid.h; L.grid_start = c->grid.start; L.grid_refs = c->grid.refs;
@@ -365,6 +377,7 @@ int vn_set_option(vn_handle c, const char* name, double value) {
     else if (k == "tile_guess") { c->tile_guess_opt = value != 0 ? 1u : 0u; }
     else if (k == "wavefront_wide") { c->wavefront_wide = value != 0 ? 1u : 0u; }
     else if (k == "split_tail") { VN_REQUIRE(c, value >= 0 && value <= 0.9, "split_tail must be in [0,0.9]"); c->split_tail = (float)value; }
+    else if (k == "qnodes") { c->qnodes_opt = value != 0 ? 1u : 0u; c->bvh_valid = false; }
     else if (k == "units") { VN_REQUIRE(c, value == 1 || value == 2 || value == 4 || value == 8 || value == 16, "units must be 1, 2, 4, 8 or 16"); c->units = (uint32_t)value; }
     else if (k == "steal_smem") { c->steal_smem = value != 0 ? 1u : 0u; }
     else if (k == "steal") { VN_REQUIRE(c, value >= 0 && value <= 1023, "steal must be in [0,1023]"); c->steal = (uint32_t)value; }
@@ -428,6 +441,9 @@ int vn_build_bvh(vn_handle c) {
         }
     }
     if (rc != 0) return fail(c, rc == -1 ? VN_ERR_INVALID : VN_ERR_CUDA, "vn_build_bvh: " + err);
+    if (c->qnodes_opt && !scene_fits_smem(c)) {       // scenes traversed from L2 / HBM: the pairs again in 32 bytes each (lbvh.cu::k_quantize_pairs)
+        if (lbvh_quantize(c->scene, c->stream, &launches, err) < 0) return fail(c, VN_ERR_CUDA, "vn_build_bvh: " + err);
+    }
     if (c->accel != 1u && c->scene.geom) {
         const int grc = grid_build(c->scene.geom, c->scene.n, c->grid_max_per_cell, c->stream, c->grid, &launches, err);
         if (grc < 0) return fail(c, VN_ERR_CUDA, "vn_build_bvh: " + err);
@@ -457,6 +473,9 @@ int vn_update_spheres(vn_handle c, const vn_sphere* host_spheres, uint64_t n) {
     const int rc = lbvh_refit(c->d_spheres, c->aabb_pad, c->huge_factor, c->stream, c->scene, c->bvh_ws, &launches, err);
     if (rc < 0) return fail(c, VN_ERR_CUDA, "vn_update_spheres: " + err);
     if (rc == 1 || c->grid.valid) return vn_build_bvh(c);
+    if (c->qnodes_opt && !scene_fits_smem(c)) {
+        if (lbvh_quantize(c->scene, c->stream, &launches, err) < 0) return fail(c, VN_ERR_CUDA, "vn_update_spheres: " + err);
+    }
     VN_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
     VN_CUDA(c, cudaStreamSynchronize(c->stream));
     VN_CUDA(c, cudaEventElapsedTime(&c->stats.ms_build, c->ev[0], c->ev[1]));

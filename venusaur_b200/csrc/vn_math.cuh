@@ -847,6 +847,48 @@ __device__ __forceinline__ uint32_t pair_node_step_dev(const node_f4* __restrict
         : "memory");
     return next;
 }
+// The same step over the QUANTISED pair (lbvh.cu::k_quantize_pairs): one 256-bit load instead of two.  A plane is q * scale + root_lo, so its
+// slab parameter is q * qa + qb with qa = scale * idir and qb = (root_lo - o) * idir, formed once per ray.  The boxes only got larger (one
+// quantum of slack beyond the outward rounding covers the decode's own rounding), so the traversal stays conservative and the closest hit is
+// the one closest_hit() finds; the ORDER of the two children can differ where their entry distances are within a quantum, which changes
+// the steps a ray takes, not what it hits.
+__device__ __forceinline__ uint32_t pair_node_step_q_dev(const uint4* __restrict__ q, uint32_t cur, f3 qa, f3 qb, float tbest, uint32_t& top, uint32_t& tos) {
+    uint32_t w0, w1, w2, w3, w4, w5, ll, lr;
+    asm volatile("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3), "=r"(w4), "=r"(w5), "=r"(ll), "=r"(lr) : "l"(q + cur));
+    // left: lo = (w0.lo, w0.hi, w1.lo), hi = (w1.hi, w2.lo, w2.hi); right: lo = (w3.lo, w3.hi, w4.lo), hi = (w4.hi, w5.lo, w5.hi)
+    const float l0x = fmaf((float)(w0 & 0xFFFFu), qa.x, qb.x), l0y = fmaf((float)(w0 >> 16), qa.y, qb.y), l0z = fmaf((float)(w1 & 0xFFFFu), qa.z, qb.z);
+    const float l1x = fmaf((float)(w1 >> 16), qa.x, qb.x), l1y = fmaf((float)(w2 & 0xFFFFu), qa.y, qb.y), l1z = fmaf((float)(w2 >> 16), qa.z, qb.z);
+    const float r0x = fmaf((float)(w3 & 0xFFFFu), qa.x, qb.x), r0y = fmaf((float)(w3 >> 16), qa.y, qb.y), r0z = fmaf((float)(w4 & 0xFFFFu), qa.z, qb.z);
+    const float r1x = fmaf((float)(w4 >> 16), qa.x, qb.x), r1y = fmaf((float)(w5 & 0xFFFFu), qa.y, qb.y), r1z = fmaf((float)(w5 >> 16), qa.z, qb.z);
+    const float tl = fmaxf(fmaxf(fminf(l0x, l1x), fminf(l0y, l1y)), fmaxf(fminf(l0z, l1z), 0.0f));
+    const float fl = fminf(fminf(fmaxf(l0x, l1x), fmaxf(l0y, l1y)), fminf(fmaxf(l0z, l1z), tbest));
+    const float tr = fmaxf(fmaxf(fminf(r0x, r1x), fminf(r0y, r1y)), fmaxf(fminf(r0z, r1z), 0.0f));
+    const float fr = fminf(fminf(fmaxf(r0x, r1x), fmaxf(r0y, r1y)), fminf(fmaxf(r0z, r1z), tbest));
+    const bool hl = tl <= fl, hr = tr <= fr;
+    const bool left_first = tl <= tr;
+    const uint32_t near = (hl && (!hr || left_first)) ? ll : lr;
+    const uint32_t far = left_first ? lr : ll;
+    uint32_t next = near;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred both, none;\n\t"
+        ".reg .u32 n;\n\t"
+        "setp.ne.u32 both, %4, 0;\n\t"
+        "setp.ne.u32 none, %5, 0;\n\t"
+        "@both st.local.u32 [%1], %2;\n\t"
+        "selp.u32 %2, %3, %2, both;\n\t"
+        "selp.u32 n, 4, 0, both;\n\t"
+        "add.u32 %1, %1, n;\n\t"
+        "@none mov.u32 %0, %2;\n\t"
+        "@none ld.local.u32 %2, [%1+-4];\n\t"
+        "@none add.u32 %1, %1, -4;\n\t"
+        "}"
+        : "+r"(next), "+r"(top), "+r"(tos)
+        : "r"(far), "r"((uint32_t)(hl && hr)), "r"((uint32_t)(!hl && !hr))
+        : "memory");
+    return next;
+}
 __device__ __forceinline__ uint32_t stack_pop32_dev(uint32_t& top, uint32_t& tos) {
     const uint32_t next = tos;
     asm volatile(
