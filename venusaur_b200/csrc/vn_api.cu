@@ -126,8 +126,9 @@ struct vn_context {
                                       // from L2 / HBM gain 9 % (1 M spheres) and 4 % (16 M spheres)
     uint32_t warp_tiles = 1;          // "warp_tiles": k_render_async phase form hands whole tiles to warps (see path_kernels.cu); 0 = lanes take single pixels
     uint32_t async_done = 26;         // k_render_async: a traversal burst ends when this many lanes hold a finished ray (0 = k_render_persistent)
-    int global_ctas = 5;              // "global_ctas": 4, 5 or 6 CTAs of 256 threads per SM for the L2 / HBM form (64 / 48 / 40 registers: more warps to hide latency,
-                                      // a few spills each; measured 4 / 5 / 6: 1 M spheres 3046 / 3037 / 2961, 16 M spheres 1726 / 1765 / 1779 Mrays/s)
+    int global_ctas = 6;              // "global_ctas": 4, 5 or 6 CTAs of 256 threads per SM for the L2 / HBM form (64 / 48 / 40 registers: more warps to hide latency,
+                                      // a few spills each).  With the fp32 pairs 4 / 5 / 6 measured 3046 / 3037 / 2961 (1 M spheres) and 1726 / 1765 / 1779 (16 M); with the
+                                      // quantised pairs the traversal is less bound by the memory system and more by latency: 3581 / 3886 / 3945 and - / 2225 / 2304 (8: 3372 / 1949)
     uint32_t global_done = 16;        // the same threshold for scenes traversed from L2 / HBM (k_render_lean<kGlobal>): long traversals, so shade earlier (measured:
                                       // 1 M spheres 2.21 -> 2.49 Grays/s, 16 M spheres 1.11 -> 1.60 against 26)
     uint32_t async_node = 0, async_leaf = 8;   // async_node 0 = phase form (no votes inside the node / leaf phases), the default
