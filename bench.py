@@ -572,7 +572,7 @@ def run_ours(args):
             peak_bw = 23100.0 if l2_resident else hbm_peak
             out["roofline"] = {"bound": "l2" if l2_resident else "hbm", "achieved": per_gpu_rate * b_seg / 1e9, "peak": peak_bw, "unit": "GB/s",
                                "frac": per_gpu_rate * b_seg / 1e9 / peak_bw, "traffic": prof.get("c4_l2_bytes_per_launch" if l2_resident else "c5_dram_bytes_per_launch"),
-                               "model": "B_seg = 64*V_node + 32*V_sphere = %.0f algorithmic bytes/segment (V_node=%.2f pair visits, V_sphere=%.2f measured in this run); %s"
+                               "model": "B_seg = 64*V_node + 32*V_sphere = %.0f algorithmic bytes/segment (SURVEY 8d's packed 32-byte nodes; the shipped kernel fetches 32-byte QUANTISED pairs, i.e. half the node bytes) (V_node=%.2f pair visits, V_sphere=%.2f measured in this run); %s"
                                         % (b_seg, v_node, v_sphere, "served by L2 (ncu: 83-94 %% L2 hits); `traffic` = ncu's L2 sectors from the SMs x 32 B per launch; peak = ncu's lts__t_sectors_srcunit_tex peak (2 sectors/cycle/slice = 23.1 TB/s), see profiles/README.md" if l2_resident
                                            else "served by HBM (ncu: 45-53 %% L2 hits); `traffic` = ncu's dram__bytes per launch; peak = measured HBM copy bandwidth")}
         if world == 1 and not args.no_cpu_baseline:
