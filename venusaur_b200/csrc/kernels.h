@@ -52,8 +52,8 @@ struct RenderLaunch {
     float q_lo[3], q_scale[3];       //   plane = q * q_scale + q_lo (the root box and its extent / 65535)
     uint32_t units_log2;             // k_render_lean<kGlobal>: the work items are (tile, unit) with a tile's spp samples cut into 1 << units_log2 sample ranges; the item
                                      //   list in tile_order carries tile | unit << 24 (path_kernels.cu, "sample-range units"); 0 = whole tiles
-    float4* carry;                   //   per pixel (tile-major: tile * 32 + position in the tile): {sum so far, camera seed} handed from a unit to the next
-    uint32_t* unit_flag;             //   per pixel: unit_epoch + number of finished units of this launch
+    float4* carry;                   //   per pixel (tile-major: tile * 32 + position in the tile) 2 x float4, written by ONE 32-byte store: {sum so far, -} {camera seed,
+                                     //   unit_epoch + finished units of this launch, -, -}: what a unit hands to the next, and the tag that says it is there
     uint32_t unit_epoch;             //   (a multiple of 32 that grows with every launch: no memset between launches)
     uint32_t steal;                  // k_render_lean: >= 1 = sample stealing inside a warp during the drain (path_kernels.cu): the fewest samples a lane must have left to give one away
     float4* steal_scratch;           //   one slot of spp + 1 float4 per lane of the grid: [0] the owner's prefix sum (.w = first sample of the suffix), [1 + k] sample k's radiance

@@ -58,8 +58,7 @@ struct vn_context {
     int pipe_flip = 0;
 
     uint32_t* d_unit_items = nullptr;           // sample-range units of k_render_lean<kGlobal> (kernels.h::RenderLaunch::units_log2): the launch's work items,
-    float4* d_unit_carry = nullptr;             //   the per-pixel hand-over {sum, seed} and
-    uint32_t* d_unit_flag = nullptr;            //   the per-pixel count of finished units (epoch-tagged)
+    float4* d_unit_carry = nullptr;             //   and the per-pixel hand-over: 32 bytes {sum, -, seed, unit_epoch + finished units, -, -}
     size_t unit_tiles_cap = 0;
     uint32_t unit_epoch = 0;
     float4* d_steal_scratch = nullptr;          // sample stealing in the drain of k_render_lean (kernels.h::RenderLaunch::steal_scratch): lanes x (spp + 1) float4
@@ -341,7 +340,7 @@ void vn_destroy(vn_handle c) {
     grid_free(c->grid);
     lbvh_workspace_free(c->bvh_ws);
     free_wavefront(c->wf); c->wf_sample_floats_ = 0;
-    cudaFree(c->d_tile_cost); cudaFree(c->d_tile_sort); cudaFree(c->d_spheres); cudaFree(c->accum_own); cudaFree(c->image_tmp); cudaFree(c->d_counters); cudaFree(c->d_flags); cudaFree(c->d_timeline); cudaFree(c->d_steal_scratch); cudaFree(c->d_steal_count); cudaFree(c->d_unit_items); cudaFree(c->d_unit_carry); cudaFree(c->d_unit_flag);
+    cudaFree(c->d_tile_cost); cudaFree(c->d_tile_sort); cudaFree(c->d_spheres); cudaFree(c->accum_own); cudaFree(c->image_tmp); cudaFree(c->d_counters); cudaFree(c->d_flags); cudaFree(c->d_timeline); cudaFree(c->d_steal_scratch); cudaFree(c->d_steal_count); cudaFree(c->d_unit_items); cudaFree(c->d_unit_carry);
     cudaFreeHost(c->h_counters);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (auto& pr : c->ev_slot) for (auto& ev : pr) if (ev) cudaEventDestroy(ev);
@@ -873,7 +872,7 @@ int vn_render(vn_handle c, const vn_params* p) {
         // never launch more lanes than there is work
         const uint64_t max_blocks = ((uint64_t)L.total_work + cfg.threads - 1) / cfg.threads;
         if ((uint64_t)cfg.blocks > max_blocks) cfg.blocks = (int)std::max<uint64_t>(1, max_blocks);
-        L.units_log2 = 0u; L.carry = nullptr; L.unit_flag = nullptr; L.unit_epoch = 0u;
+        L.units_log2 = 0u; L.carry = nullptr; L.unit_epoch = 0u;
         {
             // sample-range units for the L2 / HBM form of k_render_lean: every tile's samples in 2 or 4 ranges, all first ranges first
             uint32_t lu = c->units >= 16u ? 4u : (c->units >= 8u ? 3u : (c->units >= 4u ? 2u : (c->units >= 2u ? 1u : 0u)));
@@ -883,24 +882,23 @@ int vn_render(vn_handle c, const vn_params* p) {
                 n_tiles_u >= (uint32_t)c->num_sms * 8u) {
                 if (n_tiles_u > c->unit_tiles_cap) {
                     VN_CUDA(c, cudaStreamSynchronize(c->stream));
-                    cudaFree(c->d_unit_items); cudaFree(c->d_unit_carry); cudaFree(c->d_unit_flag);
-                    c->d_unit_items = nullptr; c->d_unit_carry = nullptr; c->d_unit_flag = nullptr; c->unit_tiles_cap = 0;
+                    cudaFree(c->d_unit_items); cudaFree(c->d_unit_carry);
+                    c->d_unit_items = nullptr; c->d_unit_carry = nullptr; c->unit_tiles_cap = 0;
                     VN_CUDA(c, cudaMalloc(&c->d_unit_items, (size_t)n_tiles_u * 16 * sizeof(uint32_t)));
-                    VN_CUDA(c, cudaMalloc(&c->d_unit_carry, (size_t)n_tiles_u * 32 * sizeof(float4)));
-                    VN_CUDA(c, cudaMalloc(&c->d_unit_flag, (size_t)n_tiles_u * 32 * sizeof(uint32_t)));
-                    VN_CUDA(c, cudaMemsetAsync(c->d_unit_flag, 0, (size_t)n_tiles_u * 32 * sizeof(uint32_t), c->stream));
+                    VN_CUDA(c, cudaMalloc(&c->d_unit_carry, (size_t)n_tiles_u * 32 * 2 * sizeof(float4)));
+                    VN_CUDA(c, cudaMemsetAsync(c->d_unit_carry, 0, (size_t)n_tiles_u * 32 * 2 * sizeof(float4), c->stream));
                     c->unit_tiles_cap = n_tiles_u;
                     c->unit_epoch = 0;
                 }
                 c->unit_epoch += 32u;
                 if (c->unit_epoch > 0x7FFFFF00u) {               // (once in 2^28 launches: start over)
-                    VN_CUDA(c, cudaMemsetAsync(c->d_unit_flag, 0, c->unit_tiles_cap * 32 * sizeof(uint32_t), c->stream));
+                    VN_CUDA(c, cudaMemsetAsync(c->d_unit_carry, 0, c->unit_tiles_cap * 32 * 2 * sizeof(float4), c->stream));
                     c->unit_epoch = 32u;
                 }
                 VN_CUDA(c, exact::launch_unit_items(L.tile_order, n_tiles_u, lu, c->d_unit_items, c->stream));
                 L.tile_order = c->d_unit_items;
                 L.total_work = (n_tiles_u << lu) * 32u;
-                L.units_log2 = lu; L.carry = c->d_unit_carry; L.unit_flag = c->d_unit_flag; L.unit_epoch = c->unit_epoch;
+                L.units_log2 = lu; L.carry = c->d_unit_carry; L.unit_epoch = c->unit_epoch;
                 launches += 1;
             }
         }
