@@ -572,7 +572,8 @@ def test_sample_stealing_keeps_the_accumulation_buffer(ctx, oracle_mod, rtiow):
         # sample-range units ("units": a tile's samples handed out in 2 or 4 ranges, sum and camera seed carried from range to range through
         # memory) with and without the stealing drain, progressive launches of one view (the first one collects the tile costs: whole tiles),
         # spp that 4 does not divide (falls back to 2 ranges), and a row shard
-        W, H = 352, 180                                           # 1980 tiles > 8 per SM: units are active
+        W, H = 352, 180                                           # 1980 tiles > 8 per SM: units are active ...
+        ctx.set_option("units_min_seg", 0)                        # ... whatever the view's mean path length (the default asks for >= 13 segments)
         cam = vb.Camera((0.0, 0.0, 120.0), 40.0, W / H, 0.0, 120.0)
         cam.SetForward((0.0, 0.0, -1.0))
         ref = None
@@ -592,7 +593,40 @@ def test_sample_stealing_keeps_the_accumulation_buffer(ctx, oracle_mod, rtiow):
     finally:
         ctx.set_option("steal", 1)
         ctx.set_option("units", 4)
+        ctx.set_option("units_min_seg", 13)
         ctx.set_option("steal_smem", 0)
+
+
+@pytest.mark.timeout(120)
+def test_units_make_progress_on_cheap_pixels(ctx):
+    """Regression: 2 000 random spheres at 1080p, traversed from L2, sample-range units forced on.  Most pixels are cheap and a few bounce for
+    long, so warps often hold a ticket whose tile still waits for one pixel of the unit before.  The lanes of such a warp used to restart
+    traversals of a stale ray, which starved the warp's lanes waiting at a leaf: the launch never ended (within 20 launches with the
+    stealing drain, within 100 without).  Progressive launches of one view, as tools/stress_probe.py does; and the picture of the last launch
+    is the one whole pixels give."""
+    n, W, H = 2000, 1920, 1080
+    S = 10.0 * (n / 500.0) ** (1.0 / 3.0)
+    ctx.set_spheres(vb.random_scene(n, 0x5EED0100 + n, S, 0))
+    ctx.build_bvh()
+    assert ctx.bvh_info().scene_in_smem == 0
+    cam = vb.Camera((0.0, 0.0, 2.0 * S), 40.0, W / H, 0.0, 2.0 * S)
+    cam.SetForward((0.0, 0.0, -1.0))
+    try:
+        ctx.set_option("units_min_seg", 0)
+        outs = []
+        for units, steal, launches in ((4, 1, 60), (4, 0, 120), (1, 1, 3)):
+            ctx.set_option("units", units)
+            ctx.set_option("steal", steal)
+            for rep in range(launches):
+                ctx.render(ctx.make_params(cam, W, H, 16, 1 + rep % 50, 50, accum_count=rep % 50, flags=VN_NO_TONEMAP))
+            a, _, st = render(ctx, cam, W, H, 16, 7, 50)
+            outs.append((a.copy(), st.segments, st.paths))
+        for a, sg, pt in outs[:2]:
+            assert np.array_equal(a.view(np.uint32), outs[2][0].view(np.uint32)) and (sg, pt) == outs[2][1:]
+    finally:
+        ctx.set_option("steal", 1)
+        ctx.set_option("units", 4)
+        ctx.set_option("units_min_seg", 13)
 
 
 def test_split_frames_keep_the_accumulation_buffer(ctx, oracle_mod, rtiow):

@@ -1202,6 +1202,11 @@ __global__ void __launch_bounds__(256) k_tile_keys(const uint32_t* __restrict__ 
     const bool all_miss = i < n && cost[stride + i] <= spp;
     const unsigned m = __ballot_sync(0xFFFFFFFFu, all_miss);
     if ((threadIdx.x & 31u) == 0u && m) atomicAdd(n_all_miss, (uint32_t)__popc(m));
+    // ... and n_all_miss[2..3] (a 64-bit word) adds the costs up: ray segments of the collecting launch, the view's mean path length for the host
+    {
+        const uint32_t w_sum = __reduce_add_sync(0xFFFFFFFFu, i < n ? cost[i] : 0u);
+        if ((threadIdx.x & 31u) == 0u && w_sum) atomicAdd(reinterpret_cast<unsigned long long*>(n_all_miss + 2), (unsigned long long)w_sum);
+    }
     if (i >= n) return;
     const uint32_t sum = cost[i], mx = cost[stride + i];
     uint32_t c = mode == 2u ? mx : (mode == 3u ? max(sum >> 3, mx) : sum);

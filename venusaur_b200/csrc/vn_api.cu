@@ -100,6 +100,7 @@ struct vn_context {
     bool tile_guess = false;          // the collecting launch of the current view may use the previous view's order
     uint32_t tile_guess_opt = 1;      // "tile_guess": 1 = after a camera / scene change the collecting launch hands the tiles out in the previous view's order (0: row-major).
                                       // (Scattered tickets -- t * golden-ratio mod n -- were tried for views without a predecessor: 6.06-6.26 instead of 5.79 ms, expensive tiles then start at random times up to the end)
+    double tile_seg_per_path = 0.0;   // ray segments per path of the current view's cost-collecting launch (0: not measured)
     uint32_t tile_all_miss = 0;       // tiles of the current view in which no path hit anything while the costs were collected: the tail of d_tile_order
     int tile_state = 0;               // 0: nothing known (the next launch collects costs), 1: costs collected (sort before the next launch), 2: order valid
     struct TileSig { uint32_t w, h, r0, r1, spp, depth; float cam[13]; uint32_t pad_; uint64_t epoch; } tile_sig{};   // no implicit padding
@@ -118,6 +119,12 @@ struct vn_context {
                                       // instead of two; 16-bit planes over the root box); 0 = the packed fp32 pairs
     uint32_t units = 4;               // "units": scenes traversed from L2 / HBM hand a tile's samples out in this many ranges (1, 2, 4, 8 or 16; path_kernels.cu, finish_unit):
                                       // a pixel of a million-sphere scene is 20 ms of one lane's time, and a launch ends with whole pixels that were started late
+    double units_min_seg = 13.0;      // "units_min_seg": ... but only for views whose paths are at least this many ray segments long on average (measured by the view's
+                                      // cost-collecting launch).  Units chain a pixel's ranges one behind the other; where most pixels are cheap and a few bounce 50
+                                      // times those chains ARE the end of the launch, and whole pixels + the stealing drain do better.  Random scenes at 1080p,
+                                      // ms per launch with 1 / 4 units (tools/units_probe.py): 2 k spheres, 1.6 segments per path: 8.5 / 13.1; 8 k, 2.9: 21.8 / 27.9;
+                                      // 30 k, 6.9: 48.6 / 51.9; 100 k, 11.4: 83.6 / 84.2; 300 k, 15.4: 122.2 / 115.1; 1 M, 18.4: 169.1 / 156.5.
+                                      // 0 = units whatever the view (and without a measurement)
     uint32_t steal = 1;               // "steal": once the tile tickets are exhausted, idle lanes of a warp take single samples of the pixels its other lanes still hold
                                       // (k_render_lean's drain, path_kernels.cu::lean_drain); the value = the fewest samples a lane must have left to give one away, 0 = off
     uint32_t steal_smem = 0;          // "steal_smem": also for scenes traversed from shared memory.  Off: measured on RTIOW 1080p the drain shrinks from 0.39 to 0.28 ms
@@ -378,6 +385,7 @@ int vn_set_option(vn_handle c, const char* name, double value) {
     else if (k == "wavefront_wide") { c->wavefront_wide = value != 0 ? 1u : 0u; }
     else if (k == "split_tail") { VN_REQUIRE(c, value >= 0 && value <= 0.9, "split_tail must be in [0,0.9]"); c->split_tail = (float)value; }
     else if (k == "qnodes") { c->qnodes_opt = value != 0 ? 1u : 0u; c->bvh_valid = false; }
+    else if (k == "units_min_seg") { VN_REQUIRE(c, value >= 0, "units_min_seg must be >= 0"); c->units_min_seg = value; }
     else if (k == "units") { VN_REQUIRE(c, value == 1 || value == 2 || value == 4 || value == 8 || value == 16, "units must be 1, 2, 4, 8 or 16"); c->units = (uint32_t)value; }
     else if (k == "steal_smem") { c->steal_smem = value != 0 ? 1u : 0u; }
     else if (k == "steal") { VN_REQUIRE(c, value >= 0 && value <= 1023, "steal must be in [0,1023]"); c->steal = (uint32_t)value; }
@@ -758,6 +766,7 @@ static int prepare_tile_order(vn_handle c, const vn_params* p, RenderLaunch& L) 
         const bool same_frame = c->tile_state == 2 && sig.w == c->tile_sig.w && sig.h == c->tile_sig.h && sig.r0 == c->tile_sig.r0 && sig.r1 == c->tile_sig.r1;
         memcpy(&c->tile_sig, &sig, sizeof sig);
         c->tile_state = 0;
+        c->tile_seg_per_path = 0.0;
         c->tile_guess = same_frame && c->tile_guess_opt;
     }
     if (c->tile_state == 0) {
@@ -774,7 +783,7 @@ static int prepare_tile_order(vn_handle c, const vn_params* p, RenderLaunch& L) 
     if (c->tile_state == 1) {
         uint32_t *k0 = c->d_tile_sort, *v0 = k0 + c->tile_cap, *k1 = v0 + c->tile_cap, *v1 = k1 + c->tile_cap;
         uint32_t* d_all_miss = reinterpret_cast<uint32_t*>(c->d_counters + 6);     // (a free word of the counter block; the launch's memset comes later)
-        VN_CUDA(c, cudaMemsetAsync(d_all_miss, 0, 4, c->stream));
+        VN_CUDA(c, cudaMemsetAsync(d_all_miss, 0, 16, c->stream));
         VN_CUDA(c, exact::launch_tile_keys(c->d_tile_cost, c->tile_cap, n_tiles, c->tile_order_opt, p->samples_per_pixel, k0, v0, d_all_miss, c->stream));
         std::string err;
         uint32_t launches = 0;
@@ -782,8 +791,12 @@ static int prepare_tile_order(vn_handle c, const vn_params* p, RenderLaunch& L) 
         if (which < 0) return fail(c, VN_ERR_CUDA, "vn_render: tile order sort failed: " + err);
         c->d_tile_order = which ? v1 : v0;
         // once per view: how many tiles saw nothing but sky in the collecting launch (they are the end of the order)
-        VN_CUDA(c, cudaMemcpyAsync(&c->tile_all_miss, d_all_miss, 4, cudaMemcpyDeviceToHost, c->stream));
+        // ... and how long its paths are (sample-range units pay when every pixel is expensive, see vn_render)
+        unsigned long long back[2] = {0ull, 0ull};
+        VN_CUDA(c, cudaMemcpyAsync(back, d_all_miss, 16, cudaMemcpyDeviceToHost, c->stream));
         VN_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->tile_all_miss = (uint32_t)(back[0] & 0xFFFFFFFFull);
+        c->tile_seg_per_path = (double)back[1] / ((double)p->width * (double)(L.row_end - L.row_begin) * (double)p->samples_per_pixel);
         c->tile_state = 2;
     }
     L.tile_order = c->d_tile_order;
@@ -878,6 +891,7 @@ int vn_render(vn_handle c, const vn_params* p) {
             uint32_t lu = c->units >= 16u ? 4u : (c->units >= 8u ? 3u : (c->units >= 4u ? 2u : (c->units >= 2u ? 1u : 0u)));
             while (lu > 0u && (p->samples_per_pixel % (1u << lu)) != 0u) lu -= 1u;
             const uint32_t n_tiles_u = L.total_work / 32u;
+            if (c->units_min_seg > 0.0 && !(c->tile_state == 2 && c->tile_seg_per_path >= c->units_min_seg)) lu = 0u;
             if (lu > 0u && cfg.lean && !cfg.scene_in_smem && !L.tile_cost && p->width < 16384u && p->height < 16384u && n_tiles_u < (1u << 22) &&
                 n_tiles_u >= (uint32_t)c->num_sms * 8u) {
                 if (n_tiles_u > c->unit_tiles_cap) {
