@@ -558,7 +558,11 @@ def run_ours(args):
             # configs[3] (1 M spheres, 57 MB of nodes + spheres) is L2-resident: ncu measures 92-94 % L2 hits and < 10 GB/s of DRAM traffic, so its
             # roofline is anchored on L2 bandwidth, with the ncu-measured L2 -> L1 throughput as the peak; configs[4] (16 M spheres,
             # 0.9 GB) is anchored on HBM with ncu's dram__bytes as `traffic`.  Both kernels are in fact bound by SIMT divergence and latency.
-            b_seg = 64.0 * v_node + 32.0 * v_sphere
+            # The shipped kernel steps through QUANTISED pairs (option "qnodes", the default): one 32-byte record per pair visit, so the
+            # algorithm's bytes are 32 per pair visit; with SURVEY 8(d)'s two packed 32-byte nodes per visit (qnodes=0) it is 64.
+            quantised = float(dict(kv.split("=", 1) for kv in args.opt if "=" in kv).get("qnodes", 1)) != 0.0
+            node_bytes = 32.0 if quantised else 64.0
+            b_seg = node_bytes * v_node + 32.0 * v_sphere
             out["roofline_issue"] = out["roofline"]
             sub = prof.get("c4" if n_prims <= 2_000_000 else "c5", {})         # the ncu summary of THIS kernel on this scene (profiles/r02_trace_kernel.json)
             out["roofline_issue"]["traffic"] = sub.get("dram_bytes_per_launch")
@@ -572,8 +576,8 @@ def run_ours(args):
             peak_bw = 23100.0 if l2_resident else hbm_peak
             out["roofline"] = {"bound": "l2" if l2_resident else "hbm", "achieved": per_gpu_rate * b_seg / 1e9, "peak": peak_bw, "unit": "GB/s",
                                "frac": per_gpu_rate * b_seg / 1e9 / peak_bw, "traffic": prof.get("c4_l2_bytes_per_launch" if l2_resident else "c5_dram_bytes_per_launch"),
-                               "model": "B_seg = 64*V_node + 32*V_sphere = %.0f algorithmic bytes/segment (SURVEY 8d's packed 32-byte nodes; the shipped kernel fetches 32-byte QUANTISED pairs, i.e. half the node bytes) (V_node=%.2f pair visits, V_sphere=%.2f measured in this run); %s"
-                                        % (b_seg, v_node, v_sphere, "served by L2 (ncu: 83-94 %% L2 hits); `traffic` = ncu's L2 sectors from the SMs x 32 B per launch; peak = ncu's lts__t_sectors_srcunit_tex peak (2 sectors/cycle/slice = 23.1 TB/s), see profiles/README.md" if l2_resident
+                               "model": "B_seg = %.0f*V_node + 32*V_sphere = %.0f algorithmic bytes/segment (%s; SURVEY 8d's figure for two packed 32-byte nodes per visit would be %.0f) (V_node=%.2f pair visits, V_sphere=%.2f measured in this run); %s"
+                                        % (node_bytes, b_seg, "one 32-byte quantised pair per visit" if quantised else "two packed 32-byte nodes per visit", 64.0 * v_node + 32.0 * v_sphere, v_node, v_sphere, "served by L2 (ncu: 83-94 %% L2 hits); `traffic` = ncu's L2 sectors from the SMs x 32 B per launch; peak = ncu's lts__t_sectors_srcunit_tex peak (2 sectors/cycle/slice = 23.1 TB/s), see profiles/README.md" if l2_resident
                                            else "served by HBM (ncu: 45-53 %% L2 hits); `traffic` = ncu's dram__bytes per launch; peak = measured HBM copy bandwidth")}
         if world == 1 and not args.no_cpu_baseline:
             rate, cores, sample, dt, _ = cpu_reference_rate(args.workload, 160 if scene_name == "rtiow" else 8)
