@@ -391,6 +391,25 @@ def run_ours(args):
         if rank == 0:
             assert int(host_images[(K - 1) & 1][..., 3].min()) == 255, "the last frame did not reach host memory"
 
+    # ---- the same K subframes as ONE call (vn_render_subframes: Renderer::Draw K times without looking at the frames in between).  Scenes rendered
+    # from shared memory take up to 64 subframes per launch -- the launch drains once instead of once per subframe; the accumulation buffer and
+    # the final frame are bit for bit those of the K single calls (tests/test_gpu_parity.py::test_subframes_in_one_launch...).  Reported next to
+    # `value`, which stays one launch per step.
+    grouped = None
+    if world == 1 and args.kernel == "persistent" and K > 1:
+        ctx.reset_accum()
+        ctx.synchronize()
+        ctx.reset_stats()
+        ev_g = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        with torch.cuda.stream(stream):
+            flush.fill_(7)
+            ev_g[0].record(stream)
+            ctx.render_subframes(ctx.make_params(cam, width, height, spp, subframe_of(0), depth, accum_count=0, image=image.data_ptr(), flags=kflag | VN_ASYNC), K)
+            ev_g[1].record(stream)
+        ctx.synchronize()
+        gst = ctx.stats()
+        grouped = {"subframes": K, "ms": ev_g[0].elapsed_time(ev_g[1]), "segments": gst.segments_total, "launches": gst.kernel_launches_total}
+
     # ---- strong scaling: ONE fixed frame of `--strong-subframes` subframes (default 64 = the 1024-spp frame of configs[1]) split over the
     # ranks, cold tile order included (the first launch of the view counts the tile costs), one reduce at the end
     strong = None
@@ -553,6 +572,12 @@ def run_ours(args):
                                              "max over ranks; includes the cold first launch of the view (row-major tiles, tile costs collected)" % (strong["subframes"], spp, world)}
         if parity is not None:
             out["parity"] = parity
+        if grouped is not None:
+            out["subframes_in_one_call"] = {"subframes": grouped["subframes"], "ms": grouped["ms"], "ms_per_subframe": grouped["ms"] / grouped["subframes"],
+                                            "value": grouped["segments"] / (grouped["ms"] * 1e-3) / 1e6, "unit": "Mrays/s", "gpu_launches": grouped["launches"],
+                                            "what": "the same %d subframes through ONE vn_render_subframes call (up to 64 subframes per launch of the path kernel for scenes "
+                                                    "rendered from shared memory, one drain per launch; tonemap once at the end); device time of the call; accumulation buffer and "
+                                                    "frame bit-identical to the %d single calls timed in `value`" % (grouped["subframes"], grouped["subframes"])}
         if not info.scene_in_smem:
             # scenes traversed from L2/HBM (C4 / C5): SURVEY 8(d) byte model, one pair visit = 2 x 32-byte nodes, one sphere = 32 bytes.
             # configs[3] (1 M spheres, 57 MB of nodes + spheres) is L2-resident: ncu measures 92-94 % L2 hits and < 10 GB/s of DRAM traffic, so its

@@ -92,10 +92,15 @@ public:
         p.accum_count = m_accumulated;
 #endif
         p.flags = m_flags | VN_ASYNC;
-        VN_CHECK(m_handle, vn_render(m_handle, &p));                    // optixLaunch, Renderer.h:75
+        // (SetSubframesPerDraw(n): what n Draw calls leave in the buffers, without the frames in between -- one launch for all of them
+        // where the scene allows, vn_render_subframes)
+        const uint32_t n = m_devices.empty() && m_subframesPerDraw > 1u ? m_subframesPerDraw : 1u;
+        if (n > 1u) VN_CHECK(m_handle, vn_render_subframes(m_handle, &p, n));
+        else VN_CHECK(m_handle, vn_render(m_handle, &p));               // optixLaunch, Renderer.h:75
         outputBuffer.unmap();                                           // Renderer.h:76
         VN_CHECK(m_handle, vn_synchronize(m_handle));                   // CUDA_SYNC_CHECK, Renderer.h:77
-        ++m_accumulated;
+        m_subframe_index += n - 1u;
+        m_accumulated += n;
     }
 
     void Cleanup() {                                                    // Renderer.h:80-97
@@ -114,6 +119,9 @@ public:
         m_devices = devices;
         m_subframesPerDraw = subframes_per_draw ? subframes_per_draw : static_cast<uint32_t>(devices.size());
     }
+    // One device: a Draw advances the progressive render by n subframes (n Draw calls of the reference, Renderer.h:35-78, without the
+    // frames in between; the accumulation buffer and the final image are bit for bit the same).
+    void SetSubframesPerDraw(uint32_t n) { if (m_devices.empty()) m_subframesPerDraw = n ? n : 1u; }
     void SetMaxDepth(uint32_t max_depth) { m_maxDepth = max_depth; }
     void SetSamplesPerPixel(uint32_t spp) { m_samplesPerPixel = spp; }
     void SetFlags(uint32_t flags) { m_flags = flags; }

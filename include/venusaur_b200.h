@@ -166,6 +166,11 @@ VN_API int vn_read_wide_bvh(vn_handle h, float* host_nodes, uint64_t cap_nodes, 
 VN_API int vn_resize(vn_handle h, uint32_t width, uint32_t height);   /* (re)allocates + zeroes accum (fixes Q3/Q4) */
 VN_API int vn_reset_accum(vn_handle h);                               /* camera.Changed() path, Renderer.h:37-45 */
 VN_API int vn_render(vn_handle h, const vn_params* p);                /* optixLaunch, Renderer.h:75 */
+/* n calls of Renderer::Draw without looking at the frames in between (the reference's frame loop, Core.cpp:358-395, with the display
+ * taken out; Renderer.h:50-54,75): subframes p->subframe_index .. + n - 1 on top of p->accum_count accumulated ones, the accumulation buffer
+ * bit for bit what n vn_render calls leave, the image (if any) made once at the end.  Scenes rendered from shared memory take all of them
+ * in ONE launch of the path kernel ("multi_subframes", <= 64 per launch): the launch drains once instead of n times. */
+VN_API int vn_render_subframes(vn_handle h, const vn_params* p, uint32_t n);
 VN_API int vn_tonemap(vn_handle h, float scale, void* image, uint32_t flags); /* image = make_color(accum*scale), RayTracer.cu:16-47,216 */
 VN_API int vn_synchronize(vn_handle h);                               /* CUDA_SYNC_CHECK, Renderer.h:77 */
 VN_API int vn_get_stats(vn_handle h, vn_stats* out);

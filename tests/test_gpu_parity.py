@@ -629,6 +629,66 @@ def test_units_make_progress_on_cheap_pixels(ctx):
         ctx.set_option("units_min_seg", 13)
 
 
+def test_subframes_in_one_launch_keep_the_accumulation_buffer(ctx, oracle_mod, rtiow):
+    """vn_render_subframes: n subframes in ONE launch of the path kernel (tickets = (subframe, tile); a pixel's subframes are blended in
+    order through a tag in accum.w while the launch runs).  The accumulation buffer, the image and the statistics are those of n vn_render
+    calls (Renderer::Draw n times, Renderer.h:35-78): a frame with a cost-ordered tile list and one without, continuing an accumulation,
+    partial sums (VN_ACCUM_SUM), row shards, more subframes than one launch takes, the fallback for scenes traversed from L2 -- and the
+    oracle's running mean."""
+    ctx.set_spheres(rtiow)
+    ctx.build_bvh()
+
+    def both(W, H, spp, depth, sub0, n, count0=0, flags=0, rows=(0, 0), multi=64, forget=False):
+        cam = vb.rtiow_camera(W, H)
+        out = []
+        for mode in (0, 1):
+            ctx.resize(W, H)                                      # (zeroes the accumulation buffer)
+            for k in range(count0):                              # what is already in the buffer
+                ctx.render(ctx.make_params(cam, W, H, spp, 100 + k, depth, accum_count=k, flags=flags | VN_NO_TONEMAP, rows=rows))
+            img = np.zeros((H, W, 4), np.uint8)
+            ctx.reset_stats()
+            if mode == 0:
+                for k in range(n):
+                    last = k == n - 1
+                    ctx.render(ctx.make_params(cam, W, H, spp, sub0 + k, depth, accum_count=0 if (flags & VN_ACCUM_SUM) else count0 + k,
+                                               image=ptr(img) if last else None, flags=flags | (VN_IMAGE_HOST if last else VN_NO_TONEMAP), rows=rows))
+            else:
+                ctx.set_option("multi_subframes", multi)
+                if forget: ctx.set_option("tile_order", 1)      # (forget the view: the first subframe collects the tile costs in a launch of its own)
+                ctx.render_subframes(ctx.make_params(cam, W, H, spp, sub0, depth, accum_count=0 if (flags & VN_ACCUM_SUM) else count0, image=ptr(img),
+                                                     flags=flags | VN_IMAGE_HOST, rows=rows), n)
+            st = ctx.stats()
+            out.append((ctx.read_accum(), img, st.segments_total, st.kernel_launches))
+        (a0, i0, s0, _), (a1, i1, s1, launches) = out
+        assert np.array_equal(a0.view(np.uint32), a1.view(np.uint32)), (W, H, n, count0, flags, rows)
+        assert np.array_equal(i0, i1) and s0 == s1, (W, H, n, count0, flags, rows)
+        return a1, launches
+
+    try:
+        a, _ = both(640, 360, 4, 50, 1, 6, forget=True)           # 7200 tiles: the first subframe collects tile costs alone, five share a launch
+        a, launches = both(640, 360, 4, 50, 1, 6)                 # the view is known now: all six in one launch
+        assert launches <= 2                                      # (path kernel + tonemap)
+        orc = oracle_mod.Oracle(rtiow)
+        cam = vb.rtiow_camera(640, 360)
+        px = np.array([y * 640 + x for y in (0, 101, 359) for x in range(0, 640, 7)], np.uint32)
+        want_acc = np.zeros((360, 640, 4), np.float32)
+        for k in range(6):
+            mean, _ = orc.render_mean(orc.params(cam.frame(), 640, 360, 4, 1 + k, 50, atten=oracle_mod.ATTEN_FORWARD), pixels=px)
+            want_acc, _ = oracle_mod.accumulate_tonemap(want_acc, mean, k > 0, np.float32(1.0) / np.float32(k + 1))      # RayTracer.cu:208-213
+        assert np.array_equal(a.reshape(-1, 4)[px, :3].view(np.uint32), want_acc.reshape(-1, 4)[px, :3].view(np.uint32))
+        both(640, 360, 4, 50, 9, 5, count0=3)                     # continues an accumulation of three subframes
+        both(640, 360, 2, 50, 1, 4, flags=VN_ACCUM_SUM)           # partial sums (one rank of a multi-GPU frame)
+        both(640, 360, 4, 12, 3, 3, rows=(40, 300))               # a row shard
+        both(64, 36, 8, 50, 1, 70)                                # no tile order; 70 subframes = 64 + 6
+        both(200, 120, 3, 50, 2, 7, multi=3)                      # three per launch: 3 + 3 + 1
+        ctx.set_spheres(vb.random_scene(50_000, 0x5EED0077, 60.0, 1))
+        ctx.build_bvh()
+        assert ctx.bvh_info().scene_in_smem == 0
+        both(96, 54, 4, 16, 1, 3)                                 # traversed from L2: one launch per subframe, same call
+    finally:
+        ctx.set_option("multi_subframes", 64)
+
+
 def test_split_frames_keep_the_accumulation_buffer(ctx, oracle_mod, rtiow):
     """"split_tail": the cheap end of the cost-ordered tile list is rendered by a second launch on another stream that overlaps the first
     launch's drain.  Disjoint tiles, same kernel: accumulation buffer, image and counters are those of the single launch,

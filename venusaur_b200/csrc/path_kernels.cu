@@ -81,6 +81,33 @@ __device__ __forceinline__ void finish_pixel(const RenderLaunch& p, uint32_t pix
     // that happen to finish a pixel in this iteration would cost every other lane of the warp the same issue slots.
 }
 
+// Several subframes in ONE launch (k_render_lean<kMulti>, vn_render_subframes): the tickets are (subframe, tile), subframe-major, so the launch
+// drains once instead of once per subframe.  The subframes of a pixel must still be blended in order (RayTracer.cu:208-213 is a running
+// mean): the accumulation buffer's .w -- 1.0f by contract (RayTracer.cu:215) -- carries "subframe j of this launch is in" while the launch
+// runs (kMultiTag + j; the last subframe writes the 1.0f back).  A pixel's float4 is read and written whole (one 16-byte L2 access each),
+// so whoever holds subframe j of a pixel sees either the value it needs, tag included, or not yet: then it keeps the finished sum and
+// asks again in its warp's next iteration.  No fences, no counters; a lane waits only where a pixel of the subframe before is still
+// bouncing (the launch's tickets hand a tile's subframes out a whole frame apart).
+// pxy of those launches: px in bits 0-12, py in bits 16-28, the subframe (0-63) in bits 13-15 and 29-31.
+constexpr uint32_t kMultiTag = 0x40000000u;
+__device__ __forceinline__ uint32_t multi_px(uint32_t pxy) { return pxy & 0x1FFFu; }
+__device__ __forceinline__ uint32_t multi_py(uint32_t pxy) { return (pxy >> 16) & 0x1FFFu; }
+__device__ __forceinline__ uint32_t multi_sub(uint32_t pxy) { return ((pxy >> 13) & 7u) | ((pxy >> 26) & 0x38u); }
+__device__ __forceinline__ bool finish_pixel_multi(const RenderLaunch& p, uint32_t pxy, f3 sum) {
+    const uint32_t j = multi_sub(pxy);
+    float4* a = p.accum + (multi_py(pxy) * p.width + multi_px(pxy));
+    f3 mean = sum * p.inv_spp;                                   // RayTracer.cu:206 (vec_math.h:483-487)
+    const uint32_t have = p.accum_count + j;                     // subframes the running mean holds when this one is blended
+    if (p.blend_mode == kBlendSum || have > 0u) {
+        const float4 prev = __ldcg(a);                           // (from L2: another SM wrote it, moments or a frame ago)
+        if (j > 0u && __float_as_uint(prev.w) != kMultiTag + j - 1u) return false;
+        if (p.blend_mode == kBlendSum) mean = mk3(prev.x, prev.y, prev.z) + mean;
+        else mean = lerp3(mk3(prev.x, prev.y, prev.z), mean, __frcp_rn((float)(have + 1u)));     // RayTracer.cu:208-213; a = 1 / (subframes + 1), as fill_launch forms it
+    }
+    __stcg(a, make_float4(mean.x, mean.y, mean.z, j + 1u == p.n_sub ? 1.0f : __uint_as_float(kMultiTag + j)));   // RayTracer.cu:215
+    return true;
+}
+
 // closest_hit_wide() with a warp vote instead of the while-while phases: every iteration the converged lanes of the warp
 // either all take a node step or all test a leaf sphere set -- the leaf turn comes when `leaf_vote` lanes wait at a leaf (or
 // nobody stands on a node).  With 4-wide nodes a ray only takes ~5 node steps between ~2 leaves, so in the while-while
@@ -916,7 +943,7 @@ __device__ __forceinline__ void lean_drain(const RenderLaunch& p, const SceneVie
     lean_epilogue<kCount>(p, cnt, w_seg, w_path);
 }
 
-template <bool kCount, bool kCost, int kMaxThreads, bool kGlobal = false, int kMinBlocks = 1, bool kDrain = false>
+template <bool kCount, bool kCost, int kMaxThreads, bool kGlobal = false, int kMinBlocks = 1, bool kDrain = false, bool kMulti = false>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const __grid_constant__ RenderLaunch p) {
     extern __shared__ float4 s_scene[];
     SceneView sc;
@@ -980,6 +1007,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
     uint32_t w_item = 0u;                          // kUnits: the warp's current work item (tile | unit << 24) ...
     bool w_pending = false;                        // ... drawn but not started: the tile's previous unit is not complete yet
     uint32_t t_seed = 0u;                          // camera seed of pixel (lane) of that tile
+    uint32_t w_sub = 0u;                           // kMulti: the subframe (of this launch) the warp's current tile belongs to
 
     for (;;) {
         const bool fin = cur == kDone && lane_state != kLaneRetired;       // holds a finished traversal, or no ray at all
@@ -1001,6 +1029,10 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
                 sd -= 1u;                                         // (shade_segment's prd.depth - 1 of a path that goes on, RayTracer.cu:314,361,417)
             }
         }
+        if (kMulti) {
+            // (a lane whose pixel still waits for its subframe before stays idle with its sum, starts nothing, and asks again next time)
+            if (fin && lane_state == kLaneIdle && sd < 0x10000u && finish_pixel_multi(p, pxy, sum)) lane_state = kLaneNoPixel;
+        } else
         if (fin && lane_state == kLaneIdle && sd < 0x10000u) {
             const uint32_t px = kUnits ? unit_px(pxy) : (pxy & 0xFFFFu), py = kUnits ? unit_py(pxy) : (pxy >> 16);
             if (kUnits) finish_unit(p, pxy, sum, cam_seed); else finish_pixel(p, py * p.width + px, sum);
@@ -1035,6 +1067,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
                         }
                         break;
                     }
+                    if (kMulti) { w_sub = t / p.tiles_per_sub; t -= w_sub * p.tiles_per_sub; }      // tickets are subframe-major
                     if (!(kUnits && w_pending)) w_item = p.tile_order ? __ldg(p.tile_order + t) : t;
                     const uint32_t tile = kUnits ? (w_item & 0x00FFFFFFu) : w_item;
                     // every lane forms the camera seed of "its" pixel of the new tile (pixel i of the tile by lane i) while the warp is
@@ -1058,7 +1091,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
                         if (w_pending) break;                      // (the askers stay without a pixel and ask again in the warp's next iteration)
                         t_seed = c_seed;
                     } else {
-                        t_seed = tea4((w_oy + ((threadIdx.x & 31u) >> 3)) * p.width + w_ox + (threadIdx.x & 7u), p.subframe_index);   // RayTracer.cu:169
+                        t_seed = tea4((w_oy + ((threadIdx.x & 31u) >> 3)) * p.width + w_ox + (threadIdx.x & 7u), p.subframe_index + (kMulti ? w_sub : 0u));   // RayTracer.cu:169
                     }
                     w_cursor = 0u;
                     if (kCount && p.timeline && (threadIdx.x & 31u) == 0u)
@@ -1071,6 +1104,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
                     if (px < p.width && py < p.row_end) {
                         need = false;
                         pxy = (py << 16) | px;
+                        if (kMulti) pxy |= ((w_sub & 7u) << 13) | ((w_sub >> 3) << 29);
                         cam_seed = in_seed;
                         sum = mk3(0.0f);
                         sd = p.spp << 16;
@@ -1088,13 +1122,13 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
                 m = __ballot_sync(kFull, need);
             }
         }
-        const bool launching = fin && lane_state == kLaneIdle;             // (a lane that just got a pixel, or whose path just ended)
+        const bool launching = fin && lane_state == kLaneIdle && !(kMulti && sd < 0x10000u);   // (a lane that just got a pixel, or whose path just ended)
         // (kUnits: the lanes of a warp whose next unit is not ready yet hold no pixel -- they start nothing and do not count in the votes below)
-        const bool starting = fin && lane_state != kLaneRetired && !(kUnits && lane_state == kLaneNoPixel);
+        const bool starting = fin && lane_state != kLaneRetired && !(kUnits && lane_state == kLaneNoPixel) && !(kMulti && lane_state == kLaneIdle && !launching);
         w_path += (uint32_t)__popc(__ballot_sync(kFull, launching));
         if (starting) {
             if (launching) {
-                camera_ray(p.cam, kUnits ? unit_px(pxy) : (pxy & 0xFFFFu), kUnits ? unit_py(pxy) : (pxy >> 16), cam_seed, st.o, st.d);   // RayTracer.cu:173-177
+                camera_ray(p.cam, kMulti ? multi_px(pxy) : kUnits ? unit_px(pxy) : (pxy & 0xFFFFu), kMulti ? multi_py(pxy) : kUnits ? unit_py(pxy) : (pxy >> 16), cam_seed, st.o, st.d);   // RayTracer.cu:173-177
                 st.thr = mk3(1.0f);
                 st.seed = cam_seed;                               // prd.seed = seed: a copy (RayTracer.cu:183)
                 sd = ((sd - 0x10000u) & 0xFFFF0000u) | (p.max_depth - 1u);   // one sample less to start; prd.depth = max_depth - 1 (RayTracer.cu:184)
@@ -1365,7 +1399,7 @@ inline uint32_t grid_for(uint64_t n, int threads) { return (uint32_t)((n + threa
 namespace {
 typedef void (*PathKernel)(const RenderLaunch);
 PathKernel pick_kernel(bool scene_in_smem, bool count, bool octant, bool wide = false, int threads = 1024, bool grid = false, bool async = false, bool phase = false, bool warp_tiles = false,
-                       bool lean = false, bool cost = false, int global_ctas = 4, bool drain = false) {
+                       bool lean = false, bool cost = false, int global_ctas = 4, bool drain = false, bool multi = false) {
     if (lean && !scene_in_smem && !wide && !grid) {        // pair nodes from L2 / HBM, asynchronous (k_render_lean<kGlobal>); 4, 5 or 6 CTAs of 256 threads per SM (64 / 48 / 40 registers)
         if (drain && !cost) {                              // with the sample-stealing drain (lean_drain)
             if (global_ctas >= 6) return count ? k_render_lean<true, false, 256, true, 6, true> : k_render_lean<false, false, 256, true, 6, true>;
@@ -1377,6 +1411,7 @@ PathKernel pick_kernel(bool scene_in_smem, bool count, bool octant, bool wide = 
         return count ? (cost ? k_render_lean<true, true, 256, true, 4> : k_render_lean<true, false, 256, true, 4>) : (cost ? k_render_lean<false, true, 256, true, 4> : k_render_lean<false, false, 256, true, 4>);
     }
     if (lean && async && phase && warp_tiles && wide && scene_in_smem && !grid) {
+        if (multi && !cost && !count) return threads <= 768 ? k_render_lean<false, false, 768, false, 1, false, true> : k_render_lean<false, false, 1024, false, 1, false, true>;
         if (drain && !cost) {
             if (threads <= 768) return count ? k_render_lean<true, false, 768, false, 1, true> : k_render_lean<false, false, 768, false, 1, true>;
             return count ? k_render_lean<true, false, 1024, false, 1, true> : k_render_lean<false, false, 1024, false, 1, true>;
@@ -1420,7 +1455,7 @@ int max_blocks_per_sm(int threads, size_t smem_bytes, bool scene_in_smem, bool c
 
 cudaError_t launch_render_persistent(const RenderLaunch& p, const KernelConfig& cfg, cudaStream_t stream) {
     PathKernel k = pick_kernel(cfg.scene_in_smem, cfg.count, cfg.octant, cfg.wide, cfg.threads, cfg.grid, cfg.async, cfg.async && p.async_node == 0u, cfg.warp_tiles,
-                               cfg.lean, p.tile_cost != nullptr, cfg.global_ctas, p.steal != 0u && p.steal_scratch != nullptr);
+                               cfg.lean, p.tile_cost != nullptr, cfg.global_ctas, p.steal != 0u && p.steal_scratch != nullptr, p.n_sub > 1u);
     if (cfg.smem_bytes > 48 * 1024) {
         const cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.smem_bytes);
         if (e != cudaSuccess) return e;

@@ -125,6 +125,8 @@ struct vn_context {
                                       // ms per launch with 1 / 4 units (tools/units_probe.py): 2 k spheres, 1.6 segments per path: 8.5 / 13.1; 8 k, 2.9: 21.8 / 27.9;
                                       // 30 k, 6.9: 48.6 / 51.9; 100 k, 11.4: 83.6 / 84.2; 300 k, 15.4: 122.2 / 115.1; 1 M, 18.4: 169.1 / 156.5.
                                       // 0 = units whatever the view (and without a measurement)
+    uint32_t multi_subframes = 64;    // "multi_subframes": vn_render_subframes renders up to this many subframes per launch (k_render_lean<kMulti>: one drain instead of
+                                      // one per subframe; the pixel's subframes are blended in order through a tag in accum.w); 0 or 1 = one launch per subframe
     uint32_t steal = 1;               // "steal": once the tile tickets are exhausted, idle lanes of a warp take single samples of the pixels its other lanes still hold
                                       // (k_render_lean's drain, path_kernels.cu::lean_drain); the value = the fewest samples a lane must have left to give one away, 0 = off
     uint32_t steal_smem = 0;          // "steal_smem": also for scenes traversed from shared memory.  Off: measured on RTIOW 1080p the drain shrinks from 0.39 to 0.28 ms
@@ -218,6 +220,7 @@ int fill_launch(vn_context* c, const vn_params* p, RenderLaunch& L) {
     if (p->flags & VN_ACCUM_SUM) { L.blend_mode = kBlendSum; L.blend_a = 0.0f; }
     else if (p->accum_count > 0) { L.blend_mode = kBlendLerp; L.blend_a = 1.0f / (float)(p->accum_count + 1u); }   // RayTracer.cu:210
     else { L.blend_mode = kBlendOverwrite; L.blend_a = 1.0f; }
+    L.n_sub = 1u; L.tiles_per_sub = 0u; L.accum_count = p->accum_count;
     L.inv_spp = 1.0f / (float)p->samples_per_pixel;                                                                // vec_math.h:483-487
     L.accum = c->accum;
     L.nodes = c->scene.nodes; L.geom = c->scene.geom; L.mat = c->scene.mat; L.type = c->scene.type;
@@ -385,6 +388,7 @@ int vn_set_option(vn_handle c, const char* name, double value) {
     else if (k == "wavefront_wide") { c->wavefront_wide = value != 0 ? 1u : 0u; }
     else if (k == "split_tail") { VN_REQUIRE(c, value >= 0 && value <= 0.9, "split_tail must be in [0,0.9]"); c->split_tail = (float)value; }
     else if (k == "qnodes") { c->qnodes_opt = value != 0 ? 1u : 0u; c->bvh_valid = false; }
+    else if (k == "multi_subframes") { VN_REQUIRE(c, value >= 0 && value <= 64, "multi_subframes must be in [0,64]"); c->multi_subframes = (uint32_t)value; }
     else if (k == "units_min_seg") { VN_REQUIRE(c, value >= 0, "units_min_seg must be >= 0"); c->units_min_seg = value; }
     else if (k == "units") { VN_REQUIRE(c, value == 1 || value == 2 || value == 4 || value == 8 || value == 16, "units must be 1, 2, 4, 8 or 16"); c->units = (uint32_t)value; }
     else if (k == "steal_smem") { c->steal_smem = value != 0 ? 1u : 0u; }
@@ -803,7 +807,10 @@ static int prepare_tile_order(vn_handle c, const vn_params* p, RenderLaunch& L) 
     return VN_OK;
 }
 
-int vn_render(vn_handle c, const vn_params* p) {
+// One call of the path kernel(s): subframe p->subframe_index, or -- when the caller has `want_n` > 1 subframes to render and the launch
+// qualifies (see n_sub below) -- all of them in one launch.  *took = subframes rendered; the image is produced by the call that renders the last.
+static int render_some(vn_handle c, const vn_params* p, uint32_t want_n, uint32_t* took) {
+    *took = 1u;
     VN_REQUIRE(c, c && p, "vn_render: NULL argument");
     VN_REQUIRE(c, c->bvh_valid, "vn_render: no BVH (call vn_set_spheres + vn_build_bvh; Renderer::Init does both)");
     VN_REQUIRE(c, p->width >= 2 && p->height >= 2, "vn_render: width and height must be >= 2");
@@ -838,6 +845,7 @@ int vn_render(vn_handle c, const vn_params* p) {
     if (pipelined && c->copied_valid[c->pipe_flip]) VN_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[c->pipe_flip], 0));
     VN_CUDA(c, cudaMemsetAsync(c->d_counters, 0, 256, c->stream));
     VN_CUDA(c, cudaEventRecord(c->ev_slot[slot][0], c->stream));
+    bool emit = want_n == 1u;           // this call renders the last of the caller's subframes: tonemap, frame copy, and the host waits unless VN_ASYNC
     if (p->flags & VN_WAVEFRONT) {
         const uint32_t rows = L.row_end - L.row_begin;
         const int rc = ensure_wavefront(c, (uint64_t)p->width * rows, p->samples_per_pixel);
@@ -940,12 +948,27 @@ int vn_render(vn_handle c, const vn_params* p) {
             L.steal_scratch = c->d_steal_scratch; L.steal_count = c->d_steal_count;
             }
         }
+        // several subframes in one launch (k_render_lean<kMulti>, path_kernels.cu::finish_pixel_multi): the shared-memory form of the lean kernel,
+        // a view whose tile costs are known (or a frame too small for a tile order), no instrumentation, no stealing drain
+        uint32_t n_sub = 1u;
+        if (want_n > 1u && c->multi_subframes > 1u && cfg.lean && cfg.scene_in_smem && cfg.wide && !cfg.grid && !L.tile_cost && !count &&
+            p->width < 8192u && p->height < 8192u) {
+            n_sub = std::min(std::min(want_n, 64u), c->multi_subframes);
+            const uint64_t cap = 0xFFFFFFFFull / std::max<uint64_t>(1u, L.total_work);
+            if ((uint64_t)n_sub > cap) n_sub = (uint32_t)std::max<uint64_t>(1u, cap);
+        }
+        if (n_sub > 1u) {
+            L.n_sub = n_sub; L.tiles_per_sub = L.total_work / 32u; L.total_work *= n_sub;
+            L.steal_scratch = nullptr; L.steal_count = nullptr;
+            *took = n_sub;
+        }
+        emit = n_sub == want_n;
         // split frame: the cheap end of the cost-ordered tile list goes to a second launch on tail_stream (same kernel, own ticket counter, the
         // statistics add up in the same counters); everything behind it on c->stream waits for both
         const uint32_t n_tiles = L.total_work / 32u;
         // ... and only tiles that saw nothing but sky when the costs were collected: uniform, cheap, no pixel that bounces for a millisecond --
         // a second launch that holds heavy-tailed tiles ends later than the first (measured: +0.2 ms as soon as it reached beyond the sky)
-        const uint32_t n_tail = (L.tile_order && !L.tile_cost && !count && cfg.lean && cfg.scene_in_smem && c->split_tail > 0.0f)
+        const uint32_t n_tail = (L.tile_order && !L.tile_cost && !count && cfg.lean && cfg.scene_in_smem && c->split_tail > 0.0f && n_sub == 1u)
                                     ? std::min(c->tile_all_miss, (uint32_t)((double)n_tiles * c->split_tail)) : 0u;
         if (n_tail > 0u && n_tail < n_tiles) {
             RenderLaunch T = L;
@@ -977,7 +1000,7 @@ int vn_render(vn_handle c, const vn_params* p) {
             VN_CUDA(c, exact_build ? exact::launch_render_persistent(L, cfg, c->stream) : fast::launch_render_persistent(L, cfg, c->stream));
         }
         launches += 1;
-        if (L.image) {
+        if (L.image && emit) {
             // sRGB + quantise of the rows just rendered (RayTracer.cu:216), as a coalesced kernel behind the path kernel
             const uint64_t begin = (uint64_t)L.row_begin * L.width, count = (uint64_t)(L.row_end - L.row_begin) * L.width;
             VN_CUDA(c, exact_build ? exact::launch_tonemap(L.accum + begin, 1.0f, L.image + begin, count, c->stream)
@@ -990,7 +1013,7 @@ int vn_render(vn_handle c, const vn_params* p) {
     const uint64_t row_px0 = (uint64_t)L.row_begin * L.width, row_px = (uint64_t)(L.row_end - L.row_begin) * L.width;
     // (the 256-byte statistics copy goes first: queued behind the frame on the D2H engine it would delay the next launch)
     VN_CUDA(c, cudaMemcpyAsync(c->h_counters + 32u * slot, c->d_counters, 256, cudaMemcpyDeviceToHost, c->stream));
-    if (pipelined) {
+    if (pipelined && emit) {
         const int f = c->pipe_flip;
         VN_CUDA(c, cudaEventRecord(c->ev_frame[f], c->stream));
         VN_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_frame[f], 0));
@@ -998,7 +1021,7 @@ int vn_render(vn_handle c, const vn_params* p) {
         VN_CUDA(c, cudaEventRecord(c->ev_copied[f], c->copy_stream));
         c->copied_valid[f] = true;
         c->pipe_flip = f ^ 1;
-    } else if (host_image) {
+    } else if (host_image && emit) {
         VN_CUDA(c, cudaMemcpyAsync(static_cast<uint32_t*>(p->image) + row_px0, c->image_tmp + row_px0, row_px * 4, cudaMemcpyDeviceToHost, c->stream));
     }
     c->slot_launches[slot] = launches;
@@ -1006,7 +1029,27 @@ int vn_render(vn_handle c, const vn_params* p) {
     c->stats.kernel_launches_total += launches;
     c->slot_head = (slot + 1u) % kStatSlots;
     c->slots_pending += 1u;
-    if (!(p->flags & VN_ASYNC)) return sync_kernels(c);
+    if (!(p->flags & VN_ASYNC) && emit) return sync_kernels(c);
+    return VN_OK;
+}
+
+int vn_render(vn_handle c, const vn_params* p) {
+    uint32_t took = 0;
+    return render_some(c, p, 1u, &took);
+}
+
+int vn_render_subframes(vn_handle c, const vn_params* p, uint32_t n) {
+    VN_REQUIRE(c, c && p, "vn_render_subframes: NULL argument");
+    VN_REQUIRE(c, n >= 1u && n <= 65536u, "vn_render_subframes: n must be in [1,65536]");
+    vn_params q = *p;
+    for (uint32_t done = 0; done < n;) {
+        q.subframe_index = p->subframe_index + done;
+        q.accum_count = p->accum_count + ((p->flags & VN_ACCUM_SUM) ? 0u : done);
+        uint32_t took = 0;
+        const int rc = render_some(c, &q, n - done, &took);
+        if (rc != VN_OK) return rc;
+        done += took;
+    }
     return VN_OK;
 }
 
