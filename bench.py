@@ -423,11 +423,12 @@ def run_ours(args):
         ev_s = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         with torch.cuda.stream(stream):
             ev_s[0].record(stream)
-            for sub in mine_sub:
-                if world > 1:
-                    ctx.render(ctx.make_params(cam, width, height, spp, sub, depth, flags=kflag | VN_ACCUM_SUM | VN_NO_TONEMAP | VN_ASYNC))
-                else:
-                    ctx.render(ctx.make_params(cam, width, height, spp, sub, depth, accum_count=sub - 1, image=image.data_ptr(), flags=kflag | VN_ASYNC))
+            # this rank's subframes (rank + 1, rank + 1 + N, ...) as ONE call: a launch of their own for the view's first subframe (tile costs),
+            # then one launch for the rest where the scene is rendered from shared memory (vn_render_subframes_strided)
+            if world > 1 and mine_sub:
+                ctx.render_subframes(ctx.make_params(cam, width, height, spp, mine_sub[0], depth, flags=kflag | VN_ACCUM_SUM | VN_NO_TONEMAP | VN_ASYNC), len(mine_sub), stride=world)
+            elif mine_sub:
+                ctx.render_subframes(ctx.make_params(cam, width, height, spp, 1, depth, accum_count=0, image=image.data_ptr(), flags=kflag | VN_ASYNC), S)
         finish_frame(S)
         with torch.cuda.stream(stream):
             ev_s[1].record(stream)
@@ -569,7 +570,7 @@ def run_ours(args):
         if strong is not None:
             out["strong_scaling"] = {"subframes": strong["subframes"], "ms": strong_ms, "value": strong_segs / (strong_ms * 1e-3) / 1e6, "unit": "Mrays/s",
                                      "what": "ONE fixed frame of %d x %d spp split over the %d GPUs (sample ranges), device time from the first launch to the end of the reduce, "
-                                             "max over ranks; includes the cold first launch of the view (row-major tiles, tile costs collected)" % (strong["subframes"], spp, world)}
+                                             "max over ranks; includes the cold first launch of the view (row-major tiles, tile costs collected); each rank's remaining subframes are one vn_render_subframes_strided call (one launch)" % (strong["subframes"], spp, world)}
         if parity is not None:
             out["parity"] = parity
         if grouped is not None:

@@ -171,6 +171,9 @@ VN_API int vn_render(vn_handle h, const vn_params* p);                /* optixLa
  * bit for bit what n vn_render calls leave, the image (if any) made once at the end.  Scenes rendered from shared memory take all of them
  * in ONE launch of the path kernel ("multi_subframes", <= 64 per launch): the launch drains once instead of n times. */
 VN_API int vn_render_subframes(vn_handle h, const vn_params* p, uint32_t n);
+/* ... subframes p->subframe_index + k * stride, k < n: the share of one device when a frame's subframes are dealt round-robin to `stride`
+ * devices (sample-range sharding; with VN_ACCUM_SUM the buffer holds the sum of the subframe means). */
+VN_API int vn_render_subframes_strided(vn_handle h, const vn_params* p, uint32_t n, uint32_t stride);
 VN_API int vn_tonemap(vn_handle h, float scale, void* image, uint32_t flags); /* image = make_color(accum*scale), RayTracer.cu:16-47,216 */
 VN_API int vn_synchronize(vn_handle h);                               /* CUDA_SYNC_CHECK, Renderer.h:77 */
 VN_API int vn_get_stats(vn_handle h, vn_stats* out);

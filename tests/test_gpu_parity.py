@@ -638,7 +638,7 @@ def test_subframes_in_one_launch_keep_the_accumulation_buffer(ctx, oracle_mod, r
     ctx.set_spheres(rtiow)
     ctx.build_bvh()
 
-    def both(W, H, spp, depth, sub0, n, count0=0, flags=0, rows=(0, 0), multi=64, forget=False):
+    def both(W, H, spp, depth, sub0, n, count0=0, flags=0, rows=(0, 0), multi=64, forget=False, stride=1):
         cam = vb.rtiow_camera(W, H)
         out = []
         for mode in (0, 1):
@@ -650,13 +650,13 @@ def test_subframes_in_one_launch_keep_the_accumulation_buffer(ctx, oracle_mod, r
             if mode == 0:
                 for k in range(n):
                     last = k == n - 1
-                    ctx.render(ctx.make_params(cam, W, H, spp, sub0 + k, depth, accum_count=0 if (flags & VN_ACCUM_SUM) else count0 + k,
+                    ctx.render(ctx.make_params(cam, W, H, spp, sub0 + k * stride, depth, accum_count=0 if (flags & VN_ACCUM_SUM) else count0 + k,
                                                image=ptr(img) if last else None, flags=flags | (VN_IMAGE_HOST if last else VN_NO_TONEMAP), rows=rows))
             else:
                 ctx.set_option("multi_subframes", multi)
                 if forget: ctx.set_option("tile_order", 1)      # (forget the view: the first subframe collects the tile costs in a launch of its own)
                 ctx.render_subframes(ctx.make_params(cam, W, H, spp, sub0, depth, accum_count=0 if (flags & VN_ACCUM_SUM) else count0, image=ptr(img),
-                                                     flags=flags | VN_IMAGE_HOST, rows=rows), n)
+                                                     flags=flags | VN_IMAGE_HOST, rows=rows), n, stride=stride)
             st = ctx.stats()
             out.append((ctx.read_accum(), img, st.segments_total, st.kernel_launches))
         (a0, i0, s0, _), (a1, i1, s1, launches) = out
@@ -679,6 +679,7 @@ def test_subframes_in_one_launch_keep_the_accumulation_buffer(ctx, oracle_mod, r
         both(640, 360, 4, 50, 9, 5, count0=3)                     # continues an accumulation of three subframes
         both(640, 360, 2, 50, 1, 4, flags=VN_ACCUM_SUM)           # partial sums (one rank of a multi-GPU frame)
         both(640, 360, 4, 12, 3, 3, rows=(40, 300))               # a row shard
+        both(640, 360, 2, 50, 3, 4, flags=VN_ACCUM_SUM, stride=8)  # rank 2's share of a frame dealt to eight devices: subframes 3, 11, 19, 27
         both(64, 36, 8, 50, 1, 70)                                # no tile order; 70 subframes = 64 + 6
         both(200, 120, 3, 50, 2, 7, multi=3)                      # three per launch: 3 + 3 + 1
         ctx.set_spheres(vb.random_scene(50_000, 0x5EED0077, 60.0, 1))

@@ -77,6 +77,7 @@ SIGNATURES = {
     "vn_reset_accum": (C.c_int, [C.c_void_p]),
     "vn_render": (C.c_int, [C.c_void_p, _P(vn_params)]),
     "vn_render_subframes": (C.c_int, [C.c_void_p, _P(vn_params), C.c_uint32]),
+    "vn_render_subframes_strided": (C.c_int, [C.c_void_p, _P(vn_params), C.c_uint32, C.c_uint32]),
     "vn_tonemap": (C.c_int, [C.c_void_p, C.c_float, C.c_void_p, C.c_uint32]),
     "vn_synchronize": (C.c_int, [C.c_void_p]),
     "vn_get_stats": (C.c_int, [C.c_void_p, _P(vn_stats)]),

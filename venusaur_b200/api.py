@@ -238,10 +238,10 @@ class Context:
         self._check(self.lib.vn_render(self.h, C.byref(params)), "vn_render")
         self.width, self.height = params.width, params.height      # vn_render (re)sizes accum to the frame
 
-    def render_subframes(self, params: vn_params, n: int):
-        """Subframes params.subframe_index .. + n - 1 as n render() calls would leave them, in as few launches as the scene allows
-        (vn_render_subframes; Renderer::Draw called n times, Renderer.h:35-78)."""
-        self._check(self.lib.vn_render_subframes(self.h, C.byref(params), n), "vn_render_subframes")
+    def render_subframes(self, params: vn_params, n: int, stride: int = 1):
+        """Subframes params.subframe_index + k * stride, k < n, as n render() calls would leave them, in as few launches as the scene allows
+        (vn_render_subframes[_strided]; Renderer::Draw called n times, Renderer.h:35-78)."""
+        self._check(self.lib.vn_render_subframes_strided(self.h, C.byref(params), n, stride), "vn_render_subframes")
         self.width, self.height = params.width, params.height
 
     def tonemap(self, scale: float, image, flags: int = 0):

@@ -23,7 +23,7 @@ struct RenderLaunch {
     uint32_t width, height, spp, subframe_index, max_depth;
     uint32_t row_begin, row_end;
     uint32_t blend_mode;
-    uint32_t n_sub, tiles_per_sub, accum_count;   // k_render_lean<kMulti>: subframes subframe_index .. + n_sub - 1 in one launch (tickets = subframe * tiles_per_sub + tile rank);
+    uint32_t n_sub, tiles_per_sub, accum_count, sub_stride;   // k_render_lean<kMulti>: subframes subframe_index + j * sub_stride, j < n_sub, in one launch (tickets = j * tiles_per_sub + tile rank);
                                                   //   accum_count = subframes the running mean holds before the first of them (path_kernels.cu::finish_pixel_multi); n_sub = 1 otherwise
     float blend_a, inv_spp;
     float4* accum;

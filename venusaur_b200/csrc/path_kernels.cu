@@ -1091,7 +1091,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) k_render_lean(const _
                         if (w_pending) break;                      // (the askers stay without a pixel and ask again in the warp's next iteration)
                         t_seed = c_seed;
                     } else {
-                        t_seed = tea4((w_oy + ((threadIdx.x & 31u) >> 3)) * p.width + w_ox + (threadIdx.x & 7u), p.subframe_index + (kMulti ? w_sub : 0u));   // RayTracer.cu:169
+                        t_seed = tea4((w_oy + ((threadIdx.x & 31u) >> 3)) * p.width + w_ox + (threadIdx.x & 7u), p.subframe_index + (kMulti ? w_sub * p.sub_stride : 0u));   // RayTracer.cu:169
                     }
                     w_cursor = 0u;
                     if (kCount && p.timeline && (threadIdx.x & 31u) == 0u)

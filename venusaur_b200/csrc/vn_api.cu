@@ -220,7 +220,7 @@ int fill_launch(vn_context* c, const vn_params* p, RenderLaunch& L) {
     if (p->flags & VN_ACCUM_SUM) { L.blend_mode = kBlendSum; L.blend_a = 0.0f; }
     else if (p->accum_count > 0) { L.blend_mode = kBlendLerp; L.blend_a = 1.0f / (float)(p->accum_count + 1u); }   // RayTracer.cu:210
     else { L.blend_mode = kBlendOverwrite; L.blend_a = 1.0f; }
-    L.n_sub = 1u; L.tiles_per_sub = 0u; L.accum_count = p->accum_count;
+    L.n_sub = 1u; L.tiles_per_sub = 0u; L.accum_count = p->accum_count; L.sub_stride = 1u;
     L.inv_spp = 1.0f / (float)p->samples_per_pixel;                                                                // vec_math.h:483-487
     L.accum = c->accum;
     L.nodes = c->scene.nodes; L.geom = c->scene.geom; L.mat = c->scene.mat; L.type = c->scene.type;
@@ -809,7 +809,7 @@ static int prepare_tile_order(vn_handle c, const vn_params* p, RenderLaunch& L) 
 
 // One call of the path kernel(s): subframe p->subframe_index, or -- when the caller has `want_n` > 1 subframes to render and the launch
 // qualifies (see n_sub below) -- all of them in one launch.  *took = subframes rendered; the image is produced by the call that renders the last.
-static int render_some(vn_handle c, const vn_params* p, uint32_t want_n, uint32_t* took) {
+static int render_some(vn_handle c, const vn_params* p, uint32_t want_n, uint32_t stride, uint32_t* took) {
     *took = 1u;
     VN_REQUIRE(c, c && p, "vn_render: NULL argument");
     VN_REQUIRE(c, c->bvh_valid, "vn_render: no BVH (call vn_set_spheres + vn_build_bvh; Renderer::Init does both)");
@@ -958,7 +958,7 @@ static int render_some(vn_handle c, const vn_params* p, uint32_t want_n, uint32_
             if ((uint64_t)n_sub > cap) n_sub = (uint32_t)std::max<uint64_t>(1u, cap);
         }
         if (n_sub > 1u) {
-            L.n_sub = n_sub; L.tiles_per_sub = L.total_work / 32u; L.total_work *= n_sub;
+            L.n_sub = n_sub; L.tiles_per_sub = L.total_work / 32u; L.total_work *= n_sub; L.sub_stride = stride;
             L.steal_scratch = nullptr; L.steal_count = nullptr;
             *took = n_sub;
         }
@@ -1035,23 +1035,26 @@ static int render_some(vn_handle c, const vn_params* p, uint32_t want_n, uint32_
 
 int vn_render(vn_handle c, const vn_params* p) {
     uint32_t took = 0;
-    return render_some(c, p, 1u, &took);
+    return render_some(c, p, 1u, 1u, &took);
 }
 
-int vn_render_subframes(vn_handle c, const vn_params* p, uint32_t n) {
+int vn_render_subframes_strided(vn_handle c, const vn_params* p, uint32_t n, uint32_t stride) {
     VN_REQUIRE(c, c && p, "vn_render_subframes: NULL argument");
     VN_REQUIRE(c, n >= 1u && n <= 65536u, "vn_render_subframes: n must be in [1,65536]");
+    VN_REQUIRE(c, stride >= 1u && stride <= 65536u, "vn_render_subframes: stride must be in [1,65536]");
     vn_params q = *p;
     for (uint32_t done = 0; done < n;) {
-        q.subframe_index = p->subframe_index + done;
+        q.subframe_index = p->subframe_index + done * stride;
         q.accum_count = p->accum_count + ((p->flags & VN_ACCUM_SUM) ? 0u : done);
         uint32_t took = 0;
-        const int rc = render_some(c, &q, n - done, &took);
+        const int rc = render_some(c, &q, n - done, stride, &took);
         if (rc != VN_OK) return rc;
         done += took;
     }
     return VN_OK;
 }
+
+int vn_render_subframes(vn_handle c, const vn_params* p, uint32_t n) { return vn_render_subframes_strided(c, p, n, 1u); }
 
 int vn_tonemap(vn_handle c, float scale, void* image, uint32_t flags) {
     VN_REQUIRE(c, c && image, "vn_tonemap: NULL argument");

@@ -196,10 +196,16 @@ int vn_multi_render(vn_multi_handle m, const vn_params* p, uint32_t n_subframes)
     q.image = nullptr;
     q.accum_count = 0;
     q.flags = (p->flags & (VN_FAST | VN_COUNTERS | VN_WAVEFRONT)) | VN_ACCUM_SUM | VN_NO_TONEMAP | VN_ASYNC;
-    for (uint32_t k = 0; k < n_subframes; k++) {
-        const int g = (int)(k % (uint32_t)N);
+    // (first one subframe per device -- a new view's first launch runs alone and the host waits for it before the next, which must not hold
+    // up the other devices' first launches -- then each device's remaining subframes in one call: one launch where the scene allows)
+    for (uint32_t k = 0; k < n_subframes && k < (uint32_t)N; k++) {
         q.subframe_index = p->subframe_index + k;
-        VNM_DEV(m, g, vn_render(m->h[g], &q));
+        VNM_DEV(m, (int)k, vn_render(m->h[k], &q));
+    }
+    for (uint32_t g = 0; g < (uint32_t)N && g + (uint32_t)N < n_subframes; g++) {
+        const uint32_t rest = (n_subframes - g + (uint32_t)N - 1u) / (uint32_t)N - 1u;
+        q.subframe_index = p->subframe_index + g + (uint32_t)N;
+        VNM_DEV(m, (int)g, vn_render_subframes_strided(m->h[g], &q, rest, (uint32_t)N));
     }
     m->accumulated += n_subframes;
     void* peers[kMaxDevices];
