@@ -933,6 +933,19 @@ def test_renderer_draw_progressive_accumulation(oracle_mod, rtiow):
         assert np.array_equal(r.ctx.read_accum().view(np.uint32), want.view(np.uint32)), "frame %d" % k
         assert np.abs(buf.getHostPointer().astype(np.int32) - want_img.astype(np.int32)).max() <= 1
     assert r.m_subframe_index == 3
+    # SetSubframesPerDraw(3): one Draw = those three, without the frames in between (vn_render_subframes)
+    r3 = vb.Renderer()
+    r3.m_flags = VN_EXACT
+    r3.m_maxDepth = 6
+    r3.SetSubframesPerDraw(3)
+    r3.Init(vb.Scene())
+    cam3 = vb.rtiow_camera(W, H)
+    buf3 = vb.CUDAOutputBuffer(vb.CUDAOutputBuffer.CUDA_DEVICE, W, H)
+    r3.Draw(cam3, buf3)
+    assert r3.m_subframe_index == 3 and r3.m_accumulated == 3
+    assert np.array_equal(r3.ctx.read_accum().view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(buf3.getHostPointer(), buf.getHostPointer())
+    r3.Cleanup()
     cam.SetFocalLength(9.5)                                     # dirty -> accumulation restarts, stream id restarts at 1
     r.Draw(cam, buf)
     mean, _ = orc.render_mean(orc.params(cam.frame(), W, H, 16, 1, 6, atten=oracle_mod.ATTEN_FORWARD))

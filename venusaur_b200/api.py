@@ -557,6 +557,12 @@ class Renderer:
         self.m_devices = [int(d) for d in devices]
         self.m_subframes_per_draw = int(subframes_per_draw) if subframes_per_draw else len(self.m_devices)
 
+    def SetSubframesPerDraw(self, n: int):
+        """Extension: on one device a Draw advances the progressive render by n subframes -- the buffers n Draw calls of the reference
+        leave (Renderer.h:35-78), without the frames in between; one launch for all of them where the scene allows."""
+        if self.m_devices is None:
+            self.m_subframes_per_draw = max(1, int(n))
+
     def Init(self, scene: Scene, ptxSource: str = ""):
         if self.m_devices is not None:
             if self.mctx is None:
@@ -602,10 +608,15 @@ class Renderer:
         count = self.m_subframe_index if self.strict_accum else self.m_accumulated
         p = self.ctx.make_params(camera, size[0], size[1], self.m_samplesPerPixel, self.m_subframe_index, self.m_maxDepth,
                                  accum_count=count, image=outputBuffer.map(), flags=self.m_flags | VN_ASYNC)
-        self.ctx.render(p)
+        n = self.m_subframes_per_draw if self.m_devices is None else 1
+        if n > 1:                                    # SetSubframesPerDraw: n Draw calls without the frames in between (vn_render_subframes)
+            self.ctx.render_subframes(p, n)
+        else:
+            self.ctx.render(p)
         outputBuffer.unmap()
         self.ctx.synchronize()
-        self.m_accumulated += 1
+        self.m_subframe_index += n - 1
+        self.m_accumulated += n
 
     def Cleanup(self):
         if self.ctx is not None:
